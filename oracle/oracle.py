@@ -1,0 +1,215 @@
+"""TEST INFRASTRUCTURE — ctypes binding of the CPU oracle (oracle/g2o_oracle.cpp).
+
+Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may
+import this module.  Nothing under ``g2o_b200/`` does.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+STATS_FIELDS = ["iteration", "numVertices", "numEdges", "chi2", "timeResiduals", "timeLinearize", "timeQuadraticForm",
+                "levenbergIterations", "timeSchurComplement", "timeSymbolicDecomposition", "timeNumericDecomposition",
+                "timeLinearSolution", "timeLinearSolver", "iterationsLinearSolver", "timeUpdate", "timeIteration",
+                "hessianDimension", "hessianPoseDimension", "hessianLandmarkDimension", "choleskyNNZ", "lambda", "result"]
+
+
+def build(force: bool = False) -> None:
+    """Compile liboracle.so (and oracle/_ref/libcsparse_ref.so when /root/reference is present)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("g2o_oracle.cpp", "orc_types.hpp", "orc_math.hpp")]
+    stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    need_ref = os.path.isdir("/root/reference/EXTERNAL/csparse") and not os.path.exists(os.path.join(_HERE, "_ref", "libcsparse_ref.so"))
+    if stale or need_ref:
+        subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(so):
+            build()
+        L = ctypes.CDLL(so)
+        L.orc_create.restype = ctypes.c_void_p
+        L.orc_create.argtypes = [ctypes.c_void_p]
+        for f in ("orc_destroy", "orc_compute_active_errors", "orc_build_system", "orc_restore_diagonal", "orc_push", "orc_pop", "orc_discard_top"):
+            getattr(L, f).argtypes = [ctypes.c_void_p]
+            getattr(L, f).restype = None
+        for f in ("orc_active_robust_chi2", "orc_active_chi2", "orc_compute_lambda_init", "orc_compute_scale"):
+            getattr(L, f).argtypes = [ctypes.c_void_p]
+            getattr(L, f).restype = ctypes.c_double
+        for f in ("orc_algorithm_init", "orc_build_structure", "orc_solve", "orc_do_schur"):
+            getattr(L, f).argtypes = [ctypes.c_void_p]
+            getattr(L, f).restype = ctypes.c_int
+        L.orc_set_num_threads.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.orc_set_solver.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
+        L.orc_set_lm_params.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_int]
+        L.orc_set_pcg_params.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_int, ctypes.c_int]
+        L.orc_initialize_optimization.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.orc_optimize.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.orc_set_lambda.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_int]
+        L.orc_set_lambda.restype = None
+        L.orc_update.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_update.restype = None
+        L.orc_set_estimates.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_set_estimates.restype = None
+        L.orc_get_i32.restype = ctypes.POINTER(ctypes.c_int32)
+        L.orc_get_i32.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64)]
+        L.orc_get_f64.restype = ctypes.POINTER(ctypes.c_double)
+        L.orc_get_f64.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64)]
+        L.orc_load_csparse.argtypes = [ctypes.c_char_p]
+        ref = os.path.join(_HERE, "_ref", "libcsparse_ref.so")
+        L._has_csparse = bool(os.path.exists(ref) and L.orc_load_csparse(ref.encode()))
+        _LIB = L
+    return _LIB
+
+
+def has_csparse() -> bool:
+    return lib()._has_csparse
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Oracle:
+    """One reference ``SparseOptimizer`` + algorithm + ``BlockSolver`` + linear solver, CPU."""
+
+    def __init__(self, graph, algorithm: str = "lm", linear: str = "pcg", threads: int = 1):
+        self._L = lib()
+        self.graph = graph
+        cg = graph.as_c()
+        self._h = self._L.orc_create(ctypes.byref(cg))
+        if not self._h:
+            raise ValueError("oracle rejected the graph (unknown type or vertex/edge type mismatch)")
+        rc = self._L.orc_set_solver(self._h, algorithm.encode(), linear.encode())
+        if rc != 0:
+            raise ValueError(f"oracle: cannot configure solver {algorithm}/{linear} (rc={rc})")
+        self._L.orc_set_num_threads(self._h, threads)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.orc_destroy(self._h)
+            self._h = None
+
+    # SparseOptimizer
+    def initialize_optimization(self, level: int = 0) -> bool:
+        return bool(self._L.orc_initialize_optimization(self._h, level))
+
+    def optimize(self, iterations: int):
+        stride = self._L.orc_stats_stride()
+        buf = np.zeros((max(iterations, 1), stride))
+        n = self._L.orc_optimize(self._h, iterations, _dp(buf))
+        stats = [dict(zip(STATS_FIELDS, row)) for row in buf[:max(n, 0)]]
+        return n, stats
+
+    def set_lm_params(self, initial_lambda=0.0, max_trials=10):
+        self._L.orc_set_lm_params(self._h, initial_lambda, max_trials)
+
+    def set_pcg_params(self, tol=1e-6, max_iter=-1, absolute=True):
+        self._L.orc_set_pcg_params(self._h, tol, max_iter, int(absolute))
+
+    def compute_active_errors(self): self._L.orc_compute_active_errors(self._h)
+    def active_robust_chi2(self) -> float: return self._L.orc_active_robust_chi2(self._h)
+    def active_chi2(self) -> float: return self._L.orc_active_chi2(self._h)
+    def update(self, x=None):
+        self._L.orc_update(self._h, None if x is None else _dp(np.ascontiguousarray(x, dtype=np.float64)))
+    def push(self): self._L.orc_push(self._h)
+    def pop(self): self._L.orc_pop(self._h)
+    def discard_top(self): self._L.orc_discard_top(self._h)
+
+    # OptimizationAlgorithm / Solver
+    def algorithm_init(self) -> bool: return bool(self._L.orc_algorithm_init(self._h))
+    def build_structure(self) -> bool: return bool(self._L.orc_build_structure(self._h))
+    def build_system(self): self._L.orc_build_system(self._h)
+    def set_lambda(self, lam: float, backup: bool = True): self._L.orc_set_lambda(self._h, lam, int(backup))
+    def restore_diagonal(self): self._L.orc_restore_diagonal(self._h)
+    def solve(self) -> bool: return bool(self._L.orc_solve(self._h))
+    def compute_lambda_init(self) -> float: return self._L.orc_compute_lambda_init(self._h)
+    def compute_scale(self) -> float: return self._L.orc_compute_scale(self._h)
+    def do_schur(self) -> bool: return bool(self._L.orc_do_schur(self._h))
+
+    def get_i32(self, name: str) -> np.ndarray:
+        n = ctypes.c_int64()
+        p = self._L.orc_get_i32(self._h, name.encode(), ctypes.byref(n))
+        if n.value < 0:
+            raise KeyError(name)
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, dtype=np.int32)
+
+    def get_f64(self, name: str) -> np.ndarray:
+        n = ctypes.c_int64()
+        p = self._L.orc_get_f64(self._h, name.encode(), ctypes.byref(n))
+        if n.value < 0:
+            raise KeyError(name)
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0)
+
+    def set_estimates(self, est: np.ndarray):
+        self._L.orc_set_estimates(self._h, _dp(np.ascontiguousarray(est, dtype=np.float64)))
+
+    def estimates(self) -> np.ndarray:
+        return self.get_f64("estimates")
+
+
+# ---- stateless per-edge helpers (Jacobian / mapping property tests) ----
+def _out(n):
+    return np.zeros(n)
+
+
+def edge_error(etype, x0, x1, z, prm=None):
+    from g2o_b200.graph import EDGE_DIM
+    L = lib(); e = _out(int(EDGE_DIM[etype]))
+    prm = np.zeros(4) if prm is None else np.ascontiguousarray(prm, dtype=np.float64)
+    L.orc_edge_error(ctypes.c_int(etype), _dp(np.ascontiguousarray(x0)), _dp(np.ascontiguousarray(x1)), _dp(np.ascontiguousarray(z)), _dp(prm), _dp(e))
+    return e
+
+
+def edge_jacobian(etype, x0, x1, z, prm=None, numeric=False):
+    from g2o_b200.graph import EDGE_DIM, EDGE_VERTEX_TYPES, VERTEX_DIM
+    L = lib(); E = int(EDGE_DIM[etype]); t0, t1 = EDGE_VERTEX_TYPES[etype]
+    J0 = _out(E * int(VERTEX_DIM[t0])); J1 = _out(E * int(VERTEX_DIM[t1]))
+    prm = np.zeros(4) if prm is None else np.ascontiguousarray(prm, dtype=np.float64)
+    f = L.orc_edge_jacobian_numeric if numeric else L.orc_edge_jacobian
+    f(ctypes.c_int(etype), _dp(np.ascontiguousarray(x0)), _dp(np.ascontiguousarray(x1)), _dp(np.ascontiguousarray(z)), _dp(prm), _dp(J0), _dp(J1))
+    return J0.reshape(-1, E).T.copy(), J1.reshape(-1, E).T.copy()   # (E x D) matrices
+
+
+def vertex_oplus(vtype, est, upd, counter=0):
+    L = lib(); est = np.array(est, dtype=np.float64); c = ctypes.c_int(counter)
+    L.orc_vertex_oplus(ctypes.c_int(vtype), _dp(est), _dp(np.ascontiguousarray(upd, dtype=np.float64)), ctypes.byref(c))
+    return est, c.value
+
+
+def dq_dR(R):
+    out = _out(27); lib().orc_dq_dR(_dp(np.asfortranarray(R).ravel(order="F").copy()), _dp(out))
+    return out.reshape(9, 3).T.copy()   # 3 x 9
+
+
+def quat_from_R(R):
+    q = _out(4); lib().orc_quat_from_R(_dp(np.asfortranarray(R).ravel(order="F").copy()), _dp(q)); return q
+
+
+def R_from_quat(q):
+    R = _out(9); lib().orc_R_from_quat(_dp(np.ascontiguousarray(q, dtype=np.float64)), _dp(R)); return R.reshape(3, 3).T.copy()
+
+
+def robustify(kind, delta, e2):
+    rho = _out(3); lib().orc_robustify(ctypes.c_int(kind), ctypes.c_double(delta), ctypes.c_double(e2), _dp(rho)); return rho
+
+
+def se3_exp(u):
+    v = _out(7); lib().orc_se3_exp(_dp(np.ascontiguousarray(u, dtype=np.float64)), _dp(v)); return v
+
+
+def se3_log(v):
+    u = _out(6); lib().orc_se3_log(_dp(np.ascontiguousarray(v, dtype=np.float64)), _dp(u)); return u
