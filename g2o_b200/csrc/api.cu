@@ -1,0 +1,804 @@
+// C ABI of libg2ocu.so (include/g2ocu.h): handle, device memory, phase sequencing and the LM / GN control flow.
+// The control flow restates OptimizationAlgorithmLevenberg::solve (optimization_algorithm_levenberg.cpp:58-150),
+// OptimizationAlgorithmGaussNewton::solve (optimization_algorithm_gauss_newton.cpp:50-91) and
+// SparseOptimizer::optimize (sparse_optimizer.cpp:374-439); all per-edge / per-block arithmetic runs in the kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/g2ocu.h"
+#include "host_structure.hpp"
+#include "kernels.hpp"
+
+using namespace g2ocu;
+
+namespace {
+
+std::string g_createError;
+
+double wallNow() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+template <class T> struct DVec {
+  T* p = nullptr; size_t n = 0;
+  DVec() {}
+  DVec(const DVec&) = delete; DVec& operator=(const DVec&) = delete;
+  ~DVec() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  cudaError_t alloc(size_t count) {
+    if (count == n && p) return cudaSuccess;
+    release();
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  cudaError_t upload(const std::vector<T>& h, cudaStream_t st) {
+    cudaError_t e = alloc(h.size());
+    if (e != cudaSuccess || h.empty()) return e;
+    return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+  }
+  cudaError_t zero(cudaStream_t st) { return n ? cudaMemsetAsync(p, 0, n * sizeof(T), st) : cudaSuccess; }
+};
+
+struct EdgeSetState {
+  EdgeSetDev dev;
+  DVec<int32_t> slot0, slot1, block, pos, byPose, chunkPose, chunkBegin, chunkEnd, poseChunkPtr, kernelKind;
+  DVec<uint8_t> transposed;
+  DVec<double> meas, info, prm, kernelDelta, partial;
+  int scratchDoubles = 0;
+};
+
+struct PhaseAcc { double seconds = 0; int64_t launches = 0; };
+struct PendingEvent { std::string phase; cudaEvent_t a, b; int64_t launches; };
+
+}  // namespace
+
+struct g2ocu_solver {
+  g2ocu_config cfg;
+  std::string err;
+  HostGraph g; bool hasGraph = false;
+  Structure st; bool optInitialized = false, structureBuilt = false, algoInitialized = false;
+  cudaStream_t stream = nullptr; bool ownStream = false, cudaReady = false;
+  // LM properties / state (optimization_algorithm_levenberg.cpp:40-52)
+  double userLambdaInit = 0.0; int maxTrialsAfterFailure = 10;
+  double currentLambda = -1.0, tau = 1e-5, goodStepUpperScale = 2. / 3., goodStepLowerScale = 1. / 3., ni = 2.0;
+  int levenbergIterations = 0;
+  // solver state
+  double lambda = 0.0;            // damping currently "set" on the diagonals (0 after restoreDiagonal)
+  double pcgResidual = -1.0;      // LinearSolverPCG::_residual, persists across solves until init()
+  int lastPcgIterations = 0;
+  bool errorsValid = false; double chi2Robust = 0, chi2Plain = 0;
+  // sharding
+  int rank = 0, world = 1; g2ocu_allreduce_fn allreduce = nullptr; void* allreduceUser = nullptr;
+  // device state
+  DVec<double> poseEst, lmEst; std::vector<DVec<double>*> poseBackup, lmBackup; int stackDepth = 0;
+  DVec<int> poseCounters, lmCounters;
+  DVec<double> Hpp, Hll, Hpl, b, x, S, Dinv, bschur, Minv, vr, vd, vq, vs, scal, partial, partialDq, scratch, out2, dbg;
+  DVec<int32_t> hppDiag, hplColPtr, hplRowIdx, sRowPtr, sColIdx, sDiag, hppToS, pairSlot, itemLm, itemBegin, itemEnd, aRowPtr, aColIdx, aDiag, spRow, spBegin, spEnd;
+  DVec<int64_t> pairPtr, off64;
+  std::vector<EdgeSetState*> sets;
+  SystemDev sys; SchurDev schur; PcgDev pcg;
+  double* hostScal = nullptr;     // pinned
+  // counters
+  int64_t launches = 0;
+  std::map<std::string, PhaseAcc> phases;
+  std::vector<PendingEvent> pending; std::vector<cudaEvent_t> eventPool;
+
+  ~g2ocu_solver() {
+    for (auto* s : sets) delete s;
+    for (auto* b2 : poseBackup) delete b2;
+    for (auto* b2 : lmBackup) delete b2;
+    for (auto& pe : pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
+    for (auto e : eventPool) cudaEventDestroy(e);
+    if (hostScal) cudaFreeHost(hostScal);
+    if (ownStream && stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+int fail(g2ocu_solver* s, int code, const std::string& msg) { if (s) s->err = msg; else g_createError = msg; return code; }
+#define CU(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(s, G2OCU_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); } while (0)
+
+int ensureCuda(g2ocu_solver* s) {
+  if (s->cudaReady) return G2OCU_OK;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return fail(s, G2OCU_E_CUDA, std::string("no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") + "); this backend has no CPU fallback");
+  if (s->cfg.device >= 0) CU(cudaSetDevice(s->cfg.device));
+  if (s->cfg.stream) { s->stream = (cudaStream_t)s->cfg.stream; s->ownStream = false; }
+  else { CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->ownStream = true; }
+  CU(cudaMallocHost((void**)&s->hostScal, 64 * sizeof(double)));
+  s->cudaReady = true;
+  return G2OCU_OK;
+}
+
+cudaEvent_t getEvent(g2ocu_solver* s) {
+  if (!s->eventPool.empty()) { cudaEvent_t e = s->eventPool.back(); s->eventPool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct PhaseTimer {
+  g2ocu_solver* s; std::string phase; cudaEvent_t a; int64_t l0;
+  PhaseTimer(g2ocu_solver* s_, const char* ph) : s(s_), phase(ph) { a = getEvent(s); cudaEventRecord(a, s->stream); l0 = s->launches; }
+  ~PhaseTimer() { cudaEvent_t b = getEvent(s); cudaEventRecord(b, s->stream); s->pending.push_back({phase, a, b, s->launches - l0}); }
+};
+// call only after the stream has been synchronised
+void resolveEvents(g2ocu_solver* s) {
+  for (auto& pe : s->pending) {
+    float ms = 0; if (cudaEventElapsedTime(&ms, pe.a, pe.b) == cudaSuccess) { auto& acc = s->phases[pe.phase]; acc.seconds += ms * 1e-3; acc.launches += pe.launches; }
+    s->eventPool.push_back(pe.a); s->eventPool.push_back(pe.b);
+  }
+  s->pending.clear();
+}
+int syncStream(g2ocu_solver* s) { CU(cudaStreamSynchronize(s->stream)); resolveEvents(s); return G2OCU_OK; }
+double phaseSeconds(g2ocu_solver* s, const char* ph) { auto it = s->phases.find(ph); return it == s->phases.end() ? 0.0 : it->second.seconds; }
+
+int allreduceDev(g2ocu_solver* s, double* buf, int64_t count, int op) {
+  if (s->world <= 1) return G2OCU_OK;
+  if (!s->allreduce) return fail(s, G2OCU_E_COMM, "world > 1 but no allreduce hook was set");
+  if (s->allreduce(buf, count, op, (void*)s->stream, s->allreduceUser) != 0) return fail(s, G2OCU_E_COMM, "allreduce hook reported an error");
+  return G2OCU_OK;
+}
+
+// ---- upload estimates of one class from the host graph ----
+int uploadEstimates(g2ocu_solver* s) {
+  const Structure& st = s->st; const HostGraph& g = s->g;
+  auto pack = [&](const std::vector<int32_t>& verts, int vtype, std::vector<double>& out) {
+    const int S = vertexEstimateDim(vtype); out.resize((size_t)verts.size() * S);
+    for (size_t i = 0; i < verts.size(); ++i) std::memcpy(&out[i * S], &g.vEst[g.vEstOff[verts[i]]], sizeof(double) * S);
+  };
+  std::vector<double> hp, hl;
+  pack(st.poseVerts, st.poseType, hp);
+  CU(s->poseEst.upload(hp, s->stream));
+  if (st.lmType) { pack(st.lmVerts, st.lmType, hl); CU(s->lmEst.upload(hl, s->stream)); }
+  CU(cudaStreamSynchronize(s->stream));   // host staging vectors go out of scope
+  s->sys.poseEst = s->poseEst.p; s->sys.lmEst = s->lmEst.p;
+  s->errorsValid = false;
+  return G2OCU_OK;
+}
+
+// device estimates -> host graph copy (the host copy is what a rebuild uploads again)
+int downloadEstimates(g2ocu_solver* s) {
+  const Structure& st = s->st; HostGraph& g = s->g;
+  std::vector<double> hp(s->poseEst.n), hl(s->lmEst.n);
+  if (hp.size()) CU(cudaMemcpyAsync(hp.data(), s->poseEst.p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (hl.size()) CU(cudaMemcpyAsync(hl.data(), s->lmEst.p, hl.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  int rc = syncStream(s); if (rc) return rc;
+  const int Sp = vertexEstimateDim(st.poseType), Sl = st.lmType ? vertexEstimateDim(st.lmType) : 0;
+  for (size_t i = 0; i < st.poseVerts.size() && hp.size(); ++i) std::memcpy(&g.vEst[g.vEstOff[st.poseVerts[i]]], &hp[i * Sp], sizeof(double) * Sp);
+  for (size_t i = 0; i < st.lmVerts.size() && hl.size(); ++i) std::memcpy(&g.vEst[g.vEstOff[st.lmVerts[i]]], &hl[i * Sl], sizeof(double) * Sl);
+  return G2OCU_OK;
+}
+
+int buildDevice(g2ocu_solver* s) {
+  const Structure& st = s->st; const HostGraph& g = s->g;
+  cudaStream_t stream = s->stream;
+  for (auto* es : s->sets) delete es;
+  s->sets.clear();
+  int rc = uploadEstimates(s); if (rc) return rc;
+  if (st.poseType == G2OCU_VERTEX_SE3) { CU(s->poseCounters.alloc(st.numPoseSlots)); CU(s->poseCounters.zero(stream)); }
+  const int P = st.P, L = st.L;
+  // ---- system matrices ----
+  CU(s->hppDiag.upload(st.hppDiag, stream));
+  CU(s->Hpp.alloc((size_t)st.hppColIdx.size() * P * P));
+  CU(s->b.alloc((size_t)st.sizePoses + st.sizeLandmarks)); CU(s->x.alloc((size_t)st.sizePoses + st.sizeLandmarks));
+  CU(s->b.zero(stream)); CU(s->x.zero(stream)); CU(s->Hpp.zero(stream));
+  SystemDev& sys = s->sys;
+  sys.numPoses = st.numPoses; sys.numLandmarks = st.numLandmarks; sys.numPoseSlots = st.numPoseSlots; sys.numLmSlots = st.numLmSlots; sys.P = P; sys.L = L;
+  sys.Hpp = s->Hpp.p; sys.hppDiag = s->hppDiag.p; sys.b = s->b.p; sys.hplShared = st.hplShared; sys.hppShared = st.hppShared;
+  if (st.doSchur) {
+    CU(s->Hll.alloc((size_t)st.numLandmarks * L * L)); CU(s->Hpl.alloc((size_t)st.hplRowIdx.size() * P * L));
+    CU(s->Hll.zero(stream)); CU(s->Hpl.zero(stream));
+    sys.Hll = s->Hll.p; sys.Hpl = s->Hpl.p;
+  } else { sys.Hll = nullptr; sys.Hpl = nullptr; }
+
+  // ---- edge sets ----
+  size_t maxScratch = 2400;
+  for (const EdgeSet& hs : st.sets) {
+    auto* es = new EdgeSetState; s->sets.push_back(es);
+    const int n = (int)hs.pos.size(); const int t = hs.etype;
+    const int E = edgeDim(t), M = edgeMeasDim(t), NP = edgeParamDim(t);
+    EdgeSetDev& d = es->dev;
+    d.etype = t; d.n = n; d.poseLandmark = hs.poseLandmark;
+    CU(es->slot0.upload(hs.slot0, stream)); CU(es->slot1.upload(hs.slot1, stream)); CU(es->block.upload(hs.block, stream));
+    CU(es->transposed.upload(hs.transposed, stream)); CU(es->pos.upload(hs.pos, stream));
+    d.slot0 = es->slot0.p; d.slot1 = es->slot1.p; d.block = es->block.p; d.transposed = es->transposed.p; d.pos = es->pos.p;
+    std::vector<double> meas((size_t)n * M), info((size_t)n * E * E), prm((size_t)n * NP), delta(n);
+    std::vector<int32_t> kind(n);
+    for (int i = 0; i < n; ++i) {
+      const int e = st.activeEdges[hs.pos[i]];
+      std::memcpy(&meas[(size_t)i * M], &g.eMeas[g.eMeasOff[e]], sizeof(double) * M);
+      std::memcpy(&info[(size_t)i * E * E], &g.eInfo[g.eInfoOff[e]], sizeof(double) * E * E);
+      if (NP) std::memcpy(&prm[(size_t)i * NP], &g.ePrm[g.ePrmOff[e]], sizeof(double) * NP);
+      kind[i] = g.eKernel[e]; delta[i] = g.eDelta[e];
+    }
+    CU(es->meas.upload(meas, stream)); d.meas = es->meas.p;
+    // information: identity / uniform / per edge
+    bool uniform = true, identity = true;
+    for (int i = 0; i < n && uniform; ++i) uniform = std::memcmp(&info[(size_t)i * E * E], &info[0], sizeof(double) * E * E) == 0;
+    for (int k = 0; k < E * E && identity; ++k) identity = info[k] == ((k % (E + 1)) == 0 ? 1.0 : 0.0);
+    if (uniform && identity) d.infoMode = 0;
+    else if (uniform) { info.resize((size_t)E * E); d.infoMode = 1; }
+    else d.infoMode = 2;
+    if (d.infoMode) { CU(es->info.upload(info, stream)); d.info = es->info.p; }
+    bool kUniform = true;
+    for (int i = 1; i < n && kUniform; ++i) kUniform = kind[i] == kind[0] && delta[i] == delta[0];
+    if (kUniform) { d.kernelMode = kind[0] ? 1 : 0; d.kKind = kind[0]; d.kDelta = delta[0]; }
+    else { d.kernelMode = 2; CU(es->kernelKind.upload(kind, stream)); CU(es->kernelDelta.upload(delta, stream)); d.kernelKind = es->kernelKind.p; d.kernelDelta = es->kernelDelta.p; }
+    if (NP) {
+      bool pUniform = true;
+      for (int i = 1; i < n && pUniform; ++i) pUniform = std::memcmp(&prm[(size_t)i * NP], &prm[0], sizeof(double) * NP) == 0;
+      if (pUniform) { prm.resize(NP); d.prmMode = 1; } else d.prmMode = 2;
+      CU(es->prm.upload(prm, stream)); d.prm = es->prm.p;
+    }
+    if (hs.poseLandmark) {
+      CU(es->byPose.upload(hs.byPose, stream)); CU(es->chunkPose.upload(hs.chunkPose, stream)); CU(es->chunkBegin.upload(hs.chunkBegin, stream));
+      CU(es->chunkEnd.upload(hs.chunkEnd, stream)); CU(es->poseChunkPtr.upload(hs.poseChunkPtr, stream));
+      d.byPose = es->byPose.p; d.nByPose = (int)hs.byPose.size(); d.chunkPose = es->chunkPose.p; d.chunkBegin = es->chunkBegin.p; d.chunkEnd = es->chunkEnd.p;
+      d.nChunks = (int)hs.chunkPose.size(); d.poseChunkPtr = es->poseChunkPtr.p;
+      CU(es->partial.alloc((size_t)d.nChunks * (P * (P + 1) / 2 + P))); d.partial = es->partial.p;
+    }
+    CU(cudaStreamSynchronize(stream));   // staging vectors die here
+    maxScratch = std::max(maxScratch, (size_t)errorScratchDoubles(n));
+  }
+  CU(s->scratch.alloc(maxScratch)); CU(s->out2.alloc(8));
+
+  // ---- Schur structures ----
+  SchurDev& sd = s->schur; sd = SchurDev();
+  if (st.doSchur) {
+    CU(s->hplColPtr.upload(st.hplColPtr, stream)); CU(s->hplRowIdx.upload(st.hplRowIdx, stream));
+    CU(s->sRowPtr.upload(st.sRowPtr, stream)); CU(s->sColIdx.upload(st.sColIdx, stream)); CU(s->sDiag.upload(st.sDiag, stream)); CU(s->hppToS.upload(st.hppToS, stream));
+    std::vector<int64_t> pairPtr(st.numLandmarks + 1, 0);
+    std::vector<int32_t> itLm, itB, itE;
+    const int64_t kMaxPairsPerItem = 384;
+    for (int l = 0; l < st.numLandmarks; ++l) {
+      const int64_t k = st.hplColPtr[l + 1] - st.hplColPtr[l];
+      pairPtr[l + 1] = pairPtr[l] + k * (k + 1) / 2;
+      int begin = 0; int64_t acc = 0;
+      if (k == 0) { itLm.push_back(l); itB.push_back(0); itE.push_back(0); continue; }
+      for (int i = 0; i < k; ++i) {
+        acc += k - i;
+        if (acc >= kMaxPairsPerItem || i == k - 1) { itLm.push_back(l); itB.push_back(begin); itE.push_back(i + 1); begin = i + 1; acc = 0; }
+      }
+    }
+    CU(s->pairPtr.upload(pairPtr, stream)); CU(s->pairSlot.alloc((size_t)std::max<int64_t>(pairPtr[st.numLandmarks], 1)));
+    CU(s->itemLm.upload(itLm, stream)); CU(s->itemBegin.upload(itB, stream)); CU(s->itemEnd.upload(itE, stream));
+    CU(s->S.alloc((size_t)st.sColIdx.size() * P * P)); CU(s->Dinv.alloc((size_t)st.numLandmarks * L * L)); CU(s->bschur.alloc((size_t)st.sizePoses));
+    sd.numPoses = st.numPoses; sd.numLandmarks = st.numLandmarks; sd.P = P; sd.L = L;
+    sd.hplColPtr = s->hplColPtr.p; sd.hplRowIdx = s->hplRowIdx.p; sd.sRowPtr = s->sRowPtr.p; sd.sColIdx = s->sColIdx.p; sd.sDiag = s->sDiag.p;
+    sd.hppToS = s->hppToS.p; sd.nnzHpp = (int)st.hppColIdx.size(); sd.nnzS = (int)st.sColIdx.size();
+    sd.pairPtr = s->pairPtr.p; sd.pairSlot = s->pairSlot.p; sd.itemLm = s->itemLm.p; sd.itemBegin = s->itemBegin.p; sd.itemEnd = s->itemEnd.p; sd.nItems = (int)itLm.size();
+    sd.S = s->S.p; sd.Dinv = s->Dinv.p; sd.bschur = s->bschur.p;
+    launchPairSlots(sd, stream, &s->launches);
+    CU(cudaStreamSynchronize(stream));
+  }
+  // ---- PCG structures over A = Hschur (Schur) or Hpp ----
+  PcgDev& pc = s->pcg; pc = PcgDev();
+  const std::vector<int32_t>& rowPtr = st.doSchur ? st.sRowPtr : st.hppRowPtr;
+  const std::vector<int32_t>& colIdx = st.doSchur ? st.sColIdx : st.hppColIdx;
+  const std::vector<int32_t>& diag = st.doSchur ? st.sDiag : st.hppDiag;
+  CU(s->aRowPtr.upload(rowPtr, stream)); CU(s->aColIdx.upload(colIdx, stream)); CU(s->aDiag.upload(diag, stream));
+  {
+    const int G = 32 / P, chunk = G * 16;
+    std::vector<int32_t> r, bgn, en;
+    for (int i = 0; i < st.numPoses; ++i)
+      for (int k = rowPtr[i]; k < rowPtr[i + 1]; k += chunk) { r.push_back(i); bgn.push_back(k); en.push_back(std::min(k + chunk, rowPtr[i + 1])); }
+    CU(s->spRow.upload(r, stream)); CU(s->spBegin.upload(bgn, stream)); CU(s->spEnd.upload(en, stream));
+    pc.nItems = (int)r.size();
+    CU(cudaStreamSynchronize(stream));
+  }
+  pc.n = st.sizePoses; pc.nb = st.numPoses; pc.P = P; pc.rowPtr = s->aRowPtr.p; pc.colIdx = s->aColIdx.p; pc.diag = s->aDiag.p; pc.nnz = (int)colIdx.size();
+  pc.A = st.doSchur ? s->S.p : s->Hpp.p;
+  CU(s->Minv.alloc((size_t)st.numPoses * P * P)); CU(s->vr.alloc(pc.n)); CU(s->vd.alloc(pc.n)); CU(s->vq.alloc(pc.n)); CU(s->vs.alloc(pc.n)); CU(s->scal.alloc(16));
+  pc.nPartial = (st.numPoses + 127) / 128; pc.nPartialDq = std::min(296, (pc.n + 255) / 256);
+  CU(s->partial.alloc(pc.nPartial)); CU(s->partialDq.alloc(pc.nPartialDq));
+  pc.Minv = s->Minv.p; pc.r = s->vr.p; pc.d = s->vd.p; pc.q = s->vq.p; pc.s = s->vs.p; pc.x = s->x.p; pc.scal = s->scal.p; pc.partial = s->partial.p; pc.partialDq = s->partialDq.p;
+  pc.itemRow = s->spRow.p; pc.itemBegin = s->spBegin.p; pc.itemEnd = s->spEnd.p;
+  CU(s->scal.zero(stream));
+  CU(cudaStreamSynchronize(stream));
+  CU(cudaGetLastError());
+  return G2OCU_OK;
+}
+
+int requireBuilt(g2ocu_solver* s) {
+  if (!s) return G2OCU_E_INVALID;
+  if (!s->structureBuilt) return fail(s, G2OCU_E_INVALID, "buildStructure has not been called");
+  return G2OCU_OK;
+}
+
+int computeErrors(g2ocu_solver* s, double* errOut, const int64_t* errOff) {
+  PhaseTimer pt(s, "errors");
+  CU(s->out2.zero(s->stream));
+  for (auto* es : s->sets) launchErrors(es->dev, s->sys, s->scratch.p, s->out2.p, errOut, errOff, s->stream, &s->launches);
+  int rc = allreduceDev(s, s->out2.p, 2, 0); if (rc) return rc;
+  CU(cudaMemcpyAsync(s->hostScal, s->out2.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  return G2OCU_OK;
+}
+int finishErrors(g2ocu_solver* s) {
+  int rc = syncStream(s); if (rc) return rc;
+  s->chi2Robust = s->hostScal[0]; s->chi2Plain = s->hostScal[1]; s->errorsValid = true;
+  return G2OCU_OK;
+}
+
+int buildSystem(g2ocu_solver* s) {
+  PhaseTimer pt(s, "build");
+  CU(s->Hpp.zero(s->stream)); CU(s->b.zero(s->stream));
+  if (s->st.doSchur) { CU(s->Hll.zero(s->stream)); if (s->st.hplShared) CU(s->Hpl.zero(s->stream)); }
+  for (auto* es : s->sets) launchBuild(es->dev, s->sys, s->stream, &s->launches);
+  CU(cudaGetLastError());
+  return G2OCU_OK;
+}
+
+int solvePcg(g2ocu_solver* s, const double* rhs) {
+  PcgDev& pc = s->pcg;
+  pc.lambda = s->st.doSchur ? 0.0 : s->lambda;
+  { PhaseTimer pt(s, "pcg_setup");
+    launchBlockInverse(pc, s->stream, &s->launches);
+    launchPcgInit(pc, rhs, s->cfg.pcg_tolerance, s->pcgResidual, s->cfg.pcg_absolute_tolerance, s->stream, &s->launches); }
+  const int maxIter = s->cfg.pcg_max_iterations < 0 ? pc.n : s->cfg.pcg_max_iterations;
+  int issued = 0; bool done = false;
+  const int kCheckEvery = 4;
+  while (!done) {
+    const int batch = std::min(kCheckEvery, maxIter - issued);
+    for (int k = 0; k < batch; ++k) {
+      { PhaseTimer pt(s, "pcg_spmv"); launchSpmv(pc, pc.d, pc.q, s->stream, &s->launches); }
+      { PhaseTimer pt(s, "pcg_vec"); launchPcgTail(pc, s->stream, &s->launches); }
+    }
+    issued += batch;
+    CU(cudaMemcpyAsync(s->hostScal + 8, pc.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    int rc = syncStream(s); if (rc) return rc;
+    const bool converged = s->hostScal[8 + 6] != 0.0;
+    if (converged || issued >= maxIter) done = true;
+    if (!std::isfinite(s->hostScal[8 + 2])) done = true;   // NaN/Inf in the recurrence: stop issuing work (the reference would spin to maxIter)
+  }
+  s->lastPcgIterations = (int)s->hostScal[8 + 7];
+  s->pcgResidual = 0.5 * s->hostScal[8 + 2];
+  return G2OCU_OK;
+}
+
+int solveSystem(g2ocu_solver* s, int* solved) {
+  const Structure& st = s->st;
+  *solved = 1;
+  if (s->cfg.linear_solver != G2OCU_LINEAR_PCG) return fail(s, G2OCU_E_UNSUPPORTED, "dense Cholesky linear solver is not available in this build");
+  if (!st.doSchur) {
+    PhaseTimer pt(s, "linear_solver");
+    return solvePcg(s, s->b.p);
+  }
+  { PhaseTimer pt(s, "schur");
+    launchSchur(s->schur, s->sys, s->lambda, s->stream, &s->launches);
+    if (s->world > 1) {
+      int rc = allreduceDev(s, s->S.p, (int64_t)s->S.n, 0); if (rc) return rc;
+      rc = allreduceDev(s, s->bschur.p, (int64_t)s->bschur.n, 0); if (rc) return rc;
+    } }
+  { PhaseTimer pt(s, "linear_solver");
+    int rc = solvePcg(s, s->bschur.p); if (rc) return rc; }
+  { PhaseTimer pt(s, "backsub");
+    launchBacksub(s->schur, s->sys, s->x.p, s->x.p + st.sizePoses, s->stream, &s->launches); }
+  CU(cudaGetLastError());
+  return G2OCU_OK;
+}
+
+int applyUpdate(g2ocu_solver* s) {
+  PhaseTimer pt(s, "update");
+  const Structure& st = s->st;
+  launchUpdate(st.poseType, s->poseEst.p, nullptr, s->poseCounters.p, s->x.p, st.numPoses, s->stream, &s->launches);
+  if (st.numLandmarks) launchUpdate(st.lmType, s->lmEst.p, nullptr, nullptr, s->x.p + st.sizePoses, st.numLandmarks, s->stream, &s->launches);
+  s->errorsValid = false;
+  CU(cudaGetLastError());
+  return G2OCU_OK;
+}
+
+int pushEstimates(g2ocu_solver* s) {
+  if ((int)s->poseBackup.size() <= s->stackDepth) { s->poseBackup.push_back(new DVec<double>); s->lmBackup.push_back(new DVec<double>); }
+  DVec<double>& pb = *s->poseBackup[s->stackDepth]; DVec<double>& lb = *s->lmBackup[s->stackDepth];
+  CU(pb.alloc(s->poseEst.n)); CU(lb.alloc(s->lmEst.n));
+  CU(cudaMemcpyAsync(pb.p, s->poseEst.p, s->poseEst.n * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+  if (s->lmEst.n) CU(cudaMemcpyAsync(lb.p, s->lmEst.p, s->lmEst.n * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+  s->stackDepth++;
+  return G2OCU_OK;
+}
+int popEstimates(g2ocu_solver* s, bool restore) {
+  if (s->stackDepth == 0) return fail(s, G2OCU_E_INVALID, "pop/discardTop on an empty backup stack");
+  s->stackDepth--;
+  if (restore) {
+    DVec<double>& pb = *s->poseBackup[s->stackDepth]; DVec<double>& lb = *s->lmBackup[s->stackDepth];
+    CU(cudaMemcpyAsync(s->poseEst.p, pb.p, s->poseEst.n * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    if (s->lmEst.n) CU(cudaMemcpyAsync(s->lmEst.p, lb.p, s->lmEst.n * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    s->errorsValid = false;
+  }
+  return G2OCU_OK;
+}
+
+int lambdaInit(g2ocu_solver* s, double* out) {
+  if (s->userLambdaInit > 0) { *out = s->userLambdaInit; return G2OCU_OK; }
+  if (s->world > 1) {   // the pose diagonals are partial sums on each rank
+    return fail(s, G2OCU_E_UNSUPPORTED, "computeLambdaInit with world > 1 requires initialLambda");
+  }
+  launchMaxDiag(s->sys, s->scratch.p, s->out2.p + 4, s->stream, &s->launches);
+  CU(cudaMemcpyAsync(s->hostScal + 4, s->out2.p + 4, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  int rc = syncStream(s); if (rc) return rc;
+  *out = s->tau * s->hostScal[4];
+  return G2OCU_OK;
+}
+int computeScale(g2ocu_solver* s, double lambda, double* out) {
+  launchScale(s->x.p, s->b.p, (int64_t)s->x.n, lambda, s->scratch.p, s->out2.p + 5, s->stream, &s->launches);
+  CU(cudaMemcpyAsync(s->hostScal + 5, s->out2.p + 5, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  int rc = syncStream(s); if (rc) return rc;
+  *out = s->hostScal[5];
+  return G2OCU_OK;
+}
+
+// OptimizationAlgorithmLevenberg::solve, optimization_algorithm_levenberg.cpp:58-150
+int solveLevenberg(g2ocu_solver* s, int iteration, int* result) {
+  int rc;
+  if (iteration == 0) { rc = g2ocu_build_structure(s); if (rc) { *result = G2OCU_RESULT_FAIL; return rc; } }
+  rc = computeErrors(s, nullptr, nullptr); if (rc) return rc;
+  rc = buildSystem(s); if (rc) return rc;          // enqueued behind the error kernels; one sync serves both
+  rc = finishErrors(s); if (rc) return rc;
+  double currentChi = s->chi2Robust, tempChi = currentChi;
+  if (iteration == 0) { rc = lambdaInit(s, &s->currentLambda); if (rc) return rc; s->ni = 2; }
+  double rho = 0; int& qmax = s->levenbergIterations; qmax = 0;
+  do {
+    rc = pushEstimates(s); if (rc) return rc;
+    s->lambda = s->currentLambda;                      // setLambda(_currentLambda, true)
+    int ok2 = 1;
+    rc = solveSystem(s, &ok2); if (rc) return rc;
+    rc = applyUpdate(s); if (rc) return rc;
+    s->lambda = 0.0;                                   // restoreDiagonal
+    rc = computeErrors(s, nullptr, nullptr); if (rc) return rc;
+    double scale = 0;
+    launchScale(s->x.p, s->b.p, (int64_t)s->x.n, s->currentLambda, s->scratch.p, s->out2.p + 5, s->stream, &s->launches);
+    CU(cudaMemcpyAsync(s->hostScal + 5, s->out2.p + 5, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    rc = finishErrors(s); if (rc) return rc;
+    scale = s->hostScal[5];
+    tempChi = s->chi2Robust;
+    if (!ok2) tempChi = std::numeric_limits<double>::max();
+    rho = (currentChi - tempChi);
+    scale += 1e-3;
+    rho /= scale;
+    if (rho > 0 && std::isfinite(tempChi)) {
+      double alpha = 1. - std::pow((2 * rho - 1), 3);
+      alpha = (std::min)(alpha, s->goodStepUpperScale);
+      const double scaleFactor = (std::max)(s->goodStepLowerScale, alpha);
+      s->currentLambda *= scaleFactor; s->ni = 2; currentChi = tempChi;
+      rc = popEstimates(s, false); if (rc) return rc;
+    } else {
+      s->currentLambda *= s->ni; s->ni *= 2;
+      rc = popEstimates(s, true); if (rc) return rc;
+      if (!std::isfinite(s->currentLambda)) break;
+    }
+    qmax++;
+  } while (rho < 0 && qmax < s->maxTrialsAfterFailure);
+  if (qmax == s->maxTrialsAfterFailure || rho == 0 || !std::isfinite(s->currentLambda)) *result = G2OCU_RESULT_TERMINATE;
+  else *result = G2OCU_RESULT_OK;
+  return G2OCU_OK;
+}
+
+// OptimizationAlgorithmGaussNewton::solve, optimization_algorithm_gauss_newton.cpp:50-91
+int solveGaussNewton(g2ocu_solver* s, int iteration, int* result) {
+  int rc;
+  if (iteration == 0) { rc = g2ocu_build_structure(s); if (rc) { *result = G2OCU_RESULT_FAIL; return rc; } }
+  rc = buildSystem(s); if (rc) return rc;
+  s->lambda = 0.0;
+  int ok = 1;
+  rc = solveSystem(s, &ok); if (rc) return rc;
+  rc = applyUpdate(s); if (rc) return rc;
+  *result = ok ? G2OCU_RESULT_OK : G2OCU_RESULT_FAIL;
+  return G2OCU_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+void g2ocu_default_config(g2ocu_config* cfg) {
+  if (!cfg) return;
+  cfg->device = -1; cfg->linear_solver = G2OCU_LINEAR_PCG; cfg->pcg_tolerance = 1e-6; cfg->pcg_max_iterations = -1; cfg->pcg_absolute_tolerance = 1; cfg->stream = nullptr;
+}
+int g2ocu_version(void) { return G2OCU_VERSION; }
+const char* g2ocu_last_error(const g2ocu_solver* s) { return s ? s->err.c_str() : g_createError.c_str(); }
+
+int g2ocu_create(const g2ocu_config* cfg, g2ocu_solver** out) {
+  if (!out) return fail(nullptr, G2OCU_E_INVALID, "null output pointer");
+  g2ocu_solver* s = new g2ocu_solver;
+  if (cfg) s->cfg = *cfg; else g2ocu_default_config(&s->cfg);
+  if (s->cfg.linear_solver != G2OCU_LINEAR_PCG && s->cfg.linear_solver != G2OCU_LINEAR_DENSE) { delete s; return fail(nullptr, G2OCU_E_INVALID, "unknown linear solver kind"); }
+  *out = s;
+  return G2OCU_OK;
+}
+void g2ocu_destroy(g2ocu_solver* s) { delete s; }
+
+int g2ocu_set_graph(g2ocu_solver* s, const g2ocu_graph* g) {
+  if (!s) return G2OCU_E_INVALID;
+  std::string err;
+  s->hasGraph = false; s->optInitialized = false; s->structureBuilt = false; s->algoInitialized = false;
+  if (!s->g.assign(g, err)) return fail(s, err.find("unsupported") != std::string::npos ? G2OCU_E_UNSUPPORTED : G2OCU_E_INVALID, err);
+  s->hasGraph = true;
+  return G2OCU_OK;
+}
+int g2ocu_set_property(g2ocu_solver* s, const char* name, double value) {
+  if (!s || !name) return G2OCU_E_INVALID;
+  const std::string n(name);
+  if (n == "initialLambda") s->userLambdaInit = value;
+  else if (n == "maxTrialsAfterFailure") s->maxTrialsAfterFailure = (int)value;
+  else if (n == "pcgTolerance") s->cfg.pcg_tolerance = value;
+  else if (n == "pcgMaxIterations") s->cfg.pcg_max_iterations = (int)value;
+  else if (n == "pcgAbsoluteTolerance") s->cfg.pcg_absolute_tolerance = (int)value;
+  else return fail(s, G2OCU_E_INVALID, "unknown property " + n);
+  return G2OCU_OK;
+}
+int g2ocu_set_shard(g2ocu_solver* s, int32_t rank, int32_t world, g2ocu_allreduce_fn fn, void* user) {
+  if (!s || world < 1 || rank < 0 || rank >= world) return fail(s, G2OCU_E_INVALID, "bad rank/world");
+  if (world > 1 && !fn) return fail(s, G2OCU_E_INVALID, "world > 1 needs an allreduce hook");
+  s->rank = rank; s->world = world; s->allreduce = fn; s->allreduceUser = user;
+  s->structureBuilt = false;
+  return G2OCU_OK;
+}
+
+int g2ocu_initialize_optimization(g2ocu_solver* s, int32_t level) {
+  if (!s) return G2OCU_E_INVALID;
+  if (!s->hasGraph) return fail(s, G2OCU_E_INVALID, "no graph set");
+  std::string err;
+  if (s->structureBuilt) { int rc0 = downloadEstimates(s); if (rc0) return rc0; }   // vertices keep their estimates
+  s->optInitialized = false; s->structureBuilt = false; s->algoInitialized = false;
+  if (!initializeOptimization(s->g, level, s->st, err)) return fail(s, G2OCU_E_INVALID, err);
+  s->optInitialized = true;
+  return G2OCU_OK;
+}
+
+// OptimizationAlgorithmWithHessian::init (+ Solver::init, LinearSolver::init): chooses Schur, resets the PCG residual.
+int g2ocu_init(g2ocu_solver* s, int32_t online) {
+  if (!s) return G2OCU_E_INVALID;
+  if (!s->optInitialized) return fail(s, G2OCU_E_INVALID, "0 vertices to optimize, maybe forgot to call initializeOptimization()");
+  (void)online;
+  s->pcgResidual = -1.0;        // LinearSolverPCG::init, linear_solver_pcg.h:64-70
+  s->algoInitialized = true;
+  return G2OCU_OK;
+}
+
+int g2ocu_build_structure(g2ocu_solver* s) {
+  if (!s) return G2OCU_E_INVALID;
+  if (!s->optInitialized) return fail(s, G2OCU_E_INVALID, "initializeOptimization has not been called");
+  std::string err;
+  if (s->structureBuilt) { int rc0 = downloadEstimates(s); if (rc0) return rc0; }   // vertices keep their state across optimize() calls
+  s->structureBuilt = false;
+  if (!buildStructure(s->g, s->st, err)) return fail(s, G2OCU_E_UNSUPPORTED, err);
+  const Structure& st = s->st;
+  const bool okDims = (st.doSchur && ((st.P == 9 && st.L == 3) || (st.P == 6 && st.L == 3) || (st.P == 3 && st.L == 2))) || (!st.doSchur && (st.P == 3 || st.P == 6 || st.P == 9));
+  if (!okDims) return fail(s, G2OCU_E_UNSUPPORTED, "unsupported block sizes P=" + std::to_string(st.P) + " L=" + std::to_string(st.L));
+  for (const EdgeSet& es : st.sets) {
+    const bool naturalPL = es.etype == G2OCU_EDGE_SE2_POINT_XY || es.etype == G2OCU_EDGE_PROJECT_XYZ2UV || es.etype == G2OCU_EDGE_SE3_PROJECT_XYZ || es.etype == G2OCU_EDGE_BAL;
+    const int naturalSide = (es.etype == G2OCU_EDGE_PROJECT_XYZ2UV || es.etype == G2OCU_EDGE_SE3_PROJECT_XYZ) ? 1 : 0;
+    if (naturalPL != es.poseLandmark || (naturalPL && naturalSide != es.poseSide))
+      return fail(s, G2OCU_E_UNSUPPORTED, "edge type " + std::to_string(es.etype) + ": the landmark-side vertices must be marginalized and the pose-side vertices must not (mixed block sizes are not supported)");
+  }
+  int rc = ensureCuda(s); if (rc) return rc;
+  rc = buildDevice(s); if (rc) return rc;
+  s->structureBuilt = true; s->lambda = 0.0; s->stackDepth = 0;
+  return G2OCU_OK;
+}
+
+int g2ocu_compute_active_errors(g2ocu_solver* s) {
+  int rc = requireBuilt(s); if (rc) return rc;
+  rc = computeErrors(s, nullptr, nullptr); if (rc) return rc;
+  return finishErrors(s);
+}
+int g2ocu_active_robust_chi2(g2ocu_solver* s, double* chi2) {
+  int rc = requireBuilt(s); if (rc) return rc;
+  if (!s->errorsValid) { rc = g2ocu_compute_active_errors(s); if (rc) return rc; }
+  if (chi2) *chi2 = s->chi2Robust;
+  return G2OCU_OK;
+}
+int g2ocu_active_chi2(g2ocu_solver* s, double* chi2) {
+  int rc = requireBuilt(s); if (rc) return rc;
+  if (!s->errorsValid) { rc = g2ocu_compute_active_errors(s); if (rc) return rc; }
+  if (chi2) *chi2 = s->chi2Plain;
+  return G2OCU_OK;
+}
+int g2ocu_build_system(g2ocu_solver* s) { int rc = requireBuilt(s); if (rc) return rc; rc = buildSystem(s); if (rc) return rc; return syncStream(s); }
+int g2ocu_set_lambda(g2ocu_solver* s, double lambda, int32_t) { int rc = requireBuilt(s); if (rc) return rc; s->lambda += lambda; return G2OCU_OK; }
+int g2ocu_restore_diagonal(g2ocu_solver* s) { int rc = requireBuilt(s); if (rc) return rc; s->lambda = 0.0; return G2OCU_OK; }
+int g2ocu_solve(g2ocu_solver* s, int32_t* solved) {
+  int rc = requireBuilt(s); if (rc) return rc;
+  int ok = 1; rc = solveSystem(s, &ok); if (rc) return rc;
+  if (solved) *solved = ok;
+  return syncStream(s);
+}
+int g2ocu_update(g2ocu_solver* s, const double* host) {
+  int rc = requireBuilt(s); if (rc) return rc;
+  if (host) CU(cudaMemcpyAsync(s->x.p, host, s->x.n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  rc = applyUpdate(s); if (rc) return rc;
+  return syncStream(s);
+}
+int g2ocu_push(g2ocu_solver* s) { int rc = requireBuilt(s); if (rc) return rc; return pushEstimates(s); }
+int g2ocu_pop(g2ocu_solver* s) { int rc = requireBuilt(s); if (rc) return rc; return popEstimates(s, true); }
+int g2ocu_discard_top(g2ocu_solver* s) { int rc = requireBuilt(s); if (rc) return rc; return popEstimates(s, false); }
+int g2ocu_compute_lambda_init(g2ocu_solver* s, double* lambda) { int rc = requireBuilt(s); if (rc) return rc; double v = 0; rc = lambdaInit(s, &v); if (lambda) *lambda = v; return rc; }
+int g2ocu_compute_scale(g2ocu_solver* s, double lambda, double* scale) { int rc = requireBuilt(s); if (rc) return rc; double v = 0; rc = computeScale(s, lambda, &v); if (scale) *scale = v; return rc; }
+
+int g2ocu_multiply_hessian(g2ocu_solver* s, double* hostDest, const double* hostSrc) {
+  int rc = requireBuilt(s); if (rc) return rc;
+  if (!hostDest || !hostSrc) return fail(s, G2OCU_E_INVALID, "null vector");
+  const int n = s->st.sizePoses;                                     // BlockSolverBase::multiplyHessian works on Hpp (block_solver.h:87-95)
+  PcgDev pc = s->pcg; pc.A = s->Hpp.p; pc.lambda = s->lambda; pc.scal = nullptr;
+  DVec<int32_t> r, bgn, en;
+  if (s->st.doSchur) {                                               // SpMV items over the Hpp pattern
+    std::vector<int32_t> hr, hb, he;
+    for (int i = 0; i < s->st.numPoses; ++i) { hr.push_back(i); hb.push_back(s->st.hppRowPtr[i]); he.push_back(s->st.hppRowPtr[i + 1]); }
+    DVec<int32_t> rp, ci;
+    CU(r.upload(hr, s->stream)); CU(bgn.upload(hb, s->stream)); CU(en.upload(he, s->stream));
+    CU(rp.upload(s->st.hppRowPtr, s->stream)); CU(ci.upload(s->st.hppColIdx, s->stream));
+    pc.itemRow = r.p; pc.itemBegin = bgn.p; pc.itemEnd = en.p; pc.nItems = (int)hr.size(); pc.rowPtr = rp.p; pc.colIdx = ci.p; pc.diag = s->hppDiag.p;
+    CU(cudaMemcpyAsync(s->vd.p, hostSrc, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    launchSpmv(pc, s->vd.p, s->vq.p, s->stream, &s->launches);
+    CU(cudaMemcpyAsync(hostDest, s->vq.p, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    return syncStream(s);
+  }
+  CU(cudaMemcpyAsync(s->vd.p, hostSrc, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  launchSpmv(pc, s->vd.p, s->vq.p, s->stream, &s->launches);
+  CU(cudaMemcpyAsync(hostDest, s->vq.p, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  return syncStream(s);
+}
+
+int g2ocu_solver_iteration(g2ocu_solver* s, int32_t algorithm, int32_t iteration, g2ocu_iteration_stats* stats) {
+  if (!s) return G2OCU_E_INVALID;
+  if (!s->algoInitialized) return fail(s, G2OCU_E_INVALID, "g2ocu_init has not been called");
+  if (iteration != 0) { int rc = requireBuilt(s); if (rc) return rc; }
+  const double t0 = wallNow();
+  const double e0 = phaseSeconds(s, "errors"), b0 = phaseSeconds(s, "build"), sc0 = phaseSeconds(s, "schur"), l0 = phaseSeconds(s, "linear_solver"), u0 = phaseSeconds(s, "update"), bs0 = phaseSeconds(s, "backsub");
+  int result = G2OCU_RESULT_FAIL;
+  int rc = (algorithm == G2OCU_ALGORITHM_LM) ? solveLevenberg(s, iteration, &result) : solveGaussNewton(s, iteration, &result);
+  if (rc) return rc;
+  if (stats) {
+    // SparseOptimizer::optimize computes the errors again for the statistics (sparse_optimizer.cpp:411-417)
+    double chi2 = 0; rc = g2ocu_active_robust_chi2(s, &chi2); if (rc) return rc;
+    std::memset(stats, 0, sizeof(*stats));
+    stats->iteration = iteration; stats->result = result; stats->levenberg_iterations = algorithm == G2OCU_ALGORITHM_LM ? s->levenbergIterations : 0;
+    stats->iterations_linear_solver = s->lastPcgIterations; stats->chi2 = chi2; stats->lambda = s->currentLambda;
+    stats->time_residuals = phaseSeconds(s, "errors") - e0; stats->time_quadratic_form = phaseSeconds(s, "build") - b0;
+    stats->time_schur_complement = phaseSeconds(s, "schur") - sc0; stats->time_linear_solver = phaseSeconds(s, "linear_solver") - l0;
+    stats->time_linear_solution = stats->time_schur_complement + stats->time_linear_solver + (phaseSeconds(s, "backsub") - bs0);
+    stats->time_update = phaseSeconds(s, "update") - u0; stats->time_iteration = wallNow() - t0;
+    stats->hessian_pose_dimension = s->st.sizePoses; stats->hessian_landmark_dimension = s->st.sizeLandmarks;
+  }
+  return G2OCU_OK;
+}
+
+// SparseOptimizer::optimize, sparse_optimizer.cpp:374-439
+int g2ocu_optimize(g2ocu_solver* s, int32_t algorithm, int32_t iterations, g2ocu_iteration_stats* stats, int32_t* performed) {
+  if (!s) return G2OCU_E_INVALID;
+  if (performed) *performed = -1;
+  if (!s->optInitialized || s->st.ivMap.empty()) return fail(s, G2OCU_E_INVALID, "0 vertices to optimize, maybe forgot to call initializeOptimization()");
+  int rc = g2ocu_init(s, 0); if (rc) return rc;
+  int cj = 0; bool ok = true; int result = G2OCU_RESULT_OK;
+  for (int i = 0; i < iterations && ok; ++i) {
+    g2ocu_iteration_stats local;
+    rc = g2ocu_solver_iteration(s, algorithm, i, stats ? &stats[i] : &local); if (rc) return rc;
+    result = stats ? stats[i].result : local.result;
+    ok = (result == G2OCU_RESULT_OK);
+    ++cj;
+  }
+  if (performed) *performed = (result == G2OCU_RESULT_FAIL) ? 0 : cj;
+  return G2OCU_OK;
+}
+
+int64_t g2ocu_vector_size(const g2ocu_solver* s) { return (s && s->structureBuilt) ? (int64_t)s->st.sizePoses + s->st.sizeLandmarks : 0; }
+
+int g2ocu_set_estimates(g2ocu_solver* s, const double* host) {
+  if (!s || !host) return G2OCU_E_INVALID;
+  if (!s->hasGraph) return fail(s, G2OCU_E_INVALID, "no graph set");
+  std::memcpy(s->g.vEst.data(), host, sizeof(double) * s->g.vEst.size());
+  if (s->structureBuilt) return uploadEstimates(s);
+  return G2OCU_OK;
+}
+int g2ocu_get_estimates(g2ocu_solver* s, double* host) {
+  if (!s || !host) return G2OCU_E_INVALID;
+  if (!s->hasGraph) return fail(s, G2OCU_E_INVALID, "no graph set");
+  if (s->structureBuilt) { int rc = downloadEstimates(s); if (rc) return rc; }
+  std::memcpy(host, s->g.vEst.data(), sizeof(double) * s->g.vEst.size());
+  return G2OCU_OK;
+}
+
+static int64_t copyOutI32(const std::vector<int32_t>& v, int32_t* out, int64_t cap) { if (out) std::memcpy(out, v.data(), sizeof(int32_t) * (size_t)std::min<int64_t>(cap, (int64_t)v.size())); return (int64_t)v.size(); }
+
+int64_t g2ocu_get_i32(g2ocu_solver* s, const char* name, int32_t* out, int64_t cap) {
+  if (!s || !name) return G2OCU_E_INVALID;
+  if (!s->optInitialized) return fail(s, G2OCU_E_INVALID, "initializeOptimization has not been called");
+  const std::string n(name); const Structure& st = s->st;
+  if (n == "hessian_index") return copyOutI32(st.hessianIndex, out, cap);
+  if (n == "active_vertices") return copyOutI32(st.activeVertices, out, cap);
+  if (n == "active_edges") return copyOutI32(st.activeEdges, out, cap);
+  if (n == "index_mapping") return copyOutI32(st.ivMap, out, cap);
+  if (st.classOf.empty()) return fail(s, G2OCU_E_INVALID, "buildStructure has not been called");
+  if (n == "dims") return copyOutI32({st.numPoses, st.numLandmarks, st.sizePoses, st.sizeLandmarks}, out, cap);
+  if (n == "pose_block_indices") return copyOutI32(st.poseBlockIndices, out, cap);
+  if (n == "landmark_block_indices") return copyOutI32(st.landmarkBlockIndices, out, cap);
+  if (n == "hpp_colptr") return copyOutI32(st.hppColPtr, out, cap);
+  if (n == "hpp_rowidx") return copyOutI32(st.hppRowIdx, out, cap);
+  if (n == "hpl_colptr") return copyOutI32(st.hplColPtr, out, cap);
+  if (n == "hpl_rowidx") return copyOutI32(st.hplRowIdx, out, cap);
+  if (n == "hschur_colptr") return copyOutI32(st.sColPtr, out, cap);
+  if (n == "hschur_rowidx") return copyOutI32(st.sRowIdx, out, cap);
+  if (n == "hschur_t_colptr") return copyOutI32(st.sRowPtr, out, cap);
+  if (n == "hschur_t_rowidx") return copyOutI32(st.sColIdx, out, cap);
+  if (n == "edge_targets") return copyOutI32(st.edgeTargets, out, cap);
+  return fail(s, G2OCU_E_INVALID, "unknown int32 array " + n);
+}
+
+static int64_t downloadF64(g2ocu_solver* s, const double* dev, size_t count, double* out, int64_t cap) {
+  if (out && count) {
+    const size_t m = (size_t)std::min<int64_t>(cap, (int64_t)count);
+    if (cudaMemcpyAsync(out, dev, m * sizeof(double), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess || cudaStreamSynchronize(s->stream) != cudaSuccess)
+      return fail(s, G2OCU_E_CUDA, "device to host copy failed");
+    resolveEvents(s);
+  }
+  return (int64_t)count;
+}
+// block values in the reference's CCS order (block index permutation ccsToCsr), each block P x Q column-major
+static int64_t downloadBlocks(g2ocu_solver* s, const double* dev, const std::vector<int32_t>& ccsToCsr, int bs, double lambdaDiag, const std::vector<int32_t>* diagCsr, double* out, int64_t cap) {
+  const size_t count = ccsToCsr.size() * (size_t)bs;
+  if (!out) return (int64_t)count;
+  std::vector<double> tmp(count);
+  if (count && (cudaMemcpyAsync(tmp.data(), dev, count * sizeof(double), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess || cudaStreamSynchronize(s->stream) != cudaSuccess))
+    return fail(s, G2OCU_E_CUDA, "device to host copy failed");
+  resolveEvents(s);
+  if (lambdaDiag != 0.0 && diagCsr) { int P = (int)std::lround(std::sqrt((double)bs)); for (int32_t k : *diagCsr) for (int q = 0; q < P; ++q) tmp[(size_t)k * bs + q * (P + 1)] += lambdaDiag; }
+  for (size_t k = 0; k < ccsToCsr.size(); ++k) {
+    if ((int64_t)((k + 1) * bs) > cap) break;
+    std::memcpy(out + k * bs, &tmp[(size_t)ccsToCsr[k] * bs], sizeof(double) * bs);
+  }
+  return (int64_t)count;
+}
+
+int64_t g2ocu_get_f64(g2ocu_solver* s, const char* name, double* out, int64_t cap) {
+  int rc = requireBuilt(s); if (rc) return rc;
+  const std::string n(name ? name : ""); const Structure& st = s->st; const int P = st.P, L = st.L;
+  if (n == "x") return downloadF64(s, s->x.p, s->x.n, out, cap);
+  if (n == "b") return downloadF64(s, s->b.p, s->b.n, out, cap);
+  if (n == "bschur") return downloadF64(s, s->bschur.p, s->bschur.n, out, cap);
+  if (n == "hpp_values") return downloadBlocks(s, s->Hpp.p, st.hppCcsToCsr, P * P, s->lambda, &st.hppDiag, out, cap);
+  if (n == "hschur_values") return downloadBlocks(s, s->S.p, st.sCcsToCsr, P * P, 0.0, nullptr, out, cap);
+  if (n == "hpl_values") return downloadF64(s, s->Hpl.p, s->Hpl.n, out, cap);
+  if (n == "hll_values") {
+    const int64_t cnt = downloadF64(s, s->Hll.p, s->Hll.n, out, cap);
+    if (out && s->lambda != 0.0) for (int64_t i = 0; i < st.numLandmarks && (i + 1) * L * L <= cap; ++i) for (int q = 0; q < L; ++q) out[i * L * L + q * (L + 1)] += s->lambda;
+    return cnt;
+  }
+  if (n == "dinv_values") return downloadF64(s, s->Dinv.p, s->Dinv.n, out, cap);
+  if (n == "errors" || n == "jacobians") {
+    const bool jac = n == "jacobians";
+    std::vector<int64_t> off(st.activeEdges.size() + 1, 0);
+    for (size_t k = 0; k < st.activeEdges.size(); ++k) {
+      const int e = st.activeEdges[k], t = s->g.eType[e], E = edgeDim(t);
+      off[k + 1] = off[k] + (jac ? E * (vertexDim(edgeVertexType(t, 0)) + vertexDim(edgeVertexType(t, 1))) : E);
+    }
+    if (!out) return off.back();
+    if (s->off64.upload(off, s->stream) != cudaSuccess || s->dbg.alloc((size_t)off.back()) != cudaSuccess) return fail(s, G2OCU_E_CUDA, "allocation failed");
+    if (jac) { for (auto* es : s->sets) launchJacobianDump(es->dev, s->sys, s->dbg.p, s->off64.p, s->stream, &s->launches); }
+    else { rc = computeErrors(s, s->dbg.p, s->off64.p); if (rc) return rc; rc = finishErrors(s); if (rc) return rc; }
+    return downloadF64(s, s->dbg.p, (size_t)off.back(), out, cap);
+  }
+  if (n == "estimates") { if (out && cap >= (int64_t)s->g.vEst.size()) { rc = g2ocu_get_estimates(s, out); if (rc) return rc; } return (int64_t)s->g.vEst.size(); }
+  if (n == "lambda") { if (out && cap >= 1) out[0] = s->currentLambda; return 1; }
+  return fail(s, G2OCU_E_INVALID, "unknown double array " + n);
+}
+
+int64_t g2ocu_launch_count(const g2ocu_solver* s) { return s ? s->launches : 0; }
+int g2ocu_phase_time(g2ocu_solver* s, const char* phase, double* seconds, int64_t* launches) {
+  if (!s || !phase) return G2OCU_E_INVALID;
+  auto it = s->phases.find(phase);
+  if (seconds) *seconds = it == s->phases.end() ? 0.0 : it->second.seconds;
+  if (launches) *launches = it == s->phases.end() ? 0 : it->second.launches;
+  return G2OCU_OK;
+}
+int g2ocu_reset_counters(g2ocu_solver* s) { if (!s) return G2OCU_E_INVALID; s->phases.clear(); s->launches = 0; return G2OCU_OK; }
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// Launch wrappers for the sm_100a kernels (definitions in kernels_build.cu / kernels_linear.cu).
+// Plain C++ signatures; everything runs on the stream passed in.  All data FP64, indices int32.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace g2ocu {
+
+// Device view of one homogeneous edge set (host_structure.hpp: EdgeSet), arrays in kernel order.
+struct EdgeSetDev {
+  int etype = 0, n = 0;
+  int poseLandmark = 0;                  // 1: (pose, landmark) edge set, sorted by landmark slot
+  const int32_t* slot0 = nullptr;        // class slot of vertices()[0]
+  const int32_t* slot1 = nullptr;
+  const int32_t* block = nullptr;        // off-diagonal target block (Hpl index / Hpp-CSR index), -1 none
+  const uint8_t* transposed = nullptr;   // pose-pose sets: write the block transposed
+  const int32_t* pos = nullptr;          // position in the active edge list
+  const double* meas = nullptr;          // n x M
+  const double* info = nullptr;          // E x E (uniform) or n x E x E
+  int infoMode = 0;                      // 0 identity, 1 uniform, 2 per edge
+  const int32_t* kernelKind = nullptr;   // per edge (kernelMode 2)
+  const double* kernelDelta = nullptr;
+  int kernelMode = 0;                    // 0 none, 1 uniform, 2 per edge
+  int kKind = 0; double kDelta = 1.0;
+  const double* prm = nullptr;           // NP (uniform) or n x NP
+  int prmMode = 0;                       // 0 none, 1 uniform, 2 per edge
+  // pose-sorted view (pose-landmark sets)
+  const int32_t* byPose = nullptr; int nByPose = 0;
+  const int32_t* chunkPose = nullptr; const int32_t* chunkBegin = nullptr; const int32_t* chunkEnd = nullptr; int nChunks = 0;
+  const int32_t* poseChunkPtr = nullptr;
+  double* partial = nullptr;             // nChunks x (P(P+1)/2 + P)
+};
+
+struct SystemDev {
+  int numPoses = 0, numLandmarks = 0, numPoseSlots = 0, numLmSlots = 0, P = 0, L = 0;
+  double* poseEst = nullptr; double* lmEst = nullptr;    // slots x S
+  double* Hpp = nullptr;        // nnzHpp x P x P (CSR-upper order), diagonal blocks full symmetric
+  const int32_t* hppDiag = nullptr;
+  double* Hll = nullptr;        // numLandmarks x L x L
+  double* Hpl = nullptr;        // nnzHpl x P x L (column-major blocks, CCS-by-landmark order)
+  double* b = nullptr;          // sizePoses + sizeLandmarks
+  int hplShared = 0, hppShared = 0;
+};
+
+// ---- build / error kernels (kernels_build.cu) ----
+// chi2 partial sums: out2[0] += sum rho0 (robust), out2[1] += sum chi2 (plain); errOut (optional) in active-edge order
+void launchErrors(const EdgeSetDev& s, const SystemDev& sys, double* scratch, double* out2, double* errOut, const int64_t* errOff, cudaStream_t st, int64_t* launches);
+void launchBuild(const EdgeSetDev& s, const SystemDev& sys, cudaStream_t st, int64_t* launches);
+void launchJacobianDump(const EdgeSetDev& s, const SystemDev& sys, double* jacOut, const int64_t* jacOff, cudaStream_t st, int64_t* launches);
+void launchUpdate(int vtype, double* est, double* backupOrNull, int* counters, const double* x, int nFree, cudaStream_t st, int64_t* launches);
+int errorScratchDoubles(int n);
+
+// ---- linear algebra kernels (kernels_linear.cu) ----
+struct SchurDev {
+  int numPoses = 0, numLandmarks = 0, P = 0, L = 0;
+  const int32_t* hplColPtr = nullptr; const int32_t* hplRowIdx = nullptr;
+  const int32_t* sRowPtr = nullptr; const int32_t* sColIdx = nullptr; const int32_t* sDiag = nullptr;
+  const int32_t* hppToS = nullptr; int nnzHpp = 0; int nnzS = 0;
+  const int64_t* pairPtr = nullptr; int32_t* pairSlot = nullptr;          // per landmark pair -> S block index
+  const int32_t* itemLm = nullptr; const int32_t* itemBegin = nullptr; const int32_t* itemEnd = nullptr; int nItems = 0;
+  double* S = nullptr; double* Dinv = nullptr; double* bschur = nullptr;
+};
+void launchPairSlots(const SchurDev& d, cudaStream_t st, int64_t* launches);
+void launchSchur(const SchurDev& d, const SystemDev& sys, double lambda, cudaStream_t st, int64_t* launches);
+void launchBacksub(const SchurDev& d, const SystemDev& sys, const double* xp, double* xl, cudaStream_t st, int64_t* launches);
+
+struct PcgDev {
+  int n = 0, nb = 0, P = 0;                // scalar size, block rows, block size
+  const int32_t* rowPtr = nullptr; const int32_t* colIdx = nullptr; const int32_t* diag = nullptr; int nnz = 0;
+  const double* A = nullptr;               // upper blocks, CSR order
+  double lambda = 0.0;                     // added to the diagonal on the fly (non-Schur mode)
+  double* Minv = nullptr;                  // nb x P x P
+  double *r = nullptr, *d = nullptr, *q = nullptr, *s = nullptr, *x = nullptr;
+  double* scal = nullptr;                  // device scalars: [0] dn, [1] d.q, [2] dn_new, [3] alpha, [4] beta, [5] d0, [6] converged flag, [7] iterations
+  double* partial = nullptr; int nPartial = 0;          // one per CTA of the block-row kernels: ceil(nb/128)
+  double* partialDq = nullptr; int nPartialDq = 0;      // one per CTA of the dot kernel
+  const int32_t* itemRow = nullptr; const int32_t* itemBegin = nullptr; const int32_t* itemEnd = nullptr; int nItems = 0;   // SpMV work items (row, block range)
+};
+void launchBlockInverse(const PcgDev& p, cudaStream_t st, int64_t* launches);
+void launchPcgInit(const PcgDev& p, const double* b, double tolerance, double residual, int absoluteTolerance, cudaStream_t st, int64_t* launches);   // x=0, r=b, d=M^-1 r, dn=r.d, d0
+void launchPcgTail(const PcgDev& p, cudaStream_t st, int64_t* launches);   // after q = A d: dot, x/r/s update, d update, commit (no-ops once converged)
+void launchSpmv(const PcgDev& p, const double* src, double* dst, cudaStream_t st, int64_t* launches);   // dst = (A + lambda I) src, symmetric upper
+
+void launchMaxDiag(const SystemDev& sys, double* scratch, double* out, cudaStream_t st, int64_t* launches);
+void launchScale(const double* x, const double* b, int64_t n, double lambda, double* scratch, double* out, cudaStream_t st, int64_t* launches);
+
+// dense FP64 Cholesky path (kernels_dense.cu)
+void launchDenseAssemble(const PcgDev& p, double* H, cudaStream_t st, int64_t* launches);      // upper blocks -> dense lower-filled n x n
+int launchDenseCholeskySolve(double* H, int n, const double* b, double* x, int* info, cudaStream_t st, int64_t* launches);
+
+}  // namespace g2ocu

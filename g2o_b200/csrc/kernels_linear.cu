@@ -1,0 +1,458 @@
+// sm_100a kernels for the linear-algebra half of the LM inner loop:
+//   schur_*            BlockSolver::solve Schur part: Dinv = (Hll+λI)^-1, S = Hpp+λI - Σ_l B Dinv B^T, b_s      (block_solver.hpp:333-405)
+//   backsub_kernel     x_l = Dinv (b_l - Hpl^T x_p)                                                            (block_solver.hpp:420-444)
+//   block_inverse      block-Jacobi preconditioner M^-1 = diag-block inverses                                    (linear_solver_pcg.hpp:93-95)
+//   spmv_sym_kernel    q = A d using the upper blocks twice                                                      (linear_solver_pcg.hpp:179-197)
+//   pcg_* kernels      the CG recurrences with device-resident scalars                                           (linear_solver_pcg.hpp:112-150)
+//   maxdiag / scale    computeLambdaInit / computeScale reductions                                               (optimization_algorithm_levenberg.cpp:152-184)
+// λ is never written into the stored diagonals: every consumer adds it on the fly, so setLambda/restoreDiagonal
+// (block_solver.hpp:525-565) cost nothing and need no backup copies.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "kernels.hpp"
+
+namespace g2ocu {
+
+#define G2D __device__ __forceinline__
+
+G2D double warpSumL(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int NT> G2D double blockSumL(double v, double* sm) {
+  v = warpSumL(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[wid] = v;
+  __syncthreads();
+  double r = 0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NT / 32; ++k) r += sm[k];
+  }
+  return r;
+}
+// every thread of the CTA gets the sum of partial[0..n) (fixed order => identical in all CTAs)
+template <int NT> G2D double sumPartialsAll(const double* partial, int n, double* sm) {
+  double v = 0;
+  for (int k = threadIdx.x; k < n; k += NT) v += partial[k];
+  v = warpSumL(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[wid] = v;
+  __syncthreads();
+  double r = 0;
+#pragma unroll
+  for (int k = 0; k < NT / 32; ++k) r += sm[k];
+  __syncthreads();
+  return r;
+}
+
+// closed-form inverses, as Eigen does for fixed sizes <= 4 (block_solver.hpp:350 Hll^-1)
+template <int L> G2D void invSmall(const double* A, double* X);
+template <> G2D void invSmall<2>(const double* A, double* X) {
+  const double id = 1.0 / (A[0] * A[3] - A[2] * A[1]);
+  X[0] = A[3] * id; X[1] = -A[1] * id; X[2] = -A[2] * id; X[3] = A[0] * id;
+}
+template <> G2D void invSmall<3>(const double* A, double* X) {
+  const double c00 = A[4] * A[8] - A[7] * A[5], c10 = A[7] * A[2] - A[1] * A[8], c20 = A[1] * A[5] - A[4] * A[2];
+  const double id = 1.0 / (c00 * A[0] + c10 * A[3] + c20 * A[6]);
+  X[0] = c00 * id; X[1] = c10 * id; X[2] = c20 * id;
+  X[3] = (A[6] * A[5] - A[3] * A[8]) * id; X[4] = (A[0] * A[8] - A[6] * A[2]) * id; X[5] = (A[3] * A[2] - A[0] * A[5]) * id;
+  X[6] = (A[3] * A[7] - A[6] * A[4]) * id; X[7] = (A[6] * A[1] - A[0] * A[7]) * id; X[8] = (A[0] * A[4] - A[3] * A[1]) * id;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one-time: S block index of every (landmark, i<=j) pair, by binary search in the CSR row of camera i
+__global__ void __launch_bounds__(128) pair_slot_kernel(SchurDev d) {
+  const int item = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (item >= d.nItems) return;
+  const int lm = d.itemLm[item], i0 = d.itemBegin[item], i1 = d.itemEnd[item];
+  const int base = d.hplColPtr[lm], k = d.hplColPtr[lm + 1] - base;
+  const int64_t pb = d.pairPtr[lm];
+  for (int i = i0; i < i1; ++i) {
+    const int ci = d.hplRowIdx[base + i];
+    const int64_t off = pb + (int64_t)i * k - (int64_t)i * (i - 1) / 2 - i;
+    const int lo0 = d.sRowPtr[ci], hi0 = d.sRowPtr[ci + 1];
+    for (int j = i + lane; j < k; j += 32) {
+      const int cj = d.hplRowIdx[base + j];
+      int lo = lo0, hi = hi0;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (d.sColIdx[mid] < cj) lo = mid + 1; else hi = mid; }
+      d.pairSlot[off + j] = lo;
+    }
+  }
+}
+
+template <int P> __global__ void schur_init_kernel(SchurDev d, const double* Hpp, const double* b, double lambda) {
+  constexpr int PP = P * P;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < (int64_t)d.nnzHpp * PP) {
+    const int k = (int)(t / PP), el = (int)(t - (int64_t)k * PP);
+    d.S[(size_t)d.hppToS[k] * PP + el] = Hpp[t];
+  }
+  if (t < (int64_t)d.numPoses * P) d.bschur[t] = b[t];
+}
+template <int P> __global__ void add_lambda_diag_kernel(double* A, const int32_t* diag, int nb, double lambda) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nb * P) return;
+  const int i = t / P, k = t - i * P;
+  A[(size_t)diag[i] * P * P + k * (P + 1)] += lambda;
+}
+
+// warp per work item (landmark, rows [i0,i1) of its observation list)
+template <int P, int L> __global__ void __launch_bounds__(128) schur_landmark_kernel(SchurDev d, const double* __restrict__ Hll, const double* __restrict__ Hpl,
+                                                                                     const double* __restrict__ b, double lambda) {
+  constexpr int PP = P * P, PLn = P * L, LL = L * L;
+  __shared__ double sBD[4][PLn];
+  __shared__ double sDinv[4][LL + L];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * 4 + w;
+  if (item >= d.nItems) return;
+  const int lm = d.itemLm[item], i0 = d.itemBegin[item], i1 = d.itemEnd[item];
+  {
+    double H[LL], X[LL], bl[L];
+#pragma unroll
+    for (int q = 0; q < LL; ++q) H[q] = Hll[(size_t)lm * LL + q];
+#pragma unroll
+    for (int q = 0; q < L; ++q) { H[q * (L + 1)] += lambda; bl[q] = b[(size_t)d.numPoses * P + (size_t)lm * L + q]; }
+    invSmall<L>(H, X);
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < LL; ++q) sDinv[w][q] = X[q];
+#pragma unroll
+      for (int r = 0; r < L; ++r) { double v = 0;
+#pragma unroll
+        for (int c = 0; c < L; ++c) v += X[r + L * c] * bl[c];
+        sDinv[w][LL + r] = v; }
+      if (i0 == 0) {
+#pragma unroll
+        for (int q = 0; q < LL; ++q) d.Dinv[(size_t)lm * LL + q] = X[q];
+      }
+    }
+  }
+  __syncwarp();
+  const int base = d.hplColPtr[lm], k = d.hplColPtr[lm + 1] - base;
+  const int64_t pb = d.pairPtr[lm];
+  for (int i = i0; i < i1; ++i) {
+    const int ci = d.hplRowIdx[base + i];
+    const double* Bi = Hpl + (size_t)(base + i) * PLn;
+    __syncwarp();
+    if (lane < PLn) {
+      const int r = lane % P, bc = lane / P;
+      double v = 0;
+#pragma unroll
+      for (int a = 0; a < L; ++a) v += Bi[r + P * a] * sDinv[w][a + L * bc];
+      sBD[w][lane] = v;
+    }
+    if (lane < P) {
+      double v = 0;
+#pragma unroll
+      for (int a = 0; a < L; ++a) v += Bi[lane + P * a] * sDinv[w][LL + a];
+      atomicAdd(d.bschur + (size_t)ci * P + lane, -v);
+    }
+    __syncwarp();
+    const int64_t off = pb + (int64_t)i * k - (int64_t)i * (i - 1) / 2 - i;
+    const int nw = (k - i) * PP;
+    for (int t = lane; t < nw; t += 32) {
+      const int jj = t / PP, el = t - jj * PP;
+      const int j = i + jj, r = el % P, c = el / P;
+      const double* Bj = Hpl + (size_t)(base + j) * PLn;
+      double v = 0;
+#pragma unroll
+      for (int a = 0; a < L; ++a) v += sBD[w][r + P * a] * Bj[c + P * a];
+      const int slot = d.pairSlot[off + j];
+      atomicAdd(d.S + (size_t)slot * PP + el, -v);
+    }
+  }
+}
+
+// x_l = Dinv (b_l - Σ_i B_i^T x_p[c_i])
+template <int P, int L> __global__ void backsub_kernel(SchurDev d, const double* __restrict__ Hpl, const double* __restrict__ b, const double* __restrict__ xp, double* __restrict__ xl) {
+  constexpr int PLn = P * L, LL = L * L;
+  const int lm = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lm >= d.numLandmarks) return;
+  double c[L];
+#pragma unroll
+  for (int q = 0; q < L; ++q) c[q] = b[(size_t)d.numPoses * P + (size_t)lm * L + q];
+  const int base = d.hplColPtr[lm], end = d.hplColPtr[lm + 1];
+  for (int k = base; k < end; ++k) {
+    const int ci = d.hplRowIdx[k];
+    const double* B = Hpl + (size_t)k * PLn;
+    double x[P];
+#pragma unroll
+    for (int r = 0; r < P; ++r) x[r] = xp[(size_t)ci * P + r];
+#pragma unroll
+    for (int q = 0; q < L; ++q) { double v = 0;
+#pragma unroll
+      for (int r = 0; r < P; ++r) v += B[r + P * q] * x[r];
+      c[q] -= v; }
+  }
+#pragma unroll
+  for (int r = 0; r < L; ++r) { double v = 0;
+#pragma unroll
+    for (int q = 0; q < L; ++q) v += d.Dinv[(size_t)lm * LL + r + L * q] * c[q];
+    xl[(size_t)lm * L + r] = v; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-Jacobi preconditioner: Gauss-Jordan with partial pivoting per diagonal block (Eigen inverse() is LU based for P > 4)
+template <int P> __global__ void block_inverse_kernel(PcgDev p) {
+  constexpr int PP = P * P;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.nb) return;
+  double A[PP], X[PP];
+  const double* src = p.A + (size_t)p.diag[i] * PP;
+#pragma unroll
+  for (int q = 0; q < PP; ++q) { A[q] = src[q]; X[q] = 0; }
+#pragma unroll
+  for (int q = 0; q < P; ++q) { A[q * (P + 1)] += p.lambda; X[q * (P + 1)] = 1; }
+  for (int k = 0; k < P; ++k) {
+    int piv = k; double best = fabs(A[k + P * k]);
+    for (int r = k + 1; r < P; ++r) { const double v = fabs(A[r + P * k]); if (v > best) { best = v; piv = r; } }
+    if (piv != k) for (int c = 0; c < P; ++c) { double t = A[k + P * c]; A[k + P * c] = A[piv + P * c]; A[piv + P * c] = t; t = X[k + P * c]; X[k + P * c] = X[piv + P * c]; X[piv + P * c] = t; }
+    const double ip = 1.0 / A[k + P * k];
+    for (int c = 0; c < P; ++c) { A[k + P * c] *= ip; X[k + P * c] *= ip; }
+    for (int r = 0; r < P; ++r) {
+      if (r == k) continue;
+      const double f = A[r + P * k];
+      for (int c = 0; c < P; ++c) { A[r + P * c] -= f * A[k + P * c]; X[r + P * c] -= f * X[k + P * c]; }
+    }
+  }
+  double* dst = p.Minv + (size_t)i * PP;
+  for (int q = 0; q < PP; ++q) dst[q] = X[q];
+}
+
+// symmetric block SpMV over work items (row, block range); q must be zero on entry.
+// Each warp stages G = 32/P consecutive blocks in shared memory with coalesced loads, then lane (g, r) forms
+// row r of A_ij d_j (kept in a register, one RED per item) and row r of A_ij^T d_i (RED into q_j).
+template <int P> __global__ void __launch_bounds__(128) spmv_sym_kernel(PcgDev p, const int32_t* __restrict__ itemRow, const int32_t* __restrict__ itemBegin,
+                                                                         const int32_t* __restrict__ itemEnd, int nItems, const double* __restrict__ src, double* __restrict__ dst) {
+  constexpr int PP = P * P, G = 32 / P;
+  __shared__ double sA[4][G * PP];
+  if (p.scal && p.scal[6] != 0.0) return;     // PCG already converged: remaining launches are no-ops
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * 4 + w;
+  if (item >= nItems) return;
+  const int row = itemRow[item], kb = itemBegin[item], ke = itemEnd[item];
+  const int g = lane / P, r = lane - g * P;
+  const bool act = g < G;
+  double di[P];
+#pragma unroll
+  for (int c = 0; c < P; ++c) di[c] = src[(size_t)row * P + c];
+  double yi = 0;
+  for (int k0 = kb; k0 < ke; k0 += G) {
+    const int nblk = min(G, ke - k0);
+    const double* Ab = p.A + (size_t)k0 * PP;
+    __syncwarp();
+    for (int t = lane; t < nblk * PP; t += 32) sA[w][t] = Ab[t];
+    __syncwarp();
+    if (act && g < nblk) {
+      const int j = p.colIdx[k0 + g];
+      const double* a = &sA[w][g * PP];
+      const double* dj = src + (size_t)j * P;
+      double y = 0, z = 0;
+#pragma unroll
+      for (int c = 0; c < P; ++c) { y += a[r + P * c] * dj[c]; z += a[c + P * r] * di[c]; }
+      if (j == row) y += p.lambda * di[r];
+      else atomicAdd(dst + (size_t)j * P + r, z);
+      yi += y;
+    }
+  }
+  if (act) atomicAdd(dst + (size_t)row * P + r, yi);
+}
+
+// d.q partial sums
+__global__ void __launch_bounds__(256) dot_partial_kernel(const double* scal, const double* a, const double* b, int n, double* partial) {
+  __shared__ double sm[8];
+  if (scal && scal[6] != 0.0) return;
+  double v = 0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) v += a[i] * b[i];
+  const double r = blockSumL<256>(v, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
+// x = 0, r = b, d = M^-1 r, partial r.d   (thread per block row)
+template <int P> __global__ void __launch_bounds__(128) pcg_init_kernel(PcgDev p, const double* __restrict__ b) {
+  constexpr int PP = P * P;
+  __shared__ double sm[4];
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  double acc = 0;
+  if (i < p.nb) {
+    double rr[P];
+#pragma unroll
+    for (int c = 0; c < P; ++c) { rr[c] = b[(size_t)i * P + c]; p.r[(size_t)i * P + c] = rr[c]; p.x[(size_t)i * P + c] = 0; }
+    const double* M = p.Minv + (size_t)i * PP;
+#pragma unroll
+    for (int r = 0; r < P; ++r) { double v = 0;
+#pragma unroll
+      for (int c = 0; c < P; ++c) v += M[r + P * c] * rr[c];
+      p.d[(size_t)i * P + r] = v; acc += rr[r] * v; }
+  }
+  const double s = blockSumL<128>(acc, sm);
+  if (threadIdx.x == 0) p.partial[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) pcg_init_finish_kernel(PcgDev p, double tolerance, double residual, int absoluteTolerance) {
+  __shared__ double sm[8];
+  const double dn = sumPartialsAll<256>(p.partial, p.nPartial, sm);
+  if (threadIdx.x == 0) {
+    double d0 = tolerance * dn;
+    if (absoluteTolerance && residual > 0.0 && residual > d0) d0 = residual;
+    p.scal[0] = dn; p.scal[2] = dn; p.scal[5] = d0; p.scal[6] = (dn <= d0) ? 1.0 : 0.0; p.scal[7] = 0.0;
+  }
+}
+// alpha = dn / (d.q);  x += alpha d;  r -= alpha q;  s = M^-1 r;  partial r.s
+template <int P> __global__ void __launch_bounds__(128) pcg_update1_kernel(PcgDev p, const double* dqPartial, int nDq) {
+  constexpr int PP = P * P;
+  __shared__ double sm[4];
+  if (p.scal[6] != 0.0) return;
+  const double dq = sumPartialsAll<128>(dqPartial, nDq, sm);
+  const double alpha = p.scal[0] / dq;
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  double acc = 0;
+  if (i < p.nb) {
+    double rr[P];
+#pragma unroll
+    for (int c = 0; c < P; ++c) {
+      const size_t o = (size_t)i * P + c;
+      p.x[o] += alpha * p.d[o];
+      rr[c] = p.r[o] - alpha * p.q[o];
+      p.r[o] = rr[c];
+    }
+    const double* M = p.Minv + (size_t)i * PP;
+#pragma unroll
+    for (int r = 0; r < P; ++r) { double v = 0;
+#pragma unroll
+      for (int c = 0; c < P; ++c) v += M[r + P * c] * rr[c];
+      p.s[(size_t)i * P + r] = v; acc += rr[r] * v; }
+  }
+  const double s = blockSumL<128>(acc, sm);
+  if (threadIdx.x == 0) p.partial[blockIdx.x] = s;
+}
+// beta = dn_new / dn;  d = s + beta d;  commit scalars (block 0)
+__global__ void __launch_bounds__(256) pcg_update2_kernel(PcgDev p) {
+  __shared__ double sm[8];
+  if (p.scal[6] != 0.0) return;
+  const double dnNew = sumPartialsAll<256>(p.partial, p.nPartial, sm);
+  const double beta = dnNew / p.scal[0];
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < p.n; i += gridDim.x * 256) p.d[i] = p.s[i] + beta * p.d[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.scal[2] = dnNew;
+}
+// single thread: dn <- dn_new, iteration count, convergence flag (runs between iterations so that no CTA races on scal[0])
+__global__ void pcg_commit_kernel(PcgDev p) {
+  if (p.scal[6] != 0.0) return;
+  const double dn = p.scal[2];
+  p.scal[0] = dn; p.scal[7] += 1.0;
+  if (dn <= p.scal[5]) p.scal[6] = 1.0;
+}
+
+// computeLambdaInit: max |H_vv(j,j)| over pose and landmark diagonal blocks (levenberg.cpp:152-175)
+__global__ void __launch_bounds__(1024) maxdiag_kernel(SystemDev sys, double* out) {
+  __shared__ double sm[32];
+  double m = 0;
+  const int P = sys.P, L = sys.L;
+  for (int t = threadIdx.x; t < sys.numPoses * P; t += 1024) { const int i = t / P, k = t - i * P; m = fmax(m, fabs(sys.Hpp[(size_t)sys.hppDiag[i] * P * P + k * (P + 1)])); }
+  for (int64_t t = threadIdx.x; t < (int64_t)sys.numLandmarks * L; t += 1024) { const int64_t i = t / L; const int k = (int)(t - i * L); m = fmax(m, fabs(sys.Hll[(size_t)i * L * L + k * (L + 1)])); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) { double r = 0; for (int k = 0; k < 32; ++k) r = fmax(r, sm[k]); out[0] = r; }
+}
+// computeScale: sum_j x_j (lambda x_j + b_j) (levenberg.cpp:177-184)
+__global__ void __launch_bounds__(256) scale_partial_kernel(const double* x, const double* b, int64_t n, double lambda, double* partial) {
+  __shared__ double sm[8];
+  double v = 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) v += x[i] * (lambda * x[i] + b[i]);
+  const double r = blockSumL<256>(v, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+__global__ void __launch_bounds__(256) final_sum_kernel(const double* partial, int n, double* out) {
+  __shared__ double sm[8];
+  const double r = sumPartialsAll<256>(partial, n, sm);
+  if (threadIdx.x == 0) out[0] = r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch wrappers
+// ------------------------------------------------------------------------------------------------
+void launchPairSlots(const SchurDev& d, cudaStream_t st, int64_t* launches) {
+  if (d.nItems == 0) return;
+  pair_slot_kernel<<<(d.nItems + 3) / 4, 128, 0, st>>>(d);
+  *launches += 1;
+}
+
+template <int P, int L> static void schurPL(const SchurDev& d, const SystemDev& sys, double lambda, cudaStream_t st, int64_t* launches) {
+  constexpr int PP = P * P;
+  cudaMemsetAsync(d.S, 0, sizeof(double) * (size_t)d.nnzS * PP, st);
+  const int64_t tot = max((int64_t)d.nnzHpp * PP, (int64_t)d.numPoses * P);
+  schur_init_kernel<P><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d, sys.Hpp, sys.b, lambda);
+  add_lambda_diag_kernel<P><<<(d.numPoses * P + 255) / 256, 256, 0, st>>>(d.S, d.sDiag, d.numPoses, lambda);
+  *launches += 3;
+  if (d.nItems > 0) {
+    schur_landmark_kernel<P, L><<<(d.nItems + 3) / 4, 128, 0, st>>>(d, sys.Hll, sys.Hpl, sys.b, lambda);
+    *launches += 1;
+  }
+}
+void launchSchur(const SchurDev& d, const SystemDev& sys, double lambda, cudaStream_t st, int64_t* launches) {
+  if (d.P == 9 && d.L == 3) schurPL<9, 3>(d, sys, lambda, st, launches);
+  else if (d.P == 6 && d.L == 3) schurPL<6, 3>(d, sys, lambda, st, launches);
+  else if (d.P == 3 && d.L == 2) schurPL<3, 2>(d, sys, lambda, st, launches);
+}
+void launchBacksub(const SchurDev& d, const SystemDev& sys, const double* xp, double* xl, cudaStream_t st, int64_t* launches) {
+  if (d.numLandmarks == 0) return;
+  const int nb = (d.numLandmarks + 127) / 128;
+  if (d.P == 9 && d.L == 3) backsub_kernel<9, 3><<<nb, 128, 0, st>>>(d, sys.Hpl, sys.b, xp, xl);
+  else if (d.P == 6 && d.L == 3) backsub_kernel<6, 3><<<nb, 128, 0, st>>>(d, sys.Hpl, sys.b, xp, xl);
+  else if (d.P == 3 && d.L == 2) backsub_kernel<3, 2><<<nb, 128, 0, st>>>(d, sys.Hpl, sys.b, xp, xl);
+  *launches += 1;
+}
+
+#define FOR_P(Pv, CALL) switch (Pv) { case 3: { CALL(3) break; } case 6: { CALL(6) break; } case 9: { CALL(9) break; } default: break; }
+
+void launchBlockInverse(const PcgDev& p, cudaStream_t st, int64_t* launches) {
+#define CALL(PV) block_inverse_kernel<PV><<<(p.nb + 63) / 64, 64, 0, st>>>(p);
+  FOR_P(p.P, CALL)
+#undef CALL
+  *launches += 1;
+}
+
+void launchSpmv(const PcgDev& p, const double* src, double* dst, cudaStream_t st, int64_t* launches) {
+  cudaMemsetAsync(dst, 0, sizeof(double) * (size_t)p.n, st);
+#define CALL(PV) spmv_sym_kernel<PV><<<(p.nItems + 3) / 4, 128, 0, st>>>(p, p.itemRow, p.itemBegin, p.itemEnd, p.nItems, src, dst);
+  FOR_P(p.P, CALL)
+#undef CALL
+  *launches += 2;
+}
+
+void launchPcgInit(const PcgDev& p, const double* b, double tolerance, double residual, int absoluteTolerance, cudaStream_t st, int64_t* launches) {
+#define CALL(PV) pcg_init_kernel<PV><<<p.nPartial, 128, 0, st>>>(p, b);
+  FOR_P(p.P, CALL)
+#undef CALL
+  pcg_init_finish_kernel<<<1, 256, 0, st>>>(p, tolerance, residual, absoluteTolerance);
+  *launches += 2;
+}
+
+void launchPcgTail(const PcgDev& p, cudaStream_t st, int64_t* launches) {
+  dot_partial_kernel<<<p.nPartialDq, 256, 0, st>>>(p.scal, p.d, p.q, p.n, p.partialDq);
+#define CALL(PV) pcg_update1_kernel<PV><<<p.nPartial, 128, 0, st>>>(p, p.partialDq, p.nPartialDq);
+  FOR_P(p.P, CALL)
+#undef CALL
+  pcg_update2_kernel<<<p.nPartialDq, 256, 0, st>>>(p);
+  pcg_commit_kernel<<<1, 1, 0, st>>>(p);
+  *launches += 4;
+}
+
+void launchMaxDiag(const SystemDev& sys, double*, double* out, cudaStream_t st, int64_t* launches) {
+  maxdiag_kernel<<<1, 1024, 0, st>>>(sys, out);
+  *launches += 1;
+}
+void launchScale(const double* x, const double* b, int64_t n, double lambda, double* scratch, double* out, cudaStream_t st, int64_t* launches) {
+  int64_t nb64 = (n + 255) / 256; const int nb = (int)(nb64 < 1184 ? nb64 : 1184);
+  scale_partial_kernel<<<nb, 256, 0, st>>>(x, b, n, lambda, scratch);
+  final_sum_kernel<<<1, 256, 0, st>>>(scratch, nb, out);
+  *launches += 2;
+}
+
+}  // namespace g2ocu

@@ -1,0 +1,207 @@
+/*
+ * g2ocu.h — C ABI of the B200-native g2o solver backend (libg2ocu.so).
+ *
+ * This is the drop-in boundary for the Levenberg-Marquardt / Gauss-Newton hot path of g2o
+ * (reference: B0Bftl/g2o, paths below are relative to the reference root).  Every entry point replaces one
+ * virtual of the reference's plugin interface; the g2o-side adapter (g2o_b200/host/g2o_solver_cuda.cpp and the
+ * binding sketch in INTEGRATION.md) forwards the virtual to the function named here.
+ *
+ *   reference interface                                                  entry point
+ *   ------------------------------------------------------------------   -------------------------------
+ *   SparseOptimizer::initializeOptimization   sparse_optimizer.cpp:208    g2ocu_initialize_optimization
+ *   OptimizationAlgorithmWithHessian::init    ..._with_hessian.cpp:48     g2ocu_init
+ *   Solver::buildStructure                    core/solver.h:64            g2ocu_build_structure
+ *   SparseOptimizer::computeActiveErrors      sparse_optimizer.cpp:63     g2ocu_compute_active_errors
+ *   SparseOptimizer::activeRobustChi2/Chi2    sparse_optimizer.cpp:92,102 g2ocu_active_robust_chi2 / g2ocu_active_chi2
+ *   Solver::buildSystem                       core/solver.h:81            g2ocu_build_system
+ *   Solver::setLambda / restoreDiagonal       core/solver.h:108,113       g2ocu_set_lambda / g2ocu_restore_diagonal
+ *   Solver::solve                             core/solver.h:86            g2ocu_solve
+ *   Solver::x / b / vectorSize                core/solver.h:94-103        g2ocu_get_f64("x"|"b") / g2ocu_vector_size
+ *   SparseOptimizer::update                   sparse_optimizer.cpp:441    g2ocu_update
+ *   SparseOptimizer::push/pop/discardTop      sparse_optimizer.cpp:624    g2ocu_push / g2ocu_pop / g2ocu_discard_top
+ *   OptimizationAlgorithm::solve(iteration)   optimization_algorithm.h:70 g2ocu_solver_iteration
+ *   SparseOptimizer::optimize                 sparse_optimizer.cpp:374    g2ocu_optimize
+ *   BlockSolverBase::multiplyHessian          core/block_solver.h:87-95   g2ocu_multiply_hessian
+ *   LinearSolver<M>::solve                    core/linear_solver.h:59     (inside g2ocu_solve; kind = g2ocu_config.linear_solver)
+ *
+ * Conventions: all functions return 0 on success and a negative G2OCU_E_* code on failure; the message is
+ * available from g2ocu_last_error().  No function aborts or throws across the boundary.  One handle = one
+ * optimizer = one CUDA stream; calls on one handle must be serialised by the caller (the reference is not
+ * thread-safe across calls either); different handles are independent.  All floating point is IEEE double
+ * (number_t = double, config.h.in:33-41).  There is NO CPU fallback: compute entry points fail with
+ * G2OCU_E_CUDA when no CUDA device is usable, and unsupported vertex/edge/kernel types are rejected at
+ * g2ocu_set_graph / g2ocu_init with G2OCU_E_UNSUPPORTED.
+ */
+#ifndef G2OCU_H
+#define G2OCU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G2OCU_VERSION 1
+
+/* status codes */
+#define G2OCU_OK 0
+#define G2OCU_E_INVALID (-1)      /* bad argument / call order                                   */
+#define G2OCU_E_UNSUPPORTED (-2)  /* type / configuration outside the supported set (rejected)     */
+#define G2OCU_E_CUDA (-3)         /* CUDA runtime error or no device                               */
+#define G2OCU_E_NUMERIC (-4)      /* linear solve failed (non-SPD system)                          */
+#define G2OCU_E_COMM (-5)         /* the user-supplied collective reported an error                */
+
+/* vertex types: estimate layout on the boundary */
+#define G2OCU_VERTEX_SE2 1         /* slam2d/vertex_se2.h        x y theta                         */
+#define G2OCU_VERTEX_POINT_XY 2    /* slam2d/vertex_point_xy.h   x y                               */
+#define G2OCU_VERTEX_SE3 3         /* slam3d/vertex_se3.h        Isometry3: R column-major(9), t(3) */
+#define G2OCU_VERTEX_SE3_EXPMAP 4  /* sba/types_six_dof_expmap.h:84  SE3Quat::toVector tx ty tz qx qy qz qw */
+#define G2OCU_VERTEX_POINT_XYZ 5   /* sba/types_sba.h:137        x y z                             */
+#define G2OCU_VERTEX_CAM_BAL 6     /* examples/bal/bal_example.cpp:65   rx ry rz tx ty tz f k1 k2  */
+#define G2OCU_VERTEX_POINT_BAL 7   /* examples/bal/bal_example.cpp:102  x y z                      */
+
+/* edge types (vertex order as in the reference class) */
+#define G2OCU_EDGE_SE2 1              /* slam2d/edge_se2.h            (SE2, SE2)          meas x y theta     */
+#define G2OCU_EDGE_SE2_POINT_XY 2     /* slam2d/edge_se2_pointxy.h    (SE2, PointXY)      meas x y           */
+#define G2OCU_EDGE_SE3 3              /* slam3d/edge_se3.h            (SE3, SE3)          meas Isometry3(12) */
+#define G2OCU_EDGE_SE3_EXPMAP 4       /* sba/types_six_dof_expmap.h:108 (Expmap, Expmap)  meas SE3Quat(7)    */
+#define G2OCU_EDGE_PROJECT_XYZ2UV 5   /* sba/types_six_dof_expmap.h:130 (PointXYZ, Expmap) meas u v; param f cx cy      */
+#define G2OCU_EDGE_SE3_PROJECT_XYZ 6  /* sba/types_six_dof_expmap.h:201 (PointXYZ, Expmap) meas u v; param fx fy cx cy */
+#define G2OCU_EDGE_BAL 7              /* examples/bal/bal_example.cpp:148 (CamBAL, PointBAL) meas u v      */
+
+/* robust kernels, core/robust_kernel_impl.cpp */
+#define G2OCU_KERNEL_NONE 0
+#define G2OCU_KERNEL_HUBER 1
+#define G2OCU_KERNEL_PSEUDO_HUBER 2
+#define G2OCU_KERNEL_CAUCHY 3
+#define G2OCU_KERNEL_GEMAN_MCCLURE 4
+#define G2OCU_KERNEL_WELSCH 5
+#define G2OCU_KERNEL_FAIR 6
+#define G2OCU_KERNEL_TUKEY 7
+#define G2OCU_KERNEL_SATURATED 8
+#define G2OCU_KERNEL_DCS 9
+
+/* algorithms (OptimizationAlgorithmLevenberg / GaussNewton) and linear solvers */
+#define G2OCU_ALGORITHM_GN 0
+#define G2OCU_ALGORITHM_LM 1
+#define G2OCU_LINEAR_PCG 0    /* solvers/pcg/linear_solver_pcg.hpp: block-Jacobi preconditioned CG           */
+#define G2OCU_LINEAR_DENSE 1  /* solvers/dense/linear_solver_dense.h semantics: dense FP64 Cholesky (small RCS) */
+
+/* SolverResult, core/optimization_algorithm.h:46 */
+#define G2OCU_RESULT_OK 1
+#define G2OCU_RESULT_TERMINATE 2
+#define G2OCU_RESULT_FAIL (-1)
+
+typedef struct g2ocu_solver g2ocu_solver;
+
+/* Graph as flat arrays.  Vertices in insertion order, edges in internalId order (optimizable_graph.cpp:267-292).
+ * Packed arrays are concatenated in vertex / edge order with the per-type strides documented above;
+ * information matrices are E x E column-major.  All arrays are copied by g2ocu_set_graph. */
+typedef struct g2ocu_graph {
+  int32_t n_vertices;
+  const int32_t* v_id;            /* g2o vertex id (unique)                                   */
+  const int32_t* v_type;          /* G2OCU_VERTEX_*                                           */
+  const uint8_t* v_fixed;         /* OptimizableGraph::Vertex::fixed()                        */
+  const uint8_t* v_marginalized;  /* OptimizableGraph::Vertex::marginalized()                 */
+  const double* v_estimate;       /* packed estimates                                         */
+  int32_t n_edges;
+  const int32_t* e_type;          /* G2OCU_EDGE_*                                             */
+  const int32_t* e_v0;            /* index (not id) of vertices()[0] in the vertex arrays     */
+  const int32_t* e_v1;            /* index of vertices()[1]                                   */
+  const int32_t* e_level;         /* Edge::level(); NULL = all 0                              */
+  const double* e_measurement;    /* packed measurements                                      */
+  const double* e_information;    /* packed information matrices                              */
+  const int32_t* e_kernel;        /* G2OCU_KERNEL_*; NULL = none                              */
+  const double* e_kernel_delta;   /* RobustKernel::delta(); NULL = 1.0                        */
+  const double* e_param;          /* packed per-edge parameters (camera intrinsics)           */
+} g2ocu_graph;
+
+typedef struct g2ocu_config {
+  int32_t device;                 /* CUDA device ordinal, -1 = current device                                   */
+  int32_t linear_solver;          /* G2OCU_LINEAR_*                                                             */
+  double pcg_tolerance;           /* LinearSolverPCG::_tolerance, default 1e-6 (linear_solver_pcg.h:53)         */
+  int32_t pcg_max_iterations;     /* LinearSolverPCG::_maxIter, <0 = matrix rows (linear_solver_pcg.hpp:128)    */
+  int32_t pcg_absolute_tolerance; /* LinearSolverPCG::_absoluteTolerance, default 1                             */
+  void* stream;                   /* optional cudaStream_t to run on; NULL = the library creates its own        */
+} g2ocu_config;
+
+/* Per-iteration record: the G2OBatchStatistics fields (core/batch_stats.h:40-78) filled from CUDA events,
+ * plus the LM state the reference prints in its verbose line (optimization_algorithm_levenberg.cpp:196-202). */
+typedef struct g2ocu_iteration_stats {
+  int32_t iteration;
+  int32_t result;                 /* G2OCU_RESULT_*                                           */
+  int32_t levenberg_iterations;   /* trials in this iteration                                 */
+  int32_t iterations_linear_solver; /* PCG iterations of the last solve                       */
+  double chi2;                    /* activeRobustChi2 after the iteration                     */
+  double lambda;                  /* currentLambda after the iteration                        */
+  double time_residuals;          /* seconds, device time                                     */
+  double time_quadratic_form;
+  double time_schur_complement;
+  double time_linear_solver;
+  double time_linear_solution;
+  double time_update;
+  double time_iteration;          /* host wall clock around the whole iteration                */
+  int64_t hessian_pose_dimension;
+  int64_t hessian_landmark_dimension;
+} g2ocu_iteration_stats;
+
+/* Collective hook for landmark-sharded multi-GPU runs: in-place sum (op 0) or max (op 1) over all ranks of
+ * `count` doubles at DEVICE pointer `buf`, ordered after all work already enqueued on `stream`; returns 0 on
+ * success.  Supplied by the host (torch.distributed / NCCL); never called when world == 1. */
+typedef int (*g2ocu_allreduce_fn)(void* buf, int64_t count, int32_t op, void* stream, void* user);
+
+void g2ocu_default_config(g2ocu_config* cfg);
+int g2ocu_version(void);
+const char* g2ocu_last_error(const g2ocu_solver* s);   /* s may be NULL: error of the last failed g2ocu_create */
+
+int g2ocu_create(const g2ocu_config* cfg, g2ocu_solver** out);
+void g2ocu_destroy(g2ocu_solver* s);
+
+int g2ocu_set_graph(g2ocu_solver* s, const g2ocu_graph* g);
+int g2ocu_set_property(g2ocu_solver* s, const char* name, double value);  /* "initialLambda", "maxTrialsAfterFailure" (levenberg.cpp:48-49) */
+int g2ocu_set_shard(g2ocu_solver* s, int32_t rank, int32_t world, g2ocu_allreduce_fn fn, void* user);
+
+int g2ocu_initialize_optimization(g2ocu_solver* s, int32_t level);
+int g2ocu_init(g2ocu_solver* s, int32_t online);
+int g2ocu_build_structure(g2ocu_solver* s);
+int g2ocu_compute_active_errors(g2ocu_solver* s);
+int g2ocu_active_robust_chi2(g2ocu_solver* s, double* chi2);
+int g2ocu_active_chi2(g2ocu_solver* s, double* chi2);
+int g2ocu_build_system(g2ocu_solver* s);
+int g2ocu_set_lambda(g2ocu_solver* s, double lambda, int32_t backup);
+int g2ocu_restore_diagonal(g2ocu_solver* s);
+int g2ocu_solve(g2ocu_solver* s, int32_t* solved);
+int g2ocu_update(g2ocu_solver* s, const double* host_update_or_null);
+int g2ocu_push(g2ocu_solver* s);
+int g2ocu_pop(g2ocu_solver* s);
+int g2ocu_discard_top(g2ocu_solver* s);
+int g2ocu_compute_lambda_init(g2ocu_solver* s, double* lambda);
+int g2ocu_compute_scale(g2ocu_solver* s, double lambda, double* scale);
+int g2ocu_multiply_hessian(g2ocu_solver* s, double* host_dest, const double* host_src);
+
+int g2ocu_solver_iteration(g2ocu_solver* s, int32_t algorithm, int32_t iteration, g2ocu_iteration_stats* stats);
+int g2ocu_optimize(g2ocu_solver* s, int32_t algorithm, int32_t iterations, g2ocu_iteration_stats* stats, int32_t* performed);
+
+int64_t g2ocu_vector_size(const g2ocu_solver* s);
+int g2ocu_set_estimates(g2ocu_solver* s, const double* host_packed);
+int g2ocu_get_estimates(g2ocu_solver* s, double* host_packed);
+
+/* Named array read-back (structure arrays for the bit-exact check of SURVEY.md Appendix B, block values, vectors).
+ * Returns the number of elements the array has (and fills at most `capacity` of them), or a negative status.
+ * int32: "hessian_index" "active_vertices" "active_edges" "index_mapping" "dims" "pose_block_indices"
+ *        "landmark_block_indices" "hpp_colptr" "hpp_rowidx" "hpl_colptr" "hpl_rowidx" "hschur_colptr" "hschur_rowidx"
+ *        "hschur_t_colptr" "hschur_t_rowidx" "edge_targets"
+ * double: "x" "b" "bschur" "hpp_values" "hpl_values" "hll_values" "hschur_values" "errors" "jacobians" "estimates" */
+int64_t g2ocu_get_i32(g2ocu_solver* s, const char* name, int32_t* out, int64_t capacity);
+int64_t g2ocu_get_f64(g2ocu_solver* s, const char* name, double* out, int64_t capacity);
+
+/* Device-side counters for measurement: number of kernel launches issued by this handle so far, and the
+ * accumulated device time (seconds) and launch count per phase name ("errors" "build" "schur" "pcg_spmv" ...). */
+int64_t g2ocu_launch_count(const g2ocu_solver* s);
+int g2ocu_phase_time(g2ocu_solver* s, const char* phase, double* seconds, int64_t* launches);
+int g2ocu_reset_counters(g2ocu_solver* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G2OCU_H */

@@ -1,0 +1,123 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+Tolerances follow BASELINE.json's north_star: structure bit-exact (tests/test_structure.py), chi2 relative 1e-8 at
+iteration 1 and 1e-6 at the end, lambda trajectory / accept-reject decisions identical, estimates 1e-6."""
+import numpy as np
+import pytest
+
+from g2o_b200 import graph as G
+from g2o_b200 import workloads as W
+from g2o_b200.binding import CudaSolver
+from oracle.oracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / max(1e-300, float(np.max(np.abs(b))))) if a.size else 0.0
+
+
+GRAPHS = {
+    "ba_demo": (lambda: W.ba_demo(), "lm_fix6_3_cuda"),
+    "ba_demo_xyz2uv_huber": (lambda: W.ba_demo(edge_type=G.EDGE_PROJECT_XYZ2UV, robust_kernel=True, outlier_ratio=0.05), "lm_fix6_3_cuda"),
+    "bal_small": (lambda: W.bal_small(), "lm_fix9_3_cuda"),
+    "bal_medium": (lambda: W.bal_synthetic(n_cameras=60, n_points=6000, n_obs=30000, seed=5, k_max=40, min_window=4), "lm_fix9_3_cuda"),
+    "sphere": (lambda: W.sphere(nodes_per_level=16, laps=8), "lm_var_cuda"),
+    "slam2d": (lambda: W.slam2d(n_poses=800, n_landmarks=200, world_size=30.0), "lm_fix3_2_cuda"),
+}
+
+
+def make(name):
+    fn, solver = GRAPHS[name]
+    g = fn()
+    s = CudaSolver(g, solver, device=0)
+    s.initialize_optimization()
+    o = Oracle(g, "lm", "pcg")
+    assert o.initialize_optimization()
+    return g, s, o
+
+
+@pytest.mark.parametrize("name", list(GRAPHS))
+def test_linear_system_blocks(name):
+    g, s, o = make(name)
+    s.init(); s.build_structure()
+    assert o.algorithm_init() and o.build_structure()
+    # errors and chi2
+    s.compute_active_errors(); o.compute_active_errors()
+    assert rel(s.get_f64("errors"), o.get_f64("errors")) < 1e-11
+    assert abs(s.active_robust_chi2() - o.active_robust_chi2()) <= 1e-11 * abs(o.active_robust_chi2())
+    assert abs(s.active_chi2() - o.active_chi2()) <= 1e-11 * abs(o.active_chi2())
+    # Jacobians (the device BAL Jacobian is hand-derived, the oracle's is forward-mode AD like the reference)
+    s.build_system(); o.build_system()
+    assert rel(s.get_f64("jacobians"), o.get_f64("jacobians")) < 1e-10
+    for n in ["b", "hpp_values"] + (["hll_values", "hpl_values"] if o.do_schur() else []):
+        assert rel(s.get_f64(n), o.get_f64(n)) < 1e-11, n
+    lam_s, lam_o = s.compute_lambda_init(), o.compute_lambda_init()
+    assert abs(lam_s - lam_o) <= 1e-12 * lam_o
+    # damped solve
+    s.set_lambda(lam_o); o.set_lambda(lam_o)
+    assert rel(s.get_f64("hpp_values"), o.get_f64("hpp_values")) < 1e-11
+    assert s.solve() and o.solve()
+    if o.do_schur():
+        assert rel(s.get_f64("hschur_values"), o.get_f64("hschur_values")) < 1e-10
+        assert rel(s.get_f64("bschur"), o.get_f64("bschur")) < 1e-10
+    xs, xo = s.x(), o.get_f64("x")
+    assert rel(xs, xo) < 1e-6            # PCG stops at a relative residual of 1e-6: solutions agree to that order
+    assert abs(s.compute_scale(lam_o) - o.compute_scale()) <= 1e-6 * abs(o.compute_scale())
+    s.restore_diagonal(); o.restore_diagonal()
+    # apply the oracle's step on both sides: the oplus operators must agree
+    s.push(); o.push()
+    s.update(xo); o.update(xo)
+    assert rel(s.get_estimates(), o.estimates()) < 1e-12
+    s.compute_active_errors(); o.compute_active_errors()
+    assert abs(s.active_robust_chi2() - o.active_robust_chi2()) <= 1e-10 * abs(o.active_robust_chi2())
+    s.pop(); o.pop()
+    assert rel(s.get_estimates(), o.estimates()) == 0.0
+
+
+@pytest.mark.parametrize("name", list(GRAPHS))
+def test_lm_trajectory(name):
+    g, s, o = make(name)
+    iters = 8
+    n, st = s.optimize(iters)
+    no, sto = o.optimize(iters)
+    assert n == no
+    assert len(st) == len(sto)
+    for i, (a, b) in enumerate(zip(st, sto)):
+        tol = 1e-8 if i == 0 else 1e-6
+        assert abs(a["chi2"] - b["chi2"]) <= tol * abs(b["chi2"]), (i, a["chi2"], b["chi2"])
+        assert a["levenberg_iterations"] == int(b["levenbergIterations"]), i
+        assert abs(a["lambda"] - b["lambda"]) <= 1e-6 * abs(b["lambda"]), i
+        assert a["result"] == int(b["result"])
+    eo = o.estimates()
+    assert np.max(np.abs(s.get_estimates() - eo) / (1.0 + np.abs(eo))) < 1e-6
+
+
+def test_gauss_newton_sphere():
+    g = W.sphere(nodes_per_level=12, laps=6)
+    s = CudaSolver(g, "gn_var_cuda", device=0); s.initialize_optimization()
+    o = Oracle(g, "gn", "pcg"); o.initialize_optimization()
+    n, st = s.optimize(4); no, sto = o.optimize(4)
+    assert n == no
+    for a, b in zip(st, sto):
+        assert abs(a["chi2"] - b["chi2"]) <= 1e-6 * abs(b["chi2"])
+
+
+def test_multiply_hessian_and_second_optimize_continues():
+    g, s, o = make("bal_small")
+    n, st = s.optimize(3)
+    n2, st2 = s.optimize(2)            # a second optimize() continues from the current estimates (vertices keep state)
+    assert st2[0]["chi2"] <= st[-1]["chi2"] * (1 + 1e-9)
+    s.build_system()
+    v = np.random.default_rng(0).normal(size=s.get_i32("dims")[2])
+    hv = s.multiply_hessian(v)
+    # reference: y = Hpp v with the upper blocks used twice (sparse_block_matrix.hpp:288-312)
+    colptr, rowidx, vals = s.get_i32("hpp_colptr"), s.get_i32("hpp_rowidx"), s.get_f64("hpp_values").reshape(-1, 9, 9)
+    y = np.zeros_like(v)
+    for c in range(len(colptr) - 1):
+        for k in range(colptr[c], colptr[c + 1]):
+            r = rowidx[k]; B = vals[k].T      # column-major block
+            y[r * 9:(r + 1) * 9] += B @ v[c * 9:(c + 1) * 9]
+            if r != c:
+                y[c * 9:(c + 1) * 9] += B.T @ v[r * 9:(r + 1) * 9]
+    assert rel(hv, y) < 1e-12
