@@ -220,8 +220,10 @@ def sphere(nodes_per_level: int = 100, laps: int = 100, radius: float = 100.0,
 def _track_lengths(rng, n_points: int, n_obs: int, k_max: int) -> np.ndarray:
     """Discrete power-law track lengths on [2, k_max] whose sum is exactly ``n_obs``."""
     mean = n_obs / n_points
+    if not (2.0 <= mean <= k_max):
+        raise ValueError(f"mean track length {mean:.3f} is outside [2, {k_max}]")
     ks = np.arange(2, k_max + 1, dtype=np.float64)
-    lo, hi = 1.01, 6.0
+    lo, hi = -4.0, 8.0
     for _ in range(80):                      # bisection on the exponent for the requested mean
         s = 0.5 * (lo + hi)
         p = ks ** (-s); p /= p.sum()
@@ -231,7 +233,9 @@ def _track_lengths(rng, n_points: int, n_obs: int, k_max: int) -> np.ndarray:
             hi = s
     k = rng.choice(ks.astype(np.int64), size=n_points, p=p)
     diff = int(n_obs - k.sum())
-    while diff != 0:                          # exact total: nudge random points by +-1
+    for _ in range(100000):                   # exact total: nudge random points by +-1
+        if diff == 0:
+            break
         idx = rng.integers(0, n_points, size=abs(diff))
         if diff > 0:
             ok = idx[k[idx] < k_max]
@@ -242,17 +246,18 @@ def _track_lengths(rng, n_points: int, n_obs: int, k_max: int) -> np.ndarray:
             ok = np.unique(ok)
             k[ok] -= 1
         diff = int(n_obs - k.sum())
+    if diff != 0:
+        raise RuntimeError("could not reach the requested number of observations")
     return k
 
 
 def bal_synthetic(n_cameras: int = 1778, n_points: int = 993_923, n_obs: int = 5_001_946, seed: int = 20260101,
                   k_max: int = 500, window_scale: float = 0.75, min_window: int = 8, huber_delta: float | None = 1.0,
                   outlier_fraction: float = 0.01, pixel_sigma: float = 1.0, name: str = "bal_venice") -> Graph:
-    """C3 (defaults) / C4.  Cameras on a closed ring looking outward (BAL model, bal_example.cpp:192-244: angle-axis,
+    """C3 (defaults) / C4.  Cameras on a closed ring looking at the scene inside it (BAL model, bal_example.cpp:192-244: angle-axis,
     t, f, k1, k2; the camera looks down -z).  Every point has a centre camera and a track length k from a truncated
     power law (mean n_obs/n_points, max ``k_max``); its observers are k distinct cameras drawn from the ring window
-    of half-width max(min_window, window_scale*k) around the centre, and its depth grows with the window so that it is
-    in front of all of them.  Observations = exact projection + N(0, pixel_sigma) (+ a few gross outliers); initial
+    of half-width max(min_window, window_scale*k) around the centre.  Observations = exact projection + N(0, pixel_sigma) (+ a few gross outliers); initial
     cameras/points are perturbed ground truth.  Edges are added point by point (the order of a BAL file).
     Vertex ids: cameras 0..Nc-1, then points (bal_example.cpp:336-377); points are marginalized; Huber kernel with
     ``huber_delta`` on every edge when not None; no fixed vertex (as in bal_example)."""
@@ -284,24 +289,24 @@ def bal_synthetic(n_cameras: int = 1778, n_points: int = 993_923, n_obs: int = 5
             cam_of_obs[idx.ravel()] = cams.ravel()
     pt_of_obs = np.repeat(np.arange(n_points), k)
 
-    # --- ground-truth geometry ---
+    # --- ground-truth geometry: cameras on a ring of radius rho looking at the scene in the middle ---
     rho = 50.0
     phi = 2 * np.pi * np.arange(nc) / nc
     C = np.stack([rho * np.cos(phi), rho * np.sin(phi), np.zeros(nc)], axis=1) + rng.normal(0, 0.05, (nc, 3))
     d = np.stack([np.cos(phi), np.sin(phi), np.zeros(nc)], axis=1)
-    xc = np.stack([np.sin(phi), -np.cos(phi), np.zeros(nc)], axis=1)
+    xc = np.stack([-np.sin(phi), np.cos(phi), np.zeros(nc)], axis=1)
     yc = np.tile([0., 0., 1.], (nc, 1))
-    R = np.stack([xc, yc, -d], axis=1)                      # rows = camera axes
-    R = R @ Rotation.from_rotvec(rng.normal(0, 0.02, (nc, 3))).as_matrix()
+    R = np.stack([xc, yc, d], axis=1)                       # rows = camera axes; the camera looks down -z = -d (inward)
+    R = Rotation.from_rotvec(rng.normal(0, 0.02, (nc, 3))).as_matrix() @ R
     tvec = -np.einsum("nij,nj->ni", R, C)
     rotvec = Rotation.from_matrix(R).as_rotvec()
     cams_true = np.concatenate([rotvec, tvec, rng.uniform(800, 1200, (nc, 1)), rng.normal(0, 1e-2, (nc, 1)),
                                 rng.normal(0, 1e-3, (nc, 1))], axis=1)
-    dphi_max = half * (2 * np.pi / nc)
-    depth = rho * (1.0 / np.cos(np.minimum(dphi_max, 1.2)) - 1.0) * 1.5 + rng.uniform(8, 25, n_points)
+    # points fill a disc of radius 0.35 rho, biased towards the side of their centre camera
     phi_p = 2 * np.pi * (centre + rng.uniform(-0.5, 0.5, n_points)) / nc
-    rad = rho + depth
-    X = np.stack([rad * np.cos(phi_p), rad * np.sin(phi_p), rng.uniform(-0.15, 0.15, n_points) * depth], axis=1)
+    rad = 0.35 * rho * np.sqrt(rng.uniform(0, 1, n_points))
+    X = np.stack([rad * np.cos(phi_p), rad * np.sin(phi_p), rng.uniform(-0.2, 0.2, n_points) * rho], axis=1)
+    depth = rho - rad
 
     # --- observations: exact BAL projection of the truth + pixel noise ---
     meas = _bal_project(cams_true[cam_of_obs], X[pt_of_obs])

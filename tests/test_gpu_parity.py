@@ -53,7 +53,7 @@ def test_linear_system_blocks(name):
     for n in ["b", "hpp_values"] + (["hll_values", "hpl_values"] if o.do_schur() else []):
         assert rel(s.get_f64(n), o.get_f64(n)) < 1e-11, n
     lam_s, lam_o = s.compute_lambda_init(), o.compute_lambda_init()
-    assert abs(lam_s - lam_o) <= 1e-12 * lam_o
+    assert abs(lam_s - lam_o) <= 1e-11 * lam_o
     # damped solve
     s.set_lambda(lam_o); o.set_lambda(lam_o)
     assert rel(s.get_f64("hpp_values"), o.get_f64("hpp_values")) < 1e-11
