@@ -1,0 +1,257 @@
+#!/usr/bin/env python
+"""Benchmark of the LM hot path (BASELINE.json metric: LM iterations/s + HBM GB/s of build / Schur / PCG on a
+BAL-Venice-shaped bundle adjustment).
+
+    python bench.py --gpus N --steps K --warmup W          # our CUDA backend (N>1: launched under torchrun)
+    python bench.py --impl reference --steps K --warmup W  # the reference's CPU algorithm (oracle port) on the host cores
+
+A step is one outer Levenberg-Marquardt iteration (`OptimizationAlgorithmLevenberg::solve`, all its trials) of
+config C3: 1778 cameras / 993 923 points / 5 001 946 observations, BlockSolver<9,3> + PCG, Huber(1.0), synthetic.
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "lm_iterations_per_second"
+UNIT = "LM iterations/s"
+
+
+def workload(name: str, scale: float):
+    from g2o_b200 import workloads as W
+    if name == "bal_venice":
+        if scale == 1.0:
+            return W.bal_venice(), "C3 bal_venice: 1778 cameras / 993923 points / 5001946 observations, Huber(1.0), BlockSolver<9,3>+PCG"
+        nc = max(16, int(1778 * scale ** 0.5)); npnt = int(993_923 * scale); nobs = int(5_001_946 * scale)
+        return (W.bal_synthetic(n_cameras=nc, n_points=npnt, n_obs=nobs, k_max=min(500, nc)),
+                f"C3 bal_venice scaled x{scale}: {nc} cameras / {npnt} points / {nobs} observations")
+    if name == "bal_large":
+        return W.bal_large(), "C4 bal_large: 10000 cameras / 4000000 points / 20000000 observations"
+    raise SystemExit(f"unknown workload {name}")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index; self.samples = []; self._stop = threading.Event(); self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True); self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_leg(graph, iterations: int, threads: int | None = None):
+    """The reference's CPU algorithm (oracle port of BlockSolver<9,3> + LinearSolverPCG, OpenMP at the reference's
+    pragma sites) on the host cores.  Returns (iterations/s, threads, seconds, per-iteration stats)."""
+    from oracle.oracle import Oracle, max_threads
+    threads = threads or max_threads()
+    o = Oracle(graph, "lm", "pcg", threads=threads)
+    o.initialize_optimization()
+    t0 = time.perf_counter()
+    n, stats = o.optimize(iterations)
+    dt = time.perf_counter() - t0
+    return max(n, 0) / dt, threads, dt, stats
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    g, desc = workload(args.workload, args.scale)
+    # bounded sample: every step = one LM iteration of the same workload; warm-up steps are untimed iterations
+    from oracle.oracle import Oracle, max_threads
+    threads = max_threads()
+    o = Oracle(g, "lm", "pcg", threads=threads)
+    o.initialize_optimization()
+    total = args.warmup + args.steps
+    t_all = []
+    # the oracle has no per-iteration entry point that keeps LM state across calls except optimize(); run it once and
+    # take the per-iteration wall-clock it records (G2OBatchStatistics::timeIteration)
+    n, stats = o.optimize(total)
+    times = [s["timeIteration"] for s in stats]
+    timed = times[args.warmup:] if len(times) > args.warmup else times
+    value = len(timed) / sum(timed) if timed else 0.0
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed), "warmup": min(args.warmup, len(times)),
+            "ms_per_step": 1e3 * sum(timed) / max(len(timed), 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": desc, "solver": "oracle port of BlockSolver<9,3> + LinearSolverPCG (reference cannot be compiled: Eigen3 absent)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{len(timed)} LM iterations of the full workload after {args.warmup} warm-up iterations"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "chi2": [s["chi2"] for s in stats]}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from g2o_b200.binding import CudaSolver
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    g, desc = workload(args.workload, args.scale)
+    est0 = g.v_estimate.copy()
+    s = CudaSolver(g, "lm_fix9_3_cuda", device=local)
+    if world > 1:
+        from g2o_b200.dist import install_torch_allreduce
+        install_torch_allreduce(s, rank, world)
+    s.initialize_optimization()
+    s.init()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed_run(e2e: bool):
+        """W untimed + K timed LM iterations from the initial estimates; returns (seconds, stats, launches, phases)."""
+        pin_in = torch.from_numpy(est0.copy()).pin_memory()
+        pin_out = torch.empty_like(pin_in).pin_memory()
+        s.set_estimates(est0)
+        s.init()
+        host_in, host_out = pin_in.numpy(), pin_out.numpy()
+        stats = []
+        for i in range(args.warmup):
+            if e2e:
+                s.set_estimates(host_in)
+            stats.append(s.solver_iteration(i))
+            if e2e:
+                s.get_estimates(host_out); host_in[:] = host_out
+        s.reset_counters()
+        sampler = ClockSampler(local); sampler.start()
+        barrier()
+        l0 = s.launch_count()
+        t0 = time.perf_counter()
+        for i in range(args.warmup, args.warmup + args.steps):
+            if e2e:
+                s.set_estimates(host_in)                       # H2D of this step's inputs (pinned)
+            stats.append(s.solver_iteration(i))
+            if e2e:
+                s.get_estimates(host_out); host_in[:] = host_out   # D2H of the step's result
+        barrier()
+        dt = time.perf_counter() - t0
+        clocks = sampler.stop()
+        phases = {ph: s.phase_time(ph) for ph in ["errors", "build", "schur", "pcg_setup", "pcg_spmv", "pcg_vec", "linear_solver", "backsub", "update"]}
+        return dt, stats, s.launch_count() - l0, phases, clocks
+
+    dt, stats, launches, phases, clocks = timed_run(False)
+    dt_e, stats_e, _, _, _ = timed_run(True)
+    if world > 1:
+        t = torch.tensor([dt, dt_e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, dt_e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    dims = s.get_i32("dims"); nnzS = int(s.get_i32("hschur_colptr")[-1]); nc, npnt = int(dims[0]), int(dims[1]); ne = g.n_edges
+    peak, peak_src = measured_peaks()
+    # algorithmic bytes per launch: P=9, L=3, E=2
+    bytes_spmv = nnzS * 81 * 8 + nc * 81 * 8 + 10 * nc * 9 * 8
+    bytes_build = ne * (16 + 8 + 216) + npnt * (24 + 72 + 24) + nc * (72 + 648 + 72)
+    bytes_schur = ne * 216 + npnt * (72 + 24) + nc * (648 + 72) + npnt * 72 + nnzS * 648 + nc * 72
+    per = {}
+    for name, nbytes in [("pcg_spmv", bytes_spmv), ("build", bytes_build), ("schur", bytes_schur)]:
+        sec, _, calls = phases[name]
+        if calls:
+            per[name] = {"seconds_total": sec, "calls": calls, "avg_ms": 1e3 * sec / calls, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (sec / calls) / 1e9}
+    dominant = max(per, key=lambda k: per[k]["seconds_total"]) if per else None
+    roof = None
+    if dominant:
+        a = per[dominant]["achieved_gbs"]
+        roof = {"kernel": {"pcg_spmv": "spmv_sym_kernel<9>", "build": "build_pl_kernel<BAL> + pose_accum_kernel<BAL>", "schur": "schur_landmark_kernel<9,3>"}[dominant],
+                "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": per[dominant]["avg_ms"], "phases": per}
+    timed_stats = stats[args.warmup:]
+    value = args.steps / dt
+    est_bytes = int(est0.nbytes)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "solver": "lm_fix9_3_cuda (Schur + block-Jacobi PCG)", "l2_policy": "working set (Hpl 1.08 GB, Hschur %.2f GB) exceeds the 126 MB L2" % (nnzS * 648 / 1e9),
+                       "nnz_hschur_blocks": nnzS, "parallelism": f"landmark-sharded x{world}" if world > 1 else "single GPU"},
+            "e2e": {"value": args.steps / dt_e, "unit": UNIT, "h2d_bytes_per_step": est_bytes, "d2h_bytes_per_step": est_bytes + 8,
+                    "note": "per step: host vertex estimates -> device (pinned), one LM iteration through g2ocu_solver_iteration, estimates + chi2 back to the host"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "phase_ms_per_step": {ph: round(1e3 * v[0] / args.steps, 4) for ph, v in phases.items()},
+            "lm": {"chi2": [st["chi2"] for st in stats], "lambda": [st["lambda"] for st in stats], "trials": [st["levenberg_iterations"] for st in stats],
+                   "pcg_iterations": [st["iterations_linear_solver"] for st in stats]}}
+    if world == 1 and not args.no_cpu:
+        # bounded CPU sample: the first LM iteration of the same graph (structure build + 1 iteration), all host threads
+        t0 = time.perf_counter()
+        v, threads, secs, cstats = cpu_reference_leg(g, args.cpu_iterations)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"first {args.cpu_iterations} LM iteration(s) of the same graph incl. buildStructure, {secs:.1f} s wall",
+                                "chi2": [c["chi2"] for c in cstats]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="bal_venice")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-iterations", type=int, default=1)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours" and not os.environ.get("G2O_BENCH_ALLOW_SHORT_WARMUP"):
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -75,7 +75,7 @@ def lib() -> ctypes.CDLL:
         "g2ocu_vector_size": (i64, [vp]), "g2ocu_set_estimates": (ctypes.c_int, [vp, vp]),
         "g2ocu_get_estimates": (ctypes.c_int, [vp, vp]), "g2ocu_get_i32": (i64, [vp, ctypes.c_char_p, vp, i64]),
         "g2ocu_get_f64": (i64, [vp, ctypes.c_char_p, vp, i64]), "g2ocu_launch_count": (i64, [vp]),
-        "g2ocu_phase_time": (ctypes.c_int, [vp, ctypes.c_char_p, P(dbl), P(i64)]), "g2ocu_reset_counters": (ctypes.c_int, [vp]),
+        "g2ocu_phase_time": (ctypes.c_int, [vp, ctypes.c_char_p, P(dbl), P(i64), P(i64)]), "g2ocu_reset_counters": (ctypes.c_int, [vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)          # AttributeError here = header/library mismatch

@@ -192,8 +192,9 @@ class CudaSolver:
     def launch_count(self) -> int: return int(self._L.g2ocu_launch_count(self._h))
 
     def phase_time(self, phase: str):
-        s = ctypes.c_double(); n = ctypes.c_int64()
-        self._ck(self._L.g2ocu_phase_time(self._h, phase.encode(), ctypes.byref(s), ctypes.byref(n)))
-        return s.value, n.value
+        """(device seconds, kernel launches, number of timed intervals) accumulated for ``phase``."""
+        s = ctypes.c_double(); n = ctypes.c_int64(); c = ctypes.c_int64()
+        self._ck(self._L.g2ocu_phase_time(self._h, phase.encode(), ctypes.byref(s), ctypes.byref(n), ctypes.byref(c)))
+        return s.value, n.value, c.value
 
     def reset_counters(self): self._ck(self._L.g2ocu_reset_counters(self._h))

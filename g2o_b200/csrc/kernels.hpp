@@ -62,7 +62,7 @@ struct SchurDev {
 };
 void launchPairSlots(const SchurDev& d, cudaStream_t st, int64_t* launches);
 void launchSchur(const SchurDev& d, const SystemDev& sys, double lambda, cudaStream_t st, int64_t* launches);
-void launchBacksub(const SchurDev& d, const SystemDev& sys, const double* xp, double* xl, cudaStream_t st, int64_t* launches);
+void launchBacksub(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, const double* xp, double* xl, cudaStream_t st, int64_t* launches);
 
 struct PcgDev {
   int n = 0, nb = 0, P = 0;                // scalar size, block rows, block size

@@ -154,41 +154,99 @@ template <int P, int L> __global__ void __launch_bounds__(128) schur_landmark_ke
     }
     __syncwarp();
     const int64_t off = pb + (int64_t)i * k - (int64_t)i * (i - 1) / 2 - i;
-    const int nw = (k - i) * PP;
-    for (int t = lane; t < nw; t += 32) {
-      const int jj = t / PP, el = t - jj * PP;
-      const int j = i + jj, r = el % P, c = el / P;
-      const double* Bj = Hpl + (size_t)(base + j) * PLn;
-      double v = 0;
+    if (PP >= 32) {
+      // one pair per step: lane owns elements lane, lane+32, ... of the P x P block; its rows of B_i Dinv stay in registers
+      constexpr int NR = (PP + 31) / 32;
+      double bd[NR][L]; int cc[NR];
 #pragma unroll
-      for (int a = 0; a < L; ++a) v += sBD[w][r + P * a] * Bj[c + P * a];
-      const int slot = d.pairSlot[off + j];
-      atomicAdd(d.S + (size_t)slot * PP + el, -v);
+      for (int q = 0; q < NR; ++q) {
+        const int el = lane + 32 * q; const int r = el % P; cc[q] = el / P;
+#pragma unroll
+        for (int a = 0; a < L; ++a) bd[q][a] = (el < PP) ? sBD[w][r + P * a] : 0.0;
+      }
+      for (int j = i; j < k; ++j) {
+        const double* Bj = Hpl + (size_t)(base + j) * PLn;
+        double* Sb = d.S + (size_t)d.pairSlot[off + j] * PP;
+#pragma unroll
+        for (int q = 0; q < NR; ++q) {
+          const int el = lane + 32 * q;
+          if (el < PP) {
+            double v = 0;
+#pragma unroll
+            for (int a = 0; a < L; ++a) v += bd[q][a] * Bj[cc[q] + P * a];
+            atomicAdd(Sb + el, -v);
+          }
+        }
+      }
+    } else {
+      // small blocks: several pairs per step
+      constexpr int PPI = 32 / PP;
+      const int sub = lane / PP, el = lane - sub * PP, r = el % P, c = el / P;
+      if (sub < PPI) {
+        double bd[L];
+#pragma unroll
+        for (int a = 0; a < L; ++a) bd[a] = sBD[w][r + P * a];
+        for (int j = i + sub; j < k; j += PPI) {
+          const double* Bj = Hpl + (size_t)(base + j) * PLn;
+          double v = 0;
+#pragma unroll
+          for (int a = 0; a < L; ++a) v += bd[a] * Bj[c + P * a];
+          atomicAdd(d.S + (size_t)d.pairSlot[off + j] * PP + el, -v);
+        }
+      }
     }
   }
 }
 
-// x_l = Dinv (b_l - Σ_i B_i^T x_p[c_i])
-template <int P, int L> __global__ void backsub_kernel(SchurDev d, const double* __restrict__ Hpl, const double* __restrict__ b, const double* __restrict__ xp, double* __restrict__ xl) {
-  constexpr int PLn = P * L, LL = L * L;
-  const int lm = blockIdx.x * blockDim.x + threadIdx.x;
-  if (lm >= d.numLandmarks) return;
-  double c[L];
-#pragma unroll
-  for (int q = 0; q < L; ++q) c[q] = b[(size_t)d.numPoses * P + (size_t)lm * L + q];
-  const int base = d.hplColPtr[lm], end = d.hplColPtr[lm + 1];
-  for (int k = base; k < end; ++k) {
-    const int ci = d.hplRowIdx[k];
-    const double* B = Hpl + (size_t)k * PLn;
+// x_l = Dinv (b_l - Σ_i B_i^T x_p[c_i])   (block_solver.hpp:420-444)
+// pass 1: thread per Hpl block; the CTA stages its 128 contiguous blocks in shared memory with coalesced loads, every thread forms
+// B^T x_p for its block, runs of equal landmark are summed by their first thread and added to the accumulator (xl, zeroed before).
+template <int P, int L> __global__ void __launch_bounds__(128) backsub_accum_kernel(SchurDev d, const double* __restrict__ Hpl, const int32_t* __restrict__ hplLm, int nBlocks,
+                                                                                    const double* __restrict__ xp, double* __restrict__ xl) {
+  constexpr int PLn = P * L;
+  __shared__ double sB[128 * PLn];
+  __shared__ double sV[128 * L];
+  __shared__ int sLm[128];
+  const int tid = threadIdx.x, k0 = blockIdx.x * 128;
+  const int nb = min(128, nBlocks - k0);
+  const double* src = Hpl + (size_t)k0 * PLn;
+  for (int t = tid; t < nb * PLn; t += 128) sB[t] = src[t];
+  __syncthreads();
+  int lm = -1;
+  if (tid < nb) {
+    const int k = k0 + tid, ci = d.hplRowIdx[k];
+    lm = hplLm[k];
     double x[P];
 #pragma unroll
     for (int r = 0; r < P; ++r) x[r] = xp[(size_t)ci * P + r];
 #pragma unroll
     for (int q = 0; q < L; ++q) { double v = 0;
 #pragma unroll
-      for (int r = 0; r < P; ++r) v += B[r + P * q] * x[r];
-      c[q] -= v; }
+      for (int r = 0; r < P; ++r) v += sB[tid * PLn + r + P * q] * x[r];
+      sV[tid * L + q] = v; }
   }
+  sLm[tid] = lm;
+  __syncthreads();
+  if (lm >= 0 && (tid == 0 || sLm[tid - 1] != lm)) {
+    double acc[L];
+#pragma unroll
+    for (int q = 0; q < L; ++q) acc[q] = sV[tid * L + q];
+    for (int t = tid + 1; t < nb && sLm[t] == lm; ++t) {
+#pragma unroll
+      for (int q = 0; q < L; ++q) acc[q] += sV[t * L + q];
+    }
+#pragma unroll
+    for (int q = 0; q < L; ++q) atomicAdd(xl + (size_t)lm * L + q, acc[q]);
+  }
+}
+// pass 2: x_l = Dinv (b_l - acc_l)
+template <int P, int L> __global__ void backsub_finish_kernel(SchurDev d, const double* __restrict__ b, double* __restrict__ xl) {
+  constexpr int LL = L * L;
+  const int lm = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lm >= d.numLandmarks) return;
+  double c[L];
+#pragma unroll
+  for (int q = 0; q < L; ++q) c[q] = b[(size_t)d.numPoses * P + (size_t)lm * L + q] - xl[(size_t)lm * L + q];
 #pragma unroll
   for (int r = 0; r < L; ++r) { double v = 0;
 #pragma unroll
@@ -400,13 +458,17 @@ void launchSchur(const SchurDev& d, const SystemDev& sys, double lambda, cudaStr
   else if (d.P == 6 && d.L == 3) schurPL<6, 3>(d, sys, lambda, st, launches);
   else if (d.P == 3 && d.L == 2) schurPL<3, 2>(d, sys, lambda, st, launches);
 }
-void launchBacksub(const SchurDev& d, const SystemDev& sys, const double* xp, double* xl, cudaStream_t st, int64_t* launches) {
+template <int P, int L> static void backsubPL(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, const double* xp, double* xl, cudaStream_t st, int64_t* launches) {
+  cudaMemsetAsync(xl, 0, sizeof(double) * (size_t)d.numLandmarks * L, st);
+  if (nBlocks > 0) { backsub_accum_kernel<P, L><<<(nBlocks + 127) / 128, 128, 0, st>>>(d, sys.Hpl, hplLm, nBlocks, xp, xl); *launches += 1; }
+  backsub_finish_kernel<P, L><<<(d.numLandmarks + 255) / 256, 256, 0, st>>>(d, sys.b, xl);
+  *launches += 2;
+}
+void launchBacksub(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, const double* xp, double* xl, cudaStream_t st, int64_t* launches) {
   if (d.numLandmarks == 0) return;
-  const int nb = (d.numLandmarks + 127) / 128;
-  if (d.P == 9 && d.L == 3) backsub_kernel<9, 3><<<nb, 128, 0, st>>>(d, sys.Hpl, sys.b, xp, xl);
-  else if (d.P == 6 && d.L == 3) backsub_kernel<6, 3><<<nb, 128, 0, st>>>(d, sys.Hpl, sys.b, xp, xl);
-  else if (d.P == 3 && d.L == 2) backsub_kernel<3, 2><<<nb, 128, 0, st>>>(d, sys.Hpl, sys.b, xp, xl);
-  *launches += 1;
+  if (d.P == 9 && d.L == 3) backsubPL<9, 3>(d, sys, hplLm, nBlocks, xp, xl, st, launches);
+  else if (d.P == 6 && d.L == 3) backsubPL<6, 3>(d, sys, hplLm, nBlocks, xp, xl, st, launches);
+  else if (d.P == 3 && d.L == 2) backsubPL<3, 2>(d, sys, hplLm, nBlocks, xp, xl, st, launches);
 }
 
 #define FOR_P(Pv, CALL) switch (Pv) { case 3: { CALL(3) break; } case 6: { CALL(6) break; } case 9: { CALL(9) break; } default: break; }

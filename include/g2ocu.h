@@ -195,10 +195,11 @@ int g2ocu_get_estimates(g2ocu_solver* s, double* host_packed);
 int64_t g2ocu_get_i32(g2ocu_solver* s, const char* name, int32_t* out, int64_t capacity);
 int64_t g2ocu_get_f64(g2ocu_solver* s, const char* name, double* out, int64_t capacity);
 
-/* Device-side counters for measurement: number of kernel launches issued by this handle so far, and the
- * accumulated device time (seconds) and launch count per phase name ("errors" "build" "schur" "pcg_spmv" ...). */
+/* Device-side counters for measurement: number of kernel launches issued by this handle so far, and per phase name
+ * ("errors" "build" "schur" "pcg_setup" "pcg_spmv" "pcg_vec" "linear_solver" "backsub" "update") the accumulated
+ * device time in seconds (CUDA events on the handle's stream), the launches inside it and how many times it ran. */
 int64_t g2ocu_launch_count(const g2ocu_solver* s);
-int g2ocu_phase_time(g2ocu_solver* s, const char* phase, double* seconds, int64_t* launches);
+int g2ocu_phase_time(g2ocu_solver* s, const char* phase, double* seconds, int64_t* launches, int64_t* calls);
 int g2ocu_reset_counters(g2ocu_solver* s);
 
 #ifdef __cplusplus
