@@ -80,9 +80,10 @@ struct g2ocu_solver {
   // device state
   DVec<double> poseEst, lmEst; std::vector<DVec<double>*> poseBackup, lmBackup; int stackDepth = 0;
   DVec<int> poseCounters, lmCounters;
-  DVec<double> Hpp, Hll, Hpl, b, x, S, Dinv, bschur, Minv, vr, vd, vq, vs, scal, partial, partialDq, scratch, out2, dbg;
-  DVec<int32_t> hppDiag, hplColPtr, hplRowIdx, sRowPtr, sColIdx, sDiag, hppToS, pairSlot, itemLm, itemBegin, itemEnd, aRowPtr, aColIdx, aDiag, spRow, spBegin, spEnd, hplLm;
-  DVec<int64_t> pairPtr, off64;
+  DVec<double> Hpp, Hll, Hpl, b, x, S, Dinv, dbv, bschur, Minv, vr, vd, vq, vs, scal, partial, partialDq, scratch, out2, dbg;
+  DVec<int32_t> hppDiag, hplColPtr, hplRowIdx, sRowPtr, sColIdx, sDiag, hppToS, pairSlot, pairEdgeI, pairEdgeJ, aRowPtr, aColIdx, aDiag, spRow, spBegin, spEnd, hplLm, tEntLm, tEntBI, tEntBJ, tChunkI, tChunkJ, tChunkB, tChunkE;
+  DVec<uint32_t> tEntMJ; DVec<uint8_t> tEntMI;
+  DVec<int64_t> off64;
   std::vector<EdgeSetState*> sets;
   SystemDev sys; SchurDev schur; PcgDev pcg;
   double* hostScal = nullptr;     // pinned
@@ -257,36 +258,61 @@ int buildDevice(g2ocu_solver* s) {
     { std::vector<int32_t> lmOf(st.hplRowIdx.size()); for (int l = 0; l < st.numLandmarks; ++l) for (int k = st.hplColPtr[l]; k < st.hplColPtr[l + 1]; ++k) lmOf[k] = l;
       CU(s->hplLm.upload(lmOf, stream)); CU(cudaStreamSynchronize(stream)); }
     CU(s->sRowPtr.upload(st.sRowPtr, stream)); CU(s->sColIdx.upload(st.sColIdx, stream)); CU(s->sDiag.upload(st.sDiag, stream)); CU(s->hppToS.upload(st.hppToS, stream));
-    std::vector<int64_t> pairPtr(st.numLandmarks + 1, 0);
-    std::vector<int32_t> itLm, itB, itE;
-    const int64_t kMaxPairsPerItem = 384;
+    // short tracks (< kTileMinTrack observations): flat pair list, landmarks visited in the order of their first camera;
+    // long tracks: entries of the output-stationary tile kernel
+    struct TileEntry { int64_t key; int32_t lm, baseI, baseJ; uint32_t maskJ; uint8_t maskI; };
+    std::vector<TileEntry> entries;
+    std::vector<int32_t> shortLm;
     for (int l = 0; l < st.numLandmarks; ++l) {
-      const int64_t k = st.hplColPtr[l + 1] - st.hplColPtr[l];
-      pairPtr[l + 1] = pairPtr[l] + k * (k + 1) / 2;
-      int begin = 0; int64_t acc = 0;
-      if (k == 0) { itLm.push_back(l); itB.push_back(0); itE.push_back(0); continue; }
+      const int cb = st.hplColPtr[l]; const int64_t k = st.hplColPtr[l + 1] - cb;
+      if (k == 0) continue;
+      if (k < kTileMinTrack) { shortLm.push_back(l); continue; }
+      struct Run { int32_t tile, base; uint32_t mask; };
+      std::vector<Run> rowsR, colsR;
       for (int i = 0; i < k; ++i) {
-        acc += k - i;
-        if (acc >= kMaxPairsPerItem || i == k - 1) { itLm.push_back(l); itB.push_back(begin); itE.push_back(i + 1); begin = i + 1; acc = 0; }
+        const int c = st.hplRowIdx[cb + i];
+        const int ti = c / kTileRows, tj = c / kTileCols;
+        if (rowsR.empty() || rowsR.back().tile != ti) rowsR.push_back({ti, cb + i, 0u});
+        rowsR.back().mask |= 1u << (c % kTileRows);
+        if (colsR.empty() || colsR.back().tile != tj) colsR.push_back({tj, cb + i, 0u});
+        colsR.back().mask |= 1u << (c % kTileCols);
       }
+      for (const Run& ri : rowsR)
+        for (const Run& rj : colsR) {
+          if ((rj.tile + 1) * kTileCols - 1 < ri.tile * kTileRows) continue;       // strip entirely left of the row tile: lower triangle
+          entries.push_back({((int64_t)ri.tile << 32) | (uint32_t)rj.tile, l, ri.base, rj.base, rj.mask, (uint8_t)ri.mask});
+        }
     }
-    {  // process the items in the order of their first camera: concurrently running warps then update a narrow band of
-       // Hschur, which stays L2 resident (761 MB of blocks updated in landmark order thrashed the 126 MB L2: 77 GB of DRAM traffic)
-      std::vector<int32_t> ord(itLm.size()), key(itLm.size());
-      for (size_t i = 0; i < itLm.size(); ++i) { ord[i] = (int32_t)i; const int32_t cb = st.hplColPtr[itLm[i]]; key[i] = (itE[i] > itB[i]) ? st.hplRowIdx[cb + itB[i]] : st.numPoses; }
-      std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
-      std::vector<int32_t> a(itLm.size()), b(itLm.size()), c(itLm.size());
-      for (size_t i = 0; i < ord.size(); ++i) { a[i] = itLm[ord[i]]; b[i] = itB[ord[i]]; c[i] = itE[ord[i]]; }
-      itLm.swap(a); itB.swap(b); itE.swap(c);
+    {
+      std::stable_sort(shortLm.begin(), shortLm.end(), [&](int32_t a, int32_t b) { return st.hplRowIdx[st.hplColPtr[a]] < st.hplRowIdx[st.hplColPtr[b]]; });
+      std::vector<int32_t> pI, pJ;
+      for (int32_t l : shortLm) { const int cb = st.hplColPtr[l], ce = st.hplColPtr[l + 1]; for (int i = cb; i < ce; ++i) for (int j = i; j < ce; ++j) { pI.push_back(i); pJ.push_back(j); } }
+      CU(s->pairEdgeI.upload(pI, stream)); CU(s->pairEdgeJ.upload(pJ, stream)); CU(s->pairSlot.alloc(std::max<size_t>(pI.size(), 1)));
+      CU(cudaStreamSynchronize(stream));
+      sd.nPairs = (int64_t)pI.size(); sd.pairEdgeI = s->pairEdgeI.p; sd.pairEdgeJ = s->pairEdgeJ.p; sd.pairSlot = s->pairSlot.p;
     }
-    CU(s->pairPtr.upload(pairPtr, stream)); CU(s->pairSlot.alloc((size_t)std::max<int64_t>(pairPtr[st.numLandmarks], 1)));
-    CU(s->itemLm.upload(itLm, stream)); CU(s->itemBegin.upload(itB, stream)); CU(s->itemEnd.upload(itE, stream));
-    CU(s->S.alloc((size_t)st.sColIdx.size() * P * P)); CU(s->Dinv.alloc((size_t)st.numLandmarks * L * L)); CU(s->bschur.alloc((size_t)st.sizePoses));
+    {  // tile entries grouped by (row tile, column strip), split in chunks of at most kTileChunk entries (one CTA each)
+      const int kTileChunk = 256;
+      std::stable_sort(entries.begin(), entries.end(), [](const TileEntry& a, const TileEntry& b) { return a.key < b.key; });
+      std::vector<int32_t> eLm(entries.size()), eBI(entries.size()), eBJ(entries.size()), cI, cJ, cB, cE; std::vector<uint32_t> eMJ(entries.size()); std::vector<uint8_t> eMI(entries.size());
+      for (size_t i = 0; i < entries.size(); ++i) { eLm[i] = entries[i].lm; eBI[i] = entries[i].baseI; eBJ[i] = entries[i].baseJ; eMJ[i] = entries[i].maskJ; eMI[i] = entries[i].maskI; }
+      for (size_t i = 0; i < entries.size();) {
+        size_t j = i; while (j < entries.size() && entries[j].key == entries[i].key) ++j;
+        for (size_t c0 = i; c0 < j; c0 += kTileChunk) { cI.push_back((int32_t)(entries[i].key >> 32)); cJ.push_back((int32_t)(entries[i].key & 0xffffffff)); cB.push_back((int32_t)c0); cE.push_back((int32_t)std::min(j, c0 + kTileChunk)); }
+        i = j;
+      }
+      CU(s->tEntLm.upload(eLm, stream)); CU(s->tEntBI.upload(eBI, stream)); CU(s->tEntBJ.upload(eBJ, stream)); CU(s->tEntMJ.upload(eMJ, stream)); CU(s->tEntMI.upload(eMI, stream));
+      CU(s->tChunkI.upload(cI, stream)); CU(s->tChunkJ.upload(cJ, stream)); CU(s->tChunkB.upload(cB, stream)); CU(s->tChunkE.upload(cE, stream));
+      CU(cudaStreamSynchronize(stream));
+      sd.nTileChunks = (int)cI.size();
+      sd.chunkI = s->tChunkI.p; sd.chunkJ = s->tChunkJ.p; sd.chunkBegin = s->tChunkB.p; sd.chunkEnd = s->tChunkE.p;
+      sd.entLm = s->tEntLm.p; sd.entBaseI = s->tEntBI.p; sd.entBaseJ = s->tEntBJ.p; sd.entMaskJ = s->tEntMJ.p; sd.entMaskI = s->tEntMI.p;
+    }
+    CU(s->S.alloc((size_t)st.sColIdx.size() * P * P)); CU(s->Dinv.alloc((size_t)st.numLandmarks * L * L)); CU(s->dbv.alloc((size_t)st.numLandmarks * L)); CU(s->bschur.alloc((size_t)st.sizePoses));
     sd.numPoses = st.numPoses; sd.numLandmarks = st.numLandmarks; sd.P = P; sd.L = L;
     sd.hplColPtr = s->hplColPtr.p; sd.hplRowIdx = s->hplRowIdx.p; sd.sRowPtr = s->sRowPtr.p; sd.sColIdx = s->sColIdx.p; sd.sDiag = s->sDiag.p;
     sd.hppToS = s->hppToS.p; sd.nnzHpp = (int)st.hppColIdx.size(); sd.nnzS = (int)st.sColIdx.size();
-    sd.pairPtr = s->pairPtr.p; sd.pairSlot = s->pairSlot.p; sd.itemLm = s->itemLm.p; sd.itemBegin = s->itemBegin.p; sd.itemEnd = s->itemEnd.p; sd.nItems = (int)itLm.size();
-    sd.S = s->S.p; sd.Dinv = s->Dinv.p; sd.bschur = s->bschur.p;
+    sd.S = s->S.p; sd.Dinv = s->Dinv.p; sd.db = s->dbv.p; sd.bschur = s->bschur.p;
     launchPairSlots(sd, stream, &s->launches);
     CU(cudaStreamSynchronize(stream));
   }
@@ -383,7 +409,7 @@ int solveSystem(g2ocu_solver* s, int* solved) {
     return solvePcg(s, s->b.p);
   }
   { PhaseTimer pt(s, "schur");
-    launchSchur(s->schur, s->sys, s->lambda, s->stream, &s->launches);
+    launchSchur(s->schur, s->sys, s->hplLm.p, (int)s->st.hplRowIdx.size(), s->lambda, s->stream, &s->launches);
     if (s->world > 1) {
       int rc = allreduceDev(s, s->S.p, (int64_t)s->S.n, 0); if (rc) return rc;
       rc = allreduceDev(s, s->bschur.p, (int64_t)s->bschur.n, 0); if (rc) return rc;

@@ -56,12 +56,18 @@ struct SchurDev {
   const int32_t* hplColPtr = nullptr; const int32_t* hplRowIdx = nullptr;
   const int32_t* sRowPtr = nullptr; const int32_t* sColIdx = nullptr; const int32_t* sDiag = nullptr;
   const int32_t* hppToS = nullptr; int nnzHpp = 0; int nnzS = 0;
-  const int64_t* pairPtr = nullptr; int32_t* pairSlot = nullptr;          // per landmark pair -> S block index
-  const int32_t* itemLm = nullptr; const int32_t* itemBegin = nullptr; const int32_t* itemEnd = nullptr; int nItems = 0;
-  double* S = nullptr; double* Dinv = nullptr; double* bschur = nullptr;
+  // short tracks: flat list of (Hpl block i, Hpl block j, Hschur block) per pair i <= j, atomics
+  int64_t nPairs = 0; const int32_t* pairEdgeI = nullptr; const int32_t* pairEdgeJ = nullptr; int32_t* pairSlot = nullptr;
+  double* S = nullptr; double* Dinv = nullptr; double* db = nullptr; double* bschur = nullptr;
+  // long tracks (>= kTileMinTrack observations): output-stationary tiles, see schur_tile_kernel
+  int nTileChunks = 0;
+  const int32_t* chunkI = nullptr; const int32_t* chunkJ = nullptr; const int32_t* chunkBegin = nullptr; const int32_t* chunkEnd = nullptr;
+  const int32_t* entLm = nullptr; const int32_t* entBaseI = nullptr; const int32_t* entBaseJ = nullptr; const uint32_t* entMaskJ = nullptr; const uint8_t* entMaskI = nullptr;
 };
+static const int kTileRows = 4, kTileCols = 32;   // cameras per tile row group / column strip
+static const int kTileMinTrack = 8;               // landmarks with at least this many observations go through the tile kernel
 void launchPairSlots(const SchurDev& d, cudaStream_t st, int64_t* launches);
-void launchSchur(const SchurDev& d, const SystemDev& sys, double lambda, cudaStream_t st, int64_t* launches);
+void launchSchur(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, double lambda, cudaStream_t st, int64_t* launches);
 void launchBacksub(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, const double* xp, double* xl, cudaStream_t st, int64_t* launches);
 
 struct PcgDev {

@@ -65,24 +65,14 @@ template <> G2D void invSmall<3>(const double* A, double* X) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// one-time: S block index of every (landmark, i<=j) pair, by binary search in the CSR row of camera i
-__global__ void __launch_bounds__(128) pair_slot_kernel(SchurDev d) {
-  const int item = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (item >= d.nItems) return;
-  const int lm = d.itemLm[item], i0 = d.itemBegin[item], i1 = d.itemEnd[item];
-  const int base = d.hplColPtr[lm], k = d.hplColPtr[lm + 1] - base;
-  const int64_t pb = d.pairPtr[lm];
-  for (int i = i0; i < i1; ++i) {
-    const int ci = d.hplRowIdx[base + i];
-    const int64_t off = pb + (int64_t)i * k - (int64_t)i * (i - 1) / 2 - i;
-    const int lo0 = d.sRowPtr[ci], hi0 = d.sRowPtr[ci + 1];
-    for (int j = i + lane; j < k; j += 32) {
-      const int cj = d.hplRowIdx[base + j];
-      int lo = lo0, hi = hi0;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (d.sColIdx[mid] < cj) lo = mid + 1; else hi = mid; }
-      d.pairSlot[off + j] = lo;
-    }
-  }
+// one-time: Hschur block index of every short-track pair (binary search in the CSR row of the first camera)
+__global__ void pair_slot_kernel(SchurDev d) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= d.nPairs) return;
+  const int ci = d.hplRowIdx[d.pairEdgeI[p]], cj = d.hplRowIdx[d.pairEdgeJ[p]];
+  int lo = d.sRowPtr[ci], hi = d.sRowPtr[ci + 1];
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (d.sColIdx[mid] < cj) lo = mid + 1; else hi = mid; }
+  d.pairSlot[p] = lo;
 }
 
 template <int P> __global__ void schur_init_kernel(SchurDev d, const double* Hpp, const double* b, double lambda) {
@@ -101,100 +91,149 @@ template <int P> __global__ void add_lambda_diag_kernel(double* A, const int32_t
   A[(size_t)diag[i] * P * P + k * (P + 1)] += lambda;
 }
 
-// warp per work item (landmark, rows [i0,i1) of its observation list)
-template <int P, int L> __global__ void __launch_bounds__(128) schur_landmark_kernel(SchurDev d, const double* __restrict__ Hll, const double* __restrict__ Hpl,
-                                                                                     const double* __restrict__ b, double lambda) {
+// Dinv_l = (Hll_l + lambda I)^-1 and db_l = Dinv_l b_l, thread per landmark (block_solver.hpp:347-356)
+template <int P, int L> __global__ void dinv_kernel(SchurDev d, const double* __restrict__ Hll, const double* __restrict__ b, double lambda) {
+  constexpr int LL = L * L;
+  const int lm = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lm >= d.numLandmarks) return;
+  double H[LL], X[LL], bl[L];
+#pragma unroll
+  for (int q = 0; q < LL; ++q) H[q] = Hll[(size_t)lm * LL + q];
+#pragma unroll
+  for (int q = 0; q < L; ++q) { H[q * (L + 1)] += lambda; bl[q] = b[(size_t)d.numPoses * P + (size_t)lm * L + q]; }
+  invSmall<L>(H, X);
+#pragma unroll
+  for (int q = 0; q < LL; ++q) d.Dinv[(size_t)lm * LL + q] = X[q];
+#pragma unroll
+  for (int r = 0; r < L; ++r) { double v = 0;
+#pragma unroll
+    for (int c = 0; c < L; ++c) v += X[r + L * c] * bl[c];
+    d.db[(size_t)lm * L + r] = v; }
+}
+
+// b_schur -= B_i (Dinv b_l) for every Hpl block (block_solver.hpp:366-374): thread per block, blocks staged through shared memory
+template <int P, int L> __global__ void __launch_bounds__(128) coeff_kernel(SchurDev d, const double* __restrict__ Hpl, const int32_t* __restrict__ hplLm, int nBlocks) {
+  constexpr int PLn = P * L;
+  __shared__ double sB[128 * PLn];
+  const int tid = threadIdx.x, k0 = blockIdx.x * 128;
+  const int nb = min(128, nBlocks - k0);
+  const double* src = Hpl + (size_t)k0 * PLn;
+  for (int t = tid; t < nb * PLn; t += 128) sB[t] = src[t];
+  __syncthreads();
+  if (tid >= nb) return;
+  const int k = k0 + tid, ci = d.hplRowIdx[k], lm = hplLm[k];
+  double dbv[L];
+#pragma unroll
+  for (int a = 0; a < L; ++a) dbv[a] = d.db[(size_t)lm * L + a];
+#pragma unroll
+  for (int r = 0; r < P; ++r) { double v = 0;
+#pragma unroll
+    for (int a = 0; a < L; ++a) v += sB[tid * PLn + r + P * a] * dbv[a];
+    atomicAdd(d.bschur + (size_t)ci * P + r, -v); }
+}
+
+// Short tracks: Hschur(ci,cj) -= B_i Dinv B_j^T with one atomic add per element; warp per pair over a flat pair list
+// (ordered by first camera so that concurrently running warps hit an L2-resident band of Hschur).
+template <int P, int L> __global__ void __launch_bounds__(256) schur_pairs_kernel(SchurDev d, const double* __restrict__ Hpl, const int32_t* __restrict__ hplLm) {
   constexpr int PP = P * P, PLn = P * L, LL = L * L;
-  __shared__ double sBD[4][PLn];
-  __shared__ double sDinv[4][LL + L];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x * 4 + w;
-  if (item >= d.nItems) return;
-  const int lm = d.itemLm[item], i0 = d.itemBegin[item], i1 = d.itemEnd[item];
-  {
-    double H[LL], X[LL], bl[L];
+  constexpr int NR = (PP + 31) / 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < d.nPairs; p += nWarps) {
+    const int eI = d.pairEdgeI[p], eJ = d.pairEdgeJ[p], slot = d.pairSlot[p];
+    const int lm = hplLm[eI];
+    const double* Bi = Hpl + (size_t)eI * PLn; const double* Bj = Hpl + (size_t)eJ * PLn;
+    // lane t < P*L holds (B_i Dinv)[r, a] with r = t % P, a = t / P
+    double bd = 0;
+    if (lane < PLn) {
+      const int r = lane % P, a = lane / P;
 #pragma unroll
-    for (int q = 0; q < LL; ++q) H[q] = Hll[(size_t)lm * LL + q];
+      for (int a2 = 0; a2 < L; ++a2) bd += Bi[r + P * a2] * d.Dinv[(size_t)lm * LL + a2 + L * a];
+    }
+    double* Sb = d.S + (size_t)slot * PP;
 #pragma unroll
-    for (int q = 0; q < L; ++q) { H[q * (L + 1)] += lambda; bl[q] = b[(size_t)d.numPoses * P + (size_t)lm * L + q]; }
-    invSmall<L>(H, X);
-    if (lane == 0) {
+    for (int q = 0; q < NR; ++q) {
+      const int el = lane + 32 * q; const int r = el % P, c = el / P;
+      double v = 0;
 #pragma unroll
-      for (int q = 0; q < LL; ++q) sDinv[w][q] = X[q];
+      for (int a = 0; a < L; ++a) { const double w = __shfl_sync(0xffffffffu, bd, (r + P * a) & 31); if (el < PP) v += w * Bj[c + P * a]; }
+      if (el < PP) atomicAdd(Sb + el, -v);
+    }
+  }
+}
+
+// Long tracks: output-stationary accumulation.  A CTA owns the Hschur blocks (rows = kTileRows consecutive cameras, columns = a strip of
+// 32 consecutive cameras): warp w <-> camera row, lane <-> camera column, every thread keeps its whole P x P block in registers and
+// walks the list of (landmark, cameras present in the rows, cameras present in the strip) entries of its tile.  The B blocks of an
+// entry are staged in shared memory once (they are contiguous in Hpl because a landmark's blocks are sorted by camera); W_i = B_i Dinv
+// is formed once per row.  Nothing is written to global memory until the end: one atomic add per block element per chunk, instead of one
+// per landmark pair (the per-pair atomics ran at ~1.4 elements/clk/SM and made this phase 20 ms on the Venice-shaped problem).
+constexpr int kTileBatch = 12;   // entries staged in shared memory per barrier pair
+constexpr int kTileThreads = kTileRows * 32;
+template <int P, int L> __global__ void __launch_bounds__(kTileThreads, 2) schur_tile_kernel(SchurDev d, const double* __restrict__ Hpl) {
+  constexpr int PP = P * P, PLn = P * L, LL = L * L, SB = PLn + 1;
+  constexpr int ENT = kTileCols * SB + kTileRows * PLn;      // doubles of shared memory per staged entry
+  extern __shared__ double smem[];
+  __shared__ int sHdr[kTileBatch][5];                        // lm, baseI, baseJ, maskJ, maskI
+  const int chunk = blockIdx.x, tid = threadIdx.x, bi = tid >> 5, lane = tid & 31;
+  const int ci = d.chunkI[chunk] * kTileRows + bi, cj = d.chunkJ[chunk] * kTileCols + lane;
+  const bool mine = ci < d.numPoses && cj < d.numPoses && cj >= ci;
+  double acc[PP];
 #pragma unroll
-      for (int r = 0; r < L; ++r) { double v = 0;
+  for (int q = 0; q < PP; ++q) acc[q] = 0;
+  bool touched = false;
+  const int eBegin = d.chunkBegin[chunk], eEnd = d.chunkEnd[chunk];
+  for (int e0 = eBegin; e0 < eEnd; e0 += kTileBatch) {
+    const int nb = min(kTileBatch, eEnd - e0);
+    __syncthreads();
+    // stage: warp w copies entries w, w+8, ... of the batch (B_j blocks of the strip, W_i = B_i Dinv of the rows)
+    for (int eb = bi; eb < nb; eb += kTileRows) {
+      const int e = e0 + eb;
+      const int lm = d.entLm[e], baseI = d.entBaseI[e], baseJ = d.entBaseJ[e];
+      const unsigned maskJ = d.entMaskJ[e], maskI = d.entMaskI[e];
+      if (lane == 0) { sHdr[eb][0] = lm; sHdr[eb][1] = baseI; sHdr[eb][2] = baseJ; sHdr[eb][3] = (int)maskJ; sHdr[eb][4] = (int)maskI; }
+      double* sB = smem + (size_t)eb * ENT; double* sW = sB + kTileCols * SB;
+      const int nJ = __popc(maskJ), nI = __popc(maskI);
+      const double* src = Hpl + (size_t)baseJ * PLn;
+      for (int q = lane; q < nJ * PLn; q += 32) { const int jb = q / PLn, el = q - jb * PLn; sB[jb * SB + el] = src[q]; }
+      for (int q = lane; q < nI * PLn; q += 32) {
+        const int ii = q / PLn, el = q - ii * PLn, r = el % P, bc = el / P;
+        const double* Bi = Hpl + (size_t)(baseI + ii) * PLn;
+        double v = 0;
 #pragma unroll
-        for (int c = 0; c < L; ++c) v += X[r + L * c] * bl[c];
-        sDinv[w][LL + r] = v; }
-      if (i0 == 0) {
+        for (int a = 0; a < L; ++a) v += Bi[r + P * a] * d.Dinv[(size_t)lm * LL + a + L * bc];
+        sW[q] = v;
+      }
+    }
+    __syncthreads();
+    if (mine) {
+      for (int eb = 0; eb < nb; ++eb) {
+        const unsigned maskJ = (unsigned)sHdr[eb][3], maskI = (unsigned)sHdr[eb][4];
+        if (!((maskI >> bi) & 1u)) continue;                 // warp-uniform
+        if (!((maskJ >> lane) & 1u)) continue;
+        touched = true;
+        const double* sB = smem + (size_t)eb * ENT;
+        const double* Wi = sB + kTileCols * SB + __popc(maskI & ((1u << bi) - 1u)) * PLn;
+        const double* Bj = sB + __popc(maskJ & ((1u << lane) - 1u)) * SB;
 #pragma unroll
-        for (int q = 0; q < LL; ++q) d.Dinv[(size_t)lm * LL + q] = X[q];
+        for (int a = 0; a < L; ++a) {
+          double wv[P], bv[P];
+#pragma unroll
+          for (int r = 0; r < P; ++r) { wv[r] = Wi[r + P * a]; bv[r] = Bj[r + P * a]; }
+#pragma unroll
+          for (int c = 0; c < P; ++c)
+#pragma unroll
+            for (int r = 0; r < P; ++r) acc[r + P * c] += wv[r] * bv[c];
+        }
       }
     }
   }
-  __syncwarp();
-  const int base = d.hplColPtr[lm], k = d.hplColPtr[lm + 1] - base;
-  const int64_t pb = d.pairPtr[lm];
-  for (int i = i0; i < i1; ++i) {
-    const int ci = d.hplRowIdx[base + i];
-    const double* Bi = Hpl + (size_t)(base + i) * PLn;
-    __syncwarp();
-    if (lane < PLn) {
-      const int r = lane % P, bc = lane / P;
-      double v = 0;
+  if (touched) {
+    int lo = d.sRowPtr[ci], hi = d.sRowPtr[ci + 1];
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (d.sColIdx[mid] < cj) lo = mid + 1; else hi = mid; }
+    double* Sb = d.S + (size_t)lo * PP;
 #pragma unroll
-      for (int a = 0; a < L; ++a) v += Bi[r + P * a] * sDinv[w][a + L * bc];
-      sBD[w][lane] = v;
-    }
-    if (lane < P) {
-      double v = 0;
-#pragma unroll
-      for (int a = 0; a < L; ++a) v += Bi[lane + P * a] * sDinv[w][LL + a];
-      atomicAdd(d.bschur + (size_t)ci * P + lane, -v);
-    }
-    __syncwarp();
-    const int64_t off = pb + (int64_t)i * k - (int64_t)i * (i - 1) / 2 - i;
-    if (PP >= 32) {
-      // one pair per step: lane owns elements lane, lane+32, ... of the P x P block; its rows of B_i Dinv stay in registers
-      constexpr int NR = (PP + 31) / 32;
-      double bd[NR][L]; int cc[NR];
-#pragma unroll
-      for (int q = 0; q < NR; ++q) {
-        const int el = lane + 32 * q; const int r = el % P; cc[q] = el / P;
-#pragma unroll
-        for (int a = 0; a < L; ++a) bd[q][a] = (el < PP) ? sBD[w][r + P * a] : 0.0;
-      }
-      for (int j = i; j < k; ++j) {
-        const double* Bj = Hpl + (size_t)(base + j) * PLn;
-        double* Sb = d.S + (size_t)d.pairSlot[off + j] * PP;
-#pragma unroll
-        for (int q = 0; q < NR; ++q) {
-          const int el = lane + 32 * q;
-          if (el < PP) {
-            double v = 0;
-#pragma unroll
-            for (int a = 0; a < L; ++a) v += bd[q][a] * Bj[cc[q] + P * a];
-            atomicAdd(Sb + el, -v);
-          }
-        }
-      }
-    } else {
-      // small blocks: several pairs per step
-      constexpr int PPI = 32 / PP;
-      const int sub = lane / PP, el = lane - sub * PP, r = el % P, c = el / P;
-      if (sub < PPI) {
-        double bd[L];
-#pragma unroll
-        for (int a = 0; a < L; ++a) bd[a] = sBD[w][r + P * a];
-        for (int j = i + sub; j < k; j += PPI) {
-          const double* Bj = Hpl + (size_t)(base + j) * PLn;
-          double v = 0;
-#pragma unroll
-          for (int a = 0; a < L; ++a) v += bd[a] * Bj[c + P * a];
-          atomicAdd(d.S + (size_t)d.pairSlot[off + j] * PP + el, -v);
-        }
-      }
-    }
+    for (int q = 0; q < PP; ++q) atomicAdd(Sb + q, -acc[q]);
   }
 }
 
@@ -436,27 +475,37 @@ __global__ void __launch_bounds__(256) final_sum_kernel(const double* partial, i
 // launch wrappers
 // ------------------------------------------------------------------------------------------------
 void launchPairSlots(const SchurDev& d, cudaStream_t st, int64_t* launches) {
-  if (d.nItems == 0) return;
-  pair_slot_kernel<<<(d.nItems + 3) / 4, 128, 0, st>>>(d);
+  if (d.nPairs == 0) return;
+  pair_slot_kernel<<<(unsigned)((d.nPairs + 255) / 256), 256, 0, st>>>(d);
   *launches += 1;
 }
 
-template <int P, int L> static void schurPL(const SchurDev& d, const SystemDev& sys, double lambda, cudaStream_t st, int64_t* launches) {
+template <int P, int L> static void schurPL(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, double lambda, cudaStream_t st, int64_t* launches) {
   constexpr int PP = P * P;
   cudaMemsetAsync(d.S, 0, sizeof(double) * (size_t)d.nnzS * PP, st);
   const int64_t tot = max((int64_t)d.nnzHpp * PP, (int64_t)d.numPoses * P);
   schur_init_kernel<P><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d, sys.Hpp, sys.b, lambda);
   add_lambda_diag_kernel<P><<<(d.numPoses * P + 255) / 256, 256, 0, st>>>(d.S, d.sDiag, d.numPoses, lambda);
   *launches += 3;
-  if (d.nItems > 0) {
-    schur_landmark_kernel<P, L><<<(d.nItems + 3) / 4, 128, 0, st>>>(d, sys.Hll, sys.Hpl, sys.b, lambda);
+  if (d.numLandmarks > 0) { dinv_kernel<P, L><<<(d.numLandmarks + 255) / 256, 256, 0, st>>>(d, sys.Hll, sys.b, lambda); *launches += 1; }
+  if (nBlocks > 0) { coeff_kernel<P, L><<<(nBlocks + 127) / 128, 128, 0, st>>>(d, sys.Hpl, hplLm, nBlocks); *launches += 1; }
+  if (d.nPairs > 0) {
+    const int64_t warpsNeeded = d.nPairs; const int nb = (int)((warpsNeeded + 7) / 8 < 148 * 8 * 4 ? (warpsNeeded + 7) / 8 : 148 * 8 * 4);
+    schur_pairs_kernel<P, L><<<nb, 256, 0, st>>>(d, sys.Hpl, hplLm);
+    *launches += 1;
+  }
+  if (d.nTileChunks > 0) {
+    constexpr int kTileSmem = kTileBatch * (kTileCols * (P * L + 1) + kTileRows * P * L) * (int)sizeof(double);
+    static bool configured = false;
+    if (!configured) { cudaFuncSetAttribute(schur_tile_kernel<P, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem); configured = true; }
+    schur_tile_kernel<P, L><<<d.nTileChunks, kTileThreads, kTileSmem, st>>>(d, sys.Hpl);
     *launches += 1;
   }
 }
-void launchSchur(const SchurDev& d, const SystemDev& sys, double lambda, cudaStream_t st, int64_t* launches) {
-  if (d.P == 9 && d.L == 3) schurPL<9, 3>(d, sys, lambda, st, launches);
-  else if (d.P == 6 && d.L == 3) schurPL<6, 3>(d, sys, lambda, st, launches);
-  else if (d.P == 3 && d.L == 2) schurPL<3, 2>(d, sys, lambda, st, launches);
+void launchSchur(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, double lambda, cudaStream_t st, int64_t* launches) {
+  if (d.P == 9 && d.L == 3) schurPL<9, 3>(d, sys, hplLm, nBlocks, lambda, st, launches);
+  else if (d.P == 6 && d.L == 3) schurPL<6, 3>(d, sys, hplLm, nBlocks, lambda, st, launches);
+  else if (d.P == 3 && d.L == 2) schurPL<3, 2>(d, sys, hplLm, nBlocks, lambda, st, launches);
 }
 template <int P, int L> static void backsubPL(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, const double* xp, double* xl, cudaStream_t st, int64_t* launches) {
   cudaMemsetAsync(xl, 0, sizeof(double) * (size_t)d.numLandmarks * L, st);
