@@ -169,25 +169,28 @@ template <int P, int L> __global__ void __launch_bounds__(256) schur_pairs_kerne
 // is formed once per row.  Nothing is written to global memory until the end: one atomic add per block element per chunk, instead of one
 // per landmark pair (the per-pair atomics ran at ~1.4 elements/clk/SM and made this phase 20 ms on the Venice-shaped problem).
 constexpr int kTileBatch = 12;   // entries staged in shared memory per barrier pair
-constexpr int kTileThreads = kTileRows * 32;
+constexpr int kTileParts = 3;    // the P x P block of one (row camera, column camera) pair is split by columns over 3 warps
+constexpr int kTileWarps = kTileRows * kTileParts, kTileThreads = kTileWarps * 32;
 template <int P, int L> __global__ void __launch_bounds__(kTileThreads, 2) schur_tile_kernel(SchurDev d, const double* __restrict__ Hpl) {
-  constexpr int PP = P * P, PLn = P * L, LL = L * L, SB = PLn + 1;
+  constexpr int PP = P * P, PLn = P * L, LL = L * L, SB = PLn | 1, CW = P / kTileParts, NA = P * CW;   // odd row stride: conflict-free 64-bit shared loads
+  static_assert(P % kTileParts == 0, "block size must split into column parts");
   constexpr int ENT = kTileCols * SB + kTileRows * PLn;      // doubles of shared memory per staged entry
   extern __shared__ double smem[];
   __shared__ int sHdr[kTileBatch][5];                        // lm, baseI, baseJ, maskJ, maskI
-  const int chunk = blockIdx.x, tid = threadIdx.x, bi = tid >> 5, lane = tid & 31;
+  const int chunk = blockIdx.x, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const int bi = wid / kTileParts, part = wid - bi * kTileParts, c0 = part * CW;
   const int ci = d.chunkI[chunk] * kTileRows + bi, cj = d.chunkJ[chunk] * kTileCols + lane;
   const bool mine = ci < d.numPoses && cj < d.numPoses && cj >= ci;
-  double acc[PP];
+  double acc[NA];                                            // columns c0 .. c0+CW-1 of the block, all P rows
 #pragma unroll
-  for (int q = 0; q < PP; ++q) acc[q] = 0;
+  for (int q = 0; q < NA; ++q) acc[q] = 0;
   bool touched = false;
   const int eBegin = d.chunkBegin[chunk], eEnd = d.chunkEnd[chunk];
   for (int e0 = eBegin; e0 < eEnd; e0 += kTileBatch) {
     const int nb = min(kTileBatch, eEnd - e0);
     __syncthreads();
-    // stage: warp w copies entries w, w+8, ... of the batch (B_j blocks of the strip, W_i = B_i Dinv of the rows)
-    for (int eb = bi; eb < nb; eb += kTileRows) {
+    // stage: warp w copies entries w, w + kTileWarps, ... of the batch (B_j blocks of the strip, W_i = B_i Dinv of the rows)
+    for (int eb = wid; eb < nb; eb += kTileWarps) {
       const int e = e0 + eb;
       const int lm = d.entLm[e], baseI = d.entBaseI[e], baseJ = d.entBaseJ[e];
       const unsigned maskJ = d.entMaskJ[e], maskI = d.entMaskI[e];
@@ -214,14 +217,16 @@ template <int P, int L> __global__ void __launch_bounds__(kTileThreads, 2) schur
         touched = true;
         const double* sB = smem + (size_t)eb * ENT;
         const double* Wi = sB + kTileCols * SB + __popc(maskI & ((1u << bi) - 1u)) * PLn;
-        const double* Bj = sB + __popc(maskJ & ((1u << lane) - 1u)) * SB;
+        const double* Bj = sB + __popc(maskJ & ((1u << lane) - 1u)) * SB + c0;
 #pragma unroll
         for (int a = 0; a < L; ++a) {
-          double wv[P], bv[P];
+          double wv[P], bv[CW];
 #pragma unroll
-          for (int r = 0; r < P; ++r) { wv[r] = Wi[r + P * a]; bv[r] = Bj[r + P * a]; }
+          for (int r = 0; r < P; ++r) wv[r] = Wi[r + P * a];
 #pragma unroll
-          for (int c = 0; c < P; ++c)
+          for (int c = 0; c < CW; ++c) bv[c] = Bj[c + P * a];
+#pragma unroll
+          for (int c = 0; c < CW; ++c)
 #pragma unroll
             for (int r = 0; r < P; ++r) acc[r + P * c] += wv[r] * bv[c];
         }
@@ -231,9 +236,9 @@ template <int P, int L> __global__ void __launch_bounds__(kTileThreads, 2) schur
   if (touched) {
     int lo = d.sRowPtr[ci], hi = d.sRowPtr[ci + 1];
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (d.sColIdx[mid] < cj) lo = mid + 1; else hi = mid; }
-    double* Sb = d.S + (size_t)lo * PP;
+    double* Sb = d.S + (size_t)lo * PP + (size_t)c0 * P;
 #pragma unroll
-    for (int q = 0; q < PP; ++q) atomicAdd(Sb + q, -acc[q]);
+    for (int q = 0; q < NA; ++q) atomicAdd(Sb + q, -acc[q]);
   }
 }
 
@@ -495,7 +500,7 @@ template <int P, int L> static void schurPL(const SchurDev& d, const SystemDev& 
     *launches += 1;
   }
   if (d.nTileChunks > 0) {
-    constexpr int kTileSmem = kTileBatch * (kTileCols * (P * L + 1) + kTileRows * P * L) * (int)sizeof(double);
+    constexpr int kTileSmem = kTileBatch * (kTileCols * ((P * L) | 1) + kTileRows * P * L) * (int)sizeof(double);
     static bool configured = false;
     if (!configured) { cudaFuncSetAttribute(schur_tile_kernel<P, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem); configured = true; }
     schur_tile_kernel<P, L><<<d.nTileChunks, kTileThreads, kTileSmem, st>>>(d, sys.Hpl);
