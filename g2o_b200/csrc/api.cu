@@ -168,6 +168,12 @@ int uploadEstimates(g2ocu_solver* s) {
 // device estimates -> host graph copy (the host copy is what a rebuild uploads again)
 int downloadEstimates(g2ocu_solver* s) {
   const Structure& st = s->st; HostGraph& g = s->g;
+  if (s->world > 1 && st.numLandmarks > 0) {   // zero the landmarks owned by other ranks and sum: afterwards every rank holds all of them
+    const int Sl = vertexEstimateDim(st.lmType);
+    if (st.lmBegin > 0) CU(cudaMemsetAsync(s->lmEst.p, 0, sizeof(double) * (size_t)st.lmBegin * Sl, s->stream));
+    if (st.lmEnd < st.numLandmarks) CU(cudaMemsetAsync(s->lmEst.p + (size_t)st.lmEnd * Sl, 0, sizeof(double) * (size_t)(st.numLandmarks - st.lmEnd) * Sl, s->stream));
+    int rc = allreduceDev(s, s->lmEst.p, (int64_t)st.numLandmarks * Sl, 0); if (rc) return rc;
+  }
   std::vector<double> hp(s->poseEst.n), hl(s->lmEst.n);
   if (hp.size()) CU(cudaMemcpyAsync(hp.data(), s->poseEst.p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   if (hl.size()) CU(cudaMemcpyAsync(hl.data(), s->lmEst.p, hl.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -201,8 +207,9 @@ int buildDevice(g2ocu_solver* s) {
   } else { sys.Hll = nullptr; sys.Hpl = nullptr; }
 
   // ---- edge sets ----
-  size_t maxScratch = 2400;
+  size_t maxScratch = 4096;
   for (const EdgeSet& hs : st.sets) {
+    if (hs.pos.empty()) continue;                 // sharded run: this rank owns no edge of the type
     auto* es = new EdgeSetState; s->sets.push_back(es);
     const int n = (int)hs.pos.size(); const int t = hs.etype;
     const int E = edgeDim(t), M = edgeMeasDim(t), NP = edgeParamDim(t);
@@ -263,7 +270,7 @@ int buildDevice(g2ocu_solver* s) {
     struct TileEntry { int64_t key; int32_t lm, baseI, baseJ; uint32_t maskJ; uint8_t maskI; };
     std::vector<TileEntry> entries;
     std::vector<int32_t> shortLm;
-    for (int l = 0; l < st.numLandmarks; ++l) {
+    for (int l = st.lmBegin; l < st.lmEnd; ++l) {   // owned landmarks only
       const int cb = st.hplColPtr[l]; const int64_t k = st.hplColPtr[l + 1] - cb;
       if (k == 0) continue;
       if (k < kTileMinTrack) { shortLm.push_back(l); continue; }
@@ -310,6 +317,7 @@ int buildDevice(g2ocu_solver* s) {
     }
     CU(s->S.alloc((size_t)st.sColIdx.size() * P * P)); CU(s->Dinv.alloc((size_t)st.numLandmarks * L * L)); CU(s->dbv.alloc((size_t)st.numLandmarks * L)); CU(s->bschur.alloc((size_t)st.sizePoses));
     sd.numPoses = st.numPoses; sd.numLandmarks = st.numLandmarks; sd.P = P; sd.L = L;
+    sd.lmBegin = st.lmBegin; sd.lmEnd = st.lmEnd; sd.blockBegin = st.hplColPtr[st.lmBegin];
     sd.hplColPtr = s->hplColPtr.p; sd.hplRowIdx = s->hplRowIdx.p; sd.sRowPtr = s->sRowPtr.p; sd.sColIdx = s->sColIdx.p; sd.sDiag = s->sDiag.p;
     sd.hppToS = s->hppToS.p; sd.nnzHpp = (int)st.hppColIdx.size(); sd.nnzS = (int)st.sColIdx.size();
     sd.S = s->S.p; sd.Dinv = s->Dinv.p; sd.db = s->dbv.p; sd.bschur = s->bschur.p;
@@ -409,15 +417,19 @@ int solveSystem(g2ocu_solver* s, int* solved) {
     return solvePcg(s, s->b.p);
   }
   { PhaseTimer pt(s, "schur");
-    launchSchur(s->schur, s->sys, s->hplLm.p, (int)s->st.hplRowIdx.size(), s->lambda, s->stream, &s->launches);
+    launchSchur(s->schur, s->sys, s->hplLm.p, st.hplColPtr[st.lmEnd] - st.hplColPtr[st.lmBegin], s->lambda, s->rank == 0 ? s->lambda : 0.0, s->stream, &s->launches);
     if (s->world > 1) {
       int rc = allreduceDev(s, s->S.p, (int64_t)s->S.n, 0); if (rc) return rc;
       rc = allreduceDev(s, s->bschur.p, (int64_t)s->bschur.n, 0); if (rc) return rc;
     } }
   { PhaseTimer pt(s, "linear_solver");
-    int rc = solvePcg(s, s->bschur.p); if (rc) return rc; }
+    int rc = solvePcg(s, s->bschur.p); if (rc) return rc;
+    if (s->world > 1) {   // the reduced system is solved redundantly; rank 0's solution is broadcast so that the replicated cameras stay bitwise identical
+      if (s->rank != 0) CU(cudaMemsetAsync(s->x.p, 0, sizeof(double) * (size_t)st.sizePoses, s->stream));
+      rc = allreduceDev(s, s->x.p, st.sizePoses, 0); if (rc) return rc;
+    } }
   { PhaseTimer pt(s, "backsub");
-    launchBacksub(s->schur, s->sys, s->hplLm.p, (int)st.hplRowIdx.size(), s->x.p, s->x.p + st.sizePoses, s->stream, &s->launches); }
+    launchBacksub(s->schur, s->sys, s->hplLm.p, st.hplColPtr[st.lmEnd] - st.hplColPtr[st.lmBegin], s->x.p, s->x.p + st.sizePoses, s->stream, &s->launches); }
   CU(cudaGetLastError());
   return G2OCU_OK;
 }
@@ -426,7 +438,7 @@ int applyUpdate(g2ocu_solver* s) {
   PhaseTimer pt(s, "update");
   const Structure& st = s->st;
   launchUpdate(st.poseType, s->poseEst.p, nullptr, s->poseCounters.p, s->x.p, st.numPoses, s->stream, &s->launches);
-  if (st.numLandmarks) launchUpdate(st.lmType, s->lmEst.p, nullptr, nullptr, s->x.p + st.sizePoses, st.numLandmarks, s->stream, &s->launches);
+  if (st.lmEnd > st.lmBegin) launchUpdate(st.lmType, s->lmEst.p + (size_t)st.lmBegin * vertexEstimateDim(st.lmType), nullptr, nullptr, s->x.p + st.sizePoses + (size_t)st.lmBegin * st.L, st.lmEnd - st.lmBegin, s->stream, &s->launches);
   s->errorsValid = false;
   CU(cudaGetLastError());
   return G2OCU_OK;
@@ -455,20 +467,38 @@ int popEstimates(g2ocu_solver* s, bool restore) {
 
 int lambdaInit(g2ocu_solver* s, double* out) {
   if (s->userLambdaInit > 0) { *out = s->userLambdaInit; return G2OCU_OK; }
-  if (s->world > 1) {   // the pose diagonals are partial sums on each rank
-    return fail(s, G2OCU_E_UNSUPPORTED, "computeLambdaInit with world > 1 requires initialLambda");
+  const double* poseDiag = nullptr;
+  if (s->world > 1) {   // the pose diagonals are partial sums on each rank: reduce them first, then max over ranks
+    launchExtractPoseDiag(s->sys, s->vq.p, s->stream, &s->launches);
+    int rc = allreduceDev(s, s->vq.p, s->st.sizePoses, 0); if (rc) return rc;
+    poseDiag = s->vq.p;
   }
-  launchMaxDiag(s->sys, s->scratch.p, s->out2.p + 4, s->stream, &s->launches);
+  launchMaxDiag(s->sys, poseDiag, s->st.lmBegin, s->st.lmEnd, s->out2.p + 4, s->stream, &s->launches);
+  { int rc = allreduceDev(s, s->out2.p + 4, 1, 1); if (rc) return rc; }
   CU(cudaMemcpyAsync(s->hostScal + 4, s->out2.p + 4, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   int rc = syncStream(s); if (rc) return rc;
   *out = s->tau * s->hostScal[4];
   return G2OCU_OK;
 }
+// sum_j x_j (lambda x_j + b_j) -> hostScal[5] + hostScal[6] after the next stream sync.
+// Sharded: b_p is a partial sum (adds up over ranks), lambda x_p^2 is counted on rank 0 only, landmarks are owned.
+int enqueueScale(g2ocu_solver* s, double lambda) {
+  const Structure& st = s->st;
+  CU(cudaMemsetAsync(s->out2.p + 5, 0, 2 * sizeof(double), s->stream));
+  if (s->world <= 1) launchScale(s->x.p, s->b.p, (int64_t)s->x.n, lambda, s->scratch.p, s->out2.p + 5, s->stream, &s->launches);
+  else {
+    launchScale(s->x.p, s->b.p, (int64_t)st.sizePoses, s->rank == 0 ? lambda : 0.0, s->scratch.p, s->out2.p + 5, s->stream, &s->launches);
+    const size_t o = (size_t)st.sizePoses + (size_t)st.lmBegin * st.L;
+    if (st.lmEnd > st.lmBegin) launchScale(s->x.p + o, s->b.p + o, (int64_t)(st.lmEnd - st.lmBegin) * st.L, lambda, s->scratch.p + 2048, s->out2.p + 6, s->stream, &s->launches);
+    int rc = allreduceDev(s, s->out2.p + 5, 2, 0); if (rc) return rc;
+  }
+  CU(cudaMemcpyAsync(s->hostScal + 5, s->out2.p + 5, 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  return G2OCU_OK;
+}
 int computeScale(g2ocu_solver* s, double lambda, double* out) {
-  launchScale(s->x.p, s->b.p, (int64_t)s->x.n, lambda, s->scratch.p, s->out2.p + 5, s->stream, &s->launches);
-  CU(cudaMemcpyAsync(s->hostScal + 5, s->out2.p + 5, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  int rc0 = enqueueScale(s, lambda); if (rc0) return rc0;
   int rc = syncStream(s); if (rc) return rc;
-  *out = s->hostScal[5];
+  *out = s->hostScal[5] + s->hostScal[6];
   return G2OCU_OK;
 }
 
@@ -491,10 +521,9 @@ int solveLevenberg(g2ocu_solver* s, int iteration, int* result) {
     s->lambda = 0.0;                                   // restoreDiagonal
     rc = computeErrors(s, nullptr, nullptr); if (rc) return rc;
     double scale = 0;
-    launchScale(s->x.p, s->b.p, (int64_t)s->x.n, s->currentLambda, s->scratch.p, s->out2.p + 5, s->stream, &s->launches);
-    CU(cudaMemcpyAsync(s->hostScal + 5, s->out2.p + 5, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    rc = enqueueScale(s, s->currentLambda); if (rc) return rc;
     rc = finishErrors(s); if (rc) return rc;
-    scale = s->hostScal[5];
+    scale = s->hostScal[5] + s->hostScal[6];
     tempChi = s->chi2Robust;
     if (!ok2) tempChi = std::numeric_limits<double>::max();
     rho = (currentChi - tempChi);
@@ -607,7 +636,7 @@ int g2ocu_build_structure(g2ocu_solver* s) {
   std::string err;
   if (s->structureBuilt) { int rc0 = downloadEstimates(s); if (rc0) return rc0; }   // vertices keep their state across optimize() calls
   s->structureBuilt = false;
-  if (!buildStructure(s->g, s->st, err)) return fail(s, G2OCU_E_UNSUPPORTED, err);
+  if (!buildStructure(s->g, s->st, err, s->rank, s->world)) return fail(s, G2OCU_E_UNSUPPORTED, err);
   const Structure& st = s->st;
   const bool okDims = (st.doSchur && ((st.P == 9 && st.L == 3) || (st.P == 6 && st.L == 3) || (st.P == 3 && st.L == 2))) || (!st.doSchur && (st.P == 3 || st.P == 6 || st.P == 9));
   if (!okDims) return fail(s, G2OCU_E_UNSUPPORTED, "unsupported block sizes P=" + std::to_string(st.P) + " L=" + std::to_string(st.L));
@@ -767,6 +796,8 @@ int64_t g2ocu_get_i32(g2ocu_solver* s, const char* name, int32_t* out, int64_t c
   if (n == "hschur_t_colptr") return copyOutI32(st.sRowPtr, out, cap);
   if (n == "hschur_t_rowidx") return copyOutI32(st.sColIdx, out, cap);
   if (n == "edge_targets") return copyOutI32(st.edgeTargets, out, cap);
+  if (n == "shard_landmark_range") return copyOutI32({st.lmBegin, st.lmEnd}, out, cap);
+  if (n == "shard_edge_positions") { std::vector<int32_t> v; for (const EdgeSet& es : st.sets) v.insert(v.end(), es.pos.begin(), es.pos.end()); return copyOutI32(v, out, cap); }
   return fail(s, G2OCU_E_INVALID, "unknown int32 array " + n);
 }
 

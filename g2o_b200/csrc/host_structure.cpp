@@ -90,7 +90,7 @@ bool initializeOptimization(const HostGraph& g, int level, Structure& st, std::s
 
 template <class T> static void sortUnique(std::vector<T>& v) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
 
-bool buildStructure(const HostGraph& g, Structure& st, std::string& err) {
+bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int rank, int world) {
   if (st.ivMap.empty()) { err = "0 vertices to optimize, maybe forgot to call initializeOptimization()"; return false; }
   // Schur iff any active vertex is marginalized (optimization_algorithm_with_hessian.cpp:48-66)
   st.doSchur = false;
@@ -245,6 +245,19 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err) {
     st.sRowPtr.clear(); st.sColIdx.clear(); st.sColPtr.clear(); st.sRowIdx.clear(); st.sCcsToCsr.clear(); st.sDiag.clear(); st.hppToS.clear();
   }
 
+  // ---- landmark ownership for sharded runs: contiguous slot ranges balanced by the number of Hpl blocks ----
+  st.lmBegin = 0; st.lmEnd = st.numLandmarks;
+  if (world > 1 && st.doSchur) {
+    const int64_t total = st.hplColPtr.empty() ? 0 : st.hplColPtr[st.numLandmarks];
+    auto splitAt = [&](int r) -> int {
+      if (r <= 0) return 0;
+      if (r >= world) return st.numLandmarks;
+      const int64_t target = total * r / world;
+      return (int)(std::lower_bound(st.hplColPtr.begin(), st.hplColPtr.end(), (int32_t)target) - st.hplColPtr.begin());
+    };
+    st.lmBegin = std::min(splitAt(rank), st.numLandmarks); st.lmEnd = std::min(splitAt(rank + 1), st.numLandmarks);
+    if (rank == world - 1) st.lmEnd = st.numLandmarks;
+  }
   // ---- edge sets in kernel order ----
   st.sets.clear();
   std::vector<int> setOfType(8, -1);
@@ -254,11 +267,23 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err) {
     st.sets[setOfType[t]].pos.push_back(k);
   }
   for (auto& s : st.sets) {
-    const int n = (int)s.pos.size();
+    int n = (int)s.pos.size();
     int e0 = st.activeEdges[s.pos[0]];
     int c0 = st.classOf[g.eV0[e0]], c1 = st.classOf[g.eV1[e0]];
     s.poseLandmark = (c0 != c1); s.poseSide = (c0 == 0) ? 0 : 1;
     if (c0 == 1 && c1 == 1) { err = "edge between two marginalized vertices is not supported"; return false; }
+    if (world > 1) {   // this rank's share: edges of owned landmarks (fixed landmarks: rank 0); pose-pose edges split evenly
+      std::vector<int32_t> keep;
+      for (int i = 0; i < n; ++i) {
+        const int e = st.activeEdges[s.pos[i]];
+        bool mine;
+        if (s.poseLandmark) { const int vl = s.poseSide == 0 ? g.eV1[e] : g.eV0[e]; const int sl = st.slotOf[vl]; mine = sl < st.numLandmarks ? (sl >= st.lmBegin && sl < st.lmEnd) : rank == 0; }
+        else mine = i >= (int64_t)n * rank / world && i < (int64_t)n * (rank + 1) / world;
+        if (mine) keep.push_back(s.pos[i]);
+      }
+      s.pos.swap(keep);
+      n = (int)s.pos.size();
+    }
     if (s.poseLandmark) {
       std::vector<int64_t> keyv(n);
       std::vector<int32_t> ord(n);

@@ -66,11 +66,12 @@ struct Structure {
   std::vector<int32_t> edgeTargets;
   std::vector<EdgeSet> sets;
   int64_t schurPairs = 0;                // sum over landmarks of k(k+1)/2
+  int lmBegin = 0, lmEnd = 0;            // landmark slots owned by this rank (all of them when world == 1)
 };
 
 static const int kChunk = 1024;          // edges per chunk of the pose-sorted accumulation pass
 
 bool initializeOptimization(const HostGraph& g, int level, Structure& st, std::string& err);
-bool buildStructure(const HostGraph& g, Structure& st, std::string& err);
+bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int rank = 0, int world = 1);
 
 }  // namespace g2ocu

@@ -53,6 +53,7 @@ int errorScratchDoubles(int n);
 // ---- linear algebra kernels (kernels_linear.cu) ----
 struct SchurDev {
   int numPoses = 0, numLandmarks = 0, P = 0, L = 0;
+  int lmBegin = 0, lmEnd = 0, blockBegin = 0;     // landmark slots / first Hpl block owned by this rank
   const int32_t* hplColPtr = nullptr; const int32_t* hplRowIdx = nullptr;
   const int32_t* sRowPtr = nullptr; const int32_t* sColIdx = nullptr; const int32_t* sDiag = nullptr;
   const int32_t* hppToS = nullptr; int nnzHpp = 0; int nnzS = 0;
@@ -67,7 +68,7 @@ struct SchurDev {
 static const int kTileRows = 4, kTileCols = 32;   // cameras per tile row group / column strip
 static const int kTileMinTrack = 8;               // landmarks with at least this many observations go through the tile kernel
 void launchPairSlots(const SchurDev& d, cudaStream_t st, int64_t* launches);
-void launchSchur(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, double lambda, cudaStream_t st, int64_t* launches);
+void launchSchur(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, double lambda, double lambdaDiag, cudaStream_t st, int64_t* launches);
 void launchBacksub(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, const double* xp, double* xl, cudaStream_t st, int64_t* launches);
 
 struct PcgDev {
@@ -87,7 +88,8 @@ void launchPcgInit(const PcgDev& p, const double* b, double tolerance, double re
 void launchPcgTail(const PcgDev& p, cudaStream_t st, int64_t* launches);   // after q = A d: dot, x/r/s update, d update, commit (no-ops once converged)
 void launchSpmv(const PcgDev& p, const double* src, double* dst, cudaStream_t st, int64_t* launches);   // dst = (A + lambda I) src, symmetric upper
 
-void launchMaxDiag(const SystemDev& sys, double* scratch, double* out, cudaStream_t st, int64_t* launches);
+void launchExtractPoseDiag(const SystemDev& sys, double* out, cudaStream_t st, int64_t* launches);
+void launchMaxDiag(const SystemDev& sys, const double* poseDiag, int lmBegin, int lmEnd, double* out, cudaStream_t st, int64_t* launches);
 void launchScale(const double* x, const double* b, int64_t n, double lambda, double* scratch, double* out, cudaStream_t st, int64_t* launches);
 
 // dense FP64 Cholesky path (kernels_dense.cu)

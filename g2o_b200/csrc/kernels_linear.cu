@@ -94,8 +94,8 @@ template <int P> __global__ void add_lambda_diag_kernel(double* A, const int32_t
 // Dinv_l = (Hll_l + lambda I)^-1 and db_l = Dinv_l b_l, thread per landmark (block_solver.hpp:347-356)
 template <int P, int L> __global__ void dinv_kernel(SchurDev d, const double* __restrict__ Hll, const double* __restrict__ b, double lambda) {
   constexpr int LL = L * L;
-  const int lm = blockIdx.x * blockDim.x + threadIdx.x;
-  if (lm >= d.numLandmarks) return;
+  const int lm = d.lmBegin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (lm >= d.lmEnd) return;
   double H[LL], X[LL], bl[L];
 #pragma unroll
   for (int q = 0; q < LL; ++q) H[q] = Hll[(size_t)lm * LL + q];
@@ -115,8 +115,8 @@ template <int P, int L> __global__ void dinv_kernel(SchurDev d, const double* __
 template <int P, int L> __global__ void __launch_bounds__(128) coeff_kernel(SchurDev d, const double* __restrict__ Hpl, const int32_t* __restrict__ hplLm, int nBlocks) {
   constexpr int PLn = P * L;
   __shared__ double sB[128 * PLn];
-  const int tid = threadIdx.x, k0 = blockIdx.x * 128;
-  const int nb = min(128, nBlocks - k0);
+  const int tid = threadIdx.x, k0 = d.blockBegin + blockIdx.x * 128;
+  const int nb = min(128, d.blockBegin + nBlocks - k0);
   const double* src = Hpl + (size_t)k0 * PLn;
   for (int t = tid; t < nb * PLn; t += 128) sB[t] = src[t];
   __syncthreads();
@@ -251,8 +251,8 @@ template <int P, int L> __global__ void __launch_bounds__(128) backsub_accum_ker
   __shared__ double sB[128 * PLn];
   __shared__ double sV[128 * L];
   __shared__ int sLm[128];
-  const int tid = threadIdx.x, k0 = blockIdx.x * 128;
-  const int nb = min(128, nBlocks - k0);
+  const int tid = threadIdx.x, k0 = d.blockBegin + blockIdx.x * 128;
+  const int nb = min(128, d.blockBegin + nBlocks - k0);
   const double* src = Hpl + (size_t)k0 * PLn;
   for (int t = tid; t < nb * PLn; t += 128) sB[t] = src[t];
   __syncthreads();
@@ -286,8 +286,8 @@ template <int P, int L> __global__ void __launch_bounds__(128) backsub_accum_ker
 // pass 2: x_l = Dinv (b_l - acc_l)
 template <int P, int L> __global__ void backsub_finish_kernel(SchurDev d, const double* __restrict__ b, double* __restrict__ xl) {
   constexpr int LL = L * L;
-  const int lm = blockIdx.x * blockDim.x + threadIdx.x;
-  if (lm >= d.numLandmarks) return;
+  const int lm = d.lmBegin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (lm >= d.lmEnd) return;
   double c[L];
 #pragma unroll
   for (int q = 0; q < L; ++q) c[q] = b[(size_t)d.numPoses * P + (size_t)lm * L + q] - xl[(size_t)lm * L + q];
@@ -450,12 +450,19 @@ __global__ void pcg_commit_kernel(PcgDev p) {
 }
 
 // computeLambdaInit: max |H_vv(j,j)| over pose and landmark diagonal blocks (levenberg.cpp:152-175)
-__global__ void __launch_bounds__(1024) maxdiag_kernel(SystemDev sys, double* out) {
+// poseDiag (optional): the pose diagonals already summed over all ranks; landmarks: the owned range only
+__global__ void extract_pose_diag_kernel(SystemDev sys, double* out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, P = sys.P;
+  if (t >= sys.numPoses * P) return;
+  const int i = t / P, k = t - i * P;
+  out[t] = sys.Hpp[(size_t)sys.hppDiag[i] * P * P + k * (P + 1)];
+}
+__global__ void __launch_bounds__(1024) maxdiag_kernel(SystemDev sys, const double* poseDiag, int lmBegin, int lmEnd, double* out) {
   __shared__ double sm[32];
   double m = 0;
   const int P = sys.P, L = sys.L;
-  for (int t = threadIdx.x; t < sys.numPoses * P; t += 1024) { const int i = t / P, k = t - i * P; m = fmax(m, fabs(sys.Hpp[(size_t)sys.hppDiag[i] * P * P + k * (P + 1)])); }
-  for (int64_t t = threadIdx.x; t < (int64_t)sys.numLandmarks * L; t += 1024) { const int64_t i = t / L; const int k = (int)(t - i * L); m = fmax(m, fabs(sys.Hll[(size_t)i * L * L + k * (L + 1)])); }
+  for (int t = threadIdx.x; t < sys.numPoses * P; t += 1024) { const int i = t / P, k = t - i * P; m = fmax(m, fabs(poseDiag ? poseDiag[t] : sys.Hpp[(size_t)sys.hppDiag[i] * P * P + k * (P + 1)])); }
+  for (int64_t t = (int64_t)lmBegin * L + threadIdx.x; t < (int64_t)lmEnd * L; t += 1024) { const int64_t i = t / L; const int k = (int)(t - i * L); m = fmax(m, fabs(sys.Hll[(size_t)i * L * L + k * (L + 1)])); }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
@@ -485,14 +492,14 @@ void launchPairSlots(const SchurDev& d, cudaStream_t st, int64_t* launches) {
   *launches += 1;
 }
 
-template <int P, int L> static void schurPL(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, double lambda, cudaStream_t st, int64_t* launches) {
+template <int P, int L> static void schurPL(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, double lambda, double lambdaDiag, cudaStream_t st, int64_t* launches) {
   constexpr int PP = P * P;
   cudaMemsetAsync(d.S, 0, sizeof(double) * (size_t)d.nnzS * PP, st);
   const int64_t tot = max((int64_t)d.nnzHpp * PP, (int64_t)d.numPoses * P);
   schur_init_kernel<P><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d, sys.Hpp, sys.b, lambda);
-  add_lambda_diag_kernel<P><<<(d.numPoses * P + 255) / 256, 256, 0, st>>>(d.S, d.sDiag, d.numPoses, lambda);
+  add_lambda_diag_kernel<P><<<(d.numPoses * P + 255) / 256, 256, 0, st>>>(d.S, d.sDiag, d.numPoses, lambdaDiag);
   *launches += 3;
-  if (d.numLandmarks > 0) { dinv_kernel<P, L><<<(d.numLandmarks + 255) / 256, 256, 0, st>>>(d, sys.Hll, sys.b, lambda); *launches += 1; }
+  if (d.lmEnd > d.lmBegin) { dinv_kernel<P, L><<<(d.lmEnd - d.lmBegin + 255) / 256, 256, 0, st>>>(d, sys.Hll, sys.b, lambda); *launches += 1; }
   if (nBlocks > 0) { coeff_kernel<P, L><<<(nBlocks + 127) / 128, 128, 0, st>>>(d, sys.Hpl, hplLm, nBlocks); *launches += 1; }
   if (d.nPairs > 0) {
     const int64_t warpsNeeded = d.nPairs; const int nb = (int)((warpsNeeded + 7) / 8 < 148 * 8 * 4 ? (warpsNeeded + 7) / 8 : 148 * 8 * 4);
@@ -507,15 +514,15 @@ template <int P, int L> static void schurPL(const SchurDev& d, const SystemDev& 
     *launches += 1;
   }
 }
-void launchSchur(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, double lambda, cudaStream_t st, int64_t* launches) {
-  if (d.P == 9 && d.L == 3) schurPL<9, 3>(d, sys, hplLm, nBlocks, lambda, st, launches);
-  else if (d.P == 6 && d.L == 3) schurPL<6, 3>(d, sys, hplLm, nBlocks, lambda, st, launches);
-  else if (d.P == 3 && d.L == 2) schurPL<3, 2>(d, sys, hplLm, nBlocks, lambda, st, launches);
+void launchSchur(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, double lambda, double lambdaDiag, cudaStream_t st, int64_t* launches) {
+  if (d.P == 9 && d.L == 3) schurPL<9, 3>(d, sys, hplLm, nBlocks, lambda, lambdaDiag, st, launches);
+  else if (d.P == 6 && d.L == 3) schurPL<6, 3>(d, sys, hplLm, nBlocks, lambda, lambdaDiag, st, launches);
+  else if (d.P == 3 && d.L == 2) schurPL<3, 2>(d, sys, hplLm, nBlocks, lambda, lambdaDiag, st, launches);
 }
 template <int P, int L> static void backsubPL(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, const double* xp, double* xl, cudaStream_t st, int64_t* launches) {
   cudaMemsetAsync(xl, 0, sizeof(double) * (size_t)d.numLandmarks * L, st);
   if (nBlocks > 0) { backsub_accum_kernel<P, L><<<(nBlocks + 127) / 128, 128, 0, st>>>(d, sys.Hpl, hplLm, nBlocks, xp, xl); *launches += 1; }
-  backsub_finish_kernel<P, L><<<(d.numLandmarks + 255) / 256, 256, 0, st>>>(d, sys.b, xl);
+  if (d.lmEnd > d.lmBegin) backsub_finish_kernel<P, L><<<(d.lmEnd - d.lmBegin + 255) / 256, 256, 0, st>>>(d, sys.b, xl);
   *launches += 2;
 }
 void launchBacksub(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, const double* xp, double* xl, cudaStream_t st, int64_t* launches) {
@@ -560,8 +567,12 @@ void launchPcgTail(const PcgDev& p, cudaStream_t st, int64_t* launches) {
   *launches += 4;
 }
 
-void launchMaxDiag(const SystemDev& sys, double*, double* out, cudaStream_t st, int64_t* launches) {
-  maxdiag_kernel<<<1, 1024, 0, st>>>(sys, out);
+void launchExtractPoseDiag(const SystemDev& sys, double* out, cudaStream_t st, int64_t* launches) {
+  extract_pose_diag_kernel<<<(sys.numPoses * sys.P + 255) / 256, 256, 0, st>>>(sys, out);
+  *launches += 1;
+}
+void launchMaxDiag(const SystemDev& sys, const double* poseDiag, int lmBegin, int lmEnd, double* out, cudaStream_t st, int64_t* launches) {
+  maxdiag_kernel<<<1, 1024, 0, st>>>(sys, poseDiag, lmBegin, lmEnd, out);
   *launches += 1;
 }
 void launchScale(const double* x, const double* b, int64_t n, double lambda, double* scratch, double* out, cudaStream_t st, int64_t* launches) {

@@ -1,0 +1,44 @@
+"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` carries the collectives of the landmark-sharded
+solve (the reduced camera system and its right-hand side once per LM trial, three scalars per chi2 / scale evaluation,
+the replicated camera step).  The C ABI only sees a function pointer (``g2ocu_allreduce_fn``)."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+
+class _DevicePointer:
+    """Exposes a raw device pointer through ``__cuda_array_interface__`` so torch can wrap it without a copy."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2, "strides": None}
+
+
+def make_allreduce(backend_is_cuda: bool = True, group=None):
+    """Returns ``fn(ptr, count, op, stream) -> int`` for :meth:`CudaSolver.set_shard`.  ``op`` 0 = sum, 1 = max.
+    With a CUDA backend the collective is enqueued in stream order on the solver's stream (no host synchronisation);
+    with gloo (CPU tests) ``ptr`` is a host pointer."""
+    import torch
+    import torch.distributed as dist
+
+    def fn(ptr, count, op, stream):
+        rop = dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MAX
+        if backend_is_cuda:
+            t = torch.as_tensor(_DevicePointer(ptr, count), device="cuda")
+            ext = torch.cuda.ExternalStream(stream) if stream else torch.cuda.current_stream()
+            with torch.cuda.stream(ext):
+                dist.all_reduce(t, op=rop, group=group)
+        else:
+            buf = (ctypes.c_double * count).from_address(ptr)
+            a = np.frombuffer(buf, dtype=np.float64)
+            t = torch.from_numpy(a)
+            dist.all_reduce(t, op=rop, group=group)
+        return 0
+    return fn
+
+
+def install_torch_allreduce(solver, rank: int, world: int, group=None):
+    import torch.distributed as dist
+    cuda = dist.get_backend(group) == "nccl"
+    solver.set_shard(rank, world, make_allreduce(cuda, group))

@@ -190,7 +190,7 @@ int g2ocu_get_estimates(g2ocu_solver* s, double* host_packed);
  * Returns the number of elements the array has (and fills at most `capacity` of them), or a negative status.
  * int32: "hessian_index" "active_vertices" "active_edges" "index_mapping" "dims" "pose_block_indices"
  *        "landmark_block_indices" "hpp_colptr" "hpp_rowidx" "hpl_colptr" "hpl_rowidx" "hschur_colptr" "hschur_rowidx"
- *        "hschur_t_colptr" "hschur_t_rowidx" "edge_targets"
+ *        "hschur_t_colptr" "hschur_t_rowidx" "edge_targets" "shard_landmark_range" "shard_edge_positions"
  * double: "x" "b" "bschur" "hpp_values" "hpl_values" "hll_values" "hschur_values" "errors" "jacobians" "estimates" */
 int64_t g2ocu_get_i32(g2ocu_solver* s, const char* name, int32_t* out, int64_t capacity);
 int64_t g2ocu_get_f64(g2ocu_solver* s, const char* name, double* out, int64_t capacity);
