@@ -378,6 +378,10 @@ int buildSystem(g2ocu_solver* s) {
   if (s->st.doSchur) { CU(s->Hll.zero(s->stream)); if (s->st.hplShared) CU(s->Hpl.zero(s->stream)); }
   for (auto* es : s->sets) launchBuild(es->dev, s->sys, s->stream, &s->launches);
   CU(cudaGetLastError());
+  if (s->world > 1 && !s->st.doSchur) {   // pose graphs are sharded by edge: every rank needs the full Hpp and b for the replicated solve
+    int rc = allreduceDev(s, s->Hpp.p, (int64_t)s->Hpp.n, 0); if (rc) return rc;
+    rc = allreduceDev(s, s->b.p, (int64_t)s->b.n, 0); if (rc) return rc;
+  }
   return G2OCU_OK;
 }
 
@@ -412,9 +416,15 @@ int solveSystem(g2ocu_solver* s, int* solved) {
   const Structure& st = s->st;
   *solved = 1;
   if (s->cfg.linear_solver != G2OCU_LINEAR_PCG) return fail(s, G2OCU_E_UNSUPPORTED, "dense Cholesky linear solver is not available in this build");
+  auto broadcastPoseStep = [&]() -> int {   // the pose system is solved redundantly on every rank; rank 0's solution wins so that replicas stay bitwise identical
+    if (s->world <= 1) return G2OCU_OK;
+    if (s->rank != 0) CU(cudaMemsetAsync(s->x.p, 0, sizeof(double) * (size_t)st.sizePoses, s->stream));
+    return allreduceDev(s, s->x.p, st.sizePoses, 0);
+  };
   if (!st.doSchur) {
     PhaseTimer pt(s, "linear_solver");
-    return solvePcg(s, s->b.p);
+    int rc = solvePcg(s, s->b.p); if (rc) return rc;
+    return broadcastPoseStep();
   }
   { PhaseTimer pt(s, "schur");
     launchSchur(s->schur, s->sys, s->hplLm.p, st.hplColPtr[st.lmEnd] - st.hplColPtr[st.lmBegin], s->lambda, s->rank == 0 ? s->lambda : 0.0, s->stream, &s->launches);
@@ -424,10 +434,7 @@ int solveSystem(g2ocu_solver* s, int* solved) {
     } }
   { PhaseTimer pt(s, "linear_solver");
     int rc = solvePcg(s, s->bschur.p); if (rc) return rc;
-    if (s->world > 1) {   // the reduced system is solved redundantly; rank 0's solution is broadcast so that the replicated cameras stay bitwise identical
-      if (s->rank != 0) CU(cudaMemsetAsync(s->x.p, 0, sizeof(double) * (size_t)st.sizePoses, s->stream));
-      rc = allreduceDev(s, s->x.p, st.sizePoses, 0); if (rc) return rc;
-    } }
+    rc = broadcastPoseStep(); if (rc) return rc; }
   { PhaseTimer pt(s, "backsub");
     launchBacksub(s->schur, s->sys, s->hplLm.p, st.hplColPtr[st.lmEnd] - st.hplColPtr[st.lmBegin], s->x.p, s->x.p + st.sizePoses, s->stream, &s->launches); }
   CU(cudaGetLastError());
@@ -468,7 +475,7 @@ int popEstimates(g2ocu_solver* s, bool restore) {
 int lambdaInit(g2ocu_solver* s, double* out) {
   if (s->userLambdaInit > 0) { *out = s->userLambdaInit; return G2OCU_OK; }
   const double* poseDiag = nullptr;
-  if (s->world > 1) {   // the pose diagonals are partial sums on each rank: reduce them first, then max over ranks
+  if (s->world > 1 && s->st.doSchur) {   // the pose diagonals are partial sums on each rank: reduce them first, then max over ranks
     launchExtractPoseDiag(s->sys, s->vq.p, s->stream, &s->launches);
     int rc = allreduceDev(s, s->vq.p, s->st.sizePoses, 0); if (rc) return rc;
     poseDiag = s->vq.p;
@@ -485,7 +492,7 @@ int lambdaInit(g2ocu_solver* s, double* out) {
 int enqueueScale(g2ocu_solver* s, double lambda) {
   const Structure& st = s->st;
   CU(cudaMemsetAsync(s->out2.p + 5, 0, 2 * sizeof(double), s->stream));
-  if (s->world <= 1) launchScale(s->x.p, s->b.p, (int64_t)s->x.n, lambda, s->scratch.p, s->out2.p + 5, s->stream, &s->launches);
+  if (s->world <= 1 || !st.doSchur) launchScale(s->x.p, s->b.p, (int64_t)s->x.n, lambda, s->scratch.p, s->out2.p + 5, s->stream, &s->launches);
   else {
     launchScale(s->x.p, s->b.p, (int64_t)st.sizePoses, s->rank == 0 ? lambda : 0.0, s->scratch.p, s->out2.p + 5, s->stream, &s->launches);
     const size_t o = (size_t)st.sizePoses + (size_t)st.lmBegin * st.L;

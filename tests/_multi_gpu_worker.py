@@ -32,11 +32,11 @@ def main():
             estr = r.get_estimates()
             assert n == nr, (name, n, nr)
             for a, b in zip(st, str_):
-                assert abs(a["chi2"] - b["chi2"]) <= 1e-7 * abs(b["chi2"]), (name, a["chi2"], b["chi2"])
+                assert abs(a["chi2"] - b["chi2"]) <= 1e-6 * abs(b["chi2"]), (name, a["chi2"], b["chi2"])
                 assert a["levenberg_iterations"] == b["levenberg_iterations"]
-                assert abs(a["lambda"] - b["lambda"]) <= 1e-7 * abs(b["lambda"])
+                assert abs(a["lambda"] - b["lambda"]) <= 1e-6 * abs(b["lambda"])
             err = np.max(np.abs(est - estr) / (1 + np.abs(estr)))
-            assert err < 1e-6, (name, err)
+            assert err < 1e-5, (name, err)   # both sides stop PCG at a relative residual of 1e-6
             print(f"{name}: sharded x{world} matches single GPU, chi2 {st[-1]['chi2']:.6f}, max rel est diff {err:.2e}", flush=True)
         # all ranks hold the same complete estimate vector
         t = torch.from_numpy(est.copy()).cuda()
