@@ -352,10 +352,13 @@ int buildDevice(g2ocu_solver* s) {
   return G2OCU_OK;
 }
 
+// SparseOptimizer::computeActiveErrors etc. work right after initializeOptimization in the reference; the device state they need is
+// created on demand here (the index map is rebuilt by the next explicit buildStructure anyway)
 int requireBuilt(g2ocu_solver* s) {
   if (!s) return G2OCU_E_INVALID;
-  if (!s->structureBuilt) return fail(s, G2OCU_E_INVALID, "buildStructure has not been called");
-  return G2OCU_OK;
+  if (s->structureBuilt) return G2OCU_OK;
+  if (!s->optInitialized) return fail(s, G2OCU_E_INVALID, "initializeOptimization has not been called");
+  return g2ocu_build_structure(s);
 }
 
 int computeErrors(g2ocu_solver* s, double* errOut, const int64_t* errOff) {
@@ -512,7 +515,7 @@ int computeScale(g2ocu_solver* s, double lambda, double* out) {
 // OptimizationAlgorithmLevenberg::solve, optimization_algorithm_levenberg.cpp:58-150
 int solveLevenberg(g2ocu_solver* s, int iteration, int* result) {
   int rc;
-  if (iteration == 0) { rc = g2ocu_build_structure(s); if (rc) { *result = G2OCU_RESULT_FAIL; return rc; } }
+  if (iteration == 0 && !s->structureBuilt) { rc = g2ocu_build_structure(s); if (rc) { *result = G2OCU_RESULT_FAIL; return rc; } }   // the map stays valid until the next initializeOptimization / set_graph
   rc = computeErrors(s, nullptr, nullptr); if (rc) return rc;
   rc = buildSystem(s); if (rc) return rc;          // enqueued behind the error kernels; one sync serves both
   rc = finishErrors(s); if (rc) return rc;
@@ -557,7 +560,7 @@ int solveLevenberg(g2ocu_solver* s, int iteration, int* result) {
 // OptimizationAlgorithmGaussNewton::solve, optimization_algorithm_gauss_newton.cpp:50-91
 int solveGaussNewton(g2ocu_solver* s, int iteration, int* result) {
   int rc;
-  if (iteration == 0) { rc = g2ocu_build_structure(s); if (rc) { *result = G2OCU_RESULT_FAIL; return rc; } }
+  if (iteration == 0 && !s->structureBuilt) { rc = g2ocu_build_structure(s); if (rc) { *result = G2OCU_RESULT_FAIL; return rc; } }   // the map stays valid until the next initializeOptimization / set_graph
   rc = buildSystem(s); if (rc) return rc;
   s->lambda = 0.0;
   int ok = 1;
