@@ -1,0 +1,53 @@
+"""Generates tests/golden/*.json with the CPU oracle (run here, in the build container):
+
+    python tests/golden/make_golden.py
+
+The reference holds no fixtures for this path and cannot be compiled here (no Eigen3), so these are
+*oracle-generated* regression vectors: they pin the oracle against accidental change and give the GPU tests a fixed target
+that does not need the oracle at all.  Inputs are the seeded synthetic graphs of g2o_b200/workloads.py."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from g2o_b200 import graph as G  # noqa: E402
+from g2o_b200 import workloads as W  # noqa: E402
+from oracle.oracle import Oracle  # noqa: E402
+
+CASES = {
+    "ba_demo_15x300": (lambda: W.ba_demo(), "lm", "pcg"),
+    "ba_demo_huber_outliers": (lambda: W.ba_demo(edge_type=G.EDGE_PROJECT_XYZ2UV, robust_kernel=True, outlier_ratio=0.05), "lm", "pcg"),
+    "bal_small": (lambda: W.bal_small(), "lm", "pcg"),
+    "sphere_16x8": (lambda: W.sphere(nodes_per_level=16, laps=8), "lm", "pcg"),
+    "slam2d_800": (lambda: W.slam2d(n_poses=800, n_landmarks=200, world_size=30.0), "lm", "pcg"),
+    "sphere_gn": (lambda: W.sphere(nodes_per_level=12, laps=6), "gn", "pcg"),
+}
+
+
+def main():
+    out = {}
+    for name, (fn, alg, lin) in CASES.items():
+        g = fn()
+        o = Oracle(g, alg, lin); o.initialize_optimization(); o.algorithm_init(); o.build_structure()
+        o.compute_active_errors(); o.build_system()
+        rec = {"n_vertices": g.n_vertices, "n_edges": g.n_edges, "chi2_0": o.active_robust_chi2(), "plain_chi2_0": o.active_chi2(),
+               "dims": o.get_i32("dims").tolist(), "b_head": o.get_f64("b")[:24].tolist(), "b_sum": float(np.sum(o.get_f64("b"))),
+               "hpp_sum": float(np.sum(o.get_f64("hpp_values"))), "lambda_init": o.compute_lambda_init(),
+               "hschur_nnz_blocks": int(o.get_i32("hschur_colptr")[-1]) if o.do_schur() else 0,
+               "structure_checksum": int(np.sum(o.get_i32("hessian_index").astype(np.int64) * (np.arange(g.n_vertices) % 97 + 1)))}
+        o2 = Oracle(g, alg, lin); o2.initialize_optimization()
+        n, st = o2.optimize(6)
+        rec.update({"iterations": n, "chi2": [s["chi2"] for s in st], "lambda": [s["lambda"] for s in st],
+                    "trials": [int(s["levenbergIterations"]) for s in st], "estimate_head": o2.estimates()[:32].tolist(),
+                    "algorithm": alg})
+        out[name] = rec
+        print(name, rec["chi2_0"], rec["chi2"][-1])
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "lm_trajectories.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+
+
+if __name__ == "__main__":
+    main()
