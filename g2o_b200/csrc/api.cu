@@ -75,6 +75,8 @@ struct g2ocu_solver {
   double pcgResidual = -1.0;      // LinearSolverPCG::_residual, persists across solves until init()
   int lastPcgIterations = 0;
   bool errorsValid = false; double chi2Robust = 0, chi2Plain = 0;
+  // estimates of each class form one contiguous run of the packed host array and together cover it: copies go straight between the caller's buffer and the device
+  bool fastEstimates = false; int64_t poseHostOff = 0, lmHostOff = 0;
   // sharding
   int rank = 0, world = 1; g2ocu_allreduce_fn allreduce = nullptr; void* allreduceUser = nullptr;
   // device state
@@ -257,6 +259,16 @@ int buildDevice(g2ocu_solver* s) {
     maxScratch = std::max(maxScratch, (size_t)errorScratchDoubles(n));
   }
   CU(s->scratch.alloc(maxScratch)); CU(s->out2.alloc(8));
+  {
+    auto contiguous = [&](const std::vector<int32_t>& verts, int vtype, int64_t& off) {
+      if (verts.empty()) { off = 0; return true; }
+      const int S = vertexEstimateDim(vtype); off = g.vEstOff[verts[0]];
+      for (size_t i = 0; i < verts.size(); ++i) if (g.vEstOff[verts[i]] != off + (int64_t)i * S) return false;
+      return true;
+    };
+    const bool cp = contiguous(st.poseVerts, st.poseType, s->poseHostOff), cl = contiguous(st.lmVerts, st.lmType ? st.lmType : st.poseType, s->lmHostOff);
+    s->fastEstimates = cp && cl && (s->poseEst.n + s->lmEst.n == g.vEst.size());
+  }
 
   // ---- Schur structures ----
   SchurDev& sd = s->schur; sd = SchurDev();
@@ -771,6 +783,12 @@ int64_t g2ocu_vector_size(const g2ocu_solver* s) { return (s && s->structureBuil
 int g2ocu_set_estimates(g2ocu_solver* s, const double* host) {
   if (!s || !host) return G2OCU_E_INVALID;
   if (!s->hasGraph) return fail(s, G2OCU_E_INVALID, "no graph set");
+  if (s->structureBuilt && s->fastEstimates) {
+    CU(cudaMemcpyAsync(s->poseEst.p, host + s->poseHostOff, s->poseEst.n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (s->lmEst.n) CU(cudaMemcpyAsync(s->lmEst.p, host + s->lmHostOff, s->lmEst.n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    s->errorsValid = false;
+    return syncStream(s);       // the caller may reuse its buffer as soon as this returns
+  }
   std::memcpy(s->g.vEst.data(), host, sizeof(double) * s->g.vEst.size());
   if (s->structureBuilt) return uploadEstimates(s);
   return G2OCU_OK;
@@ -778,6 +796,11 @@ int g2ocu_set_estimates(g2ocu_solver* s, const double* host) {
 int g2ocu_get_estimates(g2ocu_solver* s, double* host) {
   if (!s || !host) return G2OCU_E_INVALID;
   if (!s->hasGraph) return fail(s, G2OCU_E_INVALID, "no graph set");
+  if (s->structureBuilt && s->fastEstimates && s->world <= 1) {
+    CU(cudaMemcpyAsync(host + s->poseHostOff, s->poseEst.p, s->poseEst.n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (s->lmEst.n) CU(cudaMemcpyAsync(host + s->lmHostOff, s->lmEst.p, s->lmEst.n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    return syncStream(s);
+  }
   if (s->structureBuilt) { int rc = downloadEstimates(s); if (rc) return rc; }
   std::memcpy(host, s->g.vEst.data(), sizeof(double) * s->g.vEst.size());
   return G2OCU_OK;

@@ -327,8 +327,10 @@ template <int P> __global__ void block_inverse_kernel(PcgDev p) {
 }
 
 // symmetric block SpMV over work items (row, block range); q must be zero on entry.
-// Each warp stages G = 32/P consecutive blocks in shared memory with coalesced loads, then lane (g, r) forms
-// row r of A_ij d_j (kept in a register, one RED per item) and row r of A_ij^T d_i (RED into q_j).
+// Each warp stages G = 32/P consecutive blocks in shared memory with coalesced loads; lane (g, c) then owns COLUMN c of block g
+// (9 consecutive doubles, odd stride => conflict-free 64-bit shared loads): the transposed product (A_ij^T d_i)[c] is complete
+// inside the lane (one RED into q_j), and the lane's contributions A_ij[:, c] d_j[c] to q_i are kept in P registers for the
+// whole item and reduced across the warp once at its end.  Upper blocks are read once.
 template <int P> __global__ void __launch_bounds__(128) spmv_sym_kernel(PcgDev p, const int32_t* __restrict__ itemRow, const int32_t* __restrict__ itemBegin,
                                                                          const int32_t* __restrict__ itemEnd, int nItems, const double* __restrict__ src, double* __restrict__ dst) {
   constexpr int PP = P * P, G = 32 / P;
@@ -338,12 +340,11 @@ template <int P> __global__ void __launch_bounds__(128) spmv_sym_kernel(PcgDev p
   const int item = blockIdx.x * 4 + w;
   if (item >= nItems) return;
   const int row = itemRow[item], kb = itemBegin[item], ke = itemEnd[item];
-  const int g = lane / P, r = lane - g * P;
+  const int g = lane / P, c = lane - g * P;
   const bool act = g < G;
-  double di[P];
+  double di[P], yacc[P];
 #pragma unroll
-  for (int c = 0; c < P; ++c) di[c] = src[(size_t)row * P + c];
-  double yi = 0;
+  for (int r = 0; r < P; ++r) { di[r] = src[(size_t)row * P + r]; yacc[r] = 0; }
   for (int k0 = kb; k0 < ke; k0 += G) {
     const int nblk = min(G, ke - k0);
     const double* Ab = p.A + (size_t)k0 * PP;
@@ -352,17 +353,29 @@ template <int P> __global__ void __launch_bounds__(128) spmv_sym_kernel(PcgDev p
     __syncwarp();
     if (act && g < nblk) {
       const int j = p.colIdx[k0 + g];
-      const double* a = &sA[w][g * PP];
-      const double* dj = src + (size_t)j * P;
-      double y = 0, z = 0;
+      const double* a = &sA[w][g * PP + c * P];
+      const double djc = src[(size_t)j * P + c];
+      double z = 0;
 #pragma unroll
-      for (int c = 0; c < P; ++c) { y += a[r + P * c] * dj[c]; z += a[c + P * r] * di[c]; }
-      if (j == row) y += p.lambda * di[r];
-      else atomicAdd(dst + (size_t)j * P + r, z);
-      yi += y;
+      for (int r = 0; r < P; ++r) { const double v = a[r]; yacc[r] += v * djc; z += v * di[r]; }
+      if (j != row) atomicAdd(dst + (size_t)j * P + c, z);
     }
   }
-  if (act) atomicAdd(dst + (size_t)row * P + r, yi);
+  // q_i: sum the per-lane partial columns over the warp (idle lanes hold zeros), lanes 0..P-1 publish
+#pragma unroll
+  for (int r = 0; r < P; ++r) {
+    double v = yacc[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    yacc[r] = v;
+  }
+  if (lane < P) {
+    double v = 0;
+#pragma unroll
+    for (int r = 0; r < P; ++r) if (r == lane) v = yacc[r];
+    if (kb == p.rowPtr[row]) v += p.lambda * src[(size_t)row * P + lane];   // the item holding the diagonal block adds lambda d_i
+    atomicAdd(dst + (size_t)row * P + lane, v);
+  }
 }
 
 // d.q partial sums

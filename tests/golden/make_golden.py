@@ -36,8 +36,11 @@ def main():
         rec = {"n_vertices": g.n_vertices, "n_edges": g.n_edges, "chi2_0": o.active_robust_chi2(), "plain_chi2_0": o.active_chi2(),
                "dims": o.get_i32("dims").tolist(), "b_head": o.get_f64("b")[:24].tolist(), "b_sum": float(np.sum(o.get_f64("b"))),
                "hpp_sum": float(np.sum(o.get_f64("hpp_values"))), "lambda_init": o.compute_lambda_init(),
-               "hschur_nnz_blocks": int(o.get_i32("hschur_colptr")[-1]) if o.do_schur() else 0,
+               "hschur_nnz_blocks": 0,
                "structure_checksum": int(np.sum(o.get_i32("hessian_index").astype(np.int64) * (np.arange(g.n_vertices) % 97 + 1)))}
+        if o.do_schur():   # the reference adds Hpp's blocks to the Schur pattern on its first solve (block_solver.hpp:333-335)
+            o.set_lambda(1.0); o.solve(); o.restore_diagonal()
+            rec["hschur_nnz_blocks"] = int(o.get_i32("hschur_colptr")[-1])
         o2 = Oracle(g, alg, lin); o2.initialize_optimization()
         n, st = o2.optimize(6)
         rec.update({"iterations": n, "chi2": [s["chi2"] for s in st], "lambda": [s["lambda"] for s in st],
