@@ -82,7 +82,7 @@ struct g2ocu_solver {
   // device state
   DVec<double> poseEst, lmEst; std::vector<DVec<double>*> poseBackup, lmBackup; int stackDepth = 0;
   DVec<int> poseCounters, lmCounters;
-  DVec<double> Hpp, Hll, Hpl, b, x, S, Dinv, dbv, bschur, Minv, vr, vd, vq, vs, scal, partial, partialDq, scratch, out2, dbg;
+  DVec<double> Hpp, Hll, Hpl, W, b, x, S, Dinv, dbv, bschur, Minv, vr, vd, vq, vs, scal, partial, partialDq, scratch, out2, dbg;
   DVec<int32_t> hppDiag, hplColPtr, hplRowIdx, sRowPtr, sColIdx, sDiag, hppToS, pairSlot, pairEdgeI, pairEdgeJ, aRowPtr, aColIdx, aDiag, spRow, spBegin, spEnd, hplLm, tEntLm, tEntBI, tEntBJ, tChunkI, tChunkJ, tChunkB, tChunkE;
   DVec<uint32_t> tEntMJ; DVec<uint8_t> tEntMI;
   DVec<int64_t> off64;
@@ -203,7 +203,7 @@ int buildDevice(g2ocu_solver* s) {
   sys.numPoses = st.numPoses; sys.numLandmarks = st.numLandmarks; sys.numPoseSlots = st.numPoseSlots; sys.numLmSlots = st.numLmSlots; sys.P = P; sys.L = L;
   sys.Hpp = s->Hpp.p; sys.hppDiag = s->hppDiag.p; sys.b = s->b.p; sys.hplShared = st.hplShared; sys.hppShared = st.hppShared;
   if (st.doSchur) {
-    CU(s->Hll.alloc((size_t)st.numLandmarks * L * L)); CU(s->Hpl.alloc((size_t)st.hplRowIdx.size() * P * L));
+    CU(s->Hll.alloc((size_t)st.numLandmarks * L * L)); CU(s->Hpl.alloc((size_t)st.hplRowIdx.size() * P * L + 2));   // +2: 16-byte aligned bulk copies may read one double past the last block
     CU(s->Hll.zero(stream)); CU(s->Hpl.zero(stream));
     sys.Hll = s->Hll.p; sys.Hpl = s->Hpl.p;
   } else { sys.Hll = nullptr; sys.Hpl = nullptr; }
@@ -279,6 +279,8 @@ int buildDevice(g2ocu_solver* s) {
     CU(s->sRowPtr.upload(st.sRowPtr, stream)); CU(s->sColIdx.upload(st.sColIdx, stream)); CU(s->sDiag.upload(st.sDiag, stream)); CU(s->hppToS.upload(st.hppToS, stream));
     // short tracks (< kTileMinTrack observations): flat pair list, landmarks visited in the order of their first camera;
     // long tracks: entries of the output-stationary tile kernel
+    const bool useMma = schurMmaSupported(P, L);
+    const int tileRows = useMma ? kMmaTileRows : kTileRows;
     struct TileEntry { int64_t key; int32_t lm, baseI, baseJ; uint32_t maskJ; uint8_t maskI; };
     std::vector<TileEntry> entries;
     std::vector<int32_t> shortLm;
@@ -290,16 +292,23 @@ int buildDevice(g2ocu_solver* s) {
       std::vector<Run> rowsR, colsR;
       for (int i = 0; i < k; ++i) {
         const int c = st.hplRowIdx[cb + i];
-        const int ti = c / kTileRows, tj = c / kTileCols;
+        const int ti = c / tileRows, tj = c / kTileCols;
         if (rowsR.empty() || rowsR.back().tile != ti) rowsR.push_back({ti, cb + i, 0u});
-        rowsR.back().mask |= 1u << (c % kTileRows);
+        rowsR.back().mask |= 1u << (c % tileRows);
         if (colsR.empty() || colsR.back().tile != tj) colsR.push_back({tj, cb + i, 0u});
         colsR.back().mask |= 1u << (c % kTileCols);
       }
       for (const Run& ri : rowsR)
         for (const Run& rj : colsR) {
-          if ((rj.tile + 1) * kTileCols - 1 < ri.tile * kTileRows) continue;       // strip entirely left of the row tile: lower triangle
-          entries.push_back({((int64_t)ri.tile << 32) | (uint32_t)rj.tile, l, ri.base, rj.base, rj.mask, (uint8_t)ri.mask});
+          if ((rj.tile + 1) * kTileCols - 1 < ri.tile * tileRows) continue;       // strip entirely left of the row tile: lower triangle
+          int32_t baseJ = rj.base; uint32_t maskJ = rj.mask;
+          if (useMma && rj.tile * kTileCols < ri.tile * tileRows) {
+            // diagonal strip: columns left of the row group only form lower-triangle pairs - drop them from the entry
+            const uint32_t drop = maskJ & ((1u << (ri.tile * tileRows - rj.tile * kTileCols)) - 1u);
+            baseJ += __builtin_popcount(drop); maskJ &= ~drop;
+            if (maskJ == 0) continue;
+          }
+          entries.push_back({((int64_t)ri.tile << 32) | (uint32_t)rj.tile, l, ri.base, baseJ, maskJ, (uint8_t)ri.mask});
         }
     }
     {
@@ -311,7 +320,7 @@ int buildDevice(g2ocu_solver* s) {
       sd.nPairs = (int64_t)pI.size(); sd.pairEdgeI = s->pairEdgeI.p; sd.pairEdgeJ = s->pairEdgeJ.p; sd.pairSlot = s->pairSlot.p;
     }
     {  // tile entries grouped by (row tile, column strip), split in chunks of at most kTileChunk entries (one CTA each)
-      const int kTileChunk = 256;
+      const int kTileChunk = useMma ? 1024 : 256;
       std::stable_sort(entries.begin(), entries.end(), [](const TileEntry& a, const TileEntry& b) { return a.key < b.key; });
       std::vector<int32_t> eLm(entries.size()), eBI(entries.size()), eBJ(entries.size()), cI, cJ, cB, cE; std::vector<uint32_t> eMJ(entries.size()); std::vector<uint8_t> eMI(entries.size());
       for (size_t i = 0; i < entries.size(); ++i) { eLm[i] = entries[i].lm; eBI[i] = entries[i].baseI; eBJ[i] = entries[i].baseJ; eMJ[i] = entries[i].maskJ; eMI[i] = entries[i].maskI; }
@@ -327,6 +336,7 @@ int buildDevice(g2ocu_solver* s) {
       sd.chunkI = s->tChunkI.p; sd.chunkJ = s->tChunkJ.p; sd.chunkBegin = s->tChunkB.p; sd.chunkEnd = s->tChunkE.p;
       sd.entLm = s->tEntLm.p; sd.entBaseI = s->tEntBI.p; sd.entBaseJ = s->tEntBJ.p; sd.entMaskJ = s->tEntMJ.p; sd.entMaskI = s->tEntMI.p;
     }
+    if (useMma) { CU(s->W.alloc((size_t)st.hplRowIdx.size() * P * L + 2)); CU(s->W.zero(stream)); sd.W = s->W.p; }
     CU(s->S.alloc((size_t)st.sColIdx.size() * P * P)); CU(s->Dinv.alloc((size_t)st.numLandmarks * L * L)); CU(s->dbv.alloc((size_t)st.numLandmarks * L)); CU(s->bschur.alloc((size_t)st.sizePoses));
     sd.numPoses = st.numPoses; sd.numLandmarks = st.numLandmarks; sd.P = P; sd.L = L;
     sd.lmBegin = st.lmBegin; sd.lmEnd = st.lmEnd; sd.blockBegin = st.hplColPtr[st.lmBegin];
@@ -867,7 +877,7 @@ int64_t g2ocu_get_f64(g2ocu_solver* s, const char* name, double* out, int64_t ca
   if (n == "bschur") return downloadF64(s, s->bschur.p, s->bschur.n, out, cap);
   if (n == "hpp_values") return downloadBlocks(s, s->Hpp.p, st.hppCcsToCsr, P * P, s->lambda, &st.hppDiag, out, cap);
   if (n == "hschur_values") return downloadBlocks(s, s->S.p, st.sCcsToCsr, P * P, 0.0, nullptr, out, cap);
-  if (n == "hpl_values") return downloadF64(s, s->Hpl.p, s->Hpl.n, out, cap);
+  if (n == "hpl_values") return downloadF64(s, s->Hpl.p, s->st.hplRowIdx.size() * (size_t)s->st.P * s->st.L, out, cap);
   if (n == "hll_values") {
     const int64_t cnt = downloadF64(s, s->Hll.p, s->Hll.n, out, cap);
     if (out && s->lambda != 0.0) for (int64_t i = 0; i < st.numLandmarks && (i + 1) * L * L <= cap; ++i) for (int q = 0; q < L; ++q) out[i * L * L + q * (L + 1)] += s->lambda;

@@ -60,12 +60,16 @@ struct SchurDev {
   // short tracks: flat list of (Hpl block i, Hpl block j, Hschur block) per pair i <= j, atomics
   int64_t nPairs = 0; const int32_t* pairEdgeI = nullptr; const int32_t* pairEdgeJ = nullptr; int32_t* pairSlot = nullptr;
   double* S = nullptr; double* Dinv = nullptr; double* db = nullptr; double* bschur = nullptr;
+  double* W = nullptr;          // Hpl Dinv, same block order as Hpl (tensor-pipe path only)
   // long tracks (>= kTileMinTrack observations): output-stationary tiles, see schur_tile_kernel
   int nTileChunks = 0;
   const int32_t* chunkI = nullptr; const int32_t* chunkJ = nullptr; const int32_t* chunkBegin = nullptr; const int32_t* chunkEnd = nullptr;
   const int32_t* entLm = nullptr; const int32_t* entBaseI = nullptr; const int32_t* entBaseJ = nullptr; const uint32_t* entMaskJ = nullptr; const uint8_t* entMaskI = nullptr;
 };
 static const int kTileRows = 4, kTileCols = 32;   // cameras per tile row group / column strip
+static const int kMmaTileRows = 8;                // row group of the tensor-pipe tile kernel (kernels_schur_mma.cu)
+bool schurMmaSupported(int P, int L);             // block shapes routed through the DMMA tile kernel
+void launchSchurMma(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, cudaStream_t st, int64_t* launches);
 static const int kTileMinTrack = 8;               // landmarks with at least this many observations go through the tile kernel
 void launchPairSlots(const SchurDev& d, cudaStream_t st, int64_t* launches);
 void launchSchur(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, double lambda, double lambdaDiag, cudaStream_t st, int64_t* launches);

@@ -513,13 +513,15 @@ template <int P, int L> static void schurPL(const SchurDev& d, const SystemDev& 
   add_lambda_diag_kernel<P><<<(d.numPoses * P + 255) / 256, 256, 0, st>>>(d.S, d.sDiag, d.numPoses, lambdaDiag);
   *launches += 3;
   if (d.lmEnd > d.lmBegin) { dinv_kernel<P, L><<<(d.lmEnd - d.lmBegin + 255) / 256, 256, 0, st>>>(d, sys.Hll, sys.b, lambda); *launches += 1; }
-  if (nBlocks > 0) { coeff_kernel<P, L><<<(nBlocks + 127) / 128, 128, 0, st>>>(d, sys.Hpl, hplLm, nBlocks); *launches += 1; }
+  const bool mma = schurMmaSupported(P, L);
+  if (mma) launchSchurMma(d, sys, hplLm, nBlocks, st, launches);
+  else if (nBlocks > 0) { coeff_kernel<P, L><<<(nBlocks + 127) / 128, 128, 0, st>>>(d, sys.Hpl, hplLm, nBlocks); *launches += 1; }
   if (d.nPairs > 0) {
     const int64_t warpsNeeded = d.nPairs; const int nb = (int)((warpsNeeded + 7) / 8 < 148 * 8 * 4 ? (warpsNeeded + 7) / 8 : 148 * 8 * 4);
     schur_pairs_kernel<P, L><<<nb, 256, 0, st>>>(d, sys.Hpl, hplLm);
     *launches += 1;
   }
-  if (d.nTileChunks > 0) {
+  if (d.nTileChunks > 0 && !mma) {
     constexpr int kTileSmem = kTileBatch * (kTileCols * ((P * L) | 1) + kTileRows * P * L) * (int)sizeof(double);
     static bool configured = false;
     if (!configured) { cudaFuncSetAttribute(schur_tile_kernel<P, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem); configured = true; }

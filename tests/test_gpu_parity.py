@@ -22,6 +22,8 @@ GRAPHS = {
     "ba_demo_xyz2uv_huber": (lambda: W.ba_demo(edge_type=G.EDGE_PROJECT_XYZ2UV, robust_kernel=True, outlier_ratio=0.05), "lm_fix6_3_cuda"),
     "bal_small": (lambda: W.bal_small(), "lm_fix9_3_cuda"),
     "bal_medium": (lambda: W.bal_synthetic(n_cameras=60, n_points=6000, n_obs=30000, seed=5, k_max=40, min_window=4), "lm_fix9_3_cuda"),
+    # long tracks over several tile row groups / column strips, wrapping around the camera ring
+    "bal_ring": (lambda: W.bal_synthetic(n_cameras=150, n_points=8000, n_obs=60000, seed=9, k_max=120, min_window=6), "lm_fix9_3_cuda"),
     "sphere": (lambda: W.sphere(nodes_per_level=16, laps=8), "lm_var_cuda"),
     "slam2d": (lambda: W.slam2d(n_poses=800, n_landmarks=200, world_size=30.0), "lm_fix3_2_cuda"),
 }
