@@ -452,7 +452,11 @@ int solveSystem(g2ocu_solver* s, int* solved) {
     return broadcastPoseStep();
   }
   { PhaseTimer pt(s, "schur");
-    launchSchur(s->schur, s->sys, s->hplLm.p, st.hplColPtr[st.lmEnd] - st.hplColPtr[st.lmBegin], s->lambda, s->rank == 0 ? s->lambda : 0.0, s->stream, &s->launches);
+    struct MarkCtx { g2ocu_solver* s; PhaseTimer* t; } mc{s, nullptr};
+    KernelMarks marks; marks.ctx = &mc;
+    marks.begin = [](void* c, const char* name) { auto* m = (MarkCtx*)c; m->t = new PhaseTimer(m->s, name); };
+    marks.end = [](void* c) { auto* m = (MarkCtx*)c; delete m->t; m->t = nullptr; };
+    launchSchur(s->schur, s->sys, s->hplLm.p, st.hplColPtr[st.lmEnd] - st.hplColPtr[st.lmBegin], s->lambda, s->rank == 0 ? s->lambda : 0.0, s->stream, &s->launches, &marks);
     if (s->world > 1) {
       int rc = allreduceDev(s, s->S.p, (int64_t)s->S.n, 0); if (rc) return rc;
       rc = allreduceDev(s, s->bschur.p, (int64_t)s->bschur.n, 0); if (rc) return rc;

@@ -69,10 +69,13 @@ struct SchurDev {
 static const int kTileRows = 4, kTileCols = 32;   // cameras per tile row group / column strip
 static const int kMmaTileRows = 8;                // row group of the tensor-pipe tile kernel (kernels_schur_mma.cu)
 bool schurMmaSupported(int P, int L);             // block shapes routed through the DMMA tile kernel
-void launchSchurMma(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, cudaStream_t st, int64_t* launches);
+struct KernelMarks;
+void launchSchurMma(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, cudaStream_t st, int64_t* launches, const KernelMarks* marks);
 static const int kTileMinTrack = 8;               // landmarks with at least this many observations go through the tile kernel
 void launchPairSlots(const SchurDev& d, cudaStream_t st, int64_t* launches);
-void launchSchur(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, double lambda, double lambdaDiag, cudaStream_t st, int64_t* launches);
+// optional per-kernel timing hooks: begin(ctx, name) / end(ctx) bracket one kernel (CUDA events on the launching stream in api.cu)
+struct KernelMarks { void* ctx = nullptr; void (*begin)(void*, const char*) = nullptr; void (*end)(void*) = nullptr; };
+void launchSchur(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, double lambda, double lambdaDiag, cudaStream_t st, int64_t* launches, const KernelMarks* marks = nullptr);
 void launchBacksub(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, const double* xp, double* xl, cudaStream_t st, int64_t* launches);
 
 struct PcgDev {

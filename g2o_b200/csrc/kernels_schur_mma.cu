@@ -37,7 +37,14 @@ constexpr int kMmaBatch = 32;                      // entries per stage at most 
 
 struct __align__(16) MmaHdr { uint32_t offI, offJ, maskI, maskJ; };   // offsets in doubles into the stage buffer
 
-constexpr int kMmaSmemBytes = kMmaStages * kMmaStageDoubles * 8 + kMmaStages * kMmaBatch * (int)sizeof(MmaHdr) + kMmaStages * 4 * 2 /*counts, padded*/ + 2 * kMmaStages * 8 + 16;
+constexpr int kMmaZeroBytes = 256;                 // zeroed region: operand of absent cameras / padded lanes
+constexpr int kMmaScratchEntry = 48;               // per warp and entry: 8 column offsets, 8 row offsets (u16 each), presence bits
+constexpr int kMmaOffZero = kMmaStages * kMmaStageDoubles * 8;
+constexpr int kMmaOffHdr = kMmaOffZero + kMmaZeroBytes;
+constexpr int kMmaOffCnt = kMmaOffHdr + kMmaStages * kMmaBatch * (int)sizeof(MmaHdr);
+constexpr int kMmaOffBar = kMmaOffCnt + 32;
+constexpr int kMmaOffScratch = kMmaOffBar + 2 * kMmaStages * 8;
+constexpr int kMmaSmemBytes = kMmaOffScratch + kMmaConsumers * kMmaBatch * kMmaScratchEntry;
 
 G2D uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 G2D void mbarInit(uint64_t* bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count)); }
@@ -67,6 +74,16 @@ G2D void dmma(double (&c)[2], double a, double b) {
 // cannot prove convergent.  Hence: (1) every value that steers control flow is made warp-uniform through redux.sync (result lives in a
 // uniform register, no convergence barriers are emitted), (2) absent row cameras are skipped by one real branch per row (9 DMMA slots
 // each), (3) inside a present row all 8 column slots are issued, absent columns multiply a zero fragment.
+G2D double ldsF64(uint32_t addr) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v; }
+G2D uint32_t ldsU16(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+G2D uint32_t ldsU32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+G2D uint4 ldsV4(uint32_t addr) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v; }
+G2D void stsV4(uint32_t addr, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+G2D void stsU32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+template <int K> G2D uint32_t half16(const uint4& v) {   // K-th 16-bit field of a packed 8 x u16 vector
+  const uint32_t w = (K >> 1) == 0 ? v.x : (K >> 1) == 1 ? v.y : (K >> 1) == 2 ? v.z : v.w;
+  return (K & 1) ? (w >> 16) : (w & 0xffffu);
+}
 G2D uint32_t uniformOr(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
 G2D int uniformMax(int v) { return __reduce_max_sync(0xffffffffu, v); }
 
@@ -113,18 +130,18 @@ template <int P, int L> __global__ void __launch_bounds__(kMmaThreads, 1) schur_
   static_assert(L <= 4 && P <= 9 && P >= 5, "block shape not supported by the DMMA mapping");
   extern __shared__ __align__(128) unsigned char smemRaw[];
   double* sData = reinterpret_cast<double*>(smemRaw);
-  MmaHdr* sHdr = reinterpret_cast<MmaHdr*>(smemRaw + (size_t)kMmaStages * kMmaStageDoubles * 8);
-  int* sCnt = reinterpret_cast<int*>(sHdr + kMmaStages * kMmaBatch);
-  uint64_t* sFull = reinterpret_cast<uint64_t*>(sCnt + 2 * kMmaStages);
+  MmaHdr* sHdr = reinterpret_cast<MmaHdr*>(smemRaw + kMmaOffHdr);
+  int* sCnt = reinterpret_cast<int*>(smemRaw + kMmaOffCnt);
+  uint64_t* sFull = reinterpret_cast<uint64_t*>(smemRaw + kMmaOffBar);
   uint64_t* sEmpty = sFull + kMmaStages;
-  double* sZero = reinterpret_cast<double*>(sEmpty + kMmaStages);   // one zero double (k pad / rows beyond the block)
+  const uint32_t smemBase = smemAddr(smemRaw);       // 32-bit shared-window address of the dynamic segment
 
   const int chunk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tileI = d.chunkI[chunk], tileJ = d.chunkJ[chunk];
   const int eBegin = d.chunkBegin[chunk], eEnd = d.chunkEnd[chunk];
+  if (threadIdx.x < kMmaZeroBytes / 8) reinterpret_cast<double*>(smemRaw + kMmaOffZero)[threadIdx.x] = 0.0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMmaStages; ++s) { mbarInit(sFull + s, 1); mbarInit(sEmpty + s, kMmaConsumers); }
-    sZero[0] = 0.0; sZero[1] = 0.0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -182,12 +199,16 @@ template <int P, int L> __global__ void __launch_bounds__(kMmaThreads, 1) schur_
   }
 
   // -------------------------------------------------- consumers --------------------------------------------------
+  // Warp (rh, cg) owns row cameras 2 i + rh (i < 4) of the row group and column cameras 4 j + cg (j < 8) of the strip: the interleaving
+  // gives every warp the same share of a landmark's window, whichever part of the tile the window covers.
   const int warpU = uniformMax(warp);
-  const int rh = warpU >> 2, cg = warpU & 3;         // row half (4 cameras), column group (8 cameras)
+  const int rh = warpU >> 2, cg = warpU & 3;
   const int m = lane >> 2, a = lane & 3;              // fragment coordinates: (row / column inside the block, landmark coordinate)
   const bool fragOk = a < L && m < MR;
   const bool aOk = a < L;
-  const int fragOff = m + P * a;
+  const uint32_t zeroAddr = smemBase + kMmaOffZero;
+  const uint32_t strideMain = fragOk ? 8u : 0u, strideFr = aOk ? 8u : 0u;    // padded lanes stay on the zero region
+  const uint32_t scratchWarp = smemBase + kMmaOffScratch + (uint32_t)warpU * (kMmaBatch * kMmaScratchEntry);
   double Cm[4][8][2], Ca[4][2], Cb[4][2], Cc[2];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -196,7 +217,7 @@ template <int P, int L> __global__ void __launch_bounds__(kMmaThreads, 1) schur_
     Ca[i][0] = Ca[i][1] = Cb[i][0] = Cb[i][1] = 0;
   }
   Cc[0] = Cc[1] = 0;
-  uint32_t touched = 0;                               // bit 8 i + j: block (row i, column j) of this warp received a product
+  uint32_t touched = 0;                               // bit 8 i + j: block (row 2 i + rh, column 4 j + cg) received a product
 
   long long tWait = 0, tProd = 0, tSlots = 0; const long long tStart = clock64();
   auto consume = [&](auto rhc) {
@@ -210,39 +231,59 @@ template <int P, int L> __global__ void __launch_bounds__(kMmaThreads, 1) schur_
       mbarWait(sFull + stage, phase);
       if (prof) { t2 = clock64(); tProd += t1 - t0; tWait += t2 - t1; }
       const int cntAll = uniformMax(sCnt[stage]);
-      const int cnt = dbg == 2 ? 0 : cntAll;
-      const double* buf = sData + (size_t)stage * kMmaStageDoubles;
-      const MmaHdr* hdr = sHdr + stage * kMmaBatch;
-#pragma unroll 1
-      for (int q = 0; q < cnt; ++q) {
-        const MmaHdr h = hdr[q];
-        const uint32_t mJ = uniformOr((h.maskJ >> (8 * cg)) & 0xffu);
-        if (mJ == 0) continue;
-        const uint32_t mI = uniformOr((h.maskI >> (4 * RH)) & 0xfu);
-        if (!FR) { if (mI == 0) continue; }
-        else if (RH != 0 && mI == 0 && ((mJ >> 4) & 0xfu) == 0) continue;
-        // fragments: lanes that must supply zeros (k = 3 pad, rows >= MR) and absent cameras read a zeroed shared slot
-        double Bf[8], Af[4];
-        {
-          const double* pj = buf + h.offJ + __popc(h.maskJ & ((1u << (8 * cg)) - 1u)) * PLn + fragOff;
+      const uint32_t bufAddr = smemBase + (uint32_t)stage * (kMmaStageDoubles * 8);
+      // ---- batch preparation, lane = entry: block offsets of my cameras (absent -> zero region), presence bits, relevance ----
+      bool relevant = false;
+      if (lane < cntAll && dbg != 2) {
+        const uint4 h = ldsV4(smemBase + kMmaOffHdr + (uint32_t)(stage * kMmaBatch + lane) * 16u);   // offI, offJ, maskI, maskJ
+        const uint32_t zeroOff = (zeroAddr - bufAddr) >> 3;
+        uint32_t co[8], ro[8], cJ = 0, tI = 0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { const bool on = (mJ >> j) & 1u; Bf[j] = *((on && fragOk) ? pj : sZero); if (on) pj += PLn; }
-          const double* pi = buf + h.offI + __popc(h.maskI & ((1u << (4 * RH)) - 1u)) * PLn + fragOff;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { const bool on = (mI >> i) & 1u; Af[i] = *((on && fragOk) ? pi : sZero); if (on) pi += PLn; }
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t c = 4 * j + cg, on = (h.w >> c) & 1u;
+          co[j] = on ? h.y + __popc(h.w & ((1u << c) - 1u)) * PLn : zeroOff;
+          cJ |= on << j;
         }
-        double FA = 0, FB = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const uint32_t on = (h.z >> r) & 1u;
+          ro[r] = on ? h.x + __popc(h.z & ((1u << r) - 1u)) * PLn : zeroOff;
+          if ((r & 1) == RH) tI |= on << (r >> 1);
+        }
+        relevant = cJ != 0 && (tI != 0 || (FR && (RH == 0 || (cJ >> 4) != 0)));
+        const uint32_t sa = scratchWarp + (uint32_t)lane * kMmaScratchEntry;
+        stsV4(sa, make_uint4(co[0] | (co[1] << 16), co[2] | (co[3] << 16), co[4] | (co[5] << 16), co[6] | (co[7] << 16)));
+        stsV4(sa + 16, make_uint4(ro[0] | (ro[1] << 16), ro[2] | (ro[3] << 16), ro[4] | (ro[5] << 16), ro[6] | (ro[7] << 16)));
+        stsU32(sa + 32, tI | (cJ << 8));
+      }
+      uint32_t rel = uniformOr(__ballot_sync(0xffffffffu, relevant));
+      __syncwarp();
+      const uint32_t baseMain = fragOk ? bufAddr + (uint32_t)(m + P * a) * 8u : zeroAddr;
+      const uint32_t baseFr = aOk ? bufAddr + (uint32_t)(8 + P * a) * 8u : zeroAddr;
+      // ---- visits: only the entries this warp has work for ----
+#pragma unroll 1
+      while (rel) {
+        const int q = __ffs(rel) - 1; rel &= rel - 1u;
+        const uint32_t sa = scratchWarp + (uint32_t)q * kMmaScratchEntry;
+        const uint4 cp = ldsV4(sa), rp = ldsV4(sa + 16);
+        const uint32_t bits = ldsU32(sa + 32);
+        const uint32_t tI = uniformOr(bits & 0xfu), cJ = (bits >> 8) & 0xffu;
+        double Bf[8], Af[4], FA = 0, FB = 0;
+        Bf[0] = ldsF64(baseMain + half16<0>(cp) * strideMain); Bf[1] = ldsF64(baseMain + half16<1>(cp) * strideMain);
+        Bf[2] = ldsF64(baseMain + half16<2>(cp) * strideMain); Bf[3] = ldsF64(baseMain + half16<3>(cp) * strideMain);
+        Bf[4] = ldsF64(baseMain + half16<4>(cp) * strideMain); Bf[5] = ldsF64(baseMain + half16<5>(cp) * strideMain);
+        Bf[6] = ldsF64(baseMain + half16<6>(cp) * strideMain); Bf[7] = ldsF64(baseMain + half16<7>(cp) * strideMain);
+        Af[0] = ldsF64(baseMain + half16<0 + RH>(rp) * strideMain); Af[1] = ldsF64(baseMain + half16<2 + RH>(rp) * strideMain);
+        Af[2] = ldsF64(baseMain + half16<4 + RH>(rp) * strideMain); Af[3] = ldsF64(baseMain + half16<6 + RH>(rp) * strideMain);
         if (FR) {
-          // ninth column of the 8 cameras of my column group: B[k][n] = B_{j_n}[8, k];  ninth row of the 8 row cameras: A[m][k] = W_{i_m}[8, k]
-          const uint32_t bitJ = 8 * cg + m;
-          const double* pfb = (((h.maskJ >> bitJ) & 1u) && aOk) ? buf + h.offJ + __popc(h.maskJ & ((1u << bitJ) - 1u)) * PLn + 8 + P * a : sZero;
-          const double* pfa = (((h.maskI >> m) & 1u) && aOk) ? buf + h.offI + __popc(h.maskI & ((1u << m) - 1u)) * PLn + 8 + P * a : sZero;
-          FB = *pfb; FA = *pfa;
+          // ninth column of my 8 column cameras: B[k][n] = B_{j_n}[8, k];  ninth row of the 8 row cameras of the group: A[m][k] = W_{i_m}[8, k]
+          FB = ldsF64(baseFr + ldsU16(sa + 2u * m) * strideFr);
+          FA = ldsF64(baseFr + ldsU16(sa + 16u + 2u * m) * strideFr);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if ((mI >> i) & 1u) {
-            touched |= mJ << (8 * i);
+          if ((tI >> i) & 1u) {
+            touched |= cJ << (8 * i);
             if (prof) tSlots += FR ? 9 : 8;
             do {                                        // `never` is 0: the loop form keeps ptxas from predicating the 9 slots of an absent row
 #pragma unroll
@@ -274,9 +315,9 @@ template <int P, int L> __global__ void __launch_bounds__(kMmaThreads, 1) schur_
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (d.sColIdx[mid] < cj) lo = mid + 1; else hi = mid; }
     return (lo < end && d.sColIdx[lo] == cj) ? lo : -1;
   };
-  const int rowCam0 = tileI * kMmaTileRows, colCam0 = tileJ * kTileCols + 8 * cg;
+  const int rowCam0 = tileI * kMmaTileRows, colCam0 = tileJ * kTileCols + cg;   // my row cameras: rowCam0 + 2 i + rh, my column cameras: colCam0 + 4 j
   int mySlot = -1;
-  if ((touched >> lane) & 1u) mySlot = findSlot(rowCam0 + 4 * rh + (lane >> 3), colCam0 + (lane & 7));
+  if ((touched >> lane) & 1u) mySlot = findSlot(rowCam0 + 2 * (lane >> 3) + rh, colCam0 + 4 * (lane & 7));
   const int n0 = 2 * a, n1 = 2 * a + 1;               // accumulator columns held by this lane
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -289,7 +330,7 @@ template <int P, int L> __global__ void __launch_bounds__(kMmaThreads, 1) schur_
         if (n1 < MR) atomicAdd(Sb + P * n1, -Cm[i][j][1]);
       }
     }
-    if (FR) {   // rows 0..7 of column 8 of the blocks (i, 8 cg + n)
+    if (FR) {   // rows 0..7 of column 8 of the blocks (my row i, my column n)
       const int s0 = __shfl_sync(0xffffffffu, mySlot, i * 8 + n0), s1 = __shfl_sync(0xffffffffu, mySlot, i * 8 + n1);
       if (s0 >= 0) atomicAdd(d.S + (size_t)s0 * PP + m + P * 8, -Cb[i][0]);
       if (s1 >= 0) atomicAdd(d.S + (size_t)s1 * PP + m + P * 8, -Cb[i][1]);
@@ -297,15 +338,15 @@ template <int P, int L> __global__ void __launch_bounds__(kMmaThreads, 1) schur_
   }
   if (FR) {
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {   // row 8, columns 0..7 of the blocks (row camera m, column 8 cg + 4 rh + jj)
+    for (int jj = 0; jj < 4; ++jj) {   // row 8, columns 0..7 of the blocks (row camera m of the group, my column camera 4 rh + jj)
       if (Ca[jj][0] != 0.0 || Ca[jj][1] != 0.0) {
-        const int slot = findSlot(rowCam0 + m, colCam0 + 4 * rh + jj);
+        const int slot = findSlot(rowCam0 + m, colCam0 + 4 * (4 * rh + jj));
         if (slot >= 0) { double* Sb = d.S + (size_t)slot * PP + 8; atomicAdd(Sb + P * n0, -Ca[jj][0]); atomicAdd(Sb + P * n1, -Ca[jj][1]); }
       }
     }
-    if (rh == 0) {                      // element (8, 8) of the blocks (row camera m, column 8 cg + n)
-      if (Cc[0] != 0.0) { const int slot = findSlot(rowCam0 + m, colCam0 + n0); if (slot >= 0) atomicAdd(d.S + (size_t)slot * PP + 8 + P * 8, -Cc[0]); }
-      if (Cc[1] != 0.0) { const int slot = findSlot(rowCam0 + m, colCam0 + n1); if (slot >= 0) atomicAdd(d.S + (size_t)slot * PP + 8 + P * 8, -Cc[1]); }
+    if (rh == 0) {                      // element (8, 8) of the blocks (row camera m of the group, my column camera n)
+      if (Cc[0] != 0.0) { const int slot = findSlot(rowCam0 + m, colCam0 + 4 * n0); if (slot >= 0) atomicAdd(d.S + (size_t)slot * PP + 8 + P * 8, -Cc[0]); }
+      if (Cc[1] != 0.0) { const int slot = findSlot(rowCam0 + m, colCam0 + 4 * n1); if (slot >= 0) atomicAdd(d.S + (size_t)slot * PP + 8 + P * 8, -Cc[1]); }
     }
   }
   if (prof && lane == 0) {
@@ -319,15 +360,17 @@ template <int P, int L> __global__ void __launch_bounds__(kMmaThreads, 1) schur_
 
 bool schurMmaSupported(int P, int L) { return L == 3 && (P == 9 || P == 6); }
 
-template <int P, int L> static void launchMmaPL(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, cudaStream_t st, int64_t* launches) {
-  if (nBlocks > 0) { coeff_w_kernel<P, L><<<(nBlocks + 127) / 128, 128, 0, st>>>(d, sys.Hpl, hplLm, nBlocks); *launches += 1; }
+template <int P, int L> static void launchMmaPL(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, cudaStream_t st, int64_t* launches, const KernelMarks* marks) {
+  if (nBlocks > 0) { if (marks && marks->begin) marks->begin(marks->ctx, "schur_coeff"); coeff_w_kernel<P, L><<<(nBlocks + 127) / 128, 128, 0, st>>>(d, sys.Hpl, hplLm, nBlocks); *launches += 1; if (marks && marks->end) marks->end(marks->ctx); }
   if (d.nTileChunks > 0) {
     static bool configured = false;
     if (!configured) { cudaFuncSetAttribute(schur_mma_kernel<P, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes); configured = true; }
     static const int dbg = getenv("G2OCU_SCHUR_DEBUG") ? atoi(getenv("G2OCU_SCHUR_DEBUG")) : 0;
     long long* prof = nullptr;
     if (dbg == 3) cudaMalloc(&prof, sizeof(long long) * 8 * kMmaConsumers * (size_t)d.nTileChunks);
+    if (marks && marks->begin) marks->begin(marks->ctx, "schur_tiles");
     schur_mma_kernel<P, L><<<d.nTileChunks, kMmaThreads, kMmaSmemBytes, st>>>(d, sys.Hpl, dbg, 0, prof);
+    if (marks && marks->end) marks->end(marks->ctx);
     if (prof) {   // developer instrumentation: per-warp cycle breakdown of every chunk
       cudaStreamSynchronize(st);
       std::vector<long long> h((size_t)8 * kMmaConsumers * d.nTileChunks);
@@ -338,9 +381,9 @@ template <int P, int L> static void launchMmaPL(const SchurDev& d, const SystemD
   }
 }
 // coefficient pass (writes W) + tensor-pipe tile pass; the caller has initialised S / b_schur and computed Dinv / db
-void launchSchurMma(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, cudaStream_t st, int64_t* launches) {
-  if (d.P == 9 && d.L == 3) launchMmaPL<9, 3>(d, sys, hplLm, nBlocks, st, launches);
-  else if (d.P == 6 && d.L == 3) launchMmaPL<6, 3>(d, sys, hplLm, nBlocks, st, launches);
+void launchSchurMma(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, cudaStream_t st, int64_t* launches, const KernelMarks* marks) {
+  if (d.P == 9 && d.L == 3) launchMmaPL<9, 3>(d, sys, hplLm, nBlocks, st, launches, marks);
+  else if (d.P == 6 && d.L == 3) launchMmaPL<6, 3>(d, sys, hplLm, nBlocks, st, launches, marks);
 }
 
 }  // namespace g2ocu
