@@ -23,6 +23,12 @@ SOLVER_NAMES = {
     "gn_fix6_3_cuda": ("gn", 6, 3, True), "lm_fix6_3_cuda": ("lm", 6, 3, True),
     "gn_fix7_3_cuda": ("gn", 7, 3, True), "lm_fix7_3_cuda": ("lm", 7, 3, True),
     "gn_fix9_3_cuda": ("gn", 9, 3, True), "lm_fix9_3_cuda": ("lm", 9, 3, True),
+    # solvers/dense/solver_dense.cpp:91-98 (+ 9_3): BlockSolver + LinearSolverDense -> device DMMA Cholesky
+    "gn_dense_cuda": ("gn", -1, -1, False), "lm_dense_cuda": ("lm", -1, -1, False),
+    "gn_dense3_2_cuda": ("gn", 3, 2, True), "lm_dense3_2_cuda": ("lm", 3, 2, True),
+    "gn_dense6_3_cuda": ("gn", 6, 3, True), "lm_dense6_3_cuda": ("lm", 6, 3, True),
+    "gn_dense7_3_cuda": ("gn", 7, 3, True), "lm_dense7_3_cuda": ("lm", 7, 3, True),
+    "gn_dense9_3_cuda": ("gn", 9, 3, True), "lm_dense9_3_cuda": ("lm", 9, 3, True),
 }
 
 
@@ -45,6 +51,8 @@ class CudaSolver:
         cfg = _lib.Config()
         self._L.g2ocu_default_config(ctypes.byref(cfg))
         cfg.device = device
+        if "_dense" in solver_name:
+            linear = "dense"
         cfg.linear_solver = {"pcg": _lib.LINEAR_PCG, "dense": _lib.LINEAR_DENSE}[linear]
         cfg.pcg_tolerance = pcg_tolerance
         cfg.pcg_max_iterations = pcg_max_iterations

@@ -22,6 +22,7 @@ using namespace g2ocu;
 namespace {
 
 std::string g_createError;
+const int64_t kDenseMaxN = 40000;   // dense FP64 Cholesky: n x n doubles (12.8 GB at the limit)
 
 double wallNow() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -82,6 +83,7 @@ struct g2ocu_solver {
   // device state
   DVec<double> poseEst, lmEst; std::vector<DVec<double>*> poseBackup, lmBackup; int stackDepth = 0;
   DVec<int> poseCounters, lmCounters;
+  DVec<double> denseH; DVec<int> denseInfo; int* hostInfo = nullptr;
   DVec<double> Hpp, Hll, Hpl, W, b, x, S, Dinv, dbv, bschur, Minv, vr, vd, vq, vs, scal, partial, partialDq, scratch, out2, dbg;
   DVec<int32_t> hppDiag, hplColPtr, hplRowIdx, sRowPtr, sColIdx, sDiag, hppToS, pairSlot, pairEdgeI, pairEdgeJ, aRowPtr, aColIdx, aDiag, spRow, spBegin, spEnd, hplLm, tEntLm, tEntBI, tEntBJ, tChunkI, tChunkJ, tChunkB, tChunkE;
   DVec<uint32_t> tEntMJ; DVec<uint8_t> tEntMI;
@@ -101,6 +103,7 @@ struct g2ocu_solver {
     for (auto& pe : pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto e : eventPool) cudaEventDestroy(e);
     if (hostScal) cudaFreeHost(hostScal);
+    if (hostInfo) cudaFreeHost(hostInfo);
     if (ownStream && stream) cudaStreamDestroy(stream);
   }
 };
@@ -119,6 +122,7 @@ int ensureCuda(g2ocu_solver* s) {
   if (s->cfg.stream) { s->stream = (cudaStream_t)s->cfg.stream; s->ownStream = false; }
   else { CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->ownStream = true; }
   CU(cudaMallocHost((void**)&s->hostScal, 64 * sizeof(double)));
+  CU(cudaMallocHost((void**)&s->hostInfo, 16 * sizeof(int)));
   s->cudaReady = true;
   return G2OCU_OK;
 }
@@ -440,7 +444,22 @@ int solvePcg(g2ocu_solver* s, const double* rhs) {
 int solveSystem(g2ocu_solver* s, int* solved) {
   const Structure& st = s->st;
   *solved = 1;
-  if (s->cfg.linear_solver != G2OCU_LINEAR_PCG) return fail(s, G2OCU_E_UNSUPPORTED, "dense Cholesky linear solver is not available in this build");
+  const bool dense = s->cfg.linear_solver == G2OCU_LINEAR_DENSE;
+  // LinearSolverDense::solve (linear_solver_dense.h:65-115): dense copy of the solved matrix, Cholesky, x = A^-1 rhs; false when not positive
+  auto solveDense = [&](const double* rhs) -> int {
+    PcgDev& pc = s->pcg;
+    pc.lambda = st.doSchur ? 0.0 : s->lambda;
+    const int64_t n = pc.n;
+    if (n > kDenseMaxN) return fail(s, G2OCU_E_UNSUPPORTED, "dense Cholesky is limited to systems of dimension <= " + std::to_string(kDenseMaxN) + " (this one has " + std::to_string(n) + "); use the PCG solver");
+    CU(s->denseH.alloc((size_t)n * n)); CU(s->denseInfo.alloc(1));
+    { PhaseTimer pt(s, "dense_assemble"); launchDenseAssemble(pc, s->denseH.p, s->stream, &s->launches); }
+    { PhaseTimer pt(s, "dense_cholesky"); launchDenseCholeskySolve(s->denseH.p, (int)n, rhs, s->x.p, s->denseInfo.p, s->stream, &s->launches); }
+    CU(cudaMemcpyAsync(s->hostInfo, s->denseInfo.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    int rc = syncStream(s); if (rc) return rc;
+    if (*s->hostInfo != 0) *solved = 0;
+    s->lastPcgIterations = 0;
+    return G2OCU_OK;
+  };
   auto broadcastPoseStep = [&]() -> int {   // the pose system is solved redundantly on every rank; rank 0's solution wins so that replicas stay bitwise identical
     if (s->world <= 1) return G2OCU_OK;
     if (s->rank != 0) CU(cudaMemsetAsync(s->x.p, 0, sizeof(double) * (size_t)st.sizePoses, s->stream));
@@ -448,7 +467,7 @@ int solveSystem(g2ocu_solver* s, int* solved) {
   };
   if (!st.doSchur) {
     PhaseTimer pt(s, "linear_solver");
-    int rc = solvePcg(s, s->b.p); if (rc) return rc;
+    int rc = dense ? solveDense(s->b.p) : solvePcg(s, s->b.p); if (rc) return rc;
     return broadcastPoseStep();
   }
   { PhaseTimer pt(s, "schur");
@@ -462,7 +481,7 @@ int solveSystem(g2ocu_solver* s, int* solved) {
       rc = allreduceDev(s, s->bschur.p, (int64_t)s->bschur.n, 0); if (rc) return rc;
     } }
   { PhaseTimer pt(s, "linear_solver");
-    int rc = solvePcg(s, s->bschur.p); if (rc) return rc;
+    int rc = dense ? solveDense(s->bschur.p) : solvePcg(s, s->bschur.p); if (rc) return rc;
     rc = broadcastPoseStep(); if (rc) return rc; }
   { PhaseTimer pt(s, "backsub");
     launchBacksub(s->schur, s->sys, s->hplLm.p, st.hplColPtr[st.lmEnd] - st.hplColPtr[st.lmBegin], s->x.p, s->x.p + st.sizePoses, s->stream, &s->launches); }
@@ -634,6 +653,10 @@ int g2ocu_set_property(g2ocu_solver* s, const char* name, double value) {
   else if (n == "pcgTolerance") s->cfg.pcg_tolerance = value;
   else if (n == "pcgMaxIterations") s->cfg.pcg_max_iterations = (int)value;
   else if (n == "pcgAbsoluteTolerance") s->cfg.pcg_absolute_tolerance = (int)value;
+  else if (n == "linearSolver") {
+    if ((int)value != G2OCU_LINEAR_PCG && (int)value != G2OCU_LINEAR_DENSE) return fail(s, G2OCU_E_INVALID, "unknown linear solver kind");
+    s->cfg.linear_solver = (int)value;
+  }
   else return fail(s, G2OCU_E_INVALID, "unknown property " + n);
   return G2OCU_OK;
 }

@@ -133,7 +133,8 @@ void SparseOptimizer::discardTop() { check(_handle, g2ocu_discard_top(_handle), 
 // ---------------------------------------------------------------------------------------------------------------
 template <int P, int L> bool CudaBlockSolver<P, L>::init(SparseOptimizer* optimizer, bool online) {
   _optimizer = optimizer;
-  return optimizer && check(optimizer->handle(), g2ocu_init(optimizer->handle(), online), "CudaBlockSolver::init");
+  if (!optimizer || !check(optimizer->handle(), g2ocu_set_property(optimizer->handle(), "linearSolver", _linearKind), "CudaBlockSolver::init")) return false;
+  return check(optimizer->handle(), g2ocu_init(optimizer->handle(), online), "CudaBlockSolver::init");
 }
 template <int P, int L> bool CudaBlockSolver<P, L>::buildStructure(bool) {
   g2ocu_solver* h = _optimizer->handle();

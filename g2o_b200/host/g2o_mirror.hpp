@@ -241,6 +241,8 @@ class SparseOptimizer : public OptimizableGraph {
 template <int P, int L> class CudaBlockSolver : public Solver {
  public:
   static const int PoseDim = P, LandmarkDim = L;
+  // which LinearSolver the reference BlockSolver would own (block_solver.h:124): LinearSolverPCG (default) or LinearSolverDense
+  explicit CudaBlockSolver(int linearSolverKind = G2OCU_LINEAR_PCG) : _linearKind(linearSolverKind) {}
   bool init(SparseOptimizer* optimizer, bool online = false) override;
   bool buildStructure(bool zeroBlocks = false) override;
   bool buildSystem() override;
@@ -255,7 +257,7 @@ template <int P, int L> class CudaBlockSolver : public Solver {
   size_t vectorSize() const override;
   void multiplyHessian(number_t* dest, const number_t* src) const override;
  private:
-  bool _doSchur = true;
+  bool _doSchur = true; int _linearKind = G2OCU_LINEAR_PCG;
   std::vector<number_t> _x, _b;
 };
 typedef CudaBlockSolver<-1, -1> CudaBlockSolverX;

@@ -23,7 +23,8 @@ static OptimizationAlgorithm* make(const std::string& name) {
 static void testFactory() {
   std::stringstream ss; OptimizationAlgorithmFactory::instance()->listSolvers(ss);
   const std::string s = ss.str();
-  for (const char* n : {"gn_var_cuda", "lm_var_cuda", "gn_fix3_2_cuda", "lm_fix3_2_cuda", "gn_fix6_3_cuda", "lm_fix6_3_cuda", "gn_fix7_3_cuda", "lm_fix7_3_cuda", "lm_fix9_3_cuda"})
+  for (const char* n : {"gn_var_cuda", "lm_var_cuda", "gn_fix3_2_cuda", "lm_fix3_2_cuda", "gn_fix6_3_cuda", "lm_fix6_3_cuda", "gn_fix7_3_cuda", "lm_fix7_3_cuda", "lm_fix9_3_cuda",
+                        "gn_dense_cuda", "lm_dense_cuda", "lm_dense3_2_cuda", "lm_dense6_3_cuda", "lm_dense7_3_cuda", "lm_dense9_3_cuda"})
     EXPECT(s.find(n) != std::string::npos);
   OptimizationAlgorithmProperty p;
   OptimizationAlgorithm* a = OptimizationAlgorithmFactory::instance()->construct("lm_fix6_3_cuda", p);
@@ -35,9 +36,9 @@ static void testFactory() {
   EXPECT(OptimizationAlgorithmFactory::instance()->construct("lm_var_cholmod", p) == nullptr);   // not ours
 }
 
-static void edgeSE3Problem(bool rotation) {
+static void edgeSE3Problem(bool rotation, const char* solver = "lm_var_cuda") {
   SparseOptimizer optimizer;
-  optimizer.setAlgorithm(make("lm_var_cuda"));
+  optimizer.setAlgorithm(make(solver));
   VertexSE3* v = new VertexSE3(); v->setId(0); v->setFixed(true); optimizer.addVertex(v);
   v = new VertexSE3(); v->setId(1);
   double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
@@ -149,6 +150,8 @@ int main() {
   testGraphOperations();
   edgeSE3Problem(false);
   edgeSE3Problem(true);
+  edgeSE3Problem(false, "lm_dense_cuda");   // the same two problems through BlockSolverX + LinearSolverDense (device Cholesky)
+  edgeSE3Problem(true, "lm_dense_cuda");
   testClearAndRedo();
   testBundleAdjustment();
   if (g_failures) { std::printf("HOST_TESTS_FAILED %d\n", g_failures); return 1; }

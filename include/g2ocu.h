@@ -158,7 +158,7 @@ int g2ocu_create(const g2ocu_config* cfg, g2ocu_solver** out);
 void g2ocu_destroy(g2ocu_solver* s);
 
 int g2ocu_set_graph(g2ocu_solver* s, const g2ocu_graph* g);
-int g2ocu_set_property(g2ocu_solver* s, const char* name, double value);  /* "initialLambda", "maxTrialsAfterFailure" (levenberg.cpp:48-49) */
+int g2ocu_set_property(g2ocu_solver* s, const char* name, double value);  /* "initialLambda", "maxTrialsAfterFailure" (levenberg.cpp:48-49); "pcgTolerance", "pcgMaxIterations", "pcgAbsoluteTolerance" (linear_solver_pcg.h:53-57); "linearSolver" = G2OCU_LINEAR_* (which LinearSolver the BlockSolver owns, block_solver.h:124) */
 int g2ocu_set_shard(g2ocu_solver* s, int32_t rank, int32_t world, g2ocu_allreduce_fn fn, void* user);
 
 int g2ocu_initialize_optimization(g2ocu_solver* s, int32_t level);

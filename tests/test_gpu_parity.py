@@ -123,3 +123,45 @@ def test_multiply_hessian_and_second_optimize_continues():
             if r != c:
                 y[c * 9:(c + 1) * 9] += B.T @ v[r * 9:(r + 1) * 9]
     assert rel(hv, y) < 1e-12
+
+
+DENSE = {
+    "ba_demo": ("lm_fix6_3_cuda", lambda: W.ba_demo()),
+    "bal_medium": ("lm_fix9_3_cuda", lambda: W.bal_synthetic(n_cameras=60, n_points=6000, n_obs=30000, seed=5, k_max=40, min_window=4)),
+    "sphere": ("lm_var_cuda", lambda: W.sphere(nodes_per_level=16, laps=8)),
+    "slam2d": ("lm_fix3_2_cuda", lambda: W.slam2d(n_poses=800, n_landmarks=200, world_size=30.0)),
+}
+
+
+@pytest.mark.parametrize("name", list(DENSE))
+def test_dense_cholesky_trajectory(name):
+    """LinearSolverDense semantics (linear_solver_dense.h:65-115) on the device: DMMA Cholesky of the dense (reduced) system."""
+    solver, fn = DENSE[name]
+    g = fn()
+    s = CudaSolver(g, solver, linear="dense", device=0); s.initialize_optimization()
+    o = Oracle(g, "lm", "dense"); assert o.initialize_optimization()
+    n, st = s.optimize(6); no, sto = o.optimize(6)
+    assert n == no and len(st) == len(sto)
+    for i, (a, b) in enumerate(zip(st, sto)):
+        tol = 1e-8 if i == 0 else 1e-6
+        assert abs(a["chi2"] - b["chi2"]) <= tol * abs(b["chi2"]), (i, a["chi2"], b["chi2"])
+        assert a["levenberg_iterations"] == int(b["levenbergIterations"]), i
+        assert abs(a["lambda"] - b["lambda"]) <= 1e-6 * abs(b["lambda"]), i
+    eo = o.estimates()
+    assert np.max(np.abs(s.get_estimates() - eo) / (1.0 + np.abs(eo))) < 1e-6
+
+
+def test_dense_cholesky_solution_and_failure():
+    g = W.bal_synthetic(n_cameras=40, n_points=3000, n_obs=15000, seed=3, k_max=30, min_window=4)
+    s = CudaSolver(g, "lm_fix9_3_cuda", linear="dense", device=0); s.initialize_optimization()
+    p = CudaSolver(g, "lm_fix9_3_cuda", linear="pcg", device=0, pcg_tolerance=1e-14); p.initialize_optimization()
+    for t in (s, p):
+        t.init(); t.build_structure(); t.compute_active_errors(); t.build_system()
+    lam = s.compute_lambda_init()
+    s.set_lambda(lam); p.set_lambda(lam)
+    assert s.solve() and p.solve()
+    # direct factorisation against a PCG run to 1e-14: same linear system, same solution
+    assert rel(s.x(), p.x()) < 1e-7
+    s.restore_diagonal()
+    s.set_lambda(-1e15)                      # indefinite system: the reference's LDLT reports !isPositive() and solve() returns false
+    assert not s.solve()
