@@ -80,6 +80,7 @@ struct g2ocu_solver {
   bool fastEstimates = false; int64_t poseHostOff = 0, lmHostOff = 0;
   // sharding
   int rank = 0, world = 1; g2ocu_allreduce_fn allreduce = nullptr; void* allreduceUser = nullptr;
+  int64_t slabBlocks = 0;         // blocks of the reduced system per rank (slab PCG), 0 when not sharded
   // device state
   DVec<double> poseEst, lmEst; std::vector<DVec<double>*> poseBackup, lmBackup; int stackDepth = 0;
   DVec<int> poseCounters, lmCounters;
@@ -147,7 +148,9 @@ void resolveEvents(g2ocu_solver* s) {
 int syncStream(g2ocu_solver* s) { CU(cudaStreamSynchronize(s->stream)); resolveEvents(s); return G2OCU_OK; }
 double phaseSeconds(g2ocu_solver* s, const char* ph) { auto it = s->phases.find(ph); return it == s->phases.end() ? 0.0 : it->second.seconds; }
 
-int allreduceDev(g2ocu_solver* s, double* buf, int64_t count, int op) {
+int collectiveDev(g2ocu_solver* s, double* buf, int64_t count, int op);
+int allreduceDev(g2ocu_solver* s, double* buf, int64_t count, int op) { return collectiveDev(s, buf, count, op); }
+int collectiveDev(g2ocu_solver* s, double* buf, int64_t count, int op) {
   if (s->world <= 1) return G2OCU_OK;
   if (!s->allreduce) return fail(s, G2OCU_E_COMM, "world > 1 but no allreduce hook was set");
   if (s->allreduce(buf, count, op, (void*)s->stream, s->allreduceUser) != 0) return fail(s, G2OCU_E_COMM, "allreduce hook reported an error");
@@ -341,7 +344,9 @@ int buildDevice(g2ocu_solver* s) {
       sd.entLm = s->tEntLm.p; sd.entBaseI = s->tEntBI.p; sd.entBaseJ = s->tEntBJ.p; sd.entMaskJ = s->tEntMJ.p; sd.entMaskI = s->tEntMI.p;
     }
     if (useMma) { CU(s->W.alloc((size_t)st.hplRowIdx.size() * P * L + 2)); CU(s->W.zero(stream)); sd.W = s->W.p; }
-    CU(s->S.alloc((size_t)st.sColIdx.size() * P * P)); CU(s->Dinv.alloc((size_t)st.numLandmarks * L * L)); CU(s->dbv.alloc((size_t)st.numLandmarks * L)); CU(s->bschur.alloc((size_t)st.sizePoses));
+    // multi-GPU: the reduced system is reduce-scattered into equal block ranges (the last one padded), rank r solves with blocks [r c, (r+1) c)
+    CU(s->S.alloc(s->world > 1 ? (size_t)s->slabBlocks * s->world * P * P : (size_t)st.sColIdx.size() * P * P)); CU(s->S.zero(stream));
+    CU(s->Dinv.alloc((size_t)st.numLandmarks * L * L)); CU(s->dbv.alloc((size_t)st.numLandmarks * L)); CU(s->bschur.alloc((size_t)st.sizePoses));
     sd.numPoses = st.numPoses; sd.numLandmarks = st.numLandmarks; sd.P = P; sd.L = L;
     sd.lmBegin = st.lmBegin; sd.lmEnd = st.lmEnd; sd.blockBegin = st.hplColPtr[st.lmBegin];
     sd.hplColPtr = s->hplColPtr.p; sd.hplRowIdx = s->hplRowIdx.p; sd.sRowPtr = s->sRowPtr.p; sd.sColIdx = s->sColIdx.p; sd.sDiag = s->sDiag.p;
@@ -359,8 +364,13 @@ int buildDevice(g2ocu_solver* s) {
   {
     const int G = 32 / P, chunk = G * 16;
     std::vector<int32_t> r, bgn, en;
-    for (int i = 0; i < st.numPoses; ++i)
-      for (int k = rowPtr[i]; k < rowPtr[i + 1]; k += chunk) { r.push_back(i); bgn.push_back(k); en.push_back(std::min(k + chunk, rowPtr[i + 1])); }
+    const bool slab = s->world > 1 && st.doSchur;
+    const int64_t lo = slab ? s->slabBlocks * s->rank : 0, hi = slab ? std::min<int64_t>(s->slabBlocks * (s->rank + 1), (int64_t)colIdx.size()) : (int64_t)colIdx.size();
+    for (int i = 0; i < st.numPoses; ++i) {
+      const int kb = (int)std::max<int64_t>(rowPtr[i], lo), ke = (int)std::min<int64_t>(rowPtr[i + 1], hi);
+      for (int k = kb; k < ke; k += chunk) { r.push_back(i); bgn.push_back(k); en.push_back(std::min(k + chunk, ke)); }
+    }
+    pc.ownLo = (int)lo; pc.ownHi = (int)hi;
     CU(s->spRow.upload(r, stream)); CU(s->spBegin.upload(bgn, stream)); CU(s->spEnd.upload(en, stream));
     pc.nItems = (int)r.size();
     CU(cudaStreamSynchronize(stream));
@@ -417,8 +427,10 @@ int buildSystem(g2ocu_solver* s) {
 int solvePcg(g2ocu_solver* s, const double* rhs) {
   PcgDev& pc = s->pcg;
   pc.lambda = s->st.doSchur ? 0.0 : s->lambda;
+  const bool slab = s->world > 1 && s->st.doSchur;   // row-range SpMV per rank, q summed over the ranks; all vector recurrences replicated
   { PhaseTimer pt(s, "pcg_setup");
     launchBlockInverse(pc, s->stream, &s->launches);
+    if (slab) { int rc = allreduceDev(s, pc.Minv, (int64_t)pc.nb * pc.P * pc.P, 0); if (rc) return rc; }   // every rank inverts the diagonal blocks it owns
     launchPcgInit(pc, rhs, s->cfg.pcg_tolerance, s->pcgResidual, s->cfg.pcg_absolute_tolerance, s->stream, &s->launches); }
   const int maxIter = s->cfg.pcg_max_iterations < 0 ? pc.n : s->cfg.pcg_max_iterations;
   int issued = 0; bool done = false;
@@ -427,6 +439,7 @@ int solvePcg(g2ocu_solver* s, const double* rhs) {
     const int batch = std::min(kCheckEvery, maxIter - issued);
     for (int k = 0; k < batch; ++k) {
       { PhaseTimer pt(s, "pcg_spmv"); launchSpmv(pc, pc.d, pc.q, s->stream, &s->launches); }
+      if (slab) { PhaseTimer pt(s, "pcg_exchange"); int rc = allreduceDev(s, pc.q, pc.n, 0); if (rc) return rc; }
       { PhaseTimer pt(s, "pcg_vec"); launchPcgTail(pc, s->stream, &s->launches); }
     }
     issued += batch;
@@ -477,7 +490,8 @@ int solveSystem(g2ocu_solver* s, int* solved) {
     marks.end = [](void* c) { auto* m = (MarkCtx*)c; delete m->t; m->t = nullptr; };
     launchSchur(s->schur, s->sys, s->hplLm.p, st.hplColPtr[st.lmEnd] - st.hplColPtr[st.lmBegin], s->lambda, s->rank == 0 ? s->lambda : 0.0, s->stream, &s->launches, &marks);
     if (s->world > 1) {
-      int rc = allreduceDev(s, s->S.p, (int64_t)s->S.n, 0); if (rc) return rc;
+      PhaseTimer pt2(s, "schur_exchange");
+      int rc = collectiveDev(s, s->S.p, s->slabBlocks * st.P * st.P, G2OCU_OP_REDUCE_SCATTER_SUM); if (rc) return rc;   // rank r keeps the sum of its block range
       rc = allreduceDev(s, s->bschur.p, (int64_t)s->bschur.n, 0); if (rc) return rc;
     } }
   { PhaseTimer pt(s, "linear_solver");
@@ -705,6 +719,7 @@ int g2ocu_build_structure(g2ocu_solver* s) {
     if (naturalPL != es.poseLandmark || (naturalPL && naturalSide != es.poseSide))
       return fail(s, G2OCU_E_UNSUPPORTED, "edge type " + std::to_string(es.etype) + ": the landmark-side vertices must be marginalized and the pose-side vertices must not (mixed block sizes are not supported)");
   }
+  s->slabBlocks = st.doSchur ? (int64_t)((st.sColIdx.size() + s->world - 1) / s->world) : 0;   // equal block ranges of the reduced system (slab PCG)
   int rc = ensureCuda(s); if (rc) return rc;
   rc = buildDevice(s); if (rc) return rc;
   s->structureBuilt = true; s->lambda = 0.0; s->stackDepth = 0;
@@ -867,6 +882,11 @@ int64_t g2ocu_get_i32(g2ocu_solver* s, const char* name, int32_t* out, int64_t c
   if (n == "hschur_t_rowidx") return copyOutI32(st.sColIdx, out, cap);
   if (n == "edge_targets") return copyOutI32(st.edgeTargets, out, cap);
   if (n == "shard_landmark_range") return copyOutI32({st.lmBegin, st.lmEnd}, out, cap);
+  if (n == "slab_block_range") {   // blocks of the reduced system this rank solves with (CSR order); everything when not sharded
+    const int64_t nnz = (int64_t)st.sColIdx.size();
+    const int64_t lo = s->world > 1 ? std::min(nnz, s->slabBlocks * s->rank) : 0, hi = s->world > 1 ? std::min(nnz, s->slabBlocks * (s->rank + 1)) : nnz;
+    return copyOutI32({(int32_t)lo, (int32_t)hi}, out, cap);
+  }
   if (n == "shard_edge_positions") { std::vector<int32_t> v; for (const EdgeSet& es : st.sets) v.insert(v.end(), es.pos.begin(), es.pos.end()); return copyOutI32(v, out, cap); }
   return fail(s, G2OCU_E_INVALID, "unknown int32 array " + n);
 }

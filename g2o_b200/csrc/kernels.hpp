@@ -89,6 +89,7 @@ struct PcgDev {
   double* partial = nullptr; int nPartial = 0;          // one per CTA of the block-row kernels: ceil(nb/128)
   double* partialDq = nullptr; int nPartialDq = 0;      // one per CTA of the dot kernel
   const int32_t* itemRow = nullptr; const int32_t* itemBegin = nullptr; const int32_t* itemEnd = nullptr; int nItems = 0;   // SpMV work items (row, block range)
+  int ownLo = 0, ownHi = 0;                // blocks of A this rank owns (slab PCG); the whole matrix when not sharded
 };
 void launchBlockInverse(const PcgDev& p, cudaStream_t st, int64_t* launches);
 void launchPcgInit(const PcgDev& p, const double* b, double tolerance, double residual, int absoluteTolerance, cudaStream_t st, int64_t* launches);   // x=0, r=b, d=M^-1 r, dn=r.d, d0

@@ -305,6 +305,11 @@ template <int P> __global__ void block_inverse_kernel(PcgDev p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.nb) return;
   double A[PP], X[PP];
+  if (p.diag[i] < p.ownLo || p.diag[i] >= p.ownHi) {   // slab PCG: another rank owns (and inverts) this diagonal block; zero so that the sum over ranks is the inverse
+    double* dst = p.Minv + (size_t)i * PP;
+    for (int q = 0; q < PP; ++q) dst[q] = 0.0;
+    return;
+  }
   const double* src = p.A + (size_t)p.diag[i] * PP;
 #pragma unroll
   for (int q = 0; q < PP; ++q) { A[q] = src[q]; X[q] = 0; }

@@ -16,24 +16,35 @@ class _DevicePointer:
 
 
 def make_allreduce(backend_is_cuda: bool = True, group=None):
-    """Returns ``fn(ptr, count, op, stream) -> int`` for :meth:`CudaSolver.set_shard`.  ``op`` 0 = sum, 1 = max.
+    """Returns ``fn(ptr, count, op, stream) -> int`` for :meth:`CudaSolver.set_shard`.  ``op`` 0 = sum, 1 = max, 2 = in-place
+    reduce-scatter of ``world * count`` doubles.
     With a CUDA backend the collective is enqueued in stream order on the solver's stream (no host synchronisation);
     with gloo (CPU tests) ``ptr`` is a host pointer."""
     import torch
     import torch.distributed as dist
 
+    world = dist.get_world_size(group); rank = dist.get_rank(group)
+
+    def run(t, op):
+        if op == 2:     # in-place reduce-scatter: rank r keeps the sum of range r (g2ocu.h: G2OCU_OP_REDUCE_SCATTER_SUM)
+            count = t.numel() // world
+            if backend_is_cuda:
+                dist.reduce_scatter_tensor(t[rank * count:(rank + 1) * count], t, op=dist.ReduceOp.SUM, group=group)
+            else:       # gloo has no reduce_scatter: all-reduce is a superset of the contract
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MAX, group=group)
+
     def fn(ptr, count, op, stream):
-        rop = dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MAX
+        total = count * world if op == 2 else count
         if backend_is_cuda:
-            t = torch.as_tensor(_DevicePointer(ptr, count), device="cuda")
+            t = torch.as_tensor(_DevicePointer(ptr, total), device="cuda")
             ext = torch.cuda.ExternalStream(stream) if stream else torch.cuda.current_stream()
             with torch.cuda.stream(ext):
-                dist.all_reduce(t, op=rop, group=group)
+                run(t, op)
         else:
-            buf = (ctypes.c_double * count).from_address(ptr)
-            a = np.frombuffer(buf, dtype=np.float64)
-            t = torch.from_numpy(a)
-            dist.all_reduce(t, op=rop, group=group)
+            buf = (ctypes.c_double * total).from_address(ptr)
+            run(torch.from_numpy(np.frombuffer(buf, dtype=np.float64)), op)
         return 0
     return fn
 

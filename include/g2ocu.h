@@ -145,9 +145,15 @@ typedef struct g2ocu_iteration_stats {
   int64_t hessian_landmark_dimension;
 } g2ocu_iteration_stats;
 
-/* Collective hook for landmark-sharded multi-GPU runs: in-place sum (op 0) or max (op 1) over all ranks of
- * `count` doubles at DEVICE pointer `buf`, ordered after all work already enqueued on `stream`; returns 0 on
- * success.  Supplied by the host (torch.distributed / NCCL); never called when world == 1. */
+/* Collective hook for landmark-sharded multi-GPU runs, ordered after all work already enqueued on `stream`; returns 0 on
+ * success.  Supplied by the host (torch.distributed / NCCL); never called when world == 1.  `buf` is a DEVICE pointer.
+ *   op G2OCU_OP_SUM / G2OCU_OP_MAX        in-place all-reduce of `count` doubles
+ *   op G2OCU_OP_REDUCE_SCATTER_SUM        in-place reduce-scatter: `buf` holds world * `count` doubles, afterwards rank r holds the
+ *                                         sum over all ranks of buf[r * count, (r + 1) * count) in that same range (the NCCL
+ *                                         in-place convention); the other ranges are unspecified                              */
+#define G2OCU_OP_SUM 0
+#define G2OCU_OP_MAX 1
+#define G2OCU_OP_REDUCE_SCATTER_SUM 2
 typedef int (*g2ocu_allreduce_fn)(void* buf, int64_t count, int32_t op, void* stream, void* user);
 
 void g2ocu_default_config(g2ocu_config* cfg);

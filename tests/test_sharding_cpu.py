@@ -37,6 +37,10 @@ def test_partition_covers_every_edge_once():
                 s = _host(g, name, rank, world)
                 seen[s.get_i32("shard_edge_positions")] += 1
                 ranges.append(tuple(s.get_i32("shard_landmark_range")))
+                if dims[1]:   # slab PCG: equal, contiguous block ranges of the reduced system, covering it exactly once
+                    lo, hi = s.get_i32("slab_block_range")
+                    nnz = int(ref.get_i32("hschur_colptr")[-1]); c = -(-nnz // world)
+                    assert (lo, hi) == (min(nnz, rank * c), min(nnz, (rank + 1) * c))
                 # the global structure is identical on every rank
                 for arr in ("hessian_index", "hpp_colptr", "hpp_rowidx"):
                     assert np.array_equal(s.get_i32(arr), ref.get_i32(arr))
@@ -63,6 +67,10 @@ def _gloo_worker(rank, world, port, q):
     assert fn(a.ctypes.data, a.size, 0, 0) == 0
     b = np.array([rank, -rank, 3.5], dtype=np.float64)
     assert fn(b.ctypes.data, b.size, 1, 0) == 0
+    c = np.arange(3 * world, dtype=np.float64) * (rank + 1)          # in-place reduce-scatter: rank r keeps the sum of range r
+    assert fn(c.ctypes.data, 3, 2, 0) == 0
+    expect = np.arange(3 * world, dtype=np.float64) * sum(range(1, world + 1))
+    assert np.array_equal(c[3 * rank:3 * rank + 3], expect[3 * rank:3 * rank + 3])
     q.put((rank, a.tolist(), b.tolist()))
     dist.destroy_process_group()
 
