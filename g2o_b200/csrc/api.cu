@@ -203,7 +203,7 @@ int buildDevice(g2ocu_solver* s) {
   const int P = st.P, L = st.L;
   // ---- system matrices ----
   CU(s->hppDiag.upload(st.hppDiag, stream));
-  CU(s->Hpp.alloc((size_t)st.hppColIdx.size() * P * P));
+  CU(s->Hpp.alloc((size_t)st.hppColIdx.size() * P * P + 2));   // +2: see S
   CU(s->b.alloc((size_t)st.sizePoses + st.sizeLandmarks)); CU(s->x.alloc((size_t)st.sizePoses + st.sizeLandmarks));
   CU(s->b.zero(stream)); CU(s->x.zero(stream)); CU(s->Hpp.zero(stream));
   SystemDev& sys = s->sys;
@@ -345,7 +345,7 @@ int buildDevice(g2ocu_solver* s) {
     }
     if (useMma) { CU(s->W.alloc((size_t)st.hplRowIdx.size() * P * L + 2)); CU(s->W.zero(stream)); sd.W = s->W.p; }
     // multi-GPU: the reduced system is reduce-scattered into equal block ranges (the last one padded), rank r solves with blocks [r c, (r+1) c)
-    CU(s->S.alloc(s->world > 1 ? (size_t)s->slabBlocks * s->world * P * P : (size_t)st.sColIdx.size() * P * P)); CU(s->S.zero(stream));
+    CU(s->S.alloc((s->world > 1 ? (size_t)s->slabBlocks * s->world * P * P : (size_t)st.sColIdx.size() * P * P) + 2)); CU(s->S.zero(stream));   // +2: 16-byte aligned bulk copies may read one double past the last block
     CU(s->Dinv.alloc((size_t)st.numLandmarks * L * L)); CU(s->dbv.alloc((size_t)st.numLandmarks * L)); CU(s->bschur.alloc((size_t)st.sizePoses));
     sd.numPoses = st.numPoses; sd.numLandmarks = st.numLandmarks; sd.P = P; sd.L = L;
     sd.lmBegin = st.lmBegin; sd.lmEnd = st.lmEnd; sd.blockBegin = st.hplColPtr[st.lmBegin];
@@ -418,7 +418,7 @@ int buildSystem(g2ocu_solver* s) {
   for (auto* es : s->sets) launchBuild(es->dev, s->sys, s->stream, &s->launches);
   CU(cudaGetLastError());
   if (s->world > 1 && !s->st.doSchur) {   // pose graphs are sharded by edge: every rank needs the full Hpp and b for the replicated solve
-    int rc = allreduceDev(s, s->Hpp.p, (int64_t)s->Hpp.n, 0); if (rc) return rc;
+    int rc = allreduceDev(s, s->Hpp.p, (int64_t)s->st.hppColIdx.size() * s->st.P * s->st.P, 0); if (rc) return rc;
     rc = allreduceDev(s, s->b.p, (int64_t)s->b.n, 0); if (rc) return rc;
   }
   return G2OCU_OK;
