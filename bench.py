@@ -135,8 +135,11 @@ def run_ours(args):
     est0 = g.v_estimate.copy()
     s = CudaSolver(g, "lm_fix9_3_cuda", device=local)
     if world > 1:
-        from g2o_b200.dist import install_torch_allreduce
-        install_torch_allreduce(s, rank, world)
+        from g2o_b200.dist import install_nccl, install_torch_allreduce
+        if os.environ.get("G2O_BENCH_COLLECTIVES", "nccl") == "hook":
+            install_torch_allreduce(s, rank, world)      # every collective through the Python callback (debug)
+        else:
+            install_nccl(s, rank, world)                 # collectives issued by libg2ocu.so itself
     s.initialize_optimization()
     s.init()
 

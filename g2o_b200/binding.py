@@ -103,6 +103,11 @@ class CudaSolver:
             self._hook = _lib.ALLREDUCE_FN(0)
         self._ck(self._L.g2ocu_set_shard(self._h, rank, world, self._hook, None))
 
+    def set_shard_nccl(self, rank: int, world: int, nccl_library: str, unique_id: bytes):
+        """Collectives issued by the library itself through NCCL (g2ocu_set_shard_nccl); every rank must call it."""
+        assert len(unique_id) == 128
+        self._ck(self._L.g2ocu_set_shard_nccl(self._h, rank, world, nccl_library.encode(), unique_id))
+
     # ---- SparseOptimizer ----
     def initialize_optimization(self, level: int = 0) -> bool:
         self._ck(self._L.g2ocu_initialize_optimization(self._h, level))

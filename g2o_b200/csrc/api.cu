@@ -3,6 +3,7 @@
 // OptimizationAlgorithmGaussNewton::solve (optimization_algorithm_gauss_newton.cpp:50-91) and
 // SparseOptimizer::optimize (sparse_optimizer.cpp:374-439); all per-edge / per-block arithmetic runs in the kernels.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <chrono>
@@ -25,6 +26,34 @@ std::string g_createError;
 const int64_t kDenseMaxN = 40000;   // dense FP64 Cholesky: n x n doubles (12.8 GB at the limit)
 
 double wallNow() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// NCCL is resolved at run time from the library the host names (torch ships one); only the handful of entry points used here.
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, struct NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*ReduceScatter)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+struct NcclId { char internal[128]; };
+NcclApi g_nccl;
+bool loadNccl(const char* path, std::string& err) {
+  if (g_nccl.handle) return true;
+  void* h = dlopen(path && *path ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { err = std::string("dlopen(") + (path ? path : "libnccl.so.2") + "): " + dlerror(); return false; }
+  NcclApi a; a.handle = h;
+  a.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+  a.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+  a.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+  a.ReduceScatter = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclReduceScatter");
+  a.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  a.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.ReduceScatter || !a.CommDestroy || !a.GetErrorString) { err = "the NCCL library lacks a required symbol"; dlclose(h); return false; }
+  g_nccl = a;
+  return true;
+}
 
 template <class T> struct DVec {
   T* p = nullptr; size_t n = 0;
@@ -81,10 +110,11 @@ struct g2ocu_solver {
   // sharding
   int rank = 0, world = 1; g2ocu_allreduce_fn allreduce = nullptr; void* allreduceUser = nullptr;
   int64_t slabBlocks = 0;         // blocks of the reduced system per rank (slab PCG), 0 when not sharded
+  void* ncclComm = nullptr;       // set by g2ocu_set_shard_nccl: collectives go straight to NCCL on the solver's stream
   // device state
   DVec<double> poseEst, lmEst; std::vector<DVec<double>*> poseBackup, lmBackup; int stackDepth = 0;
   DVec<int> poseCounters, lmCounters;
-  DVec<double> denseH; DVec<int> denseInfo; int* hostInfo = nullptr;
+  DVec<double> denseH; DVec<int> denseInfo; DVec<unsigned int> pcgTicket; int* hostInfo = nullptr;
   DVec<double> Hpp, Hll, Hpl, W, b, x, S, Dinv, dbv, bschur, Minv, vr, vd, vq, vs, scal, partial, partialDq, scratch, out2, dbg;
   DVec<int32_t> hppDiag, hplColPtr, hplRowIdx, sRowPtr, sColIdx, sDiag, hppToS, pairSlot, pairEdgeI, pairEdgeJ, aRowPtr, aColIdx, aDiag, spRow, spBegin, spEnd, hplLm, tEntLm, tEntBI, tEntBJ, tChunkI, tChunkJ, tChunkB, tChunkE;
   DVec<uint32_t> tEntMJ; DVec<uint8_t> tEntMI;
@@ -103,6 +133,7 @@ struct g2ocu_solver {
     for (auto* b2 : lmBackup) delete b2;
     for (auto& pe : pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto e : eventPool) cudaEventDestroy(e);
+    if (ncclComm && g_nccl.CommDestroy) g_nccl.CommDestroy(ncclComm);
     if (hostScal) cudaFreeHost(hostScal);
     if (hostInfo) cudaFreeHost(hostInfo);
     if (ownStream && stream) cudaStreamDestroy(stream);
@@ -152,7 +183,15 @@ int collectiveDev(g2ocu_solver* s, double* buf, int64_t count, int op);
 int allreduceDev(g2ocu_solver* s, double* buf, int64_t count, int op) { return collectiveDev(s, buf, count, op); }
 int collectiveDev(g2ocu_solver* s, double* buf, int64_t count, int op) {
   if (s->world <= 1) return G2OCU_OK;
-  if (!s->allreduce) return fail(s, G2OCU_E_COMM, "world > 1 but no allreduce hook was set");
+  if (s->ncclComm) {
+    const int kF64 = 8, kSum = 0, kMax = 2;   // ncclFloat64, ncclSum, ncclMax (nccl.h)
+    int rc;
+    if (op == G2OCU_OP_REDUCE_SCATTER_SUM) rc = g_nccl.ReduceScatter(buf, buf + (size_t)s->rank * count, (size_t)count, kF64, kSum, s->ncclComm, s->stream);
+    else rc = g_nccl.AllReduce(buf, buf, (size_t)count, kF64, op == G2OCU_OP_MAX ? kMax : kSum, s->ncclComm, s->stream);
+    if (rc != 0) return fail(s, G2OCU_E_COMM, std::string("NCCL: ") + g_nccl.GetErrorString(rc));
+    return G2OCU_OK;
+  }
+  if (!s->allreduce) return fail(s, G2OCU_E_COMM, "world > 1 but neither an allreduce hook nor an NCCL communicator was set");
   if (s->allreduce(buf, count, op, (void*)s->stream, s->allreduceUser) != 0) return fail(s, G2OCU_E_COMM, "allreduce hook reported an error");
   return G2OCU_OK;
 }
@@ -383,6 +422,7 @@ int buildDevice(g2ocu_solver* s) {
   pc.Minv = s->Minv.p; pc.r = s->vr.p; pc.d = s->vd.p; pc.q = s->vq.p; pc.s = s->vs.p; pc.x = s->x.p; pc.scal = s->scal.p; pc.partial = s->partial.p; pc.partialDq = s->partialDq.p;
   pc.itemRow = s->spRow.p; pc.itemBegin = s->spBegin.p; pc.itemEnd = s->spEnd.p;
   CU(s->scal.zero(stream));
+  CU(s->pcgTicket.alloc(4)); CU(s->pcgTicket.zero(stream)); pc.ticket = s->pcgTicket.p;
   CU(cudaStreamSynchronize(stream));
   CU(cudaGetLastError());
   return G2OCU_OK;
@@ -438,7 +478,7 @@ int solvePcg(g2ocu_solver* s, const double* rhs) {
   while (!done) {
     const int batch = std::min(kCheckEvery, maxIter - issued);
     for (int k = 0; k < batch; ++k) {
-      { PhaseTimer pt(s, "pcg_spmv"); launchSpmv(pc, pc.d, pc.q, s->stream, &s->launches); }
+      { PhaseTimer pt(s, "pcg_spmv"); launchSpmv(pc, pc.d, pc.q, s->stream, &s->launches, issued + k > 0 && pcgSingleCtaTail(pc)); }
       if (slab) { PhaseTimer pt(s, "pcg_exchange"); int rc = allreduceDev(s, pc.q, pc.n, 0); if (rc) return rc; }
       { PhaseTimer pt(s, "pcg_vec"); launchPcgTail(pc, s->stream, &s->launches); }
     }
@@ -678,6 +718,30 @@ int g2ocu_set_shard(g2ocu_solver* s, int32_t rank, int32_t world, g2ocu_allreduc
   if (!s || world < 1 || rank < 0 || rank >= world) return fail(s, G2OCU_E_INVALID, "bad rank/world");
   if (world > 1 && !fn) return fail(s, G2OCU_E_INVALID, "world > 1 needs an allreduce hook");
   s->rank = rank; s->world = world; s->allreduce = fn; s->allreduceUser = user;
+  s->structureBuilt = false;
+  return G2OCU_OK;
+}
+
+int g2ocu_nccl_unique_id(const char* nccl_library, unsigned char unique_id[128]) {
+  std::string err;
+  if (!unique_id) return G2OCU_E_INVALID;
+  if (!loadNccl(nccl_library, err)) return fail(nullptr, G2OCU_E_COMM, err);
+  NcclId id;
+  const int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) return fail(nullptr, G2OCU_E_COMM, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc));
+  std::memcpy(unique_id, id.internal, 128);
+  return G2OCU_OK;
+}
+int g2ocu_set_shard_nccl(g2ocu_solver* s, int32_t rank, int32_t world, const char* nccl_library, const unsigned char unique_id[128]) {
+  if (!s || world < 1 || rank < 0 || rank >= world || !unique_id) return fail(s, G2OCU_E_INVALID, "bad rank/world/unique id");
+  std::string err;
+  if (!loadNccl(nccl_library, err)) return fail(s, G2OCU_E_COMM, err);
+  int rc = ensureCuda(s); if (rc) return rc;
+  if (s->ncclComm) { g_nccl.CommDestroy(s->ncclComm); s->ncclComm = nullptr; }
+  NcclId id; std::memcpy(id.internal, unique_id, 128);
+  const int nrc = g_nccl.CommInitRank(&s->ncclComm, world, id, rank);
+  if (nrc != 0) { s->ncclComm = nullptr; return fail(s, G2OCU_E_COMM, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(nrc)); }
+  s->rank = rank; s->world = world; s->allreduce = nullptr; s->allreduceUser = nullptr;
   s->structureBuilt = false;
   return G2OCU_OK;
 }

@@ -89,12 +89,14 @@ struct PcgDev {
   double* partial = nullptr; int nPartial = 0;          // one per CTA of the block-row kernels: ceil(nb/128)
   double* partialDq = nullptr; int nPartialDq = 0;      // one per CTA of the dot kernel
   const int32_t* itemRow = nullptr; const int32_t* itemBegin = nullptr; const int32_t* itemEnd = nullptr; int nItems = 0;   // SpMV work items (row, block range)
+  unsigned int* ticket = nullptr;          // zero-initialised counter for the last-CTA commit of pcg_update2_commit_kernel
   int ownLo = 0, ownHi = 0;                // blocks of A this rank owns (slab PCG); the whole matrix when not sharded
 };
 void launchBlockInverse(const PcgDev& p, cudaStream_t st, int64_t* launches);
 void launchPcgInit(const PcgDev& p, const double* b, double tolerance, double residual, int absoluteTolerance, cudaStream_t st, int64_t* launches);   // x=0, r=b, d=M^-1 r, dn=r.d, d0
 void launchPcgTail(const PcgDev& p, cudaStream_t st, int64_t* launches);   // after q = A d: dot, x/r/s update, d update, commit (no-ops once converged)
-void launchSpmv(const PcgDev& p, const double* src, double* dst, cudaStream_t st, int64_t* launches);   // dst = (A + lambda I) src, symmetric upper
+void launchSpmv(const PcgDev& p, const double* src, double* dst, cudaStream_t st, int64_t* launches, bool dstIsZero = false);   // dst = (A + lambda I) src, symmetric upper
+bool pcgSingleCtaTail(const PcgDev& p);   // launchPcgTail zeroes q itself (small systems): the next launchSpmv may skip its memset
 
 void launchExtractPoseDiag(const SystemDev& sys, double* out, cudaStream_t st, int64_t* launches);
 void launchMaxDiag(const SystemDev& sys, const double* poseDiag, int lmBegin, int lmEnd, double* out, cudaStream_t st, int64_t* launches);

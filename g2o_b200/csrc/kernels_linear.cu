@@ -539,23 +539,24 @@ template <int P> __global__ void __launch_bounds__(128) pcg_update1_kernel(PcgDe
   const double s = blockSumL<128>(acc, sm);
   if (threadIdx.x == 0) p.partial[blockIdx.x] = s;
 }
-// beta = dn_new / dn;  d = s + beta d;  commit scalars (block 0)
-__global__ void __launch_bounds__(256) pcg_update2_kernel(PcgDev p) {
+// beta = dn_new / dn;  d = s + beta d;  q = 0 for the next product;  the CTA that finishes last commits the scalars (dn <- dn_new, iteration
+// count, convergence flag): every CTA has read scal[0] / scal[6] before it takes its ticket, so the commit cannot race with them.
+__global__ void __launch_bounds__(256) pcg_update2_commit_kernel(PcgDev p, unsigned int* ticket) {
   __shared__ double sm[8];
   if (p.scal[6] != 0.0) return;
   const double dnNew = sumPartialsAll<256>(p.partial, p.nPartial, sm);
   const double beta = dnNew / p.scal[0];
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < p.n; i += gridDim.x * 256) p.d[i] = p.s[i] + beta * p.d[i];
-  if (blockIdx.x == 0 && threadIdx.x == 0) p.scal[2] = dnNew;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < p.n; i += gridDim.x * 256) { p.d[i] = p.s[i] + beta * p.d[i]; p.q[i] = 0.0; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      *ticket = 0u;
+      p.scal[2] = dnNew; p.scal[0] = dnNew; p.scal[7] += 1.0;
+      if (dnNew <= p.scal[5]) p.scal[6] = 1.0;
+    }
+  }
 }
-// single thread: dn <- dn_new, iteration count, convergence flag (runs between iterations so that no CTA races on scal[0])
-__global__ void pcg_commit_kernel(PcgDev p) {
-  if (p.scal[6] != 0.0) return;
-  const double dn = p.scal[2];
-  p.scal[0] = dn; p.scal[7] += 1.0;
-  if (dn <= p.scal[5]) p.scal[6] = 1.0;
-}
-
 // computeLambdaInit: max |H_vv(j,j)| over pose and landmark diagonal blocks (levenberg.cpp:152-175)
 // poseDiag (optional): the pose diagonals already summed over all ranks; landmarks: the owned range only
 __global__ void extract_pose_diag_kernel(SystemDev sys, double* out) {
@@ -657,8 +658,8 @@ void launchBlockInverse(const PcgDev& p, cudaStream_t st, int64_t* launches) {
   *launches += 1;
 }
 
-void launchSpmv(const PcgDev& p, const double* src, double* dst, cudaStream_t st, int64_t* launches) {
-  cudaMemsetAsync(dst, 0, sizeof(double) * (size_t)p.n, st);
+void launchSpmv(const PcgDev& p, const double* src, double* dst, cudaStream_t st, int64_t* launches, bool dstIsZero) {
+  if (!dstIsZero) cudaMemsetAsync(dst, 0, sizeof(double) * (size_t)p.n, st);
 #define CALL(PV) spmv_tma_kernel<PV><<<(p.nItems + 3) / 4, 128, 0, st>>>(p, p.itemRow, p.itemBegin, p.itemEnd, p.nItems, src, dst);
   FOR_P(p.P, CALL)
 #undef CALL
@@ -673,14 +674,14 @@ void launchPcgInit(const PcgDev& p, const double* b, double tolerance, double re
   *launches += 2;
 }
 
+bool pcgSingleCtaTail(const PcgDev&) { return true; }   // the tail leaves q zeroed for the next product
 void launchPcgTail(const PcgDev& p, cudaStream_t st, int64_t* launches) {
   dot_partial_kernel<<<p.nPartialDq, 256, 0, st>>>(p.scal, p.d, p.q, p.n, p.partialDq);
 #define CALL(PV) pcg_update1_kernel<PV><<<p.nPartial, 128, 0, st>>>(p, p.partialDq, p.nPartialDq);
   FOR_P(p.P, CALL)
 #undef CALL
-  pcg_update2_kernel<<<p.nPartialDq, 256, 0, st>>>(p);
-  pcg_commit_kernel<<<1, 1, 0, st>>>(p);
-  *launches += 4;
+  pcg_update2_commit_kernel<<<p.nPartialDq, 256, 0, st>>>(p, p.ticket);
+  *launches += 3;
 }
 
 void launchExtractPoseDiag(const SystemDev& sys, double* out, cudaStream_t st, int64_t* launches) {

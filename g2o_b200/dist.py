@@ -53,3 +53,32 @@ def install_torch_allreduce(solver, rank: int, world: int, group=None):
     import torch.distributed as dist
     cuda = dist.get_backend(group) == "nccl"
     solver.set_shard(rank, world, make_allreduce(cuda, group))
+
+
+def nccl_library_path() -> str:
+    """libnccl.so.2 of the running torch build (the nvidia-nccl wheel); falls back to the soname for a system NCCL."""
+    import glob
+    import os
+    import sys
+    for root in sys.path:
+        hits = glob.glob(os.path.join(root, "nvidia", "nccl", "lib", "libnccl.so.2"))
+        if hits:
+            return hits[0]
+    return "libnccl.so.2"
+
+
+def install_nccl(solver, rank: int, world: int, group=None):
+    """Direct NCCL: rank 0 creates an ncclUniqueId through the C ABI, torch.distributed only carries its 128 bytes to the other
+    ranks; afterwards no collective of the solve touches Python."""
+    import torch.distributed as dist
+    from . import _lib
+    path = nccl_library_path()
+    box = [None]
+    if rank == 0:
+        buf = ctypes.create_string_buffer(128)
+        rc = _lib.lib().g2ocu_nccl_unique_id(path.encode(), buf)
+        if rc != 0:
+            raise RuntimeError("g2ocu_nccl_unique_id failed: " + _lib.lib().g2ocu_last_error(None).decode())
+        box[0] = buf.raw
+    dist.broadcast_object_list(box, src=0, group=group)
+    solver.set_shard_nccl(rank, world, path, box[0])

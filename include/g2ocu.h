@@ -166,6 +166,12 @@ void g2ocu_destroy(g2ocu_solver* s);
 int g2ocu_set_graph(g2ocu_solver* s, const g2ocu_graph* g);
 int g2ocu_set_property(g2ocu_solver* s, const char* name, double value);  /* "initialLambda", "maxTrialsAfterFailure" (levenberg.cpp:48-49); "pcgTolerance", "pcgMaxIterations", "pcgAbsoluteTolerance" (linear_solver_pcg.h:53-57); "linearSolver" = G2OCU_LINEAR_* (which LinearSolver the BlockSolver owns, block_solver.h:124) */
 int g2ocu_set_shard(g2ocu_solver* s, int32_t rank, int32_t world, g2ocu_allreduce_fn fn, void* user);
+/* The same sharding with the collectives issued straight from the library through NCCL (no host callback per collective):
+ * `nccl_library` is the path of libnccl.so.2 (dlopen'ed; the build has no link-time NCCL dependency), `unique_id` the 128 bytes of an
+ * ncclUniqueId created by rank 0 with g2ocu_nccl_unique_id and distributed by the host (torch.distributed, MPI, a file ...).
+ * Collective: every rank of the job must call it; it creates one communicator on the solver's device. */
+int g2ocu_nccl_unique_id(const char* nccl_library, unsigned char unique_id[128]);
+int g2ocu_set_shard_nccl(g2ocu_solver* s, int32_t rank, int32_t world, const char* nccl_library, const unsigned char unique_id[128]);
 
 int g2ocu_initialize_optimization(g2ocu_solver* s, int32_t level);
 int g2ocu_init(g2ocu_solver* s, int32_t online);

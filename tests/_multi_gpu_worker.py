@@ -9,7 +9,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from g2o_b200 import workloads as W  # noqa: E402
 from g2o_b200.binding import CudaSolver  # noqa: E402
-from g2o_b200.dist import install_torch_allreduce  # noqa: E402
+from g2o_b200.dist import install_nccl, install_torch_allreduce  # noqa: E402
 
 
 def main():
@@ -19,9 +19,13 @@ def main():
     cases = [("bal", W.bal_synthetic(n_cameras=60, n_points=6000, n_obs=30000, seed=5, k_max=40, min_window=4), "lm_fix9_3_cuda"),
              ("slam2d", W.slam2d(n_poses=800, n_landmarks=200, world_size=30.0), "lm_fix3_2_cuda"),
              ("sphere", W.sphere(nodes_per_level=16, laps=8), "lm_var_cuda")]
-    for name, g, solver in cases:
+    for ci, (name, g, solver) in enumerate(cases):
         s = CudaSolver(g, solver, device=local)
-        install_torch_allreduce(s, rank, world)
+        # both transports of the collectives: the library's own NCCL communicator and the host callback over torch.distributed
+        if ci % 2 == 0:
+            install_nccl(s, rank, world)
+        else:
+            install_torch_allreduce(s, rank, world)
         s.initialize_optimization()
         n, st = s.optimize(6)
         est = s.get_estimates()
