@@ -155,14 +155,14 @@ def run_ours(args):
         pin_out = torch.empty_like(pin_in).pin_memory()
         s.set_estimates(est0)
         s.init()
-        host_in, host_out = pin_in.numpy(), pin_out.numpy()
+        host_in, host_out = pin_in.numpy(), pin_out.numpy()      # two pinned host buffers used in turn: a step's output is the next step's input
         stats = []
         for i in range(args.warmup):
             if e2e:
                 s.set_estimates(host_in)
             stats.append(s.solver_iteration(i))
             if e2e:
-                s.get_estimates(host_out); host_in[:] = host_out
+                s.get_estimates(host_out); host_in, host_out = host_out, host_in
         s.reset_counters()
         sampler = ClockSampler(local); sampler.start()
         barrier()
@@ -173,7 +173,7 @@ def run_ours(args):
                 s.set_estimates(host_in)                       # H2D of this step's inputs (pinned)
             stats.append(s.solver_iteration(i))
             if e2e:
-                s.get_estimates(host_out); host_in[:] = host_out   # D2H of the step's result
+                s.get_estimates(host_out); host_in, host_out = host_out, host_in   # D2H of the step's result (estimates + chi2); it feeds the next step
         barrier()
         dt = time.perf_counter() - t0
         clocks = sampler.stop()
