@@ -219,7 +219,7 @@ template <int P, int L> __global__ void __launch_bounds__(kMmaThreads, 1) schur_
   Cc[0] = Cc[1] = 0;
   uint32_t touched = 0;                               // bit 8 i + j: block (row 2 i + rh, column 4 j + cg) received a product
 
-  long long tWait = 0, tProd = 0, tSlots = 0, tSlotsB = 0, tVisits = 0; const long long tStart = clock64();
+  long long tWait = 0, tProd = 0, tSlots = 0; const long long tStart = clock64();
   auto consume = [&](auto rhc) {
     constexpr int RH = decltype(rhc)::value;
     int e = eBegin, stage = 0; uint32_t phase = 0;
@@ -298,10 +298,6 @@ template <int P, int L> __global__ void __launch_bounds__(kMmaThreads, 1) schur_
           if (RH == 0) dmma(Cc, FA, FB);
           if (prof) tSlots += RH == 0 ? 5 : 4;
         }
-        if (prof) {   // what a half-group / fringe guard would issue
-          const int halves = ((cJ & 0x0fu) ? 4 : 0) + ((cJ & 0xf0u) ? 4 : 0);
-          tSlotsB += (long long)__popc(tI) * (halves + 1) + (((cJ >> (4 * RH)) & 0xfu) ? 4 : 0) + (RH == 0 ? 1 : 0); tVisits += 1;
-        }
       }
       __syncwarp();
       if (lane == 0) mbarArrive(sEmpty + stage);
@@ -356,7 +352,7 @@ template <int P, int L> __global__ void __launch_bounds__(kMmaThreads, 1) schur_
   if (prof && lane == 0) {
     long long* o = prof + ((size_t)blockIdx.x * kMmaConsumers + warpU) * 8;
     unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    o[0] = tLoopEnd - tStart; o[1] = tWait; o[2] = tProd; o[3] = tSlots; o[4] = clock64() - tLoopEnd; o[5] = eEnd - eBegin; o[6] = tSlotsB; o[7] = tVisits;
+    o[0] = tLoopEnd - tStart; o[1] = tWait; o[2] = tProd; o[3] = tSlots; o[4] = clock64() - tLoopEnd; o[5] = eEnd - eBegin; o[6] = smid; o[7] = tStart;
   }
 }
 
