@@ -209,6 +209,12 @@ def run_ours(args):
         if calls:
             per[name] = {"seconds_total": sec, "calls": calls, "avg_ms": 1e3 * sec / calls, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (sec / calls) / 1e9,
                          "frac_of_hbm_peak": nbytes / (sec / calls) / 1e9 / peak}
+    if "pcg_spmv" in per:   # launches issued after convergence return at once: rate per ACTIVE product = per PCG iteration
+        its = sum(st["iterations_linear_solver"] for st in stats[args.warmup:])
+        if its:
+            per["pcg_spmv"].update({"active_products": its, "avg_ms_active": 1e3 * per["pcg_spmv"]["seconds_total"] / its,
+                                    "achieved_gbs": bytes_spmv / (per["pcg_spmv"]["seconds_total"] / its) / 1e9,
+                                    "frac_of_hbm_peak": bytes_spmv / (per["pcg_spmv"]["seconds_total"] / its) / 1e9 / peak})
     tpeak, tpeak_src = fp64_tensor_peak()
     for name, fl in [("schur_tiles", flops_tiles), ("schur_pairs", 2.0 * 81 * 3 * (pairs_all - pairs_tiles))]:
         sec, _, calls = phases[name]
@@ -217,17 +223,22 @@ def run_ours(args):
                          "frac_of_fp64_peak": fl / (sec / calls) / 1e12 / tpeak}
     kernels = {"pcg_spmv": "spmv_sym_kernel<9>", "build": "build_pl_kernel<BAL> + pose_accum_kernel<BAL>", "schur_coeff": "coeff_w_kernel<9,3>",
                "schur_tiles": "schur_mma_kernel<9,3>", "schur_pairs": "schur_pairs_kernel<9,3>"}
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as fh:
+            traffic = json.load(fh)
     cand = [k2 for k2 in per if k2 in kernels]
     dominant = max(cand, key=lambda k2: per[k2]["seconds_total"]) if cand else None
     roof = None
     if dominant and "algorithmic_flops" in per[dominant]:
         a = per[dominant]["achieved_tflops"]
-        roof = {"kernel": kernels[dominant], "bound": "tensor", "achieved": a, "peak": tpeak, "unit": "TFLOP/s", "frac": a / tpeak, "traffic": None, "peak_source": tpeak_src,
+        roof = {"kernel": kernels[dominant], "bound": "tensor", "achieved": a, "peak": tpeak, "unit": "TFLOP/s", "frac": a / tpeak, "traffic": traffic.get(kernels[dominant]), "peak_source": tpeak_src,
                 "note": "FP64 tensor pipe (DMMA m8n8k4); FP64 FMA shares the same pipe on B200 (tools/dmma_dfma_mix.cu), so this is the only FP64 roof",
                 "avg_launch_ms": per[dominant]["avg_ms"], "phases": per}
     elif dominant:
         a = per[dominant]["achieved_gbs"]
-        roof = {"kernel": kernels[dominant], "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": None, "peak_source": peak_src,
+        roof = {"kernel": kernels[dominant], "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": traffic.get(kernels[dominant]), "peak_source": peak_src,
                 "avg_launch_ms": per[dominant]["avg_ms"], "phases": per}
     timed_stats = stats[args.warmup:]
     value = args.steps / dt

@@ -582,7 +582,7 @@ int lambdaInit(g2ocu_solver* s, double* out) {
     int rc = allreduceDev(s, s->vq.p, s->st.sizePoses, 0); if (rc) return rc;
     poseDiag = s->vq.p;
   }
-  launchMaxDiag(s->sys, poseDiag, s->st.lmBegin, s->st.lmEnd, s->out2.p + 4, s->stream, &s->launches);
+  launchMaxDiag(s->sys, poseDiag, s->st.lmBegin, s->st.lmEnd, s->scratch.p, s->out2.p + 4, s->stream, &s->launches);
   { int rc = allreduceDev(s, s->out2.p + 4, 1, 1); if (rc) return rc; }
   CU(cudaMemcpyAsync(s->hostScal + 4, s->out2.p + 4, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   int rc = syncStream(s); if (rc) return rc;

@@ -99,7 +99,7 @@ void launchSpmv(const PcgDev& p, const double* src, double* dst, cudaStream_t st
 bool pcgSingleCtaTail(const PcgDev& p);   // launchPcgTail zeroes q itself (small systems): the next launchSpmv may skip its memset
 
 void launchExtractPoseDiag(const SystemDev& sys, double* out, cudaStream_t st, int64_t* launches);
-void launchMaxDiag(const SystemDev& sys, const double* poseDiag, int lmBegin, int lmEnd, double* out, cudaStream_t st, int64_t* launches);
+void launchMaxDiag(const SystemDev& sys, const double* poseDiag, int lmBegin, int lmEnd, double* scratch /* >= 148 doubles */, double* out, cudaStream_t st, int64_t* launches);
 void launchScale(const double* x, const double* b, int64_t n, double lambda, double* scratch, double* out, cudaStream_t st, int64_t* launches);
 
 // dense FP64 Cholesky path (kernels_dense.cu)

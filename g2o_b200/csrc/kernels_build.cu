@@ -91,14 +91,15 @@ template <int NT> G2D double blockSum(double v, double* sm /* NT/32 doubles */) 
 template <int ET> __global__ void __launch_bounds__(kThreads) errors_kernel(EdgeSetDev s, SystemDev sys, double* partial, double* errOut, const int64_t* errOff) {
   using T = EdgeT<ET>;
   __shared__ double sm[kThreads / 32];
-  const int i = blockIdx.x * kThreads + threadIdx.x;
   double rho0 = 0, chi2 = 0;
-  if (i < s.n) {
-    double x0[T::S0], x1[T::S1], z[T::M], prm[T::NP > 0 ? T::NP : 1], e[T::E], Om[T::E * T::E], w;
+  // grid-stride over the edges: a fixed edge -> thread assignment and fixed reduction trees keep chi2 bit-reproducible from run to run
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < s.n; i += gridDim.x * kThreads) {
+    double x0[T::S0], x1[T::S1], z[T::M], prm[T::NP > 0 ? T::NP : 1], e[T::E], Om[T::E * T::E], w, c2;
     loadEdge<ET>(s, sys, i, s.slot0[i], s.slot1[i], x0, x1, z, prm);
     T::template eval<false>(x0, x1, z, prm, e, nullptr, nullptr);
     loadInfo<T::E>(s, i, Om);
-    rho0 = robustWeight<T::E>(s, i, e, Om, chi2, w);
+    rho0 += robustWeight<T::E>(s, i, e, Om, c2, w);
+    chi2 += c2;
     if (errOut) { double* o = errOut + errOff[s.pos[i]];
 #pragma unroll
       for (int k = 0; k < T::E; ++k) o[k] = e[k]; }
@@ -427,11 +428,12 @@ template <int VT> __global__ void update_kernel(double* est, int* counters, cons
     default: break;                                                                  \
   }
 
-int errorScratchDoubles(int n) { return 2 * ((n + kThreads - 1) / kThreads) + 2; }
+static int errorGrid(int n) { const int nb = (n + kThreads - 1) / kThreads; return nb < 148 * 16 ? nb : 148 * 16; }   // at most 16 CTAs per SM, grid-stride beyond
+int errorScratchDoubles(int n) { return 2 * errorGrid(n) + 2; }
 
 void launchErrors(const EdgeSetDev& s, const SystemDev& sys, double* scratch, double* out2, double* errOut, const int64_t* errOff, cudaStream_t st, int64_t* launches) {
   if (s.n == 0) return;
-  const int nb = (s.n + kThreads - 1) / kThreads;
+  const int nb = errorGrid(s.n);
 #define CALL(ETV) errors_kernel<ETV><<<nb, kThreads, 0, st>>>(s, sys, scratch, errOut, errOff);
   FOR_EDGE_TYPE(s.etype, CALL)
 #undef CALL

@@ -565,17 +565,25 @@ __global__ void extract_pose_diag_kernel(SystemDev sys, double* out) {
   const int i = t / P, k = t - i * P;
   out[t] = sys.Hpp[(size_t)sys.hppDiag[i] * P * P + k * (P + 1)];
 }
-__global__ void __launch_bounds__(1024) maxdiag_kernel(SystemDev sys, const double* poseDiag, int lmBegin, int lmEnd, double* out) {
+__global__ void __launch_bounds__(1024) maxdiag_kernel(SystemDev sys, const double* poseDiag, int lmBegin, int lmEnd, double* partial) {
   __shared__ double sm[32];
   double m = 0;
   const int P = sys.P, L = sys.L;
-  for (int t = threadIdx.x; t < sys.numPoses * P; t += 1024) { const int i = t / P, k = t - i * P; m = fmax(m, fabs(poseDiag ? poseDiag[t] : sys.Hpp[(size_t)sys.hppDiag[i] * P * P + k * (P + 1)])); }
-  for (int64_t t = (int64_t)lmBegin * L + threadIdx.x; t < (int64_t)lmEnd * L; t += 1024) { const int64_t i = t / L; const int k = (int)(t - i * L); m = fmax(m, fabs(sys.Hll[(size_t)i * L * L + k * (L + 1)])); }
+  const int64_t tid = (int64_t)blockIdx.x * 1024 + threadIdx.x, nth = (int64_t)gridDim.x * 1024;
+  for (int64_t t = tid; t < (int64_t)sys.numPoses * P; t += nth) { const int i = (int)(t / P), k = (int)(t - (int64_t)i * P); m = fmax(m, fabs(poseDiag ? poseDiag[t] : sys.Hpp[(size_t)sys.hppDiag[i] * P * P + k * (P + 1)])); }
+  for (int64_t t = (int64_t)lmBegin * L + tid; t < (int64_t)lmEnd * L; t += nth) { const int64_t i = t / L; const int k = (int)(t - i * L); m = fmax(m, fabs(sys.Hll[(size_t)i * L * L + k * (L + 1)])); }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
   __syncthreads();
-  if (threadIdx.x == 0) { double r = 0; for (int k = 0; k < 32; ++k) r = fmax(r, sm[k]); out[0] = r; }
+  if (threadIdx.x == 0) { double r = 0; for (int k = 0; k < 32; ++k) r = fmax(r, sm[k]); partial[blockIdx.x] = r; }
+}
+__global__ void maxdiag_final_kernel(const double* partial, int n, double* out) {   // max is exact: any order gives the same value
+  double m = 0;
+  for (int k = threadIdx.x; k < n; k += 32) m = fmax(m, partial[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+  if (threadIdx.x == 0) out[0] = m;
 }
 // computeScale: sum_j x_j (lambda x_j + b_j) (levenberg.cpp:177-184)
 __global__ void __launch_bounds__(256) scale_partial_kernel(const double* x, const double* b, int64_t n, double lambda, double* partial) {
@@ -688,9 +696,11 @@ void launchExtractPoseDiag(const SystemDev& sys, double* out, cudaStream_t st, i
   extract_pose_diag_kernel<<<(sys.numPoses * sys.P + 255) / 256, 256, 0, st>>>(sys, out);
   *launches += 1;
 }
-void launchMaxDiag(const SystemDev& sys, const double* poseDiag, int lmBegin, int lmEnd, double* out, cudaStream_t st, int64_t* launches) {
-  maxdiag_kernel<<<1, 1024, 0, st>>>(sys, poseDiag, lmBegin, lmEnd, out);
-  *launches += 1;
+void launchMaxDiag(const SystemDev& sys, const double* poseDiag, int lmBegin, int lmEnd, double* scratch, double* out, cudaStream_t st, int64_t* launches) {
+  const int nb = 148;   // partial maxima land in scratch, one per CTA
+  maxdiag_kernel<<<nb, 1024, 0, st>>>(sys, poseDiag, lmBegin, lmEnd, scratch);
+  maxdiag_final_kernel<<<1, 32, 0, st>>>(scratch, nb, out);
+  *launches += 2;
 }
 void launchScale(const double* x, const double* b, int64_t n, double lambda, double* scratch, double* out, cudaStream_t st, int64_t* launches) {
   int64_t nb64 = (n + 255) / 256; const int nb = (int)(nb64 < 1184 ? nb64 : 1184);
