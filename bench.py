@@ -142,6 +142,10 @@ def run_ours(args):
             install_nccl(s, rank, world)                 # collectives issued by libg2ocu.so itself
     s.initialize_optimization()
     s.init()
+    if world > 1 and os.environ.get("G2O_BENCH_P2P", "1") != "0":
+        from g2o_b200.dist import install_p2p
+        s.build_structure()
+        install_p2p(s, rank, world)                      # q = A d of the slab PCG is exchanged through NVLink peer memory
 
     def barrier():
         torch.cuda.synchronize()
@@ -177,8 +181,8 @@ def run_ours(args):
         barrier()
         dt = time.perf_counter() - t0
         clocks = sampler.stop()
-        phases = {ph: s.phase_time(ph) for ph in ["errors", "build", "schur", "schur_coeff", "schur_pairs", "schur_tiles", "pcg_setup", "pcg_spmv", "pcg_vec",
-                                                  "linear_solver", "backsub", "update"]}
+        phases = {ph: s.phase_time(ph) for ph in ["errors", "build", "schur", "schur_coeff", "schur_pairs", "schur_tiles", "schur_exchange", "pcg_setup", "pcg_spmv",
+                                                  "pcg_exchange", "pcg_vec", "linear_solver", "backsub", "update"]}
         return dt, stats, s.launch_count() - l0, phases, clocks
 
     dt, stats, launches, phases, clocks = timed_run(False)

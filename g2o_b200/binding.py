@@ -103,6 +103,14 @@ class CudaSolver:
             self._hook = _lib.ALLREDUCE_FN(0)
         self._ck(self._L.g2ocu_set_shard(self._h, rank, world, self._hook, None))
 
+    def p2p_export(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        self._ck(self._L.g2ocu_p2p_export(self._h, buf))
+        return buf.raw
+
+    def p2p_import(self, handles: bytes):
+        self._ck(self._L.g2ocu_p2p_import(self._h, handles))
+
     def set_shard_nccl(self, rank: int, world: int, nccl_library: str, unique_id: bytes):
         """Collectives issued by the library itself through NCCL (g2ocu_set_shard_nccl); every rank must call it."""
         assert len(unique_id) == 128

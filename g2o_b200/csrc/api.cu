@@ -111,6 +111,7 @@ struct g2ocu_solver {
   int rank = 0, world = 1; g2ocu_allreduce_fn allreduce = nullptr; void* allreduceUser = nullptr;
   int64_t slabBlocks = 0;         // blocks of the reduced system per rank (slab PCG), 0 when not sharded
   void* ncclComm = nullptr;       // set by g2ocu_set_shard_nccl: collectives go straight to NCCL on the solver's stream
+  P2pDev p2p; bool p2pReady = false; double* p2pLocal = nullptr; void* p2pOpened[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // CUDA-IPC peer buffers for the slab-PCG exchange
   // device state
   DVec<double> poseEst, lmEst; std::vector<DVec<double>*> poseBackup, lmBackup; int stackDepth = 0;
   DVec<int> poseCounters, lmCounters;
@@ -133,6 +134,8 @@ struct g2ocu_solver {
     for (auto* b2 : lmBackup) delete b2;
     for (auto& pe : pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto e : eventPool) cudaEventDestroy(e);
+    for (void* o : p2pOpened) if (o) cudaIpcCloseMemHandle(o);
+    if (p2pLocal) cudaFree(p2pLocal);
     if (ncclComm && g_nccl.CommDestroy) g_nccl.CommDestroy(ncclComm);
     if (hostScal) cudaFreeHost(hostScal);
     if (hostInfo) cudaFreeHost(hostInfo);
@@ -476,11 +479,16 @@ int solvePcg(g2ocu_solver* s, const double* rhs) {
   int issued = 0; bool done = false;
   const int kCheckEvery = 4;
   while (!done) {
-    const int batch = std::min(kCheckEvery, maxIter - issued);
+    // the first poll comes where the previous solve converged (the counts grow slowly from one LM iteration to the next); launches past
+    // convergence are no-ops on the device, so overshooting costs microseconds while every poll drains the stream
+    const int want = issued == 0 ? std::min(std::max(kCheckEvery, s->lastPcgIterations - 1), 256) : kCheckEvery;
+    const int batch = std::min(want, maxIter - issued);
     for (int k = 0; k < batch; ++k) {
       { PhaseTimer pt(s, "pcg_spmv"); launchSpmv(pc, pc.d, pc.q, s->stream, &s->launches, issued + k > 0 && pcgSingleCtaTail(pc)); }
-      if (slab) { PhaseTimer pt(s, "pcg_exchange"); int rc = allreduceDev(s, pc.q, pc.n, 0); if (rc) return rc; }
-      { PhaseTimer pt(s, "pcg_vec"); launchPcgTail(pc, s->stream, &s->launches); }
+      const bool p2p = slab && s->p2pReady;
+      if (p2p) { PhaseTimer pt(s, "pcg_exchange"); launchP2pExchangeDot(pc, s->p2p, s->stream, &s->launches); }   // peer-memory all-reduce of q fused with d.q
+      else if (slab) { PhaseTimer pt(s, "pcg_exchange"); int rc = allreduceDev(s, pc.q, pc.n, 0); if (rc) return rc; }
+      { PhaseTimer pt(s, "pcg_vec"); launchPcgTail(pc, s->stream, &s->launches, p2p); }
     }
     issued += batch;
     CU(cudaMemcpyAsync(s->hostScal + 8, pc.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -743,6 +751,38 @@ int g2ocu_set_shard_nccl(g2ocu_solver* s, int32_t rank, int32_t world, const cha
   if (nrc != 0) { s->ncclComm = nullptr; return fail(s, G2OCU_E_COMM, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(nrc)); }
   s->rank = rank; s->world = world; s->allreduce = nullptr; s->allreduceUser = nullptr;
   s->structureBuilt = false;
+  return G2OCU_OK;
+}
+
+int g2ocu_p2p_export(g2ocu_solver* s, unsigned char handle[64]) {
+  if (!s || !handle) return G2OCU_E_INVALID;
+  if (!s->structureBuilt) return fail(s, G2OCU_E_INVALID, "g2ocu_p2p_export needs the structure (call g2ocu_build_structure first)");
+  if (s->world < 2 || s->world > 8) return fail(s, G2OCU_E_INVALID, "the peer-memory exchange supports 2..8 ranks");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  if (s->p2pLocal) { cudaFree(s->p2pLocal); s->p2pLocal = nullptr; }
+  s->p2pReady = false;
+  const int64_t cap = (s->st.sizePoses + 1) & ~(int64_t)1;
+  const size_t bytes = p2pBytes(s->world, cap);
+  CU(cudaMalloc((void**)&s->p2pLocal, bytes));
+  CU(cudaMemsetAsync(s->p2pLocal, 0, bytes, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, s->p2pLocal));
+  std::memcpy(handle, &h, 64);
+  s->p2p = P2pDev(); s->p2p.rank = s->rank; s->p2p.world = s->world; s->p2p.cap = cap;
+  return G2OCU_OK;
+}
+int g2ocu_p2p_import(g2ocu_solver* s, const unsigned char* handles) {
+  if (!s || !handles) return G2OCU_E_INVALID;
+  if (!s->p2pLocal) return fail(s, G2OCU_E_INVALID, "g2ocu_p2p_export has not been called");
+  for (int r = 0; r < s->world; ++r) {
+    if (r == s->rank) { s->p2p.peer[r] = s->p2pLocal; continue; }
+    cudaIpcMemHandle_t h; std::memcpy(&h, handles + 64 * (size_t)r, 64);
+    void* ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    s->p2pOpened[r] = ptr; s->p2p.peer[r] = (double*)ptr;
+  }
+  s->p2pReady = true;
   return G2OCU_OK;
 }
 

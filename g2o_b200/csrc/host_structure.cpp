@@ -245,15 +245,22 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int ran
     st.sRowPtr.clear(); st.sColIdx.clear(); st.sColPtr.clear(); st.sRowIdx.clear(); st.sCcsToCsr.clear(); st.sDiag.clear(); st.hppToS.clear();
   }
 
-  // ---- landmark ownership for sharded runs: contiguous slot ranges balanced by the number of Hpl blocks ----
+  // ---- landmark ownership for sharded runs: contiguous slot ranges balanced by a cost model of the per-landmark work ----
+  // k observations cost ~k in the build / coefficient / back-substitution passes and k (k + 1) / 2 block products in the Schur complement;
+  // the weights are the measured single-GPU times per unit on C3 (0.40 ns per observation, 0.085 ns per block product).
   st.lmBegin = 0; st.lmEnd = st.numLandmarks;
   if (world > 1 && st.doSchur) {
-    const int64_t total = st.hplColPtr.empty() ? 0 : st.hplColPtr[st.numLandmarks];
+    std::vector<int64_t> cum((size_t)st.numLandmarks + 1, 0);
+    for (int l = 0; l < st.numLandmarks; ++l) {
+      const int64_t k = st.hplColPtr[l + 1] - st.hplColPtr[l];
+      cum[l + 1] = cum[l] + 400 * k + 85 * (k * (k + 1) / 2);
+    }
+    const int64_t total = cum[st.numLandmarks];
     auto splitAt = [&](int r) -> int {
       if (r <= 0) return 0;
       if (r >= world) return st.numLandmarks;
-      const int64_t target = total * r / world;
-      return (int)(std::lower_bound(st.hplColPtr.begin(), st.hplColPtr.end(), (int32_t)target) - st.hplColPtr.begin());
+      const int64_t target = total / world * r;
+      return (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
     };
     st.lmBegin = std::min(splitAt(rank), st.numLandmarks); st.lmEnd = std::min(splitAt(rank + 1), st.numLandmarks);
     if (rank == world - 1) st.lmEnd = st.numLandmarks;

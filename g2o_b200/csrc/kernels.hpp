@@ -92,9 +92,20 @@ struct PcgDev {
   unsigned int* ticket = nullptr;          // zero-initialised counter for the last-CTA commit of pcg_update2_commit_kernel
   int ownLo = 0, ownHi = 0;                // blocks of A this rank owns (slab PCG); the whole matrix when not sharded
 };
+// Peer-memory exchange of the slab-PCG product (one process per GPU, buffers opened through CUDA IPC): every rank owns
+//   data[2][world][cap] doubles | flags[world] uint64 | seq uint64 | ticket[2] uint32
+// `peer[r]` is that block on rank r as mapped into this process (peer[rank] is the local one).
+struct P2pDev {
+  double* peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int rank = 0, world = 1; int64_t cap = 0;
+};
+static inline size_t p2pBytes(int world, int64_t cap) { return sizeof(double) * 2 * (size_t)world * (size_t)cap + 8 * (size_t)world + 8 + 8 + 48; }
+// q <- sum over ranks of the per-rank partial products (fixed rank order: bit-identical on every rank), partialDq <- partial sums of d.q;
+// replaces an NCCL all-reduce + dot_partial_kernel in the PCG iteration
+void launchP2pExchangeDot(const PcgDev& p, const P2pDev& x, cudaStream_t st, int64_t* launches);
 void launchBlockInverse(const PcgDev& p, cudaStream_t st, int64_t* launches);
 void launchPcgInit(const PcgDev& p, const double* b, double tolerance, double residual, int absoluteTolerance, cudaStream_t st, int64_t* launches);   // x=0, r=b, d=M^-1 r, dn=r.d, d0
-void launchPcgTail(const PcgDev& p, cudaStream_t st, int64_t* launches);   // after q = A d: dot, x/r/s update, d update, commit (no-ops once converged)
+void launchPcgTail(const PcgDev& p, cudaStream_t st, int64_t* launches, bool dotDone = false);   // after q = A d: dot, x/r/s update, d update, commit (no-ops once converged)
 void launchSpmv(const PcgDev& p, const double* src, double* dst, cudaStream_t st, int64_t* launches, bool dstIsZero = false);   // dst = (A + lambda I) src, symmetric upper
 bool pcgSingleCtaTail(const PcgDev& p);   // launchPcgTail zeroes q itself (small systems): the next launchSpmv may skip its memset
 

@@ -482,6 +482,69 @@ __global__ void __launch_bounds__(256) dot_partial_kernel(const double* scal, co
   if (threadIdx.x == 0) partial[blockIdx.x] = r;
 }
 
+// ---- slab PCG over NVLink peer memory ----------------------------------------------------------------------------------------
+// Exchange k (a device-side sequence number, so that launches skipped after convergence do not count): every rank stores its partial
+// product into slot [k & 1][rank] of EVERY rank's buffer (plain stores through the peer mappings), fences at system scope, and the last
+// CTA publishes k in flags[rank] of every rank.  The second kernel waits until all flags have reached k, sums the slots in rank order
+// and forms the d.q partial sums in the same pass.  Two buffers suffice: a rank can only start exchange k + 2 after it has received the
+// flags of k + 1, which its peers set after they finished reading exchange k.
+namespace {
+__device__ __forceinline__ uint64_t* p2pFlags(double* base, int world, int64_t cap) { return reinterpret_cast<uint64_t*>(base + 2 * (size_t)world * cap); }
+__device__ __forceinline__ uint64_t ldAcquireSys(const uint64_t* p) { uint64_t v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void stReleaseSys(uint64_t* p, uint64_t v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+}  // namespace
+__global__ void __launch_bounds__(256) p2p_push_kernel(PcgDev p, P2pDev x) {
+  if (p.scal[6] != 0.0) return;
+  double* mine = x.peer[x.rank];
+  uint64_t* fl = p2pFlags(mine, x.world, x.cap);
+  const uint64_t k = fl[x.world] + 1;                 // seq lives right after the flags
+  const size_t slot = ((size_t)(k & 1) * x.world + x.rank) * x.cap;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < p.n; i += gridDim.x * 256) {
+    const double v = p.q[i];
+    for (int r = 0; r < x.world; ++r) x.peer[r][slot + i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(fl + x.world + 1);
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    if (threadIdx.x == 0) *ticket = 0u;
+    if (threadIdx.x < x.world) stReleaseSys(p2pFlags(x.peer[threadIdx.x], x.world, x.cap) + x.rank, k);
+  }
+}
+__global__ void __launch_bounds__(256) p2p_sum_dot_kernel(PcgDev p, P2pDev x) {
+  __shared__ double sm[8];
+  if (p.scal[6] != 0.0) return;
+  double* mine = x.peer[x.rank];
+  uint64_t* fl = p2pFlags(mine, x.world, x.cap);
+  const uint64_t k = fl[x.world] + 1;
+  if (threadIdx.x < x.world) { while (ldAcquireSys(fl + threadIdx.x) < k) { } }
+  __syncthreads();
+  const double* slots = mine + (size_t)(k & 1) * x.world * x.cap;
+  double v = 0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < p.n; i += gridDim.x * 256) {
+    double s = 0;
+    for (int r = 0; r < x.world; ++r) s += __ldcv(slots + (size_t)r * x.cap + i);
+    p.q[i] = s;
+    v += p.d[i] * s;
+  }
+  const double r = blockSumL<256>(v, sm);
+  if (threadIdx.x == 0) {
+    p.partialDq[blockIdx.x] = r;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(fl + x.world + 1) + 1;
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *ticket = 0u; fl[x.world] = k; }   // every CTA has read seq: advance it
+  }
+}
+void launchP2pExchangeDot(const PcgDev& p, const P2pDev& x, cudaStream_t st, int64_t* launches) {
+  p2p_push_kernel<<<p.nPartialDq, 256, 0, st>>>(p, x);
+  p2p_sum_dot_kernel<<<p.nPartialDq, 256, 0, st>>>(p, x);
+  *launches += 2;
+}
+
 // x = 0, r = b, d = M^-1 r, partial r.d   (thread per block row)
 template <int P> __global__ void __launch_bounds__(128) pcg_init_kernel(PcgDev p, const double* __restrict__ b) {
   constexpr int PP = P * P;
@@ -683,8 +746,8 @@ void launchPcgInit(const PcgDev& p, const double* b, double tolerance, double re
 }
 
 bool pcgSingleCtaTail(const PcgDev&) { return true; }   // the tail leaves q zeroed for the next product
-void launchPcgTail(const PcgDev& p, cudaStream_t st, int64_t* launches) {
-  dot_partial_kernel<<<p.nPartialDq, 256, 0, st>>>(p.scal, p.d, p.q, p.n, p.partialDq);
+void launchPcgTail(const PcgDev& p, cudaStream_t st, int64_t* launches, bool dotDone) {
+  if (!dotDone) dot_partial_kernel<<<p.nPartialDq, 256, 0, st>>>(p.scal, p.d, p.q, p.n, p.partialDq);
 #define CALL(PV) pcg_update1_kernel<PV><<<p.nPartial, 128, 0, st>>>(p, p.partialDq, p.nPartialDq);
   FOR_P(p.P, CALL)
 #undef CALL

@@ -82,3 +82,13 @@ def install_nccl(solver, rank: int, world: int, group=None):
         box[0] = buf.raw
     dist.broadcast_object_list(box, src=0, group=group)
     solver.set_shard_nccl(rank, world, path, box[0])
+
+
+def install_p2p(solver, rank: int, world: int, group=None):
+    """NVLink peer-memory exchange for the slab PCG (after ``build_structure``): CUDA-IPC handles travel over torch.distributed once."""
+    import torch.distributed as dist
+    mine = solver.p2p_export()
+    handles = [None] * world
+    dist.all_gather_object(handles, mine, group=group)
+    solver.p2p_import(b"".join(handles))
+    dist.barrier(group=group)

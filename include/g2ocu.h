@@ -172,6 +172,12 @@ int g2ocu_set_shard(g2ocu_solver* s, int32_t rank, int32_t world, g2ocu_allreduc
  * Collective: every rank of the job must call it; it creates one communicator on the solver's device. */
 int g2ocu_nccl_unique_id(const char* nccl_library, unsigned char unique_id[128]);
 int g2ocu_set_shard_nccl(g2ocu_solver* s, int32_t rank, int32_t world, const char* nccl_library, const unsigned char unique_id[128]);
+/* Optional, single node, 2..8 ranks, after g2ocu_build_structure: the per-iteration exchange of the slab PCG (the 8 Nc P bytes of
+ * q = A d) goes through NVLink peer memory instead of an NCCL all-reduce.  export: allocates this rank's exchange buffer and returns
+ * its 64-byte cudaIpcMemHandle; the host gathers the handles of all ranks (rank order) and passes them to import, which maps the peers'
+ * buffers.  Both are collective in the sense that every rank must do both before the next solve. */
+int g2ocu_p2p_export(g2ocu_solver* s, unsigned char handle[64]);
+int g2ocu_p2p_import(g2ocu_solver* s, const unsigned char* handles /* world x 64 bytes */);
 
 int g2ocu_initialize_optimization(g2ocu_solver* s, int32_t level);
 int g2ocu_init(g2ocu_solver* s, int32_t online);

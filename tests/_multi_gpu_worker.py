@@ -9,7 +9,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from g2o_b200 import workloads as W  # noqa: E402
 from g2o_b200.binding import CudaSolver  # noqa: E402
-from g2o_b200.dist import install_nccl, install_torch_allreduce  # noqa: E402
+from g2o_b200.dist import install_nccl, install_p2p, install_torch_allreduce  # noqa: E402
 
 
 def main():
@@ -27,6 +27,9 @@ def main():
         else:
             install_torch_allreduce(s, rank, world)
         s.initialize_optimization()
+        if name == "bal":                      # slab PCG with the peer-memory exchange of q (CUDA IPC over NVLink)
+            s.init(); s.build_structure()
+            install_p2p(s, rank, world)
         n, st = s.optimize(6)
         est = s.get_estimates()
         if rank == 0:

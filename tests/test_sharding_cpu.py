@@ -51,10 +51,12 @@ def test_partition_covers_every_edge_once():
             if dims[1]:
                 assert ranges[0][0] == 0 and ranges[-1][1] == dims[1]
                 assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
-                # balanced by observations (Hpl blocks), not by landmark count
+                # balanced by the cost model (0.40 ns per observation + 0.085 ns per Schur block product), not by landmark count
                 cp = ref.get_i32("hpl_colptr").astype(np.int64)
-                loads = [cp[b] - cp[a] for a, b in ranges]
-                assert max(loads) - min(loads) <= max(64, 0.2 * cp[-1] / world)
+                k = np.diff(cp)
+                cost = np.concatenate([[0], np.cumsum(400 * k + 85 * (k * (k + 1) // 2))])
+                loads = [cost[b] - cost[a] for a, b in ranges]
+                assert max(loads) - min(loads) <= max(2 * int((400 * k + 85 * (k * (k + 1) // 2)).max()), 0.2 * cost[-1] / world)
 
 
 def _gloo_worker(rank, world, port, q):
