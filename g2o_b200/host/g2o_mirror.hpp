@@ -109,6 +109,7 @@ class OptimizableGraph {
     number_t* informationData() { return _information.data(); }                   // column-major E x E
     void setInformationDiagonal(const number_t* d) { for (int i = 0; i < _dimension; ++i) _information[(size_t)i * _dimension + i] = d[i]; }
     void setParameterData(const number_t* p) { for (size_t i = 0; i < _param.size(); ++i) _param[i] = p[i]; }
+    const number_t* parameterData() const { return _param.data(); }
     int typeCode() const { return _type; }
    protected:
     friend class SparseOptimizer;

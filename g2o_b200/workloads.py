@@ -390,9 +390,9 @@ def write_bal(g: Graph, path: str) -> None:
         fh.write(f"{nc} {npnt} {g.n_edges}\n")
         m = g.e_measurement.reshape(-1, 2)
         for i in range(g.n_edges):
-            fh.write(f"{g.e_v0[i]} {g.e_v1[i] - nc} {m[i, 0]!r} {m[i, 1]!r}\n")
+            fh.write(f"{int(g.e_v0[i])} {int(g.e_v1[i]) - nc} {float(m[i, 0])!r} {float(m[i, 1])!r}\n")
         for v in g.v_estimate:
-            fh.write(f"{v!r}\n")
+            fh.write(f"{float(v)!r}\n")
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -505,3 +505,62 @@ def slam2d(n_poses: int = 100_000, n_landmarks: int = 20_000, world_size: float 
                  e_kernel=np.full(ne, KERNEL_HUBER if huber_delta is not None else 0),
                  e_kernel_delta=np.full(ne, huber_delta if huber_delta is not None else 1.0), name="slam2d",
                  meta={"n_poses": n_poses, "n_landmarks": n_landmarks, "n_observations": int(n_obs)})
+
+
+# ----------------------------------------------------------------------------------------------------
+# .g2o text files (optimizable_graph.cpp:397-640 and the per-type read/write of the reference)
+# ----------------------------------------------------------------------------------------------------
+def _r_to_quat(R: np.ndarray) -> np.ndarray:
+    """Column-major 3x3 (9 values) -> unit quaternion (x, y, z, w) with Eigen's branch structure."""
+    m = np.asarray(R, dtype=np.float64).reshape(3, 3).T
+    t = m[0, 0] + m[1, 1] + m[2, 2]
+    q = np.zeros(4)
+    if t > 0:
+        t = math.sqrt(t + 1.0); q[3] = 0.5 * t; t = 0.5 / t
+        q[0] = (m[2, 1] - m[1, 2]) * t; q[1] = (m[0, 2] - m[2, 0]) * t; q[2] = (m[1, 0] - m[0, 1]) * t
+    else:
+        i = 0
+        if m[1, 1] > m[0, 0]:
+            i = 1
+        if m[2, 2] > m[i, i]:
+            i = 2
+        j, k = (i + 1) % 3, (i + 2) % 3
+        t = math.sqrt(m[i, i] - m[j, j] - m[k, k] + 1.0)
+        q[i] = 0.5 * t; t = 0.5 / t
+        q[3] = (m[k, j] - m[j, k]) * t; q[j] = (m[j, i] + m[i, j]) * t; q[k] = (m[k, i] + m[i, k]) * t
+    return q / np.linalg.norm(q)
+
+
+def write_g2o(g: Graph, path: str) -> None:
+    """VERTEX_SE2 / VERTEX_XY / VERTEX_SE3:QUAT / EDGE_SE2 / EDGE_SE2_XY / EDGE_SE3:QUAT and FIX lines, 17 significant digits."""
+    from .graph import EDGE_DIM, EDGE_MEAS_DIM, VERTEX_ESTIMATE_DIM
+    est_off = np.concatenate([[0], np.cumsum(VERTEX_ESTIMATE_DIM[g.v_type])])
+    meas_off = np.concatenate([[0], np.cumsum(EDGE_MEAS_DIM[g.e_type])])
+    info_off = np.concatenate([[0], np.cumsum(EDGE_DIM[g.e_type] ** 2)])
+    f = lambda xs: " ".join(repr(float(x)) for x in xs)
+    with open(path, "w") as fh:
+        for i in range(g.n_vertices):
+            x = g.v_estimate[est_off[i]:est_off[i + 1]]; t = int(g.v_type[i]); vid = int(g.v_id[i])
+            if t == VERTEX_SE2:
+                fh.write(f"VERTEX_SE2 {vid} {f(x)}\n")
+            elif t == VERTEX_POINT_XY:
+                fh.write(f"VERTEX_XY {vid} {f(x)}\n")
+            elif t == VERTEX_SE3:
+                fh.write(f"VERTEX_SE3:QUAT {vid} {f(x[9:12])} {f(_r_to_quat(x[:9]))}\n")
+            else:
+                raise ValueError(f"vertex type {t} has no .g2o writer here")
+            if g.v_fixed[i]:
+                fh.write(f"FIX {vid}\n")
+        for k in range(g.n_edges):
+            z = g.e_measurement[meas_off[k]:meas_off[k + 1]]; t = int(g.e_type[k]); d = int(EDGE_DIM[t])
+            info = g.e_information[info_off[k]:info_off[k + 1]].reshape(d, d)
+            upper = [info[i, j] for i in range(d) for j in range(i, d)]
+            a, b = int(g.v_id[g.e_v0[k]]), int(g.v_id[g.e_v1[k]])
+            if t == EDGE_SE2:
+                fh.write(f"EDGE_SE2 {a} {b} {f(z)} {f(upper)}\n")
+            elif t == EDGE_SE2_POINT_XY:
+                fh.write(f"EDGE_SE2_XY {a} {b} {f(z)} {f(upper)}\n")
+            elif t == EDGE_SE3:
+                fh.write(f"EDGE_SE3:QUAT {a} {b} {f(z[9:12])} {f(_r_to_quat(z[:9]))} {f(upper)}\n")
+            else:
+                raise ValueError(f"edge type {t} has no .g2o writer here")
