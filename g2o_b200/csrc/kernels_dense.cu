@@ -5,8 +5,10 @@
 // api.cu maps to "solve() returned false" exactly like the reference.
 //   potrf_diag_kernel   64 x 64 diagonal block, one CTA, in shared memory
 //   trsm_panel_kernel   L21 = A21 L11^-T, thread per row, L11 broadcast from shared memory
-//   syrk_dmma_kernel    A22 -= L21 L21^T on the FP64 tensor pipe (mma.sync.m8n8k4.f64): 128 x 128 tile per CTA, 8 warps x (64 x 32),
-//                       panel staged [k][row] with a row stride of 132 doubles (conflict-free 64-bit fragment loads)
+//   syrk_dmma_kernel    C -= L L^T on the FP64 tensor pipe (mma.sync.m8n8k4.f64): 128 x 128 tile per CTA, 8 warps x (64 x 32), the panels
+//                       streamed through a 2-stage cp.async ring, staged [k][row] with a row stride of 132 doubles (conflict-free 64-bit
+//                       fragment loads).  Two-level blocking: 64-wide panels inside 512-wide outer panels, so that the trailing matrix is
+//                       read and written once per 512 columns
 //   trsv_*              blocked forward / backward substitution
 // H is column-major n x n with leading dimension n; only the lower triangle is referenced after assembly.
 #include <cuda_runtime.h>
@@ -49,8 +51,11 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ H,
     if (tid == 0) sA[j][j] = sd;
     for (int r = j + 1 + tid; r < nb; r += 256) sA[r][j] /= sd;
     __syncthreads();
-    const int m = nb - j - 1;             // trailing update of the lower triangle
-    for (int t = tid; t < m * m; t += 256) { const int r = j + 1 + t % m, c = j + 1 + t / m; if (r >= c) sA[r][c] -= sA[r][j] * sA[c][j]; }
+    // trailing update of the lower triangle, 16 x 16 thread grid striding over rows / columns (no integer division in the loop)
+    for (int c = j + 1 + (tid >> 4); c < nb; c += 16) {
+      const double lc = sA[c][j];
+      for (int r = c + (tid & 15); r < nb; r += 16) sA[r][c] -= sA[r][j] * lc;
+    }
     __syncthreads();
   }
   for (int t = tid; t < nb * nb; t += 256) { const int r = t % nb, c = t / nb; if (r >= c) H[(size_t)(k0 + r) + (size_t)(k0 + c) * n] = sA[r][c]; }
@@ -83,21 +88,33 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// A22(tile) -= L21(rows of the tile) L21(columns of the tile)^T, lower tiles only (blockIdx.y >= blockIdx.x)
-__global__ void __launch_bounds__(256) syrk_dmma_kernel(double* __restrict__ H, int n, int k0, int nb) {
+// H[r, c] -= sum_k L[r, kBegin + k] L[c, kBegin + k] for the lower tiles of rows >= colBegin, columns in [colBegin, colEnd):
+// 128 x 128 tile per CTA, the two 128 x kLen panels streamed in chunks of KC columns through a 2-stage cp.async ring.
+// Used twice per outer panel: K = 64 inside the panel, K = up to 512 for the trailing matrix (one read-modify-write of C per 512 columns).
+constexpr int KC = 32;
+__device__ __forceinline__ void cpAsync8(double* dstSmem, const double* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dstSmem);
+  const int sz = valid ? 8 : 0;                       // src-size 0: zero fill
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__global__ void __launch_bounds__(256) syrk_dmma_kernel(double* __restrict__ H, int n, int kBegin, int kLen, int colBegin, int colEnd) {
   if (blockIdx.y < blockIdx.x) return;
-  extern __shared__ double smem[];
-  double* sA = smem;                      // [nb][LDS_] rows of the tile
-  double* sB = smem + NB * LDS_;          // [nb][LDS_] columns of the tile
-  const int t0 = k0 + nb;
-  const int r0 = t0 + blockIdx.y * TS, c0 = t0 + blockIdx.x * TS;
+  extern __shared__ double smem[];                    // [2 stages][A | B][KC][LDS_]
+  const int r0 = colBegin + blockIdx.y * TS, c0 = colBegin + blockIdx.x * TS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int t = tid; t < nb * TS; t += 256) {
-    const int r = t % TS, k = t / TS;
-    sA[k * LDS_ + r] = (r0 + r < n) ? H[(size_t)(r0 + r) + (size_t)(k0 + k) * n] : 0.0;
-    sB[k * LDS_ + r] = (c0 + r < n) ? H[(size_t)(c0 + r) + (size_t)(k0 + k) * n] : 0.0;
-  }
-  __syncthreads();
+  const int nChunks = (kLen + KC - 1) / KC;
+  auto load = [&](int c, int stage) {
+    double* sA = smem + (size_t)stage * 2 * KC * LDS_; double* sB = sA + KC * LDS_;
+    for (int t = tid; t < KC * TS; t += 256) {
+      const int r = t % TS, k = t / TS, kk = c * KC + k;
+      const bool kOk = kk < kLen;
+      const size_t col = (size_t)(kBegin + (kOk ? kk : 0)) * n;
+      const bool aOk = kOk && r0 + r < n, bOk = kOk && c0 + r < n;
+      cpAsync8(sA + k * LDS_ + r, H + (aOk ? (size_t)(r0 + r) : 0) + col, aOk);
+      cpAsync8(sB + k * LDS_ + r, H + (bOk ? (size_t)(c0 + r) : 0) + col, bOk);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   const int wr = (warp >> 2) * 64, wc = (warp & 3) * 32;      // warp sub-tile: 64 rows x 32 columns
   const int m = lane >> 2, kq = lane & 3;
   double C[8][4][2];
@@ -105,16 +122,25 @@ __global__ void __launch_bounds__(256) syrk_dmma_kernel(double* __restrict__ H, 
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) { C[i][j][0] = 0; C[i][j][1] = 0; }
-  for (int kk = 0; kk < nb; kk += 4) {
-    double a[8], b[4];
+  load(0, 0);
+  for (int c = 0; c < nChunks; ++c) {
+    if (c + 1 < nChunks) { load(c + 1, (c + 1) & 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const double* sA = smem + (size_t)(c & 1) * 2 * KC * LDS_; const double* sB = sA + KC * LDS_;
+#pragma unroll 2
+    for (int kk = 0; kk < KC; kk += 4) {
+      double a[8], b[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = sA[(kk + kq) * LDS_ + wr + 8 * i + m];
+      for (int i = 0; i < 8; ++i) a[i] = sA[(kk + kq) * LDS_ + wr + 8 * i + m];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = sB[(kk + kq) * LDS_ + wc + 8 * j + m];
+      for (int j = 0; j < 4; ++j) b[j] = sB[(kk + kq) * LDS_ + wc + 8 * j + m];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dmma(C[i][j], a[i], b[j]);
+        for (int j = 0; j < 4; ++j) dmma(C[i][j], a[i], b[j]);
+    }
+    __syncthreads();                                  // the stage is refilled two iterations later
   }
   const bool diagTile = blockIdx.x == blockIdx.y;
 #pragma unroll
@@ -125,23 +151,29 @@ __global__ void __launch_bounds__(256) syrk_dmma_kernel(double* __restrict__ H, 
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int gc = c0 + wc + 8 * j + 2 * kq + h;
-        if (gr < n && gc < n && (!diagTile || gr >= gc)) H[(size_t)gr + (size_t)gc * n] -= C[i][j][h];
+        if (gr < n && gc < colEnd && (!diagTile || gr >= gc)) H[(size_t)gr + (size_t)gc * n] -= C[i][j][h];
       }
     }
 }
 
 // forward: y_k = L11^-1 b_k (one CTA), then b[below] -= L21 y_k (thread per row)
-__global__ void __launch_bounds__(NB) trsv_diag_fwd_kernel(const double* __restrict__ H, int n, int k0, int nb, double* __restrict__ x) {
+__global__ void __launch_bounds__(256) trsv_diag_fwd_kernel(const double* __restrict__ H, int n, int k0, int nb, double* __restrict__ x) {
+  __shared__ double sL[NB][NB + 1];
   __shared__ double sx[NB];
   const int t = threadIdx.x;
+  for (int q = t; q < nb * nb; q += 256) { const int r = q % nb, c = q / nb; if (r >= c) sL[r][c] = H[(size_t)(k0 + r) + (size_t)(k0 + c) * n]; }
   if (t < nb) sx[t] = x[k0 + t];
   __syncthreads();
-  for (int j = 0; j < nb; ++j) {
-    if (t == j) sx[j] /= H[(size_t)(k0 + j) + (size_t)(k0 + j) * n];
-    __syncthreads();
-    if (t > j && t < nb) sx[t] -= H[(size_t)(k0 + t) + (size_t)(k0 + j) * n] * sx[j];
-    __syncthreads();
+  if (t < 32) {                                        // one warp: lane owns rows lane and lane + 32
+    for (int j = 0; j < nb; ++j) {
+      const double xj = sx[j] / sL[j][j];
+      __syncwarp();
+      if (t == 0) sx[j] = xj;
+      for (int r = j + 1 + t; r < nb; r += 32) sx[r] -= sL[r][j] * xj;
+      __syncwarp();
+    }
   }
+  __syncthreads();
   if (t < nb) x[k0 + t] = sx[t];
 }
 __global__ void __launch_bounds__(128) trsv_update_fwd_kernel(const double* __restrict__ H, int n, int k0, int nb, double* __restrict__ x) {
@@ -166,17 +198,23 @@ __global__ void __launch_bounds__(256) trsv_update_bwd_kernel(const double* __re
   __syncthreads();
   if (threadIdx.x == 0) { double r = 0; for (int q = 0; q < 8; ++q) r += sm[q]; x[k0 + j] -= r; }
 }
-__global__ void __launch_bounds__(NB) trsv_diag_bwd_kernel(const double* __restrict__ H, int n, int k0, int nb, double* __restrict__ x) {
+__global__ void __launch_bounds__(256) trsv_diag_bwd_kernel(const double* __restrict__ H, int n, int k0, int nb, double* __restrict__ x) {
+  __shared__ double sL[NB][NB + 1];
   __shared__ double sx[NB];
   const int t = threadIdx.x;
+  for (int q = t; q < nb * nb; q += 256) { const int r = q % nb, c = q / nb; if (r >= c) sL[r][c] = H[(size_t)(k0 + r) + (size_t)(k0 + c) * n]; }
   if (t < nb) sx[t] = x[k0 + t];
   __syncthreads();
-  for (int j = nb - 1; j >= 0; --j) {
-    if (t == j) sx[j] /= H[(size_t)(k0 + j) + (size_t)(k0 + j) * n];
-    __syncthreads();
-    if (t < j) sx[t] -= H[(size_t)(k0 + j) + (size_t)(k0 + t) * n] * sx[j];     // L^T(t, j) = L(j, t)
-    __syncthreads();
+  if (t < 32) {
+    for (int j = nb - 1; j >= 0; --j) {
+      const double xj = sx[j] / sL[j][j];
+      __syncwarp();
+      if (t == 0) sx[j] = xj;
+      for (int r = t; r < j; r += 32) sx[r] -= sL[j][r] * xj;      // L^T(r, j) = L(j, r)
+      __syncwarp();
+    }
   }
+  __syncthreads();
   if (t < nb) x[k0 + t] = sx[t];
 }
 
@@ -197,29 +235,40 @@ void launchDenseAssemble(const PcgDev& p, double* H, cudaStream_t st, int64_t* l
 // factorise H = L L^T in place (lower), then x = H^-1 b.  *info (device int, zeroed here) becomes non-zero when a pivot is not positive.
 int launchDenseCholeskySolve(double* H, int n, const double* b, double* x, int* info, cudaStream_t st, int64_t* launches) {
   static bool configured = false;
-  constexpr int kSyrkSmem = 2 * NB * LDS_ * (int)sizeof(double);
+  constexpr int kSyrkSmem = 2 * 2 * KC * LDS_ * (int)sizeof(double);
+  constexpr int NO = 512;                             // outer panel: the trailing matrix is updated once per NO columns
   if (!configured) { cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSyrkSmem); configured = true; }
   cudaMemsetAsync(info, 0, sizeof(int), st);
-  for (int k0 = 0; k0 < n; k0 += NB) {
-    const int nb = n - k0 < NB ? n - k0 : NB, rem = n - k0 - nb;
-    potrf_diag_kernel<<<1, 256, 0, st>>>(H, n, k0, nb, info); *launches += 1;
-    if (rem > 0) {
-      trsm_panel_kernel<<<(rem + 127) / 128, 128, 0, st>>>(H, n, k0, nb);
-      const int tiles = (rem + TS - 1) / TS;
-      syrk_dmma_kernel<<<dim3(tiles, tiles), 256, kSyrkSmem, st>>>(H, n, k0, nb);
-      *launches += 2;
+  for (int K0 = 0; K0 < n; K0 += NO) {
+    const int pend = K0 + NO < n ? K0 + NO : n;
+    for (int k0 = K0; k0 < pend; k0 += NB) {
+      const int nb = pend - k0 < NB ? pend - k0 : NB, rem = n - k0 - nb;
+      potrf_diag_kernel<<<1, 256, 0, st>>>(H, n, k0, nb, info); *launches += 1;
+      if (rem > 0) {
+        trsm_panel_kernel<<<(rem + 127) / 128, 128, 0, st>>>(H, n, k0, nb); *launches += 1;
+        const int cb = k0 + nb;                       // inside the outer panel: only its remaining columns are updated now
+        if (cb < pend) {
+          syrk_dmma_kernel<<<dim3((pend - cb + TS - 1) / TS, (n - cb + TS - 1) / TS), 256, kSyrkSmem, st>>>(H, n, k0, nb, cb, pend);
+          *launches += 1;
+        }
+      }
+    }
+    if (pend < n) {                                   // trailing matrix -= L[pend:, K0:pend] L[pend:, K0:pend]^T
+      const int tiles = (n - pend + TS - 1) / TS;
+      syrk_dmma_kernel<<<dim3(tiles, tiles), 256, kSyrkSmem, st>>>(H, n, K0, pend - K0, pend, n);
+      *launches += 1;
     }
   }
   if (x != b) cudaMemcpyAsync(x, b, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st);
   for (int k0 = 0; k0 < n; k0 += NB) {
     const int nb = n - k0 < NB ? n - k0 : NB, rem = n - k0 - nb;
-    trsv_diag_fwd_kernel<<<1, NB, 0, st>>>(H, n, k0, nb, x); *launches += 1;
+    trsv_diag_fwd_kernel<<<1, 256, 0, st>>>(H, n, k0, nb, x); *launches += 1;
     if (rem > 0) { trsv_update_fwd_kernel<<<(rem + 127) / 128, 128, 0, st>>>(H, n, k0, nb, x); *launches += 1; }
   }
   for (int k0 = ((n - 1) / NB) * NB; k0 >= 0; k0 -= NB) {
     const int nb = n - k0 < NB ? n - k0 : NB, rem = n - k0 - nb;
     if (rem > 0) { trsv_update_bwd_kernel<<<nb, 256, 0, st>>>(H, n, k0, nb, x); *launches += 1; }
-    trsv_diag_bwd_kernel<<<1, NB, 0, st>>>(H, n, k0, nb, x); *launches += 1;
+    trsv_diag_bwd_kernel<<<1, 256, 0, st>>>(H, n, k0, nb, x); *launches += 1;
   }
   return 0;
 }
