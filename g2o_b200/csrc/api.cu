@@ -420,7 +420,8 @@ int buildDevice(g2ocu_solver* s) {
   pc.n = st.sizePoses; pc.nb = st.numPoses; pc.P = P; pc.rowPtr = s->aRowPtr.p; pc.colIdx = s->aColIdx.p; pc.diag = s->aDiag.p; pc.nnz = (int)colIdx.size();
   pc.A = st.doSchur ? s->S.p : s->Hpp.p;
   CU(s->Minv.alloc((size_t)st.numPoses * P * P)); CU(s->vr.alloc(pc.n)); CU(s->vd.alloc(pc.n)); CU(s->vq.alloc(pc.n)); CU(s->vs.alloc(pc.n)); CU(s->scal.alloc(16));
-  pc.nPartial = (st.numPoses + 127) / 128; pc.nPartialDq = std::min(296, (pc.n + 255) / 256);
+  pc.nPartial = (pc.n + 255) / 256;   // one partial per CTA of the thread-per-scalar-row kernels
+  pc.nPartialDq = std::min(296, (pc.n + 255) / 256);
   CU(s->partial.alloc(pc.nPartial)); CU(s->partialDq.alloc(pc.nPartialDq));
   pc.Minv = s->Minv.p; pc.r = s->vr.p; pc.d = s->vd.p; pc.q = s->vq.p; pc.s = s->vs.p; pc.x = s->x.p; pc.scal = s->scal.p; pc.partial = s->partial.p; pc.partialDq = s->partialDq.p;
   pc.itemRow = s->spRow.p; pc.itemBegin = s->spBegin.p; pc.itemEnd = s->spEnd.p;

@@ -86,7 +86,7 @@ struct PcgDev {
   double* Minv = nullptr;                  // nb x P x P
   double *r = nullptr, *d = nullptr, *q = nullptr, *s = nullptr, *x = nullptr;
   double* scal = nullptr;                  // device scalars: [0] dn, [1] d.q, [2] dn_new, [3] alpha, [4] beta, [5] d0, [6] converged flag, [7] iterations
-  double* partial = nullptr; int nPartial = 0;          // one per CTA of the block-row kernels: ceil(nb/128)
+  double* partial = nullptr; int nPartial = 0;          // one per CTA of pcg_init / pcg_update1: ceil(n/256)
   double* partialDq = nullptr; int nPartialDq = 0;      // one per CTA of the dot kernel
   const int32_t* itemRow = nullptr; const int32_t* itemBegin = nullptr; const int32_t* itemEnd = nullptr; int nItems = 0;   // SpMV work items (row, block range)
   unsigned int* ticket = nullptr;          // zero-initialised counter for the last-CTA commit of pcg_update2_commit_kernel

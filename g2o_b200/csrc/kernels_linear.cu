@@ -545,24 +545,22 @@ void launchP2pExchangeDot(const PcgDev& p, const P2pDev& x, cudaStream_t st, int
   *launches += 2;
 }
 
-// x = 0, r = b, d = M^-1 r, partial r.d   (thread per block row)
-template <int P> __global__ void __launch_bounds__(128) pcg_init_kernel(PcgDev p, const double* __restrict__ b) {
+// x = 0, r = b, d = M^-1 r, partial r.d   (thread per scalar row: the P threads of a block row read the same r and one row of M^-1 each,
+// so every load of the warp is contiguous)
+template <int P> __global__ void __launch_bounds__(256) pcg_init_kernel(PcgDev p, const double* __restrict__ b) {
   constexpr int PP = P * P;
-  __shared__ double sm[4];
-  const int i = blockIdx.x * 128 + threadIdx.x;
+  __shared__ double sm[8];
+  const int t = blockIdx.x * 256 + threadIdx.x;
   double acc = 0;
-  if (i < p.nb) {
-    double rr[P];
+  if (t < p.n) {
+    const int i = t / P, r = t - i * P;
+    const double* M = p.Minv + (size_t)i * PP + r;
+    double v = 0, mine = 0;
 #pragma unroll
-    for (int c = 0; c < P; ++c) { rr[c] = b[(size_t)i * P + c]; p.r[(size_t)i * P + c] = rr[c]; p.x[(size_t)i * P + c] = 0; }
-    const double* M = p.Minv + (size_t)i * PP;
-#pragma unroll
-    for (int r = 0; r < P; ++r) { double v = 0;
-#pragma unroll
-      for (int c = 0; c < P; ++c) v += M[r + P * c] * rr[c];
-      p.d[(size_t)i * P + r] = v; acc += rr[r] * v; }
+    for (int c = 0; c < P; ++c) { const double rc = b[(size_t)i * P + c]; v += M[P * c] * rc; if (c == r) mine = rc; }
+    p.r[t] = mine; p.x[t] = 0; p.d[t] = v; acc = mine * v;
   }
-  const double s = blockSumL<128>(acc, sm);
+  const double s = blockSumL<256>(acc, sm);
   if (threadIdx.x == 0) p.partial[blockIdx.x] = s;
 }
 __global__ void __launch_bounds__(256) pcg_init_finish_kernel(PcgDev p, double tolerance, double residual, int absoluteTolerance) {
@@ -574,42 +572,43 @@ __global__ void __launch_bounds__(256) pcg_init_finish_kernel(PcgDev p, double t
     p.scal[0] = dn; p.scal[2] = dn; p.scal[5] = d0; p.scal[6] = (dn <= d0) ? 1.0 : 0.0; p.scal[7] = 0.0;
   }
 }
-// alpha = dn / (d.q);  x += alpha d;  r -= alpha q;  s = M^-1 r;  partial r.s
-template <int P> __global__ void __launch_bounds__(128) pcg_update1_kernel(PcgDev p, const double* dqPartial, int nDq) {
+// alpha = dn / (d.q);  x += alpha d;  s = M^-1 (r - alpha q);  partial (r - alpha q).s   (thread per scalar row, see pcg_init_kernel).
+// r itself is left untouched here - the P threads of a block row all read its old values and a block row may straddle two CTAs -
+// and is updated by pcg_update2_commit_kernel, which runs after this kernel has finished.
+template <int P> __global__ void __launch_bounds__(256) pcg_update1_kernel(PcgDev p, const double* dqPartial, int nDq) {
   constexpr int PP = P * P;
-  __shared__ double sm[4];
+  __shared__ double sm[8];
   if (p.scal[6] != 0.0) return;
-  const double dq = sumPartialsAll<128>(dqPartial, nDq, sm);
+  const double dq = sumPartialsAll<256>(dqPartial, nDq, sm);
   const double alpha = p.scal[0] / dq;
-  const int i = blockIdx.x * 128 + threadIdx.x;
+  const int t = blockIdx.x * 256 + threadIdx.x;
   double acc = 0;
-  if (i < p.nb) {
-    double rr[P];
+  if (t < p.n) {
+    const int i = t / P, r = t - i * P;
+    const double* M = p.Minv + (size_t)i * PP + r;
+    double v = 0, mine = 0;
 #pragma unroll
     for (int c = 0; c < P; ++c) {
       const size_t o = (size_t)i * P + c;
-      p.x[o] += alpha * p.d[o];
-      rr[c] = p.r[o] - alpha * p.q[o];
-      p.r[o] = rr[c];
+      const double rc = p.r[o] - alpha * p.q[o];
+      v += M[P * c] * rc;
+      if (c == r) mine = rc;
     }
-    const double* M = p.Minv + (size_t)i * PP;
-#pragma unroll
-    for (int r = 0; r < P; ++r) { double v = 0;
-#pragma unroll
-      for (int c = 0; c < P; ++c) v += M[r + P * c] * rr[c];
-      p.s[(size_t)i * P + r] = v; acc += rr[r] * v; }
+    p.x[t] += alpha * p.d[t];
+    p.s[t] = v; acc = mine * v;
   }
-  const double s = blockSumL<128>(acc, sm);
+  const double s = blockSumL<256>(acc, sm);
   if (threadIdx.x == 0) p.partial[blockIdx.x] = s;
 }
-// beta = dn_new / dn;  d = s + beta d;  q = 0 for the next product;  the CTA that finishes last commits the scalars (dn <- dn_new, iteration
+// r -= alpha q;  beta = dn_new / dn;  d = s + beta d;  q = 0 for the next product;  the CTA that finishes last commits the scalars (dn <- dn_new, iteration
 // count, convergence flag): every CTA has read scal[0] / scal[6] before it takes its ticket, so the commit cannot race with them.
 __global__ void __launch_bounds__(256) pcg_update2_commit_kernel(PcgDev p, unsigned int* ticket) {
   __shared__ double sm[8];
   if (p.scal[6] != 0.0) return;
   const double dnNew = sumPartialsAll<256>(p.partial, p.nPartial, sm);
-  const double beta = dnNew / p.scal[0];
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < p.n; i += gridDim.x * 256) { p.d[i] = p.s[i] + beta * p.d[i]; p.q[i] = 0.0; }
+  const double dq = sumPartialsAll<256>(p.partialDq, p.nPartialDq, sm);
+  const double alpha = p.scal[0] / dq, beta = dnNew / p.scal[0];     // the same alpha pcg_update1_kernel used (same partials, same order)
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < p.n; i += gridDim.x * 256) { p.r[i] -= alpha * p.q[i]; p.d[i] = p.s[i] + beta * p.d[i]; p.q[i] = 0.0; }
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -738,7 +737,7 @@ void launchSpmv(const PcgDev& p, const double* src, double* dst, cudaStream_t st
 }
 
 void launchPcgInit(const PcgDev& p, const double* b, double tolerance, double residual, int absoluteTolerance, cudaStream_t st, int64_t* launches) {
-#define CALL(PV) pcg_init_kernel<PV><<<p.nPartial, 128, 0, st>>>(p, b);
+#define CALL(PV) pcg_init_kernel<PV><<<p.nPartial, 256, 0, st>>>(p, b);
   FOR_P(p.P, CALL)
 #undef CALL
   pcg_init_finish_kernel<<<1, 256, 0, st>>>(p, tolerance, residual, absoluteTolerance);
@@ -748,7 +747,7 @@ void launchPcgInit(const PcgDev& p, const double* b, double tolerance, double re
 bool pcgSingleCtaTail(const PcgDev&) { return true; }   // the tail leaves q zeroed for the next product
 void launchPcgTail(const PcgDev& p, cudaStream_t st, int64_t* launches, bool dotDone) {
   if (!dotDone) dot_partial_kernel<<<p.nPartialDq, 256, 0, st>>>(p.scal, p.d, p.q, p.n, p.partialDq);
-#define CALL(PV) pcg_update1_kernel<PV><<<p.nPartial, 128, 0, st>>>(p, p.partialDq, p.nPartialDq);
+#define CALL(PV) pcg_update1_kernel<PV><<<p.nPartial, 256, 0, st>>>(p, p.partialDq, p.nPartialDq);
   FOR_P(p.P, CALL)
 #undef CALL
   pcg_update2_commit_kernel<<<p.nPartialDq, 256, 0, st>>>(p, p.ticket);
