@@ -217,14 +217,18 @@ int uploadEstimates(g2ocu_solver* s) {
 }
 
 // device estimates -> host graph copy (the host copy is what a rebuild uploads again)
+// sharded runs: zero the landmarks owned by other ranks and sum, afterwards every rank holds all of them (on the device)
+int gatherLandmarks(g2ocu_solver* s) {
+  const Structure& st = s->st;
+  if (s->world <= 1 || st.numLandmarks == 0) return G2OCU_OK;
+  const int Sl = vertexEstimateDim(st.lmType);
+  if (st.lmBegin > 0) CU(cudaMemsetAsync(s->lmEst.p, 0, sizeof(double) * (size_t)st.lmBegin * Sl, s->stream));
+  if (st.lmEnd < st.numLandmarks) CU(cudaMemsetAsync(s->lmEst.p + (size_t)st.lmEnd * Sl, 0, sizeof(double) * (size_t)(st.numLandmarks - st.lmEnd) * Sl, s->stream));
+  return allreduceDev(s, s->lmEst.p, (int64_t)st.numLandmarks * Sl, 0);
+}
 int downloadEstimates(g2ocu_solver* s) {
   const Structure& st = s->st; HostGraph& g = s->g;
-  if (s->world > 1 && st.numLandmarks > 0) {   // zero the landmarks owned by other ranks and sum: afterwards every rank holds all of them
-    const int Sl = vertexEstimateDim(st.lmType);
-    if (st.lmBegin > 0) CU(cudaMemsetAsync(s->lmEst.p, 0, sizeof(double) * (size_t)st.lmBegin * Sl, s->stream));
-    if (st.lmEnd < st.numLandmarks) CU(cudaMemsetAsync(s->lmEst.p + (size_t)st.lmEnd * Sl, 0, sizeof(double) * (size_t)(st.numLandmarks - st.lmEnd) * Sl, s->stream));
-    int rc = allreduceDev(s, s->lmEst.p, (int64_t)st.numLandmarks * Sl, 0); if (rc) return rc;
-  }
+  { int rc = gatherLandmarks(s); if (rc) return rc; }
   std::vector<double> hp(s->poseEst.n), hl(s->lmEst.n);
   if (hp.size()) CU(cudaMemcpyAsync(hp.data(), s->poseEst.p, hp.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   if (hl.size()) CU(cudaMemcpyAsync(hl.data(), s->lmEst.p, hl.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -953,7 +957,8 @@ int g2ocu_set_estimates(g2ocu_solver* s, const double* host) {
 int g2ocu_get_estimates(g2ocu_solver* s, double* host) {
   if (!s || !host) return G2OCU_E_INVALID;
   if (!s->hasGraph) return fail(s, G2OCU_E_INVALID, "no graph set");
-  if (s->structureBuilt && s->fastEstimates && s->world <= 1) {
+  if (s->structureBuilt && s->fastEstimates) {
+    { int rc = gatherLandmarks(s); if (rc) return rc; }
     CU(cudaMemcpyAsync(host + s->poseHostOff, s->poseEst.p, s->poseEst.n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     if (s->lmEst.n) CU(cudaMemcpyAsync(host + s->lmHostOff, s->lmEst.p, s->lmEst.n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     return syncStream(s);
