@@ -234,10 +234,9 @@ void launchDenseAssemble(const PcgDev& p, double* H, cudaStream_t st, int64_t* l
 
 // factorise H = L L^T in place (lower), then x = H^-1 b.  *info (device int, zeroed here) becomes non-zero when a pivot is not positive.
 int launchDenseCholeskySolve(double* H, int n, const double* b, double* x, int* info, cudaStream_t st, int64_t* launches) {
-  static bool configured = false;
   constexpr int kSyrkSmem = 2 * 2 * KC * LDS_ * (int)sizeof(double);
   constexpr int NO = 512;                             // outer panel: the trailing matrix is updated once per NO columns
-  if (!configured) { cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSyrkSmem); configured = true; }
+  cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSyrkSmem);   // per device: set on every call (solvers may live on several GPUs of one process)
   cudaMemsetAsync(info, 0, sizeof(int), st);
   for (int K0 = 0; K0 < n; K0 += NO) {
     const int pend = K0 + NO < n ? K0 + NO : n;

@@ -694,8 +694,7 @@ template <int P, int L> static void schurPL(const SchurDev& d, const SystemDev& 
   }
   if (d.nTileChunks > 0 && !mma) {
     constexpr int kTileSmem = kTileBatch * (kTileCols * ((P * L) | 1) + kTileRows * P * L) * (int)sizeof(double);
-    static bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(schur_tile_kernel<P, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem); configured = true; }
+    cudaFuncSetAttribute(schur_tile_kernel<P, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);   // per device, hence on every call
     MarkScope ms(marks, "schur_tiles");
     schur_tile_kernel<P, L><<<d.nTileChunks, kTileThreads, kTileSmem, st>>>(d, sys.Hpl);
     *launches += 1;

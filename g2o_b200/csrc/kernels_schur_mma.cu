@@ -5,7 +5,8 @@
 // 32 consecutive column cameras and walks the list of landmarks seen from both sides ("entries": first Hpl block + presence mask on
 // each side; a landmark's blocks are contiguous in Hpl because they are sorted by camera).
 //   * staging: per batch of up to 32 entries, one cp.async.bulk (TMA bulk copy) per side and entry brings the raw, contiguous
-//     W / Hpl blocks into a 4-stage shared-memory ring, issued lane-parallel by warp 0 three batches ahead; completion is tracked by
+//     W / Hpl blocks into a 2-stage shared-memory ring of 96 KB stages (measured: fewer, larger batches beat a deeper ring), issued
+//     lane-parallel by warp 0 one batch ahead; completion is tracked by
 //     mbarriers (no __syncthreads in the main loop).
 //   * 8 warps = (row half: 4 cameras) x (column group: 8 cameras); 2 warps per SM sub-partition leave 255 registers per thread.  One DMMA covers rows 0..7 x columns 0..7 of one (i,j)
 //     block with K = the 3 landmark coordinates (+1 zero pad): A[m][k] = W_i[m,k], B[k][n] = B_j[n,k]; absent row cameras are skipped
@@ -31,8 +32,8 @@ namespace {
 
 constexpr int kMmaConsumers = 8;                   // consumer warps
 constexpr int kMmaThreads = kMmaConsumers * 32;
-constexpr int kMmaStages = 4;
-constexpr int kMmaStageDoubles = 6 * 1024;         // 48 KB per stage
+constexpr int kMmaStages = 2;
+constexpr int kMmaStageDoubles = 12 * 1024;        // 96 KB per stage
 constexpr int kMmaBatch = 32;                      // entries per stage at most (one per producer lane)
 
 struct __align__(16) MmaHdr { uint32_t offI, offJ, maskI, maskJ; };   // offsets in doubles into the stage buffer
@@ -363,9 +364,8 @@ bool schurMmaSupported(int P, int L) { return L == 3 && (P == 9 || P == 6); }
 template <int P, int L> static void launchMmaPL(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, cudaStream_t st, int64_t* launches, const KernelMarks* marks) {
   if (nBlocks > 0) { if (marks && marks->begin) marks->begin(marks->ctx, "schur_coeff"); coeff_w_kernel<P, L><<<(nBlocks + 127) / 128, 128, 0, st>>>(d, sys.Hpl, hplLm, nBlocks); *launches += 1; if (marks && marks->end) marks->end(marks->ctx); }
   if (d.nTileChunks > 0) {
-    static bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(schur_mma_kernel<P, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes); configured = true; }
-    static const int dbg = getenv("G2OCU_SCHUR_DEBUG") ? atoi(getenv("G2OCU_SCHUR_DEBUG")) : 0;
+    cudaFuncSetAttribute(schur_mma_kernel<P, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes);   // per device, hence on every call
+    static const int dbg = getenv("G2OCU_SCHUR_DEBUG") ? atoi(getenv("G2OCU_SCHUR_DEBUG")) : 0;   // developer switches: 1 no loads, 2 no products, 3 per-warp cycle dump (tools/schur_prof.py)
     long long* prof = nullptr;
     if (dbg == 3) cudaMalloc(&prof, sizeof(long long) * 8 * kMmaConsumers * (size_t)d.nTileChunks);
     if (marks && marks->begin) marks->begin(marks->ctx, "schur_tiles");
