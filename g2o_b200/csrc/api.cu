@@ -109,6 +109,7 @@ struct g2ocu_solver {
   bool fastEstimates = false; int64_t poseHostOff = 0, lmHostOff = 0;
   // sharding
   int rank = 0, world = 1; g2ocu_allreduce_fn allreduce = nullptr; void* allreduceUser = nullptr;
+  bool kernelTiming = false;      // property "kernelTiming": CUDA events around individual kernels, not only around phases
   int64_t slabBlocks = 0;         // blocks of the reduced system per rank (slab PCG), 0 when not sharded
   void* ncclComm = nullptr;       // set by g2ocu_set_shard_nccl: collectives go straight to NCCL on the solver's stream
   P2pDev p2p; bool p2pReady = false; double* p2pLocal = nullptr; void* p2pOpened[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // CUDA-IPC peer buffers for the slab-PCG exchange
@@ -170,6 +171,13 @@ struct PhaseTimer {
   g2ocu_solver* s; std::string phase; cudaEvent_t a; int64_t l0;
   PhaseTimer(g2ocu_solver* s_, const char* ph) : s(s_), phase(ph) { a = getEvent(s); cudaEventRecord(a, s->stream); l0 = s->launches; }
   ~PhaseTimer() { cudaEvent_t b = getEvent(s); cudaEventRecord(b, s->stream); s->pending.push_back({phase, a, b, s->launches - l0}); }
+};
+// per-kernel timing (inside a phase): two event records per kernel are measurable in a PCG iteration of a few tens of microseconds,
+// so these only run when the "kernelTiming" property is set (bench.py does a separate breakdown pass with it)
+struct KernelTimer {
+  PhaseTimer* t = nullptr;
+  KernelTimer(g2ocu_solver* s, const char* ph) { if (s->kernelTiming) t = new PhaseTimer(s, ph); }
+  ~KernelTimer() { delete t; }
 };
 // call only after the stream has been synchronised
 void resolveEvents(g2ocu_solver* s) {
@@ -476,7 +484,7 @@ int solvePcg(g2ocu_solver* s, const double* rhs) {
   PcgDev& pc = s->pcg;
   pc.lambda = s->st.doSchur ? 0.0 : s->lambda;
   const bool slab = s->world > 1 && s->st.doSchur;   // row-range SpMV per rank, q summed over the ranks; all vector recurrences replicated
-  { PhaseTimer pt(s, "pcg_setup");
+  { KernelTimer pt(s, "pcg_setup");
     launchBlockInverse(pc, s->stream, &s->launches);
     if (slab) { int rc = allreduceDev(s, pc.Minv, (int64_t)pc.nb * pc.P * pc.P, 0); if (rc) return rc; }   // every rank inverts the diagonal blocks it owns
     launchPcgInit(pc, rhs, s->cfg.pcg_tolerance, s->pcgResidual, s->cfg.pcg_absolute_tolerance, s->stream, &s->launches); }
@@ -489,11 +497,11 @@ int solvePcg(g2ocu_solver* s, const double* rhs) {
     const int want = issued == 0 ? std::min(std::max(kCheckEvery, s->lastPcgIterations - 1), 256) : kCheckEvery;
     const int batch = std::min(want, maxIter - issued);
     for (int k = 0; k < batch; ++k) {
-      { PhaseTimer pt(s, "pcg_spmv"); launchSpmv(pc, pc.d, pc.q, s->stream, &s->launches, issued + k > 0 && pcgSingleCtaTail(pc)); }
+      { KernelTimer pt(s, "pcg_spmv"); launchSpmv(pc, pc.d, pc.q, s->stream, &s->launches, issued + k > 0 && pcgSingleCtaTail(pc)); }
       const bool p2p = slab && s->p2pReady;
-      if (p2p) { PhaseTimer pt(s, "pcg_exchange"); launchP2pExchangeDot(pc, s->p2p, s->stream, &s->launches); }   // peer-memory all-reduce of q fused with d.q
-      else if (slab) { PhaseTimer pt(s, "pcg_exchange"); int rc = allreduceDev(s, pc.q, pc.n, 0); if (rc) return rc; }
-      { PhaseTimer pt(s, "pcg_vec"); launchPcgTail(pc, s->stream, &s->launches, p2p); }
+      if (p2p) { KernelTimer pt(s, "pcg_exchange"); launchP2pExchangeDot(pc, s->p2p, s->stream, &s->launches); }   // peer-memory all-reduce of q fused with d.q
+      else if (slab) { KernelTimer pt(s, "pcg_exchange"); int rc = allreduceDev(s, pc.q, pc.n, 0); if (rc) return rc; }
+      { KernelTimer pt(s, "pcg_vec"); launchPcgTail(pc, s->stream, &s->launches, p2p); }
     }
     issued += batch;
     CU(cudaMemcpyAsync(s->hostScal + 8, pc.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -539,11 +547,11 @@ int solveSystem(g2ocu_solver* s, int* solved) {
   { PhaseTimer pt(s, "schur");
     struct MarkCtx { g2ocu_solver* s; PhaseTimer* t; } mc{s, nullptr};
     KernelMarks marks; marks.ctx = &mc;
-    marks.begin = [](void* c, const char* name) { auto* m = (MarkCtx*)c; m->t = new PhaseTimer(m->s, name); };
+    marks.begin = [](void* c, const char* name) { auto* m = (MarkCtx*)c; m->t = m->s->kernelTiming ? new PhaseTimer(m->s, name) : nullptr; };
     marks.end = [](void* c) { auto* m = (MarkCtx*)c; delete m->t; m->t = nullptr; };
     launchSchur(s->schur, s->sys, s->hplLm.p, st.hplColPtr[st.lmEnd] - st.hplColPtr[st.lmBegin], s->lambda, s->rank == 0 ? s->lambda : 0.0, s->stream, &s->launches, &marks);
     if (s->world > 1) {
-      PhaseTimer pt2(s, "schur_exchange");
+      KernelTimer pt2(s, "schur_exchange");
       int rc = collectiveDev(s, s->S.p, s->slabBlocks * st.P * st.P, G2OCU_OP_REDUCE_SCATTER_SUM); if (rc) return rc;   // rank r keeps the sum of its block range
       rc = allreduceDev(s, s->bschur.p, (int64_t)s->bschur.n, 0); if (rc) return rc;
     } }
@@ -720,6 +728,7 @@ int g2ocu_set_property(g2ocu_solver* s, const char* name, double value) {
   else if (n == "pcgTolerance") s->cfg.pcg_tolerance = value;
   else if (n == "pcgMaxIterations") s->cfg.pcg_max_iterations = (int)value;
   else if (n == "pcgAbsoluteTolerance") s->cfg.pcg_absolute_tolerance = (int)value;
+  else if (n == "kernelTiming") s->kernelTiming = value != 0.0;
   else if (n == "linearSolver") {
     if ((int)value != G2OCU_LINEAR_PCG && (int)value != G2OCU_LINEAR_DENSE) return fail(s, G2OCU_E_INVALID, "unknown linear solver kind");
     s->cfg.linear_solver = (int)value;

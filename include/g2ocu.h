@@ -164,7 +164,7 @@ int g2ocu_create(const g2ocu_config* cfg, g2ocu_solver** out);
 void g2ocu_destroy(g2ocu_solver* s);
 
 int g2ocu_set_graph(g2ocu_solver* s, const g2ocu_graph* g);
-int g2ocu_set_property(g2ocu_solver* s, const char* name, double value);  /* "initialLambda", "maxTrialsAfterFailure" (levenberg.cpp:48-49); "pcgTolerance", "pcgMaxIterations", "pcgAbsoluteTolerance" (linear_solver_pcg.h:53-57); "linearSolver" = G2OCU_LINEAR_* (which LinearSolver the BlockSolver owns, block_solver.h:124) */
+int g2ocu_set_property(g2ocu_solver* s, const char* name, double value);  /* "initialLambda", "maxTrialsAfterFailure" (levenberg.cpp:48-49); "pcgTolerance", "pcgMaxIterations", "pcgAbsoluteTolerance" (linear_solver_pcg.h:53-57); "linearSolver" = G2OCU_LINEAR_* (which LinearSolver the BlockSolver owns, block_solver.h:124); "kernelTiming" != 0: g2ocu_phase_time also reports per-kernel phases (schur_tiles, pcg_spmv, ...) at the price of two event records per kernel */
 int g2ocu_set_shard(g2ocu_solver* s, int32_t rank, int32_t world, g2ocu_allreduce_fn fn, void* user);
 /* The same sharding with the collectives issued straight from the library through NCCL (no host callback per collective):
  * `nccl_library` is the path of libnccl.so.2 (dlopen'ed; the build has no link-time NCCL dependency), `unique_id` the 128 bytes of an
