@@ -96,6 +96,7 @@ struct g2ocu_solver {
   HostGraph g; bool hasGraph = false;
   Structure st; bool optInitialized = false, structureBuilt = false, algoInitialized = false;
   cudaStream_t stream = nullptr; bool ownStream = false, cudaReady = false;
+  SideStream side;                // second stream for independent kernels inside a phase (forked from / joined into `stream`)
   // LM properties / state (optimization_algorithm_levenberg.cpp:40-52)
   double userLambdaInit = 0.0; int maxTrialsAfterFailure = 10;
   double currentLambda = -1.0, tau = 1e-5, goodStepUpperScale = 2. / 3., goodStepLowerScale = 1. / 3., ni = 2.0;
@@ -140,6 +141,9 @@ struct g2ocu_solver {
     if (ncclComm && g_nccl.CommDestroy) g_nccl.CommDestroy(ncclComm);
     if (hostScal) cudaFreeHost(hostScal);
     if (hostInfo) cudaFreeHost(hostInfo);
+    if (side.fork) cudaEventDestroy(side.fork);
+    if (side.join) cudaEventDestroy(side.join);
+    if (side.stream) cudaStreamDestroy(side.stream);
     if (ownStream && stream) cudaStreamDestroy(stream);
   }
 };
@@ -157,6 +161,8 @@ int ensureCuda(g2ocu_solver* s) {
   if (s->cfg.device >= 0) CU(cudaSetDevice(s->cfg.device));
   if (s->cfg.stream) { s->stream = (cudaStream_t)s->cfg.stream; s->ownStream = false; }
   else { CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->ownStream = true; }
+  CU(cudaStreamCreateWithFlags(&s->side.stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&s->side.fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&s->side.join, cudaEventDisableTiming));
   CU(cudaMallocHost((void**)&s->hostScal, 64 * sizeof(double)));
   CU(cudaMallocHost((void**)&s->hostInfo, 16 * sizeof(int)));
   s->cudaReady = true;
@@ -549,7 +555,7 @@ int solveSystem(g2ocu_solver* s, int* solved) {
     KernelMarks marks; marks.ctx = &mc;
     marks.begin = [](void* c, const char* name) { auto* m = (MarkCtx*)c; m->t = m->s->kernelTiming ? new PhaseTimer(m->s, name) : nullptr; };
     marks.end = [](void* c) { auto* m = (MarkCtx*)c; delete m->t; m->t = nullptr; };
-    launchSchur(s->schur, s->sys, s->hplLm.p, st.hplColPtr[st.lmEnd] - st.hplColPtr[st.lmBegin], s->lambda, s->rank == 0 ? s->lambda : 0.0, s->stream, &s->launches, &marks);
+    launchSchur(s->schur, s->sys, s->hplLm.p, st.hplColPtr[st.lmEnd] - st.hplColPtr[st.lmBegin], s->lambda, s->rank == 0 ? s->lambda : 0.0, s->stream, &s->launches, s->kernelTiming ? &marks : nullptr, &s->side);
     if (s->world > 1) {
       KernelTimer pt2(s, "schur_exchange");
       int rc = collectiveDev(s, s->S.p, s->slabBlocks * st.P * st.P, G2OCU_OP_REDUCE_SCATTER_SUM); if (rc) return rc;   // rank r keeps the sum of its block range

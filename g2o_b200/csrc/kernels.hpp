@@ -75,7 +75,10 @@ static const int kTileMinTrack = 8;               // landmarks with at least thi
 void launchPairSlots(const SchurDev& d, cudaStream_t st, int64_t* launches);
 // optional per-kernel timing hooks: begin(ctx, name) / end(ctx) bracket one kernel (CUDA events on the launching stream in api.cu)
 struct KernelMarks { void* ctx = nullptr; void (*begin)(void*, const char*) = nullptr; void (*end)(void*) = nullptr; };
-void launchSchur(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, double lambda, double lambdaDiag, cudaStream_t st, int64_t* launches, const KernelMarks* marks = nullptr);
+// a second stream of the solver + two events: independent kernels of one phase are forked onto it and joined before the phase ends
+struct SideStream { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+void launchSchur(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, double lambda, double lambdaDiag, cudaStream_t st, int64_t* launches, const KernelMarks* marks = nullptr,
+                 const SideStream* side = nullptr);
 void launchBacksub(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, const double* xp, double* xl, cudaStream_t st, int64_t* launches);
 
 struct PcgDev {

@@ -675,7 +675,8 @@ struct MarkScope {
   MarkScope(const KernelMarks* m_, const char* name) : m(m_) { if (m && m->begin) m->begin(m->ctx, name); }
   ~MarkScope() { if (m && m->end) m->end(m->ctx); }
 };
-template <int P, int L> static void schurPL(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, double lambda, double lambdaDiag, cudaStream_t st, int64_t* launches, const KernelMarks* marks) {
+template <int P, int L> static void schurPL(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, double lambda, double lambdaDiag, cudaStream_t st, int64_t* launches, const KernelMarks* marks,
+                                            const SideStream* side) {
   constexpr int PP = P * P;
   cudaMemsetAsync(d.S, 0, sizeof(double) * (size_t)d.nnzS * PP, st);
   const int64_t tot = max((int64_t)d.nnzHpp * PP, (int64_t)d.numPoses * P);
@@ -684,14 +685,20 @@ template <int P, int L> static void schurPL(const SchurDev& d, const SystemDev& 
   *launches += 3;
   if (d.lmEnd > d.lmBegin) { dinv_kernel<P, L><<<(d.lmEnd - d.lmBegin + 255) / 256, 256, 0, st>>>(d, sys.Hll, sys.b, lambda); *launches += 1; }
   const bool mma = schurMmaSupported(P, L);
+  // The short-track kernel is bound by the L2 reduction rate, the coefficient pass by HBM and the tile kernel by the FP64 pipe: the first
+  // runs on the side stream next to the other two (all of them only add into S / b_schur).  Serial when per-kernel timing is on.
+  const bool forked = side && side->stream && d.nPairs > 0 && !(marks && marks->begin);
+  auto pairs = [&](cudaStream_t ps) {
+    if (d.nPairs <= 0) return;
+    const int64_t warpsNeeded = d.nPairs; const int nb = (int)((warpsNeeded + 7) / 8 < 148 * 8 * 4 ? (warpsNeeded + 7) / 8 : 148 * 8 * 4);
+    MarkScope ms(forked ? nullptr : marks, "schur_pairs");
+    schur_pairs_kernel<P, L><<<nb, 256, 0, ps>>>(d, sys.Hpl, hplLm);
+    *launches += 1;
+  };
+  if (forked) { cudaEventRecord(side->fork, st); cudaStreamWaitEvent(side->stream, side->fork, 0); pairs(side->stream); cudaEventRecord(side->join, side->stream); }
   if (mma) launchSchurMma(d, sys, hplLm, nBlocks, st, launches, marks);
   else if (nBlocks > 0) { MarkScope ms(marks, "schur_coeff"); coeff_kernel<P, L><<<(nBlocks + 127) / 128, 128, 0, st>>>(d, sys.Hpl, hplLm, nBlocks); *launches += 1; }
-  if (d.nPairs > 0) {
-    const int64_t warpsNeeded = d.nPairs; const int nb = (int)((warpsNeeded + 7) / 8 < 148 * 8 * 4 ? (warpsNeeded + 7) / 8 : 148 * 8 * 4);
-    MarkScope ms(marks, "schur_pairs");
-    schur_pairs_kernel<P, L><<<nb, 256, 0, st>>>(d, sys.Hpl, hplLm);
-    *launches += 1;
-  }
+  if (!forked) pairs(st);
   if (d.nTileChunks > 0 && !mma) {
     constexpr int kTileSmem = kTileBatch * (kTileCols * ((P * L) | 1) + kTileRows * P * L) * (int)sizeof(double);
     cudaFuncSetAttribute(schur_tile_kernel<P, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);   // per device, hence on every call
@@ -699,11 +706,13 @@ template <int P, int L> static void schurPL(const SchurDev& d, const SystemDev& 
     schur_tile_kernel<P, L><<<d.nTileChunks, kTileThreads, kTileSmem, st>>>(d, sys.Hpl);
     *launches += 1;
   }
+  if (forked) cudaStreamWaitEvent(st, side->join, 0);
 }
-void launchSchur(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, double lambda, double lambdaDiag, cudaStream_t st, int64_t* launches, const KernelMarks* marks) {
-  if (d.P == 9 && d.L == 3) schurPL<9, 3>(d, sys, hplLm, nBlocks, lambda, lambdaDiag, st, launches, marks);
-  else if (d.P == 6 && d.L == 3) schurPL<6, 3>(d, sys, hplLm, nBlocks, lambda, lambdaDiag, st, launches, marks);
-  else if (d.P == 3 && d.L == 2) schurPL<3, 2>(d, sys, hplLm, nBlocks, lambda, lambdaDiag, st, launches, marks);
+void launchSchur(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, double lambda, double lambdaDiag, cudaStream_t st, int64_t* launches, const KernelMarks* marks,
+                 const SideStream* side) {
+  if (d.P == 9 && d.L == 3) schurPL<9, 3>(d, sys, hplLm, nBlocks, lambda, lambdaDiag, st, launches, marks, side);
+  else if (d.P == 6 && d.L == 3) schurPL<6, 3>(d, sys, hplLm, nBlocks, lambda, lambdaDiag, st, launches, marks, side);
+  else if (d.P == 3 && d.L == 2) schurPL<3, 2>(d, sys, hplLm, nBlocks, lambda, lambdaDiag, st, launches, marks, side);
 }
 template <int P, int L> static void backsubPL(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, const double* xp, double* xl, cudaStream_t st, int64_t* launches) {
   cudaMemsetAsync(xl, 0, sizeof(double) * (size_t)d.numLandmarks * L, st);
