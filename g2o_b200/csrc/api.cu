@@ -642,9 +642,12 @@ int computeScale(g2ocu_solver* s, double lambda, double* out) {
 int solveLevenberg(g2ocu_solver* s, int iteration, int* result) {
   int rc;
   if (iteration == 0 && !s->structureBuilt) { rc = g2ocu_build_structure(s); if (rc) { *result = G2OCU_RESULT_FAIL; return rc; } }   // the map stays valid until the next initializeOptimization / set_graph
-  rc = computeErrors(s, nullptr, nullptr); if (rc) return rc;
+  // computeActiveErrors (levenberg.cpp:72): when the previous iteration ended with an accepted step, its last trial already evaluated
+  // exactly these estimates (the error kernels are deterministic, the result would be the same bits) - skip the pass and the sync
+  const bool fresh = s->errorsValid;
+  if (!fresh) { rc = computeErrors(s, nullptr, nullptr); if (rc) return rc; }
   rc = buildSystem(s); if (rc) return rc;          // enqueued behind the error kernels; one sync serves both
-  rc = finishErrors(s); if (rc) return rc;
+  if (!fresh) { rc = finishErrors(s); if (rc) return rc; }
   double currentChi = s->chi2Robust, tempChi = currentChi;
   if (iteration == 0) { rc = lambdaInit(s, &s->currentLambda); if (rc) return rc; s->ni = 2; }
   double rho = 0; int& qmax = s->levenbergIterations; qmax = 0;
