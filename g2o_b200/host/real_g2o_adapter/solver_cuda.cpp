@@ -53,8 +53,9 @@ void packIsometry(const Isometry3& T, std::vector<double>& out) {
 
 class OptimizationAlgorithmCuda : public OptimizationAlgorithm {
  public:
-  OptimizationAlgorithmCuda(int algorithm, int poseDim, int landmarkDim) : _algorithm(algorithm), _poseDim(poseDim), _landmarkDim(landmarkDim) {
-    g2ocu_config cfg; g2ocu_default_config(&cfg); g2ocu_create(&cfg, &_h);
+  OptimizationAlgorithmCuda(int algorithm, int poseDim, int landmarkDim, int linearSolver = G2OCU_LINEAR_PCG) : _algorithm(algorithm), _poseDim(poseDim), _landmarkDim(landmarkDim) {
+    g2ocu_config cfg; g2ocu_default_config(&cfg); cfg.linear_solver = linearSolver;   // LinearSolverPCG or LinearSolverDense semantics (solvers/pcg, solvers/dense)
+    g2ocu_create(&cfg, &_h);
     _userLambdaInit = _properties.makeProperty<Property<number_t>>("initialLambda", 0.);
     _maxTrialsAfterFailure = _properties.makeProperty<Property<int>>("maxTrialsAfterFailure", 10);
   }
@@ -161,7 +162,8 @@ class CudaSolverCreator : public AbstractOptimizationAlgorithmCreator {
   explicit CudaSolverCreator(const OptimizationAlgorithmProperty& p) : AbstractOptimizationAlgorithmCreator(p) {}
   OptimizationAlgorithm* construct() override {
     const std::string& n = property().name;
-    return new OptimizationAlgorithmCuda(n.substr(0, 2) == "lm" ? G2OCU_ALGORITHM_LM : G2OCU_ALGORITHM_GN, property().poseDim, property().landmarkDim);
+    return new OptimizationAlgorithmCuda(n.substr(0, 2) == "lm" ? G2OCU_ALGORITHM_LM : G2OCU_ALGORITHM_GN, property().poseDim, property().landmarkDim,
+                                         n.find("_dense") != std::string::npos ? G2OCU_LINEAR_DENSE : G2OCU_LINEAR_PCG);
   }
 };
 
@@ -174,5 +176,17 @@ G2O_REGISTER_OPTIMIZATION_ALGORITHM(gn_fix6_3_cuda, new CudaSolverCreator(Optimi
 G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_fix6_3_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("lm_fix6_3_cuda", "Levenberg: Schur + PCG on the GPU", "CUDA", true, 6, 3)));
 G2O_REGISTER_OPTIMIZATION_ALGORITHM(gn_fix7_3_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("gn_fix7_3_cuda", "Gauss-Newton: Schur + PCG on the GPU (sim3 types are rejected at init)", "CUDA", true, 7, 3)));
 G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_fix7_3_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("lm_fix7_3_cuda", "Levenberg: Schur + PCG on the GPU (sim3 types are rejected at init)", "CUDA", true, 7, 3)));
+G2O_REGISTER_OPTIMIZATION_ALGORITHM(gn_fix9_3_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("gn_fix9_3_cuda", "Gauss-Newton: Schur + PCG on the GPU (BAL cameras)", "CUDA", true, 9, 3)));
+G2O_REGISTER_OPTIMIZATION_ALGORITHM(gn_dense_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("gn_dense_cuda", "Gauss-Newton: dense FP64 Cholesky of the (reduced) system on the GPU", "CUDA", false, Eigen::Dynamic, Eigen::Dynamic)));
+G2O_REGISTER_OPTIMIZATION_ALGORITHM(gn_dense3_2_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("gn_dense3_2_cuda", "Gauss-Newton: dense FP64 Cholesky of the (reduced) system on the GPU", "CUDA", true, 3, 2)));
+G2O_REGISTER_OPTIMIZATION_ALGORITHM(gn_dense6_3_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("gn_dense6_3_cuda", "Gauss-Newton: dense FP64 Cholesky of the (reduced) system on the GPU", "CUDA", true, 6, 3)));
+G2O_REGISTER_OPTIMIZATION_ALGORITHM(gn_dense7_3_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("gn_dense7_3_cuda", "Gauss-Newton: dense FP64 Cholesky of the (reduced) system on the GPU", "CUDA", true, 7, 3)));
+G2O_REGISTER_OPTIMIZATION_ALGORITHM(gn_dense9_3_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("gn_dense9_3_cuda", "Gauss-Newton: dense FP64 Cholesky of the (reduced) system on the GPU", "CUDA", true, 9, 3)));
+G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_fix9_3_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("lm_fix9_3_cuda", "Levenberg: Schur + PCG on the GPU (BAL cameras)", "CUDA", true, 9, 3)));
+G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_dense_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("lm_dense_cuda", "Levenberg: dense FP64 Cholesky of the (reduced) system on the GPU", "CUDA", false, Eigen::Dynamic, Eigen::Dynamic)));
+G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_dense3_2_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("lm_dense3_2_cuda", "Levenberg: dense FP64 Cholesky of the (reduced) system on the GPU", "CUDA", true, 3, 2)));
+G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_dense6_3_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("lm_dense6_3_cuda", "Levenberg: dense FP64 Cholesky of the (reduced) system on the GPU", "CUDA", true, 6, 3)));
+G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_dense7_3_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("lm_dense7_3_cuda", "Levenberg: dense FP64 Cholesky of the (reduced) system on the GPU", "CUDA", true, 7, 3)));
+G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_dense9_3_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("lm_dense9_3_cuda", "Levenberg: dense FP64 Cholesky of the (reduced) system on the GPU", "CUDA", true, 9, 3)));
 
 }  // namespace g2o

@@ -73,3 +73,29 @@ def test_cli_matches_the_binding(tmp_path):
     s = CudaSolver(g, "lm_fix9_3_cuda", device=0); s.initialize_optimization()
     nb, st = s.optimize(5)
     assert n == nb and abs(rchi2 - st[-1]["chi2"]) <= 1e-7 * abs(st[-1]["chi2"])
+
+
+def test_expmap_and_camera_parameter_tags(tmp_path):
+    """VERTEX_SE3:EXPMAP files hold camera-to-world poses (types_six_dof_expmap.cpp:92-112): the reader inverts, the writer inverts back;
+    EDGE_PROJECT_XYZ2UV:EXPMAP refers to a PARAMS_CAMERAPARAMETERS line (types_six_dof_expmap.cpp:46,190-215)."""
+    a, b = tmp_path / "ba.g2o", tmp_path / "ba_resaved.g2o"
+    q = np.array([0.1, -0.2, 0.05, 0.0]); q[3] = np.sqrt(1 - np.sum(q[:3] ** 2))
+    a.write_text("PARAMS_CAMERAPARAMETERS 0 1000 320 240 0\n"
+                 f"VERTEX_SE3:EXPMAP 0 0.5 -0.25 0.125 {float(q[0])!r} {float(q[1])!r} {float(q[2])!r} {float(q[3])!r}\n"
+                 "VERTEX_SE3:EXPMAP 1 0 0 0 0 0 0 1\nFIX 1\n"
+                 "VERTEX_XYZ 2 0.3 0.1 4.0\n"
+                 "EDGE_PROJECT_XYZ2UV:EXPMAP 2 0 0 331.5 250.25 1 0 1\n"
+                 "EDGE_PROJECT_XYZ2UV:EXPMAP 2 1 0 395 265 2 0.5 2\n")
+    r = subprocess.run([CLI, "-summary", "-o", str(b), str(a)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    assert "vertices 3 edges 2 fixed 1 dimensions 3 6" in r.stdout
+    xa, xb = _numbers(str(a)), _numbers(str(b))
+    key = lambda rec: (rec[0], rec[1][:1])
+    assert sorted(t for t, _ in xa) == sorted(t for t, _ in xb)
+    for (ta, va), (tb, vb) in zip(sorted(xa, key=key), sorted(xb, key=key)):
+        assert ta == tb and np.allclose(va, vb, rtol=1e-13, atol=1e-13), (ta, va, vb)
+    # an edge that names an unknown parameter id is an error, not a silent default
+    bad = tmp_path / "bad.g2o"
+    bad.write_text("VERTEX_SE3:EXPMAP 0 0 0 0 0 0 0 1\nVERTEX_XYZ 1 0 0 1\nEDGE_PROJECT_XYZ2UV:EXPMAP 1 0 7 1 1 1 0 1\n")
+    r = subprocess.run([CLI, "-summary", str(bad)], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "PARAMS_CAMERAPARAMETERS" in r.stderr
