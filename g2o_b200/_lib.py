@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libg2ocu.so")
 _LIB = None
 
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_NUMERIC, E_COMM = 0, -1, -2, -3, -4, -5
-ALGORITHM_GN, ALGORITHM_LM = 0, 1
+ALGORITHM_GN, ALGORITHM_LM, ALGORITHM_DOGLEG = 0, 1, 2
 LINEAR_PCG, LINEAR_DENSE = 0, 1
 RESULT_OK, RESULT_TERMINATE, RESULT_FAIL = 1, 2, -1
 

@@ -29,7 +29,11 @@ SOLVER_NAMES = {
     "gn_dense6_3_cuda": ("gn", 6, 3, True), "lm_dense6_3_cuda": ("lm", 6, 3, True),
     "gn_dense7_3_cuda": ("gn", 7, 3, True), "lm_dense7_3_cuda": ("lm", 7, 3, True),
     "gn_dense9_3_cuda": ("gn", 9, 3, True), "lm_dense9_3_cuda": ("lm", 9, 3, True),
+    # Powell's dogleg is registered for the variable-size block solver only (solvers/csparse/solver_csparse.cpp:117, dl_var)
+    "dl_var_cuda": ("dl", -1, -1, False),
 }
+_ALGORITHM_CODES = {"gn": _lib.ALGORITHM_GN, "lm": _lib.ALGORITHM_LM, "dl": _lib.ALGORITHM_DOGLEG}
+DOGLEG_STEPS = {0: "Undefined", 1: "Descent", 2: "GN", 3: "Dogleg"}   # OptimizationAlgorithmDogleg::stepType2Str, dogleg.cpp:209-217
 
 
 class G2oCudaError(RuntimeError):
@@ -46,7 +50,7 @@ class CudaSolver:
         if solver_name not in SOLVER_NAMES:
             raise KeyError(f"unknown solver {solver_name!r}; registered: {sorted(SOLVER_NAMES)}")
         self.solver_name = solver_name
-        self.algorithm = _lib.ALGORITHM_LM if SOLVER_NAMES[solver_name][0] == "lm" else _lib.ALGORITHM_GN
+        self.algorithm = _ALGORITHM_CODES[SOLVER_NAMES[solver_name][0]]
         self._L = _lib.lib()
         cfg = _lib.Config()
         self._L.g2ocu_default_config(ctypes.byref(cfg))
@@ -172,6 +176,11 @@ class CudaSolver:
 
     def compute_scale(self, lam: float) -> float:
         v = ctypes.c_double(); self._ck(self._L.g2ocu_compute_scale(self._h, lam, ctypes.byref(v))); return v.value
+
+    def dogleg_state(self) -> dict:
+        """``trustRegion()``, ``lastStep()``, tries of the last iteration, damping factor, PD flag (optimization_algorithm_dogleg.h:64-68)."""
+        d = self.get_f64("dogleg")
+        return {"delta": float(d[0]), "last_step": int(d[1]), "tries": int(d[2]), "lambda": float(d[3]), "was_pd": bool(d[4])}
 
     def multiply_hessian(self, src) -> np.ndarray:
         src = np.ascontiguousarray(src, dtype=np.float64); dst = np.zeros_like(src)

@@ -1,6 +1,7 @@
 // C ABI of libg2ocu.so (include/g2ocu.h): handle, device memory, phase sequencing and the LM / GN control flow.
 // The control flow restates OptimizationAlgorithmLevenberg::solve (optimization_algorithm_levenberg.cpp:58-150),
-// OptimizationAlgorithmGaussNewton::solve (optimization_algorithm_gauss_newton.cpp:50-91) and
+// OptimizationAlgorithmGaussNewton::solve (optimization_algorithm_gauss_newton.cpp:50-91),
+// OptimizationAlgorithmDogleg::solve (optimization_algorithm_dogleg.cpp:56-197) and
 // SparseOptimizer::optimize (sparse_optimizer.cpp:374-439); all per-edge / per-block arithmetic runs in the kernels.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -101,6 +102,9 @@ struct g2ocu_solver {
   double userLambdaInit = 0.0; int maxTrialsAfterFailure = 10;
   double currentLambda = -1.0, tau = 1e-5, goodStepUpperScale = 2. / 3., goodStepLowerScale = 1. / 3., ni = 2.0;
   int levenbergIterations = 0;
+  // Dogleg properties / state (optimization_algorithm_dogleg.cpp:40-52, optimization_algorithm_dogleg.h:77-91)
+  double dlUserDeltaInit = 1e4, dlInitialLambda = 1e-7, dlLambdaFactor = 10., dlDelta = 1e4, dlCurrentLambda = 1e-7;
+  int dlMaxTrialsAfterFailure = 100, dlLastStep = 0, dlLastNumTries = 0; bool dlWasPD = true;
   // solver state
   double lambda = 0.0;            // damping currently "set" on the diagonals (0 after restoreDiagonal)
   double pcgResidual = -1.0;      // LinearSolverPCG::_residual, persists across solves until init()
@@ -119,6 +123,8 @@ struct g2ocu_solver {
   DVec<int> poseCounters, lmCounters;
   DVec<double> denseH; DVec<int> denseInfo; DVec<unsigned int> pcgTicket; int* hostInfo = nullptr;
   DVec<double> Hpp, Hll, Hpl, W, b, x, S, Dinv, dbv, bschur, Minv, vr, vd, vq, vs, scal, partial, partialDq, scratch, out2, dbg;
+  DVec<double> hsd, hdl, aux;                                        // Dogleg: steepest-descent step, final step, auxiliary vector (vectorSize each)
+  DVec<int32_t> mhRow, mhBegin, mhEnd, mhRowPtr, mhColIdx; bool mhReady = false;   // SpMV work items over the Hpp pattern (multiplyHessian in Schur mode)
   DVec<int32_t> hppDiag, hplColPtr, hplRowIdx, sRowPtr, sColIdx, sDiag, hppToS, pairSlot, pairEdgeI, pairEdgeJ, aRowPtr, aColIdx, aDiag, spRow, spBegin, spEnd, hplLm, tEntLm, tEntBI, tEntBJ, tChunkI, tChunkJ, tChunkB, tChunkE;
   DVec<uint32_t> tEntMJ; DVec<uint8_t> tEntMI;
   DVec<int64_t> off64;
@@ -257,7 +263,7 @@ int buildDevice(g2ocu_solver* s) {
   const Structure& st = s->st; const HostGraph& g = s->g;
   cudaStream_t stream = s->stream;
   for (auto* es : s->sets) delete es;
-  s->sets.clear();
+  s->sets.clear(); s->mhReady = false;
   int rc = uploadEstimates(s); if (rc) return rc;
   if (st.poseType == G2OCU_VERTEX_SE3) { CU(s->poseCounters.alloc(st.numPoseSlots)); CU(s->poseCounters.zero(stream)); }
   const int P = st.P, L = st.L;
@@ -325,7 +331,7 @@ int buildDevice(g2ocu_solver* s) {
     CU(cudaStreamSynchronize(stream));   // staging vectors die here
     maxScratch = std::max(maxScratch, (size_t)errorScratchDoubles(n));
   }
-  CU(s->scratch.alloc(maxScratch)); CU(s->out2.alloc(8));
+  CU(s->scratch.alloc(maxScratch)); CU(s->out2.alloc(16));   // [0,1] chi2, [4] max diagonal, [5,6] computeScale, [8..15] Dogleg dot products
   {
     auto contiguous = [&](const std::vector<int32_t>& verts, int vtype, int64_t& off) {
       if (verts.empty()) { off = 0; return true; }
@@ -570,11 +576,12 @@ int solveSystem(g2ocu_solver* s, int* solved) {
   return G2OCU_OK;
 }
 
-int applyUpdate(g2ocu_solver* s) {
+int applyUpdate(g2ocu_solver* s, const double* step = nullptr) {   // step: device vector of vectorSize doubles, default the solver's x
   PhaseTimer pt(s, "update");
   const Structure& st = s->st;
-  launchUpdate(st.poseType, s->poseEst.p, nullptr, s->poseCounters.p, s->x.p, st.numPoses, s->stream, &s->launches);
-  if (st.lmEnd > st.lmBegin) launchUpdate(st.lmType, s->lmEst.p + (size_t)st.lmBegin * vertexEstimateDim(st.lmType), nullptr, nullptr, s->x.p + st.sizePoses + (size_t)st.lmBegin * st.L, st.lmEnd - st.lmBegin, s->stream, &s->launches);
+  if (!step) step = s->x.p;
+  launchUpdate(st.poseType, s->poseEst.p, nullptr, s->poseCounters.p, step, st.numPoses, s->stream, &s->launches);
+  if (st.lmEnd > st.lmBegin) launchUpdate(st.lmType, s->lmEst.p + (size_t)st.lmBegin * vertexEstimateDim(st.lmType), nullptr, nullptr, step + st.sizePoses + (size_t)st.lmBegin * st.L, st.lmEnd - st.lmBegin, s->stream, &s->launches);
   s->errorsValid = false;
   CU(cudaGetLastError());
   return G2OCU_OK;
@@ -699,6 +706,128 @@ int solveGaussNewton(g2ocu_solver* s, int iteration, int* result) {
   return G2OCU_OK;
 }
 
+// BlockSolver::multiplyHessian (block_solver.h:146) = _Hpp->multiplySymmetricUpperTriangle (sparse_block_matrix.hpp:289-313) on device
+// vectors: dst[0, sizePoses) = (Hpp + lambda I) src[0, sizePoses).  The landmark part of the reference's dest is never touched.
+int multiplyHessianDev(g2ocu_solver* s, const double* src, double* dst) {
+  const Structure& st = s->st;
+  PcgDev pc = s->pcg; pc.A = s->Hpp.p; pc.lambda = s->lambda; pc.scal = nullptr;
+  if (st.doSchur) {                                                  // the PCG items cover Hschur: the Hpp pattern needs its own
+    if (!s->mhReady) {
+      std::vector<int32_t> hr, hb, he;
+      for (int i = 0; i < st.numPoses; ++i) { hr.push_back(i); hb.push_back(st.hppRowPtr[i]); he.push_back(st.hppRowPtr[i + 1]); }
+      CU(s->mhRow.upload(hr, s->stream)); CU(s->mhBegin.upload(hb, s->stream)); CU(s->mhEnd.upload(he, s->stream));
+      CU(s->mhRowPtr.upload(st.hppRowPtr, s->stream)); CU(s->mhColIdx.upload(st.hppColIdx, s->stream));
+      CU(cudaStreamSynchronize(s->stream));                          // host staging vectors go out of scope
+      s->mhReady = true;
+    }
+    pc.itemRow = s->mhRow.p; pc.itemBegin = s->mhBegin.p; pc.itemEnd = s->mhEnd.p; pc.nItems = st.numPoses;
+    pc.rowPtr = s->mhRowPtr.p; pc.colIdx = s->mhColIdx.p; pc.diag = s->hppDiag.p; pc.nnz = (int)st.hppColIdx.size();
+    pc.ownLo = 0; pc.ownHi = pc.nnz;
+  }
+  launchSpmv(pc, src, dst, s->stream, &s->launches);
+  CU(cudaGetLastError());
+  return G2OCU_OK;
+}
+
+// OptimizationAlgorithmDogleg::solve, optimization_algorithm_dogleg.cpp:56-197.  Dot products go through the fixed-order reduction of
+// computeScale (lambda = 0), results land in out2[8..15] / hostScal[16..23]; the vectors never leave the device.
+int solveDogleg(g2ocu_solver* s, int iteration, int* result) {
+  int rc;
+  *result = G2OCU_RESULT_FAIL;
+  if (s->world > 1) return fail(s, G2OCU_E_UNSUPPORTED, "the Dogleg algorithm is not available on a sharded solver");
+  if (iteration == 0 && !s->structureBuilt) { rc = g2ocu_build_structure(s); if (rc) return rc; }
+  const Structure& st = s->st;
+  const int64_t n = (int64_t)st.sizePoses + st.sizeLandmarks, np = st.sizePoses;
+  if (iteration == 0) { s->dlDelta = s->dlUserDeltaInit; s->dlCurrentLambda = s->dlInitialLambda; s->dlWasPD = true; }
+  CU(s->hsd.alloc((size_t)n)); CU(s->hdl.alloc((size_t)n)); CU(s->aux.alloc((size_t)n));
+  int slot = 0;
+  auto dot = [&](const double* u, const double* v, int64_t len) { launchScale(u, v, len, 0.0, s->scratch.p, s->out2.p + 8 + slot, s->stream, &s->launches); return slot++; };
+  // results of the dots enqueued since the last fetch -> hostScal[16 + k]; the copy is enqueued right behind them (computeErrors clears out2)
+  auto enqueueFetch = [&]() -> int { CU(cudaMemcpyAsync(s->hostScal + 16, s->out2.p + 8, 8 * sizeof(double), cudaMemcpyDeviceToHost, s->stream)); slot = 0; return G2OCU_OK; };
+  auto fetch = [&]() -> int { int r = enqueueFetch(); if (r) return r; return syncStream(s); };
+  const double* hs = s->hostScal + 16;
+
+  const bool fresh = s->errorsValid;
+  if (!fresh) { rc = computeErrors(s, nullptr, nullptr); if (rc) return rc; }
+  rc = buildSystem(s); if (rc) return rc;
+  // alpha = |b|^2 / (b^T Hpp b) (:97-101)
+  s->lambda = 0.0;
+  rc = multiplyHessianDev(s, s->b.p, s->aux.p); if (rc) return rc;
+  dot(s->b.p, s->b.p, n); dot(s->aux.p, s->b.p, np);
+  rc = enqueueFetch(); if (rc) return rc;
+  if (!fresh) { rc = finishErrors(s); if (rc) return rc; } else { rc = syncStream(s); if (rc) return rc; }
+  const double currentChi = s->chi2Robust;
+  const double bNormSquared = hs[0], alpha = bNormSquared / hs[1];
+  launchLincomb(s->hsd.p, s->b.p, nullptr, alpha, 0, n, s->stream, &s->launches);          // _hsd = alpha * b
+  dot(s->hsd.p, s->hsd.p, n);
+  rc = fetch(); if (rc) return rc;
+  const double hsdSqrNorm = hs[0], hsdNorm = std::sqrt(hsdSqrNorm);
+  double hgnNorm = -1.;
+  bool solvedGaussNewton = false, goodStep = false;
+  int& numTries = s->dlLastNumTries; numTries = 0;
+  do {
+    ++numTries;
+    if (!solvedGaussNewton) {
+      const double minLambda = 1e-12, maxLambda = 1e3;
+      solvedGaussNewton = true;
+      bool solverOk = false;
+      while (!solverOk) {
+        // damping only after the system was found not positive definite once (:117-135)
+        s->lambda = s->dlWasPD ? 0.0 : s->dlCurrentLambda;
+        int ok = 1;
+        rc = solveSystem(s, &ok); s->lambda = 0.0; if (rc) return rc;
+        solverOk = ok != 0;
+        s->dlWasPD = s->dlWasPD && solverOk;
+        if (!s->dlWasPD) {
+          if (solverOk) s->dlCurrentLambda = std::max(minLambda, s->dlCurrentLambda / (0.5 * s->dlLambdaFactor));
+          else { s->dlCurrentLambda *= s->dlLambdaFactor; if (s->dlCurrentLambda > maxLambda) { s->dlCurrentLambda = maxLambda; *result = G2OCU_RESULT_FAIL; return G2OCU_OK; } }
+        }
+      }
+      dot(s->x.p, s->x.p, n);
+      rc = fetch(); if (rc) return rc;
+      hgnNorm = std::sqrt(hs[0]);
+    }
+    const double delta = s->dlDelta;
+    if (hgnNorm < delta) {
+      CU(cudaMemcpyAsync(s->hdl.p, s->x.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+      s->dlLastStep = G2OCU_DOGLEG_STEP_GN;
+    } else if (hsdNorm > delta) {
+      launchLincomb(s->hdl.p, s->hsd.p, nullptr, delta / hsdNorm, 0, n, s->stream, &s->launches);
+      s->dlLastStep = G2OCU_DOGLEG_STEP_SD;
+    } else {
+      launchLincomb(s->aux.p, s->hsd.p, s->x.p, 0.0, 1, n, s->stream, &s->launches);       // _auxVector = hgn - _hsd
+      dot(s->hsd.p, s->aux.p, n); dot(s->aux.p, s->aux.p, n);
+      rc = fetch(); if (rc) return rc;
+      const double c = hs[0], bmaSquaredNorm = hs[1];
+      double beta;
+      if (c <= 0.) beta = (-c + std::sqrt(c * c + bmaSquaredNorm * (delta * delta - hsdSqrNorm))) / bmaSquaredNorm;
+      else beta = (delta * delta - hsdSqrNorm) / (c + std::sqrt(c * c + bmaSquaredNorm * (delta * delta - hsdSqrNorm)));
+      launchLincomb(s->hdl.p, s->hsd.p, s->x.p, beta, 2, n, s->stream, &s->launches);      // _hdl = _hsd + beta * (hgn - _hsd)
+      s->dlLastStep = G2OCU_DOGLEG_STEP_DL;
+    }
+    // linear gain = -(Hpp hdl).hdl + 2 b.hdl (:165-168)
+    rc = multiplyHessianDev(s, s->hdl.p, s->aux.p); if (rc) return rc;
+    dot(s->aux.p, s->hdl.p, np); dot(s->b.p, s->hdl.p, n); dot(s->hdl.p, s->hdl.p, n);
+    rc = enqueueFetch(); if (rc) return rc;
+    rc = pushEstimates(s); if (rc) return rc;
+    rc = applyUpdate(s, s->hdl.p); if (rc) return rc;
+    rc = computeErrors(s, nullptr, nullptr); if (rc) return rc;
+    rc = finishErrors(s); if (rc) return rc;                 // one sync serves the dot products and the new chi2
+    double linearGain = -1 * hs[0] + 2 * hs[1];
+    const double hdlNorm = std::sqrt(hs[2]);
+    const double newChi = s->chi2Robust;
+    const double nonLinearGain = currentChi - newChi;
+    if (std::fabs(linearGain) < 1e-12) linearGain = 1e-12;
+    const double rho = nonLinearGain / linearGain;
+    if (rho > 0) { rc = popEstimates(s, false); if (rc) return rc; goodStep = true; }
+    else { rc = popEstimates(s, true); if (rc) return rc; }
+    if (rho > 0.75) s->dlDelta = std::max(s->dlDelta, 3 * hdlNorm);
+    else if (rho < 0.25) s->dlDelta *= 0.5;
+  } while (!goodStep && numTries < s->dlMaxTrialsAfterFailure);
+  *result = (numTries == s->dlMaxTrialsAfterFailure || !goodStep) ? G2OCU_RESULT_TERMINATE : G2OCU_RESULT_OK;
+  return G2OCU_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -734,6 +863,10 @@ int g2ocu_set_property(g2ocu_solver* s, const char* name, double value) {
   const std::string n(name);
   if (n == "initialLambda") s->userLambdaInit = value;
   else if (n == "maxTrialsAfterFailure") s->maxTrialsAfterFailure = (int)value;
+  else if (n == "doglegInitialDelta") s->dlUserDeltaInit = value;                   // OptimizationAlgorithmDogleg "initialDelta" (dogleg.cpp:44)
+  else if (n == "doglegMaxTrialsAfterFailure") s->dlMaxTrialsAfterFailure = (int)value;   // its own "maxTrialsAfterFailure", default 100 (:45)
+  else if (n == "doglegInitialLambda") s->dlInitialLambda = value;                  // its own "initialLambda", default 1e-7 (:46)
+  else if (n == "doglegLambdaFactor") s->dlLambdaFactor = value;                    // "lambdaFactor" (:47)
   else if (n == "pcgTolerance") s->cfg.pcg_tolerance = value;
   else if (n == "pcgMaxIterations") s->cfg.pcg_max_iterations = (int)value;
   else if (n == "pcgAbsoluteTolerance") s->cfg.pcg_absolute_tolerance = (int)value;
@@ -895,22 +1028,8 @@ int g2ocu_multiply_hessian(g2ocu_solver* s, double* hostDest, const double* host
   int rc = requireBuilt(s); if (rc) return rc;
   if (!hostDest || !hostSrc) return fail(s, G2OCU_E_INVALID, "null vector");
   const int n = s->st.sizePoses;                                     // BlockSolverBase::multiplyHessian works on Hpp (block_solver.h:87-95)
-  PcgDev pc = s->pcg; pc.A = s->Hpp.p; pc.lambda = s->lambda; pc.scal = nullptr;
-  DVec<int32_t> r, bgn, en;
-  if (s->st.doSchur) {                                               // SpMV items over the Hpp pattern
-    std::vector<int32_t> hr, hb, he;
-    for (int i = 0; i < s->st.numPoses; ++i) { hr.push_back(i); hb.push_back(s->st.hppRowPtr[i]); he.push_back(s->st.hppRowPtr[i + 1]); }
-    DVec<int32_t> rp, ci;
-    CU(r.upload(hr, s->stream)); CU(bgn.upload(hb, s->stream)); CU(en.upload(he, s->stream));
-    CU(rp.upload(s->st.hppRowPtr, s->stream)); CU(ci.upload(s->st.hppColIdx, s->stream));
-    pc.itemRow = r.p; pc.itemBegin = bgn.p; pc.itemEnd = en.p; pc.nItems = (int)hr.size(); pc.rowPtr = rp.p; pc.colIdx = ci.p; pc.diag = s->hppDiag.p;
-    CU(cudaMemcpyAsync(s->vd.p, hostSrc, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    launchSpmv(pc, s->vd.p, s->vq.p, s->stream, &s->launches);
-    CU(cudaMemcpyAsync(hostDest, s->vq.p, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    return syncStream(s);
-  }
   CU(cudaMemcpyAsync(s->vd.p, hostSrc, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-  launchSpmv(pc, s->vd.p, s->vq.p, s->stream, &s->launches);
+  rc = multiplyHessianDev(s, s->vd.p, s->vq.p); if (rc) return rc;
   CU(cudaMemcpyAsync(hostDest, s->vq.p, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   return syncStream(s);
 }
@@ -922,14 +1041,15 @@ int g2ocu_solver_iteration(g2ocu_solver* s, int32_t algorithm, int32_t iteration
   const double t0 = wallNow();
   const double e0 = phaseSeconds(s, "errors"), b0 = phaseSeconds(s, "build"), sc0 = phaseSeconds(s, "schur"), l0 = phaseSeconds(s, "linear_solver"), u0 = phaseSeconds(s, "update"), bs0 = phaseSeconds(s, "backsub");
   int result = G2OCU_RESULT_FAIL;
-  int rc = (algorithm == G2OCU_ALGORITHM_LM) ? solveLevenberg(s, iteration, &result) : solveGaussNewton(s, iteration, &result);
+  if (algorithm != G2OCU_ALGORITHM_GN && algorithm != G2OCU_ALGORITHM_LM && algorithm != G2OCU_ALGORITHM_DOGLEG) return fail(s, G2OCU_E_INVALID, "unknown algorithm code");
+  int rc = algorithm == G2OCU_ALGORITHM_LM ? solveLevenberg(s, iteration, &result) : algorithm == G2OCU_ALGORITHM_DOGLEG ? solveDogleg(s, iteration, &result) : solveGaussNewton(s, iteration, &result);
   if (rc) return rc;
   if (stats) {
     // SparseOptimizer::optimize computes the errors again for the statistics (sparse_optimizer.cpp:411-417)
     double chi2 = 0; rc = g2ocu_active_robust_chi2(s, &chi2); if (rc) return rc;
     std::memset(stats, 0, sizeof(*stats));
     stats->iteration = iteration; stats->result = result; stats->levenberg_iterations = algorithm == G2OCU_ALGORITHM_LM ? s->levenbergIterations : 0;
-    stats->iterations_linear_solver = s->lastPcgIterations; stats->chi2 = chi2; stats->lambda = s->currentLambda;
+    stats->iterations_linear_solver = s->lastPcgIterations; stats->chi2 = chi2; stats->lambda = algorithm == G2OCU_ALGORITHM_DOGLEG ? s->dlCurrentLambda : s->currentLambda;
     stats->time_residuals = phaseSeconds(s, "errors") - e0; stats->time_quadratic_form = phaseSeconds(s, "build") - b0;
     stats->time_schur_complement = phaseSeconds(s, "schur") - sc0; stats->time_linear_solver = phaseSeconds(s, "linear_solver") - l0;
     stats->time_linear_solution = stats->time_schur_complement + stats->time_linear_solver + (phaseSeconds(s, "backsub") - bs0);
@@ -1074,6 +1194,11 @@ int64_t g2ocu_get_f64(g2ocu_solver* s, const char* name, double* out, int64_t ca
   }
   if (n == "estimates") { if (out && cap >= (int64_t)s->g.vEst.size()) { rc = g2ocu_get_estimates(s, out); if (rc) return rc; } return (int64_t)s->g.vEst.size(); }
   if (n == "lambda") { if (out && cap >= 1) out[0] = s->currentLambda; return 1; }
+  if (n == "dogleg") {   // trustRegion(), lastStep() (optimization_algorithm_dogleg.h:66-68), tries of the last iteration, damping, positive-definite flag
+    const double v[5] = {s->dlDelta, (double)s->dlLastStep, (double)s->dlLastNumTries, s->dlCurrentLambda, s->dlWasPD ? 1.0 : 0.0};
+    if (out) std::memcpy(out, v, sizeof(double) * (size_t)std::min<int64_t>(cap, 5));
+    return 5;
+  }
   return fail(s, G2OCU_E_INVALID, "unknown double array " + n);
 }
 

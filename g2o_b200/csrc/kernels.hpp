@@ -114,7 +114,9 @@ bool pcgSingleCtaTail(const PcgDev& p);   // launchPcgTail zeroes q itself (smal
 
 void launchExtractPoseDiag(const SystemDev& sys, double* out, cudaStream_t st, int64_t* launches);
 void launchMaxDiag(const SystemDev& sys, const double* poseDiag, int lmBegin, int lmEnd, double* scratch /* >= 148 doubles */, double* out, cudaStream_t st, int64_t* launches);
-void launchScale(const double* x, const double* b, int64_t n, double lambda, double* scratch, double* out, cudaStream_t st, int64_t* launches);
+void launchScale(const double* x, const double* b, int64_t n, double lambda, double* scratch, double* out, cudaStream_t st, int64_t* launches);   // out[0] = sum_j x_j (lambda x_j + b_j); with lambda = 0 a fixed-order dot product
+// Dogleg step vectors: mode 0: out = a u; mode 1: out = v - u; mode 2: out = u + a (v - u)
+void launchLincomb(double* out, const double* u, const double* v, double a, int mode, int64_t n, cudaStream_t st, int64_t* launches);
 
 // dense FP64 Cholesky path (kernels_dense.cu)
 void launchDenseAssemble(const PcgDev& p, double* H, cudaStream_t st, int64_t* launches);      // upper blocks -> dense lower-filled n x n

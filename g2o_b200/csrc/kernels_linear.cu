@@ -661,9 +661,23 @@ __global__ void __launch_bounds__(256) final_sum_kernel(const double* partial, i
   if (threadIdx.x == 0) out[0] = r;
 }
 
+// Dogleg step vectors (optimization_algorithm_dogleg.cpp:102,141-157): mode 0: out = a u; mode 1: out = v - u; mode 2: out = u + a (v - u)
+__global__ void __launch_bounds__(256) lincomb_kernel(double* out, const double* u, const double* v, double a, int mode, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const double ui = u[i];
+    out[i] = mode == 0 ? a * ui : (mode == 1 ? v[i] - ui : ui + a * (v[i] - ui));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // launch wrappers
 // ------------------------------------------------------------------------------------------------
+void launchLincomb(double* out, const double* u, const double* v, double a, int mode, int64_t n, cudaStream_t st, int64_t* launches) {
+  if (n <= 0) return;
+  int64_t nb64 = (n + 255) / 256; const int nb = (int)(nb64 < 148 * 8 ? nb64 : 148 * 8);
+  lincomb_kernel<<<nb, 256, 0, st>>>(out, u, v, a, mode, n);
+  *launches += 1;
+}
 void launchPairSlots(const SchurDev& d, cudaStream_t st, int64_t* launches) {
   if (d.nPairs == 0) return;
   pair_slot_kernel<<<(unsigned)((d.nPairs + 255) / 256), 256, 0, st>>>(d);

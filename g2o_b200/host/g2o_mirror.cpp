@@ -200,6 +200,31 @@ void OptimizationAlgorithmLevenberg::printVerbose(std::ostream& os) const {
   os << "\t schur= " << _solver->schur() << "\t lambda= " << std::fixed << _currentLambda << "\t levenbergIter= " << _levenbergIterations;
 }
 
+OptimizationAlgorithm::SolverResult OptimizationAlgorithmDogleg::solve(int iteration, bool online) {
+  const SolverResult r = OptimizationAlgorithmWithHessianCuda::solve(iteration, online);
+  double d[5] = {_delta, (double)_lastStep, (double)_lastNumTries, _currentLambda, 1.0};
+  if (g2ocu_get_f64(_optimizer->handle(), "dogleg", d, 5) == 5) { _delta = d[0]; _lastStep = (int)d[1]; _lastNumTries = (int)d[2]; _currentLambda = d[3]; _wasPDInAllIterations = d[4] != 0.0; }
+  return r;
+}
+const char* OptimizationAlgorithmDogleg::stepType2Str(int stepType) {
+  switch (stepType) { case STEP_SD: return "Descent"; case STEP_GN: return "GN"; case STEP_DL: return "Dogleg"; default: return "Undefined"; }
+}
+void OptimizationAlgorithmDogleg::printVerbose(std::ostream& os) const {
+  os << "\t Delta= " << _delta << "\t step= " << stepType2Str(_lastStep) << "\t tries= " << _lastNumTries;
+  if (!_wasPDInAllIterations) os << "\t lambda= " << _currentLambda;
+}
+bool OptimizationAlgorithmDogleg::updatePropertiesFromString(const std::string& s) {   // the Dogleg property names map onto the backend's dogleg* properties
+  static const std::map<std::string, std::string> names{{"initialDelta", "doglegInitialDelta"}, {"maxTrialsAfterFailure", "doglegMaxTrialsAfterFailure"},
+                                                        {"initialLambda", "doglegInitialLambda"}, {"lambdaFactor", "doglegLambdaFactor"}};
+  std::stringstream ss(s), out; std::string kv; bool first = true;
+  while (std::getline(ss, kv, ',')) {
+    const size_t eq = kv.find('=');
+    if (eq != std::string::npos) { auto it = names.find(kv.substr(0, eq)); if (it != names.end()) kv = it->second + kv.substr(eq); }
+    out << (first ? "" : ",") << kv; first = false;
+  }
+  return OptimizationAlgorithmWithHessianCuda::updatePropertiesFromString(out.str());
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 OptimizationAlgorithmFactory* OptimizationAlgorithmFactory::instance() { static OptimizationAlgorithmFactory f; return &f; }
 void OptimizationAlgorithmFactory::registerSolver(const std::shared_ptr<AbstractOptimizationAlgorithmCreator>& c) {

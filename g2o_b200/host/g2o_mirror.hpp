@@ -297,6 +297,22 @@ class OptimizationAlgorithmGaussNewton : public OptimizationAlgorithmWithHessian
   void printVerbose(std::ostream& os) const override { os << "\t schur= " << _solver->schur(); }
 };
 
+// core/optimization_algorithm_dogleg.h:43-97: Powell's dogleg; the trial loop, the step vectors and their dot products stay on the device
+class OptimizationAlgorithmDogleg : public OptimizationAlgorithmWithHessianCuda {
+ public:
+  enum { STEP_UNDEFINED, STEP_SD, STEP_GN, STEP_DL };
+  explicit OptimizationAlgorithmDogleg(std::unique_ptr<Solver> solver) : OptimizationAlgorithmWithHessianCuda(std::move(solver), G2OCU_ALGORITHM_DOGLEG) {}
+  SolverResult solve(int iteration, bool online = false) override;
+  int lastStep() const { return _lastStep; }                           // :64
+  number_t trustRegion() const { return _delta; }                      // :66
+  static const char* stepType2Str(int stepType);                       // optimization_algorithm_dogleg.cpp:209-217
+  void printVerbose(std::ostream& os) const override;                  // :199-207
+  // properties "initialDelta", "maxTrialsAfterFailure", "initialLambda", "lambdaFactor" (:44-47)
+  bool updatePropertiesFromString(const std::string& s) override;
+ private:
+  number_t _delta = 1e4; int _lastStep = STEP_UNDEFINED, _lastNumTries = 0; bool _wasPDInAllIterations = true;
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // core/optimization_algorithm_factory.h:52-137
 class AbstractOptimizationAlgorithmCreator {

@@ -57,20 +57,31 @@ class OptimizationAlgorithmCuda : public OptimizationAlgorithm {
     g2ocu_config cfg; g2ocu_default_config(&cfg); cfg.linear_solver = linearSolver;   // LinearSolverPCG or LinearSolverDense semantics (solvers/pcg, solvers/dense)
     g2ocu_create(&cfg, &_h);
     _userLambdaInit = _properties.makeProperty<Property<number_t>>("initialLambda", 0.);
-    _maxTrialsAfterFailure = _properties.makeProperty<Property<int>>("maxTrialsAfterFailure", 10);
+    _maxTrialsAfterFailure = _properties.makeProperty<Property<int>>("maxTrialsAfterFailure", algorithm == G2OCU_ALGORITHM_DOGLEG ? 100 : 10);
+    if (algorithm == G2OCU_ALGORITHM_DOGLEG) {   // OptimizationAlgorithmDogleg's own defaults (optimization_algorithm_dogleg.cpp:44-47)
+      _userLambdaInit->setValue(1e-7);
+      _userDeltaInit = _properties.makeProperty<Property<number_t>>("initialDelta", (number_t)1e4);
+      _lambdaFactor = _properties.makeProperty<Property<number_t>>("lambdaFactor", 10.);
+    }
   }
   ~OptimizationAlgorithmCuda() { g2ocu_destroy(_h); }
 
   bool init(bool online = false) override {
     if (!packAndUpload()) return false;                       // unsupported types are rejected here
-    g2ocu_set_property(_h, "initialLambda", _userLambdaInit->value());
-    g2ocu_set_property(_h, "maxTrialsAfterFailure", _maxTrialsAfterFailure->value());
+    if (_algorithm == G2OCU_ALGORITHM_DOGLEG) {
+      g2ocu_set_property(_h, "doglegInitialDelta", _userDeltaInit->value()); g2ocu_set_property(_h, "doglegLambdaFactor", _lambdaFactor->value());
+      g2ocu_set_property(_h, "doglegInitialLambda", _userLambdaInit->value()); g2ocu_set_property(_h, "doglegMaxTrialsAfterFailure", _maxTrialsAfterFailure->value());
+    } else {
+      g2ocu_set_property(_h, "initialLambda", _userLambdaInit->value());
+      g2ocu_set_property(_h, "maxTrialsAfterFailure", _maxTrialsAfterFailure->value());
+    }
     return ok(g2ocu_initialize_optimization(_h, 0)) && ok(g2ocu_init(_h, online));
   }
   SolverResult solve(int iteration, bool /*online*/ = false) override {
     g2ocu_iteration_stats st;
     if (!ok(g2ocu_solver_iteration(_h, _algorithm, iteration, &st))) return Fail;
     _lambda = st.lambda; _levenbergIterations = st.levenberg_iterations;
+    if (_algorithm == G2OCU_ALGORITHM_DOGLEG) g2ocu_get_f64(_h, "dogleg", _dogleg, 5);   // trust region, step type, tries, damping, PD flag
     writeBack();
     if (G2OBatchStatistics* gs = G2OBatchStatistics::globalStats()) {
       gs->timeResiduals = st.time_residuals; gs->timeQuadraticForm = st.time_quadratic_form; gs->timeSchurComplement = st.time_schur_complement;
@@ -84,6 +95,12 @@ class OptimizationAlgorithmCuda : public OptimizationAlgorithm {
   bool computeMarginals(SparseBlockMatrix<MatrixX>&, const std::vector<std::pair<int, int>>&) override { return false; }   // out of scope
   bool updateStructure(const std::vector<HyperGraph::Vertex*>&, const HyperGraph::EdgeSet&) override { return false; }    // online mode: out of scope
   void printVerbose(std::ostream& os) const override {
+    if (_algorithm == G2OCU_ALGORITHM_DOGLEG) {   // optimization_algorithm_dogleg.cpp:199-217
+      static const char* const step[] = {"Undefined", "Descent", "GN", "Dogleg"};
+      os << "\t Delta= " << _dogleg[0] << "\t step= " << step[(int)_dogleg[1] & 3] << "\t tries= " << (int)_dogleg[2];
+      if (_dogleg[4] == 0.0) os << "\t lambda= " << _dogleg[3];
+      return;
+    }
     os << "\t lambda= " << FIXED(_lambda) << "\t levenbergIter= " << _levenbergIterations;
   }
 
@@ -152,6 +169,7 @@ class OptimizationAlgorithmCuda : public OptimizationAlgorithm {
   }
 
   g2ocu_solver* _h = nullptr; int _algorithm, _poseDim, _landmarkDim;
+  Property<number_t>* _userDeltaInit = nullptr; Property<number_t>* _lambdaFactor = nullptr; double _dogleg[5] = {1e4, 0, 0, 1e-7, 1};
   std::vector<OptimizableGraph::Vertex*> _vertices; size_t _estimateSize = 0;
   Property<number_t>* _userLambdaInit; Property<int>* _maxTrialsAfterFailure;
   number_t _lambda = -1; int _levenbergIterations = 0;
@@ -162,7 +180,7 @@ class CudaSolverCreator : public AbstractOptimizationAlgorithmCreator {
   explicit CudaSolverCreator(const OptimizationAlgorithmProperty& p) : AbstractOptimizationAlgorithmCreator(p) {}
   OptimizationAlgorithm* construct() override {
     const std::string& n = property().name;
-    return new OptimizationAlgorithmCuda(n.substr(0, 2) == "lm" ? G2OCU_ALGORITHM_LM : G2OCU_ALGORITHM_GN, property().poseDim, property().landmarkDim,
+    return new OptimizationAlgorithmCuda(n.substr(0, 2) == "lm" ? G2OCU_ALGORITHM_LM : n.substr(0, 2) == "dl" ? G2OCU_ALGORITHM_DOGLEG : G2OCU_ALGORITHM_GN, property().poseDim, property().landmarkDim,
                                          n.find("_dense") != std::string::npos ? G2OCU_LINEAR_DENSE : G2OCU_LINEAR_PCG);
   }
 };
@@ -188,5 +206,6 @@ G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_dense3_2_cuda, new CudaSolverCreator(Opti
 G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_dense6_3_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("lm_dense6_3_cuda", "Levenberg: dense FP64 Cholesky of the (reduced) system on the GPU", "CUDA", true, 6, 3)));
 G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_dense7_3_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("lm_dense7_3_cuda", "Levenberg: dense FP64 Cholesky of the (reduced) system on the GPU", "CUDA", true, 7, 3)));
 G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_dense9_3_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("lm_dense9_3_cuda", "Levenberg: dense FP64 Cholesky of the (reduced) system on the GPU", "CUDA", true, 9, 3)));
+G2O_REGISTER_OPTIMIZATION_ALGORITHM(dl_var_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("dl_var_cuda", "Dogleg: block-Jacobi PCG on the GPU (variable blocksize)", "CUDA", false, Eigen::Dynamic, Eigen::Dynamic)));
 
 }  // namespace g2o

@@ -26,6 +26,7 @@ OptimizationAlgorithm* createSolver(const std::string& fullSolverName) {
   const std::string methodName = fullSolverName.substr(0, 2);
   if (methodName == "gn") return new OptimizationAlgorithmGaussNewton(it->second());
   if (methodName == "lm") return new OptimizationAlgorithmLevenberg(it->second());
+  if (methodName == "dl") return new OptimizationAlgorithmDogleg(it->second());
   return nullptr;
 }
 
@@ -58,5 +59,6 @@ G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_dense3_2_cuda, new CudaSolverCreator(Opti
 G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_dense6_3_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("lm_dense6_3_cuda", "Levenberg: dense FP64 Cholesky of the (reduced) system on the GPU (fixed blocksize)", "CUDA", true, 6, 3)))
 G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_dense7_3_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("lm_dense7_3_cuda", "Levenberg: dense FP64 Cholesky of the (reduced) system on the GPU (fixed blocksize; no sim3 edge is supported: rejected at init)", "CUDA", true, 7, 3)))
 G2O_REGISTER_OPTIMIZATION_ALGORITHM(lm_dense9_3_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("lm_dense9_3_cuda", "Levenberg: dense FP64 Cholesky of the (reduced) system on the GPU (BAL cameras)", "CUDA", true, 9, 3)))
+G2O_REGISTER_OPTIMIZATION_ALGORITHM(dl_var_cuda, new CudaSolverCreator(OptimizationAlgorithmProperty("dl_var_cuda", "Dogleg: block-Jacobi PCG on the GPU (variable blocksize)", "CUDA", false, -1, -1)))
 
 }  // namespace g2o

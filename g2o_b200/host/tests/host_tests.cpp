@@ -24,7 +24,7 @@ static void testFactory() {
   std::stringstream ss; OptimizationAlgorithmFactory::instance()->listSolvers(ss);
   const std::string s = ss.str();
   for (const char* n : {"gn_var_cuda", "lm_var_cuda", "gn_fix3_2_cuda", "lm_fix3_2_cuda", "gn_fix6_3_cuda", "lm_fix6_3_cuda", "gn_fix7_3_cuda", "lm_fix7_3_cuda", "lm_fix9_3_cuda",
-                        "gn_dense_cuda", "lm_dense_cuda", "lm_dense3_2_cuda", "lm_dense6_3_cuda", "lm_dense7_3_cuda", "lm_dense9_3_cuda"})
+                        "gn_dense_cuda", "lm_dense_cuda", "lm_dense3_2_cuda", "lm_dense6_3_cuda", "lm_dense7_3_cuda", "lm_dense9_3_cuda", "dl_var_cuda"})
     EXPECT(s.find(n) != std::string::npos);
   OptimizationAlgorithmProperty p;
   OptimizationAlgorithm* a = OptimizationAlgorithmFactory::instance()->construct("lm_fix6_3_cuda", p);
@@ -65,6 +65,10 @@ static void edgeSE3Problem(bool rotation, const char* solver = "lm_var_cuda") {
   const double tn = std::sqrt(est[9] * est[9] + est[10] * est[10] + est[11] * est[11]);
   const double dn = std::sqrt((est[0] - 1) * (est[0] - 1) + (est[4] - 1) * (est[4] - 1) + (est[8] - 1) * (est[8] - 1));
   EXPECT(tn < 1e-9); EXPECT(dn < 1e-9);
+  if (auto* dl = dynamic_cast<OptimizationAlgorithmDogleg*>(optimizer.algorithm())) {   // the last iteration ends with rejected steps only: trust region shrunk
+    EXPECT(dl->lastStep() == OptimizationAlgorithmDogleg::STEP_GN); EXPECT(dl->trustRegion() > 0 && dl->trustRegion() < 1e4);
+    std::stringstream ss; dl->printVerbose(ss); EXPECT(ss.str().find("step= GN") != std::string::npos);
+  }
 }
 
 static void testClearAndRedo() {
@@ -152,6 +156,8 @@ int main() {
   edgeSE3Problem(true);
   edgeSE3Problem(false, "lm_dense_cuda");   // the same two problems through BlockSolverX + LinearSolverDense (device Cholesky)
   edgeSE3Problem(true, "lm_dense_cuda");
+  edgeSE3Problem(false, "dl_var_cuda");     // and through Powell's dogleg (optimization_algorithm_dogleg.cpp)
+  edgeSE3Problem(true, "dl_var_cuda");
   testClearAndRedo();
   testBundleAdjustment();
   if (g_failures) { std::printf("HOST_TESTS_FAILED %d\n", g_failures); return 1; }

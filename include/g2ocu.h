@@ -19,7 +19,8 @@
  *   Solver::x / b / vectorSize                core/solver.h:94-103        g2ocu_get_f64("x"|"b") / g2ocu_vector_size
  *   SparseOptimizer::update                   sparse_optimizer.cpp:441    g2ocu_update
  *   SparseOptimizer::push/pop/discardTop      sparse_optimizer.cpp:624    g2ocu_push / g2ocu_pop / g2ocu_discard_top
- *   OptimizationAlgorithm::solve(iteration)   optimization_algorithm.h:70 g2ocu_solver_iteration
+ *   OptimizationAlgorithm::solve(iteration)   optimization_algorithm.h:70 g2ocu_solver_iteration (G2OCU_ALGORITHM_GN / _LM / _DOGLEG:
+ *                                             optimization_algorithm_gauss_newton.cpp:50, _levenberg.cpp:58, _dogleg.cpp:56)
  *   SparseOptimizer::optimize                 sparse_optimizer.cpp:374    g2ocu_optimize
  *   BlockSolverBase::multiplyHessian          core/block_solver.h:87-95   g2ocu_multiply_hessian
  *   LinearSolver<M>::solve                    core/linear_solver.h:59     (inside g2ocu_solve; kind = g2ocu_config.linear_solver)
@@ -84,6 +85,12 @@ extern "C" {
 /* algorithms (OptimizationAlgorithmLevenberg / GaussNewton) and linear solvers */
 #define G2OCU_ALGORITHM_GN 0
 #define G2OCU_ALGORITHM_LM 1
+#define G2OCU_ALGORITHM_DOGLEG 2   /* core/optimization_algorithm_dogleg.cpp:56-197 (Powell's dogleg); single-GPU handles only */
+/* OptimizationAlgorithmDogleg::lastStep() values (optimization_algorithm_dogleg.h:47-50), element 1 of g2ocu_get_f64("dogleg") */
+#define G2OCU_DOGLEG_STEP_UNDEFINED 0
+#define G2OCU_DOGLEG_STEP_SD 1
+#define G2OCU_DOGLEG_STEP_GN 2
+#define G2OCU_DOGLEG_STEP_DL 3
 #define G2OCU_LINEAR_PCG 0    /* solvers/pcg/linear_solver_pcg.hpp: block-Jacobi preconditioned CG           */
 #define G2OCU_LINEAR_DENSE 1  /* solvers/dense/linear_solver_dense.h semantics: dense FP64 Cholesky (small RCS) */
 
@@ -164,7 +171,7 @@ int g2ocu_create(const g2ocu_config* cfg, g2ocu_solver** out);
 void g2ocu_destroy(g2ocu_solver* s);
 
 int g2ocu_set_graph(g2ocu_solver* s, const g2ocu_graph* g);
-int g2ocu_set_property(g2ocu_solver* s, const char* name, double value);  /* "initialLambda", "maxTrialsAfterFailure" (levenberg.cpp:48-49); "pcgTolerance", "pcgMaxIterations", "pcgAbsoluteTolerance" (linear_solver_pcg.h:53-57); "linearSolver" = G2OCU_LINEAR_* (which LinearSolver the BlockSolver owns, block_solver.h:124); "kernelTiming" != 0: g2ocu_phase_time also reports per-kernel phases (schur_tiles, pcg_spmv, ...) at the price of two event records per kernel */
+int g2ocu_set_property(g2ocu_solver* s, const char* name, double value);  /* "initialLambda", "maxTrialsAfterFailure" (levenberg.cpp:48-49); "pcgTolerance", "pcgMaxIterations", "pcgAbsoluteTolerance" (linear_solver_pcg.h:53-57); "linearSolver" = G2OCU_LINEAR_* (which LinearSolver the BlockSolver owns, block_solver.h:124); "doglegInitialDelta", "doglegMaxTrialsAfterFailure", "doglegInitialLambda", "doglegLambdaFactor" = OptimizationAlgorithmDogleg's "initialDelta" (1e4), "maxTrialsAfterFailure" (100), "initialLambda" (1e-7), "lambdaFactor" (10) (optimization_algorithm_dogleg.cpp:44-47); "kernelTiming" != 0: g2ocu_phase_time also reports per-kernel phases (schur_tiles, pcg_spmv, ...) at the price of two event records per kernel */
 int g2ocu_set_shard(g2ocu_solver* s, int32_t rank, int32_t world, g2ocu_allreduce_fn fn, void* user);
 /* The same sharding with the collectives issued straight from the library through NCCL (no host callback per collective):
  * `nccl_library` is the path of libnccl.so.2 (dlopen'ed; the build has no link-time NCCL dependency), `unique_id` the 128 bytes of an
@@ -209,7 +216,9 @@ int g2ocu_get_estimates(g2ocu_solver* s, double* host_packed);
  * int32: "hessian_index" "active_vertices" "active_edges" "index_mapping" "dims" "pose_block_indices"
  *        "landmark_block_indices" "hpp_colptr" "hpp_rowidx" "hpl_colptr" "hpl_rowidx" "hschur_colptr" "hschur_rowidx"
  *        "hschur_t_colptr" "hschur_t_rowidx" "edge_targets" "shard_landmark_range" "shard_edge_positions"
- * double: "x" "b" "bschur" "hpp_values" "hpl_values" "hll_values" "hschur_values" "errors" "jacobians" "estimates" */
+ * double: "x" "b" "bschur" "hpp_values" "hpl_values" "hll_values" "hschur_values" "errors" "jacobians" "estimates" "lambda"
+ *         "dogleg" = { trustRegion(), lastStep() (G2OCU_DOGLEG_STEP_*), tries of the last iteration, damping factor,
+ *                      1 if the system was positive definite in all iterations } (optimization_algorithm_dogleg.h:64-68,84-88) */
 int64_t g2ocu_get_i32(g2ocu_solver* s, const char* name, int32_t* out, int64_t capacity);
 int64_t g2ocu_get_f64(g2ocu_solver* s, const char* name, double* out, int64_t capacity);
 

@@ -421,7 +421,11 @@ struct Optimizer {
   std::vector<omp_lock_t> coefficientsMutex;
 #endif
   // ---- algorithm state ----
-  bool levenberg = true;
+  bool levenberg = true, dogleg = false;
+  // Dogleg properties / state (optimization_algorithm_dogleg.cpp:40-52, .h:77-91)
+  double dlUserDeltaInit = 1e4, dlInitialLambda = 1e-7, dlLambdaFactor = 10., dlDelta = 1e4, dlCurrentLambda = 1e-7;
+  int dlMaxTrialsAfterFailure = 100, dlLastStep = 0, dlLastNumTries = 0; bool dlWasPDInAllIterations = true;
+  std::vector<double> hsd, hdl, auxVector;
   double currentLambda = -1., tau = 1e-5, goodStepUpperScale = 2./3., goodStepLowerScale = 1./3., userLambdaInit = 0., ni = 2.;
   int maxTrialsAfterFailure = 10, levenbergIterations = 0;
   bool computeBatchStatistics = false;
@@ -816,6 +820,95 @@ struct Optimizer {
     if (qmax == maxTrialsAfterFailure || rho == 0 || !std::isfinite(currentLambda)) return Terminate;
     return OK;
   }
+  // BlockSolver::multiplyHessian (block_solver.h:146) = _Hpp->multiplySymmetricUpperTriangle (sparse_block_matrix.hpp:289-313):
+  // dest(pose part) += Hpp src with the stored upper blocks used on both sides; the landmark part of dest is never touched
+  void multiplyHessian(double* dest, const double* src) const {
+    for (size_t i = 0; i < Hpp.blockCols.size(); ++i) {
+      const int srcOffset = Hpp.colBaseOfBlock((int)i);
+      for (const auto& kv : Hpp.blockCols[i]) {
+        const double* a = Hpp.data(kv.second);
+        const int destOffset = Hpp.rowBaseOfBlock(kv.first);
+        if (destOffset > srcOffset) break;
+        const int r = Hpp.rowsOfBlock(kv.first), c = Hpp.colsOfBlock((int)i);
+        mv_add(a, src + srcOffset, dest + destOffset, r, c);
+        if (destOffset < srcOffset) mtv_add(a, src + destOffset, dest + srcOffset, r, c);
+      }
+    }
+  }
+  enum { STEP_UNDEFINED = 0, STEP_SD = 1, STEP_GN = 2, STEP_DL = 3 };
+  // optimization_algorithm_dogleg.cpp:56-197
+  int solveDogleg(int iteration) {
+    if (iteration == 0) {
+      if (!buildStructure()) return Fail;
+      hsd.assign(x.size(), 0.0); hdl.assign(x.size(), 0.0); auxVector.assign(x.size(), 0.0);
+      dlDelta = dlUserDeltaInit; dlCurrentLambda = dlInitialLambda; dlWasPDInAllIterations = true;
+    }
+    const size_t n = x.size();
+    auto dot = [&](const std::vector<double>& u, const std::vector<double>& v) { double s = 0; for (size_t i = 0; i < n; ++i) s += u[i]*v[i]; return s; };
+    double t = now();
+    computeActiveErrors();
+    if (g_stats) { g_stats->timeResiduals = now() - t; t = now(); }
+    const double currentChi = activeRobustChi2();
+    buildSystem();
+    if (g_stats) g_stats->timeQuadraticForm = now() - t;
+    // alpha (:97-101)
+    std::fill(auxVector.begin(), auxVector.end(), 0.0);
+    multiplyHessian(auxVector.data(), b.data());
+    const double bNormSquared = dot(b, b);
+    const double alpha = bNormSquared / dot(auxVector, b);
+    for (size_t i = 0; i < n; ++i) hsd[i] = alpha * b[i];
+    const double hsdNorm = std::sqrt(dot(hsd, hsd));
+    double hgnNorm = -1.;
+    bool solvedGaussNewton = false, goodStep = false;
+    int& numTries = dlLastNumTries; numTries = 0;
+    do {
+      ++numTries;
+      if (!solvedGaussNewton) {
+        const double minLambda = 1e-12, maxLambda = 1e3;
+        solvedGaussNewton = true;
+        bool solverOk = false;
+        while (!solverOk) {
+          if (!dlWasPDInAllIterations) setLambda(dlCurrentLambda, true);
+          solverOk = solve();
+          if (!dlWasPDInAllIterations) restoreDiagonal();
+          dlWasPDInAllIterations = dlWasPDInAllIterations && solverOk;
+          if (!dlWasPDInAllIterations) {
+            if (solverOk) dlCurrentLambda = std::max(minLambda, dlCurrentLambda / (0.5 * dlLambdaFactor));
+            else { dlCurrentLambda *= dlLambdaFactor; if (dlCurrentLambda > maxLambda) { dlCurrentLambda = maxLambda; return Fail; } }
+          }
+        }
+        hgnNorm = std::sqrt(dot(x, x));
+      }
+      const std::vector<double>& hgn = x;
+      if (hgnNorm < dlDelta) { hdl = hgn; dlLastStep = STEP_GN; }
+      else if (hsdNorm > dlDelta) { const double f = dlDelta / hsdNorm; for (size_t i = 0; i < n; ++i) hdl[i] = f * hsd[i]; dlLastStep = STEP_SD; }
+      else {
+        for (size_t i = 0; i < n; ++i) auxVector[i] = hgn[i] - hsd[i];
+        const double c = dot(hsd, auxVector), bmaSquaredNorm = dot(auxVector, auxVector);
+        double beta;
+        if (c <= 0.) beta = (-c + std::sqrt(c*c + bmaSquaredNorm * (dlDelta*dlDelta - dot(hsd, hsd)))) / bmaSquaredNorm;
+        else { const double hsdSqrNorm = dot(hsd, hsd); beta = (dlDelta*dlDelta - hsdSqrNorm) / (c + std::sqrt(c*c + bmaSquaredNorm * (dlDelta*dlDelta - hsdSqrNorm))); }
+        for (size_t i = 0; i < n; ++i) hdl[i] = hsd[i] + beta * (hgn[i] - hsd[i]);
+        dlLastStep = STEP_DL;
+      }
+      // linear gain (:165-168)
+      std::fill(auxVector.begin(), auxVector.end(), 0.0);
+      multiplyHessian(auxVector.data(), hdl.data());
+      double linearGain = -1 * dot(auxVector, hdl) + 2 * dot(b, hdl);
+      push();
+      update(hdl.data());
+      computeActiveErrors();
+      const double newChi = activeRobustChi2();
+      const double nonLinearGain = currentChi - newChi;
+      if (std::fabs(linearGain) < 1e-12) linearGain = 1e-12;
+      const double rho = nonLinearGain / linearGain;
+      if (rho > 0) { discardTop(); goodStep = true; } else pop();
+      if (rho > 0.75) dlDelta = std::max(dlDelta, 3 * std::sqrt(dot(hdl, hdl)));
+      else if (rho < 0.25) dlDelta *= 0.5;
+    } while (!goodStep && numTries < dlMaxTrialsAfterFailure);
+    if (numTries == dlMaxTrialsAfterFailure || !goodStep) return Terminate;
+    return OK;
+  }
   // optimization_algorithm_gauss_newton.cpp:50-91
   int solveGaussNewton(int iteration) {
     double t = now();
@@ -842,12 +935,12 @@ struct Optimizer {
       std::memset(cstat, 0, sizeof(BatchStats));
       g_stats = cstat; cstat->iteration = i; cstat->numEdges = activeEdges.size(); cstat->numVertices = activeVertices.size();
       double ts = now();
-      result = levenberg ? solveLevenberg(i) : solveGaussNewton(i);
+      result = dogleg ? solveDogleg(i) : levenberg ? solveLevenberg(i) : solveGaussNewton(i);
       ok = (result == OK);
       computeActiveErrors();
       cstat->chi2 = activeRobustChi2();
       cstat->timeIteration = now() - ts;
-      cstat->lambda = currentLambda; cstat->result = result;
+      cstat->lambda = dogleg ? dlCurrentLambda : currentLambda; cstat->result = result;
       if (levenberg) cstat->levenbergIterations = levenbergIterations;
       ++cjIterations;
     }
@@ -918,11 +1011,12 @@ int orc_max_threads() {
 #endif
 }
 
-// name: "<gn|lm>_<anything>" ; linear: "pcg" | "dense" | "csparse" | "csparse_block"
+// name: "<gn|lm|dl>_<anything>" ; linear: "pcg" | "dense" | "csparse" | "csparse_block"
 int orc_set_solver(void* hh, const char* algorithm, const char* linear) {
   Optimizer& o = ((Handle*)hh)->opt;
   std::string a(algorithm), l(linear);
-  if (a.substr(0, 2) == "gn") o.levenberg = false; else if (a.substr(0, 2) == "lm") o.levenberg = true; else return -1;
+  o.dogleg = false;
+  if (a.substr(0, 2) == "gn") o.levenberg = false; else if (a.substr(0, 2) == "lm") o.levenberg = true; else if (a.substr(0, 2) == "dl") { o.levenberg = false; o.dogleg = true; } else return -1;
   if (l == "pcg") o.linearSolver.reset(new LinearSolverPCG);
   else if (l == "dense") o.linearSolver.reset(new LinearSolverDense);
   else if (l == "csparse" || l == "csparse_block") { if (!g_cs.h) return -2; auto* s = new LinearSolverCSparse; s->blockOrdering = (l == "csparse_block"); o.linearSolver.reset(s); }
@@ -930,6 +1024,11 @@ int orc_set_solver(void* hh, const char* algorithm, const char* linear) {
   return 0;
 }
 void orc_set_lm_params(void* hh, double userLambdaInit, int maxTrialsAfterFailure) { Optimizer& o = ((Handle*)hh)->opt; o.userLambdaInit = userLambdaInit; o.maxTrialsAfterFailure = maxTrialsAfterFailure; }
+void orc_set_dogleg_params(void* hh, double initialDelta, int maxTrialsAfterFailure, double initialLambda, double lambdaFactor) {
+  Optimizer& o = ((Handle*)hh)->opt; o.dlUserDeltaInit = initialDelta; o.dlMaxTrialsAfterFailure = maxTrialsAfterFailure; o.dlInitialLambda = initialLambda; o.dlLambdaFactor = lambdaFactor;
+}
+// dest (zeroed here, vectorSize doubles) = Hpp src on the pose part
+void orc_multiply_hessian(void* hh, double* dest, const double* src) { Optimizer& o = ((Handle*)hh)->opt; std::fill(dest, dest + o.x.size(), 0.0); o.multiplyHessian(dest, src); }
 void orc_set_pcg_params(void* hh, double tol, int maxIter, int absoluteTolerance) {
   auto* p = dynamic_cast<LinearSolverPCG*>(((Handle*)hh)->opt.linearSolver.get());
   if (p) { p->tolerance = tol; p->maxIter = maxIter; p->absoluteTolerance = absoluteTolerance != 0; }
@@ -1004,6 +1103,7 @@ const double* orc_get_f64(void* hh, const char* name, int64_t* n) {
   else if (s == "errors") for (int ei : o.activeEdges) { const Edge& e = o.edges[ei]; out.insert(out.end(), e.err, e.err + e.dim); }
   else if (s == "jacobians") for (int ei : o.activeEdges) { const Edge& e = o.edges[ei]; out.insert(out.end(), e.J0, e.J0 + e.dim*o.vertices[e.v[0]].dim); out.insert(out.end(), e.J1, e.J1 + e.dim*o.vertices[e.v[1]].dim); }
   else if (s == "lambda") out = {o.currentLambda};
+  else if (s == "dogleg") out = {o.dlDelta, (double)o.dlLastStep, (double)o.dlLastNumTries, o.dlCurrentLambda, o.dlWasPDInAllIterations ? 1.0 : 0.0};   // trustRegion(), lastStep(), tries, damping, PD flag
   else { *n = -1; return nullptr; }
   *n = (int64_t)out.size(); return out.data();
 }

@@ -51,6 +51,9 @@ def lib() -> ctypes.CDLL:
         L.orc_set_num_threads.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.orc_set_solver.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
         L.orc_set_lm_params.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_int]
+        L.orc_set_dogleg_params.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_double]
+        L.orc_multiply_hessian.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_multiply_hessian.restype = None
         L.orc_set_pcg_params.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_int, ctypes.c_int]
         L.orc_initialize_optimization.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.orc_optimize.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
@@ -116,6 +119,18 @@ class Oracle:
 
     def set_lm_params(self, initial_lambda=0.0, max_trials=10):
         self._L.orc_set_lm_params(self._h, initial_lambda, max_trials)
+
+    def set_dogleg_params(self, initial_delta=1e4, max_trials=100, initial_lambda=1e-7, lambda_factor=10.0):
+        self._L.orc_set_dogleg_params(self._h, initial_delta, max_trials, initial_lambda, lambda_factor)
+
+    def dogleg_state(self) -> dict:
+        d = self.get_f64("dogleg")
+        return {"delta": d[0], "last_step": int(d[1]), "tries": int(d[2]), "lambda": d[3], "was_pd": bool(d[4])}
+
+    def multiply_hessian(self, src) -> np.ndarray:
+        src = np.ascontiguousarray(src, dtype=np.float64); dst = np.zeros_like(src)
+        self._L.orc_multiply_hessian(self._h, _dp(dst), _dp(src))
+        return dst
 
     def set_pcg_params(self, tol=1e-6, max_iter=-1, absolute=True):
         self._L.orc_set_pcg_params(self._h, tol, max_iter, int(absolute))

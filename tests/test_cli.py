@@ -99,3 +99,19 @@ def test_expmap_and_camera_parameter_tags(tmp_path):
     bad.write_text("VERTEX_SE3:EXPMAP 0 0 0 0 0 0 0 1\nVERTEX_XYZ 1 0 0 1\nEDGE_PROJECT_XYZ2UV:EXPMAP 1 0 7 1 1 1 0 1\n")
     r = subprocess.run([CLI, "-summary", str(bad)], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0 and "PARAMS_CAMERAPARAMETERS" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_runs_dogleg(tmp_path):
+    """`-solver dl_var_cuda` with Dogleg's own property names (optimization_algorithm_dogleg.cpp:44-47) and its verbose line (:199-207)."""
+    from g2o_b200.binding import CudaSolver
+    g = W.sphere(nodes_per_level=10, laps=5)
+    path = str(tmp_path / "sphere.g2o")
+    W.write_g2o(g, path)
+    r = subprocess.run([CLI, "-v", "-i", "4", "-solver", "dl_var_cuda", "-solverProperties", "initialDelta=50,maxTrialsAfterFailure=20", path],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Delta=" in r.stderr and "step=" in r.stderr and "tries=" in r.stderr
+    m = re.search(r"iterations (\d+) chi2 (\S+) robust_chi2 (\S+)", r.stdout)
+    s = CudaSolver(g, "dl_var_cuda", device=0); s.initialize_optimization(); s.compute_active_errors()
+    assert int(m.group(1)) > 0 and float(m.group(3)) < s.active_robust_chi2()

@@ -165,3 +165,72 @@ def test_dense_cholesky_solution_and_failure():
     s.restore_diagonal()
     s.set_lambda(-1e15)                      # indefinite system: the reference's LDLT reports !isPositive() and solve() returns false
     assert not s.solve()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Powell's dogleg (optimization_algorithm_dogleg.cpp:56-197): same trajectory, trust region and step types as the oracle
+def _bal_gauge_fixed():
+    """BAL graph with two cameras held fixed: the 7-dof gauge is gone, the undamped Gauss-Newton system is positive definite."""
+    g = W.bal_synthetic(n_cameras=60, n_points=6000, n_obs=30000, seed=5, k_max=40, min_window=4)
+    g.v_fixed = np.array(g.v_fixed, dtype=np.uint8)
+    g.v_fixed[np.flatnonzero(np.asarray(g.v_type) == G.VERTEX_CAM_BAL)[:2]] = 1
+    return g
+
+
+DOGLEG = {
+    # name: (graph, linear solver, initialDelta, iterations)
+    "sphere_dense": (lambda: W.sphere(nodes_per_level=16, laps=8), "dense", 1e4, 3),
+    "sphere_small_delta": (lambda: W.sphere(nodes_per_level=16, laps=8), "dense", 2.0, 5),
+    "slam2d_dense": (lambda: W.slam2d(n_poses=800, n_landmarks=200, world_size=30.0), "dense", 1e4, 5),
+    "slam2d_small_delta": (lambda: W.slam2d(n_poses=800, n_landmarks=200, world_size=30.0), "dense", 1.0, 5),
+    "bal_dense": (_bal_gauge_fixed, "dense", 1e4, 5),
+    "bal_pcg": (_bal_gauge_fixed, "pcg", 1e4, 5),
+}
+
+
+@pytest.mark.parametrize("name", list(DOGLEG))
+def test_dogleg_trajectory(name):
+    fn, linear, delta0, iters = DOGLEG[name]
+    g = fn()
+    s = CudaSolver(g, "dl_var_cuda", linear=linear, device=0); s.set_property("doglegInitialDelta", delta0); s.initialize_optimization()
+    o = Oracle(g, "dl", linear); o.set_dogleg_params(initial_delta=delta0); assert o.initialize_optimization()
+    n, st = s.optimize(iters); no, sto = o.optimize(iters)
+    assert n == no and len(st) == len(sto)
+    loose = linear == "pcg"            # PCG stops at a relative residual of 1e-6: the undamped steps agree to that order only
+    for i, (a, b) in enumerate(zip(st, sto)):
+        tol = 1e-5 if loose else (1e-8 if i == 0 else 1e-6)
+        assert abs(a["chi2"] - b["chi2"]) <= tol * abs(b["chi2"]), (i, a["chi2"], b["chi2"])
+        assert a["result"] == int(b["result"])
+    ds, do = s.dogleg_state(), o.dogleg_state()
+    assert ds["last_step"] == do["last_step"] and ds["tries"] == do["tries"] and ds["was_pd"] == do["was_pd"], (ds, do)
+    assert abs(ds["delta"] - do["delta"]) <= (1e-4 if loose else 1e-6) * do["delta"], (ds, do)
+    eo = o.estimates()
+    assert np.max(np.abs(s.get_estimates() - eo) / (1.0 + np.abs(eo))) < (1e-4 if loose else 1e-6)
+
+
+def test_dogleg_step_norm_and_rejection():
+    """BAL vertices add the increment: an accepted Descent / Dogleg step moves the estimates by exactly the trust-region radius."""
+    g = _bal_gauge_fixed()
+    for delta0 in (1e-4, 3e-2):
+        s = CudaSolver(g, "dl_var_cuda", linear="dense", device=0); s.set_property("doglegInitialDelta", delta0); s.initialize_optimization()
+        e0 = s.get_estimates().copy()
+        n, st = s.optimize(1)
+        d = s.dogleg_state()
+        assert n == 1 and d["tries"] == 1 and d["last_step"] in (1, 3), d
+        moved = np.linalg.norm(s.get_estimates() - e0)
+        assert abs(moved - delta0) <= 1e-9 * delta0, (d, moved)
+        assert d["delta"] >= delta0      # rho > 0.75 on a step this short: the region grows to 3 |hdl| (or stays)
+
+
+def test_dogleg_on_a_rank_deficient_system_stays_finite():
+    """No fixed vertex (7-dof gauge): the dense factorisation may fail and Dogleg damps (dogleg.cpp:117-135), or it succeeds with
+    tiny pivots and the long Gauss-Newton step is cut to the trust region.  Either way chi2 must not increase."""
+    g = W.bal_small()
+    s = CudaSolver(g, "dl_var_cuda", linear="dense", device=0); s.initialize_optimization()
+    s.compute_active_errors(); chi0 = s.active_robust_chi2()
+    n, st = s.optimize(3)
+    assert n >= 0
+    chi = s.active_robust_chi2()
+    assert np.isfinite(chi) and chi <= chi0 * (1 + 1e-12)
+    d = s.dogleg_state()
+    assert 1e-12 <= d["lambda"] <= 1e3

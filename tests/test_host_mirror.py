@@ -18,7 +18,7 @@ def test_solver_library_registers_like_a_g2o_plugin():
     for name in ["gn_var_cuda", "lm_var_cuda", "gn_fix3_2_cuda", "lm_fix3_2_cuda", "gn_fix6_3_cuda", "lm_fix6_3_cuda",
                  "gn_fix7_3_cuda", "lm_fix7_3_cuda", "gn_fix9_3_cuda", "lm_fix9_3_cuda",
                  "gn_dense_cuda", "lm_dense_cuda", "gn_dense3_2_cuda", "lm_dense3_2_cuda", "gn_dense6_3_cuda", "lm_dense6_3_cuda",
-                 "gn_dense7_3_cuda", "lm_dense7_3_cuda", "gn_dense9_3_cuda", "lm_dense9_3_cuda"]:
+                 "gn_dense7_3_cuda", "lm_dense7_3_cuda", "gn_dense9_3_cuda", "lm_dense9_3_cuda", "dl_var_cuda"]:
         assert hasattr(L, "g2o_optimization_algorithm_" + name), name
 
 

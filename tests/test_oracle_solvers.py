@@ -114,3 +114,125 @@ def test_lm_converges_like_the_reference_unit_tests():
         o.compute_active_errors(); assert o.active_chi2() < 1e-6
         e = o.estimates()[12:]
         assert np.linalg.norm(e[9:]) < 1e-12 and np.linalg.norm(np.array([e[0], e[4], e[8]]) - 1) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Powell's dogleg (core/optimization_algorithm_dogleg.cpp:56-197).  The reference holds no test for it: the oracle's restatement is
+# pinned by an independent numpy restatement of the same control flow driven through the oracle's Solver primitives, and by
+# properties of the step (trust-region norm, convergence to the LM minimum).
+def test_multiply_hessian_is_hpp_only():
+    """BlockSolver::multiplyHessian = _Hpp->multiplySymmetricUpperTriangle (block_solver.h:146): the landmark part stays zero."""
+    for name in ("bal", "sphere"):
+        o = Oracle(CASES[name](), "dl", "dense")
+        assert o.initialize_optimization() and o.algorithm_init() and o.build_structure()
+        o.compute_active_errors(); o.build_system()
+        H = dense_from_blocks(o); sp = int(o.get_i32("dims")[2])
+        v = np.random.default_rng(1).normal(size=H.shape[0])
+        y = o.multiply_hessian(v)
+        assert np.allclose(y[:sp], H[:sp, :sp] @ v[:sp], rtol=1e-12, atol=1e-12 * np.max(np.abs(y)))
+        assert np.all(y[sp:] == 0.0)
+
+
+def numpy_dogleg(o, iterations, delta=1e4, max_trials=100):
+    """The loop of optimization_algorithm_dogleg.cpp:56-197 in numpy on top of Solver::buildSystem / solve / update (positive definite case)."""
+    out = []
+    sp = int(o.get_i32("dims")[2])
+    for _ in range(iterations):
+        o.compute_active_errors(); chi = o.active_robust_chi2(); o.build_system()
+        b = o.get_f64("b"); Hpp = dense_from_blocks(o)[:sp, :sp]
+        aux = np.zeros_like(b); aux[:sp] = Hpp @ b[:sp]
+        alpha = (b @ b) / (aux @ b); hsd = alpha * b; hsd_norm = np.linalg.norm(hsd)
+        assert o.solve(); hgn = o.get_f64("x"); hgn_norm = np.linalg.norm(hgn)
+        tries, good = 0, False
+        while not good and tries < max_trials:
+            tries += 1
+            if hgn_norm < delta:
+                hdl, step = hgn.copy(), 2
+            elif hsd_norm > delta:
+                hdl, step = delta / hsd_norm * hsd, 1
+            else:
+                d = hgn - hsd; c = hsd @ d; dd = d @ d
+                if c <= 0:
+                    beta = (-c + np.sqrt(c * c + dd * (delta * delta - hsd @ hsd))) / dd
+                else:
+                    beta = (delta * delta - hsd @ hsd) / (c + np.sqrt(c * c + dd * (delta * delta - hsd @ hsd)))
+                hdl, step = hsd + beta * d, 3
+            aux = np.zeros_like(b); aux[:sp] = Hpp @ hdl[:sp]
+            gain = -(aux @ hdl) + 2 * (b @ hdl)
+            o.push(); o.update(hdl); o.compute_active_errors(); new_chi = o.active_robust_chi2()
+            if abs(gain) < 1e-12:
+                gain = 1e-12
+            rho = (chi - new_chi) / gain
+            if rho > 0:
+                o.discard_top(); good = True
+            else:
+                o.pop()
+            if rho > 0.75:
+                delta = max(delta, 3 * np.linalg.norm(hdl))
+            elif rho < 0.25:
+                delta *= 0.5
+        o.compute_active_errors()
+        out.append((o.active_robust_chi2(), delta, step, tries))
+        if not good:
+            break
+    return out
+
+
+@pytest.mark.parametrize("name,delta0", [("sphere", 1e4), ("sphere", 2.0), ("slam2d", 1e4), ("slam2d", 0.5)])
+def test_dogleg_against_numpy_restatement(name, delta0):
+    g = CASES[name]()
+    o = Oracle(g, "dl", "dense"); o.set_dogleg_params(initial_delta=delta0); assert o.initialize_optimization()
+    n, st = o.optimize(6)
+    q = Oracle(g, "dl", "dense"); assert q.initialize_optimization() and q.algorithm_init() and q.build_structure()
+    ref = numpy_dogleg(q, 6, delta=delta0)
+    assert o.dogleg_state()["was_pd"]      # the damping branch is covered by test_dogleg_damping_branch
+    assert n == len(ref)
+    for s, r in zip(st, ref):
+        assert abs(s["chi2"] - r[0]) <= 1e-7 * abs(r[0]), (s["chi2"], r)
+    d = o.dogleg_state()
+    assert abs(d["delta"] - ref[-1][1]) <= 1e-9 * ref[-1][1] and d["last_step"] == ref[-1][2] and d["tries"] == ref[-1][3]
+    assert np.max(np.abs(o.estimates() - q.estimates())) <= 1e-7 * (1 + np.max(np.abs(q.estimates())))
+
+
+def test_dogleg_step_has_the_trust_region_norm():
+    """BAL vertices add the increment (bal_example.cpp:90-94,127-131): a Descent or Dogleg step moves the estimates by exactly delta."""
+    g = CASES["bal"]()
+    seen = set()
+    for delta0 in (1e-4, 3e-2, 1e4):
+        o = Oracle(g, "dl", "dense"); o.set_dogleg_params(initial_delta=delta0); assert o.initialize_optimization()
+        e0 = o.estimates()
+        n, st = o.optimize(1)
+        d = o.dogleg_state()
+        moved = np.linalg.norm(o.estimates() - e0)
+        if d["tries"] != 1:
+            continue                                    # the trust region was shrunk before a step was accepted
+        seen.add(d["last_step"])
+        if d["last_step"] in (1, 3):
+            assert abs(moved - delta0) <= 1e-9 * delta0, (d, moved)
+        else:
+            assert moved < delta0
+    assert 1 in seen and 2 in seen
+
+
+def test_dogleg_reaches_the_lm_minimum():
+    for name in ("sphere", "slam2d"):
+        g = CASES[name]()
+        lin = "csparse" if has_csparse() else "dense"
+        d = Oracle(g, "dl", lin); d.initialize_optimization(); nd, sd = d.optimize(40)
+        l = Oracle(g, "lm", lin); l.initialize_optimization(); nl, sl = l.optimize(40)
+        assert abs(sd[-1]["chi2"] - sl[-1]["chi2"]) <= 1e-6 * sl[-1]["chi2"], (name, sd[-1]["chi2"], sl[-1]["chi2"])
+        chis = [s["chi2"] for s in sd]
+        assert all(b <= a * (1 + 1e-12) for a, b in zip(chis, chis[1:]))   # only steps with rho > 0 are kept
+
+
+def test_dogleg_damping_branch():
+    """A rank-deficient system (no fixed vertex: 7-dof gauge) makes LinearSolverDense return false; Dogleg then damps with
+    _currentLambda *= lambdaFactor until the factorisation succeeds (optimization_algorithm_dogleg.cpp:117-135)."""
+    g = CASES["bal"]()
+    o = Oracle(g, "dl", "dense"); assert o.initialize_optimization()
+    n, st = o.optimize(3)
+    d = o.dogleg_state()
+    if d["was_pd"]:
+        pytest.skip("LDL^T found only positive pivots on this problem")
+    assert n == 3 and 1e-12 <= d["lambda"] <= 1e3
+    assert st[-1]["chi2"] < st[0]["chi2"]

@@ -113,3 +113,21 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, name), name
     assert declared == set(_lib.EXPORTS)
     assert L.g2ocu_version() == 1
+
+
+def test_every_algorithm_fails_loudly_without_a_device():
+    """No CPU fallback: on a box without a GPU the iteration entry point reports G2OCU_E_CUDA for GN, LM and Dogleg alike
+    (on a GPU box this test has nothing to check)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    g = W.sphere(nodes_per_level=6, laps=3)
+    for name in ("gn_var_cuda", "lm_var_cuda", "dl_var_cuda"):
+        s = CudaSolver(g, name); s.initialize_optimization()
+        with pytest.raises(G2oCudaError) as ei:
+            s.optimize(2)
+        assert ei.value.code == _lib.E_CUDA, str(ei.value)
+    s = CudaSolver(g, "lm_var_cuda"); s.initialize_optimization(); s.init()
+    import ctypes
+    rc = s._L.g2ocu_solver_iteration(s._h, 7, 0, None)      # unknown algorithm code
+    assert rc < 0
