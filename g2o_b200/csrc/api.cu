@@ -123,6 +123,7 @@ struct g2ocu_solver {
   DVec<int> poseCounters, lmCounters;
   DVec<double> denseH; DVec<int> denseInfo; DVec<unsigned int> pcgTicket; int* hostInfo = nullptr;
   DVec<double> Hpp, Hll, Hpl, W, b, x, S, Dinv, dbv, bschur, Minv, vr, vd, vq, vs, scal, partial, partialDq, scratch, out2, dbg;
+  DVec<double> fr, fd, fq, fs;                                       // full-system PCG vectors r, d, q, s (vectorSize each)
   DVec<double> hsd, hdl, aux;                                        // Dogleg: steepest-descent step, final step, auxiliary vector (vectorSize each)
   DVec<int32_t> mhRow, mhBegin, mhEnd, mhRowPtr, mhColIdx; bool mhReady = false;   // SpMV work items over the Hpp pattern (multiplyHessian in Schur mode)
   DVec<int32_t> hppDiag, hplColPtr, hplRowIdx, sRowPtr, sColIdx, sDiag, hppToS, pairSlot, pairEdgeI, pairEdgeJ, aRowPtr, aColIdx, aDiag, spRow, spBegin, spEnd, hplLm, tEntLm, tEntBI, tEntBJ, tChunkI, tChunkJ, tChunkB, tChunkE;
@@ -527,10 +528,16 @@ int solvePcg(g2ocu_solver* s, const double* rhs) {
   return G2OCU_OK;
 }
 
+int solveFullPcg(g2ocu_solver* s);
+
 int solveSystem(g2ocu_solver* s, int* solved) {
   const Structure& st = s->st;
   *solved = 1;
   const bool dense = s->cfg.linear_solver == G2OCU_LINEAR_DENSE;
+  // Points that are not marginalized: the reference's BlockSolver has no Schur step and hands the whole matrix to its LinearSolver.
+  // PCG iterates on that whole system (its iterates differ from those of a reduced system); an exact factorisation gives the same
+  // x either way, so the dense solver eliminates the points (Schur + Cholesky of the reduced system + back-substitution below).
+  if (st.fullSystem && !dense) { PhaseTimer pt(s, "linear_solver"); return solveFullPcg(s); }
   // LinearSolverDense::solve (linear_solver_dense.h:65-115): dense copy of the solved matrix, Cholesky, x = A^-1 rhs; false when not positive
   auto solveDense = [&](const double* rhs) -> int {
     PcgDev& pc = s->pcg;
@@ -706,25 +713,95 @@ int solveGaussNewton(g2ocu_solver* s, int iteration, int* result) {
   return G2OCU_OK;
 }
 
-// BlockSolver::multiplyHessian (block_solver.h:146) = _Hpp->multiplySymmetricUpperTriangle (sparse_block_matrix.hpp:289-313) on device
-// vectors: dst[0, sizePoses) = (Hpp + lambda I) src[0, sizePoses).  The landmark part of the reference's dest is never touched.
-int multiplyHessianDev(g2ocu_solver* s, const double* src, double* dst) {
+// PCG view of Hpp (pattern, diagonal blocks, SpMV work items).  Without Schur that is the solver's own view; with the landmark class
+// present the solver's view covers Hschur and the Hpp pattern gets its own work items (one per block row), uploaded once per structure.
+int hppView(g2ocu_solver* s, PcgDev& pc) {
   const Structure& st = s->st;
-  PcgDev pc = s->pcg; pc.A = s->Hpp.p; pc.lambda = s->lambda; pc.scal = nullptr;
-  if (st.doSchur) {                                                  // the PCG items cover Hschur: the Hpp pattern needs its own
-    if (!s->mhReady) {
-      std::vector<int32_t> hr, hb, he;
-      for (int i = 0; i < st.numPoses; ++i) { hr.push_back(i); hb.push_back(st.hppRowPtr[i]); he.push_back(st.hppRowPtr[i + 1]); }
-      CU(s->mhRow.upload(hr, s->stream)); CU(s->mhBegin.upload(hb, s->stream)); CU(s->mhEnd.upload(he, s->stream));
-      CU(s->mhRowPtr.upload(st.hppRowPtr, s->stream)); CU(s->mhColIdx.upload(st.hppColIdx, s->stream));
-      CU(cudaStreamSynchronize(s->stream));                          // host staging vectors go out of scope
-      s->mhReady = true;
-    }
-    pc.itemRow = s->mhRow.p; pc.itemBegin = s->mhBegin.p; pc.itemEnd = s->mhEnd.p; pc.nItems = st.numPoses;
-    pc.rowPtr = s->mhRowPtr.p; pc.colIdx = s->mhColIdx.p; pc.diag = s->hppDiag.p; pc.nnz = (int)st.hppColIdx.size();
-    pc.ownLo = 0; pc.ownHi = pc.nnz;
+  pc = s->pcg; pc.A = s->Hpp.p; pc.lambda = s->lambda; pc.scal = nullptr;
+  if (!st.doSchur) return G2OCU_OK;
+  if (!s->mhReady) {
+    std::vector<int32_t> hr, hb, he;
+    for (int i = 0; i < st.numPoses; ++i) { hr.push_back(i); hb.push_back(st.hppRowPtr[i]); he.push_back(st.hppRowPtr[i + 1]); }
+    CU(s->mhRow.upload(hr, s->stream)); CU(s->mhBegin.upload(hb, s->stream)); CU(s->mhEnd.upload(he, s->stream));
+    CU(s->mhRowPtr.upload(st.hppRowPtr, s->stream)); CU(s->mhColIdx.upload(st.hppColIdx, s->stream));
+    CU(cudaStreamSynchronize(s->stream));                            // host staging vectors go out of scope
+    s->mhReady = true;
   }
+  pc.itemRow = s->mhRow.p; pc.itemBegin = s->mhBegin.p; pc.itemEnd = s->mhEnd.p; pc.nItems = st.numPoses;
+  pc.rowPtr = s->mhRowPtr.p; pc.colIdx = s->mhColIdx.p; pc.diag = s->hppDiag.p; pc.nnz = (int)st.hppColIdx.size();
+  pc.ownLo = 0; pc.ownHi = pc.nnz;
+  return G2OCU_OK;
+}
+
+// q = ([Hpp Hpl; Hpl^T Hll] + lambda I) d over the internal [poses | points] layout (full-system mode)
+int multFullSystem(g2ocu_solver* s, const double* d, double* q) {
+  const Structure& st = s->st; const int64_t np = st.sizePoses;
+  PcgDev pc; int rc = hppView(s, pc); if (rc) return rc;
+  launchSpmv(pc, d, q, s->stream, &s->launches);                                                                     // q_p = (Hpp + lambda I) d_p
+  launchBlockDiagMult(q + np, s->Hll.p, d + np, st.numLandmarks, st.L, s->lambda, s->stream, &s->launches);          // q_l = (Hll + lambda I) d_l
+  launchHplMult(s->Hpl.p, s->hplRowIdx.p, s->hplLm.p, (int)st.hplRowIdx.size(), st.P, st.L, d, d + np, q, q + np, s->stream, &s->launches);   // += Hpl d_l, Hpl^T d_p
+  CU(cudaGetLastError());
+  return G2OCU_OK;
+}
+
+// BlockSolver::multiplyHessian (block_solver.h:146) = _Hpp->multiplySymmetricUpperTriangle (sparse_block_matrix.hpp:289-313) on device
+// vectors.  With marginalized landmarks the reference's Hpp is the pose block only: dst[0, sizePoses) = (Hpp + lambda I) src[0, sizePoses)
+// and the landmark part of its dest is never touched.  In full-system mode the reference's Hpp is the whole matrix.
+int multiplyHessianDev(g2ocu_solver* s, const double* src, double* dst) {
+  if (s->st.fullSystem) return multFullSystem(s, src, dst);
+  PcgDev pc; int rc = hppView(s, pc); if (rc) return rc;
   launchSpmv(pc, src, dst, s->stream, &s->launches);
+  CU(cudaGetLastError());
+  return G2OCU_OK;
+}
+
+// LinearSolverPCG::solve (linear_solver_pcg.hpp:80-156) on the whole system of a graph whose points are not marginalized:
+// block-Jacobi preconditioner from the P x P and L x L diagonal blocks, _residual carried from one solve to the next.  The scalars of
+// the recurrences are formed on the host (two fixed-order dot products per iteration); this is the general-purpose `*_var` path, the
+// bundle-adjustment hot path is the Schur branch of solveSystem.
+int solveFullPcg(g2ocu_solver* s) {
+  const Structure& st = s->st;
+  const int64_t np = st.sizePoses, n = np + st.sizeLandmarks;
+  CU(s->fr.alloc((size_t)n)); CU(s->fd.alloc((size_t)n)); CU(s->fq.alloc((size_t)n)); CU(s->fs.alloc((size_t)n));
+  double* r = s->fr.p; double* d = s->fd.p; double* q = s->fq.p; double* sv = s->fs.p; double* x = s->x.p;
+  PcgDev pc; int rc = hppView(s, pc); if (rc) return rc;
+  launchBlockInverse(pc, s->stream, &s->launches);                                                                   // J_i = (Hpp_ii + lambda I)^-1 -> Minv
+  launchPointBlockInverse(s->Dinv.p, s->Hll.p, st.numLandmarks, st.L, s->lambda, s->stream, &s->launches);           // and the point blocks -> Dinv
+  auto precond = [&](const double* in, double* out) {
+    launchBlockDiagMult(out, s->Minv.p, in, st.numPoses, st.P, 0.0, s->stream, &s->launches);
+    launchBlockDiagMult(out + np, s->Dinv.p, in + np, st.numLandmarks, st.L, 0.0, s->stream, &s->launches);
+  };
+  auto dot = [&](const double* u, const double* v, double* out) -> int {
+    launchScale(u, v, n, 0.0, s->scratch.p, s->out2.p + 12, s->stream, &s->launches);
+    CU(cudaMemcpyAsync(s->hostScal + 24, s->out2.p + 12, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    int r2 = syncStream(s); if (r2) return r2;
+    *out = s->hostScal[24];
+    return G2OCU_OK;
+  };
+  CU(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), s->stream));
+  CU(cudaMemcpyAsync(r, s->b.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+  precond(r, d);
+  double dn = 0; rc = dot(r, d, &dn); if (rc) return rc;
+  double d0 = s->cfg.pcg_tolerance * dn;
+  if (s->cfg.pcg_absolute_tolerance) { if (s->pcgResidual > 0.0 && s->pcgResidual > d0) d0 = s->pcgResidual; }
+  const int64_t maxIter = s->cfg.pcg_max_iterations < 0 ? n : s->cfg.pcg_max_iterations;
+  int64_t iteration;
+  for (iteration = 0; iteration < maxIter; ++iteration) {
+    if (dn <= d0) break;
+    rc = multFullSystem(s, d, q); if (rc) return rc;
+    double dq = 0; rc = dot(d, q, &dq); if (rc) return rc;
+    const double a = dn / dq;
+    launchLincomb(x, d, nullptr, a, 3, n, s->stream, &s->launches);        // x += a d
+    launchLincomb(r, q, nullptr, -a, 3, n, s->stream, &s->launches);       // r -= a q
+    precond(r, sv);
+    const double dold = dn;
+    rc = dot(r, sv, &dn); if (rc) return rc;
+    const double ba = dn / dold;
+    launchLincomb(d, sv, nullptr, ba, 4, n, s->stream, &s->launches);      // d = s + ba d
+    if (!std::isfinite(dn)) { ++iteration; break; }                          // NaN/Inf in the recurrence: stop (the reference would spin to maxIter)
+  }
+  s->pcgResidual = 0.5 * dn;
+  s->lastPcgIterations = (int)iteration;
   CU(cudaGetLastError());
   return G2OCU_OK;
 }
@@ -737,7 +814,8 @@ int solveDogleg(g2ocu_solver* s, int iteration, int* result) {
   if (s->world > 1) return fail(s, G2OCU_E_UNSUPPORTED, "the Dogleg algorithm is not available on a sharded solver");
   if (iteration == 0 && !s->structureBuilt) { rc = g2ocu_build_structure(s); if (rc) return rc; }
   const Structure& st = s->st;
-  const int64_t n = (int64_t)st.sizePoses + st.sizeLandmarks, np = st.sizePoses;
+  const int64_t n = (int64_t)st.sizePoses + st.sizeLandmarks;
+  const int64_t np = st.fullSystem ? n : st.sizePoses;     // length of the Hessian product: the reference's Hpp (the whole system when nothing is marginalized)
   if (iteration == 0) { s->dlDelta = s->dlUserDeltaInit; s->dlCurrentLambda = s->dlInitialLambda; s->dlWasPD = true; }
   CU(s->hsd.alloc((size_t)n)); CU(s->hdl.alloc((size_t)n)); CU(s->aux.alloc((size_t)n));
   int slot = 0;
@@ -979,6 +1057,7 @@ int g2ocu_build_structure(g2ocu_solver* s) {
     if (naturalPL != es.poseLandmark || (naturalPL && naturalSide != es.poseSide))
       return fail(s, G2OCU_E_UNSUPPORTED, "edge type " + std::to_string(es.etype) + ": the landmark-side vertices must be marginalized and the pose-side vertices must not (mixed block sizes are not supported)");
   }
+  if (st.fullSystem && s->world > 1) return fail(s, G2OCU_E_UNSUPPORTED, "a graph whose points are not marginalized cannot be sharded (mark the points as marginalized)");
   s->slabBlocks = st.doSchur ? (int64_t)((st.sColIdx.size() + s->world - 1) / s->world) : 0;   // equal block ranges of the reduced system (slab PCG)
   int rc = ensureCuda(s); if (rc) return rc;
   rc = buildDevice(s); if (rc) return rc;
@@ -1014,6 +1093,12 @@ int g2ocu_solve(g2ocu_solver* s, int32_t* solved) {
 }
 int g2ocu_update(g2ocu_solver* s, const double* host) {
   int rc = requireBuilt(s); if (rc) return rc;
+  std::vector<double> tmp;
+  if (host && s->st.fullSystem) {   // the caller's vector is in the reference's order (all vertices by id)
+    tmp.resize(s->x.n);
+    for (size_t i = 0; i < tmp.size(); ++i) tmp[s->st.refToInternal[i]] = host[i];
+    host = tmp.data();
+  }
   if (host) CU(cudaMemcpyAsync(s->x.p, host, s->x.n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   rc = applyUpdate(s); if (rc) return rc;
   return syncStream(s);
@@ -1027,6 +1112,18 @@ int g2ocu_compute_scale(g2ocu_solver* s, double lambda, double* scale) { int rc 
 int g2ocu_multiply_hessian(g2ocu_solver* s, double* hostDest, const double* hostSrc) {
   int rc = requireBuilt(s); if (rc) return rc;
   if (!hostDest || !hostSrc) return fail(s, G2OCU_E_INVALID, "null vector");
+  if (s->st.fullSystem) {                                            // the reference's Hpp is the whole matrix; vectors in its order
+    const size_t n = s->x.n;
+    std::vector<double> tmp(n);
+    for (size_t i = 0; i < n; ++i) tmp[s->st.refToInternal[i]] = hostSrc[i];
+    CU(s->fd.alloc(n)); CU(s->fq.alloc(n));
+    CU(cudaMemcpyAsync(s->fd.p, tmp.data(), n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    rc = multFullSystem(s, s->fd.p, s->fq.p); if (rc) return rc;
+    CU(cudaMemcpyAsync(tmp.data(), s->fq.p, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    rc = syncStream(s); if (rc) return rc;
+    for (size_t i = 0; i < n; ++i) hostDest[i] = tmp[s->st.refToInternal[i]];
+    return G2OCU_OK;
+  }
   const int n = s->st.sizePoses;                                     // BlockSolverBase::multiplyHessian works on Hpp (block_solver.h:87-95)
   CU(cudaMemcpyAsync(s->vd.p, hostSrc, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   rc = multiplyHessianDev(s, s->vd.p, s->vq.p); if (rc) return rc;
@@ -1054,7 +1151,8 @@ int g2ocu_solver_iteration(g2ocu_solver* s, int32_t algorithm, int32_t iteration
     stats->time_schur_complement = phaseSeconds(s, "schur") - sc0; stats->time_linear_solver = phaseSeconds(s, "linear_solver") - l0;
     stats->time_linear_solution = stats->time_schur_complement + stats->time_linear_solver + (phaseSeconds(s, "backsub") - bs0);
     stats->time_update = phaseSeconds(s, "update") - u0; stats->time_iteration = wallNow() - t0;
-    stats->hessian_pose_dimension = s->st.sizePoses; stats->hessian_landmark_dimension = s->st.sizeLandmarks;
+    stats->hessian_pose_dimension = s->st.fullSystem ? s->st.sizePoses + s->st.sizeLandmarks : s->st.sizePoses;   // full-system mode: everything is in the reference's Hpp
+    stats->hessian_landmark_dimension = s->st.fullSystem ? 0 : s->st.sizeLandmarks;
   }
   return G2OCU_OK;
 }
@@ -1117,6 +1215,16 @@ int64_t g2ocu_get_i32(g2ocu_solver* s, const char* name, int32_t* out, int64_t c
   if (n == "active_edges") return copyOutI32(st.activeEdges, out, cap);
   if (n == "index_mapping") return copyOutI32(st.ivMap, out, cap);
   if (st.classOf.empty()) return fail(s, G2OCU_E_INVALID, "buildStructure has not been called");
+  if (st.fullSystem) {   // what the reference's buildStructure holds for this graph: one Hpp over all vertices in id order
+    if (n == "dims") return copyOutI32(st.refDims, out, cap);
+    if (n == "pose_block_indices") return copyOutI32(st.refPoseBlockIndices, out, cap);
+    if (n == "landmark_block_indices") return copyOutI32({}, out, cap);
+    if (n == "hpp_colptr") return copyOutI32(st.refHppColPtr, out, cap);
+    if (n == "hpp_rowidx") return copyOutI32(st.refHppRowIdx, out, cap);
+    if (n == "edge_targets") return copyOutI32(st.refEdgeTargets, out, cap);
+    if (n == "full_system_permutation") return copyOutI32(st.refToInternal, out, cap);
+    if (n == "internal_dims") return copyOutI32({st.numPoses, st.numLandmarks, st.sizePoses, st.sizeLandmarks}, out, cap);
+  }
   if (n == "dims") return copyOutI32({st.numPoses, st.numLandmarks, st.sizePoses, st.sizeLandmarks}, out, cap);
   if (n == "pose_block_indices") return copyOutI32(st.poseBlockIndices, out, cap);
   if (n == "landmark_block_indices") return copyOutI32(st.landmarkBlockIndices, out, cap);
@@ -1167,6 +1275,18 @@ static int64_t downloadBlocks(g2ocu_solver* s, const double* dev, const std::vec
 int64_t g2ocu_get_f64(g2ocu_solver* s, const char* name, double* out, int64_t cap) {
   int rc = requireBuilt(s); if (rc) return rc;
   const std::string n(name ? name : ""); const Structure& st = s->st; const int P = st.P, L = st.L;
+  if (st.fullSystem) {
+    if (n == "x" || n == "b") {   // reference order: all vertices by id
+      const size_t cnt = s->x.n;
+      if (!out) return (int64_t)cnt;
+      std::vector<double> tmp(cnt);
+      const int64_t got = downloadF64(s, n == "x" ? s->x.p : s->b.p, cnt, tmp.data(), (int64_t)cnt); if (got < 0) return got;
+      for (size_t i = 0; i < cnt && (int64_t)i < cap; ++i) out[i] = tmp[st.refToInternal[i]];
+      return (int64_t)cnt;
+    }
+    if (n == "bschur" || n == "hpp_values" || n == "hschur_values" || n == "hpl_values" || n == "hll_values" || n == "dinv_values")
+      return fail(s, G2OCU_E_UNSUPPORTED, "block values are not available in the reference's layout when the points are not marginalized (" + n + ")");
+  }
   if (n == "x") return downloadF64(s, s->x.p, s->x.n, out, cap);
   if (n == "b") return downloadF64(s, s->b.p, s->b.n, out, cap);
   if (n == "bschur") return downloadF64(s, s->bschur.p, s->bschur.n, out, cap);

@@ -93,23 +93,40 @@ template <class T> static void sortUnique(std::vector<T>& v) { std::sort(v.begin
 bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int rank, int world) {
   if (st.ivMap.empty()) { err = "0 vertices to optimize, maybe forgot to call initializeOptimization()"; return false; }
   // Schur iff any active vertex is marginalized (optimization_algorithm_with_hessian.cpp:48-66)
-  st.doSchur = false;
+  st.doSchur = false; st.fullSystem = false;
   for (int v : st.activeVertices) if (g.vMarg[v]) { st.doSchur = true; break; }
+  auto isPoint = [](int t) { return t == G2OCU_VERTEX_POINT_XY || t == G2OCU_VERTEX_POINT_XYZ || t == G2OCU_VERTEX_POINT_BAL; };
+  if (!st.doSchur) {
+    bool anyPoint = false, anyPose = false;
+    for (int v : st.ivMap) { if (isPoint(g.vType[v])) anyPoint = true; else anyPose = true; }   // free vertices only
+    st.fullSystem = anyPoint && anyPose;
+  }
+  // class of a vertex (1 = landmark class) and its index in the [poses | landmarks] order.  Full-system mode: what the flags and
+  // indices would be had the caller marginalized the points - a permutation of the reference's order, undone at the boundary.
+  std::vector<uint8_t> effMarg(g.nV, 0); std::vector<int32_t> effH(st.hessianIndex);
+  for (int v = 0; v < g.nV; ++v) effMarg[v] = st.fullSystem ? (uint8_t)isPoint(g.vType[v]) : (uint8_t)(g.vMarg[v] != 0);
+  if (st.fullSystem) {
+    st.doSchur = true;
+    int i = 0;
+    for (int k = 0; k < 2; ++k) for (int v : st.ivMap) if ((int)effMarg[v] == k) effH[v] = i++;
+  }
   st.classOf.assign(g.nV, -1); st.slotOf.assign(g.nV, -1);
   st.numPoses = st.numLandmarks = 0; st.poseType = st.lmType = 0;
-  for (int v : st.ivMap) { if (!g.vMarg[v]) st.numPoses++; else st.numLandmarks++; }
+  for (int v : st.ivMap) { if (!effMarg[v]) st.numPoses++; else st.numLandmarks++; }
   st.poseVerts.clear(); st.lmVerts.clear();
-  for (int v : st.ivMap) {
-    int c = g.vMarg[v] ? 1 : 0; st.classOf[v] = c;
+  std::vector<int32_t> byEff(st.ivMap.size());
+  for (int v : st.ivMap) byEff[effH[v]] = v;
+  for (int v : byEff) {
+    int c = effMarg[v] ? 1 : 0; st.classOf[v] = c;
     int& ty = c ? st.lmType : st.poseType;
     if (ty == 0) ty = g.vType[v];
     else if (ty != g.vType[v]) { err = std::string("mixed vertex types inside the ") + (c ? "landmark" : "pose") + " block are not supported (uniform block size required)"; return false; }
-    st.slotOf[v] = c ? st.hessianIndex[v] - st.numPoses : st.hessianIndex[v];
+    st.slotOf[v] = c ? effH[v] - st.numPoses : effH[v];
     (c ? st.lmVerts : st.poseVerts).push_back(v);
   }
   for (int v : st.activeVertices) {
     if (!g.vFixed[v]) continue;
-    int c = g.vMarg[v] ? 1 : 0; st.classOf[v] = c;
+    int c = effMarg[v] ? 1 : 0; st.classOf[v] = c;
     int& ty = c ? st.lmType : st.poseType;
     if (ty == 0) ty = g.vType[v];
     else if (ty != g.vType[v]) { err = "mixed vertex types inside one block class are not supported"; return false; }
@@ -130,16 +147,16 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int ran
   std::vector<int64_t> ppPairs, plPairs;       // encoded (row<<32|col) for Hpp (row<=col) and (lm<<32|pose) for Hpl
   for (int k = 0; k < nA; ++k) {
     int e = st.activeEdges[k]; int v0 = g.eV0[e], v1 = g.eV1[e];
-    int h0 = st.hessianIndex[v0], h1 = st.hessianIndex[v1];
+    int h0 = effH[v0], h1 = effH[v1];
     int* t = &st.edgeTargets[(size_t)k * 4]; t[3] = 0;
     if (h0 == -1 || h1 == -1) continue;
-    bool m0 = g.vMarg[v0], m1 = g.vMarg[v1];
+    bool m0 = effMarg[v0], m1 = effMarg[v1];
     if (!m0 && !m1) {
       int a = h0, b = h1; bool tr = a > b; if (tr) std::swap(a, b);
       t[0] = 0; t[1] = a; t[2] = b; t[3] = tr;
       ppPairs.push_back(((int64_t)a << 32) | (uint32_t)b);
     } else if (m0 && m1) {
-      err = "edge between two marginalized vertices (landmark-landmark block) is not supported"; return false;
+      err = st.fullSystem ? "edge between two point vertices is not supported" : "edge between two marginalized vertices (landmark-landmark block) is not supported"; return false;
     } else if (m0) { t[0] = 2; t[1] = h1; t[2] = h0 - st.numPoses; t[3] = 1; plPairs.push_back(((int64_t)t[2] << 32) | (uint32_t)t[1]); }
     else { t[0] = 2; t[1] = h0; t[2] = h1 - st.numPoses; t[3] = 0; plPairs.push_back(((int64_t)t[2] << 32) | (uint32_t)t[1]); }
   }
@@ -198,7 +215,7 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int ran
         int v = st.lmVerts[l]; buf.clear();
         for (int64_t a = g.adjPtr[v]; a < g.adjPtr[v + 1]; ++a) {
           int e = g.adjEdge[a]; int o = g.eV0[e] == v ? g.eV1[e] : g.eV0[e];
-          int h = st.hessianIndex[o];
+          int h = effH[o];
           if (h == -1) continue;
           if (h >= st.numPoses) { err = "edge between two marginalized vertices is not supported"; return false; }
           buf.push_back(h);
@@ -330,6 +347,34 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int ran
         s.poseChunkPtr[p + 1] = (int)s.chunkPose.size();
       }
     }
+  }
+  // ---- full-system mode: the arrays of the reference's own buildStructure (everything in one Hpp, vertices by id) ----
+  st.refDims.clear(); st.refPoseBlockIndices.clear(); st.refHppColPtr.clear(); st.refHppRowIdx.clear(); st.refEdgeTargets.clear(); st.refToInternal.clear();
+  if (st.fullSystem) {
+    const int nAll = (int)st.ivMap.size();
+    int off = 0;
+    for (int v : st.ivMap) {
+      const int d = vertexDim(g.vType[v]);
+      const int base = st.classOf[v] ? st.sizePoses + st.slotOf[v] * st.L : st.slotOf[v] * st.P;
+      for (int q = 0; q < d; ++q) st.refToInternal.push_back(base + q);
+      off += d; st.refPoseBlockIndices.push_back(off);
+    }
+    st.refDims = {nAll, 0, off, 0};
+    st.refEdgeTargets.assign((size_t)nA * 4, -1);
+    std::vector<int64_t> pairs;                    // (col << 32 | row), row <= col
+    for (int i = 0; i < nAll; ++i) pairs.push_back(((int64_t)i << 32) | (uint32_t)i);
+    for (int k = 0; k < nA; ++k) {
+      const int e = st.activeEdges[k]; const int h0 = st.hessianIndex[g.eV0[e]], h1 = st.hessianIndex[g.eV1[e]];
+      int* t = &st.refEdgeTargets[(size_t)k * 4]; t[3] = 0;
+      if (h0 == -1 || h1 == -1) continue;
+      const int a = std::min(h0, h1), b = std::max(h0, h1);
+      t[0] = 0; t[1] = a; t[2] = b; t[3] = h0 > h1;
+      pairs.push_back(((int64_t)b << 32) | (uint32_t)a);
+    }
+    sortUnique(pairs);
+    st.refHppColPtr.assign(nAll + 1, 0); st.refHppRowIdx.resize(pairs.size());
+    for (size_t k = 0; k < pairs.size(); ++k) { st.refHppColPtr[(int)(pairs[k] >> 32) + 1]++; st.refHppRowIdx[k] = (int)(pairs[k] & 0xffffffff); }
+    for (int i = 0; i < nAll; ++i) st.refHppColPtr[i + 1] += st.refHppColPtr[i];
   }
   return true;
 }

@@ -47,6 +47,14 @@ struct Structure {
   std::vector<int32_t> hessianIndex, activeVertices, activeEdges, ivMap;
   // ---- buildStructure ----
   bool doSchur = false;
+  // Full-system mode: no vertex is marginalized but the graph holds pose-type AND point-type vertices (`lm_var` on a SLAM / BA graph,
+  // BlockSolverX with blocks of two sizes).  Internally the points still form the landmark class (the same Hpp / Hpl / Hll storage and
+  // build kernels as with Schur, doSchur is set), but the reference solves the whole system: PCG runs over [Hpp Hpl; Hpl^T Hll] and the
+  // vectors of the boundary (x, b, update) keep the reference's order (all vertices by id).  ref* hold what the reference's
+  // buildStructure produces for this graph (one Hpp over all vertices) for the bit-exact structure check.
+  bool fullSystem = false;
+  std::vector<int32_t> refDims, refPoseBlockIndices, refHppColPtr, refHppRowIdx, refEdgeTargets;
+  std::vector<int32_t> refToInternal;    // scalar index in the reference's x / b  ->  scalar index in the internal [poses | points] layout
   int numPoses = 0, numLandmarks = 0, sizePoses = 0, sizeLandmarks = 0;
   int P = 0, L = 0;                      // uniform block dimensions
   int poseType = 0, lmType = 0;          // vertex type of each class (0 = class empty)

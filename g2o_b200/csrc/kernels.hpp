@@ -115,8 +115,13 @@ bool pcgSingleCtaTail(const PcgDev& p);   // launchPcgTail zeroes q itself (smal
 void launchExtractPoseDiag(const SystemDev& sys, double* out, cudaStream_t st, int64_t* launches);
 void launchMaxDiag(const SystemDev& sys, const double* poseDiag, int lmBegin, int lmEnd, double* scratch /* >= 148 doubles */, double* out, cudaStream_t st, int64_t* launches);
 void launchScale(const double* x, const double* b, int64_t n, double lambda, double* scratch, double* out, cudaStream_t st, int64_t* launches);   // out[0] = sum_j x_j (lambda x_j + b_j); with lambda = 0 a fixed-order dot product
-// Dogleg step vectors: mode 0: out = a u; mode 1: out = v - u; mode 2: out = u + a (v - u)
+// Dogleg step vectors: mode 0: out = a u; mode 1: out = v - u; mode 2: out = u + a (v - u); PCG recurrences: mode 3: out += a u; mode 4: out = u + a out
 void launchLincomb(double* out, const double* u, const double* v, double a, int mode, int64_t n, cudaStream_t st, int64_t* launches);
+// full-system PCG (points not marginalized): block-diagonal products / inverses and the Hpl, Hpl^T products
+void launchBlockDiagMult(double* out, const double* M, const double* in, int nBlocks, int D, double lambda, cudaStream_t st, int64_t* launches);   // out = (M + lambda I) in
+void launchPointBlockInverse(double* Dinv, const double* Hll, int n, int L, double lambda, cudaStream_t st, int64_t* launches);                      // Dinv = (Hll + lambda I)^-1, L = 2 | 3
+void launchHplMult(const double* Hpl, const int32_t* hplRow, const int32_t* hplLm, int nBlocks, int P, int L, const double* dp, const double* dl, double* qp, double* ql,
+                   cudaStream_t st, int64_t* launches);                                                                                            // qp += Hpl dl, ql += Hpl^T dp
 
 // dense FP64 Cholesky path (kernels_dense.cu)
 void launchDenseAssemble(const PcgDev& p, double* H, cudaStream_t st, int64_t* launches);      // upper blocks -> dense lower-filled n x n

@@ -661,11 +661,63 @@ __global__ void __launch_bounds__(256) final_sum_kernel(const double* partial, i
   if (threadIdx.x == 0) out[0] = r;
 }
 
-// Dogleg step vectors (optimization_algorithm_dogleg.cpp:102,141-157): mode 0: out = a u; mode 1: out = v - u; mode 2: out = u + a (v - u)
+// Dogleg step vectors (optimization_algorithm_dogleg.cpp:102,141-157): mode 0: out = a u; mode 1: out = v - u; mode 2: out = u + a (v - u);
+// PCG recurrences of the full-system solver (linear_solver_pcg.hpp:138-150): mode 3: out += a u; mode 4: out = u + a out
 __global__ void __launch_bounds__(256) lincomb_kernel(double* out, const double* u, const double* v, double a, int mode, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
     const double ui = u[i];
-    out[i] = mode == 0 ? a * ui : (mode == 1 ? v[i] - ui : ui + a * (v[i] - ui));
+    double r;
+    if (mode == 0) r = a * ui;
+    else if (mode == 1) r = v[i] - ui;
+    else if (mode == 2) r = ui + a * (v[i] - ui);
+    else if (mode == 3) r = out[i] + a * ui;
+    else r = ui + a * out[i];
+    out[i] = r;
+  }
+}
+
+// ---- full-system PCG over [Hpp Hpl; Hpl^T Hll] (graphs whose points are not marginalized; the product of the Hpp part is spmv_tma_kernel) ----
+// out = (M + lambda I) in for a block-diagonal M of nBlocks D x D column-major blocks: thread per scalar row
+__global__ void __launch_bounds__(256) blockdiag_mult_kernel(double* __restrict__ out, const double* __restrict__ M, const double* __restrict__ in, int nBlocks, int D, double lambda) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (int64_t)nBlocks * D) return;
+  const int64_t blk = i / D; const int row = (int)(i - blk * D);
+  const double* m = M + blk * D * D; const double* x = in + blk * D;
+  double v = lambda * x[row];
+  for (int k = 0; k < D; ++k) v += m[row + D * k] * x[k];
+  out[i] = v;
+}
+// Dinv = (Hll + lambda I)^-1 per point block (Eigen's fixed-size inverse(): cofactors), thread per block
+template <int L> __global__ void __launch_bounds__(128) point_block_inverse_kernel(double* __restrict__ Dinv, const double* __restrict__ Hll, int n, double lambda) {
+  constexpr int LL = L * L;
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= n) return;
+  double H[LL], X[LL];
+#pragma unroll
+  for (int q = 0; q < LL; ++q) H[q] = Hll[(size_t)i * LL + q];
+#pragma unroll
+  for (int q = 0; q < L; ++q) H[q * (L + 1)] += lambda;
+  invSmall<L>(H, X);
+#pragma unroll
+  for (int q = 0; q < LL; ++q) Dinv[(size_t)i * LL + q] = X[q];
+}
+// q_p[row] += B d_l[lm], q_l[lm] += B^T d_p[row] for every Hpl block B (P x L, column-major): thread per block
+__global__ void __launch_bounds__(128) hpl_mult_kernel(const double* __restrict__ Hpl, const int32_t* __restrict__ hplRow, const int32_t* __restrict__ hplLm, int nBlocks, int P, int L,
+                                                        const double* __restrict__ dp, const double* __restrict__ dl, double* qp, double* ql) {
+  const int k = blockIdx.x * 128 + threadIdx.x;
+  if (k >= nBlocks) return;
+  const double* B = Hpl + (size_t)k * P * L;
+  const int row = hplRow[k], lm = hplLm[k];
+  const double* xp = dp + (size_t)row * P; const double* xl = dl + (size_t)lm * L;
+  for (int c = 0; c < L; ++c) {
+    double t = 0;
+    for (int r = 0; r < P; ++r) t += B[r + P * c] * xp[r];
+    atomicAdd(ql + (size_t)lm * L + c, t);
+  }
+  for (int r = 0; r < P; ++r) {
+    double t = 0;
+    for (int c = 0; c < L; ++c) t += B[r + P * c] * xl[c];
+    atomicAdd(qp + (size_t)row * P + r, t);
   }
 }
 
@@ -676,6 +728,23 @@ void launchLincomb(double* out, const double* u, const double* v, double a, int 
   if (n <= 0) return;
   int64_t nb64 = (n + 255) / 256; const int nb = (int)(nb64 < 148 * 8 ? nb64 : 148 * 8);
   lincomb_kernel<<<nb, 256, 0, st>>>(out, u, v, a, mode, n);
+  *launches += 1;
+}
+void launchBlockDiagMult(double* out, const double* M, const double* in, int nBlocks, int D, double lambda, cudaStream_t st, int64_t* launches) {
+  if (nBlocks <= 0) return;
+  blockdiag_mult_kernel<<<(unsigned)(((int64_t)nBlocks * D + 255) / 256), 256, 0, st>>>(out, M, in, nBlocks, D, lambda);
+  *launches += 1;
+}
+void launchPointBlockInverse(double* Dinv, const double* Hll, int n, int L, double lambda, cudaStream_t st, int64_t* launches) {
+  if (n <= 0) return;
+  if (L == 2) point_block_inverse_kernel<2><<<(n + 127) / 128, 128, 0, st>>>(Dinv, Hll, n, lambda);
+  else point_block_inverse_kernel<3><<<(n + 127) / 128, 128, 0, st>>>(Dinv, Hll, n, lambda);
+  *launches += 1;
+}
+void launchHplMult(const double* Hpl, const int32_t* hplRow, const int32_t* hplLm, int nBlocks, int P, int L, const double* dp, const double* dl, double* qp, double* ql,
+                   cudaStream_t st, int64_t* launches) {
+  if (nBlocks <= 0) return;
+  hpl_mult_kernel<<<(nBlocks + 127) / 128, 128, 0, st>>>(Hpl, hplRow, hplLm, nBlocks, P, L, dp, dl, qp, ql);
   *launches += 1;
 }
 void launchPairSlots(const SchurDev& d, cudaStream_t st, int64_t* launches) {

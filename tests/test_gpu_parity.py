@@ -234,3 +234,84 @@ def test_dogleg_on_a_rank_deficient_system_stays_finite():
     assert np.isfinite(chi) and chi <= chi0 * (1 + 1e-12)
     d = s.dogleg_state()
     assert 1e-12 <= d["lambda"] <= 1e3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Points that are not marginalized (`lm_var` on SLAM / BA graphs, BlockSolverX with two block sizes): the reference solves the
+# whole system; vectors at the boundary are in its order (all vertices by id)
+def _points_free(g):
+    g.v_marginalized = np.zeros_like(g.v_marginalized)
+    return g
+
+
+FULL = {
+    "slam2d": lambda: W.slam2d(n_poses=800, n_landmarks=200, world_size=30.0, marginalize_landmarks=False),
+    "ba_demo": lambda: _points_free(W.ba_demo()),
+    "bal_small": lambda: _points_free(W.bal_small()),
+}
+
+
+@pytest.mark.parametrize("name", list(FULL))
+def test_full_system_blocks_and_solve(name):
+    g = FULL[name]()
+    s = CudaSolver(g, "lm_var_cuda", device=0); s.initialize_optimization()
+    o = Oracle(g, "lm", "pcg"); assert o.initialize_optimization()
+    s.init(); s.build_structure()
+    assert o.algorithm_init() and o.build_structure() and not o.do_schur()
+    assert np.array_equal(s.get_i32("dims"), o.get_i32("dims"))
+    s.compute_active_errors(); o.compute_active_errors()
+    assert rel(s.get_f64("errors"), o.get_f64("errors")) < 1e-11
+    assert abs(s.active_robust_chi2() - o.active_robust_chi2()) <= 1e-11 * abs(o.active_robust_chi2())
+    s.build_system(); o.build_system()
+    assert rel(s.b(), o.get_f64("b")) < 1e-11
+    lam_s, lam_o = s.compute_lambda_init(), o.compute_lambda_init()
+    assert abs(lam_s - lam_o) <= 1e-11 * lam_o
+    # H v over the whole system, with and without damping
+    v = np.random.default_rng(3).normal(size=s.vector_size())
+    assert rel(s.multiply_hessian(v), o.multiply_hessian(v)) < 1e-11
+    s.set_lambda(lam_o); o.set_lambda(lam_o)
+    assert rel(s.multiply_hessian(v), o.multiply_hessian(v)) < 1e-11
+    assert s.solve() and o.solve()
+    xs, xo = s.x(), o.get_f64("x")
+    assert rel(xs, xo) < 1e-6            # PCG stops at a relative residual of 1e-6
+    assert abs(s.compute_scale(lam_o) - o.compute_scale()) <= 1e-6 * abs(o.compute_scale())
+    s.restore_diagonal(); o.restore_diagonal()
+    s.push(); o.push()
+    s.update(xo); o.update(xo)           # a step in the reference's vector order
+    assert rel(s.get_estimates(), o.estimates()) < 1e-12
+    s.compute_active_errors(); o.compute_active_errors()
+    assert abs(s.active_robust_chi2() - o.active_robust_chi2()) <= 1e-10 * abs(o.active_robust_chi2())
+    s.pop(); o.pop()
+    assert rel(s.get_estimates(), o.estimates()) == 0.0
+
+
+@pytest.mark.parametrize("linear", ["pcg", "dense"])
+@pytest.mark.parametrize("name", list(FULL))
+def test_full_system_lm_trajectory(name, linear):
+    g = FULL[name]()
+    s = CudaSolver(g, "lm_var_cuda", linear=linear, device=0); s.initialize_optimization()
+    o = Oracle(g, "lm", linear); assert o.initialize_optimization()
+    n, st = s.optimize(6); no, sto = o.optimize(6)
+    assert n == no and len(st) == len(sto)
+    for i, (a, b) in enumerate(zip(st, sto)):
+        tol = 1e-8 if i == 0 else 1e-6
+        assert abs(a["chi2"] - b["chi2"]) <= tol * abs(b["chi2"]), (i, a["chi2"], b["chi2"])
+        assert a["levenberg_iterations"] == int(b["levenbergIterations"]), i
+        assert abs(a["lambda"] - b["lambda"]) <= 1e-6 * abs(b["lambda"]), i
+        assert a["hessian_pose_dimension"] == int(b["hessianPoseDimension"]) and a["hessian_landmark_dimension"] == 0
+    eo = o.estimates()
+    assert np.max(np.abs(s.get_estimates() - eo) / (1.0 + np.abs(eo))) < 1e-6
+
+
+def test_full_system_gauss_newton_and_dogleg():
+    g = FULL["slam2d"]()
+    for name, alg, iters in (("gn_var_cuda", "gn", 3), ("dl_var_cuda", "dl", 4)):
+        s = CudaSolver(g, name, linear="dense", device=0); s.initialize_optimization()
+        o = Oracle(g, alg, "dense"); assert o.initialize_optimization()
+        n, st = s.optimize(iters); no, sto = o.optimize(iters)
+        assert n == no
+        for i, (a, b) in enumerate(zip(st, sto)):
+            assert abs(a["chi2"] - b["chi2"]) <= (1e-8 if i == 0 else 1e-6) * abs(b["chi2"]), (name, i, a["chi2"], b["chi2"])
+        if alg == "dl":
+            ds, do = s.dogleg_state(), o.dogleg_state()
+            assert ds["last_step"] == do["last_step"] and ds["tries"] == do["tries"] and abs(ds["delta"] - do["delta"]) <= 1e-6 * do["delta"], (ds, do)

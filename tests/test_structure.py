@@ -62,6 +62,22 @@ def test_slam2d_structure():
     check(W.slam2d(n_poses=300, n_landmarks=400, world_size=60.0))      # many landmarks never observed -> inactive
 
 
+def test_points_not_marginalized():
+    """`lm_var` on graphs with poses and points and no marginalization (BlockSolverX, one Hpp with blocks of two sizes): the arrays of
+    the reference's buildStructure, and the permutation between its vector order and the internal [poses | points] layout."""
+    graphs = [W.slam2d(n_poses=150, n_landmarks=50, world_size=14.0, marginalize_landmarks=False), W.ba_demo(num_cameras=6, num_points=40), W.bal_small()]
+    for g in graphs:
+        g.v_marginalized = np.zeros_like(g.v_marginalized)
+        s, o = check(g)
+        assert not o.do_schur()
+        nposes, npoints, sp, sl = s.get_i32("internal_dims")
+        perm = s.get_i32("full_system_permutation")
+        assert sorted(perm.tolist()) == list(range(sp + sl)) and int(s.get_i32("dims")[2]) == sp + sl
+        # poses keep their relative order inside the pose part, points inside the point part
+        pose_part, point_part = perm[perm < sp], perm[perm >= sp]
+        assert np.all(np.diff(pose_part) > 0) and np.all(np.diff(point_part) > 0)
+
+
 def test_fixed_and_levels():
     g = W.bal_small()
     g.v_fixed[2] = 1                      # a fixed camera: its edges keep only the landmark diagonal
@@ -92,8 +108,9 @@ def test_rejections():
     import ctypes
     rc = s._L.g2ocu_set_graph(s._h, ctypes.byref(cg))
     assert rc == _lib.E_UNSUPPORTED and b"unsupported edge type" in s._L.g2ocu_last_error(s._h)
-    # un-marginalized points next to cameras: mixed block sizes are rejected, not silently mishandled
-    g3 = W.bal_small(); g3.v_marginalized[:] = 0
+    # some points marginalized and some not: two block sizes inside the pose block next to a Schur complement is rejected, not mishandled
+    g3 = W.bal_small(); g3.v_marginalized = g3.v_marginalized.copy()
+    g3.v_marginalized[np.flatnonzero(g3.v_marginalized)[::2]] = 0
     s3 = CudaSolver(g3, "lm_var_cuda"); s3.initialize_optimization()
     with pytest.raises(G2oCudaError) as ei:
         s3.build_structure()
