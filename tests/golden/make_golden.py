@@ -1,6 +1,6 @@
 """Generates tests/golden/*.json with the CPU oracle (run here, in the build container):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py          (adds the cases missing from the file; --all regenerates every case)
 
 The reference holds no fixtures for this path and cannot be compiled here (no Eigen3), so these are
 *oracle-generated* regression vectors: they pin the oracle against accidental change and give the GPU tests a fixed target
@@ -24,12 +24,19 @@ CASES = {
     "sphere_16x8": (lambda: W.sphere(nodes_per_level=16, laps=8), "lm", "pcg"),
     "slam2d_800": (lambda: W.slam2d(n_poses=800, n_landmarks=200, world_size=30.0), "lm", "pcg"),
     "sphere_gn": (lambda: W.sphere(nodes_per_level=12, laps=6), "gn", "pcg"),
+    # poses and points in one system (nothing marginalized, BlockSolverX with two block sizes), PCG over the whole matrix
+    "slam2d_points_free": (lambda: W.slam2d(n_poses=800, n_landmarks=200, world_size=30.0, marginalize_landmarks=False), "lm", "pcg"),
+    # Powell's dogleg with an exact linear solver
+    "slam2d_dogleg": (lambda: W.slam2d(n_poses=800, n_landmarks=200, world_size=30.0), "dl", "dense"),
 }
 
 
 def main():
-    out = {}
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lm_trajectories.json")
+    out = json.load(open(path)) if os.path.exists(path) and "--all" not in sys.argv else {}   # default: only add the cases that are missing
     for name, (fn, alg, lin) in CASES.items():
+        if name in out:
+            continue
         g = fn()
         o = Oracle(g, alg, lin); o.initialize_optimization(); o.algorithm_init(); o.build_structure()
         o.compute_active_errors(); o.build_system()
@@ -48,7 +55,7 @@ def main():
                     "algorithm": alg})
         out[name] = rec
         print(name, rec["chi2_0"], rec["chi2"][-1])
-    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "lm_trajectories.json"), "w") as fh:
+    with open(path, "w") as fh:
         json.dump(out, fh, indent=1)
 
 

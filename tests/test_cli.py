@@ -56,7 +56,9 @@ def _cli_chi2(args):
 def test_cli_matches_the_binding(tmp_path):
     from g2o_b200.binding import CudaSolver
     cases = [("sphere", W.sphere(nodes_per_level=10, laps=5), "lm_var_cuda", []),
-             ("slam2d", W.slam2d(n_poses=400, n_landmarks=100, world_size=20.0), "lm_fix3_2_cuda", ["-robustKernel", "Huber"])]
+             ("slam2d", W.slam2d(n_poses=400, n_landmarks=100, world_size=20.0), "lm_fix3_2_cuda", ["-robustKernel", "Huber"]),
+             # lm_var does not ask for marginalization (g2o.cpp:318-331): poses and points stay in one system
+             ("slam2d_free", W.slam2d(n_poses=400, n_landmarks=100, world_size=20.0, marginalize_landmarks=False), "lm_var_cuda", ["-robustKernel", "Huber"])]
     for name, g, solver, extra in cases:
         path = str(tmp_path / f"{name}.g2o")
         W.write_g2o(g, path)
