@@ -2,6 +2,9 @@
 #include "host_structure.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
 #ifdef _OPENMP
 #include <omp.h>
@@ -88,10 +91,23 @@ bool initializeOptimization(const HostGraph& g, int level, Structure& st, std::s
   return true;
 }
 
+// G2OCU_TRACE=1: wall time of the phases of buildStructure on stderr
+struct TracePhase {
+  static bool on() { static const bool v = [] { const char* e = std::getenv("G2OCU_TRACE"); return e && *e && *e != '0'; }(); return v; }
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void mark(const char* what) {
+    if (!on()) return;
+    const auto n = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[g2ocu] buildStructure %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+
 template <class T> static void sortUnique(std::vector<T>& v) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
 
 bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int rank, int world) {
   if (st.ivMap.empty()) { err = "0 vertices to optimize, maybe forgot to call initializeOptimization()"; return false; }
+  TracePhase trace;
   // Schur iff any active vertex is marginalized (optimization_algorithm_with_hessian.cpp:48-66)
   st.doSchur = false; st.fullSystem = false;
   for (int v : st.activeVertices) if (g.vMarg[v]) { st.doSchur = true; break; }
@@ -141,6 +157,7 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int ran
   for (int i = 0; i < st.numPoses; ++i) st.poseBlockIndices[i] = (i + 1) * st.P;
   for (int i = 0; i < st.numLandmarks; ++i) st.landmarkBlockIndices[i] = (i + 1) * st.L;
 
+  trace.mark("classes");
   // ---- per-edge targets (block_solver.hpp:166-214) ----
   const int nA = (int)st.activeEdges.size();
   st.edgeTargets.assign((size_t)nA * 4, -1);
@@ -160,6 +177,7 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int ran
     } else if (m0) { t[0] = 2; t[1] = h1; t[2] = h0 - st.numPoses; t[3] = 1; plPairs.push_back(((int64_t)t[2] << 32) | (uint32_t)t[1]); }
     else { t[0] = 2; t[1] = h0; t[2] = h1 - st.numPoses; t[3] = 0; plPairs.push_back(((int64_t)t[2] << 32) | (uint32_t)t[1]); }
   }
+  trace.mark("edge targets");
   // ---- Hpp pattern: diagonal + pose-pose edges, upper ----
   const size_t ppEdges = ppPairs.size();
   for (int i = 0; i < st.numPoses; ++i) ppPairs.push_back(((int64_t)i << 32) | (uint32_t)i);
@@ -187,6 +205,7 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int ran
   };
   transposeToCcs(st.numPoses, st.hppRowPtr, st.hppColIdx, st.hppColPtr, st.hppRowIdx, st.hppCcsToCsr);
 
+  trace.mark("Hpp pattern");
   // ---- Hpl pattern: CCS by landmark, ascending pose rows ----
   {
     std::vector<int64_t> all = plPairs;
@@ -202,6 +221,7 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int ran
   st.schurPairs = 0;
   for (int l = 0; l < st.numLandmarks; ++l) { int64_t k = st.hplColPtr[l + 1] - st.hplColPtr[l]; st.schurPairs += k * (k + 1) / 2; }
 
+  trace.mark("Hpl pattern");
   // ---- Schur pattern (block_solver.hpp:190-192, 224-251) ----
   if (st.doSchur) {
     // cams(l): pose hessian indices reachable through ANY incident edge of the landmark vertex (the reference walks
@@ -225,12 +245,14 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int ran
         lcPtr[l + 1] = (int32_t)lcIdx.size();
       }
     }
+    trace.mark("  cams per landmark");
     // pose -> landmarks (transpose)
     std::vector<int64_t> clPtr(st.numPoses + 1, 0); std::vector<int32_t> clIdx(lcIdx.size());
     for (int32_t c : lcIdx) clPtr[c + 1]++;
     for (int i = 0; i < st.numPoses; ++i) clPtr[i + 1] += clPtr[i];
     { std::vector<int64_t> fill(clPtr.begin(), clPtr.end() - 1);
       for (int l = 0; l < st.numLandmarks; ++l) for (int k = lcPtr[l]; k < lcPtr[l + 1]; ++k) clIdx[fill[lcIdx[k]]++] = l; }
+    trace.mark("  landmarks per cam");
     std::vector<std::vector<int32_t>> rows(st.numPoses);
 #pragma omp parallel
     {
@@ -247,6 +269,7 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int ran
         std::sort(out.begin(), out.end());
       }
     }
+    trace.mark("  marker sweep");
     st.sRowPtr.assign(st.numPoses + 1, 0);
     for (int i = 0; i < st.numPoses; ++i) st.sRowPtr[i + 1] = st.sRowPtr[i] + (int)rows[i].size();
     st.sColIdx.resize(st.sRowPtr[st.numPoses]); st.sDiag.assign(st.numPoses, -1);
@@ -262,6 +285,7 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int ran
     st.sRowPtr.clear(); st.sColIdx.clear(); st.sColPtr.clear(); st.sRowIdx.clear(); st.sCcsToCsr.clear(); st.sDiag.clear(); st.hppToS.clear();
   }
 
+  trace.mark("Hschur pattern");
   // ---- landmark ownership for sharded runs: contiguous slot ranges balanced by a cost model of the per-landmark work ----
   // k observations cost ~k in the build / coefficient / back-substitution passes and k (k + 1) / 2 block products in the Schur complement;
   // the weights are the measured single-GPU times per unit on C3 (0.40 ns per observation, 0.085 ns per block product).
@@ -348,6 +372,7 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int ran
       }
     }
   }
+  trace.mark("edge sets");
   // ---- full-system mode: the arrays of the reference's own buildStructure (everything in one Hpp, vertices by id) ----
   st.refDims.clear(); st.refPoseBlockIndices.clear(); st.refHppColPtr.clear(); st.refHppRowIdx.clear(); st.refEdgeTargets.clear(); st.refToInternal.clear();
   if (st.fullSystem) {
