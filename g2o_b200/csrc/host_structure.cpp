@@ -103,6 +103,21 @@ struct TracePhase {
   }
 };
 
+// Stable order of [0, n) by (hi, lo), keys in [0, nHi) x [0, nLo): two counting-sort passes (least significant key first) instead of a
+// comparison sort - the edge lists are millions long and the keys are vertex slots.
+static void orderByTwoKeys(const std::vector<int32_t>& hi, int nHi, const std::vector<int32_t>& lo, int nLo, std::vector<int32_t>& ord) {
+  const size_t n = hi.size();
+  std::vector<int32_t> tmp(n); ord.resize(n);
+  { std::vector<int64_t> cnt((size_t)nLo + 1, 0);
+    for (size_t i = 0; i < n; ++i) cnt[lo[i] + 1]++;
+    for (int b = 0; b < nLo; ++b) cnt[b + 1] += cnt[b];
+    for (size_t i = 0; i < n; ++i) tmp[cnt[lo[i]]++] = (int32_t)i; }
+  { std::vector<int64_t> cnt((size_t)nHi + 1, 0);
+    for (size_t i = 0; i < n; ++i) cnt[hi[i] + 1]++;
+    for (int b = 0; b < nHi; ++b) cnt[b + 1] += cnt[b];
+    for (size_t j = 0; j < n; ++j) { const int32_t i = tmp[j]; ord[cnt[hi[i]]++] = i; } }
+}
+
 template <class T> static void sortUnique(std::vector<T>& v) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
 
 bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int rank, int world) {
@@ -161,7 +176,10 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int ran
   // ---- per-edge targets (block_solver.hpp:166-214) ----
   const int nA = (int)st.activeEdges.size();
   st.edgeTargets.assign((size_t)nA * 4, -1);
-  std::vector<int64_t> ppPairs, plPairs;       // encoded (row<<32|col) for Hpp (row<=col) and (lm<<32|pose) for Hpl
+  std::vector<int64_t> ppPairs;                // encoded (row<<32|col) for Hpp (row<=col)
+  std::vector<int32_t> plLm, plPose;           // (landmark, pose) of every Hpl contribution
+  bool lmLmEdge = false;
+#pragma omp parallel for schedule(static) reduction(|| : lmLmEdge)
   for (int k = 0; k < nA; ++k) {
     int e = st.activeEdges[k]; int v0 = g.eV0[e], v1 = g.eV1[e];
     int h0 = effH[v0], h1 = effH[v1];
@@ -171,11 +189,15 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int ran
     if (!m0 && !m1) {
       int a = h0, b = h1; bool tr = a > b; if (tr) std::swap(a, b);
       t[0] = 0; t[1] = a; t[2] = b; t[3] = tr;
-      ppPairs.push_back(((int64_t)a << 32) | (uint32_t)b);
-    } else if (m0 && m1) {
-      err = st.fullSystem ? "edge between two point vertices is not supported" : "edge between two marginalized vertices (landmark-landmark block) is not supported"; return false;
-    } else if (m0) { t[0] = 2; t[1] = h1; t[2] = h0 - st.numPoses; t[3] = 1; plPairs.push_back(((int64_t)t[2] << 32) | (uint32_t)t[1]); }
-    else { t[0] = 2; t[1] = h0; t[2] = h1 - st.numPoses; t[3] = 0; plPairs.push_back(((int64_t)t[2] << 32) | (uint32_t)t[1]); }
+    } else if (m0 && m1) lmLmEdge = true;
+    else if (m0) { t[0] = 2; t[1] = h1; t[2] = h0 - st.numPoses; t[3] = 1; }
+    else { t[0] = 2; t[1] = h0; t[2] = h1 - st.numPoses; t[3] = 0; }
+  }
+  if (lmLmEdge) { err = st.fullSystem ? "edge between two point vertices is not supported" : "edge between two marginalized vertices (landmark-landmark block) is not supported"; return false; }
+  for (int k = 0; k < nA; ++k) {
+    const int* t = &st.edgeTargets[(size_t)k * 4];
+    if (t[0] == 0) ppPairs.push_back(((int64_t)t[1] << 32) | (uint32_t)t[2]);
+    else if (t[0] == 2) { plLm.push_back(t[2]); plPose.push_back(t[1]); }
   }
   trace.mark("edge targets");
   // ---- Hpp pattern: diagonal + pose-pose edges, upper ----
@@ -207,12 +229,13 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int ran
 
   trace.mark("Hpp pattern");
   // ---- Hpl pattern: CCS by landmark, ascending pose rows ----
+  std::vector<int64_t> plPairs(plLm.size());   // (lm<<32|pose), sorted, unique (a comparison sort of packed keys beats two counting passes over 1M buckets here)
   {
-    std::vector<int64_t> all = plPairs;
-    std::sort(all.begin(), all.end());
-    st.hplShared = std::adjacent_find(all.begin(), all.end()) != all.end();
-    all.erase(std::unique(all.begin(), all.end()), all.end());
-    plPairs.swap(all);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)plLm.size(); ++i) plPairs[i] = ((int64_t)plLm[i] << 32) | (uint32_t)plPose[i];
+    std::sort(plPairs.begin(), plPairs.end());
+    st.hplShared = std::adjacent_find(plPairs.begin(), plPairs.end()) != plPairs.end();
+    plPairs.erase(std::unique(plPairs.begin(), plPairs.end()), plPairs.end());
   }
   const int nnzPL = (int)plPairs.size();
   st.hplColPtr.assign(st.numLandmarks + 1, 0); st.hplRowIdx.resize(nnzPL);
@@ -332,19 +355,20 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int ran
       s.pos.swap(keep);
       n = (int)s.pos.size();
     }
-    if (s.poseLandmark) {
-      std::vector<int64_t> keyv(n);
-      std::vector<int32_t> ord(n);
+    if (s.poseLandmark) {   // kernel order: by (landmark slot, pose slot), ties in internalId order
+      std::vector<int32_t> kl(n), kp(n), ord;
+#pragma omp parallel for schedule(static)
       for (int i = 0; i < n; ++i) {
         int e = st.activeEdges[s.pos[i]];
         int vp = s.poseSide == 0 ? g.eV0[e] : g.eV1[e], vl = s.poseSide == 0 ? g.eV1[e] : g.eV0[e];
-        keyv[i] = ((int64_t)st.slotOf[vl] << 32) | (uint32_t)st.slotOf[vp]; ord[i] = i;
+        kl[i] = st.slotOf[vl]; kp[i] = st.slotOf[vp];
       }
-      std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return keyv[a] < keyv[b]; });
+      orderByTwoKeys(kl, std::max(st.numLmSlots, 1), kp, std::max(st.numPoseSlots, 1), ord);
       std::vector<int32_t> npos(n); for (int i = 0; i < n; ++i) npos[i] = s.pos[ord[i]];
       s.pos.swap(npos);
     }
     s.slot0.resize(n); s.slot1.resize(n); s.block.assign(n, -1); s.transposed.assign(n, 0);
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < n; ++i) {
       int k = s.pos[i]; int e = st.activeEdges[k];
       s.slot0[i] = st.slotOf[g.eV0[e]]; s.slot1[i] = st.slotOf[g.eV1[e]];
