@@ -113,10 +113,10 @@ int main(int argc, char** argv) {
   optimizer.computeActiveErrors();
   std::cout << "iterations " << result << " chi2 " << std::setprecision(17) << optimizer.activeChi2() << " robust_chi2 " << optimizer.activeRobustChi2() << std::endl;
   if (!statsFile.empty()) {
+    std::cerr << "writing stats to file \"" << statsFile << "\" ... ";      // g2o.cpp:655-663: one G2OBatchStatistics line per iteration
     std::ofstream os(statsFile);
-    for (const G2OBatchStatistics& s : optimizer.batchStatistics())
-      os << "iteration= " << s.iteration << "; numVertices= " << s.numVertices << "; numEdges= " << s.numEdges << "; chi2= " << std::setprecision(17) << s.chi2
-         << "; levenbergIterations= " << s.levenbergIterations << "; iterationsLinearSolver= " << s.iterationsLinearSolver << "; timeIteration= " << s.timeIteration << std::endl;
+    for (const G2OBatchStatistics& s : optimizer.batchStatistics()) os << s << std::endl;
+    std::cerr << "done." << std::endl;
   }
   if (!outputFile.empty() && !bal) { std::ofstream ofs(outputFile); if (!saveG2o(ofs, optimizer)) { std::cerr << "could not write " << outputFile << std::endl; return 4; } std::cerr << "saved " << outputFile << std::endl; }
   return result > 0 || maxIterations == 0 ? 0 : 5;

@@ -75,6 +75,20 @@ bool SparseOptimizer::uploadGraph() {
   return true;
 }
 
+#define G2O_PTHING(s) #s << "= " << (st.s) << "\t "
+std::ostream& operator<<(std::ostream& os, const G2OBatchStatistics& st) {   // batch_stats.cpp:48-83, same fields in the same order
+  os << G2O_PTHING(iteration) << G2O_PTHING(numVertices) << G2O_PTHING(numEdges) << G2O_PTHING(chi2);
+  os << G2O_PTHING(timeLinearSolution) << G2O_PTHING(iterationsLinearSolver) << G2O_PTHING(timeQrDecomposition) << G2O_PTHING(timeResiduals) << G2O_PTHING(timeLinearize)
+     << G2O_PTHING(timeQuadraticForm);
+  os << G2O_PTHING(timeSchurComplement);
+  os << G2O_PTHING(timeSymbolicDecomposition) << G2O_PTHING(timeNumericDecomposition);
+  os << G2O_PTHING(timeUpdate) << G2O_PTHING(timeIteration);
+  os << G2O_PTHING(levenbergIterations) << G2O_PTHING(timeLinearSolver);
+  os << G2O_PTHING(hessianDimension) << G2O_PTHING(hessianPoseDimension) << G2O_PTHING(hessianLandmarkDimension) << G2O_PTHING(choleskyNNZ) << G2O_PTHING(timeMarginals);
+  return os;
+}
+#undef G2O_PTHING
+
 bool SparseOptimizer::initializeOptimization(int level) {
   if (_edgeList.empty()) { std::cerr << "SparseOptimizer::initializeOptimization: Attempt to initialize an empty graph" << std::endl; return false; }
   if (!uploadGraph()) return false;                                     // vertex estimates / fixed flags may have changed since the last call
@@ -83,6 +97,7 @@ bool SparseOptimizer::initializeOptimization(int level) {
   g2ocu_get_i32(_handle, "hessian_index", hidx.data(), (int64_t)hidx.size());
   for (size_t i = 0; i < _vertexList.size(); ++i) _vertexList[i]->_hessianIndex = hidx[i];
   _numActiveEdges = (size_t)g2ocu_get_i32(_handle, "active_edges", nullptr, 0);
+  _numActiveVertices = (size_t)g2ocu_get_i32(_handle, "active_vertices", nullptr, 0);
   _ivMapSize = (size_t)g2ocu_get_i32(_handle, "index_mapping", nullptr, 0);
   return _ivMapSize > 0;
 }
@@ -98,7 +113,7 @@ int SparseOptimizer::optimize(int iterations, bool online) {
   OptimizationAlgorithm::SolverResult result = OptimizationAlgorithm::OK;
   for (int i = 0; i < iterations && ok; i++) {
     G2OBatchStatistics local; _currentStats = _computeBatchStatistics ? &_batchStatistics[i] : &local;
-    _currentStats->iteration = i; _currentStats->numEdges = (int)_numActiveEdges;
+    _currentStats->iteration = i; _currentStats->numEdges = (int)_numActiveEdges; _currentStats->numVertices = (int)_numActiveVertices;   // sparse_optimizer.cpp:399-403
     const double ts = now();
     result = _algorithm->solve(i, online);
     ok = (result == OptimizationAlgorithm::OK);

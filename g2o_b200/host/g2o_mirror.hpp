@@ -41,12 +41,15 @@ struct OptimizationAlgorithmProperty {
 
 // G2OBatchStatistics, core/batch_stats.h:40-78 (times in seconds, from CUDA events)
 struct G2OBatchStatistics {
-  int iteration = 0, numVertices = 0, numEdges = 0; number_t chi2 = 0;
+  int iteration = -1, numVertices = 0, numEdges = 0; number_t chi2 = 0;   // iteration -1: not valid yet (batch_stats.cpp:40-46)
   number_t timeResiduals = 0, timeLinearize = 0, timeQuadraticForm = 0; int levenbergIterations = 0;
   number_t timeSchurComplement = 0, timeSymbolicDecomposition = 0, timeNumericDecomposition = 0, timeLinearSolution = 0, timeLinearSolver = 0;
+  number_t timeQrDecomposition = 0;                                       // the fork's JacobiSolver field; always 0 here
   int iterationsLinearSolver = 0; number_t timeUpdate = 0, timeIteration = 0, timeMarginals = 0;
   size_t hessianDimension = 0, hessianPoseDimension = 0, hessianLandmarkDimension = 0, choleskyNNZ = 0;
 };
+// one line per iteration, "name= value\t " in the reference's field order (batch_stats.cpp:48-83); what `g2o -stats file` writes
+std::ostream& operator<<(std::ostream& os, const G2OBatchStatistics& st);
 typedef std::vector<G2OBatchStatistics> BatchStatisticsContainer;
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -224,6 +227,7 @@ class SparseOptimizer : public OptimizableGraph {
   void setComputeBatchStatistics(bool b) { _computeBatchStatistics = b; }
   const BatchStatisticsContainer& batchStatistics() const { return _batchStatistics; }
   size_t activeEdgeCount() const { return _numActiveEdges; }
+  size_t activeVertexCount() const { return _numActiveVertices; }
   size_t indexMappingSize() const { return _ivMapSize; }
   void pullEstimates();                      // device -> host vertices
   g2ocu_solver* handle() const { return _handle; }
@@ -234,7 +238,7 @@ class SparseOptimizer : public OptimizableGraph {
   OptimizationAlgorithm* _algorithm = nullptr;
   g2ocu_solver* _handle = nullptr;
   bool _graphDirty = true, _verbose = false, _computeBatchStatistics = false;
-  size_t _numActiveEdges = 0, _ivMapSize = 0;
+  size_t _numActiveEdges = 0, _numActiveVertices = 0, _ivMapSize = 0;
   BatchStatisticsContainer _batchStatistics; G2OBatchStatistics* _currentStats = nullptr;
 };
 

@@ -28,3 +28,27 @@ def test_reference_unit_tests_in_cpp():
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "HOST_TESTS_OK" in out.stdout
+
+
+def test_batch_statistics_line_has_the_reference_format(tmp_path):
+    """`g2o -stats file` writes one `operator<<(G2OBatchStatistics)` line per iteration: "name= value\\t " for 22 fields in a fixed
+    order (core/batch_stats.cpp:48-83); scripts that parse those files must keep working with the mirror's stream operator."""
+    src = tmp_path / "stats.cpp"
+    src.write_text('#include <iostream>\n#include "g2o_mirror.hpp"\n'
+                   'int main() { g2o::G2OBatchStatistics s; std::cout << s << std::endl; s.iteration = 3; s.numVertices = 7; s.numEdges = 9; s.chi2 = 1.5;\n'
+                   '  s.levenbergIterations = 2; s.iterationsLinearSolver = 11; s.hessianPoseDimension = 12; s.hessianLandmarkDimension = 30; s.hessianDimension = 42; std::cout << s << std::endl; }\n')
+    exe = tmp_path / "stats"
+    host = os.path.join(os.path.dirname(LIBDIR), "host")
+    subprocess.run(["g++", "-std=c++17", "-I", host, str(src), "-o", str(exe), "-L", LIBDIR, "-lg2o_solver_cuda", "-lg2ocu", f"-Wl,-rpath,{LIBDIR}"], check=True)
+    lines = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+    order = ["iteration", "numVertices", "numEdges", "chi2", "timeLinearSolution", "iterationsLinearSolver", "timeQrDecomposition", "timeResiduals",
+             "timeLinearize", "timeQuadraticForm", "timeSchurComplement", "timeSymbolicDecomposition", "timeNumericDecomposition", "timeUpdate",
+             "timeIteration", "levenbergIterations", "timeLinearSolver", "hessianDimension", "hessianPoseDimension", "hessianLandmarkDimension",
+             "choleskyNNZ", "timeMarginals"]
+    for line, want in zip(lines, [{"iteration": "-1"}, {"iteration": "3", "numVertices": "7", "numEdges": "9", "chi2": "1.5", "levenbergIterations": "2",
+                                                        "iterationsLinearSolver": "11", "hessianDimension": "42", "hessianPoseDimension": "12", "hessianLandmarkDimension": "30"}]):
+        fields = [f for f in line.split("\t ") if f]
+        assert [f.split("= ")[0] for f in fields] == order
+        got = dict(f.split("= ") for f in fields)
+        for k in order:
+            assert got[k] == want.get(k, "0"), (k, got[k])
