@@ -148,3 +148,19 @@ def test_every_algorithm_fails_loudly_without_a_device():
     import ctypes
     rc = s._L.g2ocu_solver_iteration(s._h, 7, 0, None)      # unknown algorithm code
     assert rc < 0
+
+
+def test_sharded_handles_reject_what_they_cannot_do():
+    """Dogleg and graphs whose points are not marginalized run on single-GPU handles only; a sharded handle says so instead of
+    computing something else (checked before any device work, so this runs without a GPU)."""
+    hook = lambda buf, count, op, stream: 0
+    g = W.slam2d(n_poses=60, n_landmarks=20, world_size=10.0, marginalize_landmarks=False)
+    s = CudaSolver(g, "lm_var_cuda"); s.set_shard(0, 2, hook); s.initialize_optimization()
+    with pytest.raises(G2oCudaError) as ei:
+        s.build_structure()
+    assert ei.value.code == _lib.E_UNSUPPORTED and "not marginalized" in str(ei.value)
+    g = W.sphere(nodes_per_level=6, laps=3)
+    s = CudaSolver(g, "dl_var_cuda"); s.set_shard(1, 2, hook); s.initialize_optimization()
+    with pytest.raises(G2oCudaError) as ei:
+        s.optimize(1)
+    assert ei.value.code == _lib.E_UNSUPPORTED and "Dogleg" in str(ei.value)
