@@ -11,9 +11,10 @@
 //
 // Parity pin status: the per-edge Jacobians, dq_dR and the two tiny LM problems are pinned by the
 // reference's own unit-test properties (unit_test/slam3d/jacobians_slam3d.cpp, slam2d/jacobians_slam2d.cpp,
-// slam3d/optimization_slam3d.cpp) re-run against this file in tests/test_oracle_*.py.  The reference holds
-// no golden vectors for Schur / PCG / BA chi2 trajectories ("parity unpinned" there); those
-// parts are cross-checked against independent numpy/scipy dense solves in the same tests.
+// slam3d/optimization_slam3d.cpp) re-run against this file in tests/test_oracle_*.py; the robust kernels, dq_dR and
+// normalize_theta additionally against the reference's own translation units compiled into oracle/_ref/libg2o_ref_leaves.so
+// (tests/test_reference_leaves.py).  The reference holds no golden vectors for Schur / PCG / Dogleg / BA chi2 trajectories
+// ("parity unpinned" there); those parts are cross-checked against independent numpy/scipy restatements in the same tests.
 #include "orc_types.hpp"
 #include <vector>
 #include <map>

@@ -25,7 +25,8 @@ def build(force: bool = False) -> None:
     so = os.path.join(_HERE, "liboracle.so")
     srcs = [os.path.join(_HERE, f) for f in ("g2o_oracle.cpp", "orc_types.hpp", "orc_math.hpp")]
     stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
-    need_ref = os.path.isdir("/root/reference/EXTERNAL/csparse") and not os.path.exists(os.path.join(_HERE, "_ref", "libcsparse_ref.so"))
+    need_ref = os.path.isdir("/root/reference/EXTERNAL/csparse") and not all(
+        os.path.exists(os.path.join(_HERE, "_ref", f)) for f in ("libcsparse_ref.so", "libg2o_ref_leaves.so"))
     if stale or need_ref:
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
 
@@ -72,6 +73,28 @@ def lib() -> ctypes.CDLL:
         L._has_csparse = bool(os.path.exists(ref) and L.orc_load_csparse(ref.encode()))
         _LIB = L
     return _LIB
+
+
+_LEAVES = None
+
+
+def reference_leaves():
+    """ctypes handle of oracle/_ref/libg2o_ref_leaves.so - leaf functions of the REAL reference (robust kernels, dq/dR, normalize_theta)
+    compiled from /root/reference by oracle/Makefile - or None when it was not built (no reference tree at build time)."""
+    global _LEAVES
+    if _LEAVES is None:
+        so = os.path.join(_HERE, "_ref", "libg2o_ref_leaves.so")
+        if not os.path.exists(so):
+            return None
+        L = ctypes.CDLL(so)
+        L.ref_robustify.argtypes = [ctypes.c_char_p, ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
+        L.ref_robustify.restype = ctypes.c_int
+        L.ref_dq_dR.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.ref_dq_dR.restype = None
+        L.ref_normalize_theta.argtypes = [ctypes.c_double]
+        L.ref_normalize_theta.restype = ctypes.c_double
+        _LEAVES = L
+    return _LEAVES
 
 
 def has_csparse() -> bool:

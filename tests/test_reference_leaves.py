@@ -1,0 +1,59 @@
+"""Leaf functions of the REAL reference, compiled from /root/reference into oracle/_ref/libg2o_ref_leaves.so (oracle/Makefile: the
+translation units use Eigen only as a typed array and build against a declaration shim), against the oracle's restatements:
+the nine robust kernels (g2o/core/robust_kernel_impl.cpp:50-181), dq/dR of EdgeSE3's Jacobian (g2o/types/slam3d/dquat2mat.cpp:35-85 and
+the generated dquat2mat_maxima_generated.cpp), normalize_theta (g2o/stuff/misc.h:114-127).  These pin parts of the oracle that the
+reference's own unit tests do not cover."""
+import ctypes
+
+import numpy as np
+import pytest
+from scipy.spatial.transform import Rotation
+
+from g2o_b200 import graph as G
+from oracle import oracle
+
+REF = oracle.reference_leaves()
+pytestmark = pytest.mark.skipif(REF is None, reason="oracle/_ref/libg2o_ref_leaves.so was not built (no reference tree at build time)")
+
+
+def ref_robustify(name, delta, e2):
+    rho = np.zeros(3)
+    assert REF.ref_robustify(name.encode(), delta, e2, rho.ctypes.data_as(ctypes.c_void_p)) == 0, name
+    return rho
+
+
+@pytest.mark.parametrize("name", [n for n in G.KERNEL_BY_NAME if n])
+def test_robust_kernels_match_the_reference_code(name):
+    kind = G.KERNEL_BY_NAME[name]
+    rng = np.random.default_rng(kind)
+    for delta in (0.3, 1.0, 2.5):
+        e2s = np.concatenate([[0.0, 1e-12, delta * delta, delta * delta * (1 + 1e-12), delta * delta * (1 - 1e-12)], rng.uniform(0, 4 * delta * delta, 40), rng.uniform(0, 400, 20)])
+        for e2 in e2s:
+            want, got = ref_robustify(name, delta, float(e2)), oracle.robustify(kind, delta, float(e2))
+            assert np.allclose(got, want, rtol=2e-15, atol=0.0), (name, delta, e2, got, want)   # a few ulps: the oracle is built with FMA contraction
+
+
+def test_unknown_kernel_name_is_unknown_to_the_reference_too():
+    assert REF.ref_robustify(b"NoSuchKernel", 1.0, 1.0, np.zeros(3).ctypes.data_as(ctypes.c_void_p)) == -1
+
+
+def test_dq_dR_matches_the_generated_reference_code():
+    rng = np.random.default_rng(7)
+    seen = set()
+    mats = [Rotation.from_rotvec(v).as_matrix() for v in rng.normal(size=(200, 3)) * rng.uniform(0.05, 3.1, size=(200, 1))]
+    mats += [Rotation.from_rotvec(np.pi * 0.999 * np.eye(3)[k]).as_matrix() for k in range(3)]      # trace < 0: the x / y / z branches
+    for R in mats:
+        R9 = np.asfortranarray(R).ravel(order="F").copy()
+        want = np.zeros(27); REF.ref_dq_dR(R9.ctypes.data_as(ctypes.c_void_p), want.ctypes.data_as(ctypes.c_void_p))
+        got = oracle.dq_dR(R)                 # 3 x 9
+        tr = np.trace(R)
+        seen.add(0 if tr > 0 else (1 if (R[0, 0] > R[1, 1] and R[0, 0] > R[2, 2]) else (2 if R[1, 1] > R[2, 2] else 3)))
+        assert np.allclose(got, want.reshape(9, 3).T, rtol=1e-14, atol=1e-15), np.max(np.abs(got - want.reshape(9, 3).T))
+    assert seen == {0, 1, 2, 3}
+
+
+def test_normalize_theta_matches_the_reference_code():
+    rng = np.random.default_rng(11)
+    for th in np.concatenate([rng.uniform(-20, 20, 200), [np.pi, -np.pi, 3 * np.pi, -3 * np.pi, 0.0, 2 * np.pi]]):
+        est, _ = oracle.vertex_oplus(G.VERTEX_SE2, [0.0, 0.0, 0.0], [0.0, 0.0, float(th)])
+        assert est[2] == REF.ref_normalize_theta(float(th)), th
