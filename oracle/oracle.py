@@ -93,6 +93,8 @@ def reference_leaves():
         L.ref_dq_dR.restype = None
         L.ref_normalize_theta.argtypes = [ctypes.c_double]
         L.ref_normalize_theta.restype = ctypes.c_double
+        L.ref_sample_gaussian_two_engines.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.ref_sample_gaussian_two_engines.restype = None
         _LEAVES = L
     return _LEAVES
 

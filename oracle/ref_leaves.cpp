@@ -3,12 +3,14 @@
 //   robust kernels  g2o/core/robust_kernel_impl.cpp:50-181, constructed by name through the reference's own RobustKernelFactory
 //   dq/dR           g2o/types/slam3d/dquat2mat.cpp:35-85 + dquat2mat_maxima_generated.cpp
 //   normalize_theta g2o/stuff/misc.h:114-127
+//   sampleGaussian  g2o/stuff/sampler.cpp:31-45 (one static std::normal_distribution shared by every engine - the noise source of create_sphere)
 // tests/test_reference_leaves.py checks the oracle's restatements (and, on the GPU, the device functions through them) against these.
 #include <cstring>
 
 #include "g2o/core/robust_kernel.h"
 #include "g2o/core/robust_kernel_factory.h"
 #include "g2o/stuff/misc.h"
+#include "g2o/stuff/sampler.h"
 #include "g2o/types/slam3d/dquat2mat.h"
 
 extern "C" {
@@ -35,5 +37,13 @@ void ref_dq_dR(const double* R9, double* out27) {
 }
 
 double ref_normalize_theta(double theta) { return g2o::normalize_theta(theta); }
+
+// out[i] = sampleGaussian(&engine[which[i]]) for two default-seeded std::mt19937 engines, as the two GaussianSampler objects of
+// create_sphere.cpp:117-132 hold them (GaussianSampler() : _generator(new std::mt19937), stuff/sampler.h:47-56).  The static
+// distribution inside sampler.cpp keeps its saved value across calls and across engines; call once per process for a clean sequence.
+void ref_sample_gaussian_two_engines(const int* which, int n, double* out) {
+  std::mt19937 engine[2];
+  for (int i = 0; i < n; ++i) out[i] = g2o::sampleGaussian(&engine[which[i] & 1]);
+}
 
 }  // extern "C"

@@ -57,3 +57,31 @@ def test_normalize_theta_matches_the_reference_code():
     for th in np.concatenate([rng.uniform(-20, 20, 200), [np.pi, -np.pi, 3 * np.pi, -3 * np.pi, 0.0, 2 * np.pi]]):
         est, _ = oracle.vertex_oplus(G.VERTEX_SE2, [0.0, 0.0, 0.0], [0.0, 0.0, float(th)])
         assert est[2] == REF.ref_normalize_theta(float(th)), th
+
+
+def test_sphere_noise_stream_matches_the_reference_sampler():
+    """create_sphere draws its measurement noise from two default-seeded std::mt19937 engines through ONE static
+    std::normal_distribution (g2o/stuff/sampler.cpp:31-45), whose saved value crosses between the engines: per edge three rotation draws
+    (engine 1), then three translation draws (engine 0) (create_sphere.cpp:175,183).  g2o_b200/workloads.py restates libstdc++'s
+    distribution and generate_canonical in Python; here the same call pattern runs through the reference's own sampleGaussian, in a fresh
+    process because the static distribution keeps state."""
+    import subprocess, sys, json
+    n_edges = 500
+    code = ("import ctypes, json, numpy as np\n"
+            "from oracle import oracle\n"
+            "L = oracle.reference_leaves()\n"
+            f"which = np.array(([1, 1, 1, 0, 0, 0] * {n_edges}), dtype=np.int32); out = np.zeros(which.size)\n"
+            "L.ref_sample_gaussian_two_engines(which.ctypes.data_as(ctypes.c_void_p), which.size, out.ctypes.data_as(ctypes.c_void_p))\n"
+            "print(json.dumps([float.hex(float(v)) for v in out]))\n")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=120)
+    assert r.returncode == 0, r.stderr
+    want = np.array([float.fromhex(h) for h in json.loads(r.stdout)])
+    from g2o_b200.workloads import _StdNormalShared
+    nd = _StdNormalShared(); gen_trans, gen_rot = nd.engine(), nd.engine()
+    got = []
+    for _ in range(n_edges):
+        got += [nd(gen_rot) for _ in range(3)]
+        got += [nd(gen_trans) for _ in range(3)]
+    assert np.array_equal(np.array(got), want)      # bit for bit
