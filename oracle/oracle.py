@@ -93,6 +93,11 @@ def reference_leaves():
         L.ref_dq_dR.restype = None
         L.ref_normalize_theta.argtypes = [ctypes.c_double]
         L.ref_normalize_theta.restype = ctypes.c_double
+        for f in ("ref_edge_se2_error", "ref_edge_se2_pointxy_error"):
+            getattr(L, f).argtypes = [ctypes.c_void_p] * 4
+            getattr(L, f).restype = None
+        L.ref_vertex_se2_oplus.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.ref_vertex_se2_oplus.restype = None
         L.ref_sample_gaussian_two_engines.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.ref_sample_gaussian_two_engines.restype = None
         _LEAVES = L

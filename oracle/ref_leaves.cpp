@@ -3,6 +3,8 @@
 //   robust kernels  g2o/core/robust_kernel_impl.cpp:50-181, constructed by name through the reference's own RobustKernelFactory
 //   dq/dR           g2o/types/slam3d/dquat2mat.cpp:35-85 + dquat2mat_maxima_generated.cpp
 //   normalize_theta g2o/stuff/misc.h:114-127
+//   SE2             g2o/types/slam2d/se2.h:39-131 (header only): composition, inverse and the places where the angle is normalised; the edge /
+//                   vertex bodies that call it are restated below from edge_se2.h:45-52, edge_se2_pointxy.h:45-50, vertex_se2.h:51-58
 //   sampleGaussian  g2o/stuff/sampler.cpp:31-45 (one static std::normal_distribution shared by every engine - the noise source of create_sphere)
 // tests/test_reference_leaves.py checks the oracle's restatements (and, on the GPU, the device functions through them) against these.
 #include <cstring>
@@ -11,6 +13,7 @@
 #include "g2o/core/robust_kernel_factory.h"
 #include "g2o/stuff/misc.h"
 #include "g2o/stuff/sampler.h"
+#include "g2o/types/slam2d/se2.h"
 #include "g2o/types/slam3d/dquat2mat.h"
 
 extern "C" {
@@ -37,6 +40,31 @@ void ref_dq_dR(const double* R9, double* out27) {
 }
 
 double ref_normalize_theta(double theta) { return g2o::normalize_theta(theta); }
+
+// EdgeSE2::computeError (edge_se2.h:45-52) with setMeasurementData (:61-65): x0, x1, z = (x, y, theta)
+void ref_edge_se2_error(const double* x0, const double* x1, const double* z, double* e) {
+  const g2o::SE2 v1(x0[0], x0[1], x0[2]), v2(x1[0], x1[1], x1[2]), measurement(z[0], z[1], z[2]);
+  const g2o::SE2 inverseMeasurement = measurement.inverse();
+  g2o::SE2 delta = inverseMeasurement * (v1.inverse() * v2);
+  const g2o::Vector3 error = delta.toVector();
+  e[0] = error[0]; e[1] = error[1]; e[2] = error[2];
+}
+// EdgeSE2PointXY::computeError (edge_se2_pointxy.h:45-50)
+void ref_edge_se2_pointxy_error(const double* x0, const double* l, const double* z, double* e) {
+  const g2o::SE2 v1(x0[0], x0[1], x0[2]);
+  const g2o::Vector2 error = (v1.inverse() * g2o::Vector2(l[0], l[1])) - g2o::Vector2(z[0], z[1]);
+  e[0] = error[0]; e[1] = error[1];
+}
+// VertexSE2::oplusImpl (vertex_se2.h:51-58)
+void ref_vertex_se2_oplus(double* est, const double* update) {
+  g2o::SE2 estimate(est[0], est[1], est[2]);
+  g2o::Vector2 t = estimate.translation();
+  t += g2o::Vector2(update[0], update[1]);
+  const number_t angle = g2o::normalize_theta(estimate.rotation().angle() + update[2]);
+  estimate.setTranslation(t);
+  estimate.setRotation(g2o::Rotation2D(angle));
+  est[0] = estimate[0]; est[1] = estimate[1]; est[2] = estimate[2];
+}
 
 // out[i] = sampleGaussian(&engine[which[i]]) for two default-seeded std::mt19937 engines, as the two GaussianSampler objects of
 // create_sphere.cpp:117-132 hold them (GaussianSampler() : _generator(new std::mt19937), stuff/sampler.h:47-56).  The static

@@ -85,3 +85,34 @@ def test_sphere_noise_stream_matches_the_reference_sampler():
         got += [nd(gen_rot) for _ in range(3)]
         got += [nd(gen_trans) for _ in range(3)]
     assert np.array_equal(np.array(got), want)      # bit for bit
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_se2_edges_and_oplus_match_the_reference_se2_class():
+    """EdgeSE2 / EdgeSE2PointXY errors and VertexSE2::oplusImpl evaluated with the reference's own SE2 class (g2o/types/slam2d/se2.h: where the
+    angle is normalised in operator*= and inverse()) against the oracle, including angles around +-pi where the normalisation matters."""
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for k in range(400):
+        big = 1.0 if k % 4 else 30.0        # some poses far outside [-pi, pi)
+        x0 = np.array([*rng.normal(size=2) * 5, rng.uniform(-np.pi, np.pi) * big]); x1 = np.array([*rng.normal(size=2) * 5, rng.uniform(-np.pi, np.pi) * big])
+        z = np.array([*rng.normal(size=2), rng.uniform(-np.pi, np.pi)])
+        if k % 7 == 0:                      # relative rotation next to the +-pi cut
+            x1[2] = x0[2] + z[2] + np.pi - 1e-9 * (k % 3 - 1)
+        want = np.zeros(3); REF.ref_edge_se2_error(_p(x0), _p(x1), _p(z), _p(want))
+        got = oracle.edge_error(G.EDGE_SE2, x0, x1, z)
+        # the angle may sit on either side of the cut only if both are within rounding of it; compare on the circle
+        d = got - want; d[2] = (d[2] + np.pi) % (2 * np.pi) - np.pi
+        worst = max(worst, float(np.max(np.abs(d))))
+        assert np.max(np.abs(d)) <= 1e-12 * (1 + np.max(np.abs(want))), (x0, x1, z, got, want)
+        l, zl = rng.normal(size=2) * 5, rng.normal(size=2)
+        want2 = np.zeros(2); REF.ref_edge_se2_pointxy_error(_p(x0), _p(l), _p(zl), _p(want2))
+        assert np.allclose(oracle.edge_error(G.EDGE_SE2_POINT_XY, x0, l, zl), want2, rtol=1e-13, atol=1e-13)
+        upd = np.array([*rng.normal(size=2), rng.uniform(-4, 4)])
+        est = x0.copy(); REF.ref_vertex_se2_oplus(_p(est), _p(upd))
+        got3, _ = oracle.vertex_oplus(G.VERTEX_SE2, x0, upd)
+        assert np.allclose(got3, est, rtol=0, atol=1e-13), (x0, upd, got3, est)   # exact up to the FMA contraction the oracle is built with
+    assert worst < 1e-12
