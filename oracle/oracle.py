@@ -98,6 +98,9 @@ def reference_leaves():
             getattr(L, f).restype = None
         L.ref_vertex_se2_oplus.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.ref_vertex_se2_oplus.restype = None
+        for f, n in (("ref_se3quat_exp", 2), ("ref_se3quat_log", 2), ("ref_vertex_se3expmap_oplus", 2), ("ref_edge_se3expmap", 6), ("ref_edge_project_xyz2uv_error", 5)):
+            getattr(L, f).argtypes = [ctypes.c_void_p] * n
+            getattr(L, f).restype = None
         L.ref_sample_gaussian_two_engines.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.ref_sample_gaussian_two_engines.restype = None
         _LEAVES = L

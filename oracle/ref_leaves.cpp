@@ -5,6 +5,8 @@
 //   normalize_theta g2o/stuff/misc.h:114-127
 //   SE2             g2o/types/slam2d/se2.h:39-131 (header only): composition, inverse and the places where the angle is normalised; the edge /
 //                   vertex bodies that call it are restated below from edge_se2.h:45-52, edge_se2_pointxy.h:45-50, vertex_se2.h:51-58
+//   SE3Quat         g2o/types/slam3d/se3quat.h:37-290 + se3_ops.hpp:27-85 (header only): exp, log, adj, product, inverse, map; the bodies that call
+//                   them are restated below from sba/types_six_dof_expmap.h:98-101,117-124, .cpp:74-80,278-293
 //   sampleGaussian  g2o/stuff/sampler.cpp:31-45 (one static std::normal_distribution shared by every engine - the noise source of create_sphere)
 // tests/test_reference_leaves.py checks the oracle's restatements (and, on the GPU, the device functions through them) against these.
 #include <cstring>
@@ -15,6 +17,7 @@
 #include "g2o/stuff/sampler.h"
 #include "g2o/types/slam2d/se2.h"
 #include "g2o/types/slam3d/dquat2mat.h"
+#include "g2o/types/slam3d/se3quat.h"
 
 extern "C" {
 
@@ -64,6 +67,35 @@ void ref_vertex_se2_oplus(double* est, const double* update) {
   estimate.setTranslation(t);
   estimate.setRotation(g2o::Rotation2D(angle));
   est[0] = estimate[0]; est[1] = estimate[1]; est[2] = estimate[2];
+}
+
+static g2o::SE3Quat se3FromVector7(const double* v) { g2o::Vector7 a; for (int i = 0; i < 7; ++i) a[i] = v[i]; g2o::SE3Quat T; T.fromVector(a); return T; }
+static void se3ToVector7(const g2o::SE3Quat& T, double* v) { const g2o::Vector7 a = T.toVector(); for (int i = 0; i < 7; ++i) v[i] = a[i]; }
+// SE3Quat::exp (se3quat.h:218-257) and log (:173-209); 7-vectors are (t, qx, qy, qz, qw)
+void ref_se3quat_exp(const double* u6, double* v7) { g2o::Vector6 u; for (int i = 0; i < 6; ++i) u[i] = u6[i]; se3ToVector7(g2o::SE3Quat::exp(u), v7); }
+void ref_se3quat_log(const double* v7, double* u6) { const g2o::Vector6 u = se3FromVector7(v7).log(); for (int i = 0; i < 6; ++i) u6[i] = u[i]; }
+// VertexSE3Expmap::oplusImpl (types_six_dof_expmap.h:98-101)
+void ref_vertex_se3expmap_oplus(double* est7, const double* update6) {
+  g2o::Vector6 update; for (int i = 0; i < 6; ++i) update[i] = update6[i];
+  se3ToVector7(g2o::SE3Quat::exp(update) * se3FromVector7(est7), est7);
+}
+// EdgeSE3Expmap::computeError (types_six_dof_expmap.h:117-124) and linearizeOplus (.cpp:278-293); J0, J1 6 x 6 column-major
+void ref_edge_se3expmap(const double* x0, const double* x1, const double* z, double* e6, double* J0, double* J1) {
+  const g2o::SE3Quat v1 = se3FromVector7(x0), v2 = se3FromVector7(x1), C = se3FromVector7(z);
+  g2o::SE3Quat error_ = v2.inverse() * C * v1;
+  const g2o::Vector6 e = error_.log();
+  for (int i = 0; i < 6; ++i) e6[i] = e[i];
+  const g2o::SE3Quat invTij = C.inverse();
+  const g2o::SE3Quat invTj_Tij = v2.inverse() * C, infTi_invTij = v1.inverse() * invTij;
+  const Eigen::Matrix<number_t, 6, 6, Eigen::ColMajor> A = invTj_Tij.adj(), B = infTi_invTij.adj();
+  for (int i = 0; i < 36; ++i) { J0[i] = A.data()[i]; J1[i] = -B.data()[i]; }
+}
+// EdgeProjectXYZ2UV::computeError (types_six_dof_expmap.h:140-147) with CameraParameters::cam_map (.cpp:74-80); prm = (f, cx, cy)
+void ref_edge_project_xyz2uv_error(const double* X, const double* T7, const double* obs, const double* prm, double* e2) {
+  const g2o::Vector3 trans_xyz = se3FromVector7(T7).map(g2o::Vector3(X[0], X[1], X[2]));
+  const g2o::Vector2 proj = g2o::project(trans_xyz);
+  e2[0] = obs[0] - (proj[0] * prm[0] + prm[1]);
+  e2[1] = obs[1] - (proj[1] * prm[0] + prm[2]);
 }
 
 // out[i] = sampleGaussian(&engine[which[i]]) for two default-seeded std::mt19937 engines, as the two GaussianSampler objects of

@@ -116,3 +116,44 @@ def test_se2_edges_and_oplus_match_the_reference_se2_class():
         got3, _ = oracle.vertex_oplus(G.VERTEX_SE2, x0, upd)
         assert np.allclose(got3, est, rtol=0, atol=1e-13), (x0, upd, got3, est)   # exact up to the FMA contraction the oracle is built with
     assert worst < 1e-12
+
+
+def _rand_se3(rng, angle_scale=1.0):
+    q = Rotation.from_rotvec(rng.normal(size=3) * angle_scale).as_quat()      # x y z w
+    if q[3] < 0:
+        q = -q
+    return np.concatenate([rng.normal(size=3) * 3, q])
+
+
+def test_se3quat_exp_log_edges_and_oplus_match_the_reference_class():
+    """SE3Quat::exp / log / adj / product / inverse / map of the reference (g2o/types/slam3d/se3quat.h, compiled) under VertexSE3Expmap::oplusImpl,
+    EdgeSE3Expmap::computeError + linearizeOplus and EdgeProjectXYZ2UV::computeError, against the oracle; both branches of exp (theta < 1e-5)
+    and log (d > 0.99999) are visited."""
+    rng = np.random.default_rng(9)
+    for k in range(300):
+        scale = [1.0, 1e-3, 1e-7, 2.5][k % 4]
+        u = np.concatenate([rng.normal(size=3) * scale, rng.normal(size=3)])
+        want = np.zeros(7); REF.ref_se3quat_exp(_p(u), _p(want))
+        assert np.allclose(oracle.se3_exp(u), want, rtol=0, atol=1e-14), (u, oracle.se3_exp(u), want)
+        T = _rand_se3(rng, scale)
+        wl = np.zeros(6); REF.ref_se3quat_log(_p(T), _p(wl))
+        assert np.allclose(oracle.se3_log(T), wl, rtol=1e-9, atol=1e-13), (T, oracle.se3_log(T), wl)     # acos near d = 1 amplifies rounding
+        est = _rand_se3(rng); upd = np.concatenate([rng.normal(size=3) * scale, rng.normal(size=3) * 0.1])
+        e2 = est.copy(); REF.ref_vertex_se3expmap_oplus(_p(e2), _p(upd))
+        got, _ = oracle.vertex_oplus(G.VERTEX_SE3_EXPMAP, est, upd)
+        assert np.allclose(got, e2, rtol=0, atol=1e-13), (est, upd, got, e2)
+        x0, x1, z = _rand_se3(rng), _rand_se3(rng), _rand_se3(rng)
+        if k % 3 == 0:
+            # measurement consistent with the poses up to a tiny perturbation: the error lands in the small-angle branch of log
+            R0, R1 = Rotation.from_quat(x0[3:]), Rotation.from_quat(x1[3:])
+            Rz = R1 * R0.inv() * Rotation.from_rotvec(rng.normal(size=3) * 1e-4)
+            q = Rz.as_quat(); q = -q if q[3] < 0 else q
+            z = np.concatenate([x1[:3] - Rz.apply(x0[:3]) + rng.normal(size=3) * 1e-3, q])
+        we, wJ0, wJ1 = np.zeros(6), np.zeros(36), np.zeros(36)
+        REF.ref_edge_se3expmap(_p(x0), _p(x1), _p(z), _p(we), _p(wJ0), _p(wJ1))
+        assert np.allclose(oracle.edge_error(G.EDGE_SE3_EXPMAP, x0, x1, z), we, rtol=1e-9, atol=1e-12), (x0, x1, z)
+        J0, J1 = oracle.edge_jacobian(G.EDGE_SE3_EXPMAP, x0, x1, z)
+        assert np.allclose(J0, wJ0.reshape(6, 6, order="F"), rtol=0, atol=1e-12) and np.allclose(J1, wJ1.reshape(6, 6, order="F"), rtol=0, atol=1e-12)
+        X = rng.normal(size=3) + np.array([0, 0, 6.0]); Tc = _rand_se3(rng, 0.1); obs = rng.normal(size=2) * 100; prm = np.array([800.0, 320.0, 240.0])
+        wp = np.zeros(2); REF.ref_edge_project_xyz2uv_error(_p(X), _p(Tc), _p(obs), _p(prm), _p(wp))
+        assert np.allclose(oracle.edge_error(G.EDGE_PROJECT_XYZ2UV, X, Tc, obs, prm), wp, rtol=1e-13, atol=1e-11)
