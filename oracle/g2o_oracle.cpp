@@ -11,9 +11,9 @@
 //
 // Parity pin status: the per-edge Jacobians, dq_dR and the two tiny LM problems are pinned by the
 // reference's own unit-test properties (unit_test/slam3d/jacobians_slam3d.cpp, slam2d/jacobians_slam2d.cpp,
-// slam3d/optimization_slam3d.cpp) re-run against this file in tests/test_oracle_*.py; the robust kernels, dq_dR and
-// normalize_theta additionally against the reference's own translation units compiled into oracle/_ref/libg2o_ref_leaves.so
-// (tests/test_reference_leaves.py).  The reference holds no golden vectors for Schur / PCG / Dogleg / BA chi2 trajectories
+// slam3d/optimization_slam3d.cpp) re-run against this file in tests/test_oracle_*.py; the robust kernels, dq_dR,
+// normalize_theta, the SE2 / SE3Quat algebra under the SE2 and SE3Expmap types and LinearSolverPCG::solve (iteration counts, _residual
+// carry-over) additionally against the reference's own code compiled into oracle/_ref/libg2o_ref_leaves.so (tests/test_reference_leaves.py).  The reference holds no golden vectors for Schur / PCG / Dogleg / BA chi2 trajectories
 // ("parity unpinned" there); those parts are cross-checked against independent numpy/scipy restatements in the same tests.
 #include "orc_types.hpp"
 #include <vector>
@@ -126,7 +126,7 @@ struct LinearSolver {
 
 // g2o/solvers/pcg/linear_solver_pcg.h:53-70, .hpp:80-197
 struct LinearSolverPCG : LinearSolver {
-  double tolerance = 1e-6, residual = -1.0; bool absoluteTolerance = true; int maxIter = -1;
+  double tolerance = 1e-6, residual = -1.0; bool absoluteTolerance = true; int maxIter = -1; int lastIterations = 0;
   std::vector<const double*> diag; std::vector<std::vector<double>> J;
   std::vector<std::pair<int,int>> indices; std::vector<const double*> sparseMat; std::vector<std::pair<int,int>> sparseDims;
   bool init() override { residual = -1.0; indices.clear(); sparseMat.clear(); sparseDims.clear(); return true; }
@@ -193,7 +193,7 @@ struct LinearSolverPCG : LinearSolver {
       double ba = dn / dold;
       for (int i = 0; i < n; ++i) d[i] = s[i] + ba*d[i];
     }
-    residual = 0.5 * dn;
+    residual = 0.5 * dn; lastIterations = iteration;
     if (g_stats) g_stats->iterationsLinearSolver = iteration;
     return true;
   }
@@ -1104,6 +1104,7 @@ const double* orc_get_f64(void* hh, const char* name, int64_t* n) {
   else if (s == "errors") for (int ei : o.activeEdges) { const Edge& e = o.edges[ei]; out.insert(out.end(), e.err, e.err + e.dim); }
   else if (s == "jacobians") for (int ei : o.activeEdges) { const Edge& e = o.edges[ei]; out.insert(out.end(), e.J0, e.J0 + e.dim*o.vertices[e.v[0]].dim); out.insert(out.end(), e.J1, e.J1 + e.dim*o.vertices[e.v[1]].dim); }
   else if (s == "lambda") out = {o.currentLambda};
+  else if (s == "pcg_state") { auto* p = dynamic_cast<LinearSolverPCG*>(o.linearSolver.get()); if (p) out = {p->residual, (double)p->lastIterations}; else { *n = -1; return nullptr; } }   // _residual, iterations of the last solve
   else if (s == "dogleg") out = {o.dlDelta, (double)o.dlLastStep, (double)o.dlLastNumTries, o.dlCurrentLambda, o.dlWasPDInAllIterations ? 1.0 : 0.0};   // trustRegion(), lastStep(), tries, damping, PD flag
   else { *n = -1; return nullptr; }
   *n = (int64_t)out.size(); return out.data();

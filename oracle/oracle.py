@@ -98,6 +98,11 @@ def reference_leaves():
             getattr(L, f).restype = None
         L.ref_vertex_se2_oplus.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.ref_vertex_se2_oplus.restype = None
+        L.ref_pcg_create.argtypes = [ctypes.c_int]; L.ref_pcg_create.restype = ctypes.c_void_p
+        L.ref_pcg_destroy.argtypes = [ctypes.c_void_p]; L.ref_pcg_destroy.restype = None
+        L.ref_pcg_init.argtypes = [ctypes.c_void_p]; L.ref_pcg_init.restype = None
+        L.ref_pcg_solve.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.ref_pcg_solve.restype = ctypes.c_int
         for f, n in (("ref_se3quat_exp", 2), ("ref_se3quat_log", 2), ("ref_vertex_se3expmap_oplus", 2), ("ref_edge_se3expmap", 6), ("ref_edge_project_xyz2uv_error", 5)):
             getattr(L, f).argtypes = [ctypes.c_void_p] * n
             getattr(L, f).restype = None

@@ -7,12 +7,17 @@
 //                   vertex bodies that call it are restated below from edge_se2.h:45-52, edge_se2_pointxy.h:45-50, vertex_se2.h:51-58
 //   SE3Quat         g2o/types/slam3d/se3quat.h:37-290 + se3_ops.hpp:27-85 (header only): exp, log, adj, product, inverse, map; the bodies that call
 //                   them are restated below from sba/types_six_dof_expmap.h:98-101,117-124, .cpp:74-80,278-293
+//   LinearSolverPCG g2o/solvers/pcg/linear_solver_pcg.h:41-113 + .hpp:27-197 over SparseBlockMatrix (g2o/core/sparse_block_matrix.h/.hpp): the solver
+//                   object lives across solves (its _residual and its cached block pointers are part of the behaviour), blocks 3x3, 6x6, 9x9 or MatrixX
 //   sampleGaussian  g2o/stuff/sampler.cpp:31-45 (one static std::normal_distribution shared by every engine - the noise source of create_sphere)
 // tests/test_reference_leaves.py checks the oracle's restatements (and, on the GPU, the device functions through them) against these.
 #include <cstring>
 
 #include "g2o/core/robust_kernel.h"
 #include "g2o/core/robust_kernel_factory.h"
+#include "g2o/core/batch_stats.h"
+#include "g2o/core/sparse_block_matrix.h"
+#include "g2o/solvers/pcg/linear_solver_pcg.h"
 #include "g2o/stuff/misc.h"
 #include "g2o/stuff/sampler.h"
 #include "g2o/types/slam2d/se2.h"
@@ -96,6 +101,61 @@ void ref_edge_project_xyz2uv_error(const double* X, const double* T7, const doub
   const g2o::Vector2 proj = g2o::project(trans_xyz);
   e2[0] = obs[0] - (proj[0] * prm[0] + prm[1]);
   e2[1] = obs[1] - (proj[1] * prm[0] + prm[2]);
+}
+
+}  // extern "C"
+
+namespace {
+struct PcgHandleBase {
+  virtual ~PcgHandleBase() {}
+  virtual int solve(int nBlocks, const int* blockIndices, const int* colptr, const int* rowidx, const double* values, const double* b, double* x,
+                    double tolerance, int maxIterations, int absoluteTolerance, int* iterations) = 0;
+  virtual void init() = 0;
+};
+template <class MatrixType> struct PcgHandle : PcgHandleBase {
+  g2o::LinearSolverPCG<MatrixType> solver;
+  std::unique_ptr<g2o::SparseBlockMatrix<MatrixType> > A;
+  PcgHandle() { solver.init(); }
+  void init() override { solver.init(); }
+  // upper-triangular block CCS (block column c: rows rowidx[colptr[c] .. colptr[c+1]), ascending), values = the blocks in that order, column-major.
+  // The matrix object is created on the first call and only refilled afterwards: BlockSolver keeps its SparseBlockMatrix for the whole
+  // optimisation and LinearSolverPCG keeps pointers to its off-diagonal blocks (linear_solver_pcg.hpp:96-99).
+  int solve(int nBlocks, const int* blockIndices, const int* colptr, const int* rowidx, const double* values, const double* b, double* x,
+            double tolerance, int maxIterations, int absoluteTolerance, int* iterations) override {
+    if (!A) A.reset(new g2o::SparseBlockMatrix<MatrixType>(blockIndices, blockIndices, nBlocks, nBlocks));
+    size_t off = 0;
+    for (int c = 0; c < nBlocks; ++c)
+      for (int k = colptr[c]; k < colptr[c + 1]; ++k) {
+        MatrixType* blk = A->block(rowidx[k], c, true);
+        const int rows = A->rowsOfBlock(rowidx[k]), cols = A->colsOfBlock(c);
+        for (int j = 0; j < cols; ++j) for (int i = 0; i < rows; ++i) (*blk)(i, j) = values[off + i + (size_t)rows * j];
+        off += (size_t)rows * cols;
+      }
+    solver.setTolerance(tolerance); solver.setMaxIterations(maxIterations); solver.setAbsoluteTolerance(absoluteTolerance != 0);
+    g2o::G2OBatchStatistics stats; g2o::G2OBatchStatistics::setGlobalStats(&stats);
+    std::vector<double> rhs(b, b + A->rows());
+    const bool ok = solver.solve(*A, x, rhs.data());
+    g2o::G2OBatchStatistics::setGlobalStats(0);
+    if (iterations) *iterations = stats.iterationsLinearSolver;
+    return ok ? 1 : 0;
+  }
+};
+}  // namespace
+
+extern "C" {
+
+// blockSize 3, 6, 9: LinearSolverPCG<Matrix<number_t, P, P>> (BlockSolver_3_2 / _6_3 / <9,3> pose blocks); anything else: LinearSolverPCG<MatrixX> (BlockSolverX)
+void* ref_pcg_create(int blockSize) {
+  if (blockSize == 3) return new PcgHandle<Eigen::Matrix<number_t, 3, 3, Eigen::ColMajor> >;
+  if (blockSize == 6) return new PcgHandle<Eigen::Matrix<number_t, 6, 6, Eigen::ColMajor> >;
+  if (blockSize == 9) return new PcgHandle<Eigen::Matrix<number_t, 9, 9, Eigen::ColMajor> >;
+  return new PcgHandle<g2o::MatrixX>;
+}
+void ref_pcg_destroy(void* h) { delete (PcgHandleBase*)h; }
+void ref_pcg_init(void* h) { ((PcgHandleBase*)h)->init(); }      // LinearSolverPCG::init(): forgets _residual and the cached blocks
+int ref_pcg_solve(void* h, int nBlocks, const int* blockIndices, const int* colptr, const int* rowidx, const double* values, const double* b, double* x,
+                  double tolerance, int maxIterations, int absoluteTolerance, int* iterations) {
+  return ((PcgHandleBase*)h)->solve(nBlocks, blockIndices, colptr, rowidx, values, b, x, tolerance, maxIterations, absoluteTolerance, iterations);
 }
 
 // out[i] = sampleGaussian(&engine[which[i]]) for two default-seeded std::mt19937 engines, as the two GaussianSampler objects of

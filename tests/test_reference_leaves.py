@@ -157,3 +157,67 @@ def test_se3quat_exp_log_edges_and_oplus_match_the_reference_class():
         X = rng.normal(size=3) + np.array([0, 0, 6.0]); Tc = _rand_se3(rng, 0.1); obs = rng.normal(size=2) * 100; prm = np.array([800.0, 320.0, 240.0])
         wp = np.zeros(2); REF.ref_edge_project_xyz2uv_error(_p(X), _p(Tc), _p(obs), _p(prm), _p(wp))
         assert np.allclose(oracle.edge_error(G.EDGE_PROJECT_XYZ2UV, X, Tc, obs, prm), wp, rtol=1e-13, atol=1e-11)
+
+
+class RefPcg:
+    """The reference's LinearSolverPCG<MatrixType> (g2o/solvers/pcg/linear_solver_pcg.hpp) over its SparseBlockMatrix, compiled; one object per optimisation."""
+
+    def __init__(self, block_size):
+        self.h = REF.ref_pcg_create(block_size)
+
+    def __del__(self):
+        REF.ref_pcg_destroy(self.h)
+
+    def solve(self, block_indices, colptr, rowidx, values, b, tol=1e-6, max_iter=-1, absolute=True):
+        bi, cp, ri = (np.ascontiguousarray(a, dtype=np.int32) for a in (block_indices, colptr, rowidx))
+        vals, rhs = np.ascontiguousarray(values, dtype=np.float64), np.ascontiguousarray(b, dtype=np.float64)
+        x = np.zeros(int(bi[-1])); it = ctypes.c_int(-1)
+        ok = REF.ref_pcg_solve(self.h, len(bi), _p(bi), _p(cp), _p(ri), _p(vals), _p(rhs), _p(x), tol, max_iter, int(absolute), ctypes.byref(it))
+        return bool(ok), x, it.value
+
+
+PCG_CASES = {
+    # name: (graph, block size handed to the reference solver; -1 = MatrixX)
+    "sphere": (lambda: __import__("g2o_b200.workloads", fromlist=["x"]).sphere(nodes_per_level=8, laps=4), 6),
+    "slam2d_schur": (lambda: __import__("g2o_b200.workloads", fromlist=["x"]).slam2d(n_poses=150, n_landmarks=50, world_size=14.0), 3),
+    "ba_demo_schur": (lambda: __import__("g2o_b200.workloads", fromlist=["x"]).ba_demo(num_cameras=8, num_points=80), 6),
+    "bal_schur": (lambda: __import__("g2o_b200.workloads", fromlist=["x"]).bal_small(), 9),
+    "slam2d_points_free": (lambda: __import__("g2o_b200.workloads", fromlist=["x"]).slam2d(n_poses=150, n_landmarks=50, world_size=14.0, marginalize_landmarks=False), -1),
+}
+
+
+@pytest.mark.parametrize("name", list(PCG_CASES))
+def test_pcg_matches_the_reference_solver(name):
+    """The oracle's restated PCG against the reference's own LinearSolverPCG::solve on the same block matrix and right-hand side: iteration
+    counts, solution, and the `_residual` carried into the next solve (three consecutive damped systems, as three LM trials would produce)."""
+    fn, bs = PCG_CASES[name]
+    g = fn()
+    o = oracle.Oracle(g, "lm", "pcg")
+    assert o.initialize_optimization() and o.algorithm_init() and o.build_structure()
+    o.compute_active_errors(); o.build_system()
+    lam = o.compute_lambda_init()
+    ref = RefPcg(bs)
+    schur = o.do_schur()
+    for trial, scale in enumerate((1.0, 10.0, 0.1)):
+        o.set_lambda(lam * scale)
+        assert o.solve()
+        x_o = o.get_f64("x"); res_o, it_o = o.get_f64("pcg_state")
+        if schur:
+            bi, cp, ri, vals, rhs = o.get_i32("pose_block_indices"), o.get_i32("hschur_colptr"), o.get_i32("hschur_rowidx"), o.get_f64("hschur_values"), o.get_f64("bschur")
+        else:
+            bi, cp, ri, vals, rhs = o.get_i32("pose_block_indices"), o.get_i32("hpp_colptr"), o.get_i32("hpp_rowidx"), o.get_f64("hpp_values"), o.get_f64("b")
+        ok, x_r, it_r = ref.solve(bi, cp, ri, vals, rhs)
+        assert ok
+        assert it_r == int(it_o), (name, trial, it_r, it_o)
+        n = len(x_r)
+        assert np.max(np.abs(x_o[:n] - x_r)) <= 1e-9 * np.max(np.abs(x_r)), (name, trial, np.max(np.abs(x_o[:n] - x_r)))
+        o.restore_diagonal()
+    # a tolerance-limited solve with the relative criterion, after LinearSolverPCG::init()
+    REF.ref_pcg_init(ref.h)
+    o2 = oracle.Oracle(g, "lm", "pcg"); o2.set_pcg_params(tol=1e-12, absolute=False)
+    assert o2.initialize_optimization() and o2.algorithm_init() and o2.build_structure()
+    o2.compute_active_errors(); o2.build_system(); o2.set_lambda(lam); assert o2.solve()
+    names = ("hschur_colptr", "hschur_rowidx", "hschur_values", "bschur") if schur else ("hpp_colptr", "hpp_rowidx", "hpp_values", "b")
+    ok, x_r, it_r = ref.solve(o2.get_i32("pose_block_indices"), o2.get_i32(names[0]), o2.get_i32(names[1]), o2.get_f64(names[2]), o2.get_f64(names[3]), tol=1e-12, absolute=False)
+    assert it_r == int(o2.get_f64("pcg_state")[1])
+    assert np.max(np.abs(o2.get_f64("x")[:len(x_r)] - x_r)) <= 1e-10 * np.max(np.abs(x_r))
