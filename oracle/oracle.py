@@ -103,6 +103,7 @@ def reference_leaves():
         L.ref_pcg_init.argtypes = [ctypes.c_void_p]; L.ref_pcg_init.restype = None
         L.ref_pcg_solve.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         L.ref_pcg_solve.restype = ctypes.c_int
+        L.ref_multiply_symmetric_upper.argtypes = [ctypes.c_void_p] * 3; L.ref_multiply_symmetric_upper.restype = None
         for f, n in (("ref_se3quat_exp", 2), ("ref_se3quat_log", 2), ("ref_vertex_se3expmap_oplus", 2), ("ref_edge_se3expmap", 6), ("ref_edge_project_xyz2uv_error", 5)):
             getattr(L, f).argtypes = [ctypes.c_void_p] * n
             getattr(L, f).restype = None

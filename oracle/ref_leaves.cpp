@@ -111,12 +111,15 @@ struct PcgHandleBase {
   virtual int solve(int nBlocks, const int* blockIndices, const int* colptr, const int* rowidx, const double* values, const double* b, double* x,
                     double tolerance, int maxIterations, int absoluteTolerance, int* iterations) = 0;
   virtual void init() = 0;
+  virtual void multiplySymmetricUpperTriangle(double* dest, const double* src) = 0;
 };
 template <class MatrixType> struct PcgHandle : PcgHandleBase {
   g2o::LinearSolverPCG<MatrixType> solver;
   std::unique_ptr<g2o::SparseBlockMatrix<MatrixType> > A;
   PcgHandle() { solver.init(); }
   void init() override { solver.init(); }
+  // SparseBlockMatrix::multiplySymmetricUpperTriangle (sparse_block_matrix.hpp:289-313) on the matrix of the last solve: dest += A src
+  void multiplySymmetricUpperTriangle(double* dest, const double* src) override { number_t* d = dest; A->multiplySymmetricUpperTriangle(d, src); }
   // upper-triangular block CCS (block column c: rows rowidx[colptr[c] .. colptr[c+1]), ascending), values = the blocks in that order, column-major.
   // The matrix object is created on the first call and only refilled afterwards: BlockSolver keeps its SparseBlockMatrix for the whole
   // optimisation and LinearSolverPCG keeps pointers to its off-diagonal blocks (linear_solver_pcg.hpp:96-99).
@@ -157,6 +160,10 @@ int ref_pcg_solve(void* h, int nBlocks, const int* blockIndices, const int* colp
                   double tolerance, int maxIterations, int absoluteTolerance, int* iterations) {
   return ((PcgHandleBase*)h)->solve(nBlocks, blockIndices, colptr, rowidx, values, b, x, tolerance, maxIterations, absoluteTolerance, iterations);
 }
+
+// dest (caller-zeroed, A.rows() doubles) += A src with the matrix handed to the last ref_pcg_solve of this handle: what
+// BlockSolver::multiplyHessian does with _Hpp (block_solver.h:146)
+void ref_multiply_symmetric_upper(void* h, double* dest, const double* src) { ((PcgHandleBase*)h)->multiplySymmetricUpperTriangle(dest, src); }
 
 // out[i] = sampleGaussian(&engine[which[i]]) for two default-seeded std::mt19937 engines, as the two GaussianSampler objects of
 // create_sphere.cpp:117-132 hold them (GaussianSampler() : _generator(new std::mt19937), stuff/sampler.h:47-56).  The static

@@ -212,6 +212,12 @@ def test_pcg_matches_the_reference_solver(name):
         n = len(x_r)
         assert np.max(np.abs(x_o[:n] - x_r)) <= 1e-9 * np.max(np.abs(x_r)), (name, trial, np.max(np.abs(x_o[:n] - x_r)))
         o.restore_diagonal()
+    if not schur:   # BlockSolver::multiplyHessian = _Hpp->multiplySymmetricUpperTriangle on the same (undamped again) matrix as the oracle's
+        ok, _, _ = ref.solve(o.get_i32("pose_block_indices"), o.get_i32("hpp_colptr"), o.get_i32("hpp_rowidx"), o.get_f64("hpp_values"), o.get_f64("b"), max_iter=0)
+        v = np.random.default_rng(2).normal(size=len(x_r)); dest = np.zeros_like(v)
+        REF.ref_multiply_symmetric_upper(ref.h, _p(dest), _p(v))
+        mine = o.multiply_hessian(v)
+        assert np.max(np.abs(mine - dest)) <= 1e-13 * np.max(np.abs(dest))
     # a tolerance-limited solve with the relative criterion, after LinearSolverPCG::init()
     REF.ref_pcg_init(ref.h)
     o2 = oracle.Oracle(g, "lm", "pcg"); o2.set_pcg_params(tol=1e-12, absolute=False)
