@@ -29,6 +29,10 @@ def build(force: bool = False) -> None:
         os.path.exists(os.path.join(_HERE, "_ref", f)) for f in ("libcsparse_ref.so", "libg2o_ref_leaves.so"))
     if stale or need_ref:
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
+    core = os.path.join(_HERE, "_ref", "libg2o_ref_core.so")
+    shim = [os.path.join(_HERE, "ref_core.cpp")] + [os.path.join(_HERE, "eigen_shim", "Eigen", f) for f in ("Core", "Geometry")]
+    if os.path.isdir("/root/reference/g2o/core") and (force or not os.path.exists(core) or any(os.path.getmtime(f) > os.path.getmtime(core) for f in shim)):
+        subprocess.run(["make", "-C", _HERE, "ref_core"], check=True, capture_output=True)   # the reference's core + slam2d types, about a minute
 
 
 def lib() -> ctypes.CDLL:
@@ -111,6 +115,73 @@ def reference_leaves():
         L.ref_sample_gaussian_two_engines.restype = None
         _LEAVES = L
     return _LEAVES
+
+
+_CORE = None
+
+
+def reference_core():
+    """ctypes handle of oracle/_ref/libg2o_ref_core.so - the REAL reference (g2o/core, BlockSolver, LM / GN / Dogleg, LinearSolverPCG, slam2d
+    types) compiled from /root/reference by `make -C oracle ref_core` - or None when it was not built."""
+    global _CORE
+    if _CORE is None:
+        so = os.path.join(_HERE, "_ref", "libg2o_ref_core.so")
+        if not os.path.exists(so):
+            return None
+        L = ctypes.CDLL(so)
+        L.refcore_create.restype = ctypes.c_void_p
+        L.refcore_create.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
+        L.refcore_destroy.argtypes = [ctypes.c_void_p]; L.refcore_destroy.restype = None
+        L.refcore_initialize_optimization.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.refcore_optimize.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        for f in ("refcore_current_lambda", "refcore_active_robust_chi2", "refcore_active_chi2"):
+            getattr(L, f).argtypes = [ctypes.c_void_p]; getattr(L, f).restype = ctypes.c_double
+        for f in ("refcore_dogleg_state", "refcore_hessian_index", "refcore_estimates"):
+            getattr(L, f).argtypes = [ctypes.c_void_p, ctypes.c_void_p]; getattr(L, f).restype = None
+        _CORE = L
+    return _CORE
+
+
+class ReferenceG2o:
+    """The real reference on a 2-D SLAM graph: ``g2o::SparseOptimizer`` + ``BlockSolver`` (``"3_2"`` or ``"var"``) + ``LinearSolverPCG`` +
+    Levenberg / Gauss-Newton / Dogleg, through oracle/ref_core.cpp."""
+
+    def __init__(self, graph, algorithm: str = "lm", block_solver: str = "3_2"):
+        self._L = reference_core()
+        if self._L is None:
+            raise RuntimeError("oracle/_ref/libg2o_ref_core.so has not been built")
+        self.graph = graph
+        cg = graph.as_c()
+        self._h = self._L.refcore_create(ctypes.byref(cg), algorithm.encode(), block_solver.encode())
+        if not self._h:
+            raise ValueError("the reference library was built with the slam2d types only / unknown solver")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.refcore_destroy(self._h)
+            self._h = None
+
+    def initialize_optimization(self, level: int = 0) -> bool:
+        return bool(self._L.refcore_initialize_optimization(self._h, level))
+
+    def optimize(self, iterations: int):
+        buf = np.zeros((max(iterations, 1), 6))
+        n = self._L.refcore_optimize(self._h, iterations, _dp(buf))
+        keys = ("chi2", "levenbergIterations", "iterationsLinearSolver", "hessianPoseDimension", "hessianLandmarkDimension", "iteration")
+        return n, [dict(zip(keys, row)) for row in buf[:max(n, 0)]]
+
+    def current_lambda(self) -> float: return self._L.refcore_current_lambda(self._h)
+    def active_robust_chi2(self) -> float: return self._L.refcore_active_robust_chi2(self._h)
+    def active_chi2(self) -> float: return self._L.refcore_active_chi2(self._h)
+
+    def dogleg_state(self) -> dict:
+        d = np.zeros(2); self._L.refcore_dogleg_state(self._h, _dp(d)); return {"delta": d[0], "last_step": int(d[1])}
+
+    def hessian_index(self) -> np.ndarray:
+        out = np.zeros(self.graph.n_vertices, dtype=np.int32); self._L.refcore_hessian_index(self._h, _dp(out)); return out
+
+    def estimates(self) -> np.ndarray:
+        out = np.zeros_like(self.graph.v_estimate); self._L.refcore_estimates(self._h, _dp(out)); return out
 
 
 def has_csparse() -> bool:

@@ -1,0 +1,136 @@
+// TEST INFRASTRUCTURE.  The REAL reference end to end for 2-D SLAM graphs: g2o/core (SparseOptimizer, OptimizableGraph, BlockSolver,
+// OptimizationAlgorithmLevenberg / GaussNewton / Dogleg, robust kernels), g2o/stuff, g2o/solvers/pcg/linear_solver_pcg.h and the slam2d
+// types VertexSE2, VertexPointXY, EdgeSE2, EdgeSE2PointXY, compiled unmodified from /root/reference against the Eigen stand-in in
+// oracle/eigen_shim (NOT Eigen; see its Core header) by `make -C oracle ref_core` into oracle/_ref/libg2o_ref_core.so.
+// This file only builds a g2o::SparseOptimizer from the flat graph layout of include/g2ocu.h, runs optimize() and reads the results back.
+// tests/test_reference_core.py compares the oracle (and through it the CUDA path) with what comes out of here.
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "g2o/core/block_solver.h"
+#include "g2o/core/optimization_algorithm_dogleg.h"
+#include "g2o/core/optimization_algorithm_gauss_newton.h"
+#include "g2o/core/optimization_algorithm_levenberg.h"
+#include "g2o/core/robust_kernel_factory.h"
+#include "g2o/core/sparse_optimizer.h"
+#include "g2o/solvers/pcg/linear_solver_pcg.h"
+#include "g2o/types/slam2d/edge_se2.h"
+#include "g2o/types/slam2d/edge_se2_pointxy.h"
+#include "g2o/types/slam2d/vertex_point_xy.h"
+#include "g2o/types/slam2d/vertex_se2.h"
+
+namespace {
+
+// same field order as g2ocu_graph (include/g2ocu.h) / orc_graph (oracle/g2o_oracle.cpp)
+struct FlatGraph {
+  int32_t n_vertices; const int32_t* v_id; const int32_t* v_type; const uint8_t* v_fixed; const uint8_t* v_marginalized; const double* v_estimate;
+  int32_t n_edges; const int32_t* e_type; const int32_t* e_v0; const int32_t* e_v1; const int32_t* e_level;
+  const double* e_measurement; const double* e_information; const int32_t* e_kernel; const double* e_kernel_delta; const double* e_param;
+};
+const char* const kKernelNames[10] = {"", "Huber", "PseudoHuber", "Cauchy", "GemanMcClure", "Welsch", "Fair", "Tukey", "Saturated", "DCS"};
+
+struct Handle {
+  g2o::SparseOptimizer optimizer;
+  std::vector<g2o::OptimizableGraph::Vertex*> vertices;      // in the caller's order
+  std::vector<int> vtype;
+  g2o::OptimizationAlgorithmLevenberg* lm = nullptr;
+  g2o::OptimizationAlgorithmDogleg* dl = nullptr;
+  std::string err;
+};
+
+template <class BlockSolverT> std::unique_ptr<BlockSolverT> makeBlockSolver() {
+  std::unique_ptr<g2o::LinearSolverPCG<typename BlockSolverT::PoseMatrixType> > linear(new g2o::LinearSolverPCG<typename BlockSolverT::PoseMatrixType>());
+  return std::unique_ptr<BlockSolverT>(new BlockSolverT(std::move(linear)));
+}
+
+}  // namespace
+
+extern "C" {
+
+// algorithm: "gn" | "lm" | "dl"; blockSolver: "3_2" (BlockSolver<BlockSolverTraits<3,2>>) | "var" (BlockSolverX); linear solver: LinearSolverPCG
+void* refcore_create(const FlatGraph* g, const char* algorithm, const char* blockSolver) {
+  std::unique_ptr<Handle> h(new Handle);
+  const std::string alg(algorithm), bs(blockSolver);
+  std::unique_ptr<g2o::BlockSolverBase> solver;
+  if (bs == "3_2") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<3, 2> > >();
+  else if (bs == "var") solver = makeBlockSolver<g2o::BlockSolverX>();
+  else return nullptr;
+  g2o::OptimizationAlgorithm* a = nullptr;
+  if (alg == "lm") a = h->lm = new g2o::OptimizationAlgorithmLevenberg(std::move(solver));
+  else if (alg == "gn") a = new g2o::OptimizationAlgorithmGaussNewton(std::move(solver));
+  else if (alg == "dl") a = h->dl = new g2o::OptimizationAlgorithmDogleg(std::move(solver));
+  else return nullptr;
+  h->optimizer.setAlgorithm(a);
+  size_t eo = 0;
+  for (int i = 0; i < g->n_vertices; ++i) {
+    g2o::OptimizableGraph::Vertex* v = nullptr;
+    if (g->v_type[i] == 1) { g2o::VertexSE2* p = new g2o::VertexSE2; p->setEstimate(g2o::SE2(g->v_estimate[eo], g->v_estimate[eo + 1], g->v_estimate[eo + 2])); eo += 3; v = p; }
+    else if (g->v_type[i] == 2) { g2o::VertexPointXY* p = new g2o::VertexPointXY; p->setEstimate(g2o::Vector2(g->v_estimate[eo], g->v_estimate[eo + 1])); eo += 2; v = p; }
+    else return nullptr;                                    // only the slam2d types are built into this library
+    v->setId(g->v_id[i]); v->setFixed(g->v_fixed[i] != 0); v->setMarginalized(g->v_marginalized[i] != 0);
+    if (!h->optimizer.addVertex(v)) return nullptr;
+    h->vertices.push_back(v); h->vtype.push_back(g->v_type[i]);
+  }
+  size_t mo = 0, io = 0;
+  for (int i = 0; i < g->n_edges; ++i) {
+    g2o::OptimizableGraph::Edge* e = nullptr;
+    if (g->e_type[i] == 1) {
+      g2o::EdgeSE2* p = new g2o::EdgeSE2; p->setMeasurement(g2o::SE2(g->e_measurement[mo], g->e_measurement[mo + 1], g->e_measurement[mo + 2]));
+      g2o::Matrix3 info; for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) info(r, c) = g->e_information[io + r + 3 * c];
+      p->setInformation(info); mo += 3; io += 9; e = p;
+    } else if (g->e_type[i] == 2) {
+      g2o::EdgeSE2PointXY* p = new g2o::EdgeSE2PointXY; p->setMeasurement(g2o::Vector2(g->e_measurement[mo], g->e_measurement[mo + 1]));
+      g2o::Matrix2 info; for (int c = 0; c < 2; ++c) for (int r = 0; r < 2; ++r) info(r, c) = g->e_information[io + r + 2 * c];
+      p->setInformation(info); mo += 2; io += 4; e = p;
+    } else return nullptr;
+    e->setVertex(0, h->vertices[g->e_v0[i]]); e->setVertex(1, h->vertices[g->e_v1[i]]);
+    e->setLevel(g->e_level ? g->e_level[i] : 0);
+    const int kernel = g->e_kernel ? g->e_kernel[i] : 0;
+    if (kernel) {
+      g2o::RobustKernel* k = g2o::RobustKernelFactory::instance()->construct(kKernelNames[kernel]);
+      if (!k) return nullptr;
+      k->setDelta(g->e_kernel_delta ? g->e_kernel_delta[i] : 1.0);
+      e->setRobustKernel(k);
+    }
+    if (!h->optimizer.addEdge(e)) return nullptr;
+  }
+  return h.release();
+}
+void refcore_destroy(void* hh) { delete (Handle*)hh; }
+
+int refcore_initialize_optimization(void* hh, int level) { return ((Handle*)hh)->optimizer.initializeOptimization(level) ? 1 : 0; }
+
+// SparseOptimizer::optimize(iterations); stats: iterations x 6 doubles = chi2, levenbergIterations, iterationsLinearSolver, lambda after the
+// iteration is not in G2OBatchStatistics (read refcore_current_lambda after the call), hessianPoseDimension, hessianLandmarkDimension, iteration
+int refcore_optimize(void* hh, int iterations, double* stats) {
+  Handle* h = (Handle*)hh;
+  h->optimizer.setComputeBatchStatistics(true);
+  const int n = h->optimizer.optimize(iterations);
+  const g2o::BatchStatisticsContainer& bs = h->optimizer.batchStatistics();
+  for (size_t i = 0; i < bs.size() && (int)i < iterations; ++i) {
+    double* s = stats + 6 * i;
+    s[0] = bs[i].chi2; s[1] = bs[i].levenbergIterations; s[2] = bs[i].iterationsLinearSolver; s[3] = (double)bs[i].hessianPoseDimension;
+    s[4] = (double)bs[i].hessianLandmarkDimension; s[5] = bs[i].iteration;
+  }
+  return n;
+}
+double refcore_current_lambda(void* hh) { Handle* h = (Handle*)hh; return h->lm ? h->lm->currentLambda() : 0.0; }
+// OptimizationAlgorithmDogleg::trustRegion(), lastStep()
+void refcore_dogleg_state(void* hh, double* out2) { Handle* h = (Handle*)hh; out2[0] = h->dl ? h->dl->trustRegion() : 0.0; out2[1] = h->dl ? h->dl->lastStep() : 0.0; }
+double refcore_active_robust_chi2(void* hh) { Handle* h = (Handle*)hh; h->optimizer.computeActiveErrors(); return h->optimizer.activeRobustChi2(); }
+double refcore_active_chi2(void* hh) { Handle* h = (Handle*)hh; h->optimizer.computeActiveErrors(); return h->optimizer.activeChi2(); }
+// hessianIndex of every vertex in the caller's order (-1 fixed / inactive)
+void refcore_hessian_index(void* hh, int32_t* out) { Handle* h = (Handle*)hh; for (size_t i = 0; i < h->vertices.size(); ++i) out[i] = h->vertices[i]->hessianIndex(); }
+// packed estimates in the caller's vertex order (SE2: x y theta; point: x y)
+void refcore_estimates(void* hh, double* out) {
+  Handle* h = (Handle*)hh; size_t o = 0;
+  for (size_t i = 0; i < h->vertices.size(); ++i) {
+    if (h->vtype[i] == 1) { const g2o::SE2& e = static_cast<g2o::VertexSE2*>(h->vertices[i])->estimate(); out[o++] = e[0]; out[o++] = e[1]; out[o++] = e[2]; }
+    else { const g2o::Vector2& e = static_cast<g2o::VertexPointXY*>(h->vertices[i])->estimate(); out[o++] = e[0]; out[o++] = e[1]; }
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+"""The REAL reference run here: g2o/core (SparseOptimizer, OptimizableGraph, BlockSolver, Levenberg / Gauss-Newton / Dogleg, robust kernels),
+g2o/stuff, LinearSolverPCG and the slam2d types are compiled unmodified from /root/reference into oracle/_ref/libg2o_ref_core.so against
+the stand-in for the absent Eigen3 (oracle/eigen_shim, NOT Eigen: eager fixed-size and dynamic arithmetic, see its Core header), with
+oracle/ref_core.cpp building the graph from the flat layout.  The oracle must reproduce what the reference does on the same 2-D SLAM
+graphs: index map, chi2 per iteration, number of LM trials, number of PCG iterations per solve, lambda, trust region, final estimates.
+The machinery checked this way (buildStructure, constructQuadraticForm with robust kernels, Schur complement, PCG with its carried
+residual, back-substitution, LM / Dogleg control) is the same for every vertex and edge type."""
+import numpy as np
+import pytest
+
+from g2o_b200 import graph as G
+from g2o_b200 import workloads as W
+from oracle import oracle
+
+pytestmark = pytest.mark.skipif(oracle.reference_core() is None, reason="oracle/_ref/libg2o_ref_core.so was not built (no reference tree at build time)")
+
+
+def _with_kernel(g, kind, delta):
+    g.e_kernel = np.full(g.n_edges, kind, dtype=np.int32); g.e_kernel_delta = np.full(g.n_edges, float(delta)); return g
+
+
+def _poses_only(g):
+    keep = np.asarray(g.e_type) == G.EDGE_SE2
+    poses = np.flatnonzero(np.asarray(g.v_type) == G.VERTEX_SE2)
+    remap = -np.ones(g.n_vertices, dtype=np.int64); remap[poses] = np.arange(len(poses))
+    est = np.concatenate([g.v_estimate[g.estimate_offsets()[v]:g.estimate_offsets()[v] + 3] for v in poses])
+    E = int(keep.sum())
+    meas = g.e_measurement[:3 * E] if np.all(keep[:E]) else None
+    idx = np.flatnonzero(keep)
+    mo = np.concatenate([[0], np.cumsum(G.EDGE_MEAS_DIM[np.asarray(g.e_type)])]); io = np.concatenate([[0], np.cumsum(G.EDGE_DIM[np.asarray(g.e_type)] ** 2)])
+    meas = np.concatenate([g.e_measurement[mo[e]:mo[e + 1]] for e in idx]); info = np.concatenate([g.e_information[io[e]:io[e + 1]] for e in idx])
+    return G.Graph(v_id=np.asarray(g.v_id)[poses], v_type=np.full(len(poses), G.VERTEX_SE2), v_fixed=np.asarray(g.v_fixed)[poses], v_marginalized=np.zeros(len(poses)),
+                   v_estimate=est, e_type=np.full(E, G.EDGE_SE2), e_v0=remap[np.asarray(g.e_v0)[idx]], e_v1=remap[np.asarray(g.e_v1)[idx]], e_measurement=meas, e_information=info,
+                   e_kernel=np.asarray(g.e_kernel)[idx], e_kernel_delta=np.asarray(g.e_kernel_delta)[idx])
+
+
+CASES = {
+    # name: (graph, algorithm, reference block solver)
+    "schur_lm_huber": (lambda: W.slam2d(n_poses=300, n_landmarks=80, world_size=20.0), "lm", "3_2"),
+    "schur_lm_no_kernel": (lambda: W.slam2d(n_poses=200, n_landmarks=60, world_size=16.0, huber_delta=None), "lm", "3_2"),
+    "schur_lm_cauchy": (lambda: _with_kernel(W.slam2d(n_poses=200, n_landmarks=60, world_size=16.0), G.KERNEL_CAUCHY, 2.0), "lm", "3_2"),
+    "schur_gn": (lambda: W.slam2d(n_poses=200, n_landmarks=60, world_size=16.0), "gn", "3_2"),
+    "schur_dogleg": (lambda: W.slam2d(n_poses=200, n_landmarks=60, world_size=16.0), "dl", "3_2"),
+    "points_free_lm": (lambda: W.slam2d(n_poses=200, n_landmarks=60, world_size=16.0, marginalize_landmarks=False), "lm", "var"),
+    "points_free_dogleg": (lambda: W.slam2d(n_poses=200, n_landmarks=60, world_size=16.0, marginalize_landmarks=False), "dl", "var"),
+    "schur_var_lm": (lambda: W.slam2d(n_poses=200, n_landmarks=60, world_size=16.0), "lm", "var"),       # BlockSolverX with Schur
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_reproduces_the_reference(name):
+    fn, alg, bs = CASES[name]
+    g = fn()
+    ref = oracle.ReferenceG2o(g, alg, bs); assert ref.initialize_optimization()
+    o = oracle.Oracle(g, alg, "pcg"); assert o.initialize_optimization()
+    assert np.array_equal(ref.hessian_index(), o.get_i32("hessian_index"))                       # buildIndexMapping, bit for bit
+    assert abs(o_chi2(o) - ref.active_robust_chi2()) <= 1e-13 * ref.active_robust_chi2()
+    iters = 6
+    n_r, st_r = ref.optimize(iters); n_o, st_o = o.optimize(iters)
+    assert n_r == n_o and len(st_r) == len(st_o)
+    for i, (a, b) in enumerate(zip(st_o, st_r)):
+        assert abs(a["chi2"] - b["chi2"]) <= 1e-9 * b["chi2"], (name, i, a["chi2"], b["chi2"])
+        assert int(a["levenbergIterations"]) == int(b["levenbergIterations"]), (name, i)
+        assert int(a["iterationsLinearSolver"]) == int(b["iterationsLinearSolver"]), (name, i, a["iterationsLinearSolver"], b["iterationsLinearSolver"])
+        assert int(a["hessianPoseDimension"]) == int(b["hessianPoseDimension"]) and int(a["hessianLandmarkDimension"]) == int(b["hessianLandmarkDimension"])
+    if alg == "lm":
+        assert abs(st_o[-1]["lambda"] - ref.current_lambda()) <= 1e-9 * ref.current_lambda()
+    if alg == "dl":
+        d_o, d_r = o.dogleg_state(), ref.dogleg_state()
+        assert d_o["last_step"] == d_r["last_step"] and abs(d_o["delta"] - d_r["delta"]) <= 1e-9 * d_r["delta"], (d_o, d_r)
+    e_r, e_o = ref.estimates(), o.estimates()
+    assert np.max(np.abs(e_o - e_r)) <= 1e-8 * (1 + np.max(np.abs(e_r)))
+
+
+def o_chi2(o):
+    o.compute_active_errors()
+    return o.active_robust_chi2()
+
+
+def _pose_graph_with_loop_closures(seed=3):
+    """Odometry chain of the slam2d workload plus noisy loop closures between random pose pairs, started from perturbed estimates."""
+    g = _poses_only(W.slam2d(n_poses=250, n_landmarks=40, world_size=16.0))
+    rng = np.random.default_rng(seed)
+    X = g.v_estimate.reshape(-1, 3).copy()
+    n = len(X); pairs = [(int(a), int(b)) for a, b in rng.integers(0, n, size=(60, 2)) if a != b]
+    meas, info = [], []
+    for a, b in pairs:      # z = X_a^-1 X_b + noise
+        c, s_ = np.cos(X[a, 2]), np.sin(X[a, 2]); d = X[b, :2] - X[a, :2]
+        meas += [c * d[0] + s_ * d[1] + rng.normal() * 0.05, -s_ * d[0] + c * d[1] + rng.normal() * 0.05, (X[b, 2] - X[a, 2] + rng.normal() * 0.02 + np.pi) % (2 * np.pi) - np.pi]
+        info += list(np.diag([500.0, 500.0, 5000.0]).ravel())
+    E = len(pairs)
+    return G.Graph(v_id=g.v_id, v_type=g.v_type, v_fixed=g.v_fixed, v_marginalized=g.v_marginalized, v_estimate=(X + rng.normal(size=X.shape) * [0.1, 0.1, 0.02]).ravel(),
+                   e_type=np.concatenate([g.e_type, np.full(E, G.EDGE_SE2)]), e_v0=np.concatenate([g.e_v0, [p[0] for p in pairs]]), e_v1=np.concatenate([g.e_v1, [p[1] for p in pairs]]),
+                   e_measurement=np.concatenate([g.e_measurement, meas]), e_information=np.concatenate([g.e_information, info]),
+                   e_kernel=np.concatenate([g.e_kernel, np.zeros(E)]), e_kernel_delta=np.concatenate([g.e_kernel_delta, np.ones(E)]))
+
+
+def test_pose_graph_and_fixed_vertices():
+    g = _pose_graph_with_loop_closures()
+    g.v_fixed = np.array(g.v_fixed, dtype=np.uint8); g.v_fixed[[0, 7, 50]] = 1                      # several fixed vertices
+    for alg in ("lm", "gn", "dl"):
+        ref = oracle.ReferenceG2o(g, alg, "var"); assert ref.initialize_optimization()
+        o = oracle.Oracle(g, alg, "pcg"); assert o.initialize_optimization()
+        assert np.array_equal(ref.hessian_index(), o.get_i32("hessian_index"))
+        n_r, st_r = ref.optimize(5); n_o, st_o = o.optimize(5)
+        assert n_r == n_o
+        for a, b in zip(st_o, st_r):
+            assert abs(a["chi2"] - b["chi2"]) <= 1e-9 * b["chi2"] and int(a["iterationsLinearSolver"]) == int(b["iterationsLinearSolver"]), (alg, a["chi2"], b["chi2"])
+        assert np.max(np.abs(o.estimates() - ref.estimates())) <= 1e-8 * (1 + np.max(np.abs(ref.estimates())))
+
+
+def test_edge_levels_are_respected():
+    g = W.slam2d(n_poses=150, n_landmarks=40, world_size=14.0)
+    g.e_level = np.zeros(g.n_edges, dtype=np.int32); g.e_level[::5] = 1                               # every fifth edge sits on level 1
+    for level in (0, 1):
+        ref = oracle.ReferenceG2o(g, "lm", "3_2"); o = oracle.Oracle(g, "lm", "pcg")
+        ok_r, ok_o = ref.initialize_optimization(level), o.initialize_optimization(level)
+        assert ok_r == ok_o
+        assert np.array_equal(ref.hessian_index(), o.get_i32("hessian_index"))
+        if ok_r and level == 0:
+            n_r, st_r = ref.optimize(3); n_o, st_o = o.optimize(3)
+            assert n_r == n_o and all(abs(a["chi2"] - b["chi2"]) <= 1e-9 * b["chi2"] for a, b in zip(st_o, st_r))
