@@ -1,6 +1,7 @@
-// TEST INFRASTRUCTURE.  The REAL reference end to end for 2-D SLAM graphs: g2o/core (SparseOptimizer, OptimizableGraph, BlockSolver,
-// OptimizationAlgorithmLevenberg / GaussNewton / Dogleg, robust kernels), g2o/stuff, g2o/solvers/pcg/linear_solver_pcg.h and the slam2d
-// types VertexSE2, VertexPointXY, EdgeSE2, EdgeSE2PointXY, compiled unmodified from /root/reference against the Eigen stand-in in
+// TEST INFRASTRUCTURE.  The REAL reference end to end for 2-D SLAM and bundle-adjustment graphs: g2o/core (SparseOptimizer, OptimizableGraph,
+// BlockSolver, OptimizationAlgorithmLevenberg / GaussNewton / Dogleg, robust kernels), g2o/stuff, g2o/solvers/pcg/linear_solver_pcg.h, the slam2d
+// types VertexSE2, VertexPointXY, EdgeSE2, EdgeSE2PointXY and the sba types VertexSE3Expmap, VertexSBAPointXYZ, EdgeProjectXYZ2UV (+ CameraParameters),
+// EdgeSE3ProjectXYZ, EdgeSE3Expmap, compiled unmodified from /root/reference against the Eigen stand-in in
 // oracle/eigen_shim (NOT Eigen; see its Core header) by `make -C oracle ref_core` into oracle/_ref/libg2o_ref_core.so.
 // This file only builds a g2o::SparseOptimizer from the flat graph layout of include/g2ocu.h, runs optimize() and reads the results back.
 // tests/test_reference_core.py compares the oracle (and through it the CUDA path) with what comes out of here.
@@ -17,6 +18,7 @@
 #include "g2o/core/robust_kernel_factory.h"
 #include "g2o/core/sparse_optimizer.h"
 #include "g2o/solvers/pcg/linear_solver_pcg.h"
+#include "g2o/types/sba/types_six_dof_expmap.h"
 #include "g2o/types/slam2d/edge_se2.h"
 #include "g2o/types/slam2d/edge_se2_pointxy.h"
 #include "g2o/types/slam2d/vertex_point_xy.h"
@@ -38,6 +40,7 @@ struct Handle {
   std::vector<int> vtype;
   g2o::OptimizationAlgorithmLevenberg* lm = nullptr;
   g2o::OptimizationAlgorithmDogleg* dl = nullptr;
+  std::vector<std::vector<double> > cameras;                 // distinct (f, cx, cy) of the EdgeProjectXYZ2UV edges -> parameter id
   std::string err;
 };
 
@@ -50,12 +53,13 @@ template <class BlockSolverT> std::unique_ptr<BlockSolverT> makeBlockSolver() {
 
 extern "C" {
 
-// algorithm: "gn" | "lm" | "dl"; blockSolver: "3_2" (BlockSolver<BlockSolverTraits<3,2>>) | "var" (BlockSolverX); linear solver: LinearSolverPCG
+// algorithm: "gn" | "lm" | "dl"; blockSolver: "3_2" | "6_3" (BlockSolver<BlockSolverTraits<P,L>>) | "var" (BlockSolverX); linear solver: LinearSolverPCG
 void* refcore_create(const FlatGraph* g, const char* algorithm, const char* blockSolver) {
   std::unique_ptr<Handle> h(new Handle);
   const std::string alg(algorithm), bs(blockSolver);
   std::unique_ptr<g2o::BlockSolverBase> solver;
   if (bs == "3_2") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<3, 2> > >();
+  else if (bs == "6_3") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<6, 3> > >();
   else if (bs == "var") solver = makeBlockSolver<g2o::BlockSolverX>();
   else return nullptr;
   g2o::OptimizationAlgorithm* a = nullptr;
@@ -69,12 +73,16 @@ void* refcore_create(const FlatGraph* g, const char* algorithm, const char* bloc
     g2o::OptimizableGraph::Vertex* v = nullptr;
     if (g->v_type[i] == 1) { g2o::VertexSE2* p = new g2o::VertexSE2; p->setEstimate(g2o::SE2(g->v_estimate[eo], g->v_estimate[eo + 1], g->v_estimate[eo + 2])); eo += 3; v = p; }
     else if (g->v_type[i] == 2) { g2o::VertexPointXY* p = new g2o::VertexPointXY; p->setEstimate(g2o::Vector2(g->v_estimate[eo], g->v_estimate[eo + 1])); eo += 2; v = p; }
-    else return nullptr;                                    // only the slam2d types are built into this library
+    else if (g->v_type[i] == 4) {                           // VertexSE3Expmap, estimate = SE3Quat::toVector (t, qx, qy, qz, qw)
+      g2o::VertexSE3Expmap* p = new g2o::VertexSE3Expmap; g2o::Vector7 a; for (int k = 0; k < 7; ++k) a[k] = g->v_estimate[eo + k];
+      g2o::SE3Quat T; T.fromVector(a); p->setEstimate(T); eo += 7; v = p;
+    } else if (g->v_type[i] == 5) { g2o::VertexSBAPointXYZ* p = new g2o::VertexSBAPointXYZ; p->setEstimate(g2o::Vector3(g->v_estimate[eo], g->v_estimate[eo + 1], g->v_estimate[eo + 2])); eo += 3; v = p; }
+    else return nullptr;                                    // slam2d and sba types only
     v->setId(g->v_id[i]); v->setFixed(g->v_fixed[i] != 0); v->setMarginalized(g->v_marginalized[i] != 0);
     if (!h->optimizer.addVertex(v)) return nullptr;
     h->vertices.push_back(v); h->vtype.push_back(g->v_type[i]);
   }
-  size_t mo = 0, io = 0;
+  size_t mo = 0, io = 0, po = 0;
   for (int i = 0; i < g->n_edges; ++i) {
     g2o::OptimizableGraph::Edge* e = nullptr;
     if (g->e_type[i] == 1) {
@@ -85,6 +93,29 @@ void* refcore_create(const FlatGraph* g, const char* algorithm, const char* bloc
       g2o::EdgeSE2PointXY* p = new g2o::EdgeSE2PointXY; p->setMeasurement(g2o::Vector2(g->e_measurement[mo], g->e_measurement[mo + 1]));
       g2o::Matrix2 info; for (int c = 0; c < 2; ++c) for (int r = 0; r < 2; ++r) info(r, c) = g->e_information[io + r + 2 * c];
       p->setInformation(info); mo += 2; io += 4; e = p;
+    } else if (g->e_type[i] == 4) {                         // EdgeSE3Expmap, measurement SE3Quat (7)
+      g2o::EdgeSE3Expmap* p = new g2o::EdgeSE3Expmap; g2o::Vector7 a; for (int k = 0; k < 7; ++k) a[k] = g->e_measurement[mo + k];
+      g2o::SE3Quat Z; Z.fromVector(a); p->setMeasurement(Z);
+      Eigen::Matrix<number_t, 6, 6> info; for (int c = 0; c < 6; ++c) for (int r = 0; r < 6; ++r) info(r, c) = g->e_information[io + r + 6 * c];
+      p->setInformation(info); mo += 7; io += 36; e = p;
+    } else if (g->e_type[i] == 5 || g->e_type[i] == 6) {    // (VertexSBAPointXYZ, VertexSE3Expmap) projections
+      g2o::Matrix2 info; for (int c = 0; c < 2; ++c) for (int r = 0; r < 2; ++r) info(r, c) = g->e_information[io + r + 2 * c];
+      const g2o::Vector2 z(g->e_measurement[mo], g->e_measurement[mo + 1]);
+      if (g->e_type[i] == 5) {                              // EdgeProjectXYZ2UV with CameraParameters (f, cx, cy)
+        std::vector<double> cam(g->e_param + po, g->e_param + po + 3); po += 3;
+        size_t id = 0; while (id < h->cameras.size() && h->cameras[id] != cam) ++id;
+        if (id == h->cameras.size()) {
+          h->cameras.push_back(cam);
+          g2o::CameraParameters* cp = new g2o::CameraParameters(cam[0], g2o::Vector2(cam[1], cam[2]), 0.);
+          cp->setId((int)id);
+          if (!h->optimizer.addParameter(cp)) return nullptr;
+        }
+        g2o::EdgeProjectXYZ2UV* p = new g2o::EdgeProjectXYZ2UV; p->setMeasurement(z); p->setInformation(info); p->setParameterId(0, (int)id); e = p;
+      } else {                                              // the fork's EdgeSE3ProjectXYZ with fx, fy, cx, cy members
+        g2o::EdgeSE3ProjectXYZ* p = new g2o::EdgeSE3ProjectXYZ; p->setMeasurement(z); p->setInformation(info);
+        p->fx = g->e_param[po]; p->fy = g->e_param[po + 1]; p->cx = g->e_param[po + 2]; p->cy = g->e_param[po + 3]; po += 4; e = p;
+      }
+      mo += 2; io += 4;
     } else return nullptr;
     e->setVertex(0, h->vertices[g->e_v0[i]]); e->setVertex(1, h->vertices[g->e_v1[i]]);
     e->setLevel(g->e_level ? g->e_level[i] : 0);
@@ -129,7 +160,9 @@ void refcore_estimates(void* hh, double* out) {
   Handle* h = (Handle*)hh; size_t o = 0;
   for (size_t i = 0; i < h->vertices.size(); ++i) {
     if (h->vtype[i] == 1) { const g2o::SE2& e = static_cast<g2o::VertexSE2*>(h->vertices[i])->estimate(); out[o++] = e[0]; out[o++] = e[1]; out[o++] = e[2]; }
-    else { const g2o::Vector2& e = static_cast<g2o::VertexPointXY*>(h->vertices[i])->estimate(); out[o++] = e[0]; out[o++] = e[1]; }
+    else if (h->vtype[i] == 2) { const g2o::Vector2& e = static_cast<g2o::VertexPointXY*>(h->vertices[i])->estimate(); out[o++] = e[0]; out[o++] = e[1]; }
+    else if (h->vtype[i] == 4) { const g2o::Vector7 e = static_cast<g2o::VertexSE3Expmap*>(h->vertices[i])->estimate().toVector(); for (int k = 0; k < 7; ++k) out[o++] = e[k]; }
+    else { const g2o::Vector3& e = static_cast<g2o::VertexSBAPointXYZ*>(h->vertices[i])->estimate(); out[o++] = e[0]; out[o++] = e[1]; out[o++] = e[2]; }
   }
 }
 
