@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE.  The REAL reference end to end for 2-D SLAM and bundle-adjustment graphs: g2o/core (SparseOptimizer, OptimizableGraph,
 // BlockSolver, OptimizationAlgorithmLevenberg / GaussNewton / Dogleg, robust kernels), g2o/stuff, g2o/solvers/pcg/linear_solver_pcg.h, the slam2d
 // types VertexSE2, VertexPointXY, EdgeSE2, EdgeSE2PointXY and the sba types VertexSE3Expmap, VertexSBAPointXYZ, EdgeProjectXYZ2UV (+ CameraParameters),
-// EdgeSE3ProjectXYZ, EdgeSE3Expmap, compiled unmodified from /root/reference against the Eigen stand-in in
+// EdgeSE3ProjectXYZ, EdgeSE3Expmap and the slam3d types VertexSE3, EdgeSE3, compiled unmodified from /root/reference against the Eigen stand-in in
 // oracle/eigen_shim (NOT Eigen; see its Core header) by `make -C oracle ref_core` into oracle/_ref/libg2o_ref_core.so.
 // This file only builds a g2o::SparseOptimizer from the flat graph layout of include/g2ocu.h, runs optimize() and reads the results back.
 // tests/test_reference_core.py compares the oracle (and through it the CUDA path) with what comes out of here.
@@ -19,6 +19,8 @@
 #include "g2o/core/sparse_optimizer.h"
 #include "g2o/solvers/pcg/linear_solver_pcg.h"
 #include "g2o/types/sba/types_six_dof_expmap.h"
+#include "g2o/types/slam3d/edge_se3.h"
+#include "g2o/types/slam3d/vertex_se3.h"
 #include "g2o/types/slam2d/edge_se2.h"
 #include "g2o/types/slam2d/edge_se2_pointxy.h"
 #include "g2o/types/slam2d/vertex_point_xy.h"
@@ -32,6 +34,12 @@ struct FlatGraph {
   int32_t n_edges; const int32_t* e_type; const int32_t* e_v0; const int32_t* e_v1; const int32_t* e_level;
   const double* e_measurement; const double* e_information; const int32_t* e_kernel; const double* e_kernel_delta; const double* e_param;
 };
+g2o::Isometry3 isoFrom12(const double* v) {      // R column-major (9) + t (3), the layout of include/g2ocu.h
+  g2o::Isometry3 T = g2o::Isometry3::Identity();
+  for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) T.linear()(r, c) = v[r + 3 * c];
+  for (int r = 0; r < 3; ++r) T.translation()[r] = v[9 + r];
+  return T;
+}
 const char* const kKernelNames[10] = {"", "Huber", "PseudoHuber", "Cauchy", "GemanMcClure", "Welsch", "Fair", "Tukey", "Saturated", "DCS"};
 
 struct Handle {
@@ -73,11 +81,12 @@ void* refcore_create(const FlatGraph* g, const char* algorithm, const char* bloc
     g2o::OptimizableGraph::Vertex* v = nullptr;
     if (g->v_type[i] == 1) { g2o::VertexSE2* p = new g2o::VertexSE2; p->setEstimate(g2o::SE2(g->v_estimate[eo], g->v_estimate[eo + 1], g->v_estimate[eo + 2])); eo += 3; v = p; }
     else if (g->v_type[i] == 2) { g2o::VertexPointXY* p = new g2o::VertexPointXY; p->setEstimate(g2o::Vector2(g->v_estimate[eo], g->v_estimate[eo + 1])); eo += 2; v = p; }
+    else if (g->v_type[i] == 3) { g2o::VertexSE3* p = new g2o::VertexSE3; p->setEstimate(isoFrom12(g->v_estimate + eo)); eo += 12; v = p; }
     else if (g->v_type[i] == 4) {                           // VertexSE3Expmap, estimate = SE3Quat::toVector (t, qx, qy, qz, qw)
       g2o::VertexSE3Expmap* p = new g2o::VertexSE3Expmap; g2o::Vector7 a; for (int k = 0; k < 7; ++k) a[k] = g->v_estimate[eo + k];
       g2o::SE3Quat T; T.fromVector(a); p->setEstimate(T); eo += 7; v = p;
     } else if (g->v_type[i] == 5) { g2o::VertexSBAPointXYZ* p = new g2o::VertexSBAPointXYZ; p->setEstimate(g2o::Vector3(g->v_estimate[eo], g->v_estimate[eo + 1], g->v_estimate[eo + 2])); eo += 3; v = p; }
-    else return nullptr;                                    // slam2d and sba types only
+    else return nullptr;                                    // slam2d, slam3d and sba types only
     v->setId(g->v_id[i]); v->setFixed(g->v_fixed[i] != 0); v->setMarginalized(g->v_marginalized[i] != 0);
     if (!h->optimizer.addVertex(v)) return nullptr;
     h->vertices.push_back(v); h->vtype.push_back(g->v_type[i]);
@@ -93,6 +102,10 @@ void* refcore_create(const FlatGraph* g, const char* algorithm, const char* bloc
       g2o::EdgeSE2PointXY* p = new g2o::EdgeSE2PointXY; p->setMeasurement(g2o::Vector2(g->e_measurement[mo], g->e_measurement[mo + 1]));
       g2o::Matrix2 info; for (int c = 0; c < 2; ++c) for (int r = 0; r < 2; ++r) info(r, c) = g->e_information[io + r + 2 * c];
       p->setInformation(info); mo += 2; io += 4; e = p;
+    } else if (g->e_type[i] == 3) {                         // EdgeSE3, measurement Isometry3 (12)
+      g2o::EdgeSE3* p = new g2o::EdgeSE3; p->setMeasurement(isoFrom12(g->e_measurement + mo));
+      Eigen::Matrix<number_t, 6, 6> info; for (int c = 0; c < 6; ++c) for (int r = 0; r < 6; ++r) info(r, c) = g->e_information[io + r + 6 * c];
+      p->setInformation(info); mo += 12; io += 36; e = p;
     } else if (g->e_type[i] == 4) {                         // EdgeSE3Expmap, measurement SE3Quat (7)
       g2o::EdgeSE3Expmap* p = new g2o::EdgeSE3Expmap; g2o::Vector7 a; for (int k = 0; k < 7; ++k) a[k] = g->e_measurement[mo + k];
       g2o::SE3Quat Z; Z.fromVector(a); p->setMeasurement(Z);
@@ -161,6 +174,8 @@ void refcore_estimates(void* hh, double* out) {
   for (size_t i = 0; i < h->vertices.size(); ++i) {
     if (h->vtype[i] == 1) { const g2o::SE2& e = static_cast<g2o::VertexSE2*>(h->vertices[i])->estimate(); out[o++] = e[0]; out[o++] = e[1]; out[o++] = e[2]; }
     else if (h->vtype[i] == 2) { const g2o::Vector2& e = static_cast<g2o::VertexPointXY*>(h->vertices[i])->estimate(); out[o++] = e[0]; out[o++] = e[1]; }
+    else if (h->vtype[i] == 3) { const g2o::Isometry3& e = static_cast<g2o::VertexSE3*>(h->vertices[i])->estimate();
+      for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) out[o++] = e.linear()(r, c); for (int r = 0; r < 3; ++r) out[o++] = e.translation()[r]; }
     else if (h->vtype[i] == 4) { const g2o::Vector7 e = static_cast<g2o::VertexSE3Expmap*>(h->vertices[i])->estimate().toVector(); for (int k = 0; k < 7; ++k) out[o++] = e[k]; }
     else { const g2o::Vector3& e = static_cast<g2o::VertexSBAPointXYZ*>(h->vertices[i])->estimate(); out[o++] = e[0]; out[o++] = e[1]; out[o++] = e[2]; }
   }

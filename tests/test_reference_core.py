@@ -1,8 +1,9 @@
 """The REAL reference run here: g2o/core (SparseOptimizer, OptimizableGraph, BlockSolver, Levenberg / Gauss-Newton / Dogleg, robust kernels),
-g2o/stuff, LinearSolverPCG and the slam2d and sba types (VertexSE3Expmap, VertexSBAPointXYZ, EdgeProjectXYZ2UV, the fork's EdgeSE3ProjectXYZ) are compiled unmodified from /root/reference into oracle/_ref/libg2o_ref_core.so against
+g2o/stuff, LinearSolverPCG and the slam2d, slam3d (VertexSE3, EdgeSE3) and sba types (VertexSE3Expmap, VertexSBAPointXYZ, EdgeProjectXYZ2UV, the fork's EdgeSE3ProjectXYZ) are
+compiled unmodified from /root/reference into oracle/_ref/libg2o_ref_core.so against
 the stand-in for the absent Eigen3 (oracle/eigen_shim, NOT Eigen: eager fixed-size and dynamic arithmetic, see its Core header), with
 oracle/ref_core.cpp building the graph from the flat layout.  The oracle must reproduce what the reference does on the same 2-D SLAM and
-bundle-adjustment graphs (among them BASELINE.json's config C1, ba_demo with BlockSolver_6_3): index map, chi2 per iteration, number of LM trials, number of PCG iterations per solve, lambda, trust region, final estimates.
+bundle-adjustment graphs and 3-D pose graphs (among them BASELINE.json's config C1, ba_demo with BlockSolver_6_3, and sphere graphs as in C2): index map, chi2 per iteration, number of LM trials, number of PCG iterations per solve, lambda, trust region, final estimates.
 The machinery checked this way (buildStructure, constructQuadraticForm with robust kernels, Schur complement, PCG with its carried
 residual, back-substitution, LM / Dogleg control) is the same for every vertex and edge type."""
 import numpy as np
@@ -51,6 +52,10 @@ CASES = {
     "ba_dogleg": (lambda: W.ba_demo(num_cameras=8, num_points=80), "dl", "6_3"),
     "ba_var_schur": (lambda: W.ba_demo(num_cameras=8, num_points=80), "lm", "var"),
     "ba_points_free": (lambda: _points_free(W.ba_demo(num_cameras=8, num_points=80, edge_type=G.EDGE_PROJECT_XYZ2UV)), "lm", "var"),
+    # 3-D pose graphs with the reference's slam3d types (VertexSE3 / EdgeSE3): the shape of BASELINE config C2 (create_sphere + lm_var)
+    "sphere_lm": (lambda: W.sphere(nodes_per_level=16, laps=8), "lm", "var"),
+    "sphere_small_gn": (lambda: W.sphere(nodes_per_level=10, laps=5), "gn", "var"),
+    "sphere_small_dogleg": (lambda: W.sphere(nodes_per_level=10, laps=5), "dl", "var"),
 }
 
 
