@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE.  The REAL reference end to end for 2-D SLAM and bundle-adjustment graphs: g2o/core (SparseOptimizer, OptimizableGraph,
 // BlockSolver, OptimizationAlgorithmLevenberg / GaussNewton / Dogleg, robust kernels), g2o/stuff, g2o/solvers/pcg/linear_solver_pcg.h, the slam2d
 // types VertexSE2, VertexPointXY, EdgeSE2, EdgeSE2PointXY and the sba types VertexSE3Expmap, VertexSBAPointXYZ, EdgeProjectXYZ2UV (+ CameraParameters),
-// EdgeSE3ProjectXYZ, EdgeSE3Expmap and the slam3d types VertexSE3, EdgeSE3, compiled unmodified from /root/reference against the Eigen stand-in in
+// EdgeSE3ProjectXYZ, EdgeSE3Expmap, the slam3d types VertexSE3, EdgeSE3 and the BAL types of examples/bal/bal_example.cpp, compiled unmodified from /root/reference against the Eigen stand-in in
 // oracle/eigen_shim (NOT Eigen; see its Core header) by `make -C oracle ref_core` into oracle/_ref/libg2o_ref_core.so.
 // This file only builds a g2o::SparseOptimizer from the flat graph layout of include/g2ocu.h, runs optimize() and reads the results back.
 // tests/test_reference_core.py compares the oracle (and through it the CUDA path) with what comes out of here.
@@ -25,6 +25,15 @@
 #include "g2o/types/slam2d/edge_se2_pointxy.h"
 #include "g2o/types/slam2d/vertex_point_xy.h"
 #include "g2o/types/slam2d/vertex_se2.h"
+
+// the BAL types come from g2o/examples/bal/bal_example.cpp through oracle/ref_core_bal.cpp
+extern "C" {
+g2o::OptimizableGraph::Vertex* refbal_new_camera(const double* est9);
+g2o::OptimizableGraph::Vertex* refbal_new_point(const double* est3);
+g2o::OptimizableGraph::Edge* refbal_new_edge(const double* z2, const double* info4);
+void refbal_camera_estimate(const g2o::OptimizableGraph::Vertex* v, double* out9);
+void refbal_point_estimate(const g2o::OptimizableGraph::Vertex* v, double* out3);
+}
 
 namespace {
 
@@ -61,13 +70,14 @@ template <class BlockSolverT> std::unique_ptr<BlockSolverT> makeBlockSolver() {
 
 extern "C" {
 
-// algorithm: "gn" | "lm" | "dl"; blockSolver: "3_2" | "6_3" (BlockSolver<BlockSolverTraits<P,L>>) | "var" (BlockSolverX); linear solver: LinearSolverPCG
+// algorithm: "gn" | "lm" | "dl"; blockSolver: "3_2" | "6_3" | "9_3" (BlockSolver<BlockSolverTraits<P,L>>) | "var" (BlockSolverX); linear solver: LinearSolverPCG
 void* refcore_create(const FlatGraph* g, const char* algorithm, const char* blockSolver) {
   std::unique_ptr<Handle> h(new Handle);
   const std::string alg(algorithm), bs(blockSolver);
   std::unique_ptr<g2o::BlockSolverBase> solver;
   if (bs == "3_2") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<3, 2> > >();
   else if (bs == "6_3") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<6, 3> > >();
+  else if (bs == "9_3") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<9, 3> > >();   // bal_example.cpp:301
   else if (bs == "var") solver = makeBlockSolver<g2o::BlockSolverX>();
   else return nullptr;
   g2o::OptimizationAlgorithm* a = nullptr;
@@ -86,7 +96,9 @@ void* refcore_create(const FlatGraph* g, const char* algorithm, const char* bloc
       g2o::VertexSE3Expmap* p = new g2o::VertexSE3Expmap; g2o::Vector7 a; for (int k = 0; k < 7; ++k) a[k] = g->v_estimate[eo + k];
       g2o::SE3Quat T; T.fromVector(a); p->setEstimate(T); eo += 7; v = p;
     } else if (g->v_type[i] == 5) { g2o::VertexSBAPointXYZ* p = new g2o::VertexSBAPointXYZ; p->setEstimate(g2o::Vector3(g->v_estimate[eo], g->v_estimate[eo + 1], g->v_estimate[eo + 2])); eo += 3; v = p; }
-    else return nullptr;                                    // slam2d, slam3d and sba types only
+    else if (g->v_type[i] == 6) { v = refbal_new_camera(g->v_estimate + eo); eo += 9; }
+    else if (g->v_type[i] == 7) { v = refbal_new_point(g->v_estimate + eo); eo += 3; }
+    else return nullptr;
     v->setId(g->v_id[i]); v->setFixed(g->v_fixed[i] != 0); v->setMarginalized(g->v_marginalized[i] != 0);
     if (!h->optimizer.addVertex(v)) return nullptr;
     h->vertices.push_back(v); h->vtype.push_back(g->v_type[i]);
@@ -129,7 +141,8 @@ void* refcore_create(const FlatGraph* g, const char* algorithm, const char* bloc
         p->fx = g->e_param[po]; p->fy = g->e_param[po + 1]; p->cx = g->e_param[po + 2]; p->cy = g->e_param[po + 3]; po += 4; e = p;
       }
       mo += 2; io += 4;
-    } else return nullptr;
+    } else if (g->e_type[i] == 7) { e = refbal_new_edge(g->e_measurement + mo, g->e_information + io); mo += 2; io += 4; }   // EdgeObservationBAL (camera, point)
+    else return nullptr;
     e->setVertex(0, h->vertices[g->e_v0[i]]); e->setVertex(1, h->vertices[g->e_v1[i]]);
     e->setLevel(g->e_level ? g->e_level[i] : 0);
     const int kernel = g->e_kernel ? g->e_kernel[i] : 0;
@@ -177,6 +190,8 @@ void refcore_estimates(void* hh, double* out) {
     else if (h->vtype[i] == 3) { const g2o::Isometry3& e = static_cast<g2o::VertexSE3*>(h->vertices[i])->estimate();
       for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) out[o++] = e.linear()(r, c); for (int r = 0; r < 3; ++r) out[o++] = e.translation()[r]; }
     else if (h->vtype[i] == 4) { const g2o::Vector7 e = static_cast<g2o::VertexSE3Expmap*>(h->vertices[i])->estimate().toVector(); for (int k = 0; k < 7; ++k) out[o++] = e[k]; }
+    else if (h->vtype[i] == 6) { refbal_camera_estimate(h->vertices[i], out + o); o += 9; }
+    else if (h->vtype[i] == 7) { refbal_point_estimate(h->vertices[i], out + o); o += 3; }
     else { const g2o::Vector3& e = static_cast<g2o::VertexSBAPointXYZ*>(h->vertices[i])->estimate(); out[o++] = e[0]; out[o++] = e[1]; out[o++] = e[2]; }
   }
 }

@@ -3,7 +3,7 @@ g2o/stuff, LinearSolverPCG and the slam2d, slam3d (VertexSE3, EdgeSE3) and sba t
 compiled unmodified from /root/reference into oracle/_ref/libg2o_ref_core.so against
 the stand-in for the absent Eigen3 (oracle/eigen_shim, NOT Eigen: eager fixed-size and dynamic arithmetic, see its Core header), with
 oracle/ref_core.cpp building the graph from the flat layout.  The oracle must reproduce what the reference does on the same 2-D SLAM and
-bundle-adjustment graphs and 3-D pose graphs (among them BASELINE.json's config C1, ba_demo with BlockSolver_6_3, and sphere graphs as in C2): index map, chi2 per iteration, number of LM trials, number of PCG iterations per solve, lambda, trust region, final estimates.
+bundle-adjustment graphs and 3-D pose graphs (among them BASELINE.json's config C1, ba_demo with BlockSolver_6_3, sphere graphs as in C2 and BAL graphs with the code of C3): index map, chi2 per iteration, number of LM trials, number of PCG iterations per solve, lambda, trust region, final estimates.
 The machinery checked this way (buildStructure, constructQuadraticForm with robust kernels, Schur complement, PCG with its carried
 residual, back-substitution, LM / Dogleg control) is the same for every vertex and edge type."""
 import numpy as np
@@ -56,6 +56,12 @@ CASES = {
     "sphere_lm": (lambda: W.sphere(nodes_per_level=16, laps=8), "lm", "var"),
     "sphere_small_gn": (lambda: W.sphere(nodes_per_level=10, laps=5), "gn", "var"),
     "sphere_small_dogleg": (lambda: W.sphere(nodes_per_level=10, laps=5), "dl", "var"),
+    # the BAL camera edge of examples/bal/bal_example.cpp (ceres autodiff Jacobian), BlockSolver<9,3> + PCG + LM: the code of BASELINE config C3
+    "bal_small_huber": (lambda: W.bal_small(), "lm", "9_3"),
+    "bal_medium_huber": (lambda: W.bal_synthetic(n_cameras=60, n_points=6000, n_obs=30000, seed=5, k_max=40, min_window=4), "lm", "9_3"),
+    "bal_ring_long_tracks": (lambda: W.bal_synthetic(n_cameras=150, n_points=8000, n_obs=60000, seed=9, k_max=120, min_window=6), "lm", "9_3"),
+    "bal_no_kernel_gn": (lambda: W.bal_synthetic(n_cameras=20, n_points=800, n_obs=4000, seed=2, k_max=12, min_window=4, huber_delta=None), "gn", "9_3"),
+    "bal_points_free": (lambda: _points_free(W.bal_small()), "lm", "var"),
 }
 
 
