@@ -3,7 +3,7 @@
 BAL-Venice-shaped bundle adjustment).
 
     python bench.py --gpus N --steps K --warmup W          # our CUDA backend (N>1: launched under torchrun)
-    python bench.py --impl reference --steps K --warmup W  # the reference's CPU algorithm (oracle port) on the host cores
+    python bench.py --impl reference --steps K --warmup W  # the reference itself (oracle/_ref/libg2o_ref_core.so, else the oracle port) on the host cores
 
 A step is one outer Levenberg-Marquardt iteration (`OptimizationAlgorithmLevenberg::solve`, all its trials) of
 config C3: 1778 cameras / 993 923 points / 5 001 946 observations, BlockSolver<9,3> + PCG, Huber(1.0), synthetic.
@@ -123,29 +123,62 @@ def fp64_tensor_peak():
 
 
 def run_reference(args):
-    """The reference's CPU algorithm on the host cores: the oracle port (the reference itself needs Eigen3, absent here) with
-    OpenMP at the reference's pragma sites and all host threads.  Bounded sample: at most 1 warm-up + 3 timed LM iterations
-    of the full workload (a steady-state CPU iteration takes ~15 s on 8 cores; iteration 0 also pays buildStructure)."""
+    """The reference's own CPU implementation on the host cores.  When oracle/_ref/libg2o_ref_core.so exists (built from /root/reference by
+    `make -C oracle ref_core`: g2o/core + BlockSolver + LinearSolverPCG + the types, unmodified, against the stand-in for the absent Eigen3,
+    OpenMP on) that is the real reference: SparseOptimizer::optimize with OptimizationAlgorithmLevenberg over BlockSolver<9,3> + PCG, as
+    examples/bal/bal_example.cpp sets it up.  Otherwise the oracle port.  Bounded sample: at most 1 warm-up + 3 timed LM iterations of the
+    full workload (iteration 0 also pays buildStructure and is never timed); per-iteration times are G2OBatchStatistics::timeIteration."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import numpy as np
     g, desc = workload(args.workload, args.scale)
-    from oracle.oracle import Oracle, max_threads
-    threads = max_threads()
-    warm, steps = min(args.warmup, 1), max(1, min(args.steps, 3))
-    o = Oracle(g, "lm", "pcg", threads=threads)
-    o.initialize_optimization()
-    n, stats = o.optimize(warm + steps)
-    times = [s["timeIteration"] for s in stats]
-    timed = times[warm:] if len(times) > warm else times
-    value = len(timed) / sum(timed) if timed else 0.0
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed), "warmup": min(warm, len(times)),
+    from oracle import oracle as orc
+    threads = orc.max_threads()
+    warm, steps = 1, max(1, min(args.steps, 3))
+
+    def timed_part(stats):
+        times = [s["timeIteration"] for s in stats]
+        timed = times[warm:] if len(times) > warm else times
+        return timed, (len(timed) / sum(timed) if timed and sum(timed) > 0 else 0.0)
+
+    kind, solver, extra = "port", "CPU oracle port of BlockSolver + LinearSolverPCG (oracle/g2o_oracle.cpp)", {}
+    stats = None
+    if orc.reference_core() is not None:
+        vt = set(int(t) for t in np.unique(g.v_type)); marg = bool(np.any(g.v_marginalized))
+        bs = "9_3" if marg and 6 in vt else "6_3" if marg and 4 in vt else "3_2" if marg and 1 in vt else "var"
+        try:
+            ref = orc.ReferenceG2o(g, "lm", bs)
+            if ref.initialize_optimization():
+                n, stats = ref.optimize(warm + steps)
+                kind = "reference"
+                solver = f"the reference itself: SparseOptimizer + OptimizationAlgorithmLevenberg + BlockSolver<{bs.replace("_", ",")}> + LinearSolverPCG compiled from /root/reference (Eigen3 replaced by oracle/eigen_shim, OpenMP, -O3)"
+        except Exception as e:      # fall back to the port, say why
+            extra["reference_error"] = str(e)[:200]
+            stats = None
+    if stats is None:
+        o = orc.Oracle(g, "lm", "pcg", threads=threads)
+        o.initialize_optimization()
+        n, stats = o.optimize(warm + steps)
+    timed, value = timed_part(stats)
+    if kind == "reference" and not args.no_cpu:      # the port on the same sample, for comparison
+        try:
+            o = orc.Oracle(g, "lm", "pcg", threads=threads)
+            o.initialize_optimization()
+            _, pstats = o.optimize(warm + steps)
+            ptimed, pvalue = timed_part(pstats)
+            extra["port"] = {"value": pvalue, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": 1e3 * sum(ptimed) / max(len(ptimed), 1),
+                             "chi2": [s["chi2"] for s in pstats]}
+        except Exception as e:
+            extra["port_error"] = str(e)[:200]
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed), "warmup": min(warm, len(stats)),
             "ms_per_step": 1e3 * sum(timed) / max(len(timed), 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": desc, "solver": "CPU oracle port of BlockSolver<9,3> + LinearSolverPCG (reference cannot be compiled: Eigen3 absent)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{len(timed)} LM iteration(s) of the full workload after {min(warm, len(times))} warm-up iteration(s) (requested steps={args.steps}, warmup={args.warmup}; capped to keep the run within minutes)"},
+            "data": "synthetic", "config": {"workload": desc, "solver": solver},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                             "sample": f"{len(timed)} LM iteration(s) of the full workload after {min(warm, len(stats))} warm-up iteration(s) (requested steps={args.steps}, warmup={args.warmup}; capped to keep the run within minutes)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
             "chi2": [s["chi2"] for s in stats]}
+    line.update(extra)
     print(json.dumps(line), flush=True)
 
 

@@ -165,9 +165,9 @@ class ReferenceG2o:
         return bool(self._L.refcore_initialize_optimization(self._h, level))
 
     def optimize(self, iterations: int):
-        buf = np.zeros((max(iterations, 1), 6))
+        buf = np.zeros((max(iterations, 1), 8))
         n = self._L.refcore_optimize(self._h, iterations, _dp(buf))
-        keys = ("chi2", "levenbergIterations", "iterationsLinearSolver", "hessianPoseDimension", "hessianLandmarkDimension", "iteration")
+        keys = ("chi2", "levenbergIterations", "iterationsLinearSolver", "hessianPoseDimension", "hessianLandmarkDimension", "iteration", "timeIteration", "timeLinearSolution")
         return n, [dict(zip(keys, row)) for row in buf[:max(n, 0)]]
 
     def current_lambda(self) -> float: return self._L.refcore_current_lambda(self._h)
