@@ -148,7 +148,7 @@ def run_reference(args):
         vt = set(int(t) for t in np.unique(g.v_type)); marg = bool(np.any(g.v_marginalized))
         bs = "9_3" if marg and 6 in vt else "6_3" if marg and 4 in vt else "3_2" if marg and 1 in vt else "var"
         try:
-            ref = orc.ReferenceG2o(g, "lm", bs)
+            ref = orc.ReferenceG2o(g, "lm", bs, threads=threads)
             if ref.initialize_optimization():
                 n, stats = ref.optimize(warm + steps)
                 kind = "reference"
@@ -195,7 +195,7 @@ def cpu_sample(g):
         try:
             vt = set(int(t) for t in np.unique(g.v_type)); marg = bool(np.any(g.v_marginalized))
             bs = "9_3" if marg and 6 in vt else "6_3" if marg and 4 in vt else "3_2" if marg and 1 in vt else "var"
-            ref = orc.ReferenceG2o(g, "lm", bs)
+            ref = orc.ReferenceG2o(g, "lm", bs, threads=threads)
             if ref.initialize_optimization():
                 _, cstats = ref.optimize(2)
                 kind = "reference"

@@ -132,6 +132,8 @@ def reference_core():
         L.refcore_create.restype = ctypes.c_void_p
         L.refcore_create.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
         L.refcore_destroy.argtypes = [ctypes.c_void_p]; L.refcore_destroy.restype = None
+        L.refcore_set_num_threads.argtypes = [ctypes.c_int]; L.refcore_set_num_threads.restype = None
+        L.refcore_set_pcg.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_int, ctypes.c_int]; L.refcore_set_pcg.restype = None
         L.refcore_initialize_optimization.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.refcore_optimize.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         for f in ("refcore_current_lambda", "refcore_active_robust_chi2", "refcore_active_chi2"):
@@ -146,10 +148,12 @@ class ReferenceG2o:
     """The real reference on a 2-D SLAM graph: ``g2o::SparseOptimizer`` + ``BlockSolver`` (``"3_2"`` or ``"var"``) + ``LinearSolverPCG`` +
     Levenberg / Gauss-Newton / Dogleg, through oracle/ref_core.cpp."""
 
-    def __init__(self, graph, algorithm: str = "lm", block_solver: str = "3_2"):
+    def __init__(self, graph, algorithm: str = "lm", block_solver: str = "3_2", threads: int = 0):
+        """``threads`` > 0 fixes the number of OpenMP threads of the reference (1 = deterministic summation order); 0 leaves the default (all)."""
         self._L = reference_core()
         if self._L is None:
             raise RuntimeError("oracle/_ref/libg2o_ref_core.so has not been built")
+        self._L.refcore_set_num_threads(int(threads))
         self.graph = graph
         cg = graph.as_c()
         self._h = self._L.refcore_create(ctypes.byref(cg), algorithm.encode(), block_solver.encode())
@@ -169,6 +173,9 @@ class ReferenceG2o:
         n = self._L.refcore_optimize(self._h, iterations, _dp(buf))
         keys = ("chi2", "levenbergIterations", "iterationsLinearSolver", "hessianPoseDimension", "hessianLandmarkDimension", "iteration", "timeIteration", "timeLinearSolution")
         return n, [dict(zip(keys, row)) for row in buf[:max(n, 0)]]
+
+    def set_pcg_params(self, tol=1e-6, max_iter=-1, absolute=True):
+        self._L.refcore_set_pcg(self._h, tol, max_iter, int(absolute))
 
     def current_lambda(self) -> float: return self._L.refcore_current_lambda(self._h)
     def active_robust_chi2(self) -> float: return self._L.refcore_active_robust_chi2(self._h)

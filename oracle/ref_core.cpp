@@ -5,8 +5,12 @@
 // oracle/eigen_shim (NOT Eigen; see its Core header) by `make -C oracle ref_core` into oracle/_ref/libg2o_ref_core.so.
 // This file only builds a g2o::SparseOptimizer from the flat graph layout of include/g2ocu.h, runs optimize() and reads the results back.
 // tests/test_reference_core.py compares the oracle (and through it the CUDA path) with what comes out of here.
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
@@ -57,12 +61,16 @@ struct Handle {
   std::vector<int> vtype;
   g2o::OptimizationAlgorithmLevenberg* lm = nullptr;
   g2o::OptimizationAlgorithmDogleg* dl = nullptr;
+  std::function<void(double, int, bool)> setPcg;             // LinearSolverPCG::setTolerance / setMaxIterations / setAbsoluteTolerance
   std::vector<std::vector<double> > cameras;                 // distinct (f, cx, cy) of the EdgeProjectXYZ2UV edges -> parameter id
   std::string err;
 };
 
-template <class BlockSolverT> std::unique_ptr<BlockSolverT> makeBlockSolver() {
-  std::unique_ptr<g2o::LinearSolverPCG<typename BlockSolverT::PoseMatrixType> > linear(new g2o::LinearSolverPCG<typename BlockSolverT::PoseMatrixType>());
+template <class BlockSolverT> std::unique_ptr<BlockSolverT> makeBlockSolver(std::function<void(double, int, bool)>& setPcg) {
+  typedef g2o::LinearSolverPCG<typename BlockSolverT::PoseMatrixType> Pcg;
+  std::unique_ptr<Pcg> linear(new Pcg());
+  Pcg* raw = linear.get();                                   // owned by the block solver, which the algorithm owns, which the optimizer owns
+  setPcg = [raw](double tol, int maxIter, bool absolute) { raw->setTolerance(tol); raw->setMaxIterations(maxIter); raw->setAbsoluteTolerance(absolute); };
   return std::unique_ptr<BlockSolverT>(new BlockSolverT(std::move(linear)));
 }
 
@@ -75,10 +83,10 @@ void* refcore_create(const FlatGraph* g, const char* algorithm, const char* bloc
   std::unique_ptr<Handle> h(new Handle);
   const std::string alg(algorithm), bs(blockSolver);
   std::unique_ptr<g2o::BlockSolverBase> solver;
-  if (bs == "3_2") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<3, 2> > >();
-  else if (bs == "6_3") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<6, 3> > >();
-  else if (bs == "9_3") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<9, 3> > >();   // bal_example.cpp:301
-  else if (bs == "var") solver = makeBlockSolver<g2o::BlockSolverX>();
+  if (bs == "3_2") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<3, 2> > >(h->setPcg);
+  else if (bs == "6_3") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<6, 3> > >(h->setPcg);
+  else if (bs == "9_3") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<9, 3> > >(h->setPcg);   // bal_example.cpp:301
+  else if (bs == "var") solver = makeBlockSolver<g2o::BlockSolverX>(h->setPcg);
   else return nullptr;
   g2o::OptimizationAlgorithm* a = nullptr;
   if (alg == "lm") a = h->lm = new g2o::OptimizationAlgorithmLevenberg(std::move(solver));
@@ -157,6 +165,16 @@ void* refcore_create(const FlatGraph* g, const char* algorithm, const char* bloc
   return h.release();
 }
 void refcore_destroy(void* hh) { delete (Handle*)hh; }
+// LinearSolverPCG properties (linear_solver_pcg.h:53-57 defaults: 1e-6, -1, absolute)
+void refcore_set_pcg(void* hh, double tolerance, int maxIterations, int absoluteTolerance) { Handle* h = (Handle*)hh; if (h->setPcg) h->setPcg(tolerance, maxIterations, absoluteTolerance != 0); }
+// threads of the reference's OpenMP regions (its summation order, hence its last digits, depends on them); 0 or less: leave as is
+void refcore_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 
 int refcore_initialize_optimization(void* hh, int level) { return ((Handle*)hh)->optimizer.initializeOptimization(level) ? 1 : 0; }
 

