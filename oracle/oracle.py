@@ -39,7 +39,11 @@ def build(force: bool = False) -> None:
         so = os.path.join(ref, name)
         return force or not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in shim)
 
-    for target, name in (("ref", "libg2o_ref_leaves.so"), ("ref_core", "libg2o_ref_core.so")):      # ref also builds libcsparse_ref.so
+    shim.append(os.path.join(os.path.dirname(_HERE), "g2o_b200", "host", "real_g2o_adapter", "solver_cuda.cpp"))
+    # ref also builds libcsparse_ref.so; ref_adapter = the CUDA plugin for the real g2o against the reference's headers (needs libg2ocu.so)
+    for target, name in (("ref", "libg2o_ref_leaves.so"), ("ref_core", "libg2o_ref_core.so"), ("ref_adapter", "libg2o_solver_cuda.so")):
+        if target == "ref_adapter" and not os.path.exists(os.path.join(os.path.dirname(_HERE), "g2o_b200", "lib", "libg2ocu.so")):
+            continue
         if outdated(name) or not os.path.exists(os.path.join(ref, "libcsparse_ref.so")):
             r = subprocess.run(["make", "-C", _HERE, target], capture_output=True, text=True)
             if r.returncode != 0 or not os.path.exists(os.path.join(ref, name)):

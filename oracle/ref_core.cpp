@@ -17,6 +17,7 @@
 
 #include "g2o/core/block_solver.h"
 #include "g2o/core/optimization_algorithm_dogleg.h"
+#include "g2o/core/optimization_algorithm_factory.h"
 #include "g2o/core/optimization_algorithm_gauss_newton.h"
 #include "g2o/core/optimization_algorithm_levenberg.h"
 #include "g2o/core/robust_kernel_factory.h"
@@ -78,6 +79,7 @@ template <class BlockSolverT> std::unique_ptr<BlockSolverT> makeBlockSolver(std:
 
 extern "C" {
 
+// algorithm: "factory" with blockSolver = a name known to OptimizationAlgorithmFactory (plugins), or
 // algorithm: "gn" | "lm" | "dl"; blockSolver: "3_2" | "6_3" | "9_3" (BlockSolver<BlockSolverTraits<P,L>>) | "var" (BlockSolverX); linear solver: LinearSolverPCG
 void* refcore_create(const FlatGraph* g, const char* algorithm, const char* blockSolver) {
   std::unique_ptr<Handle> h(new Handle);
@@ -87,12 +89,17 @@ void* refcore_create(const FlatGraph* g, const char* algorithm, const char* bloc
   else if (bs == "6_3") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<6, 3> > >(h->setPcg);
   else if (bs == "9_3") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<9, 3> > >(h->setPcg);   // bal_example.cpp:301
   else if (bs == "var") solver = makeBlockSolver<g2o::BlockSolverX>(h->setPcg);
-  else return nullptr;
+  else if (alg != "factory") return nullptr;
   g2o::OptimizationAlgorithm* a = nullptr;
+  if (alg == "factory") {      // a solver registered with the reference's OptimizationAlgorithmFactory, e.g. by the CUDA plugin libg2o_solver_cuda.so
+    g2o::OptimizationAlgorithmProperty prop;
+    a = g2o::OptimizationAlgorithmFactory::instance()->construct(bs, prop);
+    if (!a) return nullptr;
+  } else
   if (alg == "lm") a = h->lm = new g2o::OptimizationAlgorithmLevenberg(std::move(solver));
   else if (alg == "gn") a = new g2o::OptimizationAlgorithmGaussNewton(std::move(solver));
   else if (alg == "dl") a = h->dl = new g2o::OptimizationAlgorithmDogleg(std::move(solver));
-  else return nullptr;
+  else if (alg != "factory") return nullptr;
   h->optimizer.setAlgorithm(a);
   size_t eo = 0;
   for (int i = 0; i < g->n_vertices; ++i) {

@@ -151,3 +151,37 @@ def test_edge_levels_are_respected():
         if ok_r and level == 0:
             n_r, st_r = ref.optimize(3); n_o, st_o = o.optimize(3)
             assert n_r == n_o and all(abs(a["chi2"] - b["chi2"]) <= 1e-9 * b["chi2"] for a, b in zip(st_o, st_r))
+
+
+def test_real_g2o_adapter_plugs_into_the_reference_factory():
+    """g2o_b200/host/real_g2o_adapter/solver_cuda.cpp - the plugin a g2o maintainer adds - compiled against the reference's own
+    headers (`make -C oracle ref_adapter`) and loaded next to the reference core: its solvers are constructed by the reference's
+    OptimizationAlgorithmFactory and driven by the reference's SparseOptimizer::optimize.  Without a GPU the backend refuses loudly (init /
+    solve fail, optimize() reports it); with one, the same call runs the CUDA path."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, "oracle", "_ref", "libg2o_solver_cuda.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libg2o_solver_cuda.so was not built")
+    code = ("import ctypes, sys\n"
+            "from oracle import oracle\n"
+            "from g2o_b200 import workloads as W\n"
+            "import torch\n"
+            "oracle.reference_core()\n"
+            f"ad = ctypes.CDLL({so!r})\n"
+            "assert hasattr(ad, 'g2o_optimization_library_cuda') and hasattr(ad, 'g2o_optimization_algorithm_lm_fix6_3_cuda')\n"
+            "g = W.sphere(nodes_per_level=8, laps=4)\n"
+            "ref = oracle.ReferenceG2o(g, 'factory', 'lm_var_cuda')\n"
+            "assert ref.initialize_optimization()\n"
+            "n, st = ref.optimize(3)\n"
+            "print('GPU' if torch.cuda.is_available() else 'NOGPU', n)\n"
+            "try:\n"
+            "    oracle.ReferenceG2o(g, 'factory', 'lm_var_cholmod'); print('BAD')\n"
+            "except ValueError:\n"
+            "    print('UNKNOWN_REJECTED')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "UNKNOWN_REJECTED" in r.stdout
+    if "NOGPU" in r.stdout:
+        assert "NOGPU 0" in r.stdout or "NOGPU -1" in r.stdout                     # optimize() reports the failure
+        assert "no usable CUDA device" in r.stderr and "no CPU fallback" in r.stderr
