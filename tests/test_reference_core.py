@@ -185,3 +185,34 @@ def test_real_g2o_adapter_plugs_into_the_reference_factory():
     if "NOGPU" in r.stdout:
         assert "NOGPU 0" in r.stdout or "NOGPU -1" in r.stdout                     # optimize() reports the failure
         assert "no usable CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="first GPU run of the real g2o + CUDA plugin pairing: built and CPU-checked in round 1, not yet run on a GPU")
+def test_real_g2o_with_the_cuda_plugin_matches_real_g2o_on_the_cpu():
+    """The drop-in itself: the reference's SparseOptimizer (compiled from /root/reference) optimises the same graph once with its own
+    BlockSolver + PCG on the CPU and once with the `*_cuda` solver from the plugin library; chi2 per iteration (evaluated by the reference on the
+    host from the written-back estimates) and the final estimates must agree within BASELINE's gate."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, "oracle", "_ref", "libg2o_solver_cuda.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libg2o_solver_cuda.so was not built")
+    code = ("import ctypes, numpy as np\n"
+            "from oracle import oracle\n"
+            "from g2o_b200 import workloads as W\n"
+            "oracle.reference_core()\n"
+            f"ctypes.CDLL({so!r})\n"
+            "cases = [(W.sphere(nodes_per_level=10, laps=5), 'var', 'lm_var_cuda'), (W.ba_demo(num_cameras=8, num_points=80), '6_3', 'lm_fix6_3_cuda'),\n"
+            "         (W.slam2d(n_poses=200, n_landmarks=60, world_size=16.0), '3_2', 'lm_fix3_2_cuda')]\n"
+            "for g, bs, name in cases:\n"
+            "    cpu = oracle.ReferenceG2o(g, 'lm', bs, threads=1); assert cpu.initialize_optimization(); n1, s1 = cpu.optimize(5)\n"
+            "    gpu = oracle.ReferenceG2o(g, 'factory', name); assert gpu.initialize_optimization(); n2, s2 = gpu.optimize(5)\n"
+            "    assert n1 == n2, (name, n1, n2)\n"
+            "    for i, (a, b) in enumerate(zip(s2, s1)):\n"
+            "        assert abs(a['chi2'] - b['chi2']) <= (1e-8 if i == 0 else 1e-6) * b['chi2'], (name, i, a['chi2'], b['chi2'])\n"
+            "    e1, e2 = cpu.estimates(), gpu.estimates()\n"
+            "    assert np.max(np.abs(e1 - e2) / (1 + np.abs(e1))) < 1e-6, name\n"
+            "print('PAIRING_OK')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=180)
+    assert r.returncode == 0 and "PAIRING_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
