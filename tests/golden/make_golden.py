@@ -2,9 +2,10 @@
 
     python tests/golden/make_golden.py          (adds the cases missing from the file; --all regenerates every case)
 
-The reference holds no fixtures for this path and cannot be compiled here (no Eigen3), so these are
-*oracle-generated* regression vectors: they pin the oracle against accidental change and give the GPU tests a fixed target
-that does not need the oracle at all.  Inputs are the seeded synthetic graphs of g2o_b200/workloads.py."""
+The reference holds no fixtures for this path.  The vectors are written by the oracle; tests/test_golden.py checks that the
+REAL reference (oracle/_ref/libg2o_ref_core.so: g2o/core + BlockSolver + LM / GN + LinearSolverPCG + the types compiled from /root/reference)
+reproduces every PCG case of them - so the GPU tests, which only read this file, compare the CUDA path with what the reference itself
+produces, without needing the reference or the oracle on the GPU box.  Inputs are the seeded synthetic graphs of g2o_b200/workloads.py."""
 import json
 import os
 import sys
