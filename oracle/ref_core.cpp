@@ -22,6 +22,7 @@
 #include "g2o/core/optimization_algorithm_levenberg.h"
 #include "g2o/core/robust_kernel_factory.h"
 #include "g2o/core/sparse_optimizer.h"
+#include "g2o/solvers/csparse/linear_solver_csparse.h"
 #include "g2o/solvers/pcg/linear_solver_pcg.h"
 #include "g2o/types/sba/types_six_dof_expmap.h"
 #include "g2o/types/slam3d/edge_se3.h"
@@ -75,12 +76,21 @@ template <class BlockSolverT> std::unique_ptr<BlockSolverT> makeBlockSolver(std:
   return std::unique_ptr<BlockSolverT>(new BlockSolverT(std::move(linear)));
 }
 
+// BlockSolver + LinearSolverCSparse (solvers/csparse/solver_csparse.cpp:44-52): block ordering for the fixed-size solvers, scalar AMD for `var`
+template <class BlockSolverT> std::unique_ptr<BlockSolverT> makeCSparseBlockSolver(bool blockOrdering) {
+  typedef g2o::LinearSolverCSparse<typename BlockSolverT::PoseMatrixType> Chol;
+  std::unique_ptr<Chol> linear(new Chol());
+  linear->setBlockOrdering(blockOrdering);
+  return std::unique_ptr<BlockSolverT>(new BlockSolverT(std::move(linear)));
+}
+
 }  // namespace
 
 extern "C" {
 
 // algorithm: "factory" with blockSolver = a name known to OptimizationAlgorithmFactory (plugins), or
-// algorithm: "gn" | "lm" | "dl"; blockSolver: "3_2" | "6_3" | "9_3" (BlockSolver<BlockSolverTraits<P,L>>) | "var" (BlockSolverX); linear solver: LinearSolverPCG
+// algorithm: "gn" | "lm" | "dl"; blockSolver: "3_2" | "6_3" | "9_3" (BlockSolver<BlockSolverTraits<P,L>>) | "var" (BlockSolverX) with LinearSolverPCG, or the same
+// names + "_csparse" with LinearSolverCSparse (the reference's gn_/lm_fixP_L and lm_var solvers, solvers/csparse/solver_csparse.cpp)
 void* refcore_create(const FlatGraph* g, const char* algorithm, const char* blockSolver) {
   std::unique_ptr<Handle> h(new Handle);
   const std::string alg(algorithm), bs(blockSolver);
@@ -89,6 +99,10 @@ void* refcore_create(const FlatGraph* g, const char* algorithm, const char* bloc
   else if (bs == "6_3") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<6, 3> > >(h->setPcg);
   else if (bs == "9_3") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<9, 3> > >(h->setPcg);   // bal_example.cpp:301
   else if (bs == "var") solver = makeBlockSolver<g2o::BlockSolverX>(h->setPcg);
+  else if (bs == "3_2_csparse") solver = makeCSparseBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<3, 2> > >(true);
+  else if (bs == "6_3_csparse") solver = makeCSparseBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<6, 3> > >(true);
+  else if (bs == "9_3_csparse") solver = makeCSparseBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<9, 3> > >(true);
+  else if (bs == "var_csparse") solver = makeCSparseBlockSolver<g2o::BlockSolverX>(false);
   else if (alg != "factory") return nullptr;
   g2o::OptimizationAlgorithm* a = nullptr;
   if (alg == "factory") {      // a solver registered with the reference's OptimizationAlgorithmFactory, e.g. by the CUDA plugin libg2o_solver_cuda.so

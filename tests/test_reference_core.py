@@ -140,6 +140,34 @@ def test_pose_graph_and_fixed_vertices():
         assert np.max(np.abs(o.estimates() - ref.estimates())) <= 1e-8 * (1 + np.max(np.abs(ref.estimates())))
 
 
+CSPARSE_CASES = {
+    # name: (graph, reference block solver + LinearSolverCSparse, oracle linear solver)
+    "ba_demo_c1_csparse": (lambda: W.ba_demo(), "6_3_csparse", "csparse_block"),                 # BASELINE configs[0]: ba_demo, BlockSolver_6_3 + LinearSolverCSparse
+    "sphere_lm_var": (lambda: W.sphere(nodes_per_level=16, laps=8), "var_csparse", "csparse"),   # configs[1]: create_sphere graph with the g2o CLI's lm_var (CSparse, scalar AMD)
+    "slam2d_fix3_2": (lambda: W.slam2d(n_poses=200, n_landmarks=60, world_size=16.0), "3_2_csparse", "csparse_block"),
+    "bal_9_3": (lambda: W.bal_small(), "9_3_csparse", "csparse_block"),
+}
+
+
+@pytest.mark.parametrize("name", list(CSPARSE_CASES))
+def test_oracle_reproduces_the_reference_with_its_csparse_solver(name):
+    """The reference's default solver family (solvers/csparse/solver_csparse.cpp: gn_/lm_fixP_L with block ordering, lm_var with scalar AMD),
+    LinearSolverCSparse + csparse_extension + the vendored CSparse, against the oracle's restatement of linear_solver_csparse.h."""
+    if not oracle.has_csparse():
+        pytest.skip("oracle/_ref/libcsparse_ref.so was not built")
+    fn, bs, olin = CSPARSE_CASES[name]
+    g = fn()
+    ref = oracle.ReferenceG2o(g, "lm", bs, threads=1); assert ref.initialize_optimization()
+    o = oracle.Oracle(g, "lm", olin); assert o.initialize_optimization()
+    n_r, st_r = ref.optimize(6); n_o, st_o = o.optimize(6)
+    assert n_r == n_o
+    for i, (a, b) in enumerate(zip(st_o, st_r)):
+        assert abs(a["chi2"] - b["chi2"]) <= 1e-9 * b["chi2"], (name, i, a["chi2"], b["chi2"])       # exact factorisations: no stopping rule in the way
+        assert int(a["levenbergIterations"]) == int(b["levenbergIterations"])
+    assert abs(st_o[-1]["lambda"] - ref.current_lambda()) <= 1e-9 * ref.current_lambda()
+    assert np.max(np.abs(o.estimates() - ref.estimates())) <= 1e-9 * (1 + np.max(np.abs(ref.estimates())))
+
+
 def test_edge_levels_are_respected():
     g = W.slam2d(n_poses=150, n_landmarks=40, world_size=14.0)
     g.e_level = np.zeros(g.n_edges, dtype=np.int32); g.e_level[::5] = 1                               # every fifth edge sits on level 1
