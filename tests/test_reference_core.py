@@ -244,3 +244,25 @@ def test_real_g2o_with_the_cuda_plugin_matches_real_g2o_on_the_cpu():
             "print('PAIRING_OK')\n")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=180)
     assert r.returncode == 0 and "PAIRING_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="direct CUDA-vs-compiled-reference comparison added at the end of round 1, not yet run on a GPU (both sides are verified against the oracle)")
+@pytest.mark.parametrize("name", ["ba_demo_c1", "bal_medium_huber", "sphere_lm", "schur_lm_huber", "points_free_lm"])
+def test_cuda_path_against_the_reference_itself(name):
+    """The CUDA path (through the C ABI) and the reference compiled from /root/reference, on the same graph in the same process."""
+    from g2o_b200.binding import CudaSolver
+    fn, alg, bs = CASES[name]
+    g = fn()
+    solver = {"6_3": "lm_fix6_3_cuda", "9_3": "lm_fix9_3_cuda", "3_2": "lm_fix3_2_cuda", "var": "lm_var_cuda"}[bs]
+    ref = oracle.ReferenceG2o(g, alg, bs, threads=1); assert ref.initialize_optimization()
+    s = CudaSolver(g, solver, device=0); s.initialize_optimization()
+    assert np.array_equal(ref.hessian_index(), s.get_i32("hessian_index"))
+    n_r, st_r = ref.optimize(6); n_s, st_s = s.optimize(6)
+    assert n_r == n_s
+    for i, (a, b) in enumerate(zip(st_s, st_r)):
+        assert abs(a["chi2"] - b["chi2"]) <= (1e-8 if i == 0 else 1e-6) * b["chi2"], (name, i, a["chi2"], b["chi2"])
+        assert a["levenberg_iterations"] == int(b["levenbergIterations"])
+    assert abs(st_s[-1]["lambda"] - ref.current_lambda()) <= 1e-6 * ref.current_lambda()
+    e_r = ref.estimates()
+    assert np.max(np.abs(s.get_estimates() - e_r) / (1.0 + np.abs(e_r))) < 1e-6
