@@ -177,7 +177,8 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                              "sample": f"{len(timed)} LM iteration(s) of the full workload after {min(warm, len(stats))} warm-up iteration(s) (requested steps={args.steps}, warmup={args.warmup}; capped to keep the run within minutes)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
-            "chi2": [s["chi2"] for s in stats]}
+            "chi2": [s["chi2"] for s in stats],
+            "phases_s": {k: stats[-1][k] for k in ("timeResiduals", "timeQuadraticForm", "timeSchurComplement", "timeLinearSolver", "timeUpdate")} if stats else None}
     line.update(extra)
     print(json.dumps(line), flush=True)
 
@@ -212,7 +213,7 @@ def cpu_sample(g):
     out = {"value": 1.0 / it, "unit": UNIT, "cores": threads, "kind": kind,
            "sample": f"LM iteration 1 of the same graph ({it:.2f} s; graph construction + optimize(2) took {secs:.1f} s incl. buildStructure in iteration 0){note}",
            "chi2": [c["chi2"] for c in cstats]}
-    if kind == "port" and cstats:
+    if cstats:      # G2OBatchStatistics of the timed iteration (both the reference and the port fill the same fields)
         out["phases_s"] = {k: cstats[-1][k] for k in ("timeResiduals", "timeQuadraticForm", "timeSchurComplement", "timeLinearSolver", "timeUpdate")}
     return out
 

@@ -185,9 +185,10 @@ class ReferenceG2o:
         return bool(self._L.refcore_initialize_optimization(self._h, level))
 
     def optimize(self, iterations: int):
-        buf = np.zeros((max(iterations, 1), 8))
+        buf = np.zeros((max(iterations, 1), 13))
         n = self._L.refcore_optimize(self._h, iterations, _dp(buf))
-        keys = ("chi2", "levenbergIterations", "iterationsLinearSolver", "hessianPoseDimension", "hessianLandmarkDimension", "iteration", "timeIteration", "timeLinearSolution")
+        keys = ("chi2", "levenbergIterations", "iterationsLinearSolver", "hessianPoseDimension", "hessianLandmarkDimension", "iteration", "timeIteration", "timeLinearSolution",
+                "timeResiduals", "timeQuadraticForm", "timeSchurComplement", "timeLinearSolver", "timeUpdate")
         return n, [dict(zip(keys, row)) for row in buf[:max(n, 0)]]
 
     def set_pcg_params(self, tol=1e-6, max_iter=-1, absolute=True):

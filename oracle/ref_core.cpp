@@ -199,17 +199,19 @@ void refcore_set_num_threads(int n) {
 
 int refcore_initialize_optimization(void* hh, int level) { return ((Handle*)hh)->optimizer.initializeOptimization(level) ? 1 : 0; }
 
-// SparseOptimizer::optimize(iterations); stats: iterations x 8 doubles from G2OBatchStatistics = chi2, levenbergIterations, iterationsLinearSolver,
-// hessianPoseDimension, hessianLandmarkDimension, iteration, timeIteration, timeLinearSolution (lambda is not in there: refcore_current_lambda)
+// SparseOptimizer::optimize(iterations); stats: iterations x 13 doubles from G2OBatchStatistics = chi2, levenbergIterations, iterationsLinearSolver,
+// hessianPoseDimension, hessianLandmarkDimension, iteration, timeIteration, timeLinearSolution, timeResiduals, timeQuadraticForm,
+// timeSchurComplement, timeLinearSolver, timeUpdate (lambda is not in there: refcore_current_lambda)
 int refcore_optimize(void* hh, int iterations, double* stats) {
   Handle* h = (Handle*)hh;
   h->optimizer.setComputeBatchStatistics(true);
   const int n = h->optimizer.optimize(iterations);
   const g2o::BatchStatisticsContainer& bs = h->optimizer.batchStatistics();
   for (size_t i = 0; i < bs.size() && (int)i < iterations; ++i) {
-    double* s = stats + 8 * i;
+    double* s = stats + 13 * i;
     s[0] = bs[i].chi2; s[1] = bs[i].levenbergIterations; s[2] = bs[i].iterationsLinearSolver; s[3] = (double)bs[i].hessianPoseDimension;
     s[4] = (double)bs[i].hessianLandmarkDimension; s[5] = bs[i].iteration; s[6] = bs[i].timeIteration; s[7] = bs[i].timeLinearSolution;
+    s[8] = bs[i].timeResiduals; s[9] = bs[i].timeQuadraticForm; s[10] = bs[i].timeSchurComplement; s[11] = bs[i].timeLinearSolver; s[12] = bs[i].timeUpdate;
   }
   return n;
 }
