@@ -132,8 +132,20 @@ def run_reference(args):
     if rank != 0:
         return
     import numpy as np
-    g, desc = workload(args.workload, args.scale)
     from oracle import oracle as orc
+    if orc.reference_core() is not None and not os.environ.get("G2O_BENCH_REFERENCE_CHILD"):
+        # the leg that drives the compiled reference runs in a child process; if it dies, this process still reports the oracle port
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], capture_output=True, text=True, timeout=1500,
+                               env=dict(os.environ, G2O_BENCH_REFERENCE_CHILD="1", RANK="0"))
+            if r.returncode == 0 and r.stdout.strip():
+                print(r.stdout.strip().splitlines()[-1], flush=True)
+                return
+            sys.stderr.write(f"bench: reference child failed (exit {r.returncode}): {r.stderr[-400:]}\n")
+        except Exception as e:
+            sys.stderr.write(f"bench: reference child failed: {e}\n")
+        orc.reference_core = lambda: None
+    g, desc = workload(args.workload, args.scale)
     threads = orc.max_threads()
     warm, steps = 1, max(1, min(args.steps, 3))
 
