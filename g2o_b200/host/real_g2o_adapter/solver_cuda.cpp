@@ -1,6 +1,7 @@
 // Adapter for the REAL g2o (B0Bftl/g2o) headers: compile this file inside the reference tree as
 //   g2o/solvers/cuda/solver_cuda.cpp  ->  libg2o_solver_cuda.so   (needs Eigen3 + the g2o headers; links libg2ocu.so)
-// It is NOT built in this repository (Eigen3 is not available here); the Eigen-free mirror in ../g2o_mirror.* has the same
+// Here it is compiled against the reference's headers with a stand-in for Eigen3 (`make -C oracle ref_adapter`, oracle/_ref/libg2o_solver_cuda.so,
+// tests/test_reference_core.py); a production build uses real Eigen3.  The Eigen-free mirror in ../g2o_mirror.* has the same
 // structure and is what the tests exercise.  See INTEGRATION.md for the CMake lines.
 //
 // What it does: packs SparseOptimizer::activeEdges()/indexMapping() into the flat g2ocu_graph, forwards every virtual of
