@@ -41,7 +41,7 @@ def build(force: bool = False) -> None:
 
     shim.append(os.path.join(os.path.dirname(_HERE), "g2o_b200", "host", "real_g2o_adapter", "solver_cuda.cpp"))
     # ref also builds libcsparse_ref.so; ref_adapter = the CUDA plugin for the real g2o against the reference's headers (needs libg2ocu.so)
-    for target, name in (("ref", "libg2o_ref_leaves.so"), ("ref_core", "libg2o_ref_core.so"), ("ref_adapter", "libg2o_solver_cuda.so")):
+    for target, name in (("ref", "libg2o_ref_leaves.so"), ("ref_core", "libg2o_ref_core.so"), ("ref_adapter", "libg2o_solver_cuda.so"), ("ref_tools", "create_sphere")):
         if target == "ref_adapter" and not os.path.exists(os.path.join(os.path.dirname(_HERE), "g2o_b200", "lib", "libg2ocu.so")):
             continue
         if outdated(name) or not os.path.exists(os.path.join(ref, "libcsparse_ref.so")):

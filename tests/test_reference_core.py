@@ -266,3 +266,42 @@ def test_cuda_path_against_the_reference_itself(name):
     assert abs(st_s[-1]["lambda"] - ref.current_lambda()) <= 1e-6 * ref.current_lambda()
     e_r = ref.estimates()
     assert np.max(np.abs(s.get_estimates() - e_r) / (1.0 + np.abs(e_r))) < 1e-6
+
+
+def test_sphere_workload_matches_the_reference_create_sphere_program(tmp_path):
+    """BASELINE config C2's graph generator: the reference's own create_sphere program (g2o/examples/sphere/create_sphere.cpp, compiled as it
+    lies into oracle/_ref/create_sphere) writes a .g2o file; g2o_b200.workloads.sphere must describe the same graph - vertices, topology,
+    noisy measurements (the two default-seeded samplers sharing one static distribution), information, odometry-chained initial guess - to
+    the six digits the file carries."""
+    import os, subprocess
+    from scipy.spatial.transform import Rotation
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "create_sphere")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/create_sphere was not built (make -C oracle ref_tools)")
+    out = tmp_path / "sphere.g2o"
+    r = subprocess.run([exe, "-o", str(out), "-nodesPerLevel", "16", "-laps", "8"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    rows = [[float(t) for t in line.split()] for line in open(out)]      # the tag is empty: the type factory is not populated in this build
+    verts = [v for v in rows if len(v) == 8]; edges = [e for e in rows if len(e) == 2 + 7 + 21]
+    g = W.sphere(nodes_per_level=16, laps=8)
+    assert len(verts) == g.n_vertices and len(edges) == g.n_edges and len(verts) + len(edges) == len(rows)
+
+    def close(a, b):      # six significant digits in the file
+        a, b = np.asarray(a), np.asarray(b)
+        return np.all(np.abs(a - b) <= 2e-5 * (1 + np.abs(b)))
+
+    est = g.v_estimate.reshape(-1, 12)
+    for k, (v, e) in enumerate(zip(verts, est)):
+        assert int(v[0]) == int(g.v_id[k])
+        R = e[:9].reshape(3, 3, order="F"); q = Rotation.from_matrix(R).as_quat()
+        qf = np.array(v[4:8]); qf = qf if np.dot(qf, q) >= 0 else -qf          # q and -q are the same rotation
+        assert close(v[1:4], e[9:12]) and close(qf, q), (v, e)
+    meas = g.e_measurement.reshape(-1, 12); info = g.e_information.reshape(-1, 6, 6)
+    for k, e in enumerate(edges):
+        assert int(e[0]) == int(g.v_id[g.e_v0[k]]) and int(e[1]) == int(g.v_id[g.e_v1[k]])
+        R = meas[k, :9].reshape(3, 3, order="F"); q = Rotation.from_matrix(R).as_quat()
+        qf = np.array(e[5:9]); qf = qf if np.dot(qf, q) >= 0 else -qf
+        assert close(e[2:5], meas[k, 9:12]) and close(qf, q), (k, e[:9], meas[k])
+        upper = [info[k].T[i, j] for i in range(6) for j in range(i, 6)]        # EdgeSE3::write: upper triangle, row by row
+        assert close(e[9:], upper)
