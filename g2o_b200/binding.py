@@ -16,18 +16,17 @@ from . import _lib
 from .graph import Graph
 
 # name -> (algorithm, poseDim, landmarkDim, requiresMarginalize); mirrors solvers/pcg/solver_pcg.cpp:41-98 and
-# solvers/csparse/solver_csparse.cpp:54-117 (the reference has no named 9_3 solver: bal_example.cpp:301 instantiates it)
+# solvers/csparse/solver_csparse.cpp:54-117 (the reference has no named 9_3 solver: bal_example.cpp:301 instantiates it).  The reference's
+# fix7_3 names (sim3) are not registered: the backend has no 7-dof types, and a name that cannot solve anything is worse than an unknown one.
 SOLVER_NAMES = {
     "gn_var_cuda": ("gn", -1, -1, False), "lm_var_cuda": ("lm", -1, -1, False),
     "gn_fix3_2_cuda": ("gn", 3, 2, True), "lm_fix3_2_cuda": ("lm", 3, 2, True),
     "gn_fix6_3_cuda": ("gn", 6, 3, True), "lm_fix6_3_cuda": ("lm", 6, 3, True),
-    "gn_fix7_3_cuda": ("gn", 7, 3, True), "lm_fix7_3_cuda": ("lm", 7, 3, True),
     "gn_fix9_3_cuda": ("gn", 9, 3, True), "lm_fix9_3_cuda": ("lm", 9, 3, True),
     # solvers/dense/solver_dense.cpp:91-98 (+ 9_3): BlockSolver + LinearSolverDense -> device DMMA Cholesky
     "gn_dense_cuda": ("gn", -1, -1, False), "lm_dense_cuda": ("lm", -1, -1, False),
     "gn_dense3_2_cuda": ("gn", 3, 2, True), "lm_dense3_2_cuda": ("lm", 3, 2, True),
     "gn_dense6_3_cuda": ("gn", 6, 3, True), "lm_dense6_3_cuda": ("lm", 6, 3, True),
-    "gn_dense7_3_cuda": ("gn", 7, 3, True), "lm_dense7_3_cuda": ("lm", 7, 3, True),
     "gn_dense9_3_cuda": ("gn", 9, 3, True), "lm_dense9_3_cuda": ("lm", 9, 3, True),
     # Powell's dogleg is registered for the variable-size block solver only (solvers/csparse/solver_csparse.cpp:117, dl_var)
     "dl_var_cuda": ("dl", -1, -1, False),
@@ -84,10 +83,18 @@ class CudaSolver:
 
     # ---- graph ----
     def set_graph(self, graph: Graph):
+        # BlockSolver<BlockSolverTraits<p,l>> holds blocks of exactly these sizes: build_structure rejects a graph with others
         pd, ld = SOLVER_NAMES[self.solver_name][1:3]
+        self.set_property("poseDim", pd); self.set_property("landmarkDim", ld)
         self.graph = graph
         cg = graph.as_c()
         self._ck(self._L.g2ocu_set_graph(self._h, ctypes.byref(cg)))
+
+    def set_force_stop_flag(self, flag):
+        """``SparseOptimizer::setForceStopFlag`` (sparse_optimizer.h:186-190): ``flag`` is a ``ctypes.c_ubyte`` owned by the caller (kept alive
+        here); while it is non-zero no further iteration / LM trial starts.  ``None`` removes it."""
+        self._stop = flag
+        self._ck(self._L.g2ocu_set_force_stop_flag(self._h, ctypes.addressof(flag) if flag is not None else None))
 
     def set_property(self, name: str, value: float):
         self._ck(self._L.g2ocu_set_property(self._h, name.encode(), float(value)))

@@ -114,6 +114,8 @@ struct g2ocu_solver {
   bool fastEstimates = false; int64_t poseHostOff = 0, lmHostOff = 0;
   // sharding
   int rank = 0, world = 1; g2ocu_allreduce_fn allreduce = nullptr; void* allreduceUser = nullptr;
+  const volatile unsigned char* forceStop = nullptr;   // SparseOptimizer::_forceStopFlag (sparse_optimizer.h:186-190); read between trials / iterations
+  int expectPoseDim = -1, expectLandmarkDim = -1;      // BlockSolver<BlockSolverTraits<p,l>>: block sizes the solver was registered for (-1 = variable)
   bool kernelTiming = false;      // property "kernelTiming": CUDA events around individual kernels, not only around phases
   int64_t slabBlocks = 0;         // blocks of the reduced system per rank (slab PCG), 0 when not sharded
   void* ncclComm = nullptr;       // set by g2ocu_set_shard_nccl: collectives go straight to NCCL on the solver's stream
@@ -158,6 +160,7 @@ struct g2ocu_solver {
 namespace {
 
 int fail(g2ocu_solver* s, int code, const std::string& msg) { if (s) s->err = msg; else g_createError = msg; return code; }
+bool terminateRequested(const g2ocu_solver* s) { return s->forceStop && *s->forceStop != 0; }   // SparseOptimizer::terminate()
 #define CU(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(s, G2OCU_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); } while (0)
 
 int ensureCuda(g2ocu_solver* s) {
@@ -203,6 +206,13 @@ void resolveEvents(g2ocu_solver* s) {
 int syncStream(g2ocu_solver* s) { CU(cudaStreamSynchronize(s->stream)); resolveEvents(s); return G2OCU_OK; }
 double phaseSeconds(g2ocu_solver* s, const char* ph) { auto it = s->phases.find(ph); return it == s->phases.end() ? 0.0 : it->second.seconds; }
 
+// The peer-memory exchange buffers are sized for one structure: any change of graph, shard or structure drops the mappings (the host
+// exports / imports again after the next g2ocu_build_structure).
+void dropP2p(g2ocu_solver* s) {
+  s->p2pReady = false;
+  for (void*& o : s->p2pOpened) if (o) { cudaIpcCloseMemHandle(o); o = nullptr; }
+  s->p2p = P2pDev();
+}
 int collectiveDev(g2ocu_solver* s, double* buf, int64_t count, int op);
 int allreduceDev(g2ocu_solver* s, double* buf, int64_t count, int op) { return collectiveDev(s, buf, count, op); }
 int collectiveDev(g2ocu_solver* s, double* buf, int64_t count, int op) {
@@ -511,7 +521,7 @@ int solvePcg(g2ocu_solver* s, const double* rhs) {
     const int batch = std::min(want, maxIter - issued);
     for (int k = 0; k < batch; ++k) {
       { KernelTimer pt(s, "pcg_spmv"); launchSpmv(pc, pc.d, pc.q, s->stream, &s->launches, issued + k > 0 && pcgSingleCtaTail(pc)); }
-      const bool p2p = slab && s->p2pReady;
+      const bool p2p = slab && s->p2pReady && pc.n <= s->p2p.cap;
       if (p2p) { KernelTimer pt(s, "pcg_exchange"); launchP2pExchangeDot(pc, s->p2p, s->stream, &s->launches); }   // peer-memory all-reduce of q fused with d.q
       else if (slab) { KernelTimer pt(s, "pcg_exchange"); int rc = allreduceDev(s, pc.q, pc.n, 0); if (rc) return rc; }
       { KernelTimer pt(s, "pcg_vec"); launchPcgTail(pc, s->stream, &s->launches, p2p); }
@@ -694,7 +704,7 @@ int solveLevenberg(g2ocu_solver* s, int iteration, int* result) {
       if (!std::isfinite(s->currentLambda)) break;
     }
     qmax++;
-  } while (rho < 0 && qmax < s->maxTrialsAfterFailure);
+  } while (rho < 0 && qmax < s->maxTrialsAfterFailure && !terminateRequested(s));   // levenberg.cpp:145
   if (qmax == s->maxTrialsAfterFailure || rho == 0 || !std::isfinite(s->currentLambda)) *result = G2OCU_RESULT_TERMINATE;
   else *result = G2OCU_RESULT_OK;
   return G2OCU_OK;
@@ -931,7 +941,7 @@ void g2ocu_destroy(g2ocu_solver* s) { delete s; }
 int g2ocu_set_graph(g2ocu_solver* s, const g2ocu_graph* g) {
   if (!s) return G2OCU_E_INVALID;
   std::string err;
-  s->hasGraph = false; s->optInitialized = false; s->structureBuilt = false; s->algoInitialized = false;
+  s->hasGraph = false; s->optInitialized = false; s->structureBuilt = false; s->algoInitialized = false; dropP2p(s);
   if (!s->g.assign(g, err)) return fail(s, err.find("unsupported") != std::string::npos ? G2OCU_E_UNSUPPORTED : G2OCU_E_INVALID, err);
   s->hasGraph = true;
   return G2OCU_OK;
@@ -949,6 +959,8 @@ int g2ocu_set_property(g2ocu_solver* s, const char* name, double value) {
   else if (n == "pcgMaxIterations") s->cfg.pcg_max_iterations = (int)value;
   else if (n == "pcgAbsoluteTolerance") s->cfg.pcg_absolute_tolerance = (int)value;
   else if (n == "kernelTiming") s->kernelTiming = value != 0.0;
+  else if (n == "poseDim") s->expectPoseDim = (int)value;
+  else if (n == "landmarkDim") s->expectLandmarkDim = (int)value;
   else if (n == "linearSolver") {
     if ((int)value != G2OCU_LINEAR_PCG && (int)value != G2OCU_LINEAR_DENSE) return fail(s, G2OCU_E_INVALID, "unknown linear solver kind");
     s->cfg.linear_solver = (int)value;
@@ -956,11 +968,12 @@ int g2ocu_set_property(g2ocu_solver* s, const char* name, double value) {
   else return fail(s, G2OCU_E_INVALID, "unknown property " + n);
   return G2OCU_OK;
 }
+int g2ocu_set_force_stop_flag(g2ocu_solver* s, const unsigned char* flag) { if (!s) return G2OCU_E_INVALID; s->forceStop = flag; return G2OCU_OK; }
 int g2ocu_set_shard(g2ocu_solver* s, int32_t rank, int32_t world, g2ocu_allreduce_fn fn, void* user) {
   if (!s || world < 1 || rank < 0 || rank >= world) return fail(s, G2OCU_E_INVALID, "bad rank/world");
   if (world > 1 && !fn) return fail(s, G2OCU_E_INVALID, "world > 1 needs an allreduce hook");
   s->rank = rank; s->world = world; s->allreduce = fn; s->allreduceUser = user;
-  s->structureBuilt = false;
+  s->structureBuilt = false; dropP2p(s);
   return G2OCU_OK;
 }
 
@@ -984,7 +997,7 @@ int g2ocu_set_shard_nccl(g2ocu_solver* s, int32_t rank, int32_t world, const cha
   const int nrc = g_nccl.CommInitRank(&s->ncclComm, world, id, rank);
   if (nrc != 0) { s->ncclComm = nullptr; return fail(s, G2OCU_E_COMM, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(nrc)); }
   s->rank = rank; s->world = world; s->allreduce = nullptr; s->allreduceUser = nullptr;
-  s->structureBuilt = false;
+  s->structureBuilt = false; dropP2p(s);
   return G2OCU_OK;
 }
 
@@ -993,8 +1006,8 @@ int g2ocu_p2p_export(g2ocu_solver* s, unsigned char handle[64]) {
   if (!s->structureBuilt) return fail(s, G2OCU_E_INVALID, "g2ocu_p2p_export needs the structure (call g2ocu_build_structure first)");
   if (s->world < 2 || s->world > 8) return fail(s, G2OCU_E_INVALID, "the peer-memory exchange supports 2..8 ranks");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  dropP2p(s);                                      // peers' mappings of the old buffer are closed by their own export
   if (s->p2pLocal) { cudaFree(s->p2pLocal); s->p2pLocal = nullptr; }
-  s->p2pReady = false;
   const int64_t cap = (s->st.sizePoses + 1) & ~(int64_t)1;
   const size_t bytes = p2pBytes(s->world, cap);
   CU(cudaMalloc((void**)&s->p2pLocal, bytes));
@@ -1025,7 +1038,7 @@ int g2ocu_initialize_optimization(g2ocu_solver* s, int32_t level) {
   if (!s->hasGraph) return fail(s, G2OCU_E_INVALID, "no graph set");
   std::string err;
   if (s->structureBuilt) { int rc0 = downloadEstimates(s); if (rc0) return rc0; }   // vertices keep their estimates
-  s->optInitialized = false; s->structureBuilt = false; s->algoInitialized = false;
+  s->optInitialized = false; s->structureBuilt = false; s->algoInitialized = false; dropP2p(s);
   if (!initializeOptimization(s->g, level, s->st, err)) return fail(s, G2OCU_E_INVALID, err);
   s->optInitialized = true;
   return G2OCU_OK;
@@ -1046,10 +1059,13 @@ int g2ocu_build_structure(g2ocu_solver* s) {
   if (!s->optInitialized) return fail(s, G2OCU_E_INVALID, "initializeOptimization has not been called");
   std::string err;
   if (s->structureBuilt) { int rc0 = downloadEstimates(s); if (rc0) return rc0; }   // vertices keep their state across optimize() calls
-  s->structureBuilt = false;
+  s->structureBuilt = false; dropP2p(s);
   if (!buildStructure(s->g, s->st, err, s->rank, s->world)) return fail(s, G2OCU_E_UNSUPPORTED, err);
   const Structure& st = s->st;
   const bool okDims = (st.doSchur && ((st.P == 9 && st.L == 3) || (st.P == 6 && st.L == 3) || (st.P == 3 && st.L == 2))) || (!st.doSchur && (st.P == 3 || st.P == 6 || st.P == 9));
+  // BlockSolver<BlockSolverTraits<p,l>> maps fixed-size blocks: a graph with other block sizes does not fit a fixN_M solver (block_solver.hpp:103-256)
+  if ((s->expectPoseDim > 0 && st.numPoses > 0 && st.P != s->expectPoseDim) || (s->expectLandmarkDim > 0 && st.numLandmarks > 0 && st.L != s->expectLandmarkDim))
+    return fail(s, G2OCU_E_UNSUPPORTED, "block sizes P=" + std::to_string(st.P) + " L=" + std::to_string(st.L) + " do not match the solver's fixed sizes " + std::to_string(s->expectPoseDim) + "_" + std::to_string(s->expectLandmarkDim));
   if (!okDims) return fail(s, G2OCU_E_UNSUPPORTED, "unsupported block sizes P=" + std::to_string(st.P) + " L=" + std::to_string(st.L));
   for (const EdgeSet& es : st.sets) {
     const bool naturalPL = es.etype == G2OCU_EDGE_SE2_POINT_XY || es.etype == G2OCU_EDGE_PROJECT_XYZ2UV || es.etype == G2OCU_EDGE_SE3_PROJECT_XYZ || es.etype == G2OCU_EDGE_BAL;
@@ -1164,7 +1180,7 @@ int g2ocu_optimize(g2ocu_solver* s, int32_t algorithm, int32_t iterations, g2ocu
   if (!s->optInitialized || s->st.ivMap.empty()) return fail(s, G2OCU_E_INVALID, "0 vertices to optimize, maybe forgot to call initializeOptimization()");
   int rc = g2ocu_init(s, 0); if (rc) return rc;
   int cj = 0; bool ok = true; int result = G2OCU_RESULT_OK;
-  for (int i = 0; i < iterations && ok; ++i) {
+  for (int i = 0; i < iterations && !terminateRequested(s) && ok; ++i) {   // sparse_optimizer.cpp:396
     g2ocu_iteration_stats local;
     rc = g2ocu_solver_iteration(s, algorithm, i, stats ? &stats[i] : &local); if (rc) return rc;
     result = stats ? stats[i].result : local.result;
@@ -1225,7 +1241,7 @@ int64_t g2ocu_get_i32(g2ocu_solver* s, const char* name, int32_t* out, int64_t c
     if (n == "full_system_permutation") return copyOutI32(st.refToInternal, out, cap);
     if (n == "internal_dims") return copyOutI32({st.numPoses, st.numLandmarks, st.sizePoses, st.sizeLandmarks}, out, cap);
   }
-  if (n == "dims") return copyOutI32({st.numPoses, st.numLandmarks, st.sizePoses, st.sizeLandmarks}, out, cap);
+  if (n == "dims" || n == "internal_dims") return copyOutI32({st.numPoses, st.numLandmarks, st.sizePoses, st.sizeLandmarks}, out, cap);
   if (n == "pose_block_indices") return copyOutI32(st.poseBlockIndices, out, cap);
   if (n == "landmark_block_indices") return copyOutI32(st.landmarkBlockIndices, out, cap);
   if (n == "hpp_colptr") return copyOutI32(st.hppColPtr, out, cap);
@@ -1234,8 +1250,8 @@ int64_t g2ocu_get_i32(g2ocu_solver* s, const char* name, int32_t* out, int64_t c
   if (n == "hpl_rowidx") return copyOutI32(st.hplRowIdx, out, cap);
   if (n == "hschur_colptr") return copyOutI32(st.sColPtr, out, cap);
   if (n == "hschur_rowidx") return copyOutI32(st.sRowIdx, out, cap);
-  if (n == "hschur_t_colptr") return copyOutI32(st.sRowPtr, out, cap);
-  if (n == "hschur_t_rowidx") return copyOutI32(st.sColIdx, out, cap);
+  if (n == "hschur_t_colptr") return copyOutI32(st.sTRefRowPtr, out, cap);
+  if (n == "hschur_t_rowidx") return copyOutI32(st.sTRefColIdx, out, cap);
   if (n == "edge_targets") return copyOutI32(st.edgeTargets, out, cap);
   if (n == "shard_landmark_range") return copyOutI32({st.lmBegin, st.lmEnd}, out, cap);
   if (n == "slab_block_range") {   // blocks of the reduced system this rank solves with (CSR order); everything when not sharded
@@ -1299,6 +1315,23 @@ int64_t g2ocu_get_f64(g2ocu_solver* s, const char* name, double* out, int64_t ca
     return cnt;
   }
   if (n == "dinv_values") return downloadF64(s, s->Dinv.p, s->Dinv.n, out, cap);
+  if (n == "diagonal_blocks") {   // the Hessian block of every vertex of the index mapping, in its order (what OptimizableGraph::Vertex::hessian maps, block_solver.hpp:150-170)
+    int64_t total = 0;
+    for (int32_t v : st.ivMap) { const int D = st.classOf[v] == 0 ? P : L; total += (int64_t)D * D; }
+    if (!out) return total;
+    std::vector<double> hpp(s->Hpp.n), hll(s->Hll.n);
+    if (downloadF64(s, s->Hpp.p, hpp.size(), hpp.data(), (int64_t)hpp.size()) < 0) return G2OCU_E_CUDA;
+    if (hll.size() && downloadF64(s, s->Hll.p, hll.size(), hll.data(), (int64_t)hll.size()) < 0) return G2OCU_E_CUDA;
+    int64_t o = 0;
+    for (int32_t v : st.ivMap) {
+      const bool pose = st.classOf[v] == 0; const int D = pose ? P : L;
+      if (o + D * D > cap) break;
+      const double* src = pose ? &hpp[(size_t)st.hppDiag[st.slotOf[v]] * P * P] : &hll[(size_t)st.slotOf[v] * L * L];
+      for (int k = 0; k < D * D; ++k) out[o + k] = src[k] + ((k % (D + 1)) == 0 ? s->lambda : 0.0);
+      o += D * D;
+    }
+    return total;
+  }
   if (n == "errors" || n == "jacobians") {
     const bool jac = n == "jacobians";
     std::vector<int64_t> off(st.activeEdges.size() + 1, 0);

@@ -298,6 +298,14 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int ran
     st.sColIdx.resize(st.sRowPtr[st.numPoses]); st.sDiag.assign(st.numPoses, -1);
     for (int i = 0; i < st.numPoses; ++i) { std::copy(rows[i].begin(), rows[i].end(), st.sColIdx.begin() + st.sRowPtr[i]); st.sDiag[i] = st.sRowPtr[i]; }
     transposeToCcs(st.numPoses, st.sRowPtr, st.sColIdx, st.sColPtr, st.sRowIdx, st.sCcsToCsr);
+    // The reference's _HschurTransposedCCS is filled once in buildStructure (block_solver.hpp:253) from the co-observation pairs and the
+    // pose-pose edges; the diagonal blocks of poses that observe no landmark join Hschur only in the first solve (_Hpp->add, :333-335)
+    // and never reach that mirror.  The read-back arrays reproduce it as the reference holds it.
+    st.sTRefRowPtr.assign(1, 0); st.sTRefColIdx.clear();
+    for (int i = 0; i < st.numPoses; ++i) {
+      for (int k = st.sRowPtr[i]; k < st.sRowPtr[i + 1]; ++k) if (st.sColIdx[k] != i || clPtr[i + 1] > clPtr[i]) st.sTRefColIdx.push_back(st.sColIdx[k]);
+      st.sTRefRowPtr.push_back((int32_t)st.sTRefColIdx.size());
+    }
     st.hppToS.resize(nnzPP);
     for (int r = 0; r < st.numPoses; ++r)
       for (int k = st.hppRowPtr[r]; k < st.hppRowPtr[r + 1]; ++k) {
@@ -305,7 +313,7 @@ bool buildStructure(const HostGraph& g, Structure& st, std::string& err, int ran
         st.hppToS[k] = (int)(std::lower_bound(b, e, st.hppColIdx[k]) - st.sColIdx.data());
       }
   } else {
-    st.sRowPtr.clear(); st.sColIdx.clear(); st.sColPtr.clear(); st.sRowIdx.clear(); st.sCcsToCsr.clear(); st.sDiag.clear(); st.hppToS.clear();
+    st.sRowPtr.clear(); st.sColIdx.clear(); st.sColPtr.clear(); st.sRowIdx.clear(); st.sCcsToCsr.clear(); st.sDiag.clear(); st.hppToS.clear(); st.sTRefRowPtr.clear(); st.sTRefColIdx.clear();
   }
 
   trace.mark("Hschur pattern");

@@ -68,6 +68,7 @@ struct Structure {
   std::vector<int32_t> hplColPtr, hplRowIdx;
   // Hschur: reference CCS + internal CSR (== the reference's HschurTransposedCCS)
   std::vector<int32_t> sColPtr, sRowIdx, sRowPtr, sColIdx, sCcsToCsr, sDiag, hppToS;
+  std::vector<int32_t> sTRefRowPtr, sTRefColIdx;   // the reference's _HschurTransposedCCS as it holds it (built before the first solve extends Hschur)
   bool hplShared = false;                // some Hpl block receives more than one edge (parallel edges)
   bool hppShared = false;
   // per active edge (internalId order): matrix id (0 Hpp, 1 Hll, 2 Hpl, -1 none), block row, block col, transposed

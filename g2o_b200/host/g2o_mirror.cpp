@@ -149,6 +149,7 @@ void SparseOptimizer::discardTop() { check(_handle, g2ocu_discard_top(_handle), 
 template <int P, int L> bool CudaBlockSolver<P, L>::init(SparseOptimizer* optimizer, bool online) {
   _optimizer = optimizer;
   if (!optimizer || !check(optimizer->handle(), g2ocu_set_property(optimizer->handle(), "linearSolver", _linearKind), "CudaBlockSolver::init")) return false;
+  g2ocu_set_property(optimizer->handle(), "poseDim", P); g2ocu_set_property(optimizer->handle(), "landmarkDim", L);   // BlockSolverTraits<P,L>: fixed block sizes
   return check(optimizer->handle(), g2ocu_init(optimizer->handle(), online), "CudaBlockSolver::init");
 }
 template <int P, int L> bool CudaBlockSolver<P, L>::buildStructure(bool) {
@@ -175,7 +176,6 @@ template <int P, int L> size_t CudaBlockSolver<P, L>::vectorSize() const { retur
 template <int P, int L> void CudaBlockSolver<P, L>::multiplyHessian(number_t* dest, const number_t* src) const { check(_optimizer->handle(), g2ocu_multiply_hessian(_optimizer->handle(), dest, src), "CudaBlockSolver::multiplyHessian"); }
 template class CudaBlockSolver<-1, -1>;
 template class CudaBlockSolver<6, 3>;
-template class CudaBlockSolver<7, 3>;
 template class CudaBlockSolver<3, 2>;
 template class CudaBlockSolver<9, 3>;
 

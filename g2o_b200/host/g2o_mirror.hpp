@@ -267,7 +267,6 @@ template <int P, int L> class CudaBlockSolver : public Solver {
 };
 typedef CudaBlockSolver<-1, -1> CudaBlockSolverX;
 typedef CudaBlockSolver<6, 3> CudaBlockSolver_6_3;
-typedef CudaBlockSolver<7, 3> CudaBlockSolver_7_3;
 typedef CudaBlockSolver<3, 2> CudaBlockSolver_3_2;
 typedef CudaBlockSolver<9, 3> CudaBlockSolver_9_3;
 

@@ -23,8 +23,8 @@ static OptimizationAlgorithm* make(const std::string& name) {
 static void testFactory() {
   std::stringstream ss; OptimizationAlgorithmFactory::instance()->listSolvers(ss);
   const std::string s = ss.str();
-  for (const char* n : {"gn_var_cuda", "lm_var_cuda", "gn_fix3_2_cuda", "lm_fix3_2_cuda", "gn_fix6_3_cuda", "lm_fix6_3_cuda", "gn_fix7_3_cuda", "lm_fix7_3_cuda", "lm_fix9_3_cuda",
-                        "gn_dense_cuda", "lm_dense_cuda", "lm_dense3_2_cuda", "lm_dense6_3_cuda", "lm_dense7_3_cuda", "lm_dense9_3_cuda", "dl_var_cuda"})
+  for (const char* n : {"gn_var_cuda", "lm_var_cuda", "gn_fix3_2_cuda", "lm_fix3_2_cuda", "gn_fix6_3_cuda", "lm_fix6_3_cuda", "lm_fix9_3_cuda",
+                        "gn_dense_cuda", "lm_dense_cuda", "lm_dense3_2_cuda", "lm_dense6_3_cuda", "lm_dense9_3_cuda", "dl_var_cuda"})
     EXPECT(s.find(n) != std::string::npos);
   OptimizationAlgorithmProperty p;
   OptimizationAlgorithm* a = OptimizationAlgorithmFactory::instance()->construct("lm_fix6_3_cuda", p);

@@ -14,7 +14,7 @@ import math
 
 import numpy as np
 
-from .graph import (EDGE_BAL, EDGE_PROJECT_XYZ2UV, EDGE_SE2, EDGE_SE2_POINT_XY, EDGE_SE3, EDGE_SE3_PROJECT_XYZ,
+from .graph import (EDGE_BAL, EDGE_PROJECT_XYZ2UV, EDGE_SE2, EDGE_SE2_POINT_XY, EDGE_SE3, EDGE_SE3_EXPMAP, EDGE_SE3_PROJECT_XYZ,
                     KERNEL_HUBER, VERTEX_CAM_BAL, VERTEX_POINT_BAL, VERTEX_POINT_XY, VERTEX_POINT_XYZ, VERTEX_SE2,
                     VERTEX_SE3, VERTEX_SE3_EXPMAP, Graph)
 
@@ -212,6 +212,53 @@ def sphere(nodes_per_level: int = 100, laps: int = 100, radius: float = 100.0,
                  v_estimate=est.ravel(), e_type=np.full(ne, EDGE_SE3), e_v0=[p[0] for p in pairs], e_v1=[p[1] for p in pairs],
                  e_measurement=meas.ravel(), e_information=np.tile(info.ravel(order="F"), ne), name="sphere",
                  meta={"nodes_per_level": nodes_per_level, "laps": laps})
+
+
+def _se3quat_inverse_of_iso(iso12: np.ndarray) -> np.ndarray:
+    """Isometry (R column-major 9, t 3)  ->  SE3Quat::toVector (t, qx qy qz qw) of its inverse."""
+    R = iso12[:9].reshape(3, 3, order="F"); t = iso12[9:]
+    Ri = R.T
+    return np.concatenate([-Ri @ t, _r_to_quat(Ri.ravel(order="F"))])
+
+
+def sphere_expmap(nodes_per_level: int = 16, laps: int = 8, **kw) -> Graph:
+    """The sphere pose graph of C2 expressed with the sba types (types_six_dof_expmap.h:84-127): VertexSE3Expmap holds the world-to-body
+    transform T_i = X_i^-1, EdgeSE3Expmap (v1 = i, v2 = j) has error log(T_j^-1 C T_i), so C = Z_ij^-1 for the EdgeSE3 measurement
+    Z_ij = X_i^-1 X_j.  SE3Quat::log orders the error (rotation, translation): the information blocks are swapped accordingly."""
+    g = sphere(nodes_per_level=nodes_per_level, laps=laps, **kw)
+    est = np.concatenate([_se3quat_inverse_of_iso(v) for v in g.v_estimate.reshape(-1, 12)])
+    meas = np.concatenate([_se3quat_inverse_of_iso(m) for m in g.e_measurement.reshape(-1, 12)])
+    info = g.e_information.reshape(-1, 6, 6)
+    perm = [3, 4, 5, 0, 1, 2]
+    info = info[:, perm][:, :, perm]
+    return Graph(v_id=g.v_id, v_type=np.full(g.n_vertices, VERTEX_SE3_EXPMAP), v_fixed=g.v_fixed, v_marginalized=g.v_marginalized, v_estimate=est,
+                 e_type=np.full(g.n_edges, EDGE_SE3_EXPMAP), e_v0=g.e_v0, e_v1=g.e_v1, e_measurement=meas, e_information=info.ravel(),
+                 name="sphere_expmap", meta=dict(g.meta))
+
+
+def ba_demo_with_pose_constraints(sigma_t: float = 0.01, sigma_r: float = 0.005, seed: int = 3, **kw) -> Graph:
+    """ba_demo plus an EdgeSE3Expmap between consecutive cameras (a visual-inertial style relative-pose prior): Hpp gets off-diagonal blocks
+    next to the Schur complement of the points.  The cameras of ba_demo are T_i = (I, t_i); C = T_j T_i^-1 + noise."""
+    g = ba_demo(**kw)
+    rng = np.random.default_rng(seed)
+    cams = np.flatnonzero(np.asarray(g.v_type) == VERTEX_SE3_EXPMAP)
+    off = g.estimate_offsets()
+    e_v0, e_v1, meas, info = [], [], [], []
+    I6 = np.diag([1 / sigma_r ** 2] * 3 + [1 / sigma_t ** 2] * 3)
+    for a, b in zip(cams[:-1], cams[1:]):
+        ta, tb = g.v_estimate[off[a]:off[a] + 3], g.v_estimate[off[b]:off[b] + 3]
+        w = rng.normal(0, sigma_r, 3); q = np.concatenate([0.5 * w, [1.0]]); q /= np.linalg.norm(q)
+        e_v0.append(a); e_v1.append(b); meas.extend(list(tb - ta + rng.normal(0, sigma_t, 3)) + list(q)); info.extend(I6.ravel())
+    n = len(e_v0)
+    # cameras start off their true place so that the priors and the projections pull against each other
+    est = g.v_estimate.copy()
+    for c in cams[1:]:
+        est[off[c]:off[c] + 3] += rng.normal(0, 0.02, 3)
+    return Graph(v_id=g.v_id, v_type=g.v_type, v_fixed=g.v_fixed, v_marginalized=g.v_marginalized, v_estimate=est,
+                 e_type=np.concatenate([g.e_type, np.full(n, EDGE_SE3_EXPMAP)]), e_v0=np.concatenate([g.e_v0, e_v0]), e_v1=np.concatenate([g.e_v1, e_v1]),
+                 e_measurement=np.concatenate([g.e_measurement, meas]), e_information=np.concatenate([g.e_information, info]),
+                 e_param=g.e_param, e_kernel=np.concatenate([g.e_kernel, np.zeros(n)]), e_kernel_delta=np.concatenate([g.e_kernel_delta, np.ones(n)]),
+                 name="ba_demo_pose_constraints", meta=dict(g.meta))
 
 
 # ----------------------------------------------------------------------------------------------------

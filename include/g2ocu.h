@@ -171,7 +171,11 @@ int g2ocu_create(const g2ocu_config* cfg, g2ocu_solver** out);
 void g2ocu_destroy(g2ocu_solver* s);
 
 int g2ocu_set_graph(g2ocu_solver* s, const g2ocu_graph* g);
-int g2ocu_set_property(g2ocu_solver* s, const char* name, double value);  /* "initialLambda", "maxTrialsAfterFailure" (levenberg.cpp:48-49); "pcgTolerance", "pcgMaxIterations", "pcgAbsoluteTolerance" (linear_solver_pcg.h:53-57); "linearSolver" = G2OCU_LINEAR_* (which LinearSolver the BlockSolver owns, block_solver.h:124); "doglegInitialDelta", "doglegMaxTrialsAfterFailure", "doglegInitialLambda", "doglegLambdaFactor" = OptimizationAlgorithmDogleg's "initialDelta" (1e4), "maxTrialsAfterFailure" (100), "initialLambda" (1e-7), "lambdaFactor" (10) (optimization_algorithm_dogleg.cpp:44-47); "kernelTiming" != 0: g2ocu_phase_time also reports per-kernel phases (schur_tiles, pcg_spmv, ...) at the price of two event records per kernel */
+int g2ocu_set_property(g2ocu_solver* s, const char* name, double value);  /* "initialLambda", "maxTrialsAfterFailure" (levenberg.cpp:48-49); "pcgTolerance", "pcgMaxIterations", "pcgAbsoluteTolerance" (linear_solver_pcg.h:53-57); "linearSolver" = G2OCU_LINEAR_* (which LinearSolver the BlockSolver owns, block_solver.h:124); "doglegInitialDelta", "doglegMaxTrialsAfterFailure", "doglegInitialLambda", "doglegLambdaFactor" = OptimizationAlgorithmDogleg's "initialDelta" (1e4), "maxTrialsAfterFailure" (100), "initialLambda" (1e-7), "lambdaFactor" (10) (optimization_algorithm_dogleg.cpp:44-47); "poseDim", "landmarkDim" = the fixed block sizes of BlockSolver<BlockSolverTraits<p,l>> (-1 = variable, the default): g2ocu_build_structure rejects a graph whose block sizes differ; "kernelTiming" != 0: g2ocu_phase_time also reports per-kernel phases (schur_tiles, pcg_spmv, ...) at the price of two event records per kernel */
+/* SparseOptimizer::setForceStopFlag / terminate() (core/sparse_optimizer.h:186-190): `flag` points at a byte owned by the caller (g2o's bool); while it
+ * is non-zero g2ocu_optimize starts no further iteration (sparse_optimizer.cpp:396) and the Levenberg trial loop stops after the current
+ * trial (optimization_algorithm_levenberg.cpp:145).  NULL (default) = never. */
+int g2ocu_set_force_stop_flag(g2ocu_solver* s, const unsigned char* flag);
 int g2ocu_set_shard(g2ocu_solver* s, int32_t rank, int32_t world, g2ocu_allreduce_fn fn, void* user);
 /* The same sharding with the collectives issued straight from the library through NCCL (no host callback per collective):
  * `nccl_library` is the path of libnccl.so.2 (dlopen'ed; the build has no link-time NCCL dependency), `unique_id` the 128 bytes of an
@@ -219,8 +223,10 @@ int g2ocu_get_estimates(g2ocu_solver* s, double* host_packed);
  *        (graphs with poses and points of which none is marginalized - BlockSolverX with two block sizes: "dims",
  *        "pose_block_indices", "hpp_colptr", "hpp_rowidx", "edge_targets" describe the reference's single Hpp over all
  *        vertices in id order; "full_system_permutation" maps a scalar index of its x / b to the internal [poses | points]
- *        layout, "internal_dims" = poses, points, their scalar sizes)
+ *        layout; "internal_dims" = poses, points, their scalar sizes, available for every graph)
  * double: "x" "b" "bschur" "hpp_values" "hpl_values" "hll_values" "hschur_values" "errors" "jacobians" "estimates" "lambda"
+ *         "diagonal_blocks" = the D x D Hessian block of every vertex of the index mapping, in its order (what the reference maps into
+ *                      OptimizableGraph::Vertex::hessian, block_solver.hpp:150-170; computeLambdaInit reads its diagonal, levenberg.cpp:152-175)
  *         "dogleg" = { trustRegion(), lastStep() (G2OCU_DOGLEG_STEP_*), tries of the last iteration, damping factor,
  *                      1 if the system was positive definite in all iterations } (optimization_algorithm_dogleg.h:64-68,84-88) */
 int64_t g2ocu_get_i32(g2ocu_solver* s, const char* name, int32_t* out, int64_t capacity);

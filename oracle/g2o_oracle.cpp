@@ -699,13 +699,13 @@ struct Optimizer {
     double t = now();
     Hschur.clear();
     {  // _Hpp->add(*_Hschur): sparse_block_matrix.hpp:175-187 (allocates missing blocks in dest)
-      size_t before = Hschur.blocks.size();
       for (size_t i = 0; i < Hpp.blockCols.size(); ++i) for (auto& kv : Hpp.blockCols[i]) {
         int d = Hschur.block(kv.first, (int)i, true);
         const auto& s = Hpp.blocks[kv.second]; auto& dst = Hschur.blocks[d];
         for (size_t k = 0; k < s.size(); ++k) dst[k] += s[k];
       }
-      if (Hschur.blocks.size() != before) rebuildSchurTransposed();   // keeps our bookkeeping consistent; the reference leaves the CCS stale
+      // _HschurTransposedCCS is NOT rebuilt: the reference fills it once in buildStructure (block_solver.hpp:253), so the diagonal blocks of poses
+      // that observe no landmark - added to Hschur here - never appear in it (the landmark loop below only looks up co-observation pairs)
     }
     std::fill(coefficients.begin(), coefficients.begin() + sizePoses, 0.0);
 #pragma omp parallel for default(shared) schedule(dynamic, 10) num_threads(nthreads)

@@ -156,6 +156,9 @@ def reference_core():
             getattr(L, f).argtypes = [ctypes.c_void_p]; getattr(L, f).restype = ctypes.c_double
         for f in ("refcore_dogleg_state", "refcore_hessian_index", "refcore_estimates"):
             getattr(L, f).argtypes = [ctypes.c_void_p, ctypes.c_void_p]; getattr(L, f).restype = None
+        L.refcore_linearize.argtypes = [ctypes.c_void_p, ctypes.c_double]; L.refcore_linearize.restype = ctypes.c_int
+        for f in ("refcore_structure_i32", "refcore_structure_f64"):
+            getattr(L, f).argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64]; getattr(L, f).restype = ctypes.c_int64
         _CORE = L
     return _CORE
 
@@ -206,6 +209,26 @@ class ReferenceG2o:
 
     def estimates(self) -> np.ndarray:
         out = np.zeros_like(self.graph.v_estimate); self._L.refcore_estimates(self._h, _dp(out)); return out
+
+    def linearize(self, lam: float) -> bool:
+        """init, buildStructure, computeActiveErrors, buildSystem, setLambda(lam, true), solve, restoreDiagonal through the reference's own
+        Solver virtuals; the BlockSolver's matrices can be read afterwards with structure_i32 / structure_f64."""
+        return self._L.refcore_linearize(self._h, float(lam)) == 1
+
+    def structure_i32(self, name: str) -> np.ndarray:
+        """Block pattern arrays of the reference's BlockSolver (its protected _Hpp / _Hll / _Hpl / _Hschur / _HschurTransposedCCS), in the format of
+        g2ocu_get_i32: pose_block_indices, landmark_block_indices, hpp_/hpl_/hll_/hschur_/hschur_t_ colptr + rowidx, dims."""
+        n = self._L.refcore_structure_i32(self._h, name.encode(), None, 0)
+        if n < 0:
+            raise KeyError(name)
+        out = np.zeros(n, dtype=np.int32); self._L.refcore_structure_i32(self._h, name.encode(), _dp(out), n); return out
+
+    def structure_f64(self, name: str) -> np.ndarray:
+        """hpp_values, hpl_values, hll_values, hschur_values (blocks in CCS order, column-major), b, x, bschur of the reference's BlockSolver."""
+        n = self._L.refcore_structure_f64(self._h, name.encode(), None, 0)
+        if n < 0:
+            raise KeyError(name)
+        out = np.zeros(n); self._L.refcore_structure_f64(self._h, name.encode(), _dp(out), n); return out
 
 
 def has_csparse() -> bool:

@@ -8,6 +8,7 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <functional>
@@ -64,16 +65,66 @@ struct Handle {
   g2o::OptimizationAlgorithmLevenberg* lm = nullptr;
   g2o::OptimizationAlgorithmDogleg* dl = nullptr;
   std::function<void(double, int, bool)> setPcg;             // LinearSolverPCG::setTolerance / setMaxIterations / setAbsoluteTolerance
+  g2o::BlockSolverBase* blockSolver = nullptr;               // owned by the algorithm
+  std::function<bool(const std::string&, std::vector<int32_t>&)> structureI32;   // block patterns of the BlockSolver's protected matrices
+  std::function<bool(const std::string&, std::vector<double>&)> structureF64;    // and their values
   std::vector<std::vector<double> > cameras;                 // distinct (f, cx, cy) of the EdgeProjectXYZ2UV edges -> parameter id
   std::string err;
 };
 
-template <class BlockSolverT> std::unique_ptr<BlockSolverT> makeBlockSolver(std::function<void(double, int, bool)>& setPcg) {
+// BlockSolver keeps _Hpp / _Hll / _Hpl / _Hschur protected (block_solver.h:150-170); this subclass adds nothing but read access, so that the
+// patterns buildStructure produced (block_solver.hpp:103-256) and the values buildSystem / solve left in them can be compared with the backend's.
+template <class M> void patternOf(const M& mat, std::vector<int32_t>& out, bool ptr) {
+  out.clear();
+  if (ptr) { int n = 0; for (const auto& c : mat.blockCols()) { out.push_back(n); n += (int)c.size(); } out.push_back(n); }
+  else for (const auto& c : mat.blockCols()) for (const auto& kv : c) out.push_back(kv.first);
+}
+template <class M> void valuesOf(const M& mat, std::vector<double>& out) {
+  out.clear();
+  for (const auto& c : mat.blockCols()) for (const auto& kv : c) { const auto& b = *kv.second; for (int cc = 0; cc < b.cols(); ++cc) for (int r = 0; r < b.rows(); ++r) out.push_back(b(r, cc)); }
+}
+template <class BlockSolverT> struct ExposedBlockSolver : public BlockSolverT {
+  using BlockSolverT::BlockSolverT;
+  bool i32(const std::string& n, std::vector<int32_t>& out) const {
+    if (n == "pose_block_indices" && this->_Hpp) { out.assign(this->_Hpp->colBlockIndices().begin(), this->_Hpp->colBlockIndices().end()); return true; }
+    if (n == "landmark_block_indices" && this->_Hll) { out.assign(this->_Hll->colBlockIndices().begin(), this->_Hll->colBlockIndices().end()); return true; }
+    if ((n == "hpp_colptr" || n == "hpp_rowidx") && this->_Hpp) { patternOf(*this->_Hpp, out, n == "hpp_colptr"); return true; }
+    if ((n == "hpl_colptr" || n == "hpl_rowidx") && this->_Hpl) { patternOf(*this->_Hpl, out, n == "hpl_colptr"); return true; }
+    if ((n == "hll_colptr" || n == "hll_rowidx") && this->_Hll) { patternOf(*this->_Hll, out, n == "hll_colptr"); return true; }
+    if ((n == "hschur_colptr" || n == "hschur_rowidx") && this->_Hschur) { patternOf(*this->_Hschur, out, n == "hschur_colptr"); return true; }
+    if ((n == "hschur_t_colptr" || n == "hschur_t_rowidx") && this->_HschurTransposedCCS) {   // row-major mirror of the upper pattern (block_solver.hpp:253)
+      out.clear(); int c = 0;
+      for (const auto& col : this->_HschurTransposedCCS->blockCols()) { if (n == "hschur_t_colptr") { out.push_back(c); c += (int)col.size(); } else for (const auto& rb : col) out.push_back(rb.row); }
+      if (n == "hschur_t_colptr") out.push_back(c);
+      return true;
+    }
+    if (n == "dims") { out = {this->_numPoses, this->_numLandmarks, this->_sizePoses, this->_sizeLandmarks}; return true; }
+    return false;
+  }
+  bool f64(const std::string& n, std::vector<double>& out) const {
+    if (n == "hpp_values" && this->_Hpp) { valuesOf(*this->_Hpp, out); return true; }
+    if (n == "hpl_values" && this->_Hpl) { valuesOf(*this->_Hpl, out); return true; }
+    if (n == "hll_values" && this->_Hll) { valuesOf(*this->_Hll, out); return true; }
+    if (n == "hschur_values" && this->_Hschur) { valuesOf(*this->_Hschur, out); return true; }
+    if (n == "b" || n == "x") { const double* v = n == "b" ? this->b() : this->x(); out.assign(v, v + this->vectorSize()); return true; }
+    if (n == "bschur" && this->_bschur) { out.assign(this->_bschur.get(), this->_bschur.get() + this->_sizePoses); return true; }
+    return false;
+  }
+};
+template <class BlockSolverT> void expose(Handle& h, ExposedBlockSolver<BlockSolverT>* raw) {
+  h.blockSolver = raw;
+  h.structureI32 = [raw](const std::string& n, std::vector<int32_t>& out) { return raw->i32(n, out); };
+  h.structureF64 = [raw](const std::string& n, std::vector<double>& out) { return raw->f64(n, out); };
+}
+
+template <class BlockSolverT> std::unique_ptr<BlockSolverT> makeBlockSolver(Handle& h) {
   typedef g2o::LinearSolverPCG<typename BlockSolverT::PoseMatrixType> Pcg;
   std::unique_ptr<Pcg> linear(new Pcg());
   Pcg* raw = linear.get();                                   // owned by the block solver, which the algorithm owns, which the optimizer owns
-  setPcg = [raw](double tol, int maxIter, bool absolute) { raw->setTolerance(tol); raw->setMaxIterations(maxIter); raw->setAbsoluteTolerance(absolute); };
-  return std::unique_ptr<BlockSolverT>(new BlockSolverT(std::move(linear)));
+  h.setPcg = [raw](double tol, int maxIter, bool absolute) { raw->setTolerance(tol); raw->setMaxIterations(maxIter); raw->setAbsoluteTolerance(absolute); };
+  ExposedBlockSolver<BlockSolverT>* bs = new ExposedBlockSolver<BlockSolverT>(std::move(linear));
+  expose(h, bs);
+  return std::unique_ptr<BlockSolverT>(bs);
 }
 
 // BlockSolver + LinearSolverCSparse (solvers/csparse/solver_csparse.cpp:44-52): block ordering for the fixed-size solvers, scalar AMD for `var`
@@ -95,10 +146,10 @@ void* refcore_create(const FlatGraph* g, const char* algorithm, const char* bloc
   std::unique_ptr<Handle> h(new Handle);
   const std::string alg(algorithm), bs(blockSolver);
   std::unique_ptr<g2o::BlockSolverBase> solver;
-  if (bs == "3_2") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<3, 2> > >(h->setPcg);
-  else if (bs == "6_3") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<6, 3> > >(h->setPcg);
-  else if (bs == "9_3") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<9, 3> > >(h->setPcg);   // bal_example.cpp:301
-  else if (bs == "var") solver = makeBlockSolver<g2o::BlockSolverX>(h->setPcg);
+  if (bs == "3_2") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<3, 2> > >(*h);
+  else if (bs == "6_3") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<6, 3> > >(*h);
+  else if (bs == "9_3") solver = makeBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<9, 3> > >(*h);   // bal_example.cpp:301
+  else if (bs == "var") solver = makeBlockSolver<g2o::BlockSolverX>(*h);
   else if (bs == "3_2_csparse") solver = makeCSparseBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<3, 2> > >(true);
   else if (bs == "6_3_csparse") solver = makeCSparseBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<6, 3> > >(true);
   else if (bs == "9_3_csparse") solver = makeCSparseBlockSolver<g2o::BlockSolver<g2o::BlockSolverTraits<9, 3> > >(true);
@@ -186,6 +237,33 @@ void* refcore_create(const FlatGraph* g, const char* algorithm, const char* bloc
   return h.release();
 }
 void refcore_destroy(void* hh) { delete (Handle*)hh; }
+// One linearisation through the reference's own virtuals, as OptimizationAlgorithmLevenberg::solve strings them together (levenberg.cpp:58-110):
+// init, buildStructure, computeActiveErrors, buildSystem, setLambda(lambda, true), solve, restoreDiagonal.  Afterwards the structure / value
+// getters below read the BlockSolver's matrices (Hschur holds the damped reduced system of that solve).
+int refcore_linearize(void* hh, double lambda) {
+  Handle* h = (Handle*)hh;
+  if (!h->blockSolver || !h->optimizer.solver()) return -1;
+  if (!h->optimizer.solver()->init(false)) return -2;
+  if (!h->blockSolver->buildStructure()) return -3;
+  h->optimizer.computeActiveErrors();
+  h->blockSolver->buildSystem();                 // returns false unconditionally in the reference (block_solver.hpp:520); its callers ignore it
+  h->blockSolver->setLambda(lambda, true);
+  const bool ok = h->blockSolver->solve();
+  h->blockSolver->restoreDiagonal();
+  return ok ? 1 : 0;
+}
+int64_t refcore_structure_i32(void* hh, const char* name, int32_t* out, int64_t cap) {
+  Handle* h = (Handle*)hh; std::vector<int32_t> v;
+  if (!h->structureI32 || !h->structureI32(name, v)) return -1;
+  if (out) std::memcpy(out, v.data(), sizeof(int32_t) * (size_t)std::min<int64_t>(cap, (int64_t)v.size()));
+  return (int64_t)v.size();
+}
+int64_t refcore_structure_f64(void* hh, const char* name, double* out, int64_t cap) {
+  Handle* h = (Handle*)hh; std::vector<double> v;
+  if (!h->structureF64 || !h->structureF64(name, v)) return -1;
+  if (out) std::memcpy(out, v.data(), sizeof(double) * (size_t)std::min<int64_t>(cap, (int64_t)v.size()));
+  return (int64_t)v.size();
+}
 // LinearSolverPCG properties (linear_solver_pcg.h:53-57 defaults: 1e-6, -1, absolute)
 void refcore_set_pcg(void* hh, double tolerance, int maxIterations, int absoluteTolerance) { Handle* h = (Handle*)hh; if (h->setPcg) h->setPcg(tolerance, maxIterations, absoluteTolerance != 0); }
 // threads of the reference's OpenMP regions (its summation order, hence its last digits, depends on them); 0 or less: leave as is

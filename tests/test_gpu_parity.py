@@ -26,6 +26,9 @@ GRAPHS = {
     "bal_ring": (lambda: W.bal_synthetic(n_cameras=150, n_points=8000, n_obs=60000, seed=9, k_max=120, min_window=6), "lm_fix9_3_cuda"),
     "sphere": (lambda: W.sphere(nodes_per_level=16, laps=8), "lm_var_cuda"),
     "slam2d": (lambda: W.slam2d(n_poses=800, n_landmarks=200, world_size=30.0), "lm_fix3_2_cuda"),
+    # VertexSE3Expmap / EdgeSE3Expmap (types_six_dof_expmap.h:108-127, .cpp:278-293): as a pose graph, and next to projection edges in one BA
+    "sphere_expmap": (lambda: W.sphere_expmap(nodes_per_level=16, laps=8), "lm_var_cuda"),
+    "ba_pose_constraints": (lambda: W.ba_demo_with_pose_constraints(), "lm_fix6_3_cuda"),
 }
 
 
@@ -93,6 +96,53 @@ def test_lm_trajectory(name):
         assert a["result"] == int(b["result"])
     eo = o.estimates()
     assert np.max(np.abs(s.get_estimates() - eo) / (1.0 + np.abs(eo))) < 1e-6
+
+
+KERNELS = {"Huber": G.KERNEL_HUBER, "PseudoHuber": G.KERNEL_PSEUDO_HUBER, "Cauchy": G.KERNEL_CAUCHY, "GemanMcClure": G.KERNEL_GEMAN_MCCLURE,
+           "Welsch": G.KERNEL_WELSCH, "Fair": G.KERNEL_FAIR, "Tukey": G.KERNEL_TUKEY, "Saturated": G.KERNEL_SATURATED, "DCS": G.KERNEL_DCS}
+
+
+@pytest.mark.parametrize("kernel", list(KERNELS))
+@pytest.mark.parametrize("shape", ["bal", "slam2d"])
+def test_every_robust_kernel_on_the_device(kernel, shape):
+    """The nine kernels of core/robust_kernel_impl.cpp:50-170 in the device error / build kernels (edge_math.cuh): robustified chi2, the
+    weighted right-hand side and Hessian blocks, and three LM iterations against the oracle (whose kernels are pinned to the reference's
+    RobustKernelFactory classes by tests/test_reference_leaves.py).  The width sits inside the residual distribution so that both branches
+    of the piecewise kernels (Huber, Tukey, Saturated) are taken."""
+    if shape == "bal":
+        g = W.bal_synthetic(n_cameras=24, n_points=1200, n_obs=6000, seed=4, k_max=16, min_window=4, outlier_fraction=0.05); solver = "lm_fix9_3_cuda"
+    else:
+        g = W.slam2d(n_poses=300, n_landmarks=80, world_size=20.0); solver = "lm_fix3_2_cuda"
+    g.e_kernel = np.full(g.n_edges, KERNELS[kernel], dtype=np.int32); g.e_kernel_delta = np.full(g.n_edges, 1.5)
+    s = CudaSolver(g, solver, device=0); s.initialize_optimization(); s.init(); s.build_structure()
+    o = Oracle(g, "lm", "pcg"); assert o.initialize_optimization() and o.algorithm_init() and o.build_structure()
+    s.compute_active_errors(); o.compute_active_errors()
+    assert abs(s.active_robust_chi2() - o.active_robust_chi2()) <= 1e-11 * abs(o.active_robust_chi2())
+    assert abs(s.active_chi2() - o.active_chi2()) <= 1e-11 * abs(o.active_chi2())
+    assert abs(o.active_robust_chi2() - o.active_chi2()) > 1e-3 * o.active_chi2()      # the kernel does change the cost here
+    s.build_system(); o.build_system()
+    for n in ["b", "hpp_values", "hll_values", "hpl_values"]:
+        assert rel(s.get_f64(n), o.get_f64(n)) < 1e-11, n
+    s = CudaSolver(g, solver, device=0); s.initialize_optimization()
+    o = Oracle(g, "lm", "pcg"); assert o.initialize_optimization()
+    n, st = s.optimize(3); no, sto = o.optimize(3)
+    assert n == no
+    for i, (a, b) in enumerate(zip(st, sto)):
+        assert abs(a["chi2"] - b["chi2"]) <= (1e-8 if i == 0 else 1e-6) * abs(b["chi2"]), (kernel, i, a["chi2"], b["chi2"])
+        assert a["levenberg_iterations"] == int(b["levenbergIterations"]) and abs(a["lambda"] - b["lambda"]) <= 1e-6 * abs(b["lambda"])
+
+
+def test_force_stop_flag_ends_the_optimisation():
+    """SparseOptimizer::terminate() (sparse_optimizer.h:186-190): with the flag raised optimize() starts no iteration (sparse_optimizer.cpp:396)."""
+    import ctypes
+    g = W.bal_small()
+    s = CudaSolver(g, "lm_fix9_3_cuda", device=0); s.initialize_optimization()
+    flag = ctypes.c_ubyte(0); s.set_force_stop_flag(flag)
+    n, st = s.optimize(2); assert n == 2
+    flag.value = 1
+    n, st = s.optimize(5); assert n == 0
+    flag.value = 0
+    n, st = s.optimize(1); assert n == 1
 
 
 def test_gauss_newton_sphere():

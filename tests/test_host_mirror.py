@@ -16,10 +16,11 @@ def test_solver_library_registers_like_a_g2o_plugin():
     L = ctypes.CDLL(so)
     assert hasattr(L, "g2o_optimization_library_cuda")   # G2O_REGISTER_OPTIMIZATION_LIBRARY(cuda)
     for name in ["gn_var_cuda", "lm_var_cuda", "gn_fix3_2_cuda", "lm_fix3_2_cuda", "gn_fix6_3_cuda", "lm_fix6_3_cuda",
-                 "gn_fix7_3_cuda", "lm_fix7_3_cuda", "gn_fix9_3_cuda", "lm_fix9_3_cuda",
+                 "gn_fix9_3_cuda", "lm_fix9_3_cuda",
                  "gn_dense_cuda", "lm_dense_cuda", "gn_dense3_2_cuda", "lm_dense3_2_cuda", "gn_dense6_3_cuda", "lm_dense6_3_cuda",
-                 "gn_dense7_3_cuda", "lm_dense7_3_cuda", "gn_dense9_3_cuda", "lm_dense9_3_cuda", "dl_var_cuda"]:
+                 "gn_dense9_3_cuda", "lm_dense9_3_cuda", "dl_var_cuda"]:
         assert hasattr(L, "g2o_optimization_algorithm_" + name), name
+    assert not hasattr(L, "g2o_optimization_algorithm_lm_fix7_3_cuda")      # no sim3 types in the backend: the name is not offered
 
 
 @pytest.mark.gpu

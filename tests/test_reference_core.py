@@ -62,6 +62,11 @@ CASES = {
     "bal_ring_long_tracks": (lambda: W.bal_synthetic(n_cameras=150, n_points=8000, n_obs=60000, seed=9, k_max=120, min_window=6), "lm", "9_3"),
     "bal_no_kernel_gn": (lambda: W.bal_synthetic(n_cameras=20, n_points=800, n_obs=4000, seed=2, k_max=12, min_window=4, huber_delta=None), "gn", "9_3"),
     "bal_points_free": (lambda: _points_free(W.bal_small()), "lm", "var"),
+    # VertexSE3Expmap / EdgeSE3Expmap (types_six_dof_expmap.h:108-127, .cpp:278-293): a pose graph, and BA with relative-pose constraints between the
+    # cameras (off-diagonal Hpp blocks next to the Schur complement of the points)
+    "sphere_expmap_lm": (lambda: W.sphere_expmap(nodes_per_level=12, laps=6), "lm", "var"),
+    "sphere_expmap_gn": (lambda: W.sphere_expmap(nodes_per_level=10, laps=5), "gn", "var"),
+    "ba_pose_constraints": (lambda: W.ba_demo_with_pose_constraints(num_cameras=10, num_points=120), "lm", "6_3"),
 }
 
 
@@ -101,6 +106,54 @@ def test_oracle_reproduces_the_reference(name):
         assert d_o["last_step"] == d_r["last_step"] and abs(d_o["delta"] - d_r["delta"]) <= 1e-6 * d_r["delta"], (d_o, d_r)
     e_r, e_o = ref.estimates(), o.estimates()
     assert np.max(np.abs(e_o - e_r)) <= 1e-6 * (1 + np.max(np.abs(e_r)))
+
+
+STRUCTURE_CASES = ["schur_lm_huber", "ba_demo_c1", "ba_pose_constraints", "bal_medium_huber", "bal_ring_long_tracks", "sphere_lm", "sphere_expmap_lm", "schur_var_lm", "points_free_lm"]
+
+
+@pytest.mark.parametrize("name", STRUCTURE_CASES)
+def test_block_patterns_are_the_reference_s_own(name):
+    """SURVEY.md Appendix B, pinned to the reference itself: the block patterns BlockSolver::buildStructure produced (block_solver.hpp:103-256; its
+    protected _Hpp / _Hll / _Hpl / _Hschur / _HschurTransposedCCS, read through a subclass in oracle/ref_core.cpp) equal, bit for bit, the ones
+    the backend's host structure build and the oracle derive; the block values of the reference after buildSystem + one damped solve agree
+    with the oracle's.  The host half of the backend runs without a GPU."""
+    from tests.test_structure import host_structure
+    fn, alg, bs = CASES[name]
+    g = fn()
+    ref = oracle.ReferenceG2o(g, "lm", bs, threads=1); assert ref.initialize_optimization()
+    assert ref.linearize(1.0)
+    s = host_structure(g)
+    o = oracle.Oracle(g, "lm", "pcg"); assert o.initialize_optimization() and o.algorithm_init() and o.build_structure()
+    o.compute_active_errors(); o.build_system(); o.set_lambda(1.0); assert o.solve(); o.restore_diagonal()
+    names = ["dims", "pose_block_indices", "hpp_colptr", "hpp_rowidx"]
+    if o.do_schur():
+        names += ["landmark_block_indices", "hpl_colptr", "hpl_rowidx", "hschur_colptr", "hschur_rowidx", "hschur_t_colptr", "hschur_t_rowidx"]
+    for n in names:
+        r = ref.structure_i32(n)
+        assert np.array_equal(r, s.get_i32(n)), ("backend", n)
+        assert np.array_equal(r, o.get_i32(n)), ("oracle", n)
+    for n in ["b", "hpp_values"] + (["hpl_values", "hll_values", "hschur_values", "bschur"] if o.do_schur() else []):
+        r, v = ref.structure_f64(n), o.get_f64(n)
+        tol = 1e-10 if n in ("hschur_values", "bschur") else 1e-11      # differences of large sums: the Schur terms cancel most of Hpp / b
+        assert r.shape == v.shape and np.max(np.abs(r - v)) <= tol * np.max(np.abs(r)), n
+    # per-edge scatter targets (Appendix B item 7): each active edge's block is the (min, max) hessian-index pair of its vertices in the matrix its
+    # vertex classes select, transposed when vertices()[0] has the larger index (block_solver.hpp:166-214) - derived from the reference's own
+    # hessianIndex values and compared with the backend's table
+    hi = ref.hessian_index(); marg = np.asarray(g.v_marginalized, dtype=bool)
+    full = (not marg.any()) and s.get_i32("edge_targets").size > 0
+    t = s.get_i32("edge_targets").reshape(-1, 4)
+    npz = int(ref.structure_i32("dims")[0])
+    for k, e in enumerate(s.get_i32("active_edges")):
+        a, b = int(g.e_v0[e]), int(g.e_v1[e]); ia, ib = int(hi[a]), int(hi[b])
+        if ia < 0 or ib < 0:
+            assert t[k][0] == -1; continue
+        if marg[a] == marg[b]:
+            want = (1 if marg[a] else 0, min(ia, ib) - (npz if marg[a] else 0), max(ia, ib) - (npz if marg[a] else 0), 1 if ia > ib else 0)
+        elif marg[a]:
+            want = (2, ib, ia - npz, 1)
+        else:
+            want = (2, ia, ib - npz, 0)
+        assert tuple(int(x) for x in t[k]) == want, (k, t[k], want)
 
 
 def o_chi2(o):
@@ -215,54 +268,102 @@ def test_real_g2o_adapter_plugs_into_the_reference_factory():
         assert "no usable CUDA device" in r.stderr and "no CPU fallback" in r.stderr
 
 
-@pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first GPU run of the real g2o + CUDA plugin pairing: built and CPU-checked in round 1, not yet run on a GPU")
-def test_real_g2o_with_the_cuda_plugin_matches_real_g2o_on_the_cpu():
-    """The drop-in itself: the reference's SparseOptimizer (compiled from /root/reference) optimises the same graph once with its own
-    BlockSolver + PCG on the CPU and once with the `*_cuda` solver from the plugin library; chi2 per iteration (evaluated by the reference on the
-    host from the written-back estimates) and the final estimates must agree within BASELINE's gate."""
-    import os, subprocess, sys
+PAIRING = {
+    # name: (graph, reference block solver on the CPU, plugin solver name, algorithm)
+    "sphere_lm_var": (lambda: W.sphere(nodes_per_level=10, laps=5), "var", "lm_var_cuda", "lm"),
+    "sphere_expmap_lm_var": (lambda: W.sphere_expmap(nodes_per_level=10, laps=5), "var", "lm_var_cuda", "lm"),
+    "ba_demo_fix6_3": (lambda: W.ba_demo(num_cameras=8, num_points=80), "6_3", "lm_fix6_3_cuda", "lm"),
+    "ba_xyz2uv_huber_fix6_3": (lambda: W.ba_demo(num_cameras=8, num_points=80, edge_type=G.EDGE_PROJECT_XYZ2UV, robust_kernel=True), "6_3", "lm_fix6_3_cuda", "lm"),
+    "ba_pose_constraints_fix6_3": (lambda: W.ba_demo_with_pose_constraints(num_cameras=8, num_points=80), "6_3", "lm_fix6_3_cuda", "lm"),
+    "slam2d_fix3_2": (lambda: W.slam2d(n_poses=200, n_landmarks=60, world_size=16.0), "3_2", "lm_fix3_2_cuda", "lm"),
+    "slam2d_gn_fix3_2": (lambda: W.slam2d(n_poses=200, n_landmarks=60, world_size=16.0), "3_2", "gn_fix3_2_cuda", "gn"),
+    "slam2d_dogleg_var": (lambda: W.slam2d(n_poses=200, n_landmarks=60, world_size=16.0), "var", "dl_var_cuda", "dl"),
+    # the benchmarked solver: BAL cameras, BlockSolver<9,3> + PCG + LM + Huber, through the reference's SparseOptimizer
+    "bal_small_fix9_3": (lambda: W.bal_small(), "9_3", "lm_fix9_3_cuda", "lm"),
+    "bal_medium_fix9_3": (lambda: W.bal_synthetic(n_cameras=60, n_points=6000, n_obs=30000, seed=5, k_max=40, min_window=4), "9_3", "lm_fix9_3_cuda", "lm"),
+    # the reference's own OptimizationAlgorithmLevenberg / GaussNewton / Dogleg over CudaBlockSolver<P,L> : BlockSolverBase (Solver-level drop-in)
+    "bal_small_fix9_3_solver": (lambda: W.bal_small(), "9_3", "lm_fix9_3_cuda_solver", "lm"),
+    "ba_demo_fix6_3_solver": (lambda: W.ba_demo(num_cameras=8, num_points=80), "6_3", "lm_fix6_3_cuda_solver", "lm"),
+    "slam2d_fix3_2_solver": (lambda: W.slam2d(n_poses=200, n_landmarks=60, world_size=16.0), "3_2", "lm_fix3_2_cuda_solver", "lm"),
+    "sphere_var_solver": (lambda: W.sphere(nodes_per_level=10, laps=5), "var", "lm_var_cuda_solver", "lm"),
+    "sphere_gn_var_solver": (lambda: W.sphere(nodes_per_level=10, laps=5), "var", "gn_var_cuda_solver", "gn"),
+    "slam2d_dogleg_var_solver": (lambda: W.slam2d(n_poses=200, n_landmarks=60, world_size=16.0), "var", "dl_var_cuda_solver", "dl"),
+}
+
+
+def _plugin():
+    import ctypes, os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     so = os.path.join(root, "oracle", "_ref", "libg2o_solver_cuda.so")
     if not os.path.exists(so):
         pytest.skip("oracle/_ref/libg2o_solver_cuda.so was not built")
-    code = ("import ctypes, numpy as np\n"
-            "from oracle import oracle\n"
-            "from g2o_b200 import workloads as W\n"
-            "oracle.reference_core()\n"
-            f"ctypes.CDLL({so!r})\n"
-            "cases = [(W.sphere(nodes_per_level=10, laps=5), 'var', 'lm_var_cuda'), (W.ba_demo(num_cameras=8, num_points=80), '6_3', 'lm_fix6_3_cuda'),\n"
-            "         (W.slam2d(n_poses=200, n_landmarks=60, world_size=16.0), '3_2', 'lm_fix3_2_cuda')]\n"
-            "for g, bs, name in cases:\n"
-            "    cpu = oracle.ReferenceG2o(g, 'lm', bs, threads=1); assert cpu.initialize_optimization(); n1, s1 = cpu.optimize(5)\n"
-            "    gpu = oracle.ReferenceG2o(g, 'factory', name); assert gpu.initialize_optimization(); n2, s2 = gpu.optimize(5)\n"
-            "    assert n1 == n2, (name, n1, n2)\n"
-            "    for i, (a, b) in enumerate(zip(s2, s1)):\n"
-            "        assert abs(a['chi2'] - b['chi2']) <= (1e-8 if i == 0 else 1e-6) * b['chi2'], (name, i, a['chi2'], b['chi2'])\n"
-            "    e1, e2 = cpu.estimates(), gpu.estimates()\n"
-            "    assert np.max(np.abs(e1 - e2) / (1 + np.abs(e1))) < 1e-6, name\n"
-            "print('PAIRING_OK')\n")
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=180)
-    assert r.returncode == 0 and "PAIRING_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+    return ctypes.CDLL(so)
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="direct CUDA-vs-compiled-reference comparison added at the end of round 1, not yet run on a GPU (both sides are verified against the oracle)")
-@pytest.mark.parametrize("name", ["ba_demo_c1", "bal_medium_huber", "sphere_lm", "schur_lm_huber", "points_free_lm"])
+@pytest.mark.parametrize("name", list(PAIRING))
+def test_real_g2o_with_the_cuda_plugin_matches_real_g2o_on_the_cpu(name):
+    """The drop-in itself: the reference's SparseOptimizer (compiled from /root/reference) optimises the same graph once with its own
+    BlockSolver + PCG on the CPU and once with a solver of the plugin library (g2o_b200/host/real_g2o_adapter/solver_cuda.cpp, constructed by
+    the reference's OptimizationAlgorithmFactory); chi2 per iteration (evaluated by the reference on the host from the written-back
+    estimates), the number of LM trials, the number of PCG iterations and the final estimates must agree within BASELINE's gate."""
+    _plugin()
+    fn, bs, solver, alg = PAIRING[name]
+    g = fn()
+    cpu = oracle.ReferenceG2o(g, alg, bs, threads=1); assert cpu.initialize_optimization(); n1, s1 = cpu.optimize(5)
+    gpu = oracle.ReferenceG2o(g, "factory", solver); assert gpu.initialize_optimization(); n2, s2 = gpu.optimize(5)
+    assert n1 == n2, (name, n1, n2)
+    for i, (a, b) in enumerate(zip(s2, s1)):
+        assert abs(a["chi2"] - b["chi2"]) <= (1e-8 if i == 0 else 1e-6) * b["chi2"], (name, i, a["chi2"], b["chi2"])
+        assert int(a["levenbergIterations"]) == int(b["levenbergIterations"]), (name, i)
+        assert int(a["iterationsLinearSolver"]) == int(b["iterationsLinearSolver"]), (name, i, a["iterationsLinearSolver"], b["iterationsLinearSolver"])
+    e1, e2 = cpu.estimates(), gpu.estimates()
+    assert np.max(np.abs(e1 - e2) / (1 + np.abs(e1))) < 1e-6, name
+
+
+def test_fixed_size_plugin_solver_rejects_other_block_sizes():
+    """BlockSolver<BlockSolverTraits<6,3>> cannot hold 9 x 9 blocks; lm_fix6_3_cuda refuses a BAL graph at init (before any device work)."""
+    _plugin()
+    gpu = oracle.ReferenceG2o(W.bal_small(), "factory", "lm_fix6_3_cuda"); assert gpu.initialize_optimization()
+    n, _ = gpu.optimize(2)
+    assert n <= 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ba_demo_c1", "bal_medium_huber", "sphere_lm", "sphere_expmap_lm", "ba_pose_constraints", "schur_lm_huber", "points_free_lm"])
 def test_cuda_path_against_the_reference_itself(name):
-    """The CUDA path (through the C ABI) and the reference compiled from /root/reference, on the same graph in the same process."""
+    """The CUDA path (through the C ABI) and the reference compiled from /root/reference, on the same graph in the same process: index map,
+    block patterns, block values of one damped linearisation, then the LM trajectory."""
     from g2o_b200.binding import CudaSolver
     fn, alg, bs = CASES[name]
     g = fn()
     solver = {"6_3": "lm_fix6_3_cuda", "9_3": "lm_fix9_3_cuda", "3_2": "lm_fix3_2_cuda", "var": "lm_var_cuda"}[bs]
+    # one linearisation: the reference's BlockSolver matrices against the device arrays
+    ref = oracle.ReferenceG2o(g, alg, bs, threads=1); assert ref.initialize_optimization()
+    s = CudaSolver(g, solver, device=0); s.initialize_optimization(); s.init(); s.build_structure()
+    assert np.array_equal(ref.hessian_index(), s.get_i32("hessian_index"))
+    full = not np.asarray(g.v_marginalized).any() and len(set(np.asarray(g.v_type).tolist())) > 1
+    if not full:
+        assert ref.linearize(1.0)
+        s.compute_active_errors(); s.build_system(); s.set_lambda(1.0); assert s.solve()
+        schur = bool(np.asarray(g.v_marginalized).any())
+        for n in ["hpp_colptr", "hpp_rowidx"] + (["hpl_colptr", "hpl_rowidx", "hschur_colptr", "hschur_rowidx", "hschur_t_colptr", "hschur_t_rowidx"] if schur else []):
+            assert np.array_equal(ref.structure_i32(n), s.get_i32(n)), n
+        for n, tol in [("b", 1e-11), ("hpl_values", 1e-11), ("hschur_values", 1e-10), ("bschur", 1e-10)] if schur else [("b", 1e-11)]:
+            r, v = ref.structure_f64(n), s.get_f64(n)
+            assert r.shape == v.shape and np.max(np.abs(r - v)) <= tol * np.max(np.abs(r)), n
+        s.restore_diagonal()
+        r, v = ref.structure_f64("hpp_values"), s.get_f64("hpp_values")                 # after restoreDiagonal on both sides
+        assert r.shape == v.shape and np.max(np.abs(r - v)) <= 1e-11 * np.max(np.abs(r))
+    # trajectory
     ref = oracle.ReferenceG2o(g, alg, bs, threads=1); assert ref.initialize_optimization()
     s = CudaSolver(g, solver, device=0); s.initialize_optimization()
-    assert np.array_equal(ref.hessian_index(), s.get_i32("hessian_index"))
     n_r, st_r = ref.optimize(6); n_s, st_s = s.optimize(6)
     assert n_r == n_s
     for i, (a, b) in enumerate(zip(st_s, st_r)):
         assert abs(a["chi2"] - b["chi2"]) <= (1e-8 if i == 0 else 1e-6) * b["chi2"], (name, i, a["chi2"], b["chi2"])
         assert a["levenberg_iterations"] == int(b["levenbergIterations"])
+        assert a["iterations_linear_solver"] == int(b["iterationsLinearSolver"])
     assert abs(st_s[-1]["lambda"] - ref.current_lambda()) <= 1e-6 * ref.current_lambda()
     e_r = ref.estimates()
     assert np.max(np.abs(s.get_estimates() - e_r) / (1.0 + np.abs(e_r))) < 1e-6
