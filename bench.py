@@ -4,10 +4,11 @@ BAL-Venice-shaped bundle adjustment).
 
     python bench.py --gpus N --steps K --warmup W          # our CUDA backend (N>1: launched under torchrun)
     python bench.py --impl reference --steps K --warmup W  # the reference itself (oracle/_ref/libg2o_ref_core.so, else the oracle port) on the host cores
+    python bench.py --workload c1|c2|c3|c4|c5 ...          # the other BASELINE.json configs (default c3 = the one the metric is quoted on)
 
-A step is one outer Levenberg-Marquardt iteration (`OptimizationAlgorithmLevenberg::solve`, all its trials) of
-config C3: 1778 cameras / 993 923 points / 5 001 946 observations, BlockSolver<9,3> + PCG, Huber(1.0), synthetic.
-One JSON line is printed by rank 0.
+A step is one outer Levenberg-Marquardt iteration (`OptimizationAlgorithmLevenberg::solve`, all its trials); both arms run LM iterations
+0 .. W+K-1 from the same initial estimates and time iterations W .. W+K-1.  Default workload: config C3, 1778 cameras / 993 923 points /
+5 001 946 observations, BlockSolver<9,3> + PCG, Huber(1.0), synthetic.  One JSON line is printed by rank 0.
 """
 from __future__ import annotations
 
@@ -28,16 +29,37 @@ UNIT = "LM iterations/s"
 
 
 def workload(name: str, scale: float):
+    """(graph, description, CUDA solver name) of a BASELINE.json config."""
     from g2o_b200 import workloads as W
-    if name == "bal_venice":
+    if name in ("bal_venice", "c3"):
         if scale == 1.0:
-            return W.bal_venice(), "C3 bal_venice: 1778 cameras / 993923 points / 5001946 observations, Huber(1.0), BlockSolver<9,3>+PCG"
+            return W.bal_venice(), "C3 bal_venice: 1778 cameras / 993923 points / 5001946 observations, Huber(1.0), BlockSolver<9,3>+PCG", "lm_fix9_3_cuda"
         nc = max(16, int(1778 * scale ** 0.5)); npnt = int(993_923 * scale); nobs = int(5_001_946 * scale)
         return (W.bal_synthetic(n_cameras=nc, n_points=npnt, n_obs=nobs, k_max=min(500, nc)),
-                f"C3 bal_venice scaled x{scale}: {nc} cameras / {npnt} points / {nobs} observations")
-    if name == "bal_large":
-        return W.bal_large(), "C4 bal_large: 10000 cameras / 4000000 points / 20000000 observations"
+                f"C3 bal_venice scaled x{scale}: {nc} cameras / {npnt} points / {nobs} observations", "lm_fix9_3_cuda")
+    if name in ("bal_large", "c4"):
+        return W.bal_large(), "C4 bal_large: 10000 cameras / 4000000 points / 20000000 observations, Huber(1.0), BlockSolver<9,3>+PCG", "lm_fix9_3_cuda"
+    if name == "c1":
+        return W.ba_demo(), "C1 ba_demo: 15 cameras / 300 points, EdgeSE3ProjectXYZ, pixel noise 1, BlockSolver_6_3+PCG", "lm_fix6_3_cuda"
+    if name == "c2":
+        return W.sphere(), "C2 create_sphere: 10000 VertexSE3 / 39599 EdgeSE3, lm_var (BlockSolverX) + PCG", "lm_var_cuda"
+    if name == "c5":
+        return W.slam2d(), "C5 simulator2d-shaped SLAM: 100000 poses / 20000 landmarks, EdgeSE2 + EdgeSE2PointXY, Huber(1.0), BlockSolver<3,2> (Schur) + PCG", "lm_fix3_2_cuda"
     raise SystemExit(f"unknown workload {name}")
+
+
+def reference_block_solver(g) -> str:
+    import numpy as np
+    vt = set(int(t) for t in np.unique(g.v_type)); marg = bool(np.any(g.v_marginalized))
+    return "9_3" if marg and 6 in vt else "6_3" if marg and 4 in vt else "3_2" if marg and 1 in vt else "var"
+
+
+def host_threads() -> int:
+    """All host cores this process may use - not OMP_NUM_THREADS, which torchrun sets to 1 for its children."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 class ClockSampler:
@@ -122,21 +144,25 @@ def fp64_tensor_peak():
     return 37.2, "nominal (148 SMs x 64 FP64 FMA/clk x 1.965 GHz)"
 
 
+REFERENCE_BUDGET_S = 600.0      # wall-clock cap of the reference arm's optimize(): the reference's own forceStopFlag ends it between iterations
+
+
 def run_reference(args):
-    """The reference's own CPU implementation on the host cores.  When oracle/_ref/libg2o_ref_core.so exists (built from /root/reference by
-    `make -C oracle ref_core`: g2o/core + BlockSolver + LinearSolverPCG + the types, unmodified, against the stand-in for the absent Eigen3,
-    OpenMP on) that is the real reference: SparseOptimizer::optimize with OptimizationAlgorithmLevenberg over BlockSolver<9,3> + PCG, as
-    examples/bal/bal_example.cpp sets it up.  Otherwise the oracle port.  Bounded sample: at most 1 warm-up + 3 timed LM iterations of the
-    full workload (iteration 0 also pays buildStructure and is never timed); per-iteration times are G2OBatchStatistics::timeIteration."""
+    """The reference's own CPU implementation on the host cores, all of them (sched_getaffinity, whatever OMP_NUM_THREADS says).  When
+    oracle/_ref/libg2o_ref_core.so exists (built from /root/reference by `make -C oracle ref_core`: g2o/core + BlockSolver + LinearSolverPCG +
+    the types, unmodified, against the stand-in for the absent Eigen3, OpenMP on) that is the real reference: SparseOptimizer::optimize with
+    OptimizationAlgorithmLevenberg over BlockSolver<P,L> + PCG, as examples/bal/bal_example.cpp sets it up.  Otherwise the oracle port.
+    The same LM iterations as the CUDA arm: optimize(W + K) from the same initial estimates, iterations W .. W+K-1 timed
+    (G2OBatchStatistics::timeIteration).  Bounded by REFERENCE_BUDGET_S: if the budget ends first, fewer iterations are timed and the
+    line says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
     from oracle import oracle as orc
     if orc.reference_core() is not None and not os.environ.get("G2O_BENCH_REFERENCE_CHILD"):
         # the leg that drives the compiled reference runs in a child process; if it dies, this process still reports the oracle port
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], capture_output=True, text=True, timeout=1500,
+            r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], capture_output=True, text=True, timeout=REFERENCE_BUDGET_S + 900,
                                env=dict(os.environ, G2O_BENCH_REFERENCE_CHILD="1", RANK="0"))
             if r.returncode == 0 and r.stdout.strip():
                 print(r.stdout.strip().splitlines()[-1], flush=True)
@@ -145,51 +171,47 @@ def run_reference(args):
         except Exception as e:
             sys.stderr.write(f"bench: reference child failed: {e}\n")
         orc.reference_core = lambda: None
-    g, desc = workload(args.workload, args.scale)
-    threads = orc.max_threads()
-    warm, steps = 1, max(1, min(args.steps, 3))
+    g, desc, _ = workload(args.workload, args.scale)
+    threads = host_threads()
+    warm, steps = args.warmup, args.steps
+    budget = float(os.environ.get("G2O_BENCH_REFERENCE_BUDGET_S", REFERENCE_BUDGET_S))
 
-    def timed_part(stats):
+    def timed_part(stats, w):
         times = [s["timeIteration"] for s in stats]
-        timed = times[warm:] if len(times) > warm else times
-        return timed, (len(timed) / sum(timed) if timed and sum(timed) > 0 else 0.0)
+        if len(times) > w:
+            timed, w_used = times[w:], w
+        else:                      # the budget ended inside the warm-up window: time what ran after iteration 0 (which pays buildStructure)
+            timed, w_used = (times[1:], 1) if len(times) > 1 else (times, 0)
+        return timed, w_used, (len(timed) / sum(timed) if timed and sum(timed) > 0 else 0.0)
 
-    kind, solver, extra = "port", "CPU oracle port of BlockSolver + LinearSolverPCG (oracle/g2o_oracle.cpp)", {}
+    kind, impl_detail, extra = "port", "CPU oracle port of BlockSolver + LinearSolverPCG (oracle/g2o_oracle.cpp)", {}
     stats = None
     if orc.reference_core() is not None:
-        vt = set(int(t) for t in np.unique(g.v_type)); marg = bool(np.any(g.v_marginalized))
-        bs = "9_3" if marg and 6 in vt else "6_3" if marg and 4 in vt else "3_2" if marg and 1 in vt else "var"
+        bs = reference_block_solver(g)
         try:
             ref = orc.ReferenceG2o(g, "lm", bs, threads=threads)
             if ref.initialize_optimization():
-                n, stats = ref.optimize(warm + steps)
+                n, stats = ref.optimize(warm + steps, budget_seconds=budget)
                 kind = "reference"
-                solver = f"the reference itself: SparseOptimizer + OptimizationAlgorithmLevenberg + BlockSolver<{bs.replace("_", ",")}> + LinearSolverPCG compiled from /root/reference (Eigen3 replaced by oracle/eigen_shim, OpenMP, -O3)"
+                impl_detail = f"the reference itself: SparseOptimizer + OptimizationAlgorithmLevenberg + BlockSolver<{bs.replace('_', ',')}> + LinearSolverPCG compiled from /root/reference (Eigen3 replaced by the scalar stand-in oracle/eigen_shim - no SIMD expression templates -, OpenMP, -O3)"
         except Exception as e:      # fall back to the port, say why
             extra["reference_error"] = str(e)[:200]
             stats = None
     if stats is None:
         o = orc.Oracle(g, "lm", "pcg", threads=threads)
         o.initialize_optimization()
-        n, stats = o.optimize(warm + steps)
-    timed, value = timed_part(stats)
-    if kind == "reference" and not args.no_cpu:      # the port on the same sample, for comparison
-        try:
-            o = orc.Oracle(g, "lm", "pcg", threads=threads)
-            o.initialize_optimization()
-            _, pstats = o.optimize(warm + 1)          # one timed iteration is enough for the side-by-side
-            ptimed, pvalue = timed_part(pstats)
-            extra["port"] = {"value": pvalue, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": 1e3 * sum(ptimed) / max(len(ptimed), 1),
-                             "chi2": [s["chi2"] for s in pstats]}
-        except Exception as e:
-            extra["port_error"] = str(e)[:200]
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed), "warmup": min(warm, len(stats)),
+        n, stats = o.optimize(min(warm + steps, 4))
+    timed, w_used, value = timed_part(stats, warm)
+    same = len(timed) == steps and w_used == warm
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(timed), "warmup": w_used,
             "ms_per_step": 1e3 * sum(timed) / max(len(timed), 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": desc, "solver": solver},
+            "data": "synthetic", "config": {"workload": desc}, "impl_detail": impl_detail,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
-                             "sample": f"{len(timed)} LM iteration(s) of the full workload after {min(warm, len(stats))} warm-up iteration(s) (requested steps={args.steps}, warmup={args.warmup}; capped to keep the run within minutes)"},
+                             "sample": (f"LM iterations {w_used}..{w_used + len(timed) - 1} of the full workload, optimize({warm + steps}) from the initial estimates"
+                                        + ("" if same else f" - stopped by the {budget:.0f} s budget after {len(stats)} iterations (requested steps={steps}, warmup={warm})"))},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
-            "chi2": [s["chi2"] for s in stats],
+            "lm": {"chi2": [s["chi2"] for s in stats], "trials": [int(s["levenbergIterations"]) for s in stats], "pcg_iterations": [int(s["iterationsLinearSolver"]) for s in stats],
+                   "seconds": [s["timeIteration"] for s in stats]},
             "phases_s": {k: stats[-1][k] for k in ("timeResiduals", "timeQuadraticForm", "timeSchurComplement", "timeLinearSolver", "timeUpdate")} if stats else None}
     line.update(extra)
     print(json.dumps(line), flush=True)
@@ -199,15 +221,13 @@ def cpu_sample(g):
     """cpu_baseline of the main arm: LM iteration 1 of the same graph on all host threads (steady state: iteration 0 additionally pays
     buildStructure, which the GPU arm also keeps outside its timed region) - the real reference when oracle/_ref/libg2o_ref_core.so is there
     (kind "reference"), else the oracle port (kind "port").  Never raises: a failure of the reference leg falls back to the port."""
-    import numpy as np
     from oracle import oracle as orc
-    threads = orc.max_threads()
+    threads = host_threads()
     t0 = time.perf_counter()
     kind, cstats, note = "port", None, ""
     if orc.reference_core() is not None:
         try:
-            vt = set(int(t) for t in np.unique(g.v_type)); marg = bool(np.any(g.v_marginalized))
-            bs = "9_3" if marg and 6 in vt else "6_3" if marg and 4 in vt else "3_2" if marg and 1 in vt else "var"
+            bs = reference_block_solver(g)
             ref = orc.ReferenceG2o(g, "lm", bs, threads=threads)
             if ref.initialize_optimization():
                 _, cstats = ref.optimize(2)
@@ -263,9 +283,10 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    g, desc = workload(args.workload, args.scale)
+    g, desc, solver_name = workload(args.workload, args.scale)
     est0 = g.v_estimate.copy()
-    s = CudaSolver(g, "lm_fix9_3_cuda", device=local)
+    stream = torch.cuda.Stream(device=local)           # the solver runs on this stream, so torch's CUDA events bracket exactly its work
+    s = CudaSolver(g, solver_name, device=local, stream=stream.cuda_stream)
     if world > 1:
         from g2o_b200.dist import install_nccl, install_torch_allreduce
         if os.environ.get("G2O_BENCH_COLLECTIVES", "nccl") == "hook":
@@ -274,10 +295,17 @@ def run_ours(args):
             install_nccl(s, rank, world)                 # collectives issued by libg2ocu.so itself
     s.initialize_optimization()
     s.init()
-    if world > 1 and os.environ.get("G2O_BENCH_P2P", "1") != "0":
+    schur_graph = bool(np.any(g.v_marginalized))
+    s.build_structure()
+    if world > 1 and schur_graph and os.environ.get("G2O_BENCH_P2P", "1") != "0":
         from g2o_b200.dist import install_p2p
-        s.build_structure()
-        install_p2p(s, rank, world)                      # q = A d of the slab PCG is exchanged through NVLink peer memory
+        install_p2p(s, rank, world)                      # the reduced system and q = A d of the slab PCG are exchanged through NVLink peer memory
+    # timing rule: inputs larger than L2, or an L2 flush between timed iterations.  The matrices every iteration streams through (Hpl + the
+    # solved system) decide which; small workloads get a 256 MB write on the solver's stream between iterations (inside the timed region)
+    _d = s.get_i32("internal_dims"); _P = int(_d[2]) // max(int(_d[0]), 1); _L = int(_d[3]) // max(int(_d[1]), 1) if int(_d[1]) else 0
+    _nnz = int(s.get_i32("hschur_colptr")[-1]) if schur_graph else int(s.get_i32("hpp_colptr")[-1])
+    working_set_mb = (int(s.get_i32("hpl_colptr")[-1]) * _P * _L * 8 if schur_graph else 0) / 1e6 + _nnz * _P * _P * 8 / 1e6
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}") if working_set_mb <= 126 else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -301,20 +329,29 @@ def run_ours(args):
                 s.get_estimates(host_out); host_in, host_out = host_out, host_in
         s.reset_counters()
         sampler = ClockSampler(local); sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         l0 = s.launch_count()
         t0 = time.perf_counter()
+        ev0.record(stream)
         for i in range(args.warmup, args.warmup + args.steps):
+            if flush is not None:
+                with torch.cuda.stream(stream):
+                    flush.zero_()                              # L2 flush (the workload fits the 126 MB L2)
             if e2e:
                 s.set_estimates(host_in)                       # H2D of this step's inputs (pinned)
             stats.append(s.solver_iteration(i))
             if e2e:
                 s.get_estimates(host_out); host_in, host_out = host_out, host_in   # D2H of the step's result (estimates + chi2); it feeds the next step
+        ev1.record(stream)
         barrier()
-        dt = time.perf_counter() - t0
-        clocks = sampler.stop()
+        wall = time.perf_counter() - t0
+        dt = 1e-3 * ev0.elapsed_time(ev1)                      # device time between the two events on the solver's stream (host control included: the stream idles while the host decides)
+        clocks = sampler.stop(); clocks["wall_over_device"] = round(wall / dt, 4) if dt > 0 else None
+        pcg_total = int(s.get_i32("linear_solver_iterations_total")[0])     # PCG iterations of ALL solves of the timed steps (rejected trials included)
         phases = {ph: s.phase_time(ph) for ph in ["errors", "build", "schur", "schur_coeff", "schur_pairs", "schur_tiles", "schur_exchange", "pcg_setup", "pcg_spmv",
                                                   "pcg_exchange", "pcg_vec", "linear_solver", "backsub", "update"]}
+        phases["_pcg_total"] = pcg_total
         return dt, stats, s.launch_count() - l0, phases, clocks
 
     dt, stats, launches, _, clocks = timed_run(False)          # headline: phase-level events only
@@ -331,64 +368,83 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    dims = s.get_i32("dims"); nnzS = int(s.get_i32("hschur_colptr")[-1]); nc, npnt = int(dims[0]), int(dims[1]); ne = g.n_edges
+    from g2o_b200.graph import EDGE_DIM, EDGE_MEAS_DIM
+    dims = s.get_i32("internal_dims"); nc, npnt = int(dims[0]), int(dims[1])
+    P = int(dims[2]) // max(nc, 1); L = int(dims[3]) // max(npnt, 1) if npnt else 0
+    et = np.asarray(g.e_type); marg = np.asarray(g.v_marginalized, dtype=bool)
+    pl_edge = marg[np.asarray(g.e_v0)] != marg[np.asarray(g.e_v1)]
+    ne_pl, ne_pp = int(pl_edge.sum()), int((~pl_edge).sum())
+    E_pl = int(EDGE_DIM[et[pl_edge][0]]) if ne_pl else 0
+    E_pp, M_pp = (int(EDGE_DIM[et[~pl_edge][0]]), int(EDGE_MEAS_DIM[et[~pl_edge][0]])) if ne_pp else (0, 0)
+    Sp = (len(g.v_estimate) - 3 * int(marg.sum() if L == 3 else 0) - 2 * int(marg.sum() if L == 2 else 0)) // max(int((~marg).sum()), 1)   # stored pose estimate size
+    nnzA = int(s.get_i32("hschur_colptr")[-1]) if schur_graph else int(s.get_i32("hpp_colptr")[-1])
     peak, peak_src = measured_peaks()
-    # algorithmic bytes per launch: P=9, L=3, E=2
-    bytes_spmv = nnzS * 81 * 8 + nc * 81 * 8 + 10 * nc * 9 * 8
-    bytes_build = ne * (16 + 8 + 216) + npnt * (24 + 72 + 24) + nc * (72 + 648 + 72)
-    bytes_schur = ne * 216 + npnt * (72 + 24) + nc * (648 + 72) + npnt * 72 + nnzS * 648 + nc * 72
-    # Schur tile kernel: FP64 tensor pipe.  Algorithmic flops = 2 P P L per (landmark, camera pair i <= j) of the tracks it handles (>= 8 observations)
-    k = np.bincount(np.asarray(g.e_v1) - nc, minlength=npnt).astype(np.int64)
-    pairs_all = int((k * (k + 1) // 2).sum()); kt = k[k >= 8]; pairs_tiles = int((kt * (kt + 1) // 2).sum())
-    flops_tiles = 2.0 * 81 * 3 * pairs_tiles
-    bytes_coeff = ne * 216 * 2 + npnt * (72 + 24) + nc * 72        # read Hpl, write W = Hpl Dinv, read Dinv/db, update b_schur
+    # algorithmic bytes per launch for block sizes P, L and error dimensions E
+    bytes_spmv = nnzA * P * P * 8 + nc * P * P * 8 + 10 * nc * P * 8
+    bytes_build = ne_pl * (E_pl * 8 + 8 + P * L * 8) + ne_pp * (M_pp * 8 + 8 + P * P * 8) + npnt * (L * 8 + L * L * 8 + L * 8) + nc * (Sp * 8 + P * P * 8 + P * 8)
+    bytes_schur = ne_pl * P * L * 8 + npnt * (L * L + L) * 8 + nc * (P * P + P) * 8 + npnt * L * L * 8 + nnzA * P * P * 8 + nc * P * 8
+    # Schur product kernels: FP64 pipe.  Algorithmic flops = 2 P P L per (landmark, camera pair i <= j); this rank's landmarks only (sharded runs)
+    flops_tiles = flops_pairs = 0.0
+    pairs_all = 0
+    if schur_graph:
+        lm_slot = s.get_i32("hessian_index")[np.asarray(g.e_v0)[pl_edge]] if marg[np.asarray(g.e_v0)[pl_edge][0]] else s.get_i32("hessian_index")[np.asarray(g.e_v1)[pl_edge]]
+        k = np.bincount(lm_slot[lm_slot >= 0] - nc, minlength=npnt).astype(np.int64)
+        lo, hi = (int(v) for v in s.get_i32("shard_landmark_range")) if world > 1 else (0, npnt)
+        k = k[lo:hi]
+        pairs_all = int((k * (k + 1) // 2).sum()); kt = k[k >= 8]; pairs_tiles = int((kt * (kt + 1) // 2).sum())
+        flops_tiles = 2.0 * P * P * L * pairs_tiles; flops_pairs = 2.0 * P * P * L * (pairs_all - pairs_tiles)
+    bytes_coeff = ne_pl * P * L * 8 + npnt * (L * L + L) * 8 + nc * P * 8        # read Hpl, Dinv, db; update b_schur
     per = {}
     for name, nbytes in [("pcg_spmv", bytes_spmv), ("build", bytes_build), ("schur", bytes_schur), ("schur_coeff", bytes_coeff)]:
         sec, _, calls = phases[name]
         if calls:
             per[name] = {"seconds_total": sec, "calls": calls, "avg_ms": 1e3 * sec / calls, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (sec / calls) / 1e9,
                          "frac_of_hbm_peak": nbytes / (sec / calls) / 1e9 / peak}
-    if "pcg_spmv" in per:   # launches issued after convergence return at once: rate per ACTIVE product = per PCG iteration
-        its = sum(st["iterations_linear_solver"] for st in stats[args.warmup:])
-        if its:
-            per["pcg_spmv"].update({"active_products": its, "avg_ms_active": 1e3 * per["pcg_spmv"]["seconds_total"] / its,
-                                    "achieved_gbs": bytes_spmv / (per["pcg_spmv"]["seconds_total"] / its) / 1e9,
-                                    "frac_of_hbm_peak": bytes_spmv / (per["pcg_spmv"]["seconds_total"] / its) / 1e9 / peak})
+    active_products = phases.pop("_pcg_total")      # every solve of every trial: stats[*].iterations_linear_solver only holds the last solve of an iteration
+    if "pcg_spmv" in per and active_products:   # launches issued after convergence return at once: rate per ACTIVE product = per PCG iteration
+        sec_active = per["pcg_spmv"]["seconds_total"] / active_products
+        slab = bytes_spmv / world if world > 1 and schur_graph else bytes_spmv          # slab PCG: each rank multiplies its block range
+        per["pcg_spmv"].update({"active_products": active_products, "avg_ms_active": 1e3 * sec_active, "algorithmic_bytes": int(slab),
+                                "achieved_gbs": slab / sec_active / 1e9, "frac_of_hbm_peak": slab / sec_active / 1e9 / peak})
     tpeak, tpeak_src = fp64_tensor_peak()
-    for name, fl in [("schur_tiles", flops_tiles), ("schur_pairs", 2.0 * 81 * 3 * (pairs_all - pairs_tiles))]:
+    for name, fl in [("schur_tiles", flops_tiles), ("schur_pairs", flops_pairs)]:
         sec, _, calls = phases[name]
-        if calls:
+        if calls and fl:
             per[name] = {"seconds_total": sec, "calls": calls, "avg_ms": 1e3 * sec / calls, "algorithmic_flops": fl, "achieved_tflops": fl / (sec / calls) / 1e12,
                          "frac_of_fp64_peak": fl / (sec / calls) / 1e12 / tpeak}
-    kernels = {"pcg_spmv": "spmv_sym_kernel<9>", "build": "build_pl_kernel<BAL> + pose_accum_kernel<BAL>", "schur_coeff": "coeff_w_kernel<9,3>",
-               "schur_tiles": "schur_mma_kernel<9,3>", "schur_pairs": "schur_pairs_kernel<9,3>"}
+    mma = P in (6, 9) and L == 3
+    kernels = {"pcg_spmv": f"spmv_tma_kernel<{P}>", "build": "build_pl_kernel + pose_accum_kernel" if ne_pl else "build_pp_kernel", "schur_coeff": f"schur_coeff_kernel<{P},{L}>",
+               "schur_tiles": f"schur_mma_kernel<{P},{L}>" if mma else f"schur_tile_kernel<{P},{L}>", "schur_pairs": f"schur_pairs_kernel<{P},{L}>"}
     traffic = {}
-    tp = os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if os.path.exists(tp):
         with open(tp) as fh:
-            traffic = json.load(fh)
-    cand = [k2 for k2 in per if k2 in kernels]
+            traffic = json.load(fh).get(args.workload if args.workload != "bal_venice" else "c3", {})
+    cand = [k2 for k2 in per if k2 in kernels and k2 != "schur"]
     dominant = max(cand, key=lambda k2: per[k2]["seconds_total"]) if cand else None
     roof = None
     if dominant and "algorithmic_flops" in per[dominant]:
         a = per[dominant]["achieved_tflops"]
         roof = {"kernel": kernels[dominant], "bound": "tensor", "achieved": a, "peak": tpeak, "unit": "TFLOP/s", "frac": a / tpeak, "traffic": traffic.get(kernels[dominant]), "peak_source": tpeak_src,
-                "note": "FP64 tensor pipe (DMMA m8n8k4); FP64 FMA shares the same pipe on B200 (tools/dmma_dfma_mix.cu), so this is the only FP64 roof",
+                "note": "FP64 tensor pipe (DMMA m8n8k4); FP64 FMA shares the same pipe on B200 (tools/dmma_dfma_mix.cu), so this is the only FP64 roof"
+                        + ("; flops and time are rank 0's share of the landmarks" if world > 1 else ""),
                 "avg_launch_ms": per[dominant]["avg_ms"], "phases": per}
     elif dominant:
         a = per[dominant]["achieved_gbs"]
         roof = {"kernel": kernels[dominant], "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": traffic.get(kernels[dominant]), "peak_source": peak_src,
-                "avg_launch_ms": per[dominant]["avg_ms"], "phases": per}
-    timed_stats = stats[args.warmup:]
+                "avg_launch_ms": per[dominant].get("avg_ms_active", per[dominant]["avg_ms"]), "phases": per}
     value = args.steps / dt
     est_bytes = int(est0.nbytes)
+    ws = working_set_mb
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "solver": "lm_fix9_3_cuda (Schur + block-Jacobi PCG)", "l2_policy": "working set (Hpl 1.08 GB, Hschur %.2f GB) exceeds the 126 MB L2" % (nnzS * 648 / 1e9),
-                       "nnz_hschur_blocks": nnzS, "parallelism": f"landmark-sharded x{world}" if world > 1 else "single GPU"},
+            "config": {"workload": desc},
+            "impl_detail": {"solver": solver_name, "parallelism": f"landmark-sharded x{world}" if world > 1 else "single GPU", "nnz_system_blocks": nnzA,
+                            "l2_policy": ("working set (Hpl + reduced system = %.0f MB) exceeds the 126 MB L2" % ws) if ws > 126 else
+                                         ("working set (%.1f MB) fits the 126 MB L2; 256 MB are written between timed iterations to flush it" % ws)},
             "e2e": {"value": args.steps / dt_e, "unit": UNIT, "h2d_bytes_per_step": est_bytes, "d2h_bytes_per_step": est_bytes + 8,
                     "note": "per step: host vertex estimates -> device (pinned), one LM iteration through g2ocu_solver_iteration, estimates + chi2 back to the host"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "gpu_launches": int(launches), "active_products": int(active_products), "clocks": clocks, "roofline": roof,
             "phase_ms_per_step": {ph: round(1e3 * v[0] / args.steps, 4) for ph, v in phases.items()},
             "phase_note": "from a separate pass of the same steps with per-kernel CUDA events (%.3f ms per step in that pass)" % (1e3 * dt_k / args.steps),
             "lm": {"chi2": [st["chi2"] for st in stats], "lambda": [st["lambda"] for st in stats], "trials": [st["levenberg_iterations"] for st in stats],
@@ -415,7 +471,7 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     elif args.impl == "cpu_sample":
-        g, _ = workload(args.workload, args.scale)
+        g, _, _ = workload(args.workload, args.scale)
         print(json.dumps(cpu_sample(g)), flush=True)
     else:
         run_ours(args)

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -108,7 +109,7 @@ struct g2ocu_solver {
   // solver state
   double lambda = 0.0;            // damping currently "set" on the diagonals (0 after restoreDiagonal)
   double pcgResidual = -1.0;      // LinearSolverPCG::_residual, persists across solves until init()
-  int lastPcgIterations = 0;
+  int lastPcgIterations = 0; int64_t totalPcgIterations = 0;   // of the last solve / of all solves since g2ocu_reset_counters
   bool errorsValid = false; double chi2Robust = 0, chi2Plain = 0;
   // estimates of each class form one contiguous run of the packed host array and together cover it: copies go straight between the caller's buffer and the device
   bool fastEstimates = false; int64_t poseHostOff = 0, lmHostOff = 0;
@@ -405,7 +406,10 @@ int buildDevice(g2ocu_solver* s) {
     }
     {  // tile entries grouped by (row tile, column strip), split in chunks of at most kTileChunk entries (one CTA each)
       const int kTileChunk = useMma ? 1024 : 256;
-      std::stable_sort(entries.begin(), entries.end(), [](const TileEntry& a, const TileEntry& b) { return a.key < b.key; });
+      // inside a tile: landmarks that touch the same groups of 8 column cameras next to each other (the K-packed tile kernel skips a group
+      // none of the landmarks sharing a DMMA touches)
+      auto groupsOf = [](uint32_t m) { return ((m & 0xffu) ? 1u : 0u) | ((m & 0xff00u) ? 2u : 0u) | ((m & 0xff0000u) ? 4u : 0u) | ((m & 0xff000000u) ? 8u : 0u); };
+      std::stable_sort(entries.begin(), entries.end(), [&](const TileEntry& a, const TileEntry& b) { return a.key != b.key ? a.key < b.key : groupsOf(a.maskJ) < groupsOf(b.maskJ); });
       std::vector<int32_t> eLm(entries.size()), eBI(entries.size()), eBJ(entries.size()), cI, cJ, cB, cE; std::vector<uint32_t> eMJ(entries.size()); std::vector<uint8_t> eMI(entries.size());
       for (size_t i = 0; i < entries.size(); ++i) { eLm[i] = entries[i].lm; eBI[i] = entries[i].baseI; eBJ[i] = entries[i].baseJ; eMJ[i] = entries[i].maskJ; eMI[i] = entries[i].maskI; }
       for (size_t i = 0; i < entries.size();) {
@@ -420,7 +424,7 @@ int buildDevice(g2ocu_solver* s) {
       sd.chunkI = s->tChunkI.p; sd.chunkJ = s->tChunkJ.p; sd.chunkBegin = s->tChunkB.p; sd.chunkEnd = s->tChunkE.p;
       sd.entLm = s->tEntLm.p; sd.entBaseI = s->tEntBI.p; sd.entBaseJ = s->tEntBJ.p; sd.entMaskJ = s->tEntMJ.p; sd.entMaskI = s->tEntMI.p;
     }
-    if (useMma) { CU(s->W.alloc((size_t)st.hplRowIdx.size() * P * L + 2)); CU(s->W.zero(stream)); sd.W = s->W.p; }
+    if (useMma && !schurKpackEnabled()) { CU(s->W.alloc((size_t)st.hplRowIdx.size() * P * L + 2)); CU(s->W.zero(stream)); sd.W = s->W.p; }
     // multi-GPU: the reduced system is reduce-scattered into equal block ranges (the last one padded), rank r solves with blocks [r c, (r+1) c)
     CU(s->S.alloc((s->world > 1 ? (size_t)s->slabBlocks * s->world * P * P : (size_t)st.sColIdx.size() * P * P) + 2)); CU(s->S.zero(stream));   // +2: 16-byte aligned bulk copies may read one double past the last block
     CU(s->Dinv.alloc((size_t)st.numLandmarks * L * L)); CU(s->dbv.alloc((size_t)st.numLandmarks * L)); CU(s->bschur.alloc((size_t)st.sizePoses));
@@ -533,7 +537,7 @@ int solvePcg(g2ocu_solver* s, const double* rhs) {
     if (converged || issued >= maxIter) done = true;
     if (!std::isfinite(s->hostScal[8 + 2])) done = true;   // NaN/Inf in the recurrence: stop issuing work (the reference would spin to maxIter)
   }
-  s->lastPcgIterations = (int)s->hostScal[8 + 7];
+  s->lastPcgIterations = (int)s->hostScal[8 + 7]; s->totalPcgIterations += s->lastPcgIterations;
   s->pcgResidual = 0.5 * s->hostScal[8 + 2];
   return G2OCU_OK;
 }
@@ -1230,6 +1234,8 @@ int64_t g2ocu_get_i32(g2ocu_solver* s, const char* name, int32_t* out, int64_t c
   if (n == "active_vertices") return copyOutI32(st.activeVertices, out, cap);
   if (n == "active_edges") return copyOutI32(st.activeEdges, out, cap);
   if (n == "index_mapping") return copyOutI32(st.ivMap, out, cap);
+  if (n == "linear_solver_iterations_total") return copyOutI32({(int32_t)std::min<int64_t>(s->totalPcgIterations, INT32_MAX)}, out, cap);   // all solves since g2ocu_reset_counters
+  if (n == "linear_solver_iterations") return copyOutI32({(int32_t)s->lastPcgIterations}, out, cap);   // G2OBatchStatistics::iterationsLinearSolver of the last solve (linear_solver_pcg.hpp:150-153)
   if (st.classOf.empty()) return fail(s, G2OCU_E_INVALID, "buildStructure has not been called");
   if (st.fullSystem) {   // what the reference's buildStructure holds for this graph: one Hpp over all vertices in id order
     if (n == "dims") return copyOutI32(st.refDims, out, cap);
@@ -1364,6 +1370,6 @@ int g2ocu_phase_time(g2ocu_solver* s, const char* phase, double* seconds, int64_
   if (calls) *calls = it == s->phases.end() ? 0 : it->second.calls;
   return G2OCU_OK;
 }
-int g2ocu_reset_counters(g2ocu_solver* s) { if (!s) return G2OCU_E_INVALID; s->phases.clear(); s->launches = 0; return G2OCU_OK; }
+int g2ocu_reset_counters(g2ocu_solver* s) { if (!s) return G2OCU_E_INVALID; s->phases.clear(); s->launches = 0; s->totalPcgIterations = 0; return G2OCU_OK; }
 
 }  // extern "C"

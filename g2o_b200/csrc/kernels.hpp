@@ -71,6 +71,10 @@ static const int kMmaTileRows = 8;                // row group of the tensor-pip
 bool schurMmaSupported(int P, int L);             // block shapes routed through the DMMA tile kernel
 struct KernelMarks;
 void launchSchurMma(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, cudaStream_t st, int64_t* launches, const KernelMarks* marks);
+// second generation of the tensor-pipe tile pass (kernels_schur_kpack.cu): K packed across landmarks, W formed on the fly (no W array);
+// G2OCU_SCHUR_KERNEL=mma selects the first generation (kernels_schur_mma.cu)
+void launchSchurKpack(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, cudaStream_t st, int64_t* launches, const KernelMarks* marks);
+bool schurKpackEnabled();
 static const int kTileMinTrack = 8;               // landmarks with at least this many observations go through the tile kernel
 void launchPairSlots(const SchurDev& d, cudaStream_t st, int64_t* launches);
 // optional per-kernel timing hooks: begin(ctx, name) / end(ctx) bracket one kernel (CUDA events on the launching stream in api.cu)

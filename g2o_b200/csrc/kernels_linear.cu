@@ -779,7 +779,8 @@ template <int P, int L> static void schurPL(const SchurDev& d, const SystemDev& 
     *launches += 1;
   };
   if (forked) { cudaEventRecord(side->fork, st); cudaStreamWaitEvent(side->stream, side->fork, 0); pairs(side->stream); cudaEventRecord(side->join, side->stream); }
-  if (mma) launchSchurMma(d, sys, hplLm, nBlocks, st, launches, marks);
+  if (mma && schurKpackEnabled()) launchSchurKpack(d, sys, hplLm, nBlocks, st, launches, marks);
+  else if (mma) launchSchurMma(d, sys, hplLm, nBlocks, st, launches, marks);
   else if (nBlocks > 0) { MarkScope ms(marks, "schur_coeff"); coeff_kernel<P, L><<<(nBlocks + 127) / 128, 128, 0, st>>>(d, sys.Hpl, hplLm, nBlocks); *launches += 1; }
   if (!forked) pairs(st);
   if (d.nTileChunks > 0 && !mma) {

@@ -301,7 +301,9 @@ class CudaBlockSolverImpl : public BlockSolverBase {
       g2ocu_phase_time(_h, "schur", &sec, &n, &c); gs->timeSchurComplement = sec;
       g2ocu_phase_time(_h, "linear_solver", &sec, &n, &c); gs->timeLinearSolver = sec;
       int32_t dims[4] = {0, 0, 0, 0}; g2ocu_get_i32(_h, "internal_dims", dims, 4);
-      gs->hessianPoseDimension = dims[2]; gs->hessianLandmarkDimension = dims[3]; gs->hessianDimension = dims[2] + dims[3];
+      // block_solver.hpp:323,411-413: without Schur everything sits in Hpp
+      gs->hessianPoseDimension = _doSchur ? dims[2] : dims[2] + dims[3]; gs->hessianLandmarkDimension = _doSchur ? dims[3] : 0; gs->hessianDimension = dims[2] + dims[3];
+      int32_t its = 0; g2ocu_get_i32(_h, "linear_solver_iterations", &its, 1); gs->iterationsLinearSolver = its;   // what LinearSolverPCG::solve records (linear_solver_pcg.hpp:150-153)
     }
     return solved != 0;
   }

@@ -220,6 +220,7 @@ int g2ocu_get_estimates(g2ocu_solver* s, double* host_packed);
  * int32: "hessian_index" "active_vertices" "active_edges" "index_mapping" "dims" "pose_block_indices"
  *        "landmark_block_indices" "hpp_colptr" "hpp_rowidx" "hpl_colptr" "hpl_rowidx" "hschur_colptr" "hschur_rowidx"
  *        "hschur_t_colptr" "hschur_t_rowidx" "edge_targets" "shard_landmark_range" "shard_edge_positions"
+ *        "linear_solver_iterations" (1 element: PCG iterations of the last g2ocu_solve, G2OBatchStatistics::iterationsLinearSolver)
  *        (graphs with poses and points of which none is marginalized - BlockSolverX with two block sizes: "dims",
  *        "pose_block_indices", "hpp_colptr", "hpp_rowidx", "edge_targets" describe the reference's single Hpp over all
  *        vertices in id order; "full_system_permutation" maps a scalar index of its x / b to the internal [poses | points]

@@ -156,6 +156,7 @@ def reference_core():
             getattr(L, f).argtypes = [ctypes.c_void_p]; getattr(L, f).restype = ctypes.c_double
         for f in ("refcore_dogleg_state", "refcore_hessian_index", "refcore_estimates"):
             getattr(L, f).argtypes = [ctypes.c_void_p, ctypes.c_void_p]; getattr(L, f).restype = None
+        L.refcore_optimize_budget.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_double]
         L.refcore_linearize.argtypes = [ctypes.c_void_p, ctypes.c_double]; L.refcore_linearize.restype = ctypes.c_int
         for f in ("refcore_structure_i32", "refcore_structure_f64"):
             getattr(L, f).argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64]; getattr(L, f).restype = ctypes.c_int64
@@ -187,9 +188,14 @@ class ReferenceG2o:
     def initialize_optimization(self, level: int = 0) -> bool:
         return bool(self._L.refcore_initialize_optimization(self._h, level))
 
-    def optimize(self, iterations: int):
+    def optimize(self, iterations: int, budget_seconds: float | None = None):
+        """``SparseOptimizer::optimize(iterations)``; with ``budget_seconds`` the reference's own forceStopFlag is raised after that time, so
+        that no further iteration starts (the returned count / stats then cover the iterations that ran)."""
         buf = np.zeros((max(iterations, 1), 13))
-        n = self._L.refcore_optimize(self._h, iterations, _dp(buf))
+        if budget_seconds is None:
+            n = self._L.refcore_optimize(self._h, iterations, _dp(buf))
+        else:
+            n = self._L.refcore_optimize_budget(self._h, iterations, _dp(buf), float(budget_seconds))
         keys = ("chi2", "levenbergIterations", "iterationsLinearSolver", "hessianPoseDimension", "hessianLandmarkDimension", "iteration", "timeIteration", "timeLinearSolution",
                 "timeResiduals", "timeQuadraticForm", "timeSchurComplement", "timeLinearSolver", "timeUpdate")
         return n, [dict(zip(keys, row)) for row in buf[:max(n, 0)]]

@@ -9,6 +9,9 @@
 #include <omp.h>
 #endif
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <cstdint>
 #include <cstring>
 #include <functional>
@@ -291,6 +294,24 @@ int refcore_optimize(void* hh, int iterations, double* stats) {
     s[4] = (double)bs[i].hessianLandmarkDimension; s[5] = bs[i].iteration; s[6] = bs[i].timeIteration; s[7] = bs[i].timeLinearSolution;
     s[8] = bs[i].timeResiduals; s[9] = bs[i].timeQuadraticForm; s[10] = bs[i].timeSchurComplement; s[11] = bs[i].timeLinearSolver; s[12] = bs[i].timeUpdate;
   }
+  return n;
+}
+// The same, bounded in time with the reference's own stop mechanism: SparseOptimizer::setForceStopFlag (sparse_optimizer.h:186-190) - a watcher
+// thread raises the flag after `seconds`, optimize() then starts no further iteration (sparse_optimizer.cpp:396).  Returns what optimize returned.
+int refcore_optimize_budget(void* hh, int iterations, double* stats, double seconds) {
+  Handle* h = (Handle*)hh;
+  bool stop = false; std::atomic<bool> done(false);
+  h->optimizer.setForceStopFlag(&stop);
+  std::thread watcher([&]() {
+    const auto t0 = std::chrono::steady_clock::now();
+    while (!done.load()) {
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > seconds) { stop = true; break; }
+      std::this_thread::sleep_for(std::chrono::milliseconds(50));
+    }
+  });
+  const int n = refcore_optimize(hh, iterations, stats);
+  done.store(true); watcher.join();
+  h->optimizer.setForceStopFlag(nullptr);
   return n;
 }
 double refcore_current_lambda(void* hh) { Handle* h = (Handle*)hh; return h->lm ? h->lm->currentLambda() : 0.0; }
