@@ -129,7 +129,7 @@ struct g2ocu_solver {
   DVec<double> fr, fd, fq, fs;                                       // full-system PCG vectors r, d, q, s (vectorSize each)
   DVec<double> hsd, hdl, aux;                                        // Dogleg: steepest-descent step, final step, auxiliary vector (vectorSize each)
   DVec<int32_t> mhRow, mhBegin, mhEnd, mhRowPtr, mhColIdx; bool mhReady = false;   // SpMV work items over the Hpp pattern (multiplyHessian in Schur mode)
-  DVec<int32_t> hppDiag, hplColPtr, hplRowIdx, sRowPtr, sColIdx, sDiag, hppToS, pairSlot, pairEdgeI, pairEdgeJ, aRowPtr, aColIdx, aDiag, spRow, spBegin, spEnd, hplLm, tEntLm, tEntBI, tEntBJ, tChunkI, tChunkJ, tChunkB, tChunkE;
+  DVec<int32_t> hppDiag, hplColPtr, hplRowIdx, sRowPtr, sColIdx, sDiag, hppToS, pairSlot, pairEdgeI, pairEdgeJ, aRowPtr, aColIdx, aDiag, spRow, spBegin, spEnd, hplLm, tEntLm, tEntBI, tEntBJ, tChunkI, tChunkJ, tChunkB, tChunkE, tChunkSlots;
   DVec<uint32_t> tEntMJ; DVec<uint8_t> tEntMI;
   DVec<int64_t> off64;
   std::vector<EdgeSetState*> sets;
@@ -419,6 +419,23 @@ int buildDevice(g2ocu_solver* s) {
       }
       CU(s->tEntLm.upload(eLm, stream)); CU(s->tEntBI.upload(eBI, stream)); CU(s->tEntBJ.upload(eBJ, stream)); CU(s->tEntMJ.upload(eMJ, stream)); CU(s->tEntMI.upload(eMI, stream));
       CU(s->tChunkI.upload(cI, stream)); CU(s->tChunkJ.upload(cJ, stream)); CU(s->tChunkB.upload(cB, stream)); CU(s->tChunkE.upload(cE, stream));
+      if (useMma) {   // Hschur slot of every block of every chunk's tile: the tile kernel's write-out needs no search
+        std::vector<int32_t> slots(cI.size() * (size_t)kMmaTileRows * kTileCols, -1);
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < (int64_t)cI.size(); ++c)
+          for (int w = 0; w < kMmaTileRows; ++w) {
+            const int ci = cI[c] * kMmaTileRows + w;
+            if (ci >= st.numPoses) continue;
+            const int32_t* rb = &st.sColIdx[st.sRowPtr[ci]]; const int32_t* re = &st.sColIdx[st.sRowPtr[ci + 1]];
+            for (int n = 0; n < kTileCols; ++n) {
+              const int cj = cJ[c] * kTileCols + n;
+              if (cj < ci || cj >= st.numPoses) continue;
+              const int32_t* it = std::lower_bound(rb, re, cj);
+              if (it != re && *it == cj) slots[((size_t)c * kMmaTileRows + w) * kTileCols + n] = (int32_t)(it - st.sColIdx.data());
+            }
+          }
+        CU(s->tChunkSlots.upload(slots, stream)); sd.chunkSlots = s->tChunkSlots.p;
+      }
       CU(cudaStreamSynchronize(stream));
       sd.nTileChunks = (int)cI.size();
       sd.chunkI = s->tChunkI.p; sd.chunkJ = s->tChunkJ.p; sd.chunkBegin = s->tChunkB.p; sd.chunkEnd = s->tChunkE.p;

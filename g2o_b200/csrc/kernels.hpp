@@ -64,6 +64,7 @@ struct SchurDev {
   // long tracks (>= kTileMinTrack observations): output-stationary tiles, see schur_tile_kernel
   int nTileChunks = 0;
   const int32_t* chunkI = nullptr; const int32_t* chunkJ = nullptr; const int32_t* chunkBegin = nullptr; const int32_t* chunkEnd = nullptr;
+  const int32_t* chunkSlots = nullptr;   // per chunk: Hschur block of (row camera w, column camera n) of the tile, 8 x 32 ints, -1 = none / lower triangle (tensor-pipe tiles only)
   const int32_t* entLm = nullptr; const int32_t* entBaseI = nullptr; const int32_t* entBaseJ = nullptr; const uint32_t* entMaskJ = nullptr; const uint8_t* entMaskI = nullptr;
 };
 static const int kTileRows = 4, kTileCols = 32;   // cameras per tile row group / column strip

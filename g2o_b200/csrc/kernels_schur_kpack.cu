@@ -42,7 +42,7 @@ constexpr int kKpZeroRow = kKpStages * kKpRows;   // rows 64..67: zeros, one per
 //   [64 + 2 (4 w + a) ..] queue of row camera w, DMMA lane group a: byte t = t-th operand row = a (mod 4) of an entry the camera is part of,
 //   [128 + w] the 4 queue lengths (one byte each), [136 + w] steps = longest of them, [144 + w] column groups touched by step t (nibble t),
 //   [152 + w] column cameras the row camera meets in this batch, [160] column cameras of the whole batch
-constexpr int kHdrQueue = 64, kHdrLens = 128, kHdrSteps = 136, kHdrGroups = 144, kHdrTouched = 152, kHdrTouchedAll = 160, kHdrGroups9 = 161, kHdrWords = 176;
+constexpr int kHdrQueue = 64, kHdrLens = 128, kHdrSteps = 136, kHdrGroups = 144, kHdrTouched = 152, kHdrTouchedAll = 160, kHdrWords = 176;
 
 template <int P> struct KpLayout {
   static constexpr int NS = 32 * P;                    // stacked scalar columns of the strip
@@ -121,7 +121,6 @@ template <int P> __global__ void __launch_bounds__(kKpThreads, 1) schur_kpack_ke
   uint64_t* sEmpty = sFull + kKpStages;
 
   const int chunk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tileI = d.chunkI[chunk], tileJ = d.chunkJ[chunk];
   const int eBegin = d.chunkBegin[chunk], eEnd = d.chunkEnd[chunk];
   {  // all operand rows start as zeros: rows 64..67 stay zero for good (operand of padded K slots), and a stage row no batch has written yet
      // may be multiplied by a zero of the other operand - it must not hold a NaN bit pattern
@@ -160,62 +159,56 @@ template <int P> __global__ void __launch_bounds__(kKpThreads, 1) schur_kpack_ke
       asm volatile("bar.sync 1, %0;" ::"n"(kKpProducerThreads) : "memory");
       loadDesc(e0 + kKpBatch);
       const int rows = 3 * nE;
-      if (tp < 32) {
-        // queues of the 8 row cameras x 4 lane groups (thread = (w, a)); a quad of threads shares a row camera
-        const int qw = tp >> 2, qa = tp & 3;
+      if (tp >= kKpProducerThreads - 32) {
+        // Queues of the 8 row cameras x 4 lane groups, by the last producer warp (lane = (w, a); a quad of lanes shares a row camera).
+        // Branch free: lane p < 10 holds the descriptor of entry p in registers, the others read it with shuffles.
+        const int ql = tp - (kKpProducerThreads - 32), qw = ql >> 2, qa = ql & 3;
+        const uint32_t eMi = ql < nE ? hdr[4 + 4 * ql] : 0u, eMj = ql < nE ? hdr[4 + 4 * ql + 1] : 0u, eG = ql < nE ? hdr[4 + 4 * ql + 2] : 0u;
         uint32_t qlo = 0, qhi = 0, len = 0, gseq = 0, tch = 0;
 #pragma unroll
         for (int t = 0; t < kKpRows / 4; ++t) {
-          const int k = 4 * t + qa;
-          if (k < rows) {
-            const int p = (k * 11) >> 5;
-            if ((hdr[4 + 4 * p] >> qw) & 1u) {
-              if (len < 4) qlo |= (uint32_t)k << (8 * len); else qhi |= (uint32_t)k << (8 * (len - 4));
-              gseq |= hdr[4 + 4 * p + 2] << (4 * len);
-              tch |= hdr[4 + 4 * p + 1];
-              ++len;
-            }
-          }
+          const int k = 4 * t + qa, pe = (k * 11) >> 5;          // rows past the batch belong to entries >= nE, whose masks read as 0
+          const uint32_t mi = __shfl_sync(0xffffffffu, eMi, pe & 31), mj = __shfl_sync(0xffffffffu, eMj, pe & 31), g = __shfl_sync(0xffffffffu, eG, pe & 31);
+          const uint32_t on = (mi >> qw) & 1u;
+          const uint32_t sh = 8u * (len & 3u), kv = on ? (uint32_t)k << sh : 0u;
+          qlo |= len < 4 ? kv : 0u; qhi |= len < 4 ? 0u : kv;
+          gseq |= on ? g << (4u * len) : 0u;
+          tch |= on ? mj : 0u;
+          len += on;
         }
-        uint32_t steps = len;
+        uint32_t steps = len, all = eMj;
 #pragma unroll
         for (int o = 1; o < 4; o <<= 1) {
           gseq |= __shfl_xor_sync(0xffffffffu, gseq, o); tch |= __shfl_xor_sync(0xffffffffu, tch, o);
           steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
         }
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) all |= __shfl_xor_sync(0xffffffffu, all, o);   // lanes 0..15 cover the 10 entries
         uint32_t lens = len << (8 * qa);
         lens |= __shfl_xor_sync(0xffffffffu, lens, 1); lens |= __shfl_xor_sync(0xffffffffu, lens, 2);
-        hdr[kHdrQueue + 2 * tp] = qlo; hdr[kHdrQueue + 2 * tp + 1] = qhi;
+        hdr[kHdrQueue + 2 * ql] = qlo; hdr[kHdrQueue + 2 * ql + 1] = qhi;
         if (qa == 0) { hdr[kHdrLens + qw] = lens; hdr[kHdrSteps + qw] = steps; hdr[kHdrGroups + qw] = gseq; hdr[kHdrTouched + qw] = tch; }
-      } else if (tp < 40) {
-        const int t = tp - 32;
-        uint32_t g = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const int k = 4 * t + q; if (k < rows) g |= hdr[4 + 4 * ((k * 11) >> 5) + 2]; }
-        hdr[kHdrGroups9 + t] = g;
-      } else if (tp == 40) {
-        uint32_t all = 0;
-        for (int p = 0; p < nE; ++p) all |= hdr[4 + 4 * p + 1];
-        hdr[kHdrTouchedAll] = all;
+        if (ql == 0) hdr[kHdrTouchedAll] = all;
       }
       const uint32_t Bd = smemBase + LY::offB + (uint32_t)stage * kKpRows * LY::BS * 8;
       const uint32_t Ad = smemBase + LY::offA + (uint32_t)stage * kKpRows * LY::AS * 8;
-      // One item = (row k = 3 p + c, camera n): the P contiguous doubles of coordinate c of one Hpl block, copied asynchronously (cp.async,
-      // 8 bytes each: the blocks are only 8-byte aligned); n < 32 are the column cameras (B rows), n >= 32 the 8 row cameras (A rows).
-      // An absent camera is the same copy with source size 0, which writes zeros.
-      for (int idx = tp; idx < rows * 40; idx += kKpProducerThreads) {
-        const int k = idx / 40, n = idx - k * 40;
-        const int p = (k * 11) >> 5, c = k - 3 * p;
-        const bool colSide = n < 32;
-        const int cam = colSide ? n : n - 32;
-        const uint32_t mask = colSide ? hdr[4 + 4 * p + 1] : hdr[4 + 4 * p];
-        const int first = (int)(colSide ? hdr[4 + 4 * p + 3] : hdr[4 + kKpBatch * 4 + 2 * p]);
-        const bool on = (mask >> cam) & 1u;
-        const double* src = Hpl + (on ? (size_t)(first + __popc(mask & ((1u << cam) - 1u))) * PLn + P * c : 0);
-        const uint32_t dst = colSide ? Bd + (uint32_t)(k * LY::BS + cam * P) * 8u : Ad + (uint32_t)(k * LY::AS + cam * P) * 8u;
-        const uint32_t sz = on ? 8u : 0u;
+      // Copies: a thread owns a scalar column of the stage (one of the 32 x P of the column cameras' B rows or of the 8 x P of the row
+      // cameras' A rows) and walks the rows, so that a warp writes 32 consecutive doubles of a row with each cp.async (8 bytes per lane: the
+      // Hpl blocks are only 8-byte aligned).  An absent camera is the same copy with source size 0, which writes zeros.
+      for (int col = tp; col < LY::NS + 8 * P; col += kKpProducerThreads) {
+        const bool colSide = col < LY::NS;
+        const int s2 = colSide ? col : col - LY::NS, cam = s2 / P, r = s2 - cam * P;
+        const uint32_t dstCol = (colSide ? Bd : Ad) + (uint32_t)s2 * 8u;
+        const uint32_t rowBytes = colSide ? LY::BS * 8 : LY::AS * 8;
+        for (int pe = 0; pe < nE; ++pe) {
+          const uint32_t mask = colSide ? hdr[4 + 4 * pe + 1] : hdr[4 + 4 * pe];
+          const int first = (int)(colSide ? hdr[4 + 4 * pe + 3] : hdr[4 + kKpBatch * 4 + 2 * pe]);
+          const bool on = (mask >> cam) & 1u;
+          const double* src = Hpl + (on ? (size_t)(first + __popc(mask & ((1u << cam) - 1u))) * PLn + r : 0);
+          const uint32_t dst = dstCol + (uint32_t)(3 * pe) * rowBytes, sz = on ? 8u : 0u;
 #pragma unroll
-        for (int r = 0; r < P; ++r) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + 8u * r), "l"(src + r), "r"(sz) : "memory");
+          for (int c = 0; c < 3; ++c) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + (uint32_t)c * rowBytes), "l"(src + P * c), "r"(sz) : "memory");
+        }
       }
       if (tp < nE * 9) {   // Dinv of the landmarks
         const int p = tp / 9, q = tp - 9 * p;
@@ -322,16 +315,9 @@ template <int P> __global__ void __launch_bounds__(kKpThreads, 1) schur_kpack_ke
   }
 
   // ------------------------------------------------------------ write-out ------------------------------------------------------------
-  auto findSlot = [&](int ci, int cj) -> int {
-    if (ci >= d.numPoses || cj >= d.numPoses || cj < ci) return -1;
-    int lo = d.sRowPtr[ci]; const int end = d.sRowPtr[ci + 1]; int hi = end;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (d.sColIdx[mid] < cj) lo = mid + 1; else hi = mid; }
-    return (lo < end && d.sColIdx[lo] == cj) ? lo : -1;
-  };
   touched = uniformOr(touched); touched9 = uniformOr(touched9);
-  const int rowCam0 = tileI * kMmaTileRows, colCam0 = tileJ * kTileCols;
   // lane n holds the Hschur slot of block (row camera w, column camera n); the table of all 8 row cameras serves the ninth-row tiles
-  const int mySlot = ((touched >> lane) & 1u) ? findSlot(rowCam0 + w, colCam0 + lane) : -1;
+  const int mySlot = ((touched >> lane) & 1u) ? d.chunkSlots[((size_t)chunk * kMmaTileRows + w) * kTileCols + lane] : -1;
   int* slotTab = reinterpret_cast<int*>(smemRaw + LY::offSlots);
   if (FR) { slotTab[32 * w + lane] = mySlot; asm volatile("bar.sync 2, %0;" ::"n"(kKpConsumers * 32) : "memory"); }
 #pragma unroll
