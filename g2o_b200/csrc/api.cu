@@ -129,7 +129,7 @@ struct g2ocu_solver {
   DVec<double> fr, fd, fq, fs;                                       // full-system PCG vectors r, d, q, s (vectorSize each)
   DVec<double> hsd, hdl, aux;                                        // Dogleg: steepest-descent step, final step, auxiliary vector (vectorSize each)
   DVec<int32_t> mhRow, mhBegin, mhEnd, mhRowPtr, mhColIdx; bool mhReady = false;   // SpMV work items over the Hpp pattern (multiplyHessian in Schur mode)
-  DVec<int32_t> hppDiag, hplColPtr, hplRowIdx, sRowPtr, sColIdx, sDiag, hppToS, pairSlot, pairEdgeI, pairEdgeJ, aRowPtr, aColIdx, aDiag, spRow, spBegin, spEnd, hplLm, tEntLm, tEntBI, tEntBJ, tChunkI, tChunkJ, tChunkB, tChunkE, tChunkSlots;
+  DVec<int32_t> hppDiag, hplColPtr, hplRowIdx, sRowPtr, sColIdx, sDiag, hppToS, pairSlot, pairEdgeI, pairEdgeJ, aRowPtr, aColIdx, aDiag, spRow, spBegin, spEnd, hplLm, tEntLm, tEntBI, tEntBJ, tChunkI, tChunkJ, tChunkB, tChunkE, tChunkSlots, pairSegB, pairSegS;
   DVec<uint32_t> tEntMJ; DVec<uint8_t> tEntMI;
   DVec<int64_t> off64;
   std::vector<EdgeSetState*> sets;
@@ -400,6 +400,29 @@ int buildDevice(g2ocu_solver* s) {
       std::stable_sort(shortLm.begin(), shortLm.end(), [&](int32_t a, int32_t b) { return st.hplRowIdx[st.hplColPtr[a]] < st.hplRowIdx[st.hplColPtr[b]]; });
       std::vector<int32_t> pI, pJ;
       for (int32_t l : shortLm) { const int cb = st.hplColPtr[l], ce = st.hplColPtr[l + 1]; for (int i = cb; i < ce; ++i) for (int j = i; j < ce; ++j) { pI.push_back(i); pJ.push_back(j); } }
+      {  // sort the pairs by target Hschur block (counting sort) and cut them into segments of one block each
+        const size_t np = pI.size();
+        std::vector<int32_t> slot(np);
+#pragma omp parallel for schedule(static)
+        for (int64_t k = 0; k < (int64_t)np; ++k) {
+          const int ci = st.hplRowIdx[pI[k]], cj = st.hplRowIdx[pJ[k]];
+          const int32_t* rb = &st.sColIdx[st.sRowPtr[ci]]; const int32_t* re = &st.sColIdx[st.sRowPtr[ci + 1]];
+          slot[k] = (int32_t)(std::lower_bound(rb, re, cj) - st.sColIdx.data());
+        }
+        std::vector<int64_t> cnt(st.sColIdx.size() + 1, 0);
+        for (size_t k = 0; k < np; ++k) cnt[slot[k] + 1]++;
+        for (size_t b2 = 0; b2 < st.sColIdx.size(); ++b2) cnt[b2 + 1] += cnt[b2];
+        std::vector<int32_t> sI(np), sJ(np), segB, segS;
+        { std::vector<int64_t> fill(cnt.begin(), cnt.end() - 1);
+          for (size_t k = 0; k < np; ++k) { const int64_t o = fill[slot[k]]++; sI[o] = pI[k]; sJ[o] = pJ[k]; } }
+        for (size_t b2 = 0; b2 < st.sColIdx.size(); ++b2)
+          for (int64_t o = cnt[b2]; o < cnt[b2 + 1]; o += kPairSegment) { segB.push_back((int32_t)o); segS.push_back((int32_t)b2); }
+        segB.push_back((int32_t)np);
+        pI.swap(sI); pJ.swap(sJ);
+        CU(s->pairSegB.upload(segB, stream)); CU(s->pairSegS.upload(segS, stream));
+        CU(cudaStreamSynchronize(stream));
+        sd.nPairSegs = (int)segS.size(); sd.pairSegBegin = s->pairSegB.p; sd.pairSegSlot = s->pairSegS.p;
+      }
       CU(s->pairEdgeI.upload(pI, stream)); CU(s->pairEdgeJ.upload(pJ, stream)); CU(s->pairSlot.alloc(std::max<size_t>(pI.size(), 1)));
       CU(cudaStreamSynchronize(stream));
       sd.nPairs = (int64_t)pI.size(); sd.pairEdgeI = s->pairEdgeI.p; sd.pairEdgeJ = s->pairEdgeJ.p; sd.pairSlot = s->pairSlot.p;

@@ -59,6 +59,8 @@ struct SchurDev {
   const int32_t* hppToS = nullptr; int nnzHpp = 0; int nnzS = 0;
   // short tracks: flat list of (Hpl block i, Hpl block j, Hschur block) per pair i <= j, atomics
   int64_t nPairs = 0; const int32_t* pairEdgeI = nullptr; const int32_t* pairEdgeJ = nullptr; int32_t* pairSlot = nullptr;
+  // the same pairs sorted by target Hschur block and cut into segments of <= kPairSegment pairs of one block: a warp sums a segment in registers, one RED per element
+  int nPairSegs = 0; const int32_t* pairSegBegin = nullptr; const int32_t* pairSegSlot = nullptr;
   double* S = nullptr; double* Dinv = nullptr; double* db = nullptr; double* bschur = nullptr;
   double* W = nullptr;          // Hpl Dinv, same block order as Hpl (tensor-pipe path only)
   // long tracks (>= kTileMinTrack observations): output-stationary tiles, see schur_tile_kernel
@@ -76,6 +78,7 @@ void launchSchurMma(const SchurDev& d, const SystemDev& sys, const int32_t* hplL
 // G2OCU_SCHUR_KERNEL=mma selects the first generation (kernels_schur_mma.cu)
 void launchSchurKpack(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, cudaStream_t st, int64_t* launches, const KernelMarks* marks);
 bool schurKpackEnabled();
+static const int kPairSegment = 16;               // pairs per segment of the short-track kernel
 static const int kTileMinTrack = 8;               // landmarks with at least this many observations go through the tile kernel
 void launchPairSlots(const SchurDev& d, cudaStream_t st, int64_t* launches);
 // optional per-kernel timing hooks: begin(ctx, name) / end(ctx) bracket one kernel (CUDA events on the launching stream in api.cu)

@@ -7,8 +7,10 @@
 //   maxdiag / scale    computeLambdaInit / computeScale reductions                                               (optimization_algorithm_levenberg.cpp:152-184)
 // λ is never written into the stored diagonals: every consumer adds it on the fly, so setLambda/restoreDiagonal
 // (block_solver.hpp:525-565) cost nothing and need no backup copies.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "kernels.hpp"
 
@@ -159,6 +161,45 @@ template <int P, int L> __global__ void __launch_bounds__(256) schur_pairs_kerne
       for (int a = 0; a < L; ++a) { const double w = __shfl_sync(0xffffffffu, bd, (r + P * a) & 31); if (el < PP) v += w * Bj[c + P * a]; }
       if (el < PP) atomicAdd(Sb + el, -v);
     }
+  }
+}
+
+// Short tracks, segmented: the pair list is sorted by target block on the host (the short tracks of a ring of cameras hit a narrow band
+// of Hschur: 5.8 M pairs fall on 30 k blocks on C3) and cut into segments of <= kPairSegment pairs of one block; a warp sums its
+// segment in registers and issues one RED per element per segment instead of per pair - the L2 reduction rate that bounded the kernel
+// above (470 M REDs) is out of the way, what remains is the read of the two Hpl blocks of every pair.
+template <int P, int L> __global__ void __launch_bounds__(256) schur_pairs_seg_kernel(SchurDev d, const double* __restrict__ Hpl, const int32_t* __restrict__ hplLm) {
+  constexpr int PP = P * P, PLn = P * L, LL = L * L;
+  constexpr int NR = (PP + 31) / 32;
+  const int lane = threadIdx.x & 31;
+  const int nWarps = gridDim.x * (blockDim.x >> 5);
+  for (int sgm = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); sgm < d.nPairSegs; sgm += nWarps) {
+    const int pb = d.pairSegBegin[sgm], pe = d.pairSegBegin[sgm + 1];
+    double acc[NR];
+#pragma unroll
+    for (int q = 0; q < NR; ++q) acc[q] = 0;
+    for (int p = pb; p < pe; ++p) {
+      const int eI = d.pairEdgeI[p], eJ = d.pairEdgeJ[p];
+      const int lm = hplLm[eI];
+      const double* Bi = Hpl + (size_t)eI * PLn; const double* Bj = Hpl + (size_t)eJ * PLn;
+      double bd = 0;                                   // lane t < P*L holds (B_i Dinv)[r, a] with r = t % P, a = t / P
+      if (lane < PLn) {
+        const int r = lane % P, a = lane / P;
+#pragma unroll
+        for (int a2 = 0; a2 < L; ++a2) bd += Bi[r + P * a2] * d.Dinv[(size_t)lm * LL + a2 + L * a];
+      }
+#pragma unroll
+      for (int q = 0; q < NR; ++q) {
+        const int el = lane + 32 * q; const int r = el % P, c = el / P;
+        double v = 0;
+#pragma unroll
+        for (int a = 0; a < L; ++a) { const double w = __shfl_sync(0xffffffffu, bd, (r + P * a) & 31); if (el < PP) v += w * Bj[c + P * a]; }
+        acc[q] += v;
+      }
+    }
+    double* Sb = d.S + (size_t)d.pairSegSlot[sgm] * PP;
+#pragma unroll
+    for (int q = 0; q < NR; ++q) { const int el = lane + 32 * q; if (el < PP) atomicAdd(Sb + el, -acc[q]); }
   }
 }
 
@@ -619,6 +660,103 @@ __global__ void __launch_bounds__(256) pcg_update2_commit_kernel(PcgDev p, unsig
     }
   }
 }
+// The three kernels above (dot_partial, pcg_update1, pcg_update2_commit) as ONE launch for systems of up to 65 536 unknowns: a thread-block
+// cluster of 8 CTAs x 1024 threads; the two global reductions of a CG iteration (d.q and r.s) go through distributed shared memory and two
+// cluster barriers instead of two kernel boundaries.  Every sum is formed in exactly the order of the three-kernel path - 256 consecutive
+// unknowns per partial (8 warp trees, then in warp order), partials summed the way sumPartialsAll<256> does - so that both paths give
+// bit-identical iterates and the iteration counts compared with the reference do not depend on the path taken.
+namespace cg = cooperative_groups;
+constexpr int kFusedCtas = 8, kFusedThreads = 1024, kFusedRoundsMax = 8;   // 8 x 4 groups of 256 threads per round
+template <int P> __global__ void __cluster_dims__(kFusedCtas, 1, 1) __launch_bounds__(kFusedThreads) pcg_tail_fused_kernel(PcgDev p, int dotDone) {
+  constexpr int PP = P * P;
+  __shared__ double sWarp[32];                       // one sum per warp of this CTA
+  __shared__ double sPart[2][256];                   // all partials of the cluster: [0] d.q, [1] r.s (every CTA holds a full copy)
+  __shared__ double sFinal[8];
+  if (p.scal[6] != 0.0) return;                      // converged: the same value in every CTA, nobody reaches a cluster barrier
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cta = (int)cluster.block_rank(), tid = threadIdx.x, grp = tid >> 8, t256 = tid & 255, lane = tid & 31, wid = tid >> 5;
+  const int nPart = (p.n + 255) >> 8, rounds = (nPart + 31) >> 5;
+  // partial k of a quantity = sum over the unknowns [256 k, 256 k + 256): warp trees, then the 8 warps in order (blockSumL<256>)
+  auto reducePartials = [&](const double (&acc)[kFusedRoundsMax], int which) {
+#pragma unroll
+    for (int ro = 0; ro < kFusedRoundsMax; ++ro) {
+      if (ro < rounds) {                               // uniform over the cluster
+        const double v = warpSumL(acc[ro]);
+        __syncthreads();
+        if (lane == 0) sWarp[wid] = v;
+        __syncthreads();
+        const int vb = cta * 4 + grp + 32 * ro;
+        if (t256 == 0 && vb < nPart) {
+          double r = 0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) r += sWarp[8 * grp + k];
+          for (int c = 0; c < kFusedCtas; ++c) cluster.map_shared_rank(&sPart[which][0], c)[vb] = r;
+        }
+      }
+    }
+    cluster.sync();
+  };
+  // sum of partial[0 .. n) the way sumPartialsAll<256> forms it
+  auto sumPartials = [&](const double* part, int n) -> double {
+    double v = 0;
+    if (tid < 256) { for (int k = tid; k < n; k += 256) v += part[k]; v = warpSumL(v); }
+    __syncthreads();
+    if (tid < 256 && lane == 0) sFinal[wid] = v;
+    __syncthreads();
+    double r = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += sFinal[k];
+    __syncthreads();
+    return r;
+  };
+  double acc[kFusedRoundsMax];
+  double dq;
+  if (!dotDone) {
+#pragma unroll
+    for (int ro = 0; ro < kFusedRoundsMax; ++ro) {
+      acc[ro] = 0;
+      const int t = (cta * 4 + grp + 32 * ro) * 256 + t256;
+      if (ro < rounds && t < p.n) acc[ro] = 0.0 + p.d[t] * p.q[t];
+    }
+    reducePartials(acc, 0);
+    dq = sumPartials(sPart[0], nPart);
+  } else {
+    dq = sumPartials(p.partialDq, p.nPartialDq);     // formed by the peer-memory exchange kernel
+  }
+  const double dn = p.scal[0], alpha = dn / dq;
+  double sv[kFusedRoundsMax];
+#pragma unroll
+  for (int ro = 0; ro < kFusedRoundsMax; ++ro) {
+    acc[ro] = 0; sv[ro] = 0;
+    const int t = (cta * 4 + grp + 32 * ro) * 256 + t256;
+    if (ro < rounds && t < p.n) {
+      const int i = t / P, r = t - i * P;
+      const double* M = p.Minv + (size_t)i * PP + r;
+      double v = 0, mine = 0;
+#pragma unroll
+      for (int c = 0; c < P; ++c) {
+        const size_t o = (size_t)i * P + c;
+        const double rc = p.r[o] - alpha * p.q[o];
+        v += M[P * c] * rc;
+        if (c == r) mine = rc;
+      }
+      p.x[t] += alpha * p.d[t];
+      sv[ro] = v; acc[ro] = mine * v;
+    }
+  }
+  reducePartials(acc, 1);                            // also orders every read of r / q above before the writes below, cluster wide
+  const double dnNew = sumPartials(sPart[1], nPart);
+  const double beta = dnNew / dn;
+#pragma unroll
+  for (int ro = 0; ro < kFusedRoundsMax; ++ro) {
+    const int t = (cta * 4 + grp + 32 * ro) * 256 + t256;
+    if (ro < rounds && t < p.n) { p.r[t] -= alpha * p.q[t]; p.d[t] = sv[ro] + beta * p.d[t]; p.q[t] = 0.0; }
+  }
+  if (cta == 0 && tid == 0) {
+    p.scal[2] = dnNew; p.scal[0] = dnNew; p.scal[7] += 1.0;
+    if (dnNew <= p.scal[5]) p.scal[6] = 1.0;
+  }
+}
 // computeLambdaInit: max |H_vv(j,j)| over pose and landmark diagonal blocks (levenberg.cpp:152-175)
 // poseDiag (optional): the pose diagonals already summed over all ranks; landmarks: the owned range only
 __global__ void extract_pose_diag_kernel(SystemDev sys, double* out) {
@@ -775,7 +913,8 @@ template <int P, int L> static void schurPL(const SchurDev& d, const SystemDev& 
     if (d.nPairs <= 0) return;
     const int64_t warpsNeeded = d.nPairs; const int nb = (int)((warpsNeeded + 7) / 8 < 148 * 8 * 4 ? (warpsNeeded + 7) / 8 : 148 * 8 * 4);
     MarkScope ms(forked ? nullptr : marks, "schur_pairs");
-    schur_pairs_kernel<P, L><<<nb, 256, 0, ps>>>(d, sys.Hpl, hplLm);
+    if (d.nPairSegs > 0) { const int nbs = (d.nPairSegs + 7) / 8 < 148 * 8 * 4 ? (d.nPairSegs + 7) / 8 : 148 * 8 * 4; schur_pairs_seg_kernel<P, L><<<nbs, 256, 0, ps>>>(d, sys.Hpl, hplLm); }
+    else schur_pairs_kernel<P, L><<<nb, 256, 0, ps>>>(d, sys.Hpl, hplLm);
     *launches += 1;
   };
   if (forked) { cudaEventRecord(side->fork, st); cudaStreamWaitEvent(side->stream, side->fork, 0); pairs(side->stream); cudaEventRecord(side->join, side->stream); }
@@ -837,7 +976,18 @@ void launchPcgInit(const PcgDev& p, const double* b, double tolerance, double re
 }
 
 bool pcgSingleCtaTail(const PcgDev&) { return true; }   // the tail leaves q zeroed for the next product
+static bool pcgFusedTailEnabled() {
+  static const bool on = [] { const char* e = getenv("G2OCU_PCG_TAIL"); return !(e && (e[0] == 's' || e[0] == 'S')); }();   // G2OCU_PCG_TAIL=split: the three-kernel path
+  return on;
+}
 void launchPcgTail(const PcgDev& p, cudaStream_t st, int64_t* launches, bool dotDone) {
+  if (pcgFusedTailEnabled() && p.n <= 256 * 32 * kFusedRoundsMax) {
+#define CALL(PV) pcg_tail_fused_kernel<PV><<<kFusedCtas, kFusedThreads, 0, st>>>(p, dotDone ? 1 : 0);
+    FOR_P(p.P, CALL)
+#undef CALL
+    *launches += 1;
+    return;
+  }
   if (!dotDone) dot_partial_kernel<<<p.nPartialDq, 256, 0, st>>>(p.scal, p.d, p.q, p.n, p.partialDq);
 #define CALL(PV) pcg_update1_kernel<PV><<<p.nPartial, 256, 0, st>>>(p, p.partialDq, p.nPartialDq);
   FOR_P(p.P, CALL)

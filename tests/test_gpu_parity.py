@@ -145,6 +145,30 @@ def test_force_stop_flag_ends_the_optimisation():
     n, st = s.optimize(1); assert n == 1
 
 
+def test_fused_pcg_tail_matches_the_three_kernel_path():
+    """The CG recurrences of one iteration run as ONE cluster kernel (distributed shared memory for the two reductions) for systems of up to
+    65 536 unknowns; G2OCU_PCG_TAIL=split selects the three-kernel path.  Every sum of the tail is formed in the same order on both; the
+    products before it add with atomics, so two runs agree to rounding, not to the bit: same LM trials, same PCG iteration counts, chi2 to 1e-9."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import json, numpy as np\n"
+            "from g2o_b200 import workloads as W\n"
+            "from g2o_b200.binding import CudaSolver\n"
+            "out = []\n"
+            "for g, name in [(W.bal_synthetic(n_cameras=60, n_points=6000, n_obs=30000, seed=5, k_max=40, min_window=4), 'lm_fix9_3_cuda'), (W.sphere(nodes_per_level=16, laps=8), 'lm_var_cuda'), (W.ba_demo(), 'lm_fix6_3_cuda')]:\n"
+            "    s = CudaSolver(g, name, device=0); s.initialize_optimization(); n, st = s.optimize(4)\n"
+            "    out.append([n, [x['chi2'] for x in st], [x['iterations_linear_solver'] for x in st], [x['levenberg_iterations'] for x in st]])\n"
+            "print(json.dumps(out))\n")
+    outs = []
+    for mode in ("fused", "split"):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=300, env=dict(os.environ, G2OCU_PCG_TAIL=mode))
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    for a, b in zip(*outs):
+        assert a[0] == b[0] and a[2] == b[2] and a[3] == b[3], (a, b)
+        assert all(abs(x - y) <= 1e-9 * abs(y) for x, y in zip(a[1], b[1])), (a[1], b[1])
+
+
 def test_gauss_newton_sphere():
     g = W.sphere(nodes_per_level=12, laps=6)
     s = CudaSolver(g, "gn_var_cuda", device=0); s.initialize_optimization()
