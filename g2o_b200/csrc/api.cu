@@ -440,6 +440,14 @@ int buildDevice(g2ocu_solver* s) {
         for (size_t c0 = i; c0 < j; c0 += kTileChunk) { cI.push_back((int32_t)(entries[i].key >> 32)); cJ.push_back((int32_t)(entries[i].key & 0xffffffff)); cB.push_back((int32_t)c0); cE.push_back((int32_t)std::min(j, c0 + kTileChunk)); }
         i = j;
       }
+      if (useMma) {   // largest chunks first: one CTA per chunk, dispatched in index order - the small ones fill the gaps at the end of the launch
+        std::vector<int32_t> order(cI.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = (int32_t)i;
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return cE[a] - cB[a] > cE[b] - cB[b]; });
+        std::vector<int32_t> nI(cI.size()), nJ(cI.size()), nB(cI.size()), nE2(cI.size());
+        for (size_t i = 0; i < order.size(); ++i) { nI[i] = cI[order[i]]; nJ[i] = cJ[order[i]]; nB[i] = cB[order[i]]; nE2[i] = cE[order[i]]; }
+        cI.swap(nI); cJ.swap(nJ); cB.swap(nB); cE.swap(nE2);
+      }
       CU(s->tEntLm.upload(eLm, stream)); CU(s->tEntBI.upload(eBI, stream)); CU(s->tEntBJ.upload(eBJ, stream)); CU(s->tEntMJ.upload(eMJ, stream)); CU(s->tEntMI.upload(eMI, stream));
       CU(s->tChunkI.upload(cI, stream)); CU(s->tChunkJ.upload(cJ, stream)); CU(s->tChunkB.upload(cB, stream)); CU(s->tChunkE.upload(cE, stream));
       if (useMma) {   // Hschur slot of every block of every chunk's tile: the tile kernel's write-out needs no search
