@@ -322,6 +322,9 @@ def run_ours(args):
         host_in, host_out = pin_in.numpy(), pin_out.numpy()      # two pinned host buffers used in turn: a step's output is the next step's input
         stats = []
         for i in range(args.warmup):
+            if flush is not None:
+                with torch.cuda.stream(stream):
+                    flush.zero_()
             if e2e:
                 s.set_estimates(host_in)
             stats.append(s.solver_iteration(i))
@@ -414,7 +417,8 @@ def run_ours(args):
                          "frac_of_fp64_peak": fl / (sec / calls) / 1e12 / tpeak}
     mma = P in (6, 9) and L == 3
     kernels = {"pcg_spmv": f"spmv_tma_kernel<{P}>", "build": "build_pl_kernel + pose_accum_kernel" if ne_pl else "build_pp_kernel", "schur_coeff": f"schur_coeff_kernel<{P},{L}>",
-               "schur_tiles": f"schur_mma_kernel<{P},{L}>" if mma else f"schur_tile_kernel<{P},{L}>", "schur_pairs": f"schur_pairs_kernel<{P},{L}>"}
+               "schur_tiles": (f"schur_mma_kernel<{P},{L}>" if os.environ.get("G2OCU_SCHUR_KERNEL", "").lower().startswith("m") else f"schur_kpack_kernel<{P}>") if mma else f"schur_tile_kernel<{P},{L}>",
+               "schur_pairs": f"schur_pairs_seg_kernel<{P},{L}>"}
     traffic = {}
     tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if os.path.exists(tp):
