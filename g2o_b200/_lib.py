@@ -38,7 +38,7 @@ ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, c
 
 # every symbol include/g2ocu.h declares
 EXPORTS = ["g2ocu_default_config", "g2ocu_version", "g2ocu_last_error", "g2ocu_create", "g2ocu_destroy", "g2ocu_set_graph",
-           "g2ocu_set_property", "g2ocu_set_force_stop_flag", "g2ocu_set_shard", "g2ocu_nccl_unique_id", "g2ocu_set_shard_nccl", "g2ocu_p2p_export", "g2ocu_p2p_import", "g2ocu_initialize_optimization", "g2ocu_init", "g2ocu_build_structure",
+           "g2ocu_set_property", "g2ocu_set_force_stop_flag", "g2ocu_set_shard", "g2ocu_nccl_unique_id", "g2ocu_set_shard_nccl", "g2ocu_p2p_export", "g2ocu_p2p_import", "g2ocu_p2p_export_schur", "g2ocu_p2p_import_schur", "g2ocu_initialize_optimization", "g2ocu_init", "g2ocu_build_structure",
            "g2ocu_compute_active_errors", "g2ocu_active_robust_chi2", "g2ocu_active_chi2", "g2ocu_build_system",
            "g2ocu_set_lambda", "g2ocu_restore_diagonal", "g2ocu_solve", "g2ocu_update", "g2ocu_push", "g2ocu_pop",
            "g2ocu_discard_top", "g2ocu_compute_lambda_init", "g2ocu_compute_scale", "g2ocu_multiply_hessian",
@@ -66,6 +66,7 @@ def lib() -> ctypes.CDLL:
         "g2ocu_nccl_unique_id": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p]),
         "g2ocu_set_shard_nccl": (ctypes.c_int, [vp, i32, i32, ctypes.c_char_p, ctypes.c_char_p]),
         "g2ocu_p2p_export": (ctypes.c_int, [vp, ctypes.c_char_p]), "g2ocu_p2p_import": (ctypes.c_int, [vp, ctypes.c_char_p]),
+        "g2ocu_p2p_export_schur": (ctypes.c_int, [vp, ctypes.c_char_p]), "g2ocu_p2p_import_schur": (ctypes.c_int, [vp, ctypes.c_char_p]),
         "g2ocu_initialize_optimization": (ctypes.c_int, [vp, i32]), "g2ocu_init": (ctypes.c_int, [vp, i32]),
         "g2ocu_build_structure": (ctypes.c_int, [vp]), "g2ocu_compute_active_errors": (ctypes.c_int, [vp]),
         "g2ocu_active_robust_chi2": (ctypes.c_int, [vp, P(dbl)]), "g2ocu_active_chi2": (ctypes.c_int, [vp, P(dbl)]),

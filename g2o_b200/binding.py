@@ -122,6 +122,14 @@ class CudaSolver:
     def p2p_import(self, handles: bytes):
         self._ck(self._L.g2ocu_p2p_import(self._h, handles))
 
+    def p2p_export_schur(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        self._ck(self._L.g2ocu_p2p_export_schur(self._h, buf))
+        return buf.raw
+
+    def p2p_import_schur(self, handles: bytes):
+        self._ck(self._L.g2ocu_p2p_import_schur(self._h, handles))
+
     def set_shard_nccl(self, rank: int, world: int, nccl_library: str, unique_id: bytes):
         """Collectives issued by the library itself through NCCL (g2ocu_set_shard_nccl); every rank must call it."""
         assert len(unique_id) == 128

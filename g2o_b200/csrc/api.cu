@@ -120,6 +120,7 @@ struct g2ocu_solver {
   bool kernelTiming = false;      // property "kernelTiming": CUDA events around individual kernels, not only around phases
   int64_t slabBlocks = 0;         // blocks of the reduced system per rank (slab PCG), 0 when not sharded
   void* ncclComm = nullptr;       // set by g2ocu_set_shard_nccl: collectives go straight to NCCL on the solver's stream
+  P2pDev schurPeers; bool schurP2pReady = false; void* schurOpened[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // peers' partial-Hschur buffers (CUDA IPC)
   P2pDev p2p; bool p2pReady = false; double* p2pLocal = nullptr; void* p2pOpened[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // CUDA-IPC peer buffers for the slab-PCG exchange
   // device state
   DVec<double> poseEst, lmEst; std::vector<DVec<double>*> poseBackup, lmBackup; int stackDepth = 0;
@@ -147,6 +148,7 @@ struct g2ocu_solver {
     for (auto& pe : pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto e : eventPool) cudaEventDestroy(e);
     for (void* o : p2pOpened) if (o) cudaIpcCloseMemHandle(o);
+    for (void* o : schurOpened) if (o) cudaIpcCloseMemHandle(o);
     if (p2pLocal) cudaFree(p2pLocal);
     if (ncclComm && g_nccl.CommDestroy) g_nccl.CommDestroy(ncclComm);
     if (hostScal) cudaFreeHost(hostScal);
@@ -213,6 +215,9 @@ void dropP2p(g2ocu_solver* s) {
   s->p2pReady = false;
   for (void*& o : s->p2pOpened) if (o) { cudaIpcCloseMemHandle(o); o = nullptr; }
   s->p2p = P2pDev();
+  s->schurP2pReady = false;
+  for (void*& o : s->schurOpened) if (o) { cudaIpcCloseMemHandle(o); o = nullptr; }
+  s->schurPeers = P2pDev();
 }
 int collectiveDev(g2ocu_solver* s, double* buf, int64_t count, int op);
 int allreduceDev(g2ocu_solver* s, double* buf, int64_t count, int op) { return collectiveDev(s, buf, count, op); }
@@ -574,6 +579,7 @@ int solvePcg(g2ocu_solver* s, const double* rhs) {
     for (int k = 0; k < batch; ++k) {
       { KernelTimer pt(s, "pcg_spmv"); launchSpmv(pc, pc.d, pc.q, s->stream, &s->launches, issued + k > 0 && pcgSingleCtaTail(pc)); }
       const bool p2p = slab && s->p2pReady && pc.n <= s->p2p.cap;
+      if (p2p && pcgFusedTail(pc)) { KernelTimer pt(s, "pcg_vec"); launchP2pPushAndTail(pc, s->p2p, s->stream, &s->launches); continue; }   // push + one kernel: wait for the peers, sum, d.q, recurrences
       if (p2p) { KernelTimer pt(s, "pcg_exchange"); launchP2pExchangeDot(pc, s->p2p, s->stream, &s->launches); }   // peer-memory all-reduce of q fused with d.q
       else if (slab) { KernelTimer pt(s, "pcg_exchange"); int rc = allreduceDev(s, pc.q, pc.n, 0); if (rc) return rc; }
       { KernelTimer pt(s, "pcg_vec"); launchPcgTail(pc, s->stream, &s->launches, p2p); }
@@ -633,8 +639,17 @@ int solveSystem(g2ocu_solver* s, int* solved) {
     launchSchur(s->schur, s->sys, s->hplLm.p, st.hplColPtr[st.lmEnd] - st.hplColPtr[st.lmBegin], s->lambda, s->rank == 0 ? s->lambda : 0.0, s->stream, &s->launches, s->kernelTiming ? &marks : nullptr, &s->side);
     if (s->world > 1) {
       KernelTimer pt2(s, "schur_exchange");
-      int rc = collectiveDev(s, s->S.p, s->slabBlocks * st.P * st.P, G2OCU_OP_REDUCE_SCATTER_SUM); if (rc) return rc;   // rank r keeps the sum of its block range
-      rc = allreduceDev(s, s->bschur.p, (int64_t)s->bschur.n, 0); if (rc) return rc;
+      if (s->schurP2pReady && !dense) {
+        // Peer-memory reduction.  The all-reduce of b_schur doubles as the barrier in front of it (it completes on this rank only after
+        // every rank has enqueued it behind its own Schur kernels); the all-reduce of the block inverses at the start of solvePcg is the
+        // barrier behind it (no rank clears its buffer for the next trial before every rank has read it).
+        int rc = allreduceDev(s, s->bschur.p, (int64_t)s->bschur.n, 0); if (rc) return rc;
+        const size_t bs = (size_t)st.P * st.P, lo = (size_t)s->slabBlocks * s->rank * bs, hi = std::min((size_t)s->slabBlocks * (s->rank + 1), st.sColIdx.size()) * bs;
+        if (hi > lo) launchSlabReduce(s->schurPeers, lo, hi - lo, s->stream, &s->launches);
+      } else {
+        int rc = collectiveDev(s, s->S.p, s->slabBlocks * st.P * st.P, G2OCU_OP_REDUCE_SCATTER_SUM); if (rc) return rc;   // rank r keeps the sum of its block range
+        rc = allreduceDev(s, s->bschur.p, (int64_t)s->bschur.n, 0); if (rc) return rc;
+      }
     } }
   { PhaseTimer pt(s, "linear_solver");
     int rc = dense ? solveDense(s->bschur.p) : solvePcg(s, s->bschur.p); if (rc) return rc;
@@ -1082,6 +1097,32 @@ int g2ocu_p2p_import(g2ocu_solver* s, const unsigned char* handles) {
     s->p2pOpened[r] = ptr; s->p2p.peer[r] = (double*)ptr;
   }
   s->p2pReady = true;
+  return G2OCU_OK;
+}
+
+// The same for the reduction of the reduced camera system: export this rank's partial-Hschur buffer, import the peers'.
+int g2ocu_p2p_export_schur(g2ocu_solver* s, unsigned char handle[64]) {
+  if (!s || !handle) return G2OCU_E_INVALID;
+  if (!s->structureBuilt || !s->st.doSchur) return fail(s, G2OCU_E_INVALID, "g2ocu_p2p_export_schur needs the structure of a graph with marginalized landmarks");
+  if (s->world < 2 || s->world > 8) return fail(s, G2OCU_E_INVALID, "the peer-memory exchange supports 2..8 ranks");
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, s->S.p));
+  std::memcpy(handle, &h, 64);
+  return G2OCU_OK;
+}
+int g2ocu_p2p_import_schur(g2ocu_solver* s, const unsigned char* handles) {
+  if (!s || !handles) return G2OCU_E_INVALID;
+  if (!s->structureBuilt || !s->st.doSchur) return fail(s, G2OCU_E_INVALID, "g2ocu_p2p_import_schur needs the structure of a graph with marginalized landmarks");
+  s->schurP2pReady = false;
+  s->schurPeers = P2pDev(); s->schurPeers.rank = s->rank; s->schurPeers.world = s->world; s->schurPeers.cap = (int64_t)s->S.n;
+  for (int r = 0; r < s->world; ++r) {
+    if (r == s->rank) { s->schurPeers.peer[r] = s->S.p; continue; }
+    cudaIpcMemHandle_t h; std::memcpy(&h, handles + 64 * (size_t)r, 64);
+    void* ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    s->schurOpened[r] = ptr; s->schurPeers.peer[r] = (double*)ptr;
+  }
+  s->schurP2pReady = true;
   return G2OCU_OK;
 }
 

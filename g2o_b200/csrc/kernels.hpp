@@ -114,10 +114,14 @@ static inline size_t p2pBytes(int world, int64_t cap) { return sizeof(double) * 
 // q <- sum over ranks of the per-rank partial products (fixed rank order: bit-identical on every rank), partialDq <- partial sums of d.q;
 // replaces an NCCL all-reduce + dot_partial_kernel in the PCG iteration
 void launchP2pExchangeDot(const PcgDev& p, const P2pDev& x, cudaStream_t st, int64_t* launches);
+// x.peer[r] = rank r's partial Hschur buffer: mine[begin, begin + count) <- sum over the ranks, in rank order
+void launchSlabReduce(const P2pDev& x, size_t begin, size_t count, cudaStream_t st, int64_t* launches);
 void launchBlockInverse(const PcgDev& p, cudaStream_t st, int64_t* launches);
 void launchPcgInit(const PcgDev& p, const double* b, double tolerance, double residual, int absoluteTolerance, cudaStream_t st, int64_t* launches);   // x=0, r=b, d=M^-1 r, dn=r.d, d0
 void launchPcgTail(const PcgDev& p, cudaStream_t st, int64_t* launches, bool dotDone = false);   // after q = A d: dot, x/r/s update, d update, commit (no-ops once converged)
 void launchSpmv(const PcgDev& p, const double* src, double* dst, cudaStream_t st, int64_t* launches, bool dstIsZero = false);   // dst = (A + lambda I) src, symmetric upper
+bool pcgFusedTail(const PcgDev& p);        // launchPcgTail runs the recurrences as one cluster kernel (n <= 65 536)
+void launchP2pPushAndTail(const PcgDev& p, const P2pDev& x, cudaStream_t st, int64_t* launches);   // slab PCG: peer-memory exchange fused into that kernel
 bool pcgSingleCtaTail(const PcgDev& p);   // launchPcgTail zeroes q itself (small systems): the next launchSpmv may skip its memset
 
 void launchExtractPoseDiag(const SystemDev& sys, double* out, cudaStream_t st, int64_t* launches);

@@ -580,6 +580,37 @@ __global__ void __launch_bounds__(256) p2p_sum_dot_kernel(PcgDev p, P2pDev x) {
     if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *ticket = 0u; fl[x.world] = k; }   // every CTA has read seq: advance it
   }
 }
+// Reduction of the reduced camera system over NVLink peer memory: every rank holds its partial Hschur (all blocks) in a buffer its peers
+// have mapped; rank r sums the slab it solves with - blocks [begin, begin + count) - over all ranks in rank order by reading the peers'
+// partial sums directly (16-byte loads through the peer mappings).  Replaces ncclReduceScatter of the whole 0.76 GB buffer.
+__global__ void __launch_bounds__(256) slab_reduce_kernel(P2pDev x, size_t begin, size_t count) {
+  // only [begin, begin + count) of this rank's buffer is written: the neighbours read everything else of it
+  const size_t head = begin & 1, body = (count - head) >> 1, tail = (count - head) & 1;
+  double* base = x.peer[x.rank];
+  double2* mine = reinterpret_cast<double2*>(base + begin + head);
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < body; i += (size_t)gridDim.x * 256) {
+    double2 v = make_double2(0.0, 0.0);
+    for (int r = 0; r < x.world; ++r) {
+      const double2 u = r == x.rank ? mine[i] : __ldcv(reinterpret_cast<const double2*>(x.peer[r] + begin + head) + i);
+      v.x += u.x; v.y += u.y;
+    }
+    mine[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 2) {
+    const bool doIt = threadIdx.x == 0 ? head != 0 : tail != 0;
+    const size_t i = threadIdx.x == 0 ? begin : begin + count - 1;
+    if (doIt) {
+      double v = 0.0;
+      for (int r = 0; r < x.world; ++r) v += r == x.rank ? base[i] : __ldcv(x.peer[r] + i);
+      base[i] = v;
+    }
+  }
+}
+void launchSlabReduce(const P2pDev& x, size_t begin, size_t count, cudaStream_t st, int64_t* launches) {
+  if (count == 0) return;
+  slab_reduce_kernel<<<148 * 8, 256, 0, st>>>(x, begin, count);
+  *launches += 1;
+}
 void launchP2pExchangeDot(const PcgDev& p, const P2pDev& x, cudaStream_t st, int64_t* launches) {
   p2p_push_kernel<<<p.nPartialDq, 256, 0, st>>>(p, x);
   p2p_sum_dot_kernel<<<p.nPartialDq, 256, 0, st>>>(p, x);
@@ -667,7 +698,7 @@ __global__ void __launch_bounds__(256) pcg_update2_commit_kernel(PcgDev p, unsig
 // bit-identical iterates and the iteration counts compared with the reference do not depend on the path taken.
 namespace cg = cooperative_groups;
 constexpr int kFusedCtas = 8, kFusedThreads = 1024, kFusedRoundsMax = 8;   // 8 x 4 groups of 256 threads per round
-template <int P> __global__ void __cluster_dims__(kFusedCtas, 1, 1) __launch_bounds__(kFusedThreads) pcg_tail_fused_kernel(PcgDev p, int dotDone) {
+template <int P> __global__ void __cluster_dims__(kFusedCtas, 1, 1) __launch_bounds__(kFusedThreads) pcg_tail_fused_kernel(PcgDev p, int dotDone, P2pDev x) {
   constexpr int PP = P * P;
   __shared__ double sWarp[32];                       // one sum per warp of this CTA
   __shared__ double sPart[2][256];                   // all partials of the cluster: [0] d.q, [1] r.s (every CTA holds a full copy)
@@ -711,7 +742,30 @@ template <int P> __global__ void __cluster_dims__(kFusedCtas, 1, 1) __launch_bou
   };
   double acc[kFusedRoundsMax];
   double dq;
-  if (!dotDone) {
+  if (dotDone == 2) {
+    // slab PCG over NVLink peer memory: wait until every rank has published its partial product of this exchange (p2p_push_kernel), sum the
+    // slots in rank order (bit-identical on all ranks) into q and form d.q in the same pass - what p2p_sum_dot_kernel does as a launch of its own
+    double* mine = x.peer[x.rank];
+    uint64_t* fl = p2pFlags(mine, x.world, x.cap);
+    const uint64_t k = fl[x.world] + 1;
+    if (tid < x.world) { while (ldAcquireSys(fl + tid) < k) { } }
+    __syncthreads();
+    const double* slots = mine + (size_t)(k & 1) * x.world * x.cap;
+#pragma unroll
+    for (int ro = 0; ro < kFusedRoundsMax; ++ro) {
+      acc[ro] = 0;
+      const int t = (cta * 4 + grp + 32 * ro) * 256 + t256;
+      if (ro < rounds && t < p.n) {
+        double sum = 0;
+        for (int r = 0; r < x.world; ++r) sum += __ldcv(slots + (size_t)r * x.cap + t);
+        p.q[t] = sum;
+        acc[ro] = 0.0 + p.d[t] * sum;
+      }
+    }
+    reducePartials(acc, 0);                          // its cluster barrier also makes q visible to the whole cluster
+    if (cta == 0 && tid == 0) fl[x.world] = k;       // every CTA has read the sequence number and its slots: advance it
+    dq = sumPartials(sPart[0], nPart);
+  } else if (!dotDone) {
 #pragma unroll
     for (int ro = 0; ro < kFusedRoundsMax; ++ro) {
       acc[ro] = 0;
@@ -980,9 +1034,19 @@ static bool pcgFusedTailEnabled() {
   static const bool on = [] { const char* e = getenv("G2OCU_PCG_TAIL"); return !(e && (e[0] == 's' || e[0] == 'S')); }();   // G2OCU_PCG_TAIL=split: the three-kernel path
   return on;
 }
+bool pcgFusedTail(const PcgDev& p) { return pcgFusedTailEnabled() && p.n <= 256 * 32 * kFusedRoundsMax; }
+// slab PCG with the peer-memory exchange and the one-launch tail: push the partial product, the tail does the rest (waits for the peers,
+// sums, d.q, recurrences)
+void launchP2pPushAndTail(const PcgDev& p, const P2pDev& x, cudaStream_t st, int64_t* launches) {
+  p2p_push_kernel<<<p.nPartialDq, 256, 0, st>>>(p, x);
+#define CALL(PV) pcg_tail_fused_kernel<PV><<<kFusedCtas, kFusedThreads, 0, st>>>(p, 2, x);
+  FOR_P(p.P, CALL)
+#undef CALL
+  *launches += 2;
+}
 void launchPcgTail(const PcgDev& p, cudaStream_t st, int64_t* launches, bool dotDone) {
-  if (pcgFusedTailEnabled() && p.n <= 256 * 32 * kFusedRoundsMax) {
-#define CALL(PV) pcg_tail_fused_kernel<PV><<<kFusedCtas, kFusedThreads, 0, st>>>(p, dotDone ? 1 : 0);
+  if (pcgFusedTail(p)) {
+#define CALL(PV) pcg_tail_fused_kernel<PV><<<kFusedCtas, kFusedThreads, 0, st>>>(p, dotDone ? 1 : 0, P2pDev());
     FOR_P(p.P, CALL)
 #undef CALL
     *launches += 1;

@@ -84,11 +84,16 @@ def install_nccl(solver, rank: int, world: int, group=None):
     solver.set_shard_nccl(rank, world, path, box[0])
 
 
-def install_p2p(solver, rank: int, world: int, group=None):
+def install_p2p(solver, rank: int, world: int, group=None, schur: bool = True):
     """NVLink peer-memory exchange for the slab PCG (after ``build_structure``): CUDA-IPC handles travel over torch.distributed once."""
     import torch.distributed as dist
     mine = solver.p2p_export()
     handles = [None] * world
     dist.all_gather_object(handles, mine, group=group)
     solver.p2p_import(b"".join(handles))
+    if schur:   # the reduction of the reduced camera system through peer memory as well (PCG solver)
+        mine = solver.p2p_export_schur()
+        handles = [None] * world
+        dist.all_gather_object(handles, mine, group=group)
+        solver.p2p_import_schur(b"".join(handles))
     dist.barrier(group=group)

@@ -189,6 +189,11 @@ int g2ocu_set_shard_nccl(g2ocu_solver* s, int32_t rank, int32_t world, const cha
  * buffers.  Both are collective in the sense that every rank must do both before the next solve. */
 int g2ocu_p2p_export(g2ocu_solver* s, unsigned char handle[64]);
 int g2ocu_p2p_import(g2ocu_solver* s, const unsigned char* handles /* world x 64 bytes */);
+/* The same for the reduction of the reduced camera system (once per LM trial): every rank exports its partial-Hschur buffer, the peers map it,
+ * and each rank sums the slab it solves with by reading the peers' buffers over NVLink - instead of an NCCL reduce-scatter of the whole buffer.
+ * PCG solver only; without these calls (or with the dense solver) the reduce-scatter is used. */
+int g2ocu_p2p_export_schur(g2ocu_solver* s, unsigned char handle[64]);
+int g2ocu_p2p_import_schur(g2ocu_solver* s, const unsigned char* handles /* world x 64 bytes */);
 
 int g2ocu_initialize_optimization(g2ocu_solver* s, int32_t level);
 int g2ocu_init(g2ocu_solver* s, int32_t online);
