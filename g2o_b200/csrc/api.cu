@@ -587,6 +587,7 @@ int solvePcg(g2ocu_solver* s, const double* rhs) {
     issued += batch;
     CU(cudaMemcpyAsync(s->hostScal + 8, pc.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     int rc = syncStream(s); if (rc) return rc;
+    if (s->hostScal[8 + 6] == 3.0) return fail(s, G2OCU_E_COMM, "slab PCG: a peer rank did not publish its partial product within the wait budget (about 2 s) - the rank has probably failed");
     const bool converged = s->hostScal[8 + 6] != 0.0;
     if (converged || issued >= maxIter) done = true;
     if (!std::isfinite(s->hostScal[8 + 2])) done = true;   // NaN/Inf in the recurrence: stop issuing work (the reference would spin to maxIter)

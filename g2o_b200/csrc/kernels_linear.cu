@@ -532,6 +532,13 @@ __global__ void __launch_bounds__(256) dot_partial_kernel(const double* scal, co
 namespace {
 __device__ __forceinline__ uint64_t* p2pFlags(double* base, int world, int64_t cap) { return reinterpret_cast<uint64_t*>(base + 2 * (size_t)world * cap); }
 __device__ __forceinline__ uint64_t ldAcquireSys(const uint64_t* p) { uint64_t v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+// Bounded wait for a peer's flag: a rank that died (CUDA error, host exception) must not hang the others for ever.  After 2^32 cycles
+// (about 2 s) the wait gives up and returns false; the caller marks the solve as failed (scal[6] = 3), the host returns G2OCU_E_COMM.
+__device__ __forceinline__ bool waitFlagAtLeast(const uint64_t* p, uint64_t k) {
+  const long long t0 = clock64();
+  while (ldAcquireSys(p) < k) { if (clock64() - t0 > (1LL << 32)) return false; }
+  return true;
+}
 __device__ __forceinline__ void stReleaseSys(uint64_t* p, uint64_t v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 }  // namespace
 __global__ void __launch_bounds__(256) p2p_push_kernel(PcgDev p, P2pDev x) {
@@ -562,7 +569,7 @@ __global__ void __launch_bounds__(256) p2p_sum_dot_kernel(PcgDev p, P2pDev x) {
   double* mine = x.peer[x.rank];
   uint64_t* fl = p2pFlags(mine, x.world, x.cap);
   const uint64_t k = fl[x.world] + 1;
-  if (threadIdx.x < x.world) { while (ldAcquireSys(fl + threadIdx.x) < k) { } }
+  if (threadIdx.x < x.world && !waitFlagAtLeast(fl + threadIdx.x, k)) p.scal[6] = 3.0;   // peer lost: the solve fails (host: G2OCU_E_COMM)
   __syncthreads();
   const double* slots = mine + (size_t)(k & 1) * x.world * x.cap;
   double v = 0;
@@ -748,7 +755,7 @@ template <int P> __global__ void __cluster_dims__(kFusedCtas, 1, 1) __launch_bou
     double* mine = x.peer[x.rank];
     uint64_t* fl = p2pFlags(mine, x.world, x.cap);
     const uint64_t k = fl[x.world] + 1;
-    if (tid < x.world) { while (ldAcquireSys(fl + tid) < k) { } }
+    if (tid < x.world && !waitFlagAtLeast(fl + tid, k)) p.scal[6] = 3.0;   // peer lost: the solve fails (host: G2OCU_E_COMM); this launch still runs to its end
     __syncthreads();
     const double* slots = mine + (size_t)(k & 1) * x.world * x.cap;
 #pragma unroll
@@ -808,7 +815,7 @@ template <int P> __global__ void __cluster_dims__(kFusedCtas, 1, 1) __launch_bou
   }
   if (cta == 0 && tid == 0) {
     p.scal[2] = dnNew; p.scal[0] = dnNew; p.scal[7] += 1.0;
-    if (dnNew <= p.scal[5]) p.scal[6] = 1.0;
+    if (dnNew <= p.scal[5] && p.scal[6] == 0.0) p.scal[6] = 1.0;
   }
 }
 // computeLambdaInit: max |H_vv(j,j)| over pose and landmark diagonal blocks (levenberg.cpp:152-175)

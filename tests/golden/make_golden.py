@@ -29,7 +29,16 @@ CASES = {
     "slam2d_points_free": (lambda: W.slam2d(n_poses=800, n_landmarks=200, world_size=30.0, marginalize_landmarks=False), "lm", "pcg"),
     # Powell's dogleg with an exact linear solver
     "slam2d_dogleg": (lambda: W.slam2d(n_poses=800, n_landmarks=200, world_size=30.0), "dl", "dense"),
+    # round 2: VertexSE3Expmap / EdgeSE3Expmap as a pose graph and next to projection edges in one BA; a BAL graph under the Cauchy kernel
+    "sphere_expmap": (lambda: W.sphere_expmap(nodes_per_level=16, laps=8), "lm", "pcg"),
+    "ba_pose_constraints": (lambda: W.ba_demo_with_pose_constraints(), "lm", "pcg"),
+    "bal_cauchy": (lambda: _with_kernel(W.bal_synthetic(n_cameras=24, n_points=1200, n_obs=6000, seed=4, k_max=16, min_window=4, outlier_fraction=0.05), G.KERNEL_CAUCHY, 1.5), "lm", "pcg"),
 }
+
+
+def _with_kernel(g, kind, delta):
+    g.e_kernel = np.full(g.n_edges, kind, dtype=np.int32); g.e_kernel_delta = np.full(g.n_edges, float(delta)); return g
+
 
 
 def main():
