@@ -1462,4 +1462,76 @@ int g2ocu_phase_time(g2ocu_solver* s, const char* phase, double* seconds, int64_
 }
 int g2ocu_reset_counters(g2ocu_solver* s) { if (!s) return G2OCU_E_INVALID; s->phases.clear(); s->launches = 0; s->totalPcgIterations = 0; return G2OCU_OK; }
 
+// =================================================================================================
+// LinearSolver<MatrixType> level (core/linear_solver.h:42-105): the block-Jacobi PCG of solvers/pcg/linear_solver_pcg.hpp:80-156 as a
+// stand-alone solve of a symmetric block matrix handed over in the reference's own layout - for callers that keep g2o's BlockSolver
+// (its CPU buildSystem and Schur complement) and only swap the linear solver.  The matrix crosses the bus on every solve.
+struct g2ocu_linear_solver {
+  g2ocu_solver core;                                  // stream, PCG state (_residual carry-over), counters
+  std::vector<int32_t> colptr, rowidx;                // pattern of the last solve (the flattened view is rebuilt only when it changes)
+  std::vector<int32_t> csrOfCcs;                      // CCS position -> CSR position of a block
+  DVec<double> A, rhs; std::vector<double> staged;
+};
+
+int g2ocu_linear_create(const g2ocu_config* cfg, g2ocu_linear_solver** out) {
+  if (!out) return fail(nullptr, G2OCU_E_INVALID, "null output pointer");
+  g2ocu_linear_solver* L = new g2ocu_linear_solver;
+  if (cfg) L->core.cfg = *cfg; else g2ocu_default_config(&L->core.cfg);
+  L->core.cfg.linear_solver = G2OCU_LINEAR_PCG;
+  *out = L;
+  return G2OCU_OK;
+}
+void g2ocu_linear_destroy(g2ocu_linear_solver* L) { delete L; }
+const char* g2ocu_linear_last_error(const g2ocu_linear_solver* L) { return L ? L->core.err.c_str() : g_createError.c_str(); }
+int g2ocu_linear_init(g2ocu_linear_solver* L) { if (!L) return G2OCU_E_INVALID; L->core.pcgResidual = -1.0; return G2OCU_OK; }   // LinearSolverPCG::init, linear_solver_pcg.h:64-70
+int g2ocu_linear_set_property(g2ocu_linear_solver* L, const char* name, double value) { return L ? g2ocu_set_property(&L->core, name, value) : G2OCU_E_INVALID; }
+
+int g2ocu_linear_solve(g2ocu_linear_solver* L, int32_t nBlockCols, int32_t blockDim, const int32_t* colptr, const int32_t* rowidx, const double* values,
+                       const double* b, double* x, int32_t* solved, int32_t* iterations) {
+  if (!L || !colptr || !rowidx || !values || !b || !x || nBlockCols <= 0) return fail(L ? &L->core : nullptr, G2OCU_E_INVALID, "g2ocu_linear_solve: bad argument");
+  g2ocu_solver* s = &L->core;
+  if (blockDim != 3 && blockDim != 6 && blockDim != 9) return fail(s, G2OCU_E_UNSUPPORTED, "g2ocu_linear_solve: block dimension " + std::to_string(blockDim) + " (supported: 3, 6, 9; blocks of one size)");
+  int rc = ensureCuda(s); if (rc) return rc;
+  const int P = blockDim, PP = P * P; const int64_t nnz = colptr[nBlockCols];
+  const bool samePattern = (int)L->colptr.size() == nBlockCols + 1 && std::memcmp(L->colptr.data(), colptr, sizeof(int32_t) * (nBlockCols + 1)) == 0 &&
+                           (int64_t)L->rowidx.size() == nnz && std::memcmp(L->rowidx.data(), rowidx, sizeof(int32_t) * nnz) == 0 && s->pcg.P == P;
+  if (!samePattern) {
+    // upper blocks by column (ascending rows, the diagonal block last)  ->  CSR over the same blocks (row r: columns c >= r ascending, diagonal first)
+    L->colptr.assign(colptr, colptr + nBlockCols + 1); L->rowidx.assign(rowidx, rowidx + nnz);
+    std::vector<int32_t> rowPtr(nBlockCols + 1, 0), colIdx(nnz), diag(nBlockCols, -1);
+    for (int c = 0; c < nBlockCols; ++c) for (int k = colptr[c]; k < colptr[c + 1]; ++k) { if (rowidx[k] > c || rowidx[k] < 0) return fail(s, G2OCU_E_INVALID, "g2ocu_linear_solve: expected the upper blocks (row <= column)"); rowPtr[rowidx[k] + 1]++; }
+    for (int r = 0; r < nBlockCols; ++r) rowPtr[r + 1] += rowPtr[r];
+    L->csrOfCcs.resize(nnz);
+    { std::vector<int32_t> fill(rowPtr.begin(), rowPtr.end() - 1);
+      for (int c = 0; c < nBlockCols; ++c) for (int k = colptr[c]; k < colptr[c + 1]; ++k) { const int o = fill[rowidx[k]]++; colIdx[o] = c; L->csrOfCcs[k] = o; } }
+    for (int r = 0; r < nBlockCols; ++r) { if (rowPtr[r] == rowPtr[r + 1] || colIdx[rowPtr[r]] != r) return fail(s, G2OCU_E_INVALID, "g2ocu_linear_solve: block row " + std::to_string(r) + " has no diagonal block"); diag[r] = rowPtr[r]; }
+    CU(s->aRowPtr.upload(rowPtr, s->stream)); CU(s->aColIdx.upload(colIdx, s->stream)); CU(s->aDiag.upload(diag, s->stream));
+    std::vector<int32_t> ir, ib, ie; const int chunk = (32 / P) * 16;
+    for (int r = 0; r < nBlockCols; ++r) for (int k = rowPtr[r]; k < rowPtr[r + 1]; k += chunk) { ir.push_back(r); ib.push_back(k); ie.push_back(std::min(k + chunk, rowPtr[r + 1])); }
+    CU(s->spRow.upload(ir, s->stream)); CU(s->spBegin.upload(ib, s->stream)); CU(s->spEnd.upload(ie, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    PcgDev& pc = s->pcg; pc = PcgDev();
+    pc.n = nBlockCols * P; pc.nb = nBlockCols; pc.P = P; pc.nnz = (int)nnz; pc.nItems = (int)ir.size(); pc.ownLo = 0; pc.ownHi = (int)nnz;
+    CU(L->A.alloc((size_t)nnz * PP + 2)); CU(L->rhs.alloc(pc.n)); CU(s->x.alloc(pc.n));
+    CU(s->Minv.alloc((size_t)nBlockCols * PP)); CU(s->vr.alloc(pc.n)); CU(s->vd.alloc(pc.n)); CU(s->vq.alloc(pc.n)); CU(s->vs.alloc(pc.n)); CU(s->scal.alloc(16));
+    pc.nPartial = (pc.n + 255) / 256; pc.nPartialDq = std::min(296, (pc.n + 255) / 256);
+    CU(s->partial.alloc(pc.nPartial)); CU(s->partialDq.alloc(pc.nPartialDq)); CU(s->pcgTicket.alloc(4)); CU(s->pcgTicket.zero(s->stream)); CU(s->scal.zero(s->stream));
+    pc.rowPtr = s->aRowPtr.p; pc.colIdx = s->aColIdx.p; pc.diag = s->aDiag.p; pc.A = L->A.p; pc.Minv = s->Minv.p;
+    pc.r = s->vr.p; pc.d = s->vd.p; pc.q = s->vq.p; pc.s = s->vs.p; pc.x = s->x.p; pc.scal = s->scal.p; pc.partial = s->partial.p; pc.partialDq = s->partialDq.p;
+    pc.itemRow = s->spRow.p; pc.itemBegin = s->spBegin.p; pc.itemEnd = s->spEnd.p; pc.ticket = s->pcgTicket.p;
+  }
+  L->staged.resize((size_t)nnz * PP);
+#pragma omp parallel for schedule(static)
+  for (int64_t k = 0; k < nnz; ++k) std::memcpy(&L->staged[(size_t)L->csrOfCcs[k] * PP], values + (size_t)k * PP, sizeof(double) * PP);
+  CU(cudaMemcpyAsync(L->A.p, L->staged.data(), sizeof(double) * (size_t)nnz * PP, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(L->rhs.p, b, sizeof(double) * (size_t)s->pcg.n, cudaMemcpyHostToDevice, s->stream));
+  s->st.doSchur = false; s->lambda = 0.0; s->world = 1;
+  rc = solvePcg(s, L->rhs.p); if (rc) return rc;
+  CU(cudaMemcpyAsync(x, s->x.p, sizeof(double) * (size_t)s->pcg.n, cudaMemcpyDeviceToHost, s->stream));
+  rc = syncStream(s); if (rc) return rc;
+  if (solved) *solved = 1;                           // LinearSolverPCG::solve always reports success (linear_solver_pcg.hpp:155)
+  if (iterations) *iterations = s->lastPcgIterations;
+  return G2OCU_OK;
+}
+
 }  // extern "C"

@@ -10,7 +10,10 @@
 //   *_cuda_solver   the reference's own OptimizationAlgorithmLevenberg / GaussNewton / Dogleg driving CudaBlockSolver<P,L> : BlockSolverBase
 //                   (core/solver.h:44-155, core/block_solver.h:87-95): buildStructure / buildSystem / setLambda / solve / multiplyHessian on the
 //                   device, computeActiveErrors / update / push / pop stay the reference's host loops (estimates cross the bus per buildSystem).
-// Both pack SparseOptimizer::activeVertices() / activeEdges() into the flat g2ocu_graph (include/g2ocu.h) and check that the backend's
+//   *_cuda_linear   the reference's own algorithm AND its own BlockSolver<BlockSolverTraits<P,L>> (CPU buildSystem and Schur complement) over
+//                   LinearSolverCuda<MatrixType> : LinearSolver<MatrixType> (core/linear_solver.h:42-105): only LinearSolverPCG::solve runs on the
+//                   device (g2ocu_linear_solve); the reduced system crosses the bus on every solve.
+// The first two pack SparseOptimizer::activeVertices() / activeEdges() into the flat g2ocu_graph (include/g2ocu.h) and check that the backend's
 // hessianIndex of every vertex equals the one SparseOptimizer::buildIndexMapping assigned (sparse_optimizer.cpp:168-193).
 // Types are recognised by dynamic_cast; the BAL types, which the reference defines inside examples/bal/bal_example.cpp (no header),
 // by their class name + their BaseVertex / BaseEdge instantiation.  Anything else is rejected at init - there is no CPU fallback.
@@ -21,6 +24,7 @@
 #include "g2o/core/base_binary_edge.h"
 #include "g2o/core/base_vertex.h"
 #include "g2o/core/block_solver.h"
+#include "g2o/core/linear_solver.h"
 #include "g2o/core/optimization_algorithm.h"
 #include "g2o/core/optimization_algorithm_dogleg.h"
 #include "g2o/core/optimization_algorithm_factory.h"
@@ -329,6 +333,50 @@ template <int P, int L> class CudaBlockSolver : public CudaBlockSolverImpl {
 };
 
 // ------------------------------------------------------------------------------------------------------------------------------------
+// LinearSolver level: what LinearSolverPCG<MatrixType> is to the reference's BlockSolver (solvers/pcg/linear_solver_pcg.h), on the device.
+template <typename MatrixType> class LinearSolverCuda : public LinearSolver<MatrixType> {
+ public:
+  LinearSolverCuda() { g2ocu_config cfg; g2ocu_default_config(&cfg); g2ocu_linear_create(&cfg, &_h); }
+  ~LinearSolverCuda() override { g2ocu_linear_destroy(_h); }
+  bool init() override { return g2ocu_linear_init(_h) == G2OCU_OK; }      // LinearSolverPCG::init: the carried residual starts over
+  bool solve(const SparseBlockMatrix<MatrixType>& A, number_t* x, number_t* b) override {
+    // the upper blocks by column, exactly the walk of LinearSolverPCG::solve (linear_solver_pcg.hpp:86-110)
+    const int nCols = (int)A.blockCols().size();
+    _colptr.assign(1, 0); _rowidx.clear(); _values.clear();
+    int dim = -1;
+    for (int i = 0; i < nCols; ++i) {
+      for (const auto& kv : A.blockCols()[i]) {
+        if (kv.first > i) break;
+        const MatrixType& m = *kv.second;
+        if (dim < 0) dim = (int)m.rows();
+        if ((int)m.rows() != dim || (int)m.cols() != dim) { std::cerr << "solver_cuda: LinearSolverCuda needs blocks of one size" << std::endl; return false; }
+        _rowidx.push_back(kv.first);
+        for (int c = 0; c < dim; ++c) for (int r = 0; r < dim; ++r) _values.push_back(m(r, c));
+      }
+      _colptr.push_back((int32_t)_rowidx.size());
+    }
+    int32_t solved = 0, iterations = 0;
+    if (g2ocu_linear_solve(_h, nCols, dim, _colptr.data(), _rowidx.data(), _values.data(), b, x, &solved, &iterations) != G2OCU_OK) {
+      std::cerr << "solver_cuda: " << g2ocu_linear_last_error(_h) << std::endl;
+      return false;
+    }
+    if (G2OBatchStatistics* gs = G2OBatchStatistics::globalStats()) gs->iterationsLinearSolver = iterations;   // linear_solver_pcg.hpp:150-153
+    return solved != 0;
+  }
+  void setTolerance(number_t tolerance) { g2ocu_linear_set_property(_h, "pcgTolerance", tolerance); }
+  void setMaxIterations(int maxIter) { g2ocu_linear_set_property(_h, "pcgMaxIterations", maxIter); }
+  void setAbsoluteTolerance(bool absoluteTolerance) { g2ocu_linear_set_property(_h, "pcgAbsoluteTolerance", absoluteTolerance); }
+
+ private:
+  g2ocu_linear_solver* _h = nullptr;
+  std::vector<int32_t> _colptr, _rowidx; std::vector<double> _values;
+};
+template <int P, int L> std::unique_ptr<Solver> allocateLinearLevelSolver() {
+  typedef BlockSolverPL<P, L> BS;
+  return std::unique_ptr<Solver>(new BS(std::unique_ptr<typename BS::LinearSolverType>(new LinearSolverCuda<typename BS::PoseMatrixType>())));
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------------
 class CudaSolverCreator : public AbstractOptimizationAlgorithmCreator {
  public:
   explicit CudaSolverCreator(const OptimizationAlgorithmProperty& p) : AbstractOptimizationAlgorithmCreator(p) {}
@@ -337,6 +385,11 @@ class CudaSolverCreator : public AbstractOptimizationAlgorithmCreator {
     const int algorithm = n.substr(0, 2) == "lm" ? G2OCU_ALGORITHM_LM : n.substr(0, 2) == "dl" ? G2OCU_ALGORITHM_DOGLEG : G2OCU_ALGORITHM_GN;
     const int linear = n.find("_dense") != std::string::npos ? G2OCU_LINEAR_DENSE : G2OCU_LINEAR_PCG;
     const int P = property().poseDim, L = property().landmarkDim;
+    if (n.size() > 12 && n.compare(n.size() - 12, 12, "_cuda_linear") == 0) {   // g2o's own algorithm and BlockSolver, the CUDA linear solver
+      std::unique_ptr<Solver> bs = P == 3 ? allocateLinearLevelSolver<3, 2>() : P == 6 ? allocateLinearLevelSolver<6, 3>() : allocateLinearLevelSolver<9, 3>();
+      if (algorithm == G2OCU_ALGORITHM_LM) return new OptimizationAlgorithmLevenberg(std::move(bs));
+      return new OptimizationAlgorithmGaussNewton(std::move(bs));
+    }
     if (n.size() < 12 || n.compare(n.size() - 12, 12, "_cuda_solver") != 0) return new OptimizationAlgorithmCuda(algorithm, P, L, linear);
     // the reference's own algorithm classes over the CUDA block solver
     std::unique_ptr<BlockSolverBase> bs;
@@ -381,5 +434,11 @@ G2OCU_REGISTER(gn_fix6_3_cuda_solver, "Gauss-Newton (g2o's own) over the CUDA bl
 G2OCU_REGISTER(lm_fix6_3_cuda_solver, "Levenberg (g2o's own) over the CUDA block solver: Schur + PCG on the GPU", true, 6, 3);
 G2OCU_REGISTER(gn_fix9_3_cuda_solver, "Gauss-Newton (g2o's own) over the CUDA block solver: Schur + PCG on the GPU (BAL cameras)", true, 9, 3);
 G2OCU_REGISTER(lm_fix9_3_cuda_solver, "Levenberg (g2o's own) over the CUDA block solver: Schur + PCG on the GPU (BAL cameras)", true, 9, 3);
+// g2o's own algorithm and BlockSolver<BlockSolverTraits<P,L>> over LinearSolverCuda (block-Jacobi PCG on the device)
+G2OCU_REGISTER(gn_fix3_2_cuda_linear, "Gauss-Newton, g2o's BlockSolver_3_2 on the CPU, block-Jacobi PCG on the GPU", true, 3, 2);
+G2OCU_REGISTER(lm_fix3_2_cuda_linear, "Levenberg, g2o's BlockSolver_3_2 on the CPU, block-Jacobi PCG on the GPU", true, 3, 2);
+G2OCU_REGISTER(gn_fix6_3_cuda_linear, "Gauss-Newton, g2o's BlockSolver_6_3 on the CPU, block-Jacobi PCG on the GPU", true, 6, 3);
+G2OCU_REGISTER(lm_fix6_3_cuda_linear, "Levenberg, g2o's BlockSolver_6_3 on the CPU, block-Jacobi PCG on the GPU", true, 6, 3);
+G2OCU_REGISTER(lm_fix9_3_cuda_linear, "Levenberg, g2o's BlockSolver<9,3> on the CPU, block-Jacobi PCG on the GPU (BAL cameras)", true, 9, 3);
 
 }  // namespace g2o

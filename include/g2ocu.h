@@ -23,7 +23,7 @@
  *                                             optimization_algorithm_gauss_newton.cpp:50, _levenberg.cpp:58, _dogleg.cpp:56)
  *   SparseOptimizer::optimize                 sparse_optimizer.cpp:374    g2ocu_optimize
  *   BlockSolverBase::multiplyHessian          core/block_solver.h:87-95   g2ocu_multiply_hessian
- *   LinearSolver<M>::solve                    core/linear_solver.h:59     (inside g2ocu_solve; kind = g2ocu_config.linear_solver)
+ *   LinearSolver<M>::solve                    core/linear_solver.h:59     (inside g2ocu_solve; kind = g2ocu_config.linear_solver) / g2ocu_linear_solve (stand-alone)
  *
  * Conventions: all functions return 0 on success and a negative G2OCU_E_* code on failure; the message is
  * available from g2ocu_last_error().  No function aborts or throws across the boundary.  One handle = one
@@ -244,6 +244,21 @@ int64_t g2ocu_get_f64(g2ocu_solver* s, const char* name, double* out, int64_t ca
 int64_t g2ocu_launch_count(const g2ocu_solver* s);
 int g2ocu_phase_time(g2ocu_solver* s, const char* phase, double* seconds, int64_t* launches, int64_t* calls);
 int g2ocu_reset_counters(g2ocu_solver* s);
+
+/* ---- LinearSolver<MatrixType> level (core/linear_solver.h:42-105) -------------------------------------------------------------------
+ * For callers that keep g2o's own BlockSolver and only swap the linear solver: LinearSolverPCG::solve (solvers/pcg/linear_solver_pcg.hpp:80-156,
+ * block-Jacobi preconditioned CG incl. the _residual carried from solve to solve) on a symmetric block matrix given by its UPPER blocks
+ * in the reference's block-column layout (SparseBlockMatrix::blockCols(): per block column the blocks with row <= column, ascending rows,
+ * each block column-major, one block size for the whole matrix: 3, 6 or 9).  `b`, `x` are host vectors of n_block_cols * block_dim doubles.
+ * g2ocu_linear_init = LinearSolver::init (resets the carried residual); properties: "pcgTolerance", "pcgMaxIterations", "pcgAbsoluteTolerance". */
+typedef struct g2ocu_linear_solver g2ocu_linear_solver;
+int g2ocu_linear_create(const g2ocu_config* cfg, g2ocu_linear_solver** out);
+void g2ocu_linear_destroy(g2ocu_linear_solver* s);
+const char* g2ocu_linear_last_error(const g2ocu_linear_solver* s);
+int g2ocu_linear_init(g2ocu_linear_solver* s);
+int g2ocu_linear_set_property(g2ocu_linear_solver* s, const char* name, double value);
+int g2ocu_linear_solve(g2ocu_linear_solver* s, int32_t n_block_cols, int32_t block_dim, const int32_t* colptr, const int32_t* rowidx, const double* values,
+                       const double* b, double* x, int32_t* solved, int32_t* iterations);
 
 #ifdef __cplusplus
 }

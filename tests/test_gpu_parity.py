@@ -169,6 +169,57 @@ def test_fused_pcg_tail_matches_the_three_kernel_path():
         assert all(abs(x - y) <= 1e-9 * abs(y) for x, y in zip(a[1], b[1])), (a[1], b[1])
 
 
+@pytest.mark.parametrize("dim", [3, 6, 9])
+def test_linear_solver_level_entry_point(dim):
+    """g2ocu_linear_solve = LinearSolverPCG::solve (linear_solver_pcg.hpp:80-156) on a block matrix in the reference's block-column layout:
+    the iterates stop at the reference's rule (r.M^-1 r <= 1e-6 of its initial value), so the residual is small in that norm and the
+    solution agrees with a dense solve to the conditioning of the system; a second solve with the same pattern reuses the flattened view."""
+    import ctypes
+    from g2o_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(dim)
+    nb = 40
+    dense = np.zeros((nb * dim, nb * dim))
+    colptr, rowidx, vals = [0], [], []
+    for c in range(nb):
+        for r in range(c + 1):
+            if r == c or rng.random() < 0.15:
+                B = rng.normal(size=(dim, dim))
+                if r == c:
+                    B = B @ B.T + 3 * dim * np.eye(dim)
+                dense[r * dim:(r + 1) * dim, c * dim:(c + 1) * dim] = B
+                if r != c:
+                    dense[c * dim:(c + 1) * dim, r * dim:(r + 1) * dim] = B.T
+                rowidx.append(r); vals.append(B.ravel(order="F"))
+        colptr.append(len(rowidx))
+    dense += 2.0 * np.sum(np.abs(dense), axis=1).max() / 10 * np.eye(nb * dim)          # comfortably positive definite
+    k = 0
+    for c in range(nb):                                                               # the diagonal shift into the block list as well
+        for j in range(colptr[c], colptr[c + 1]):
+            if rowidx[j] == c:
+                vals[j] = dense[c * dim:(c + 1) * dim, c * dim:(c + 1) * dim].ravel(order="F")
+    colptr = np.asarray(colptr, dtype=np.int32); rowidx = np.asarray(rowidx, dtype=np.int32); vals = np.ascontiguousarray(np.concatenate(vals))
+    h = ctypes.c_void_p(); cfg = _lib.Config(); L.g2ocu_default_config(ctypes.byref(cfg)); cfg.device = 0
+    assert L.g2ocu_linear_create(ctypes.byref(cfg), ctypes.byref(h)) == 0
+    try:
+        assert L.g2ocu_linear_init(h) == 0
+        for trial in range(2):
+            b = rng.normal(size=nb * dim); x = np.zeros(nb * dim)
+            ok = ctypes.c_int32(); its = ctypes.c_int32()
+            rc = L.g2ocu_linear_solve(h, nb, dim, colptr.ctypes.data_as(ctypes.c_void_p), rowidx.ctypes.data_as(ctypes.c_void_p), vals.ctypes.data_as(ctypes.c_void_p),
+                                      b.ctypes.data_as(ctypes.c_void_p), x.ctypes.data_as(ctypes.c_void_p), ctypes.byref(ok), ctypes.byref(its))
+            assert rc == 0, L.g2ocu_linear_last_error(h)
+            assert ok.value == 1 and 0 < its.value < nb * dim
+            xd = np.linalg.solve(dense, b)
+            assert np.linalg.norm(x - xd) <= 1e-4 * np.linalg.norm(xd), (trial, its.value)
+            L.g2ocu_linear_init(h)
+        bad = rowidx.copy(); bad[0] = 5                                               # a block below the diagonal is refused
+        assert L.g2ocu_linear_solve(h, nb, dim, colptr.ctypes.data_as(ctypes.c_void_p), bad.ctypes.data_as(ctypes.c_void_p), vals.ctypes.data_as(ctypes.c_void_p),
+                                    b.ctypes.data_as(ctypes.c_void_p), x.ctypes.data_as(ctypes.c_void_p), None, None) < 0
+    finally:
+        L.g2ocu_linear_destroy(h)
+
+
 def test_gauss_newton_sphere():
     g = W.sphere(nodes_per_level=12, laps=6)
     s = CudaSolver(g, "gn_var_cuda", device=0); s.initialize_optimization()

@@ -288,6 +288,11 @@ PAIRING = {
     "sphere_var_solver": (lambda: W.sphere(nodes_per_level=10, laps=5), "var", "lm_var_cuda_solver", "lm"),
     "sphere_gn_var_solver": (lambda: W.sphere(nodes_per_level=10, laps=5), "var", "gn_var_cuda_solver", "gn"),
     "slam2d_dogleg_var_solver": (lambda: W.slam2d(n_poses=200, n_landmarks=60, world_size=16.0), "var", "dl_var_cuda_solver", "dl"),
+    # the reference's own algorithm AND BlockSolver over LinearSolverCuda<MatrixType> : LinearSolver<MatrixType> (LinearSolver-level drop-in)
+    "ba_demo_fix6_3_linear": (lambda: W.ba_demo(num_cameras=8, num_points=80), "6_3", "lm_fix6_3_cuda_linear", "lm"),
+    "slam2d_fix3_2_linear": (lambda: W.slam2d(n_poses=200, n_landmarks=60, world_size=16.0), "3_2", "lm_fix3_2_cuda_linear", "lm"),
+    "slam2d_gn_fix3_2_linear": (lambda: W.slam2d(n_poses=200, n_landmarks=60, world_size=16.0), "3_2", "gn_fix3_2_cuda_linear", "gn"),
+    "bal_small_fix9_3_linear": (lambda: W.bal_small(), "9_3", "lm_fix9_3_cuda_linear", "lm"),
 }
 
 
