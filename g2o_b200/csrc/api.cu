@@ -110,6 +110,9 @@ struct g2ocu_solver {
   // solver state
   double lambda = 0.0;            // damping currently "set" on the diagonals (0 after restoreDiagonal)
   double pcgResidual = -1.0;      // LinearSolverPCG::_residual, persists across solves until init()
+  // CUDA graph of kPcgGraphIters CG iterations (product + one-launch tail, + the peer-memory push when sharded): launched instead of the
+  // individual kernels between two convergence polls; re-captured when a kernel argument changes (matrix, lambda, transport)
+  cudaGraphExec_t pcgGraph = nullptr; double pcgGraphLambda = 0; bool pcgGraphP2p = false; const double* pcgGraphA = nullptr; int pcgGraphN = 0;
   int lastPcgIterations = 0; int64_t totalPcgIterations = 0;   // of the last solve / of all solves since g2ocu_reset_counters
   bool errorsValid = false; double chi2Robust = 0, chi2Plain = 0;
   // estimates of each class form one contiguous run of the packed host array and together cover it: copies go straight between the caller's buffer and the device
@@ -151,6 +154,7 @@ struct g2ocu_solver {
     for (void* o : p2pOpened) if (o) cudaIpcCloseMemHandle(o);
     for (void* o : schurOpened) if (o) cudaIpcCloseMemHandle(o);
     if (p2pLocal) cudaFree(p2pLocal);
+    if (pcgGraph) cudaGraphExecDestroy(pcgGraph);
     if (ncclComm && g_nccl.CommDestroy) g_nccl.CommDestroy(ncclComm);
     if (hostScal) cudaFreeHost(hostScal);
     if (hostInfo) cudaFreeHost(hostInfo);
@@ -213,6 +217,7 @@ double phaseSeconds(g2ocu_solver* s, const char* ph) { auto it = s->phases.find(
 // The peer-memory exchange buffers are sized for one structure: any change of graph, shard or structure drops the mappings (the host
 // exports / imports again after the next g2ocu_build_structure).
 void dropP2p(g2ocu_solver* s) {
+  if (s->pcgGraph) { cudaGraphExecDestroy(s->pcgGraph); s->pcgGraph = nullptr; }   // its kernel arguments hold the old pointers
   s->p2pReady = false;
   for (void*& o : s->p2pOpened) if (o) { cudaIpcCloseMemHandle(o); o = nullptr; }
   s->p2p = P2pDev();
@@ -561,6 +566,28 @@ int buildSystem(g2ocu_solver* s) {
   return G2OCU_OK;
 }
 
+const int kPcgGraphIters = 4;
+// The CG iterations between two convergence polls as one graph launch (the kernels are tens of microseconds long at most - at 8 GPUs
+// shorter than their launch gaps).  Only with the one-launch tail; not while per-kernel timing is on.
+int ensurePcgGraph(g2ocu_solver* s, bool p2p) {
+  PcgDev& pc = s->pcg;
+  if (s->pcgGraph && s->pcgGraphLambda == pc.lambda && s->pcgGraphP2p == p2p && s->pcgGraphA == pc.A && s->pcgGraphN == pc.n) return G2OCU_OK;
+  if (s->pcgGraph) { cudaGraphExecDestroy(s->pcgGraph); s->pcgGraph = nullptr; }
+  int64_t dummy = 0;
+  CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+  for (int k = 0; k < kPcgGraphIters; ++k) {
+    launchSpmv(pc, pc.d, pc.q, s->stream, &dummy, true);
+    if (p2p) launchP2pPushAndTail(pc, s->p2p, s->stream, &dummy); else launchPcgTail(pc, s->stream, &dummy, false);
+  }
+  cudaGraph_t graph = nullptr;
+  CU(cudaStreamEndCapture(s->stream, &graph));
+  const cudaError_t e = cudaGraphInstantiate(&s->pcgGraph, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { s->pcgGraph = nullptr; return fail(s, G2OCU_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+  s->pcgGraphLambda = pc.lambda; s->pcgGraphP2p = p2p; s->pcgGraphA = pc.A; s->pcgGraphN = pc.n;
+  return G2OCU_OK;
+}
+
 int solvePcg(g2ocu_solver* s, const double* rhs) {
   PcgDev& pc = s->pcg;
   pc.lambda = s->st.doSchur ? 0.0 : s->lambda;
@@ -579,9 +606,17 @@ int solvePcg(g2ocu_solver* s, const double* rhs) {
     // convergence are no-ops on the device, so overshooting costs microseconds while every poll drains the stream
     const int want = issued == 0 ? std::min(std::max(kCheckEvery, s->lastPcgIterations - 1), 256) : kCheckEvery;
     const int batch = std::min(want, maxIter - issued);
+    const bool p2p = slab && s->p2pReady && pc.n <= s->p2p.cap;
+    static const bool graphsOn = [] { const char* e = getenv("G2OCU_PCG_GRAPH"); return !(e && e[0] == '0'); }();
+    const bool useGraph = graphsOn && !s->kernelTiming && pcgFusedTail(pc) && (!slab || p2p);
     for (int k = 0; k < batch; ++k) {
+      if (useGraph && issued + k > 0 && batch - k >= kPcgGraphIters) {      // (the first product of a solve clears q itself)
+        int rc = ensurePcgGraph(s, p2p); if (rc) return rc;
+        CU(cudaGraphLaunch(s->pcgGraph, s->stream));
+        s->launches += kPcgGraphIters * (p2p ? 3 : 2); k += kPcgGraphIters - 1;
+        continue;
+      }
       { KernelTimer pt(s, "pcg_spmv"); launchSpmv(pc, pc.d, pc.q, s->stream, &s->launches, issued + k > 0 && pcgSingleCtaTail(pc)); }
-      const bool p2p = slab && s->p2pReady && pc.n <= s->p2p.cap;
       if (p2p && pcgFusedTail(pc)) { KernelTimer pt(s, "pcg_vec"); launchP2pPushAndTail(pc, s->p2p, s->stream, &s->launches); continue; }   // push + one kernel: wait for the peers, sum, d.q, recurrences
       if (p2p) { KernelTimer pt(s, "pcg_exchange"); launchP2pExchangeDot(pc, s->p2p, s->stream, &s->launches); }   // peer-memory all-reduce of q fused with d.q
       else if (slab) { KernelTimer pt(s, "pcg_exchange"); int rc = allreduceDev(s, pc.q, pc.n, 0); if (rc) return rc; }
