@@ -192,32 +192,40 @@ template <int P> __global__ void __launch_bounds__(kKpThreads, 1) schur_kpack_ke
       }
       const uint32_t Bd = smemBase + LY::offB + (uint32_t)stage * kKpRows * LY::BS * 8;
       const uint32_t Ad = smemBase + LY::offA + (uint32_t)stage * kKpRows * LY::AS * 8;
-      // Copies: a thread owns a scalar column of the stage (one of the 32 x P of the column cameras' B rows or of the 8 x P of the row
-      // cameras' A rows) and walks the rows, so that a warp writes 32 consecutive doubles of a row with each cp.async (8 bytes per lane: the
-      // Hpl blocks are only 8-byte aligned).  An absent camera is the same copy with source size 0, which writes zeros.
-      for (int col = tp; col < LY::NS + 8 * P; col += kKpProducerThreads) {
-        const bool colSide = col < LY::NS;
-        const int s2 = colSide ? col : col - LY::NS, cam = s2 / P, r = s2 - cam * P;
-        const uint32_t dstCol = (colSide ? Bd : Ad) + (uint32_t)s2 * 8u;
-        const uint32_t rowBytes = colSide ? LY::BS * 8 : LY::AS * 8;
-        for (int pe = 0; pe < nE; ++pe) {
-          const uint32_t mask = colSide ? hdr[4 + 4 * pe + 1] : hdr[4 + 4 * pe];
-          const int first = (int)(colSide ? hdr[4 + 4 * pe + 3] : hdr[4 + kKpBatch * 4 + 2 * pe]);
-          const bool on = (mask >> cam) & 1u;
-          const double* src = Hpl + (on ? (size_t)(first + __popc(mask & ((1u << cam) - 1u))) * PLn + r : 0);
-          const uint32_t dst = dstCol + (uint32_t)(3 * pe) * rowBytes, sz = on ? 8u : 0u;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + (uint32_t)c * rowBytes), "l"(src + P * c), "r"(sz) : "memory");
-        }
-      }
+      // Copies: a thread owns a scalar column of the stage (one of the 8 x P of the row cameras' A rows or of the 32 x P of the column
+      // cameras' B rows) and walks the rows, so that a warp writes 32 consecutive doubles of a row with each cp.async (8 bytes per lane: the
+      // Hpl blocks are only 8-byte aligned).  An absent camera is the same copy with source size 0, which writes zeros.  The row side and
+      // Dinv go first, in a cp.async group of their own: W is formed while the rest of the column side is still landing.
       if (tp < nE * 9) {   // Dinv of the landmarks
         const int p = tp / 9, q = tp - 9 * p;
         const double* src = d.Dinv + (size_t)(int)hdr[4 + kKpBatch * 4 + 2 * p + 1] * 9 + q;
         const uint32_t dst = smemBase + LY::offDinv + (uint32_t)((stage * kKpBatch + p) * 10 + q) * 8u;
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
       }
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      asm volatile("bar.sync 1, %0;" ::"n"(kKpProducerThreads) : "memory");     // every producer's copies have landed
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        const int col = tp + pass * kKpProducerThreads;          // columns 0 .. 8 P - 1: row side, then the column side
+        if (col < LY::NS + 8 * P) {
+          const bool rowSide = col < 8 * P;
+          const int s2 = rowSide ? col : col - 8 * P, cam = s2 / P, r = s2 - cam * P;
+          const uint32_t dstCol = (rowSide ? Ad : Bd) + (uint32_t)s2 * 8u;
+          const uint32_t rowBytes = rowSide ? LY::AS * 8 : LY::BS * 8;
+          const uint32_t below = (1u << cam) - 1u;
+#pragma unroll 5
+          for (int pe = 0; pe < nE; ++pe) {
+            const uint32_t mask = rowSide ? hdr[4 + 4 * pe] : hdr[4 + 4 * pe + 1];
+            const int first = (int)(rowSide ? hdr[4 + kKpBatch * 4 + 2 * pe] : hdr[4 + 4 * pe + 3]);
+            const bool on = (mask >> cam) & 1u;
+            const double* src = Hpl + (on ? (size_t)(first + __popc(mask & below)) * PLn + r : 0);
+            const uint32_t dst = dstCol + (uint32_t)(3 * pe) * rowBytes, sz = on ? 8u : 0u;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + (uint32_t)c * rowBytes), "l"(src + P * c), "r"(sz) : "memory");
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      asm volatile("cp.async.wait_group 1;" ::: "memory");                        // this thread's first pass (row side, Dinv) has landed
+      asm volatile("bar.sync 1, %0;" ::"n"(kKpProducerThreads) : "memory");     // ... and everybody else's
       {  // row side in place: W[r, :] = B[r, :] Dinv (block_solver.hpp:366, BDinv = Bi1 * DInvBlock); item = (entry p, scalar column s of the 8 row cameras)
         double* Arows = reinterpret_cast<double*>(smemRaw + LY::offA) + (size_t)stage * kKpRows * LY::AS;
         const double* Dv = reinterpret_cast<const double*>(smemRaw + LY::offDinv) + (size_t)stage * kKpBatch * 10;
@@ -233,6 +241,7 @@ template <int P> __global__ void __launch_bounds__(kKpThreads, 1) schur_kpack_ke
         if (FR && nE < kKpBatch)   // last batch of the chunk: the ninth-row pass reads all 32 row slots, the unused ones must be zero
           for (int t = rows * LY::AS + tp; t < kKpRows * LY::AS; t += kKpProducerThreads) Arows[t] = 0.0;
       }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbarArrive(sFull + stage);
       if (++stage == kKpStages) { stage = 0; phase ^= 1u; }
