@@ -41,7 +41,7 @@ EXPORTS = ["g2ocu_default_config", "g2ocu_version", "g2ocu_last_error", "g2ocu_c
            "g2ocu_set_property", "g2ocu_set_force_stop_flag", "g2ocu_set_shard", "g2ocu_nccl_unique_id", "g2ocu_set_shard_nccl", "g2ocu_p2p_export", "g2ocu_p2p_import", "g2ocu_p2p_export_schur", "g2ocu_p2p_import_schur", "g2ocu_initialize_optimization", "g2ocu_init", "g2ocu_build_structure",
            "g2ocu_compute_active_errors", "g2ocu_active_robust_chi2", "g2ocu_active_chi2", "g2ocu_build_system",
            "g2ocu_set_lambda", "g2ocu_restore_diagonal", "g2ocu_solve", "g2ocu_update", "g2ocu_push", "g2ocu_pop",
-           "g2ocu_discard_top", "g2ocu_compute_lambda_init", "g2ocu_compute_scale", "g2ocu_multiply_hessian",
+           "g2ocu_discard_top", "g2ocu_compute_lambda_init", "g2ocu_compute_scale", "g2ocu_multiply_hessian", "g2ocu_compute_marginals",
            "g2ocu_solver_iteration", "g2ocu_optimize", "g2ocu_vector_size", "g2ocu_set_estimates", "g2ocu_get_estimates",
            "g2ocu_get_i32", "g2ocu_get_f64", "g2ocu_launch_count", "g2ocu_phase_time", "g2ocu_reset_counters",
            "g2ocu_linear_create", "g2ocu_linear_destroy", "g2ocu_linear_last_error", "g2ocu_linear_init", "g2ocu_linear_set_property", "g2ocu_linear_solve"]
@@ -76,6 +76,7 @@ def lib() -> ctypes.CDLL:
         "g2ocu_update": (ctypes.c_int, [vp, vp]), "g2ocu_push": (ctypes.c_int, [vp]), "g2ocu_pop": (ctypes.c_int, [vp]),
         "g2ocu_discard_top": (ctypes.c_int, [vp]), "g2ocu_compute_lambda_init": (ctypes.c_int, [vp, P(dbl)]),
         "g2ocu_compute_scale": (ctypes.c_int, [vp, dbl, P(dbl)]), "g2ocu_multiply_hessian": (ctypes.c_int, [vp, vp, vp]),
+        "g2ocu_compute_marginals": (ctypes.c_int, [vp, i32, vp, vp, vp, P(i32)]),
         "g2ocu_solver_iteration": (ctypes.c_int, [vp, i32, i32, P(IterationStats)]),
         "g2ocu_optimize": (ctypes.c_int, [vp, i32, i32, P(IterationStats), P(i32)]),
         "g2ocu_vector_size": (i64, [vp]), "g2ocu_set_estimates": (ctypes.c_int, [vp, vp]),

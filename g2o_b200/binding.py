@@ -202,6 +202,19 @@ class CudaSolver:
         self._ck(self._L.g2ocu_multiply_hessian(self._h, dst.ctypes.data_as(ctypes.c_void_p), src.ctypes.data_as(ctypes.c_void_p)))
         return dst
 
+    def compute_marginals(self, pairs):
+        """``SparseOptimizer::computeMarginals(spinv, blockIndices)`` (sparse_optimizer.cpp:594-596): ``pairs`` = (row, col) hessian indices of pose
+        vertices; returns the list of blocks of the inverse of Hpp (poseDim x poseDim arrays), or None where the reference returns false."""
+        pairs = [(int(r), int(c)) for r, c in pairs]
+        rows = np.array([p[0] for p in pairs], dtype=np.int32); cols = np.array([p[1] for p in pairs], dtype=np.int32)
+        dims = self.get_i32("dims"); P = int(dims[2]) // max(int(dims[0]), 1)
+        out = np.zeros(len(pairs) * P * P); ok = ctypes.c_int32(0)
+        self._ck(self._L.g2ocu_compute_marginals(self._h, len(pairs), rows.ctypes.data_as(ctypes.c_void_p), cols.ctypes.data_as(ctypes.c_void_p),
+                                                 out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(ok)))
+        if not ok.value:
+            return None
+        return [out[i * P * P:(i + 1) * P * P].reshape(P, P, order="F").copy() for i in range(len(pairs))]
+
     def vector_size(self) -> int: return int(self._L.g2ocu_vector_size(self._h))
     def x(self) -> np.ndarray: return self.get_f64("x")
     def b(self) -> np.ndarray: return self.get_f64("b")

@@ -1279,6 +1279,74 @@ int g2ocu_multiply_hessian(g2ocu_solver* s, double* hostDest, const double* host
   return syncStream(s);
 }
 
+// SparseOptimizer::computeMarginals (sparse_optimizer.cpp:594-596) -> BlockSolver::computeMarginals (block_solver.hpp:451-459) ->
+// LinearSolver::solvePattern(spinv, blockIndices, *_Hpp) (linear_solver.h:89-98; the CSparse / CHOLMOD solvers answer it through
+// MarginalCovarianceCholesky, marginal_covariance_cholesky.cpp:153-222): blocks (row, col) of the inverse of Hpp as it stands - the pose
+// block of the last buildSystem, plus whatever setLambda has put on its diagonal.  Here: dense copy of Hpp, FP64 Cholesky on the tensor
+// pipe (kernels_dense.cu), (L L^T)^-1 applied to the unit columns of the requested block columns (at most 1 GiB of them at a time), the
+// requested blocks gathered on the device.  *computed = 0 where the reference's solvePattern returns false: factorisation failed.
+int g2ocu_compute_marginals(g2ocu_solver* s, int32_t nPairs, const int32_t* blockRows, const int32_t* blockCols, double* out, int32_t* computed) {
+  int rc = requireBuilt(s); if (rc) return rc;
+  if (computed) *computed = 0;
+  if (nPairs < 0 || (nPairs > 0 && (!blockRows || !blockCols || !out))) return fail(s, G2OCU_E_INVALID, "g2ocu_compute_marginals: null argument");
+  const Structure& st = s->st;
+  if (st.fullSystem) return fail(s, G2OCU_E_UNSUPPORTED, "g2ocu_compute_marginals: the graph has points that are not marginalized (its Hpp is the whole system with two block sizes); marginalize the points or use a pose graph");
+  const int P = st.P; const int64_t n = st.sizePoses;
+  if (P != 3 && P != 6 && P != 9) return fail(s, G2OCU_E_UNSUPPORTED, "g2ocu_compute_marginals: pose dimension " + std::to_string(P));
+  if (n > kDenseMaxN) return fail(s, G2OCU_E_UNSUPPORTED, "g2ocu_compute_marginals: the dense factorisation is limited to pose systems of dimension <= " + std::to_string(kDenseMaxN) + " (this one has " + std::to_string(n) + ")");
+  for (int i = 0; i < nPairs; ++i)
+    if (blockRows[i] < 0 || blockRows[i] >= st.numPoses || blockCols[i] < 0 || blockCols[i] >= st.numPoses)
+      return fail(s, G2OCU_E_INVALID, "g2ocu_compute_marginals: block (" + std::to_string(blockRows[i]) + ", " + std::to_string(blockCols[i]) + ") is outside Hpp (" + std::to_string(st.numPoses) + " block rows)");
+  if (nPairs == 0) { if (computed) *computed = 1; return G2OCU_OK; }
+  PhaseTimer pt(s, "marginals");
+  PcgDev pc; rc = hppView(s, pc); if (rc) return rc;
+  DVec<double> hppSum;
+  if (s->world > 1 && st.doSchur) {   // landmark shards hold partial pose blocks: sum a copy
+    const size_t cnt = st.hppColIdx.size() * (size_t)P * P;
+    CU(hppSum.alloc(cnt)); CU(cudaMemcpyAsync(hppSum.p, s->Hpp.p, cnt * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+    rc = allreduceDev(s, hppSum.p, (int64_t)cnt, 0); if (rc) return rc;
+    pc.A = hppSum.p;
+  }
+  CU(s->denseH.alloc((size_t)n * n)); CU(s->denseInfo.alloc(1));
+  launchDenseAssemble(pc, s->denseH.p, s->stream, &s->launches);
+  launchDenseCholeskyFactor(s->denseH.p, (int)n, s->denseInfo.p, s->stream, &s->launches);
+  CU(cudaMemcpyAsync(s->hostInfo, s->denseInfo.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  rc = syncStream(s); if (rc) return rc;
+  if (*s->hostInfo != 0) return G2OCU_OK;                            // not positive definite: solvePattern == false
+  // pairs by block column; a batch = as many distinct block columns as fit the column budget
+  std::vector<int32_t> order(nPairs);
+  for (int i = 0; i < nPairs; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return blockCols[a] < blockCols[b]; });
+  const int64_t slotsMax = std::max<int64_t>(1, ((int64_t)1 << 27) / n / P);
+  DVec<double> X, outDev; DVec<int32_t> dCol, dRow, dSlot, dOut;
+  CU(outDev.alloc((size_t)nPairs * P * P));
+  size_t at = 0;
+  while (at < order.size()) {
+    std::vector<int32_t> cols, pr, ps, po;
+    int minRow = st.numPoses;
+    size_t e = at;
+    for (; e < order.size(); ++e) {
+      const int32_t c = blockCols[order[e]];
+      if (cols.empty() || cols.back() != c) { if ((int64_t)cols.size() == slotsMax) break; cols.push_back(c); }
+      pr.push_back(blockRows[order[e]]); ps.push_back((int32_t)cols.size() - 1); po.push_back(order[e]);
+      minRow = std::min(minRow, (int)blockRows[order[e]]);
+    }
+    const int nSlots = (int)cols.size(), nrhs = nSlots * P;
+    CU(X.alloc((size_t)n * nrhs));
+    CU(dCol.upload(cols, s->stream)); CU(dRow.upload(pr, s->stream)); CU(dSlot.upload(ps, s->stream)); CU(dOut.upload(po, s->stream));
+    launchUnitColumns(X.p, (size_t)n, dCol.p, P, nSlots, s->stream, &s->launches);
+    launchDenseSolveMany(s->denseH.p, (int)n, X.p, (size_t)n, nrhs, cols.front() * P, minRow * P, s->stream, &s->launches);
+    launchGatherBlocks(X.p, (size_t)n, dRow.p, dSlot.p, dOut.p, (int)pr.size(), P, outDev.p, s->stream, &s->launches);
+    CU(cudaGetLastError());
+    rc = syncStream(s); if (rc) return rc;                           // the host staging vectors go out of scope
+    at = e;
+  }
+  CU(cudaMemcpyAsync(out, outDev.p, (size_t)nPairs * P * P * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  rc = syncStream(s); if (rc) return rc;
+  if (computed) *computed = 1;
+  return G2OCU_OK;
+}
+
 int g2ocu_solver_iteration(g2ocu_solver* s, int32_t algorithm, int32_t iteration, g2ocu_iteration_stats* stats) {
   if (!s) return G2OCU_E_INVALID;
   if (!s->algoInitialized) return fail(s, G2OCU_E_INVALID, "g2ocu_init has not been called");

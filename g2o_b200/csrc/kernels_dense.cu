@@ -157,10 +157,11 @@ __global__ void __launch_bounds__(256) syrk_dmma_kernel(double* __restrict__ H, 
 }
 
 // forward: y_k = L11^-1 b_k (one CTA), then b[below] -= L21 y_k (thread per row)
-__global__ void __launch_bounds__(256) trsv_diag_fwd_kernel(const double* __restrict__ H, int n, int k0, int nb, double* __restrict__ x) {
+__global__ void __launch_bounds__(256) trsv_diag_fwd_kernel(const double* __restrict__ H, int n, int k0, int nb, double* __restrict__ x, size_t ldx) {
   __shared__ double sL[NB][NB + 1];
   __shared__ double sx[NB];
   const int t = threadIdx.x;
+  x += (size_t)blockIdx.x * ldx;                       // one CTA per right-hand side
   for (int q = t; q < nb * nb; q += 256) { const int r = q % nb, c = q / nb; if (r >= c) sL[r][c] = H[(size_t)(k0 + r) + (size_t)(k0 + c) * n]; }
   if (t < nb) sx[t] = x[k0 + t];
   __syncthreads();
@@ -198,10 +199,11 @@ __global__ void __launch_bounds__(256) trsv_update_bwd_kernel(const double* __re
   __syncthreads();
   if (threadIdx.x == 0) { double r = 0; for (int q = 0; q < 8; ++q) r += sm[q]; x[k0 + j] -= r; }
 }
-__global__ void __launch_bounds__(256) trsv_diag_bwd_kernel(const double* __restrict__ H, int n, int k0, int nb, double* __restrict__ x) {
+__global__ void __launch_bounds__(256) trsv_diag_bwd_kernel(const double* __restrict__ H, int n, int k0, int nb, double* __restrict__ x, size_t ldx) {
   __shared__ double sL[NB][NB + 1];
   __shared__ double sx[NB];
   const int t = threadIdx.x;
+  x += (size_t)blockIdx.x * ldx;
   for (int q = t; q < nb * nb; q += 256) { const int r = q % nb, c = q / nb; if (r >= c) sL[r][c] = H[(size_t)(k0 + r) + (size_t)(k0 + c) * n]; }
   if (t < nb) sx[t] = x[k0 + t];
   __syncthreads();
@@ -218,6 +220,65 @@ __global__ void __launch_bounds__(256) trsv_diag_bwd_kernel(const double* __rest
   if (t < nb) x[k0 + t] = sx[t];
 }
 
+// ---- several right-hand sides at once (blocks of the inverse, computeMarginals) ----
+// X is n x nrhs, column-major with leading dimension ldx.  A CTA of the update kernels serves RC right-hand sides, so that the panel of
+// L is read once per RC columns: forward, a thread keeps its row of the panel in registers and walks the RC columns staged in shared
+// memory; backward, a CTA owns one panel column and RC dot products over the rows below the panel.
+constexpr int RC = 16;
+__global__ void __launch_bounds__(128) trsm_update_fwd_kernel(const double* __restrict__ H, int n, int k0, int nb, double* __restrict__ X, size_t ldx, int nrhs) {
+  __shared__ double sx[RC][NB];
+  const int c0 = blockIdx.y * RC, nc = min(RC, nrhs - c0);
+  for (int t = threadIdx.x; t < RC * NB; t += 128) { const int c = t / NB, j = t % NB; sx[c][j] = (c < nc && j < nb) ? X[(size_t)(c0 + c) * ldx + k0 + j] : 0.0; }
+  __syncthreads();
+  const int row = k0 + nb + blockIdx.x * 128 + threadIdx.x;
+  if (row >= n) return;
+  double l[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) l[j] = j < nb ? H[(size_t)row + (size_t)(k0 + j) * n] : 0.0;
+  for (int c = 0; c < nc; ++c) {
+    double v = 0;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) v += l[j] * sx[c][j];
+    X[(size_t)(c0 + c) * ldx + row] -= v;
+  }
+}
+__global__ void __launch_bounds__(256) trsm_update_bwd_kernel(const double* __restrict__ H, int n, int k0, int nb, double* __restrict__ X, size_t ldx, int nrhs) {
+  __shared__ double sm[RC][8];
+  const int j = blockIdx.x, c0 = blockIdx.y * RC, nc = min(RC, nrhs - c0);
+  double acc[RC];
+#pragma unroll
+  for (int c = 0; c < RC; ++c) acc[c] = 0;
+  for (int row = k0 + nb + threadIdx.x; row < n; row += 256) {
+    const double l = H[(size_t)row + (size_t)(k0 + j) * n];
+#pragma unroll
+    for (int c = 0; c < RC; ++c) if (c < nc) acc[c] += l * X[(size_t)(c0 + c) * ldx + row];
+  }
+#pragma unroll
+  for (int c = 0; c < RC; ++c) {
+    double v = acc[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[c][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < nc) { double r = 0; for (int q = 0; q < 8; ++q) r += sm[threadIdx.x][q]; X[(size_t)(c0 + threadIdx.x) * ldx + k0 + j] -= r; }
+}
+// column slot * P + q of X = unit vector of scalar column blockCol[slot] * P + q
+__global__ void unit_columns_kernel(double* __restrict__ X, size_t ldx, const int32_t* __restrict__ blockCol, int P, int nSlots) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nSlots * P) return;
+  const int slot = t / P, q = t - slot * P;
+  X[(size_t)t * ldx + (size_t)blockCol[slot] * P + q] = 1.0;
+}
+// out block i (P x P, column-major) = rows of block pairRow[i] of the P columns of slot pairSlot[i]
+__global__ void gather_blocks_kernel(const double* __restrict__ X, size_t ldx, const int32_t* __restrict__ pairRow, const int32_t* __restrict__ pairSlot,
+                                     const int32_t* __restrict__ pairOut, int P, double* __restrict__ out) {
+  const int i = blockIdx.x, el = threadIdx.x;
+  if (el >= P * P) return;
+  const int r = el % P, c = el / P;
+  out[(size_t)pairOut[i] * P * P + el] = X[(size_t)(pairSlot[i] * P + c) * ldx + (size_t)pairRow[i] * P + r];
+}
+
 }  // namespace
 
 void launchDenseAssemble(const PcgDev& p, double* H, cudaStream_t st, int64_t* launches) {
@@ -232,8 +293,8 @@ void launchDenseAssemble(const PcgDev& p, double* H, cudaStream_t st, int64_t* l
   *launches += 1;
 }
 
-// factorise H = L L^T in place (lower), then x = H^-1 b.  *info (device int, zeroed here) becomes non-zero when a pivot is not positive.
-int launchDenseCholeskySolve(double* H, int n, const double* b, double* x, int* info, cudaStream_t st, int64_t* launches) {
+// factorise H = L L^T in place (lower).  *info (device int, zeroed here) becomes non-zero when a pivot is not positive.
+int launchDenseCholeskyFactor(double* H, int n, int* info, cudaStream_t st, int64_t* launches) {
   constexpr int kSyrkSmem = 2 * 2 * KC * LDS_ * (int)sizeof(double);
   constexpr int NO = 512;                             // outer panel: the trailing matrix is updated once per NO columns
   cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSyrkSmem);   // per device: set on every call (solvers may live on several GPUs of one process)
@@ -258,18 +319,48 @@ int launchDenseCholeskySolve(double* H, int n, const double* b, double* x, int* 
       *launches += 1;
     }
   }
+  return 0;
+}
+
+// ... then x = H^-1 b
+int launchDenseCholeskySolve(double* H, int n, const double* b, double* x, int* info, cudaStream_t st, int64_t* launches) {
+  launchDenseCholeskyFactor(H, n, info, st, launches);
   if (x != b) cudaMemcpyAsync(x, b, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st);
   for (int k0 = 0; k0 < n; k0 += NB) {
     const int nb = n - k0 < NB ? n - k0 : NB, rem = n - k0 - nb;
-    trsv_diag_fwd_kernel<<<1, 256, 0, st>>>(H, n, k0, nb, x); *launches += 1;
+    trsv_diag_fwd_kernel<<<1, 256, 0, st>>>(H, n, k0, nb, x, 0); *launches += 1;
     if (rem > 0) { trsv_update_fwd_kernel<<<(rem + 127) / 128, 128, 0, st>>>(H, n, k0, nb, x); *launches += 1; }
   }
   for (int k0 = ((n - 1) / NB) * NB; k0 >= 0; k0 -= NB) {
     const int nb = n - k0 < NB ? n - k0 : NB, rem = n - k0 - nb;
     if (rem > 0) { trsv_update_bwd_kernel<<<nb, 256, 0, st>>>(H, n, k0, nb, x); *launches += 1; }
-    trsv_diag_bwd_kernel<<<1, 256, 0, st>>>(H, n, k0, nb, x); *launches += 1;
+    trsv_diag_bwd_kernel<<<1, 256, 0, st>>>(H, n, k0, nb, x, 0); *launches += 1;
   }
   return 0;
+}
+
+// X <- (L L^T)^-1 X for nrhs columns.  Rows above `firstNonZero` are zero in every column on entry (the forward sweep starts at that
+// panel); rows above `firstNeeded` of the result are not needed (the backward sweep stops there).
+void launchDenseSolveMany(const double* H, int n, double* X, size_t ldx, int nrhs, int firstNonZero, int firstNeeded, cudaStream_t st, int64_t* launches) {
+  const int yb = (nrhs + RC - 1) / RC;
+  for (int k0 = (firstNonZero / NB) * NB; k0 < n; k0 += NB) {
+    const int nb = n - k0 < NB ? n - k0 : NB, rem = n - k0 - nb;
+    trsv_diag_fwd_kernel<<<nrhs, 256, 0, st>>>(H, n, k0, nb, X, ldx); *launches += 1;
+    if (rem > 0) { trsm_update_fwd_kernel<<<dim3((rem + 127) / 128, yb), 128, 0, st>>>(H, n, k0, nb, X, ldx, nrhs); *launches += 1; }
+  }
+  for (int k0 = ((n - 1) / NB) * NB; k0 >= (firstNeeded / NB) * NB; k0 -= NB) {
+    const int nb = n - k0 < NB ? n - k0 : NB, rem = n - k0 - nb;
+    if (rem > 0) { trsm_update_bwd_kernel<<<dim3(nb, yb), 256, 0, st>>>(H, n, k0, nb, X, ldx, nrhs); *launches += 1; }
+    trsv_diag_bwd_kernel<<<nrhs, 256, 0, st>>>(H, n, k0, nb, X, ldx); *launches += 1;
+  }
+}
+void launchUnitColumns(double* X, size_t ldx, const int32_t* blockCol, int P, int nSlots, cudaStream_t st, int64_t* launches) {
+  cudaMemsetAsync(X, 0, sizeof(double) * ldx * (size_t)nSlots * P, st);
+  unit_columns_kernel<<<(nSlots * P + 127) / 128, 128, 0, st>>>(X, ldx, blockCol, P, nSlots); *launches += 1;
+}
+void launchGatherBlocks(const double* X, size_t ldx, const int32_t* pairRow, const int32_t* pairSlot, const int32_t* pairOut, int nPairs, int P, double* out, cudaStream_t st, int64_t* launches) {
+  if (nPairs <= 0) return;
+  gather_blocks_kernel<<<nPairs, 96, 0, st>>>(X, ldx, pairRow, pairSlot, pairOut, P, out); *launches += 1;
 }
 
 }  // namespace g2ocu

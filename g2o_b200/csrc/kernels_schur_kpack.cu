@@ -56,7 +56,8 @@ template <int P> struct KpLayout {
   static constexpr int offDinv = offA + kAllRows * AS * 8;        // per stage and entry: Dinv of the landmark (9 doubles, padded to 10)
   static constexpr int offHdr = offDinv + kKpStages * kKpBatch * 10 * 8;
   static constexpr int hdrStage = 4 * kHdrWords;
-  static constexpr int offSlots = offHdr + kKpStages * hdrStage;   // write-out: Hschur slot of block (row camera w, column camera n), 8 x 32 ints
+  static constexpr int offDesc = offHdr + kKpStages * hdrStage;     // entry descriptors of the current and the next batch (2 x 64 words), producers only
+  static constexpr int offSlots = offDesc + 2 * 64 * 4;   // write-out: Hschur slot of block (row camera w, column camera n), 8 x 32 ints
   static constexpr int offBar = offSlots + 8 * 32 * 4;
   static constexpr int bytes = offBar + 2 * kKpStages * 8;
 };
@@ -143,27 +144,40 @@ template <int P> __global__ void __launch_bounds__(kKpThreads, 1) schur_kpack_ke
     auto loadDesc = [&](int e0) {
       if (e0 + tp < eEnd && tp < kKpBatch) { nMi = d.entMaskI[e0 + tp]; nMj = d.entMaskJ[e0 + tp]; nBj = d.entBaseJ[e0 + tp]; nBi = d.entBaseI[e0 + tp]; nLm = d.entLm[e0 + tp]; }
     };
-    loadDesc(eBegin);
-    for (int e0 = eBegin; e0 < eEnd; e0 += kKpBatch) {
-      const int nE = min(kKpBatch, eEnd - e0);
-      mbarWait(sEmpty + stage, phase ^ 1u);
-      uint32_t* hdr = reinterpret_cast<uint32_t*>(smemRaw + LY::offHdr + stage * LY::hdrStage);
-      if (tp < nE) {
+    // ... and reach shared memory one batch ahead (two slots, by batch parity), so that nothing but the copies themselves stands between
+    // the release of a stage and its refill: slot layout = [4 + 4 p ..] maskI, maskJ, column groups, first column-side block of entry p,
+    // [44 + 2 p ..] first row-side block, landmark
+    uint32_t* descRing = reinterpret_cast<uint32_t*>(smemRaw + LY::offDesc);
+    auto storeDesc = [&](uint32_t* slot) {
+      if (tp < kKpBatch) {
         uint32_t g = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) g |= ((nMj >> (8 * q)) & 0xffu) ? (1u << q) : 0u;
-        hdr[4 + 4 * tp] = nMi; hdr[4 + 4 * tp + 1] = nMj; hdr[4 + 4 * tp + 2] = g; hdr[4 + 4 * tp + 3] = (uint32_t)nBj;
-        hdr[4 + kKpBatch * 4 + 2 * tp] = (uint32_t)nBi; hdr[4 + kKpBatch * 4 + 2 * tp + 1] = (uint32_t)nLm;
+        slot[4 + 4 * tp] = nMi; slot[4 + 4 * tp + 1] = nMj; slot[4 + 4 * tp + 2] = g; slot[4 + 4 * tp + 3] = (uint32_t)nBj;
+        slot[4 + kKpBatch * 4 + 2 * tp] = (uint32_t)nBi; slot[4 + kKpBatch * 4 + 2 * tp + 1] = (uint32_t)nLm;
       }
+    };
+    loadDesc(eBegin);
+    storeDesc(descRing);
+    loadDesc(eBegin + kKpBatch);
+    asm volatile("bar.sync 1, %0;" ::"n"(kKpProducerThreads) : "memory");
+    int batchIdx = 0;
+    for (int e0 = eBegin; e0 < eEnd; e0 += kKpBatch, ++batchIdx) {
+      const int nE = min(kKpBatch, eEnd - e0);
+      mbarWait(sEmpty + stage, phase ^ 1u);
+      uint32_t* hdr = reinterpret_cast<uint32_t*>(smemRaw + LY::offHdr + stage * LY::hdrStage);
+      const uint32_t* desc = descRing + (batchIdx & 1) * 64;
       if (tp == 0) hdr[0] = (uint32_t)nE;
-      asm volatile("bar.sync 1, %0;" ::"n"(kKpProducerThreads) : "memory");
-      loadDesc(e0 + kKpBatch);
+      // descriptors of batch b + 1 into the other slot (its readers finished with batch b - 1 before the barrier of the previous iteration);
+      // the barrier further down publishes them.  Those of batch b + 2 start their way through the registers.
+      storeDesc(descRing + ((batchIdx + 1) & 1) * 64);
+      loadDesc(e0 + 2 * kKpBatch);
       const int rows = 3 * nE;
       if (tp >= kKpProducerThreads - 32) {
         // Queues of the 8 row cameras x 4 lane groups, by the last producer warp (lane = (w, a); a quad of lanes shares a row camera).
         // Branch free: lane p < 10 holds the descriptor of entry p in registers, the others read it with shuffles.
         const int ql = tp - (kKpProducerThreads - 32), qw = ql >> 2, qa = ql & 3;
-        const uint32_t eMi = ql < nE ? hdr[4 + 4 * ql] : 0u, eMj = ql < nE ? hdr[4 + 4 * ql + 1] : 0u, eG = ql < nE ? hdr[4 + 4 * ql + 2] : 0u;
+        const uint32_t eMi = ql < nE ? desc[4 + 4 * ql] : 0u, eMj = ql < nE ? desc[4 + 4 * ql + 1] : 0u, eG = ql < nE ? desc[4 + 4 * ql + 2] : 0u;
         uint32_t qlo = 0, qhi = 0, len = 0, gseq = 0, tch = 0;
 #pragma unroll
         for (int t = 0; t < kKpRows / 4; ++t) {
@@ -198,7 +212,7 @@ template <int P> __global__ void __launch_bounds__(kKpThreads, 1) schur_kpack_ke
       // Dinv go first, in a cp.async group of their own: W is formed while the rest of the column side is still landing.
       if (tp < nE * 9) {   // Dinv of the landmarks
         const int p = tp / 9, q = tp - 9 * p;
-        const double* src = d.Dinv + (size_t)(int)hdr[4 + kKpBatch * 4 + 2 * p + 1] * 9 + q;
+        const double* src = d.Dinv + (size_t)(int)desc[4 + kKpBatch * 4 + 2 * p + 1] * 9 + q;
         const uint32_t dst = smemBase + LY::offDinv + (uint32_t)((stage * kKpBatch + p) * 10 + q) * 8u;
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
       }
@@ -213,8 +227,8 @@ template <int P> __global__ void __launch_bounds__(kKpThreads, 1) schur_kpack_ke
           const uint32_t below = (1u << cam) - 1u;
 #pragma unroll 5
           for (int pe = 0; pe < nE; ++pe) {
-            const uint32_t mask = rowSide ? hdr[4 + 4 * pe] : hdr[4 + 4 * pe + 1];
-            const int first = (int)(rowSide ? hdr[4 + kKpBatch * 4 + 2 * pe] : hdr[4 + 4 * pe + 3]);
+            const uint32_t mask = rowSide ? desc[4 + 4 * pe] : desc[4 + 4 * pe + 1];
+            const int first = (int)(rowSide ? desc[4 + kKpBatch * 4 + 2 * pe] : desc[4 + 4 * pe + 3]);
             const bool on = (mask >> cam) & 1u;
             const double* src = Hpl + (on ? (size_t)(first + __popc(mask & below)) * PLn + r : 0);
             const uint32_t dst = dstCol + (uint32_t)(3 * pe) * rowBytes, sz = on ? 8u : 0u;

@@ -1,10 +1,11 @@
 // g2o_cuda: the command line of the reference's `g2o` application (g2o/apps/g2o_cli/g2o.cpp:101-693) for the graphs the CUDA backend
 // supports, on top of the host mirror.  Same flags where they make sense:
 //   g2o_cuda [-i N] [-solver lm_var_cuda] [-robustKernel Huber] [-robustKernelWidth w] [-solverProperties k=v,...] [-gaugeId id]
-//            [-marginalize] [-stats file] [-o out.g2o] [-v] [-listSolvers] [-summary] [-bal] input
+//            [-marginalize] [-computeMarginals] [-stats file] [-o out.g2o] [-v] [-listSolvers] [-summary] [-bal] input
 // -summary only loads and reports (no GPU needed).  Gauge: as g2o.cpp:283-316, a graph without a fixed vertex gets one fixed; the
 // reference picks "the first maximum-dimension vertex" in unordered_map order (sparse_optimizer.cpp:118-137, not reproducible), here it
 // is the one with the lowest id.  Landmarks are marginalized when the solver requires it (g2o.cpp:318-331).
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -31,7 +32,7 @@ static RobustKernel* makeKernel(const std::string& n) {   // RobustKernelFactory
 }
 
 int main(int argc, char** argv) {
-  int maxIterations = 5, gaugeId = -1; bool verbose = false, listSolvers = false, summary = false, bal = false, marginalize = false;
+  int maxIterations = 5, gaugeId = -1; bool verbose = false, listSolvers = false, summary = false, bal = false, marginalize = false, computeMarginals = false;
   std::string solver = "lm_var_cuda", robustKernel, outputFile, statsFile, solverProperties, input; double kernelWidth = -1.0;
   for (int a = 1; a < argc; ++a) {
     const std::string f = argv[a];
@@ -46,6 +47,7 @@ int main(int argc, char** argv) {
     else if (f == "-stats") statsFile = next();
     else if (f == "-v") verbose = true;
     else if (f == "-marginalize") marginalize = true;
+    else if (f == "-computeMarginals") computeMarginals = true;
     else if (f == "-listSolvers") listSolvers = true;
     else if (f == "-summary") summary = true;
     else if (f == "-bal") bal = true;
@@ -110,6 +112,22 @@ int main(int argc, char** argv) {
   std::cerr << "Initial chi2 = " << std::fixed << optimizer.activeChi2() << std::endl;
   const int result = optimizer.optimize(maxIterations);
   if (maxIterations > 0 && result <= 0) std::cerr << "optimize() returned " << result << ": the solver failed, result might be invalid" << std::endl;
+  if (computeMarginals && !(maxIterations > 0 && result <= 0)) {   // g2o.cpp:581-608: per active vertex the blocks (h, h) and (h - 1, h) of the inverse
+    std::vector<std::pair<int, int> > blockIndices; std::vector<int> ids;
+    for (const auto* v : optimizer.vertexList()) {
+      if (v->hessianIndex() >= 0) { blockIndices.push_back(std::make_pair(v->hessianIndex(), v->hessianIndex())); ids.push_back(v->id()); }
+      if (v->hessianIndex() > 0) { blockIndices.push_back(std::make_pair(v->hessianIndex() - 1, v->hessianIndex())); ids.push_back(v->id()); }
+    }
+    std::vector<std::vector<number_t> > spinv;
+    if (optimizer.computeMarginals(spinv, blockIndices)) {
+      for (size_t i = 0; i < blockIndices.size(); ++i) {
+        if (blockIndices[i].first == blockIndices[i].second) std::cerr << "Vertex id:" << ids[i] << std::endl;
+        std::cerr << "inv block :" << blockIndices[i].first << ", " << blockIndices[i].second << std::endl;
+        const int d = (int)std::lround(std::sqrt((double)spinv[i].size()));
+        for (int r = 0; r < d; ++r) { for (int c = 0; c < d; ++c) std::cerr << (c ? " " : "") << std::setprecision(6) << std::defaultfloat << spinv[i][r + (size_t)d * c]; std::cerr << std::endl; }
+      }
+    }
+  }
   optimizer.computeActiveErrors();
   std::cout << "iterations " << result << " chi2 " << std::setprecision(17) << optimizer.activeChi2() << " robust_chi2 " << optimizer.activeRobustChi2() << std::endl;
   if (!statsFile.empty()) {

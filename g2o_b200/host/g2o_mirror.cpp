@@ -144,6 +144,19 @@ void SparseOptimizer::update(const number_t* u) { check(_handle, g2ocu_update(_h
 void SparseOptimizer::push() { check(_handle, g2ocu_push(_handle), "SparseOptimizer::push"); }
 void SparseOptimizer::pop() { check(_handle, g2ocu_pop(_handle), "SparseOptimizer::pop"); }
 void SparseOptimizer::discardTop() { check(_handle, g2ocu_discard_top(_handle), "SparseOptimizer::discardTop"); }
+bool SparseOptimizer::computeMarginals(std::vector<std::vector<number_t> >& spinv, const std::vector<std::pair<int, int> >& blockIndices) {
+  spinv.clear();
+  int32_t dims[4] = {0, 0, 0, 0};
+  if (!_handle || g2ocu_get_i32(_handle, "dims", dims, 4) < 4 || dims[0] <= 0) return false;
+  const size_t PP = (size_t)(dims[2] / dims[0]) * (size_t)(dims[2] / dims[0]);
+  std::vector<int32_t> rows, cols;
+  for (const auto& rc : blockIndices) { rows.push_back(rc.first); cols.push_back(rc.second); }
+  std::vector<number_t> out(blockIndices.size() * PP);
+  int32_t computed = 0;
+  if (!check(_handle, g2ocu_compute_marginals(_handle, (int32_t)blockIndices.size(), rows.data(), cols.data(), out.data(), &computed), "SparseOptimizer::computeMarginals") || !computed) return false;
+  for (size_t i = 0; i < blockIndices.size(); ++i) spinv.emplace_back(out.begin() + i * PP, out.begin() + (i + 1) * PP);
+  return true;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 template <int P, int L> bool CudaBlockSolver<P, L>::init(SparseOptimizer* optimizer, bool online) {

@@ -221,6 +221,9 @@ class SparseOptimizer : public OptimizableGraph {
   void push();
   void pop();
   void discardTop();
+  // computeMarginals(spinv, blockIndices) (sparse_optimizer.h:129, sparse_optimizer.cpp:594-596): block i of `spinv` is block
+  // (blockIndices[i].first, .second) of the inverse of Hpp in hessian-index units, column-major; false as the reference's solvePattern
+  bool computeMarginals(std::vector<std::vector<number_t> >& spinv, const std::vector<std::pair<int, int> >& blockIndices);
   void clear();
   void setVerbose(bool v) { _verbose = v; }
   bool verbose() const { return _verbose; }

@@ -195,6 +195,30 @@ void fillBatchStatistics(const g2ocu_iteration_stats& st) {
 
 // ------------------------------------------------------------------------------------------------------------------------------------
 // Algorithm level: one virtual call per outer iteration, everything else on the device.
+// SparseOptimizer::computeMarginals (sparse_optimizer.cpp:594-596): blocks of the inverse of Hpp from the device.  `spinv` gets the layout
+// MarginalCovarianceCholesky::computeCovariance gives it (marginal_covariance_cholesky.cpp:153-160: a square block matrix over the block
+// rows of Hpp, the requested blocks allocated); false where the reference's solvePattern answers false (no factorisation) and where the
+// backend has no answer (points that are not marginalized, pose systems beyond the dense factorisation's limit).
+static bool marginalsFromDevice(g2ocu_solver* h, SparseBlockMatrix<MatrixX>& spinv, const std::vector<std::pair<int, int>>& blockIndices) {
+  int32_t dims[4] = {0, 0, 0, 0};
+  if (!h || g2ocu_get_i32(h, "dims", dims, 4) < 4 || dims[0] <= 0) return false;
+  const int nb = dims[0], P = dims[2] / dims[0];
+  std::vector<int32_t> rows, cols;
+  for (const auto& rc : blockIndices) { rows.push_back(rc.first); cols.push_back(rc.second); }
+  std::vector<double> out(blockIndices.size() * (size_t)P * P);
+  int32_t computed = 0;
+  if (g2ocu_compute_marginals(h, (int32_t)blockIndices.size(), rows.data(), cols.data(), out.data(), &computed) != G2OCU_OK) { std::cerr << "solver_cuda: " << g2ocu_last_error(h) << std::endl; return false; }
+  if (!computed) return false;
+  std::vector<int> blockEnds(nb);
+  for (int i = 0; i < nb; ++i) blockEnds[i] = (i + 1) * P;
+  spinv = SparseBlockMatrix<MatrixX>(blockEnds.data(), blockEnds.data(), nb, nb, true);
+  for (size_t i = 0; i < blockIndices.size(); ++i) {
+    MatrixX* b = spinv.block(rows[i], cols[i], true);
+    for (int c = 0; c < P; ++c) for (int r = 0; r < P; ++r) (*b)(r, c) = out[i * (size_t)P * P + (size_t)c * P + r];
+  }
+  return true;
+}
+
 class OptimizationAlgorithmCuda : public OptimizationAlgorithm {
  public:
   OptimizationAlgorithmCuda(int algorithm, int poseDim, int landmarkDim, int linearSolver = G2OCU_LINEAR_PCG) : _algorithm(algorithm), _poseDim(poseDim), _landmarkDim(landmarkDim) {
@@ -231,7 +255,7 @@ class OptimizationAlgorithmCuda : public OptimizationAlgorithm {
     fillBatchStatistics(st);
     return st.result == G2OCU_RESULT_OK ? OK : (st.result == G2OCU_RESULT_TERMINATE ? Terminate : Fail);
   }
-  bool computeMarginals(SparseBlockMatrix<MatrixX>&, const std::vector<std::pair<int, int>>&) override { return false; }   // as LinearSolverPCG / Dense: solvePattern is not provided (linear_solver.h:89-98)
+  bool computeMarginals(SparseBlockMatrix<MatrixX>& spinv, const std::vector<std::pair<int, int>>& blockIndices) override { return marginalsFromDevice(_h, spinv, blockIndices); }
   bool updateStructure(const std::vector<HyperGraph::Vertex*>&, const HyperGraph::EdgeSet&) override { return false; }    // online mode: out of scope
   void printVerbose(std::ostream& os) const override {
     if (_algorithm == G2OCU_ALGORITHM_DOGLEG) {   // optimization_algorithm_dogleg.cpp:199-217
@@ -311,7 +335,7 @@ class CudaBlockSolverImpl : public BlockSolverBase {
     }
     return solved != 0;
   }
-  bool computeMarginals(SparseBlockMatrix<MatrixX>&, const std::vector<std::pair<int, int>>&) override { return false; }   // as with LinearSolverPCG / Dense (linear_solver.h:89-98)
+  bool computeMarginals(SparseBlockMatrix<MatrixX>& spinv, const std::vector<std::pair<int, int>>& blockIndices) override { return marginalsFromDevice(_h, spinv, blockIndices); }   // block_solver.hpp:451-459
   bool supportsSchur() override { return true; }
   bool schur() override { return _doSchur; }
   void setSchur(bool s) override { _doSchur = s; }                         // the backend derives it from the marginalized flags exactly like with_hessian.cpp:48-66

@@ -65,6 +65,14 @@ static void edgeSE3Problem(bool rotation, const char* solver = "lm_var_cuda") {
   const double tn = std::sqrt(est[9] * est[9] + est[10] * est[10] + est[11] * est[11]);
   const double dn = std::sqrt((est[0] - 1) * (est[0] - 1) + (est[4] - 1) * (est[4] - 1) + (est[8] - 1) * (est[8] - 1));
   EXPECT(tn < 1e-9); EXPECT(dn < 1e-9);
+  {  // marginal covariance of the free vertex (sparse_optimizer.h:137-144: the (hessianIndex, hessianIndex) block of the inverse of Hpp)
+    std::vector<std::vector<number_t> > spinv;
+    EXPECT(optimizer.computeMarginals(spinv, std::vector<std::pair<int, int> >(1, std::make_pair(0, 0))));
+    EXPECT(spinv.size() == 1 && spinv[0].size() == 36);
+    if (spinv.size() == 1 && spinv[0].size() == 36)
+      for (int c = 0; c < 6; ++c) { EXPECT(spinv[0][c + 6 * c] > 0 && std::isfinite(spinv[0][c + 6 * c])); for (int r = 0; r < c; ++r) EXPECT(std::fabs(spinv[0][r + 6 * c] - spinv[0][c + 6 * r]) < 1e-12); }
+    EXPECT(!optimizer.computeMarginals(spinv, std::vector<std::pair<int, int> >(1, std::make_pair(0, 5))));   // outside Hpp
+  }
   if (auto* dl = dynamic_cast<OptimizationAlgorithmDogleg*>(optimizer.algorithm())) {   // the last iteration ends with rejected steps only: trust region shrunk
     EXPECT(dl->lastStep() == OptimizationAlgorithmDogleg::STEP_GN); EXPECT(dl->trustRegion() > 0 && dl->trustRegion() < 1e4);
     std::stringstream ss; dl->printVerbose(ss); EXPECT(ss.str().find("step= GN") != std::string::npos);

@@ -500,7 +500,8 @@ def slam2d(n_poses: int = 100_000, n_landmarks: int = 20_000, world_size: float 
             off = np.arange(tot) - np.repeat(np.cumsum(cnt) - cnt, cnt)
             lidx = order[np.repeat(starts[cid], cnt) + off]
             obs_pose.append(pidx); obs_lm.append(lidx)
-    obs_pose = np.concatenate(obs_pose); obs_lm = np.concatenate(obs_lm)
+    obs_pose = np.concatenate(obs_pose) if obs_pose else np.zeros(0, dtype=np.int64)     # n_landmarks = 0: an odometry-only pose chain
+    obs_lm = np.concatenate(obs_lm) if obs_lm else np.zeros(0, dtype=np.int64)
     rel = lm[obs_lm] - gt[obs_pose, :2]
     cp, sp = np.cos(gt[obs_pose, 2]), np.sin(gt[obs_pose, 2])
     local = np.stack([cp * rel[:, 0] + sp * rel[:, 1], -sp * rel[:, 0] + cp * rel[:, 1]], axis=1)

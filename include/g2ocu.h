@@ -23,6 +23,8 @@
  *                                             optimization_algorithm_gauss_newton.cpp:50, _levenberg.cpp:58, _dogleg.cpp:56)
  *   SparseOptimizer::optimize                 sparse_optimizer.cpp:374    g2ocu_optimize
  *   BlockSolverBase::multiplyHessian          core/block_solver.h:87-95   g2ocu_multiply_hessian
+ *   SparseOptimizer::computeMarginals         sparse_optimizer.cpp:594    g2ocu_compute_marginals (Solver::computeMarginals, solver.h:78;
+ *                                             LinearSolver::solvePattern, linear_solver.h:89-98)
  *   LinearSolver<M>::solve                    core/linear_solver.h:59     (inside g2ocu_solve; kind = g2ocu_config.linear_solver) / g2ocu_linear_solve (stand-alone)
  *
  * Conventions: all functions return 0 on success and a negative G2OCU_E_* code on failure; the message is
@@ -212,6 +214,12 @@ int g2ocu_discard_top(g2ocu_solver* s);
 int g2ocu_compute_lambda_init(g2ocu_solver* s, double* lambda);
 int g2ocu_compute_scale(g2ocu_solver* s, double lambda, double* scale);
 int g2ocu_multiply_hessian(g2ocu_solver* s, double* host_dest, const double* host_src);
+/* Blocks of the inverse of Hpp (the marginal covariances of pose vertices): pair i = (block_rows[i], block_cols[i]) in hessian-index
+ * units, as the std::pair<int,int> list of SparseOptimizer::computeMarginals; out receives n_pairs blocks of poseDim x poseDim doubles, each
+ * column-major (the MatrixX blocks of `spinv`).  *computed = 1 / 0 is the bool the reference returns (0: Hpp is not positive definite).
+ * Needs a built system (g2ocu_build_system or an iteration).  G2OCU_E_UNSUPPORTED for graphs whose points are not marginalized and for
+ * pose systems beyond the dense factorisation's limit (40 000 scalar rows). */
+int g2ocu_compute_marginals(g2ocu_solver* s, int32_t n_pairs, const int32_t* block_rows, const int32_t* block_cols, double* out, int32_t* computed);
 
 int g2ocu_solver_iteration(g2ocu_solver* s, int32_t algorithm, int32_t iteration, g2ocu_iteration_stats* stats);
 int g2ocu_optimize(g2ocu_solver* s, int32_t algorithm, int32_t iterations, g2ocu_iteration_stats* stats, int32_t* performed);

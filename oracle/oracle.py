@@ -221,6 +221,24 @@ class ReferenceG2o:
         Solver virtuals; the BlockSolver's matrices can be read afterwards with structure_i32 / structure_f64."""
         return self._L.refcore_linearize(self._h, float(lam)) == 1
 
+    def compute_marginals(self, pairs):
+        """SparseOptimizer::computeMarginals (sparse_optimizer.cpp:594-596) of the compiled reference; needs a `*_csparse` block solver (the PCG
+        linear solver has no solvePattern, linear_solver.h:89-98).  Returns the blocks (column-major MatrixX -> 2-d arrays) or None."""
+        rows = np.array([p[0] for p in pairs], dtype=np.int32); cols = np.array([p[1] for p in pairs], dtype=np.int32)
+        cap = 81 * max(len(pairs), 1); out = np.zeros(cap)
+        self._L.refcore_compute_marginals.restype = ctypes.c_int
+        self._L.refcore_compute_marginals.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+        rc = self._L.refcore_compute_marginals(self._h, len(pairs), _dp(rows), _dp(cols), _dp(out), cap)
+        if rc != 1:
+            return None
+        VERTEX_DIM = (0, 3, 2, 6, 6, 3, 9, 3)   # minimal dimension by vertex type code (include/g2ocu.h), as the reference's BaseVertex<D, T>
+        hi = self.hessian_index(); dim_of = {int(hi[v]): int(VERTEX_DIM[int(self.graph.v_type[v])]) for v in range(len(hi)) if hi[v] >= 0}
+        blocks, off = [], 0
+        for r, c in pairs:
+            dr, dc = dim_of[int(r)], dim_of[int(c)]
+            blocks.append(out[off:off + dr * dc].reshape(dr, dc, order="F").copy()); off += dr * dc
+        return blocks
+
     def structure_i32(self, name: str) -> np.ndarray:
         """Block pattern arrays of the reference's BlockSolver (its protected _Hpp / _Hll / _Hpl / _Hschur / _HschurTransposedCCS), in the format of
         g2ocu_get_i32: pose_block_indices, landmark_block_indices, hpp_/hpl_/hll_/hschur_/hschur_t_ colptr + rowidx, dims."""

@@ -278,6 +278,26 @@ void refcore_set_num_threads(int n) {
 #endif
 }
 
+// SparseOptimizer::computeMarginals(spinv, blockIndices) (sparse_optimizer.cpp:594-596 -> block_solver.hpp:451-459 -> the linear solver's
+// solvePattern on Hpp, linear_solver_csparse.h:190-216, marginal_covariance_cholesky.cpp:153-222).  Pairs are block (hessian) indices;
+// out receives the blocks one after the other, each column-major.  Returns 1 / 0 as the reference does, -1 when `cap` is too small.
+int refcore_compute_marginals(void* hh, int nPairs, const int32_t* rows, const int32_t* cols, double* out, int64_t cap) {
+  Handle* h = (Handle*)hh;
+  std::vector<std::pair<int, int> > idx;
+  for (int i = 0; i < nPairs; ++i) idx.push_back(std::make_pair((int)rows[i], (int)cols[i]));
+  g2o::SparseBlockMatrix<g2o::MatrixX> spinv;
+  if (!h->optimizer.computeMarginals(spinv, idx)) return 0;
+  int64_t off = 0;
+  for (int i = 0; i < nPairs; ++i) {
+    const g2o::MatrixX* b = spinv.block(rows[i], cols[i]);
+    if (!b) return 0;
+    const int64_t sz = (int64_t)b->rows() * b->cols();
+    if (off + sz > cap) return -1;
+    for (int c = 0; c < b->cols(); ++c) for (int r = 0; r < b->rows(); ++r) out[off++] = (*b)(r, c);
+  }
+  return 1;
+}
+
 int refcore_initialize_optimization(void* hh, int level) { return ((Handle*)hh)->optimizer.initializeOptimization(level) ? 1 : 0; }
 
 // SparseOptimizer::optimize(iterations); stats: iterations x 13 doubles from G2OBatchStatistics = chi2, levenbergIterations, iterationsLinearSolver,

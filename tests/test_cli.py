@@ -117,3 +117,22 @@ def test_cli_runs_dogleg(tmp_path):
     m = re.search(r"iterations (\d+) chi2 (\S+) robust_chi2 (\S+)", r.stdout)
     s = CudaSolver(g, "dl_var_cuda", device=0); s.initialize_optimization(); s.compute_active_errors()
     assert int(m.group(1)) > 0 and float(m.group(3)) < s.active_robust_chi2()
+
+
+@pytest.mark.gpu
+def test_cli_compute_marginals(tmp_path):
+    """`-computeMarginals` (g2o.cpp:581-608): per active vertex the blocks (h, h) and (h - 1, h) of the inverse of the system matrix on stderr;
+    the printed diagonal block of the last vertex against the binding's answer for the same graph and iterations."""
+    from g2o_b200.binding import CudaSolver
+    g = W.sphere(nodes_per_level=8, laps=4)
+    path = str(tmp_path / "sphere.g2o")
+    W.write_g2o(g, path)
+    r = subprocess.run([CLI, "-i", "3", "-solver", "gn_var_cuda", "-computeMarginals", path], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    s = CudaSolver(g, "gn_var_cuda", device=0); s.initialize_optimization(); s.optimize(3)
+    nb = int(s.get_i32("dims")[0])
+    assert r.stderr.count("inv block :") == 2 * nb - 1
+    want = s.compute_marginals([(nb - 1, nb - 1)])[0]
+    text = r.stderr[r.stderr.index(f"inv block :{nb - 1}, {nb - 1}"):].splitlines()[1:7]
+    got = np.array([[float(x) for x in line.split()] for line in text])
+    assert got.shape == (6, 6) and np.max(np.abs(got - want)) <= 1e-5 * np.max(np.abs(want))

@@ -221,6 +221,55 @@ def test_linear_solver_level_entry_point(dim):
         L.g2ocu_linear_destroy(h)
 
 
+def _dense_hpp(s):
+    """Hpp of the device (upper blocks, CCS order, column-major) as a dense symmetric matrix."""
+    dims = s.get_i32("dims"); nb, n = int(dims[0]), int(dims[2]); P = n // nb
+    colptr, rowidx, vals = s.get_i32("hpp_colptr"), s.get_i32("hpp_rowidx"), s.get_f64("hpp_values").reshape(-1, P, P)
+    H = np.zeros((n, n))
+    for c in range(nb):
+        for k in range(colptr[c], colptr[c + 1]):
+            r = int(rowidx[k]); blk = vals[k].T                        # stored column-major
+            H[r * P:(r + 1) * P, c * P:(c + 1) * P] = blk
+            H[c * P:(c + 1) * P, r * P:(r + 1) * P] = blk.T
+    return H, P
+
+
+@pytest.mark.parametrize("name", ["sphere", "bal_medium", "slam2d", "ba_pose_constraints"])
+def test_compute_marginals_are_blocks_of_the_inverse_of_hpp(name):
+    """g2ocu_compute_marginals (SparseOptimizer::computeMarginals, sparse_optimizer.cpp:594-596): every requested block against numpy's
+    inverse of the same Hpp; all diagonal blocks at once (several column batches on the larger graphs), symmetric pairs, the damped matrix
+    after setLambda; the error paths."""
+    g, s, o = make(name)
+    s.init(); s.build_structure(); s.compute_active_errors(); s.build_system()
+    H, P = _dense_hpp(s); nb = H.shape[0] // P
+    inv = np.linalg.inv(H); scale = float(np.max(np.abs(inv)))
+    pairs = [(i, i) for i in range(nb)] + [(0, nb - 1), (nb - 1, 0), (nb // 2, nb // 3), (nb // 3, nb // 2)]
+    got = s.compute_marginals(pairs)
+    assert got is not None and len(got) == len(pairs)
+    for (r, c), b in zip(pairs, got):
+        assert np.max(np.abs(b - inv[r * P:(r + 1) * P, c * P:(c + 1) * P])) <= 1e-9 * scale, (name, r, c)
+    s.set_lambda(0.5)                                                  # the reference factorises Hpp as it stands: damped until restoreDiagonal
+    inv2 = np.linalg.inv(H + 0.5 * np.eye(H.shape[0]))
+    b = s.compute_marginals([(1, 1)])[0]
+    assert np.max(np.abs(b - inv2[P:2 * P, P:2 * P])) <= 1e-9 * float(np.max(np.abs(inv2)))
+    s.restore_diagonal()
+    assert s.compute_marginals([]) == []
+    with pytest.raises(Exception):
+        s.compute_marginals([(0, nb)])
+
+
+def test_compute_marginals_of_a_singular_system_and_of_a_full_system():
+    """Not positive definite -> the bool of the reference's solvePattern is false (None here); points that are not marginalized -> unsupported."""
+    g = W.sphere(nodes_per_level=8, laps=4, fix_first=False)          # gauge freedom: Hpp is singular
+    s = CudaSolver(g, "gn_var_cuda", device=0); s.initialize_optimization(); s.init(); s.build_structure(); s.compute_active_errors(); s.build_system()
+    s.set_lambda(-1.0)                                                 # make sure a pivot goes negative whatever the rounding does
+    assert s.compute_marginals([(0, 0)]) is None
+    g = W.slam2d(n_poses=60, n_landmarks=20, world_size=10.0, marginalize_landmarks=False)
+    s = CudaSolver(g, "gn_var_cuda", device=0); s.initialize_optimization(); s.init(); s.build_structure(); s.compute_active_errors(); s.build_system()
+    with pytest.raises(Exception):
+        s.compute_marginals([(0, 0)])
+
+
 def test_gauss_newton_sphere():
     g = W.sphere(nodes_per_level=12, laps=6)
     s = CudaSolver(g, "gn_var_cuda", device=0); s.initialize_optimization()

@@ -374,6 +374,45 @@ def test_cuda_path_against_the_reference_itself(name):
     assert np.max(np.abs(s.get_estimates() - e_r) / (1.0 + np.abs(e_r))) < 1e-6
 
 
+# Pose graphs only.  With marginalized points the reference hands Hpp to a LinearSolverCSparse whose CCS pattern and symbolic factorisation were
+# made for Hschur by the solve before (fillCSparse(A, onlyValues = true), linear_solver_csparse.h:191-196): what it returns then is not the
+# inverse of Hpp; tests/test_gpu_parity.py checks those graphs against numpy's inverse of Hpp instead.
+MARGINALS = {
+    "sphere": (lambda: W.sphere(nodes_per_level=12, laps=6), "var_csparse", "gn_var_cuda"),
+    "sphere_expmap": (lambda: W.sphere_expmap(nodes_per_level=10, laps=5), "var_csparse", "gn_var_cuda"),
+    "slam2d_odometry_chain": (lambda: W.slam2d(n_poses=300, n_landmarks=0, world_size=20.0), "3_2_csparse", "gn_fix3_2_cuda"),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(MARGINALS))
+def test_marginals_against_the_reference_s_solve_pattern(name):
+    """SparseOptimizer::computeMarginals: the reference answers it with LinearSolverCSparse::solvePattern + MarginalCovarianceCholesky on Hpp
+    (block_solver.hpp:451-459, marginal_covariance_cholesky.cpp:153-222), the CUDA path with its dense FP64 Cholesky.  Both on the Hpp of the
+    first linearisation (the reference runs one Gauss-Newton iteration, whose buildSystem happens at the initial estimates)."""
+    from g2o_b200.binding import CudaSolver
+    fn, bs, solver = MARGINALS[name]
+    g = fn()
+    ref = oracle.ReferenceG2o(g, "gn", bs, threads=1); assert ref.initialize_optimization(); ref.optimize(1)
+    s = CudaSolver(g, solver, device=0); s.initialize_optimization(); s.init(); s.build_structure(); s.compute_active_errors(); s.build_system()
+    n = int(s.get_i32("dims")[0])
+    rng = np.random.default_rng(3)
+    pairs = [(0, 0), (n - 1, n - 1), (0, n - 1), (n - 1, 0)] + [(int(a), int(b)) for a, b in rng.integers(0, n, size=(12, 2))] + [(i, i) for i in range(0, n, max(1, n // 9))]
+    want, got = ref.compute_marginals(pairs), s.compute_marginals(pairs)
+    assert want is not None and got is not None and len(want) == len(got)
+    scale = max(float(np.max(np.abs(b))) for b in want)
+    for (r, c), a, b in zip(pairs, got, want):
+        assert a.shape == b.shape and np.max(np.abs(a - b)) <= 1e-8 * scale, (name, r, c, float(np.max(np.abs(a - b))), scale)
+    # and as the drop-in: the reference's SparseOptimizer::computeMarginals answered by the plugin, at the algorithm and at the Solver level
+    _plugin()
+    for plugin_solver in (solver, solver + "_solver"):
+        gpu = oracle.ReferenceG2o(g, "factory", plugin_solver); assert gpu.initialize_optimization(); gpu.optimize(1)
+        through = gpu.compute_marginals(pairs)
+        assert through is not None and len(through) == len(want), plugin_solver
+        for a, b in zip(through, want):
+            assert a.shape == b.shape and np.max(np.abs(a - b)) <= 1e-8 * scale, (name, plugin_solver)
+
+
 def test_sphere_workload_matches_the_reference_create_sphere_program(tmp_path):
     """BASELINE config C2's graph generator: the reference's own create_sphere program (g2o/examples/sphere/create_sphere.cpp, compiled as it
     lies into oracle/_ref/create_sphere) writes a .g2o file; g2o_b200.workloads.sphere must describe the same graph - vertices, topology,
