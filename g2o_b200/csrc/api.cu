@@ -130,11 +130,11 @@ struct g2ocu_solver {
   DVec<double> poseEst, lmEst; std::vector<DVec<double>*> poseBackup, lmBackup; int stackDepth = 0;
   DVec<int> poseCounters, lmCounters;
   DVec<double> denseH; DVec<int> denseInfo; DVec<unsigned int> pcgTicket; int* hostInfo = nullptr;
-  DVec<double> Hpp, Hll, Hpl, W, b, x, S, Dinv, dbv, bschur, Minv, vr, vd, vq, vs, scal, partial, partialDq, scratch, out2, dbg;
+  DVec<double> Hpp, Hll, Hpl, W, Wshort, b, x, S, Dinv, dbv, bschur, Minv, vr, vd, vq, vs, scal, partial, partialDq, scratch, out2, dbg;
   DVec<double> fr, fd, fq, fs;                                       // full-system PCG vectors r, d, q, s (vectorSize each)
   DVec<double> hsd, hdl, aux;                                        // Dogleg: steepest-descent step, final step, auxiliary vector (vectorSize each)
   DVec<int32_t> mhRow, mhBegin, mhEnd, mhRowPtr, mhColIdx; bool mhReady = false;   // SpMV work items over the Hpp pattern (multiplyHessian in Schur mode)
-  DVec<int32_t> hppDiag, hplColPtr, hplRowIdx, sRowPtr, sColIdx, sDiag, hppToS, pairSlot, pairEdgeI, pairEdgeJ, aRowPtr, aColIdx, aDiag, spRow, spBegin, spEnd, hplLm, tEntLm, tEntBI, tEntBJ, tChunkI, tChunkJ, tChunkB, tChunkE, tChunkSlots, pairSegB, pairSegS;
+  DVec<int32_t> hppDiag, hplColPtr, hplRowIdx, sRowPtr, sColIdx, sDiag, hppToS, pairSlot, pairEdgeI, pairEdgeJ, aRowPtr, aColIdx, aDiag, spRow, spBegin, spEnd, hplLm, tEntLm, tEntBI, tEntBJ, tChunkI, tChunkJ, tChunkB, tChunkE, tChunkSlots, pairSegB, pairSegS, hplShortIdx, pairW;
   DVec<uint32_t> tEntMJ; DVec<uint8_t> tEntMI;
   DVec<int64_t> off64;
   std::vector<EdgeSetState*> sets;
@@ -437,6 +437,17 @@ int buildDevice(g2ocu_solver* s) {
       CU(s->pairEdgeI.upload(pI, stream)); CU(s->pairEdgeJ.upload(pJ, stream)); CU(s->pairSlot.alloc(std::max<size_t>(pI.size(), 1)));
       CU(cudaStreamSynchronize(stream));
       sd.nPairs = (int64_t)pI.size(); sd.pairEdgeI = s->pairEdgeI.p; sd.pairEdgeJ = s->pairEdgeJ.p; sd.pairSlot = s->pairSlot.p;
+      // W = B Dinv of the short tracks' blocks is formed by the coefficient pass for the pair kernel: compact index per Hpl block (in block
+      // order, so that the pass writes it front to back), and per pair the index of its row-side block.  (The older tile path forms all of W.)
+      if (!pI.empty() && !(useMma && !schurKpackEnabled())) {
+        std::vector<int32_t> shortIdx(st.hplRowIdx.size(), -1); int32_t nShort = 0;
+        for (int l = st.lmBegin; l < st.lmEnd; ++l) { const int cb = st.hplColPtr[l], ce = st.hplColPtr[l + 1]; if (ce - cb > 0 && ce - cb < kTileMinTrack) for (int k = cb; k < ce; ++k) shortIdx[k] = nShort++; }
+        std::vector<int32_t> pW(pI.size());
+        for (size_t k = 0; k < pI.size(); ++k) pW[k] = shortIdx[pI[k]];
+        CU(s->hplShortIdx.upload(shortIdx, stream)); CU(s->pairW.upload(pW, stream)); CU(s->Wshort.alloc((size_t)nShort * P * L + 2)); CU(s->Wshort.zero(stream));
+        CU(cudaStreamSynchronize(stream));
+        sd.hplShortIdx = s->hplShortIdx.p; sd.pairW = s->pairW.p; sd.Wshort = s->Wshort.p;
+      }
     }
     {  // tile entries grouped by (row tile, column strip), split in chunks of at most kTileChunk entries (one CTA each)
       const int kTileChunk = useMma ? 1024 : 256;

@@ -61,6 +61,9 @@ struct SchurDev {
   int64_t nPairs = 0; const int32_t* pairEdgeI = nullptr; const int32_t* pairEdgeJ = nullptr; int32_t* pairSlot = nullptr;
   // the same pairs sorted by target Hschur block and cut into segments of <= kPairSegment pairs of one block: a warp sums a segment in registers, one RED per element
   int nPairSegs = 0; const int32_t* pairSegBegin = nullptr; const int32_t* pairSegSlot = nullptr;
+  // W = B Dinv of the blocks of short tracks, formed by the coefficient pass: compact index of every Hpl block (-1: long track), the W blocks
+  // in that order, and per pair the compact index of its row-side block
+  const int32_t* hplShortIdx = nullptr; double* Wshort = nullptr; const int32_t* pairW = nullptr;
   double* S = nullptr; double* Dinv = nullptr; double* db = nullptr; double* bschur = nullptr;
   double* W = nullptr;          // Hpl Dinv, same block order as Hpl (tensor-pipe path only)
   // long tracks (>= kTileMinTrack observations): output-stationary tiles, see schur_tile_kernel

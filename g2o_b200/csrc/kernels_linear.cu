@@ -113,25 +113,56 @@ template <int P, int L> __global__ void dinv_kernel(SchurDev d, const double* __
     d.db[(size_t)lm * L + r] = v; }
 }
 
-// b_schur -= B_i (Dinv b_l) for every Hpl block (block_solver.hpp:366-374): thread per block, blocks staged through shared memory
+// b_schur -= B_i (Dinv b_l) for every Hpl block (block_solver.hpp:366-374): thread per block, blocks staged through shared memory.
+// The blocks of short tracks also leave as W = B Dinv (block_solver.hpp:366, BDinv) for the pair kernel: formed in place in the stage and
+// written with coalesced stores at the block's compact index (d.hplShortIdx; 2.6 M of the 5.0 M blocks on C3).
 template <int P, int L> __global__ void __launch_bounds__(128) coeff_kernel(SchurDev d, const double* __restrict__ Hpl, const int32_t* __restrict__ hplLm, int nBlocks) {
-  constexpr int PLn = P * L;
+  constexpr int PLn = P * L, LL = L * L;
   __shared__ double sB[128 * PLn];
+  __shared__ int32_t sW[128];
   const int tid = threadIdx.x, k0 = d.blockBegin + blockIdx.x * 128;
   const int nb = min(128, d.blockBegin + nBlocks - k0);
   const double* src = Hpl + (size_t)k0 * PLn;
   for (int t = tid; t < nb * PLn; t += 128) sB[t] = src[t];
   __syncthreads();
-  if (tid >= nb) return;
-  const int k = k0 + tid, ci = d.hplRowIdx[k], lm = hplLm[k];
-  double dbv[L];
+  int wi = -1;
+  if (tid < nb) {
+    const int k = k0 + tid, ci = d.hplRowIdx[k], lm = hplLm[k];
+    double dbv[L];
 #pragma unroll
-  for (int a = 0; a < L; ++a) dbv[a] = d.db[(size_t)lm * L + a];
+    for (int a = 0; a < L; ++a) dbv[a] = d.db[(size_t)lm * L + a];
+    double* blk = sB + tid * PLn;
 #pragma unroll
-  for (int r = 0; r < P; ++r) { double v = 0;
+    for (int r = 0; r < P; ++r) { double v = 0;
 #pragma unroll
-    for (int a = 0; a < L; ++a) v += sB[tid * PLn + r + P * a] * dbv[a];
-    atomicAdd(d.bschur + (size_t)ci * P + r, -v); }
+      for (int a = 0; a < L; ++a) v += blk[r + P * a] * dbv[a];
+      atomicAdd(d.bschur + (size_t)ci * P + r, -v); }
+    if (d.hplShortIdx) wi = d.hplShortIdx[k];
+    if (wi >= 0) {
+      double Di[LL];
+#pragma unroll
+      for (int a = 0; a < LL; ++a) Di[a] = d.Dinv[(size_t)lm * LL + a];
+#pragma unroll
+      for (int r = 0; r < P; ++r) {
+        double bv[L];
+#pragma unroll
+        for (int a = 0; a < L; ++a) bv[a] = blk[r + P * a];
+#pragma unroll
+        for (int a = 0; a < L; ++a) { double w = 0;
+#pragma unroll
+          for (int a2 = 0; a2 < L; ++a2) w += bv[a2] * Di[a2 + L * a];
+          blk[r + P * a] = w; }
+      }
+    }
+  }
+  sW[tid] = wi;
+  __syncthreads();
+  if (!d.hplShortIdx) return;
+  for (int t = tid; t < nb * PLn; t += 128) { const int bk = t / PLn, w = sW[bk]; if (w >= 0) d.Wshort[(size_t)w * PLn + (t - bk * PLn)] = sB[t]; }
+}
+
+__device__ __forceinline__ void pairDmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
 // Short tracks: Hschur(ci,cj) -= B_i Dinv B_j^T with one atomic add per element; warp per pair over a flat pair list
@@ -200,6 +231,57 @@ template <int P, int L> __global__ void __launch_bounds__(256) schur_pairs_seg_k
     double* Sb = d.S + (size_t)d.pairSegSlot[sgm] * PP;
 #pragma unroll
     for (int q = 0; q < NR; ++q) { const int el = lane + 32 * q; if (el < PP) atomicAdd(Sb + el, -acc[q]); }
+  }
+}
+
+// Short tracks on the FP64 tensor pipe: the pairs of a segment all add into one block, Hschur(i,j) -= sum_p W_p B_p^T, which is one small GEMM
+// with the pairs stacked along K (L scalars each, <= kPairSegment pairs: K <= 48).  One warp per segment; per K step of 4 a lane fetches one
+// scalar of W (row m of the pair its K slot belongs to, from the coefficient pass) and one of B_j and issues the DMMA of rows / columns
+// 0..7; for P = 9 row 8 and column 8 are three plain FMAs per lane on the ninth scalars of its K slot, summed over the 4 K lanes at the
+// end.  Against the scalar kernel above: 4 loads + 1 DMMA + 3 FMAs per 4/3 pairs instead of 18 loads + 12 FMAs + 9 shuffles per pair (that kernel sat at 86 % of the L1
+// pipe).  wIdx = index of the row-side W block per pair (d.pairW into d.Wshort, or d.pairEdgeI into the full W of the older tile path).
+template <int P, int L> __global__ void __launch_bounds__(256) schur_pairs_dmma_kernel(SchurDev d, const double* __restrict__ Hpl, const double* __restrict__ W, const int32_t* __restrict__ wIdx) {
+  constexpr int PP = P * P, PLn = P * L;
+  constexpr bool kFringe = P > 8;
+  const int lane = threadIdx.x & 31, m = lane >> 2, kq = lane & 3;
+  const int nWarps = gridDim.x * (blockDim.x >> 5);
+  for (int sgm = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); sgm < d.nPairSegs; sgm += nWarps) {
+    const int pb = d.pairSegBegin[sgm], np = d.pairSegBegin[sgm + 1] - pb;
+    int myW = 0, myJ = 0;                               // lane t < np: the blocks of pair t
+    if (lane < np) { myW = wIdx[pb + lane]; myJ = d.pairEdgeJ[pb + lane]; }
+    double C00[2] = {0, 0}, c01 = 0, c10 = 0, c11 = 0;   // fringe partial sums over this lane's K slots: (row m, col 8), (row 8, col m), (8, 8)
+    const int K = np * L;
+    for (int k0 = 0; k0 < K; k0 += 16) {                 // four K steps at a time: their 16 loads are in flight together
+      double a0[4], b0[4], w8[4], b8[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kg = k0 + 4 * u + kq, pi = kg / L, a = kg - pi * L;
+        const bool on = kg < K;
+        const int wi = __shfl_sync(0xffffffffu, myW, pi & 31), ej = __shfl_sync(0xffffffffu, myJ, pi & 31);
+        const double* wp = W + (size_t)wi * PLn + P * a; const double* bp = Hpl + (size_t)ej * PLn + P * a;
+        const bool in = on && m < P;
+        a0[u] = in ? wp[m] : 0.0; b0[u] = in ? bp[m] : 0.0;
+        if (kFringe) { w8[u] = on ? wp[8] : 0.0; b8[u] = on ? bp[8] : 0.0; }   // row 8 / column 8: every lane reads the two ninth scalars of its K slot
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (k0 + 4 * u < K) pairDmma(C00, a0[u], b0[u]);
+        if (kFringe) { c01 += a0[u] * b8[u]; c10 += w8[u] * b0[u]; c11 += w8[u] * b8[u]; }   // plain FMAs (three more DMMAs would be 15/16 padding)
+      }
+    }
+    double* Sb = d.S + (size_t)d.pairSegSlot[sgm] * PP;   // column-major block: element (r, c) at r + P c
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = 2 * kq + h;
+      if (m < P && c < P) atomicAdd(Sb + m + P * c, -C00[h]);
+    }
+    if (kFringe) {
+#pragma unroll
+      for (int o = 1; o < 4; o <<= 1) { c01 += __shfl_xor_sync(0xffffffffu, c01, o); c10 += __shfl_xor_sync(0xffffffffu, c10, o); c11 += __shfl_xor_sync(0xffffffffu, c11, o); }
+      if (kq == 0) atomicAdd(Sb + m + P * 8, -c01);
+      if (kq == 1) atomicAdd(Sb + 8 + P * m, -c10);
+      if (lane == 2) atomicAdd(Sb + 8 + P * 8, -c11);
+    }
   }
 }
 
@@ -970,18 +1052,21 @@ template <int P, int L> static void schurPL(const SchurDev& d, const SystemDev& 
   // The short-track kernel is bound by the L2 reduction rate, the coefficient pass by HBM and the tile kernel by the FP64 pipe: the first
   // runs on the side stream next to the other two (all of them only add into S / b_schur).  Serial when per-kernel timing is on.
   const bool forked = side && side->stream && d.nPairs > 0 && !(marks && marks->begin);
+  const bool kpack = mma && schurKpackEnabled();
   auto pairs = [&](cudaStream_t ps) {
     if (d.nPairs <= 0) return;
-    const int64_t warpsNeeded = d.nPairs; const int nb = (int)((warpsNeeded + 7) / 8 < 148 * 8 * 4 ? (warpsNeeded + 7) / 8 : 148 * 8 * 4);
     MarkScope ms(forked ? nullptr : marks, "schur_pairs");
-    if (d.nPairSegs > 0) { const int nbs = (d.nPairSegs + 7) / 8 < 148 * 8 * 4 ? (d.nPairSegs + 7) / 8 : 148 * 8 * 4; schur_pairs_seg_kernel<P, L><<<nbs, 256, 0, ps>>>(d, sys.Hpl, hplLm); }
-    else schur_pairs_kernel<P, L><<<nb, 256, 0, ps>>>(d, sys.Hpl, hplLm);
+    const double* W = d.Wshort ? d.Wshort : d.W; const int32_t* wIdx = d.Wshort ? d.pairW : d.pairEdgeI;
+    if (d.nPairSegs > 0 && W) { const int nbs = (d.nPairSegs + 7) / 8 < 148 * 8 * 4 ? (d.nPairSegs + 7) / 8 : 148 * 8 * 4; schur_pairs_dmma_kernel<P, L><<<nbs, 256, 0, ps>>>(d, sys.Hpl, W, wIdx); }
+    else if (d.nPairSegs > 0) { const int nbs = (d.nPairSegs + 7) / 8 < 148 * 8 * 4 ? (d.nPairSegs + 7) / 8 : 148 * 8 * 4; schur_pairs_seg_kernel<P, L><<<nbs, 256, 0, ps>>>(d, sys.Hpl, hplLm); }
+    else { const int nb = (int)((d.nPairs + 7) / 8 < 148 * 8 * 4 ? (d.nPairs + 7) / 8 : 148 * 8 * 4); schur_pairs_kernel<P, L><<<nb, 256, 0, ps>>>(d, sys.Hpl, hplLm); }
     *launches += 1;
   };
-  if (forked) { cudaEventRecord(side->fork, st); cudaStreamWaitEvent(side->stream, side->fork, 0); pairs(side->stream); cudaEventRecord(side->join, side->stream); }
-  if (mma && schurKpackEnabled()) launchSchurKpack(d, sys, hplLm, nBlocks, st, launches, marks);
-  else if (mma) launchSchurMma(d, sys, hplLm, nBlocks, st, launches, marks);
+  // coefficient pass first: b_schur, and W of the short tracks for the pair kernel (the older tile path forms all of W in its own pass)
+  if (mma && !kpack) launchSchurMma(d, sys, hplLm, nBlocks, st, launches, marks);
   else if (nBlocks > 0) { MarkScope ms(marks, "schur_coeff"); coeff_kernel<P, L><<<(nBlocks + 127) / 128, 128, 0, st>>>(d, sys.Hpl, hplLm, nBlocks); *launches += 1; }
+  if (forked) { cudaEventRecord(side->fork, st); cudaStreamWaitEvent(side->stream, side->fork, 0); pairs(side->stream); cudaEventRecord(side->join, side->stream); }
+  if (kpack) launchSchurKpack(d, sys, hplLm, nBlocks, st, launches, marks);
   if (!forked) pairs(st);
   if (d.nTileChunks > 0 && !mma) {
     constexpr int kTileSmem = kTileBatch * (kTileCols * ((P * L) | 1) + kTileRows * P * L) * (int)sizeof(double);

@@ -84,31 +84,6 @@ G2D uint32_t ldsU32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0,
 G2D uint32_t uniformOr(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
 G2D int uniformMax(int v) { return __reduce_max_sync(0xffffffffu, v); }
 
-// b_schur[c_k] -= B_k (Dinv_l b_l) for every Hpl block k (block_solver.hpp:366-374): thread per block, blocks staged through shared memory
-// for a coalesced read.  The products W = B Dinv themselves are formed inside the tile kernel.
-template <int P, int L> __global__ void __launch_bounds__(128) schur_coeff_kernel(SchurDev d, const double* __restrict__ Hpl, const int32_t* __restrict__ hplLm, int nBlocks) {
-  constexpr int PLn = P * L;
-  __shared__ double sB[128 * PLn];
-  const int tid = threadIdx.x, k0 = d.blockBegin + blockIdx.x * 128;
-  const int nb = min(128, d.blockBegin + nBlocks - k0);
-  const double* src = Hpl + (size_t)k0 * PLn;
-  for (int t = tid; t < nb * PLn; t += 128) sB[t] = src[t];
-  __syncthreads();
-  if (tid < nb) {
-    const int k = k0 + tid, ci = d.hplRowIdx[k], lm = hplLm[k];
-    double dbv[L];
-#pragma unroll
-    for (int a = 0; a < L; ++a) dbv[a] = d.db[(size_t)lm * L + a];
-    const double* blk = sB + tid * PLn;
-#pragma unroll
-    for (int r = 0; r < P; ++r) {
-      double v = 0;
-#pragma unroll
-      for (int a = 0; a < L; ++a) v += blk[r + P * a] * dbv[a];
-      atomicAdd(d.bschur + (size_t)ci * P + r, -v);
-    }
-  }
-}
 
 template <int P> __global__ void __launch_bounds__(kKpThreads, 1) schur_kpack_kernel(SchurDev d, const double* __restrict__ Hpl) {
   using LY = KpLayout<P>;
@@ -373,11 +348,6 @@ template <int P> __global__ void __launch_bounds__(kKpThreads, 1) schur_kpack_ke
 }  // namespace
 
 template <int P> static void launchKpackP(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, cudaStream_t st, int64_t* launches, const KernelMarks* marks) {
-  if (nBlocks > 0) {
-    if (marks && marks->begin) marks->begin(marks->ctx, "schur_coeff");
-    schur_coeff_kernel<P, 3><<<(nBlocks + 127) / 128, 128, 0, st>>>(d, sys.Hpl, hplLm, nBlocks); *launches += 1;
-    if (marks && marks->end) marks->end(marks->ctx);
-  }
   if (d.nTileChunks > 0) {
     cudaFuncSetAttribute(schur_kpack_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, KpLayout<P>::bytes);   // per device, hence on every call
     if (marks && marks->begin) marks->begin(marks->ctx, "schur_tiles");
@@ -390,7 +360,7 @@ bool schurKpackEnabled() {
   static const bool on = [] { const char* e = getenv("G2OCU_SCHUR_KERNEL"); return !(e && (e[0] == 'm' || e[0] == 'M')); }();
   return on;
 }
-// coefficient pass (b_schur) + K-packed tensor-pipe tile pass; the caller has initialised S / b_schur and computed Dinv / db
+// K-packed tensor-pipe tile pass; the caller has initialised S, computed Dinv and run the coefficient pass (b_schur)
 void launchSchurKpack(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, cudaStream_t st, int64_t* launches, const KernelMarks* marks) {
   if (d.P == 9 && d.L == 3) launchKpackP<9>(d, sys, hplLm, nBlocks, st, launches, marks);
   else if (d.P == 6 && d.L == 3) launchKpackP<6>(d, sys, hplLm, nBlocks, st, launches, marks);
