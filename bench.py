@@ -388,15 +388,17 @@ def run_ours(args):
     bytes_schur = ne_pl * P * L * 8 + npnt * (L * L + L) * 8 + nc * (P * P + P) * 8 + npnt * L * L * 8 + nnzA * P * P * 8 + nc * P * 8
     # Schur product kernels: FP64 pipe.  Algorithmic flops = 2 P P L per (landmark, camera pair i <= j); this rank's landmarks only (sharded runs)
     flops_tiles = flops_pairs = 0.0
-    pairs_all = 0
+    pairs_all = short_blocks = 0
     if schur_graph:
         lm_slot = s.get_i32("hessian_index")[np.asarray(g.e_v0)[pl_edge]] if marg[np.asarray(g.e_v0)[pl_edge][0]] else s.get_i32("hessian_index")[np.asarray(g.e_v1)[pl_edge]]
         k = np.bincount(lm_slot[lm_slot >= 0] - nc, minlength=npnt).astype(np.int64)
         lo, hi = (int(v) for v in s.get_i32("shard_landmark_range")) if world > 1 else (0, npnt)
         k = k[lo:hi]
-        pairs_all = int((k * (k + 1) // 2).sum()); kt = k[k >= 8]; pairs_tiles = int((kt * (kt + 1) // 2).sum())
+        split = int(s.get_i32("tile_min_track")[0])                # tracks below it: pair kernel, the others: tile kernel
+        pairs_all = int((k * (k + 1) // 2).sum()); kt = k[k >= split]; pairs_tiles = int((kt * (kt + 1) // 2).sum())
+        short_blocks = int(k[k < split].sum())
         flops_tiles = 2.0 * P * P * L * pairs_tiles; flops_pairs = 2.0 * P * P * L * (pairs_all - pairs_tiles)
-    bytes_coeff = ne_pl * P * L * 8 + npnt * (L * L + L) * 8 + nc * P * 8        # read Hpl, Dinv, db; update b_schur
+    bytes_coeff = ne_pl * P * L * 8 + npnt * (L * L + L) * 8 + nc * P * 8 + short_blocks * P * L * 8   # read Hpl, Dinv, db; update b_schur; write W of the short tracks
     per = {}
     for name, nbytes in [("pcg_spmv", bytes_spmv), ("build", bytes_build), ("schur", bytes_schur), ("schur_coeff", bytes_coeff)]:
         sec, _, calls = phases[name]
@@ -416,9 +418,9 @@ def run_ours(args):
             per[name] = {"seconds_total": sec, "calls": calls, "avg_ms": 1e3 * sec / calls, "algorithmic_flops": fl, "achieved_tflops": fl / (sec / calls) / 1e12,
                          "frac_of_fp64_peak": fl / (sec / calls) / 1e12 / tpeak}
     mma = P in (6, 9) and L == 3
-    kernels = {"pcg_spmv": f"spmv_tma_kernel<{P}>", "build": "build_pl_kernel + pose_accum_kernel" if ne_pl else "build_pp_kernel", "schur_coeff": f"schur_coeff_kernel<{P},{L}>",
+    kernels = {"pcg_spmv": f"spmv_tma_kernel<{P}>", "build": "build_pl_kernel + pose_accum_kernel" if ne_pl else "build_pp_kernel", "schur_coeff": f"coeff_kernel<{P},{L}>",
                "schur_tiles": (f"schur_mma_kernel<{P},{L}>" if os.environ.get("G2OCU_SCHUR_KERNEL", "").lower().startswith("m") else f"schur_kpack_kernel<{P}>") if mma else f"schur_tile_kernel<{P},{L}>",
-               "schur_pairs": f"schur_pairs_seg_kernel<{P},{L}>"}
+               "schur_pairs": f"schur_pairs_dmma_kernel<{P},{L}>"}
     traffic = {}
     tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if os.path.exists(tp):

@@ -113,6 +113,7 @@ struct g2ocu_solver {
   // CUDA graph of kPcgGraphIters CG iterations (product + one-launch tail, + the peer-memory push when sharded): launched instead of the
   // individual kernels between two convergence polls; re-captured when a kernel argument changes (matrix, lambda, transport)
   cudaGraphExec_t pcgGraph = nullptr; double pcgGraphLambda = 0; bool pcgGraphP2p = false; const double* pcgGraphA = nullptr; int pcgGraphN = 0;
+  int tileMinTrack = kTileMinTrack;                            // tracks with fewer observations go through the pair kernel
   int lastPcgIterations = 0; int64_t totalPcgIterations = 0;   // of the last solve / of all solves since g2ocu_reset_counters
   bool errorsValid = false; double chi2Robust = 0, chi2Plain = 0;
   // estimates of each class form one contiguous run of the packed host array and together cover it: copies go straight between the caller's buffer and the device
@@ -134,7 +135,7 @@ struct g2ocu_solver {
   DVec<double> fr, fd, fq, fs;                                       // full-system PCG vectors r, d, q, s (vectorSize each)
   DVec<double> hsd, hdl, aux;                                        // Dogleg: steepest-descent step, final step, auxiliary vector (vectorSize each)
   DVec<int32_t> mhRow, mhBegin, mhEnd, mhRowPtr, mhColIdx; bool mhReady = false;   // SpMV work items over the Hpp pattern (multiplyHessian in Schur mode)
-  DVec<int32_t> hppDiag, hplColPtr, hplRowIdx, sRowPtr, sColIdx, sDiag, hppToS, pairSlot, pairEdgeI, pairEdgeJ, aRowPtr, aColIdx, aDiag, spRow, spBegin, spEnd, hplLm, tEntLm, tEntBI, tEntBJ, tChunkI, tChunkJ, tChunkB, tChunkE, tChunkSlots, pairSegB, pairSegS, hplShortIdx, pairW;
+  DVec<int32_t> hppDiag, hplColPtr, hplRowIdx, sRowPtr, sColIdx, sDiag, hppToS, pairEdgeI, pairEdgeJ, aRowPtr, aColIdx, aDiag, spRow, spBegin, spEnd, hplLm, tEntLm, tEntBI, tEntBJ, tChunkI, tChunkJ, tChunkB, tChunkE, tChunkSlots, pairSegB, pairSegS, hplShortIdx, pairW;
   DVec<uint32_t> tEntMJ; DVec<uint8_t> tEntMI;
   DVec<int64_t> off64;
   std::vector<EdgeSetState*> sets;
@@ -377,13 +378,16 @@ int buildDevice(g2ocu_solver* s) {
     // long tracks: entries of the output-stationary tile kernel
     const bool useMma = schurMmaSupported(P, L);
     const int tileRows = useMma ? kMmaTileRows : kTileRows;
+    static const int tileMinTrackEnv = [] { const char* e = getenv("G2OCU_TILE_MIN_TRACK"); return e ? atoi(e) : 0; }();   // developer switch
+    const int tileMinTrack = tileMinTrackEnv > 0 ? tileMinTrackEnv : kTileMinTrack;
+    s->tileMinTrack = tileMinTrack;
     struct TileEntry { int64_t key; int32_t lm, baseI, baseJ; uint32_t maskJ; uint8_t maskI; };
     std::vector<TileEntry> entries;
     std::vector<int32_t> shortLm;
     for (int l = st.lmBegin; l < st.lmEnd; ++l) {   // owned landmarks only
       const int cb = st.hplColPtr[l]; const int64_t k = st.hplColPtr[l + 1] - cb;
       if (k == 0) continue;
-      if (k < kTileMinTrack) { shortLm.push_back(l); continue; }
+      if (k < tileMinTrack) { shortLm.push_back(l); continue; }
       struct Run { int32_t tile, base; uint32_t mask; };
       std::vector<Run> rowsR, colsR;
       for (int i = 0; i < k; ++i) {
@@ -434,14 +438,14 @@ int buildDevice(g2ocu_solver* s) {
         CU(cudaStreamSynchronize(stream));
         sd.nPairSegs = (int)segS.size(); sd.pairSegBegin = s->pairSegB.p; sd.pairSegSlot = s->pairSegS.p;
       }
-      CU(s->pairEdgeI.upload(pI, stream)); CU(s->pairEdgeJ.upload(pJ, stream)); CU(s->pairSlot.alloc(std::max<size_t>(pI.size(), 1)));
+      CU(s->pairEdgeI.upload(pI, stream)); CU(s->pairEdgeJ.upload(pJ, stream));
       CU(cudaStreamSynchronize(stream));
-      sd.nPairs = (int64_t)pI.size(); sd.pairEdgeI = s->pairEdgeI.p; sd.pairEdgeJ = s->pairEdgeJ.p; sd.pairSlot = s->pairSlot.p;
+      sd.nPairs = (int64_t)pI.size(); sd.pairEdgeI = s->pairEdgeI.p; sd.pairEdgeJ = s->pairEdgeJ.p;
       // W = B Dinv of the short tracks' blocks is formed by the coefficient pass for the pair kernel: compact index per Hpl block (in block
       // order, so that the pass writes it front to back), and per pair the index of its row-side block.  (The older tile path forms all of W.)
       if (!pI.empty() && !(useMma && !schurKpackEnabled())) {
         std::vector<int32_t> shortIdx(st.hplRowIdx.size(), -1); int32_t nShort = 0;
-        for (int l = st.lmBegin; l < st.lmEnd; ++l) { const int cb = st.hplColPtr[l], ce = st.hplColPtr[l + 1]; if (ce - cb > 0 && ce - cb < kTileMinTrack) for (int k = cb; k < ce; ++k) shortIdx[k] = nShort++; }
+        for (int l = st.lmBegin; l < st.lmEnd; ++l) { const int cb = st.hplColPtr[l], ce = st.hplColPtr[l + 1]; if (ce - cb > 0 && ce - cb < tileMinTrack) for (int k = cb; k < ce; ++k) shortIdx[k] = nShort++; }
         std::vector<int32_t> pW(pI.size());
         for (size_t k = 0; k < pI.size(); ++k) pW[k] = shortIdx[pI[k]];
         CU(s->hplShortIdx.upload(shortIdx, stream)); CU(s->pairW.upload(pW, stream)); CU(s->Wshort.alloc((size_t)nShort * P * L + 2)); CU(s->Wshort.zero(stream));
@@ -503,7 +507,6 @@ int buildDevice(g2ocu_solver* s) {
     sd.hplColPtr = s->hplColPtr.p; sd.hplRowIdx = s->hplRowIdx.p; sd.sRowPtr = s->sRowPtr.p; sd.sColIdx = s->sColIdx.p; sd.sDiag = s->sDiag.p;
     sd.hppToS = s->hppToS.p; sd.nnzHpp = (int)st.hppColIdx.size(); sd.nnzS = (int)st.sColIdx.size();
     sd.S = s->S.p; sd.Dinv = s->Dinv.p; sd.db = s->dbv.p; sd.bschur = s->bschur.p;
-    launchPairSlots(sd, stream, &s->launches);
     CU(cudaStreamSynchronize(stream));
   }
   // ---- PCG structures over A = Hschur (Schur) or Hpp ----
@@ -1454,6 +1457,7 @@ int64_t g2ocu_get_i32(g2ocu_solver* s, const char* name, int32_t* out, int64_t c
     if (n == "full_system_permutation") return copyOutI32(st.refToInternal, out, cap);
     if (n == "internal_dims") return copyOutI32({st.numPoses, st.numLandmarks, st.sizePoses, st.sizeLandmarks}, out, cap);
   }
+  if (n == "tile_min_track") return copyOutI32({s->tileMinTrack}, out, cap);
   if (n == "dims" || n == "internal_dims") return copyOutI32({st.numPoses, st.numLandmarks, st.sizePoses, st.sizeLandmarks}, out, cap);
   if (n == "pose_block_indices") return copyOutI32(st.poseBlockIndices, out, cap);
   if (n == "landmark_block_indices") return copyOutI32(st.landmarkBlockIndices, out, cap);

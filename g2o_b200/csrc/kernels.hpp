@@ -57,9 +57,9 @@ struct SchurDev {
   const int32_t* hplColPtr = nullptr; const int32_t* hplRowIdx = nullptr;
   const int32_t* sRowPtr = nullptr; const int32_t* sColIdx = nullptr; const int32_t* sDiag = nullptr;
   const int32_t* hppToS = nullptr; int nnzHpp = 0; int nnzS = 0;
-  // short tracks: flat list of (Hpl block i, Hpl block j, Hschur block) per pair i <= j, atomics
-  int64_t nPairs = 0; const int32_t* pairEdgeI = nullptr; const int32_t* pairEdgeJ = nullptr; int32_t* pairSlot = nullptr;
-  // the same pairs sorted by target Hschur block and cut into segments of <= kPairSegment pairs of one block: a warp sums a segment in registers, one RED per element
+  // short tracks: flat list of (Hpl block i, Hpl block j) per pair i <= j, sorted by target Hschur block and cut into segments of <= kPairSegment
+  // pairs of one block: a warp forms a segment's sum as one K-stacked DMMA product, one RED per element
+  int64_t nPairs = 0; const int32_t* pairEdgeI = nullptr; const int32_t* pairEdgeJ = nullptr;
   int nPairSegs = 0; const int32_t* pairSegBegin = nullptr; const int32_t* pairSegSlot = nullptr;
   // W = B Dinv of the blocks of short tracks, formed by the coefficient pass: compact index of every Hpl block (-1: long track), the W blocks
   // in that order, and per pair the compact index of its row-side block
@@ -82,8 +82,7 @@ void launchSchurMma(const SchurDev& d, const SystemDev& sys, const int32_t* hplL
 void launchSchurKpack(const SchurDev& d, const SystemDev& sys, const int32_t* hplLm, int nBlocks, cudaStream_t st, int64_t* launches, const KernelMarks* marks);
 bool schurKpackEnabled();
 static const int kPairSegment = 16;               // pairs per segment of the short-track kernel
-static const int kTileMinTrack = 8;               // landmarks with at least this many observations go through the tile kernel
-void launchPairSlots(const SchurDev& d, cudaStream_t st, int64_t* launches);
+static const int kTileMinTrack = 16;              // landmarks with at least this many observations go through the tile kernel
 // optional per-kernel timing hooks: begin(ctx, name) / end(ctx) bracket one kernel (CUDA events on the launching stream in api.cu)
 struct KernelMarks { void* ctx = nullptr; void (*begin)(void*, const char*) = nullptr; void (*end)(void*) = nullptr; };
 // a second stream of the solver + two events: independent kernels of one phase are forked onto it and joined before the phase ends

@@ -66,16 +66,6 @@ template <> G2D void invSmall<3>(const double* A, double* X) {
   X[6] = (A[3] * A[7] - A[6] * A[4]) * id; X[7] = (A[6] * A[1] - A[0] * A[7]) * id; X[8] = (A[0] * A[4] - A[3] * A[1]) * id;
 }
 
-// ------------------------------------------------------------------------------------------------
-// one-time: Hschur block index of every short-track pair (binary search in the CSR row of the first camera)
-__global__ void pair_slot_kernel(SchurDev d) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= d.nPairs) return;
-  const int ci = d.hplRowIdx[d.pairEdgeI[p]], cj = d.hplRowIdx[d.pairEdgeJ[p]];
-  int lo = d.sRowPtr[ci], hi = d.sRowPtr[ci + 1];
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (d.sColIdx[mid] < cj) lo = mid + 1; else hi = mid; }
-  d.pairSlot[p] = lo;
-}
 
 template <int P> __global__ void schur_init_kernel(SchurDev d, const double* Hpp, const double* b, double lambda) {
   constexpr int PP = P * P;
@@ -165,75 +155,11 @@ __device__ __forceinline__ void pairDmma(double (&c)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// Short tracks: Hschur(ci,cj) -= B_i Dinv B_j^T with one atomic add per element; warp per pair over a flat pair list
-// (ordered by first camera so that concurrently running warps hit an L2-resident band of Hschur).
-template <int P, int L> __global__ void __launch_bounds__(256) schur_pairs_kernel(SchurDev d, const double* __restrict__ Hpl, const int32_t* __restrict__ hplLm) {
-  constexpr int PP = P * P, PLn = P * L, LL = L * L;
-  constexpr int NR = (PP + 31) / 32;
-  const int lane = threadIdx.x & 31;
-  const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < d.nPairs; p += nWarps) {
-    const int eI = d.pairEdgeI[p], eJ = d.pairEdgeJ[p], slot = d.pairSlot[p];
-    const int lm = hplLm[eI];
-    const double* Bi = Hpl + (size_t)eI * PLn; const double* Bj = Hpl + (size_t)eJ * PLn;
-    // lane t < P*L holds (B_i Dinv)[r, a] with r = t % P, a = t / P
-    double bd = 0;
-    if (lane < PLn) {
-      const int r = lane % P, a = lane / P;
-#pragma unroll
-      for (int a2 = 0; a2 < L; ++a2) bd += Bi[r + P * a2] * d.Dinv[(size_t)lm * LL + a2 + L * a];
-    }
-    double* Sb = d.S + (size_t)slot * PP;
-#pragma unroll
-    for (int q = 0; q < NR; ++q) {
-      const int el = lane + 32 * q; const int r = el % P, c = el / P;
-      double v = 0;
-#pragma unroll
-      for (int a = 0; a < L; ++a) { const double w = __shfl_sync(0xffffffffu, bd, (r + P * a) & 31); if (el < PP) v += w * Bj[c + P * a]; }
-      if (el < PP) atomicAdd(Sb + el, -v);
-    }
-  }
-}
-
-// Short tracks, segmented: the pair list is sorted by target block on the host (the short tracks of a ring of cameras hit a narrow band
-// of Hschur: 5.8 M pairs fall on 30 k blocks on C3) and cut into segments of <= kPairSegment pairs of one block; a warp sums its
-// segment in registers and issues one RED per element per segment instead of per pair - the L2 reduction rate that bounded the kernel
-// above (470 M REDs) is out of the way, what remains is the read of the two Hpl blocks of every pair.
-template <int P, int L> __global__ void __launch_bounds__(256) schur_pairs_seg_kernel(SchurDev d, const double* __restrict__ Hpl, const int32_t* __restrict__ hplLm) {
-  constexpr int PP = P * P, PLn = P * L, LL = L * L;
-  constexpr int NR = (PP + 31) / 32;
-  const int lane = threadIdx.x & 31;
-  const int nWarps = gridDim.x * (blockDim.x >> 5);
-  for (int sgm = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); sgm < d.nPairSegs; sgm += nWarps) {
-    const int pb = d.pairSegBegin[sgm], pe = d.pairSegBegin[sgm + 1];
-    double acc[NR];
-#pragma unroll
-    for (int q = 0; q < NR; ++q) acc[q] = 0;
-    for (int p = pb; p < pe; ++p) {
-      const int eI = d.pairEdgeI[p], eJ = d.pairEdgeJ[p];
-      const int lm = hplLm[eI];
-      const double* Bi = Hpl + (size_t)eI * PLn; const double* Bj = Hpl + (size_t)eJ * PLn;
-      double bd = 0;                                   // lane t < P*L holds (B_i Dinv)[r, a] with r = t % P, a = t / P
-      if (lane < PLn) {
-        const int r = lane % P, a = lane / P;
-#pragma unroll
-        for (int a2 = 0; a2 < L; ++a2) bd += Bi[r + P * a2] * d.Dinv[(size_t)lm * LL + a2 + L * a];
-      }
-#pragma unroll
-      for (int q = 0; q < NR; ++q) {
-        const int el = lane + 32 * q; const int r = el % P, c = el / P;
-        double v = 0;
-#pragma unroll
-        for (int a = 0; a < L; ++a) { const double w = __shfl_sync(0xffffffffu, bd, (r + P * a) & 31); if (el < PP) v += w * Bj[c + P * a]; }
-        acc[q] += v;
-      }
-    }
-    double* Sb = d.S + (size_t)d.pairSegSlot[sgm] * PP;
-#pragma unroll
-    for (int q = 0; q < NR; ++q) { const int el = lane + 32 * q; if (el < PP) atomicAdd(Sb + el, -acc[q]); }
-  }
-}
-
+// Short tracks (fewer than kTileMinTrack observations): the pairs (block i, block j), i <= j, of every such landmark are sorted by target
+// Hschur block on the host (the short tracks of a ring of cameras hit a narrow band of Hschur: 5.8 M pairs fall on 30 k blocks on C3) and cut
+// into segments of <= kPairSegment pairs of one block.  Earlier forms of this kernel: a warp per pair with one RED per element per pair
+// (round 1: 470 M REDs, bound by the L2 reduction rate, 1.55 ms on C3), then a warp per segment summing scalar products in registers
+// (1.25 ms, 86 % of the L1 pipe: 18 loads + 12 FMAs + 9 shuffles per pair).
 // Short tracks on the FP64 tensor pipe: the pairs of a segment all add into one block, Hschur(i,j) -= sum_p W_p B_p^T, which is one small GEMM
 // with the pairs stacked along K (L scalars each, <= kPairSegment pairs: K <= 48).  One warp per segment; per K step of 4 a lane fetches one
 // scalar of W (row m of the pair its K slot belongs to, from the coefficient pass) and one of B_j and issues the DMMA of rows / columns
@@ -1028,11 +954,6 @@ void launchHplMult(const double* Hpl, const int32_t* hplRow, const int32_t* hplL
   hpl_mult_kernel<<<(nBlocks + 127) / 128, 128, 0, st>>>(Hpl, hplRow, hplLm, nBlocks, P, L, dp, dl, qp, ql);
   *launches += 1;
 }
-void launchPairSlots(const SchurDev& d, cudaStream_t st, int64_t* launches) {
-  if (d.nPairs == 0) return;
-  pair_slot_kernel<<<(unsigned)((d.nPairs + 255) / 256), 256, 0, st>>>(d);
-  *launches += 1;
-}
 
 struct MarkScope {
   const KernelMarks* m;
@@ -1054,12 +975,11 @@ template <int P, int L> static void schurPL(const SchurDev& d, const SystemDev& 
   const bool forked = side && side->stream && d.nPairs > 0 && !(marks && marks->begin);
   const bool kpack = mma && schurKpackEnabled();
   auto pairs = [&](cudaStream_t ps) {
-    if (d.nPairs <= 0) return;
+    if (d.nPairSegs <= 0) return;
     MarkScope ms(forked ? nullptr : marks, "schur_pairs");
     const double* W = d.Wshort ? d.Wshort : d.W; const int32_t* wIdx = d.Wshort ? d.pairW : d.pairEdgeI;
-    if (d.nPairSegs > 0 && W) { const int nbs = (d.nPairSegs + 7) / 8 < 148 * 8 * 4 ? (d.nPairSegs + 7) / 8 : 148 * 8 * 4; schur_pairs_dmma_kernel<P, L><<<nbs, 256, 0, ps>>>(d, sys.Hpl, W, wIdx); }
-    else if (d.nPairSegs > 0) { const int nbs = (d.nPairSegs + 7) / 8 < 148 * 8 * 4 ? (d.nPairSegs + 7) / 8 : 148 * 8 * 4; schur_pairs_seg_kernel<P, L><<<nbs, 256, 0, ps>>>(d, sys.Hpl, hplLm); }
-    else { const int nb = (int)((d.nPairs + 7) / 8 < 148 * 8 * 4 ? (d.nPairs + 7) / 8 : 148 * 8 * 4); schur_pairs_kernel<P, L><<<nb, 256, 0, ps>>>(d, sys.Hpl, hplLm); }
+    const int nbs = (d.nPairSegs + 7) / 8 < 148 * 8 * 4 ? (d.nPairSegs + 7) / 8 : 148 * 8 * 4;
+    schur_pairs_dmma_kernel<P, L><<<nbs, 256, 0, ps>>>(d, sys.Hpl, W, wIdx);
     *launches += 1;
   };
   // coefficient pass first: b_schur, and W of the short tracks for the pair kernel (the older tile path forms all of W in its own pass)

@@ -234,6 +234,8 @@ int g2ocu_get_estimates(g2ocu_solver* s, double* host_packed);
  *        "landmark_block_indices" "hpp_colptr" "hpp_rowidx" "hpl_colptr" "hpl_rowidx" "hschur_colptr" "hschur_rowidx"
  *        "hschur_t_colptr" "hschur_t_rowidx" "edge_targets" "shard_landmark_range" "shard_edge_positions"
  *        "linear_solver_iterations" (1 element: PCG iterations of the last g2ocu_solve, G2OBatchStatistics::iterationsLinearSolver)
+ *        "tile_min_track" (1 element: landmarks with fewer observations go through the pair kernel of the Schur product, the others through
+ *        the tile kernel - an implementation split the benchmark needs for its per-kernel flop counts)
  *        (graphs with poses and points of which none is marginalized - BlockSolverX with two block sizes: "dims",
  *        "pose_block_indices", "hpp_colptr", "hpp_rowidx", "edge_targets" describe the reference's single Hpp over all
  *        vertices in id order; "full_system_permutation" maps a scalar index of its x / b to the internal [poses | points]
