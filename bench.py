@@ -320,16 +320,20 @@ def run_ours(args):
         s.set_estimates(est0)
         s.init()
         host_in, host_out = pin_in.numpy(), pin_out.numpy()      # two pinned host buffers used in turn: a step's output is the next step's input
+        # landmark shards: a rank moves every pose and ITS landmarks (it never reads the others); the job as a whole moves every estimate once per step
+        sharded = world > 1 and schur_graph
+        put = s.set_estimates_owned if sharded else s.set_estimates
+        get = s.get_estimates_owned if sharded else s.get_estimates
         stats = []
         for i in range(args.warmup):
             if flush is not None:
                 with torch.cuda.stream(stream):
                     flush.zero_()
             if e2e:
-                s.set_estimates(host_in)
+                put(host_in)
             stats.append(s.solver_iteration(i))
             if e2e:
-                s.get_estimates(host_out); host_in, host_out = host_out, host_in
+                get(host_out); host_in, host_out = host_out, host_in
         s.reset_counters()
         sampler = ClockSampler(local); sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -342,10 +346,10 @@ def run_ours(args):
                 with torch.cuda.stream(stream):
                     flush.zero_()                              # L2 flush (the workload fits the 126 MB L2)
             if e2e:
-                s.set_estimates(host_in)                       # H2D of this step's inputs (pinned)
+                put(host_in)                                   # H2D of this step's inputs (pinned)
             stats.append(s.solver_iteration(i))
             if e2e:
-                s.get_estimates(host_out); host_in, host_out = host_out, host_in   # D2H of the step's result (estimates + chi2); it feeds the next step
+                get(host_out); host_in, host_out = host_out, host_in   # D2H of the step's result (estimates + chi2); it feeds the next step
         ev1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
@@ -362,10 +366,17 @@ def run_ours(args):
     s.set_property("kernelTiming", 1.0)                         # breakdown pass: the same steps with CUDA events around every kernel
     dt_k, _, _, phases, _ = timed_run(False)
     s.set_property("kernelTiming", 0.0)
+    rank_phases = None
     if world > 1:
         t = torch.tensor([dt, dt_e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt, dt_e = float(t[0]), float(t[1])
+        # every rank's own breakdown (rank 0's phases include its waits for the slower ranks): milliseconds per step
+        names = ["build", "schur_coeff", "schur_pairs", "schur_tiles", "schur_exchange", "pcg_spmv", "pcg_vec", "backsub"]
+        mine = torch.tensor([phases[n][0] for n in names], device="cuda", dtype=torch.float64)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        rank_phases = {n: [round(1e3 * float(every[r][i]) / args.steps, 4) for r in range(world)] for i, n in enumerate(names)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -382,10 +393,6 @@ def run_ours(args):
     Sp = (len(g.v_estimate) - 3 * int(marg.sum() if L == 3 else 0) - 2 * int(marg.sum() if L == 2 else 0)) // max(int((~marg).sum()), 1)   # stored pose estimate size
     nnzA = int(s.get_i32("hschur_colptr")[-1]) if schur_graph else int(s.get_i32("hpp_colptr")[-1])
     peak, peak_src = measured_peaks()
-    # algorithmic bytes per launch for block sizes P, L and error dimensions E
-    bytes_spmv = nnzA * P * P * 8 + nc * P * P * 8 + 10 * nc * P * 8
-    bytes_build = ne_pl * (E_pl * 8 + 8 + P * L * 8) + ne_pp * (M_pp * 8 + 8 + P * P * 8) + npnt * (L * 8 + L * L * 8 + L * 8) + nc * (Sp * 8 + P * P * 8 + P * 8)
-    bytes_schur = ne_pl * P * L * 8 + npnt * (L * L + L) * 8 + nc * (P * P + P) * 8 + npnt * L * L * 8 + nnzA * P * P * 8 + nc * P * 8
     # Schur product kernels: FP64 pipe.  Algorithmic flops = 2 P P L per (landmark, camera pair i <= j); this rank's landmarks only (sharded runs)
     flops_tiles = flops_pairs = 0.0
     pairs_all = short_blocks = 0
@@ -398,6 +405,12 @@ def run_ours(args):
         pairs_all = int((k * (k + 1) // 2).sum()); kt = k[k >= split]; pairs_tiles = int((kt * (kt + 1) // 2).sum())
         short_blocks = int(k[k < split].sum())
         flops_tiles = 2.0 * P * P * L * pairs_tiles; flops_pairs = 2.0 * P * P * L * (pairs_all - pairs_tiles)
+        if world > 1:                                              # landmark shards: this rank builds and eliminates its own points and their edges only
+            ne_pl, npnt = int(k.sum()), hi - lo
+    # algorithmic bytes per launch ON THIS RANK for block sizes P, L and error dimensions E
+    bytes_spmv = nnzA * P * P * 8 + nc * P * P * 8 + 10 * nc * P * 8
+    bytes_build = ne_pl * (E_pl * 8 + 8 + P * L * 8) + ne_pp * (M_pp * 8 + 8 + P * P * 8) + npnt * (L * 8 + L * L * 8 + L * 8) + nc * (Sp * 8 + P * P * 8 + P * 8)
+    bytes_schur = ne_pl * P * L * 8 + npnt * (L * L + L) * 8 + nc * (P * P + P) * 8 + npnt * L * L * 8 + nnzA * P * P * 8 + nc * P * 8
     bytes_coeff = ne_pl * P * L * 8 + npnt * (L * L + L) * 8 + nc * P * 8 + short_blocks * P * L * 8   # read Hpl, Dinv, db; update b_schur; write W of the short tracks
     per = {}
     for name, nbytes in [("pcg_spmv", bytes_spmv), ("build", bytes_build), ("schur", bytes_schur), ("schur_coeff", bytes_coeff)]:
@@ -440,7 +453,7 @@ def run_ours(args):
         roof = {"kernel": kernels[dominant], "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": traffic.get(kernels[dominant]), "peak_source": peak_src,
                 "avg_launch_ms": per[dominant].get("avg_ms_active", per[dominant]["avg_ms"]), "phases": per}
     value = args.steps / dt
-    est_bytes = int(est0.nbytes)
+    est_bytes = int(est0.nbytes) + ((world - 1) * nc * Sp * 8 if world > 1 and schur_graph else 0)   # landmark shards: every rank moves all poses and its own landmarks
     ws = working_set_mb
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -449,9 +462,11 @@ def run_ours(args):
                             "l2_policy": ("working set (Hpl + reduced system = %.0f MB) exceeds the 126 MB L2" % ws) if ws > 126 else
                                          ("working set (%.1f MB) fits the 126 MB L2; 256 MB are written between timed iterations to flush it" % ws)},
             "e2e": {"value": args.steps / dt_e, "unit": UNIT, "h2d_bytes_per_step": est_bytes, "d2h_bytes_per_step": est_bytes + 8,
-                    "note": "per step: host vertex estimates -> device (pinned), one LM iteration through g2ocu_solver_iteration, estimates + chi2 back to the host"},
+                    "note": "per step: host vertex estimates -> device (pinned), one LM iteration through g2ocu_solver_iteration, estimates + chi2 back to the host" +
+                            ("; bytes are the job's total: every rank moves all poses and its own landmark range (g2ocu_set_estimates_owned / g2ocu_get_estimates_owned)" if world > 1 and schur_graph else "")},
             "gpu_launches": int(launches), "active_products": int(active_products), "clocks": clocks, "roofline": roof,
             "phase_ms_per_step": {ph: round(1e3 * v[0] / args.steps, 4) for ph, v in phases.items()},
+            **({"phase_ms_per_step_by_rank": rank_phases} if rank_phases else {}),
             "phase_note": "from a separate pass of the same steps with per-kernel CUDA events (%.3f ms per step in that pass)" % (1e3 * dt_k / args.steps),
             "lm": {"chi2": [st["chi2"] for st in stats], "lambda": [st["lambda"] for st in stats], "trials": [st["levenberg_iterations"] for st in stats],
                    "pcg_iterations": [st["iterations_linear_solver"] for st in stats]}}

@@ -42,7 +42,7 @@ EXPORTS = ["g2ocu_default_config", "g2ocu_version", "g2ocu_last_error", "g2ocu_c
            "g2ocu_compute_active_errors", "g2ocu_active_robust_chi2", "g2ocu_active_chi2", "g2ocu_build_system",
            "g2ocu_set_lambda", "g2ocu_restore_diagonal", "g2ocu_solve", "g2ocu_update", "g2ocu_push", "g2ocu_pop",
            "g2ocu_discard_top", "g2ocu_compute_lambda_init", "g2ocu_compute_scale", "g2ocu_multiply_hessian", "g2ocu_compute_marginals",
-           "g2ocu_solver_iteration", "g2ocu_optimize", "g2ocu_vector_size", "g2ocu_set_estimates", "g2ocu_get_estimates",
+           "g2ocu_solver_iteration", "g2ocu_optimize", "g2ocu_vector_size", "g2ocu_set_estimates", "g2ocu_get_estimates", "g2ocu_set_estimates_owned", "g2ocu_get_estimates_owned",
            "g2ocu_get_i32", "g2ocu_get_f64", "g2ocu_launch_count", "g2ocu_phase_time", "g2ocu_reset_counters",
            "g2ocu_linear_create", "g2ocu_linear_destroy", "g2ocu_linear_last_error", "g2ocu_linear_init", "g2ocu_linear_set_property", "g2ocu_linear_solve"]
 
@@ -80,7 +80,7 @@ def lib() -> ctypes.CDLL:
         "g2ocu_solver_iteration": (ctypes.c_int, [vp, i32, i32, P(IterationStats)]),
         "g2ocu_optimize": (ctypes.c_int, [vp, i32, i32, P(IterationStats), P(i32)]),
         "g2ocu_vector_size": (i64, [vp]), "g2ocu_set_estimates": (ctypes.c_int, [vp, vp]),
-        "g2ocu_get_estimates": (ctypes.c_int, [vp, vp]), "g2ocu_get_i32": (i64, [vp, ctypes.c_char_p, vp, i64]),
+        "g2ocu_get_estimates": (ctypes.c_int, [vp, vp]), "g2ocu_set_estimates_owned": (ctypes.c_int, [vp, vp]), "g2ocu_get_estimates_owned": (ctypes.c_int, [vp, vp]), "g2ocu_get_i32": (i64, [vp, ctypes.c_char_p, vp, i64]),
         "g2ocu_get_f64": (i64, [vp, ctypes.c_char_p, vp, i64]), "g2ocu_launch_count": (i64, [vp]),
         "g2ocu_phase_time": (ctypes.c_int, [vp, ctypes.c_char_p, P(dbl), P(i64), P(i64)]), "g2ocu_reset_counters": (ctypes.c_int, [vp]),
         "g2ocu_linear_create": (ctypes.c_int, [P(Config), P(vp)]), "g2ocu_linear_destroy": (None, [vp]), "g2ocu_linear_last_error": (ctypes.c_char_p, [vp]),

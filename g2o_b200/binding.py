@@ -232,6 +232,18 @@ class CudaSolver:
         self._ck(self._L.g2ocu_get_estimates(self._h, out.ctypes.data_as(ctypes.c_void_p)))
         return out
 
+    def set_estimates_owned(self, est):
+        """Sharded runs: upload every pose and this rank's own landmark range only (``g2ocu_set_estimates_owned``)."""
+        est = np.ascontiguousarray(est, dtype=np.float64)
+        if est.shape[0] != self.graph.v_estimate.shape[0]:
+            raise ValueError("estimate vector has the wrong length")
+        self._ck(self._L.g2ocu_set_estimates_owned(self._h, est.ctypes.data_as(ctypes.c_void_p)))
+
+    def get_estimates_owned(self, out: np.ndarray) -> np.ndarray:
+        """Sharded runs: read back every pose and this rank's own landmark range into ``out``; the other entries are left as they are."""
+        self._ck(self._L.g2ocu_get_estimates_owned(self._h, out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
     def get_i32(self, name: str) -> np.ndarray:
         n = self._ck(self._L.g2ocu_get_i32(self._h, name.encode(), None, 0))
         out = np.zeros(n, dtype=np.int32)

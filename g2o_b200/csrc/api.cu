@@ -1434,6 +1434,35 @@ int g2ocu_get_estimates(g2ocu_solver* s, double* host) {
   return G2OCU_OK;
 }
 
+// Landmark-sharded runs: the same two transfers restricted to what this rank works on - every pose estimate and the estimates of its own
+// landmark range [lmBegin, lmEnd).  A rank never reads the other landmarks (its edges are those of its own landmarks), so the job's host
+// side moves every estimate once per step instead of once per rank, and the result needs no all-gather.
+int g2ocu_set_estimates_owned(g2ocu_solver* s, const double* host) {
+  if (!s || !host) return G2OCU_E_INVALID;
+  if (!s->hasGraph) return fail(s, G2OCU_E_INVALID, "no graph set");
+  if (!(s->structureBuilt && s->fastEstimates) || s->world <= 1) return g2ocu_set_estimates(s, host);
+  const Structure& st = s->st;
+  CU(cudaMemcpyAsync(s->poseEst.p, host + s->poseHostOff, s->poseEst.n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  if (st.lmEnd > st.lmBegin) {
+    const size_t Sl = vertexEstimateDim(st.lmType), off = (size_t)st.lmBegin * Sl, cnt = (size_t)(st.lmEnd - st.lmBegin) * Sl;
+    CU(cudaMemcpyAsync(s->lmEst.p + off, host + s->lmHostOff + off, cnt * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  }
+  s->errorsValid = false;
+  return syncStream(s);
+}
+int g2ocu_get_estimates_owned(g2ocu_solver* s, double* host) {
+  if (!s || !host) return G2OCU_E_INVALID;
+  if (!s->hasGraph) return fail(s, G2OCU_E_INVALID, "no graph set");
+  if (!(s->structureBuilt && s->fastEstimates) || s->world <= 1) return g2ocu_get_estimates(s, host);
+  const Structure& st = s->st;
+  CU(cudaMemcpyAsync(host + s->poseHostOff, s->poseEst.p, s->poseEst.n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (st.lmEnd > st.lmBegin) {
+    const size_t Sl = vertexEstimateDim(st.lmType), off = (size_t)st.lmBegin * Sl, cnt = (size_t)(st.lmEnd - st.lmBegin) * Sl;
+    CU(cudaMemcpyAsync(host + s->lmHostOff + off, s->lmEst.p + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  }
+  return syncStream(s);
+}
+
 static int64_t copyOutI32(const std::vector<int32_t>& v, int32_t* out, int64_t cap) { if (out) std::memcpy(out, v.data(), sizeof(int32_t) * (size_t)std::min<int64_t>(cap, (int64_t)v.size())); return (int64_t)v.size(); }
 
 int64_t g2ocu_get_i32(g2ocu_solver* s, const char* name, int32_t* out, int64_t cap) {

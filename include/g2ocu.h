@@ -227,6 +227,12 @@ int g2ocu_optimize(g2ocu_solver* s, int32_t algorithm, int32_t iterations, g2ocu
 int64_t g2ocu_vector_size(const g2ocu_solver* s);
 int g2ocu_set_estimates(g2ocu_solver* s, const double* host_packed);
 int g2ocu_get_estimates(g2ocu_solver* s, double* host_packed);
+/* Landmark-sharded runs (g2ocu_set_shard*): the same two transfers restricted to what this rank works on - every pose estimate and the
+ * estimates of its own landmark range ("shard_landmark_range"); the other entries of host_packed are neither read nor written, and the
+ * read-back needs no all-gather.  The job's host side then moves every estimate once per step instead of once per rank.  Without a
+ * shard they are g2ocu_set_estimates / g2ocu_get_estimates. */
+int g2ocu_set_estimates_owned(g2ocu_solver* s, const double* host_packed);
+int g2ocu_get_estimates_owned(g2ocu_solver* s, double* host_packed);
 
 /* Named array read-back (structure arrays for the bit-exact check of SURVEY.md Appendix B, block values, vectors).
  * Returns the number of elements the array has (and fills at most `capacity` of them), or a negative status.

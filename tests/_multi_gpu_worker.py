@@ -45,6 +45,21 @@ def main():
             err = np.max(np.abs(est - estr) / (1 + np.abs(estr)))
             assert err < 1e-5, (name, err)   # both sides stop PCG at a relative residual of 1e-6
             print(f"{name}: sharded x{world} matches single GPU, chi2 {st[-1]['chi2']:.6f}, max rel est diff {err:.2e}", flush=True)
+        # the shard-restricted transfers: the ranks' read-backs, each into a buffer of NaNs, tile the complete vector (poses on every rank, a
+        # landmark on exactly one); uploading them again changes nothing
+        own = np.full_like(est, np.nan); s.get_estimates_owned(own)
+        have = ~np.isnan(own)
+        assert np.array_equal(own[have], est[have]), name
+        cover = torch.from_numpy(have.astype(np.int32)).cuda(); dist.all_reduce(cover)
+        marg = np.repeat(np.asarray(g.v_marginalized, dtype=bool), np.diff(g.estimate_offsets()))
+        restricted = torch.tensor([int((~have).any())], device="cuda"); dist.all_reduce(restricted, op=dist.ReduceOp.MIN)
+        if name == "bal":
+            assert int(restricted) == 1, "the BAL case must take the shard-restricted path"
+        if int(restricted):                    # (graphs with inactive vertices fall back to the complete transfer)
+            assert bool((cover.cpu().numpy()[marg] == 1).all()) and bool((cover.cpu().numpy()[~marg] == world).all()), name
+        s.set_estimates_owned(np.where(have, own, 0.0)); s.compute_active_errors()
+        chi_after = s.active_robust_chi2()
+        assert abs(chi_after - st[-1]["chi2"]) <= 1e-9 * abs(st[-1]["chi2"]), (name, chi_after, st[-1]["chi2"])
         # all ranks hold the same complete estimate vector
         t = torch.from_numpy(est.copy()).cuda()
         lo, hi = t.clone(), t.clone()
