@@ -27,6 +27,8 @@ def build(force: bool = False) -> None:
     stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if stale:
         subprocess.run(["make", "-C", _HERE, os.path.join(_HERE, "liboracle.so")] + (["-B"] if force else []), check=True, capture_output=True)
+    # the Eigen stand-in's own algorithms as a probe library (checked against numpy / scipy in tests/test_reference_leaves.py); no dependency
+    subprocess.run(["make", "-C", _HERE, os.path.join(_HERE, "libshim_probe.so")], check=True, capture_output=True)
     # pieces of the reference itself, compiled from /root/reference when that tree is present (the GPU box only has the prebuilt files).  A failure
     # here must not take the oracle down with it: the tests that need these libraries skip when they are missing.
     if not os.path.isdir("/root/reference/g2o/core"):
@@ -96,6 +98,17 @@ def lib() -> ctypes.CDLL:
 
 
 _LEAVES = None
+
+
+def shim_probe() -> ctypes.CDLL:
+    """oracle/libshim_probe.so: the numerical routines of oracle/eigen_shim (the stand-in the reference is compiled against), one export each."""
+    build()
+    L = ctypes.CDLL(os.path.join(_HERE, "libshim_probe.so"))
+    L.shim_determinant.restype = ctypes.c_double
+    L.shim_determinant.argtypes = [ctypes.c_int, ctypes.c_void_p]
+    L.shim_angle_axis_R.argtypes = [ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
+    L.shim_rotation2d.argtypes = [ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    return L
 
 
 def reference_leaves():

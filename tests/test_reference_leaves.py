@@ -227,3 +227,67 @@ def test_pcg_matches_the_reference_solver(name):
     ok, x_r, it_r = ref.solve(o2.get_i32("pose_block_indices"), o2.get_i32(names[0]), o2.get_i32(names[1]), o2.get_f64(names[2]), o2.get_f64(names[3]), tol=1e-12, absolute=False)
     assert it_r == int(o2.get_f64("pcg_state")[1])
     assert np.max(np.abs(o2.get_f64("x")[:len(x_r)] - x_r)) <= 1e-10 * np.max(np.abs(x_r))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# The Eigen stand-in against independent implementations.  The reference under oracle/_ref is compiled against oracle/eigen_shim, which
+# restates the Eigen algorithms the path calls; the oracle restates them too.  These tests pin the stand-in's routines (exported one by one
+# by oracle/shim_probe.cpp) to LAPACK (numpy) and to scipy's Rotation, so that an error common to both restatements cannot hide.
+def _p(a):
+    return a.ctypes.data_as(__import__("ctypes").c_void_p)
+
+
+def test_stand_in_inverse_determinant_and_llt_against_lapack():
+    L = oracle.shim_probe()
+    rng = np.random.default_rng(11)
+    for n in (2, 3, 6, 7, 9):
+        for trial in range(20):
+            A = rng.normal(size=(n, n)); S = A @ A.T + (0.1 + trial) * np.eye(n)          # general and SPD, well and less well conditioned
+            for M in (A, S):
+                Mf = np.asfortranarray(M); out = np.zeros((n, n), order="F")
+                assert L.shim_inverse(n, _p(Mf), _p(out)) == 1
+                ref = np.linalg.inv(M)
+                assert np.max(np.abs(out - ref)) <= 1e-11 * np.linalg.cond(M) * np.max(np.abs(ref)), (n, trial)
+                out2 = np.zeros((n, n), order="F"); L.shim_inverse_dynamic(n, _p(Mf), _p(out2))
+                assert np.max(np.abs(out2 - ref)) <= 1e-11 * np.linalg.cond(M) * np.max(np.abs(ref)), (n, trial)
+                if n in (2, 3, 6):
+                    d = L.shim_determinant(n, _p(Mf)); dr = np.linalg.det(M)
+                    assert abs(d - dr) <= 1e-11 * abs(dr) * np.linalg.cond(M), (n, trial)
+            if n in (2, 3, 6):                                                             # BaseVertex::solveDirect: H.llt().solve(b)
+                b = rng.normal(size=n); x = np.zeros(n); Sf = np.asfortranarray(S)
+                assert L.shim_llt_solve(n, _p(Sf), _p(b), _p(x)) == 1
+                xr = np.linalg.solve(S, b)
+                assert np.max(np.abs(x - xr)) <= 1e-11 * np.linalg.cond(S) * np.max(np.abs(xr))
+                bad = np.asfortranarray(S - (np.max(np.linalg.eigvalsh(S)) + 1.0) * np.eye(n))
+                assert L.shim_llt_solve(n, _p(bad), _p(b), _p(x)) == 0                      # not positive definite: info() != Success
+
+
+def test_stand_in_rotations_against_scipy():
+    L = oracle.shim_probe()
+    rng = np.random.default_rng(12)
+    for trial in range(200):
+        # all branches of Quaternion(Matrix3): positive trace and each of the three diagonal entries largest (angles near pi)
+        rv = rng.normal(size=3); rv *= (rng.uniform(0, np.pi) if trial % 2 else np.pi - 1e-3 * rng.random()) / np.linalg.norm(rv)
+        R = Rotation.from_rotvec(rv).as_matrix()
+        q = np.zeros(4); L.shim_quat_from_R(_p(np.asfortranarray(R)), _p(q))
+        qs = Rotation.from_matrix(R).as_quat()
+        assert min(np.max(np.abs(q - qs)), np.max(np.abs(q + qs))) < 1e-12, trial            # same rotation, either sign
+        Rb = np.zeros((3, 3), order="F"); L.shim_R_from_quat(_p(q), _p(Rb))
+        assert np.max(np.abs(Rb - R)) < 1e-12
+        q2 = Rotation.from_rotvec(rng.normal(size=3)).as_quat(); prod = np.zeros(4); L.shim_quat_mul(_p(q), _p(q2), _p(prod))
+        ps = (Rotation.from_quat(q) * Rotation.from_quat(q2)).as_quat()
+        assert min(np.max(np.abs(prod - ps)), np.max(np.abs(prod + ps))) < 1e-12
+        v = rng.normal(size=3); rot = np.zeros(3); L.shim_quat_rotate(_p(q), _p(v), _p(rot))
+        assert np.max(np.abs(rot - R @ v)) < 1e-12
+        axis = rv / np.linalg.norm(rv); Ra = np.zeros((3, 3), order="F"); L.shim_angle_axis_R(float(np.linalg.norm(rv)), _p(axis), _p(Ra))
+        assert np.max(np.abs(Ra - R)) < 1e-12
+        # Isometry3: A^-1 B and A v (EdgeSE3's error is (Z^-1 (T0^-1 T1)), isometry3d_mappings / edge_se3.cpp)
+        A = np.concatenate([R.ravel(order="F"), rng.normal(size=3)]); R2 = Rotation.from_quat(q2).as_matrix(); B = np.concatenate([R2.ravel(order="F"), rng.normal(size=3)])
+        out = np.zeros(12); L.shim_iso_inverse_times(_p(A), _p(B), _p(out))
+        assert np.max(np.abs(out[:9].reshape(3, 3, order="F") - R.T @ R2)) < 1e-12 and np.max(np.abs(out[9:] - R.T @ (B[9:] - A[9:]))) < 1e-12
+        av = np.zeros(3); L.shim_iso_apply(_p(A), _p(v), _p(av))
+        assert np.max(np.abs(av - (R @ v + A[9:]))) < 1e-12
+        ang = float(rng.uniform(-np.pi, np.pi)); v2 = rng.normal(size=2); o2 = np.zeros(2); back = np.zeros(1)
+        L.shim_rotation2d(ang, _p(v2), _p(o2), _p(back))
+        c, s = np.cos(ang), np.sin(ang)
+        assert np.max(np.abs(o2 - np.array([c * v2[0] - s * v2[1], s * v2[0] + c * v2[1]]))) < 1e-14 and abs(back[0] - ang) < 1e-14
