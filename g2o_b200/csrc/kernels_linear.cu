@@ -113,25 +113,29 @@ template <int P, int L> __global__ void __launch_bounds__(128) coeff_kernel(Schu
   const int tid = threadIdx.x, k0 = d.blockBegin + blockIdx.x * 128;
   const int nb = min(128, d.blockBegin + nBlocks - k0);
   const double* src = Hpl + (size_t)k0 * PLn;
-  for (int t = tid; t < nb * PLn; t += 128) sB[t] = src[t];
-  __syncthreads();
-  int wi = -1;
+  // this thread's block: camera, landmark, Dinv b_l, compact index and (short tracks) Dinv first - dependent global loads that then overlap the
+  // load of the tile
+  int wi = -1, ci = 0, lm = 0; double dbv[L], Di[LL];
   if (tid < nb) {
-    const int k = k0 + tid, ci = d.hplRowIdx[k], lm = hplLm[k];
-    double dbv[L];
+    const int k = k0 + tid; ci = d.hplRowIdx[k]; lm = hplLm[k];
+    if (d.hplShortIdx) wi = d.hplShortIdx[k];
 #pragma unroll
     for (int a = 0; a < L; ++a) dbv[a] = d.db[(size_t)lm * L + a];
+    if (wi >= 0) {
+#pragma unroll
+      for (int a = 0; a < LL; ++a) Di[a] = d.Dinv[(size_t)lm * LL + a];
+    }
+  }
+  for (int t = tid; t < nb * PLn; t += 128) sB[t] = src[t];
+  __syncthreads();
+  if (tid < nb) {
     double* blk = sB + tid * PLn;
 #pragma unroll
     for (int r = 0; r < P; ++r) { double v = 0;
 #pragma unroll
       for (int a = 0; a < L; ++a) v += blk[r + P * a] * dbv[a];
       atomicAdd(d.bschur + (size_t)ci * P + r, -v); }
-    if (d.hplShortIdx) wi = d.hplShortIdx[k];
     if (wi >= 0) {
-      double Di[LL];
-#pragma unroll
-      for (int a = 0; a < LL; ++a) Di[a] = d.Dinv[(size_t)lm * LL + a];
 #pragma unroll
       for (int r = 0; r < P; ++r) {
         double bv[L];
@@ -306,15 +310,17 @@ template <int P, int L> __global__ void __launch_bounds__(128) backsub_accum_ker
   const int tid = threadIdx.x, k0 = d.blockBegin + blockIdx.x * 128;
   const int nb = min(128, d.blockBegin + nBlocks - k0);
   const double* src = Hpl + (size_t)k0 * PLn;
-  for (int t = tid; t < nb * PLn; t += 128) sB[t] = src[t];
-  __syncthreads();
-  int lm = -1;
+  // this thread's block: camera, landmark and the camera's step first - two dependent global loads that then overlap the load of the tile
+  int lm = -1; double x[P];
   if (tid < nb) {
     const int k = k0 + tid, ci = d.hplRowIdx[k];
     lm = hplLm[k];
-    double x[P];
 #pragma unroll
     for (int r = 0; r < P; ++r) x[r] = xp[(size_t)ci * P + r];
+  }
+  for (int t = tid; t < nb * PLn; t += 128) sB[t] = src[t];
+  __syncthreads();
+  if (tid < nb) {
 #pragma unroll
     for (int q = 0; q < L; ++q) { double v = 0;
 #pragma unroll
