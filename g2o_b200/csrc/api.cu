@@ -622,16 +622,16 @@ int solvePcg(g2ocu_solver* s, const double* rhs) {
     const int batch = std::min(want, maxIter - issued);
     const bool p2p = slab && s->p2pReady && pc.n <= s->p2p.cap;
     static const bool graphsOn = [] { const char* e = getenv("G2OCU_PCG_GRAPH"); return !(e && e[0] == '0'); }();
-    const bool useGraph = graphsOn && !s->kernelTiming && pcgFusedTail(pc) && (!slab || p2p);
+    const bool useGraph = graphsOn && !s->kernelTiming && (slab ? (p2p && pcgFusedTailFits(pc)) : true);
     for (int k = 0; k < batch; ++k) {
       if (useGraph && issued + k > 0 && batch - k >= kPcgGraphIters) {      // (the first product of a solve clears q itself)
         int rc = ensurePcgGraph(s, p2p); if (rc) return rc;
         CU(cudaGraphLaunch(s->pcgGraph, s->stream));
-        s->launches += kPcgGraphIters * (p2p ? 3 : 2); k += kPcgGraphIters - 1;
+        s->launches += kPcgGraphIters * (p2p ? 3 : (pcgFusedTail(pc) ? 2 : 4)); k += kPcgGraphIters - 1;
         continue;
       }
       { KernelTimer pt(s, "pcg_spmv"); launchSpmv(pc, pc.d, pc.q, s->stream, &s->launches, issued + k > 0 && pcgSingleCtaTail(pc)); }
-      if (p2p && pcgFusedTail(pc)) { KernelTimer pt(s, "pcg_vec"); launchP2pPushAndTail(pc, s->p2p, s->stream, &s->launches); continue; }   // push + one kernel: wait for the peers, sum, d.q, recurrences
+      if (p2p && pcgFusedTailFits(pc)) { KernelTimer pt(s, "pcg_vec"); launchP2pPushAndTail(pc, s->p2p, s->stream, &s->launches); continue; }   // push + one kernel: wait for the peers, sum, d.q, recurrences
       if (p2p) { KernelTimer pt(s, "pcg_exchange"); launchP2pExchangeDot(pc, s->p2p, s->stream, &s->launches); }   // peer-memory all-reduce of q fused with d.q
       else if (slab) { KernelTimer pt(s, "pcg_exchange"); int rc = allreduceDev(s, pc.q, pc.n, 0); if (rc) return rc; }
       { KernelTimer pt(s, "pcg_vec"); launchPcgTail(pc, s->stream, &s->launches, p2p); }

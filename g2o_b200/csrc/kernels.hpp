@@ -122,7 +122,8 @@ void launchBlockInverse(const PcgDev& p, cudaStream_t st, int64_t* launches);
 void launchPcgInit(const PcgDev& p, const double* b, double tolerance, double residual, int absoluteTolerance, cudaStream_t st, int64_t* launches);   // x=0, r=b, d=M^-1 r, dn=r.d, d0
 void launchPcgTail(const PcgDev& p, cudaStream_t st, int64_t* launches, bool dotDone = false);   // after q = A d: dot, x/r/s update, d update, commit (no-ops once converged)
 void launchSpmv(const PcgDev& p, const double* src, double* dst, cudaStream_t st, int64_t* launches, bool dstIsZero = false);   // dst = (A + lambda I) src, symmetric upper
-bool pcgFusedTail(const PcgDev& p);        // launchPcgTail runs the recurrences as one cluster kernel (n <= 65 536)
+bool pcgFusedTail(const PcgDev& p);        // launchPcgTail runs the recurrences as one cluster kernel (single GPU: small systems, see kernels_linear.cu)
+bool pcgFusedTailFits(const PcgDev& p);   // the one-launch tail can hold the system (slab PCG over peer memory uses it whenever it can)
 void launchP2pPushAndTail(const PcgDev& p, const P2pDev& x, cudaStream_t st, int64_t* launches);   // slab PCG: peer-memory exchange fused into that kernel
 bool pcgSingleCtaTail(const PcgDev& p);   // launchPcgTail zeroes q itself (small systems): the next launchSpmv may skip its memset
 

@@ -736,6 +736,7 @@ __global__ void __launch_bounds__(256) pcg_update2_commit_kernel(PcgDev p, unsig
 // bit-identical iterates and the iteration counts compared with the reference do not depend on the path taken.
 namespace cg = cooperative_groups;
 constexpr int kFusedCtas = 8, kFusedThreads = 1024, kFusedRoundsMax = 8;   // 8 x 4 groups of 256 threads per round
+constexpr int kFusedTailMaxUnknowns = 256 * 32 * kFusedRoundsMax;           // what the kernel can hold; see pcgFusedTail for what it is used for
 template <int P> __global__ void __cluster_dims__(kFusedCtas, 1, 1) __launch_bounds__(kFusedThreads) pcg_tail_fused_kernel(PcgDev p, int dotDone, P2pDev x) {
   constexpr int PP = P * P;
   __shared__ double sWarp[32];                       // one sum per warp of this CTA
@@ -1069,7 +1070,15 @@ static bool pcgFusedTailEnabled() {
   static const bool on = [] { const char* e = getenv("G2OCU_PCG_TAIL"); return !(e && (e[0] == 's' || e[0] == 'S')); }();   // G2OCU_PCG_TAIL=split: the three-kernel path
   return on;
 }
-bool pcgFusedTail(const PcgDev& p) { return pcgFusedTailEnabled() && p.n <= 256 * 32 * kFusedRoundsMax; }
+// Where the one-launch tail is used.  On one GPU: small systems only - its 8 CTAs work on 8 of the 148 SMs, and inside a CUDA graph the three
+// launches of the split path cost less than that from about 10^4 unknowns on (C1, 84 unknowns: 1185 vs 1061 LM it/s with / without it; C3,
+// 16 002: 35.3 vs 35.6; C2, 60 000: 312 vs 543).  In the slab PCG over peer memory: whenever the system fits (it saves a launch per exchange).
+static int pcgFusedTailMax() {
+  static const int n = [] { const char* e = getenv("G2OCU_PCG_FUSED_MAX"); const int v = e ? atoi(e) : 0; return v > 0 ? (v < kFusedTailMaxUnknowns ? v : kFusedTailMaxUnknowns) : 8192; }();   // developer switch
+  return n;
+}
+bool pcgFusedTail(const PcgDev& p) { return pcgFusedTailEnabled() && p.n <= pcgFusedTailMax(); }
+bool pcgFusedTailFits(const PcgDev& p) { return pcgFusedTailEnabled() && p.n <= kFusedTailMaxUnknowns; }
 // slab PCG with the peer-memory exchange and the one-launch tail: push the partial product, the tail does the rest (waits for the peers,
 // sums, d.q, recurrences)
 void launchP2pPushAndTail(const PcgDev& p, const P2pDev& x, cudaStream_t st, int64_t* launches) {

@@ -146,8 +146,9 @@ def test_force_stop_flag_ends_the_optimisation():
 
 
 def test_fused_pcg_tail_matches_the_three_kernel_path():
-    """The CG recurrences of one iteration run as ONE cluster kernel (distributed shared memory for the two reductions) for systems of up to
-    65 536 unknowns; G2OCU_PCG_TAIL=split selects the three-kernel path.  Every sum of the tail is formed in the same order on both; the
+    """The CG recurrences of one iteration can run as ONE cluster kernel (distributed shared memory for the two reductions) for systems of up to
+    65 536 unknowns - on one GPU it is used for small systems, in the slab PCG over peer memory whenever it fits; G2OCU_PCG_FUSED_MAX raises the
+    single-GPU limit, G2OCU_PCG_TAIL=split selects the three-kernel path.  Every sum of the tail is formed in the same order on both; the
     products before it add with atomics, so two runs agree to rounding, not to the bit: same LM trials, same PCG iteration counts, chi2 to 1e-9."""
     import json, os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -161,7 +162,7 @@ def test_fused_pcg_tail_matches_the_three_kernel_path():
             "print(json.dumps(out))\n")
     outs = []
     for mode in ("fused", "split"):
-        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=300, env=dict(os.environ, G2OCU_PCG_TAIL=mode))
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=300, env=dict(os.environ, G2OCU_PCG_TAIL=mode, G2OCU_PCG_FUSED_MAX="65536"))
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
     for a, b in zip(*outs):
