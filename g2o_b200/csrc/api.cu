@@ -132,7 +132,7 @@ struct g2ocu_solver {
   DVec<int> poseCounters, lmCounters;
   DVec<double> denseH; DVec<int> denseInfo; DVec<unsigned int> pcgTicket; int* hostInfo = nullptr;
   DVec<double> Hpp, Hll, Hpl, W, Wshort, b, x, S, Dinv, dbv, bschur, Minv, vr, vd, vq, vs, scal, partial, partialDq, scratch, out2, dbg;
-  DVec<double> fr, fd, fq, fs;                                       // full-system PCG vectors r, d, q, s (vectorSize each)
+  DVec<double> fr, fd, fq, fs, fPartial, fPartialDq;                 // full-system PCG vectors r, d, q, s (vectorSize each) and its partial sums
   DVec<double> hsd, hdl, aux;                                        // Dogleg: steepest-descent step, final step, auxiliary vector (vectorSize each)
   DVec<int32_t> mhRow, mhBegin, mhEnd, mhRowPtr, mhColIdx; bool mhReady = false;   // SpMV work items over the Hpp pattern (multiplyHessian in Schur mode)
   DVec<int32_t> hppDiag, hplColPtr, hplRowIdx, sRowPtr, sColIdx, sDiag, hppToS, pairEdgeI, pairEdgeJ, aRowPtr, aColIdx, aDiag, spRow, spBegin, spEnd, hplLm, tEntLm, tEntBI, tEntBJ, tChunkI, tChunkJ, tChunkB, tChunkE, tChunkSlots, pairSegB, pairSegS, hplShortIdx, pairW;
@@ -886,52 +886,42 @@ int multiplyHessianDev(g2ocu_solver* s, const double* src, double* dst) {
 }
 
 // LinearSolverPCG::solve (linear_solver_pcg.hpp:80-156) on the whole system of a graph whose points are not marginalized:
-// block-Jacobi preconditioner from the P x P and L x L diagonal blocks, _residual carried from one solve to the next.  The scalars of
-// the recurrences are formed on the host (two fixed-order dot products per iteration); this is the general-purpose `*_var` path, the
-// bundle-adjustment hot path is the Schur branch of solveSystem.
+// block-Jacobi preconditioner from the P x P and L x L diagonal blocks, _residual carried from one solve to the next.  As in the Schur-path
+// PCG the scalars of the recurrences and the convergence flag live on the device (dot_partial / pcg_full_update1 / pcg_update2_commit, every
+// sum in a fixed order); the host polls every 4 iterations, the first time where the previous solve converged.  The product is three
+// kernels (Hpp part, point blocks, Hpl blocks with atomics into both halves).
 int solveFullPcg(g2ocu_solver* s) {
   const Structure& st = s->st;
   const int64_t np = st.sizePoses, n = np + st.sizeLandmarks;
   CU(s->fr.alloc((size_t)n)); CU(s->fd.alloc((size_t)n)); CU(s->fq.alloc((size_t)n)); CU(s->fs.alloc((size_t)n));
-  double* r = s->fr.p; double* d = s->fd.p; double* q = s->fq.p; double* sv = s->fs.p; double* x = s->x.p;
   PcgDev pc; int rc = hppView(s, pc); if (rc) return rc;
   launchBlockInverse(pc, s->stream, &s->launches);                                                                   // J_i = (Hpp_ii + lambda I)^-1 -> Minv
   launchPointBlockInverse(s->Dinv.p, s->Hll.p, st.numLandmarks, st.L, s->lambda, s->stream, &s->launches);           // and the point blocks -> Dinv
-  auto precond = [&](const double* in, double* out) {
-    launchBlockDiagMult(out, s->Minv.p, in, st.numPoses, st.P, 0.0, s->stream, &s->launches);
-    launchBlockDiagMult(out + np, s->Dinv.p, in + np, st.numLandmarks, st.L, 0.0, s->stream, &s->launches);
-  };
-  auto dot = [&](const double* u, const double* v, double* out) -> int {
-    launchScale(u, v, n, 0.0, s->scratch.p, s->out2.p + 12, s->stream, &s->launches);
-    CU(cudaMemcpyAsync(s->hostScal + 24, s->out2.p + 12, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    int r2 = syncStream(s); if (r2) return r2;
-    *out = s->hostScal[24];
-    return G2OCU_OK;
-  };
-  CU(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), s->stream));
-  CU(cudaMemcpyAsync(r, s->b.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
-  precond(r, d);
-  double dn = 0; rc = dot(r, d, &dn); if (rc) return rc;
-  double d0 = s->cfg.pcg_tolerance * dn;
-  if (s->cfg.pcg_absolute_tolerance) { if (s->pcgResidual > 0.0 && s->pcgResidual > d0) d0 = s->pcgResidual; }
+  PcgDev fp;                                                                                                        // the whole system as the tail kernels see it
+  fp.n = (int)n; fp.nb = st.numPoses + st.numLandmarks; fp.P = st.P; fp.Minv = s->Minv.p;
+  fp.r = s->fr.p; fp.d = s->fd.p; fp.q = s->fq.p; fp.s = s->fs.p; fp.x = s->x.p; fp.scal = s->scal.p; fp.ticket = s->pcgTicket.p;
+  fp.nPartial = (int)((n + 255) / 256); fp.nPartialDq = std::min(296, fp.nPartial);
+  CU(s->fPartial.alloc(fp.nPartial)); CU(s->fPartialDq.alloc(fp.nPartialDq));
+  fp.partial = s->fPartial.p; fp.partialDq = s->fPartialDq.p;
+  launchFullPcgInit(fp, (int)np, s->Dinv.p, st.L, s->b.p, s->cfg.pcg_tolerance, s->pcgResidual, s->cfg.pcg_absolute_tolerance, s->stream, &s->launches);   // x = 0, r = b, d = M^-1 r, dn, d0
   const int64_t maxIter = s->cfg.pcg_max_iterations < 0 ? n : s->cfg.pcg_max_iterations;
-  int64_t iteration;
-  for (iteration = 0; iteration < maxIter; ++iteration) {
-    if (dn <= d0) break;
-    rc = multFullSystem(s, d, q); if (rc) return rc;
-    double dq = 0; rc = dot(d, q, &dq); if (rc) return rc;
-    const double a = dn / dq;
-    launchLincomb(x, d, nullptr, a, 3, n, s->stream, &s->launches);        // x += a d
-    launchLincomb(r, q, nullptr, -a, 3, n, s->stream, &s->launches);       // r -= a q
-    precond(r, sv);
-    const double dold = dn;
-    rc = dot(r, sv, &dn); if (rc) return rc;
-    const double ba = dn / dold;
-    launchLincomb(d, sv, nullptr, ba, 4, n, s->stream, &s->launches);      // d = s + ba d
-    if (!std::isfinite(dn)) { ++iteration; break; }                          // NaN/Inf in the recurrence: stop (the reference would spin to maxIter)
+  int64_t issued = 0; bool done = false;
+  const int kCheckEvery = 4;
+  while (!done) {
+    const int64_t want = issued == 0 ? std::min<int64_t>(std::max(kCheckEvery, s->lastPcgIterations - 1), 256) : kCheckEvery;
+    const int64_t batch = std::min(want, maxIter - issued);
+    for (int64_t k = 0; k < batch; ++k) {                                  // launches past convergence: the tail kernels return at once, the product runs idle
+      { KernelTimer pt(s, "pcg_spmv"); rc = multFullSystem(s, fp.d, fp.q); if (rc) return rc; }
+      { KernelTimer pt(s, "pcg_vec"); launchFullPcgTail(fp, (int)np, s->Dinv.p, st.L, s->stream, &s->launches); }
+    }
+    issued += batch;
+    CU(cudaMemcpyAsync(s->hostScal + 8, fp.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    rc = syncStream(s); if (rc) return rc;
+    if (s->hostScal[8 + 6] != 0.0 || issued >= maxIter) done = true;
+    if (!std::isfinite(s->hostScal[8 + 2])) done = true;                   // NaN/Inf in the recurrence: stop issuing work (the reference would spin to maxIter)
   }
-  s->pcgResidual = 0.5 * dn;
-  s->lastPcgIterations = (int)iteration;
+  s->lastPcgIterations = (int)s->hostScal[8 + 7]; s->totalPcgIterations += s->lastPcgIterations;
+  s->pcgResidual = 0.5 * s->hostScal[8 + 2];
   CU(cudaGetLastError());
   return G2OCU_OK;
 }

@@ -121,6 +121,9 @@ void launchSlabReduce(const P2pDev& x, size_t begin, size_t count, cudaStream_t 
 void launchBlockInverse(const PcgDev& p, cudaStream_t st, int64_t* launches);
 void launchPcgInit(const PcgDev& p, const double* b, double tolerance, double residual, int absoluteTolerance, cudaStream_t st, int64_t* launches);   // x=0, r=b, d=M^-1 r, dn=r.d, d0
 void launchPcgTail(const PcgDev& p, cudaStream_t st, int64_t* launches, bool dotDone = false);   // after q = A d: dot, x/r/s update, d update, commit (no-ops once converged)
+// whole-system PCG (points not marginalized): the same with a preconditioner of two block sizes (unknowns [0, np): blocks of p.P from p.Minv, the rest blocks of L from Dinv)
+void launchFullPcgInit(const PcgDev& p, int np, const double* Dinv, int L, const double* b, double tolerance, double residual, int absoluteTolerance, cudaStream_t st, int64_t* launches);
+void launchFullPcgTail(const PcgDev& p, int np, const double* Dinv, int L, cudaStream_t st, int64_t* launches);
 void launchSpmv(const PcgDev& p, const double* src, double* dst, cudaStream_t st, int64_t* launches, bool dstIsZero = false);   // dst = (A + lambda I) src, symmetric upper
 bool pcgFusedTail(const PcgDev& p);        // launchPcgTail runs the recurrences as one cluster kernel (single GPU: small systems, see kernels_linear.cu)
 bool pcgFusedTailFits(const PcgDev& p);   // the one-launch tail can hold the system (slab PCG over peer memory uses it whenever it can)

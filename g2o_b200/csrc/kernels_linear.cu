@@ -729,6 +729,37 @@ __global__ void __launch_bounds__(256) pcg_update2_commit_kernel(PcgDev p, unsig
     }
   }
 }
+// ---- whole-system PCG (poses and points in one matrix, nothing marginalized): the same recurrences with a block-Jacobi preconditioner of TWO
+// block sizes - unknowns [0, np) are pose blocks of P (inverses in p.Minv), the rest point blocks of L (inverses in Dinv).  Thread per scalar row;
+// dot_partial_kernel and pcg_update2_commit_kernel above serve this path unchanged.
+__device__ __forceinline__ void precondRow2(const PcgDev& p, int np, const double* __restrict__ Dinv, int L, int t, const double* __restrict__ rv, const double* __restrict__ qv,
+                                            double alpha, double& v, double& mine) {
+  int B, r; const double* M; size_t o;
+  if (t < np) { B = p.P; const int i = t / B; r = t - i * B; M = p.Minv + (size_t)i * B * B + r; o = (size_t)i * B; }
+  else { B = L; const int u = t - np, i = u / B; r = u - i * B; M = Dinv + (size_t)i * B * B + r; o = (size_t)np + (size_t)i * B; }
+  v = 0; mine = 0;
+  for (int c = 0; c < B; ++c) { double rc = rv[o + c]; if (qv) rc -= alpha * qv[o + c]; v += M[B * c] * rc; if (c == r) mine = rc; }
+}
+__global__ void __launch_bounds__(256) pcg_full_init_kernel(PcgDev p, int np, const double* __restrict__ Dinv, int L, const double* __restrict__ b) {
+  __shared__ double sm[8];
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  double acc = 0;
+  if (t < p.n) { double v, mine; precondRow2(p, np, Dinv, L, t, b, nullptr, 0.0, v, mine); p.r[t] = mine; p.x[t] = 0; p.d[t] = v; acc = mine * v; }
+  const double s = blockSumL<256>(acc, sm);
+  if (threadIdx.x == 0) p.partial[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) pcg_full_update1_kernel(PcgDev p, int np, const double* __restrict__ Dinv, int L, const double* dqPartial, int nDq) {
+  __shared__ double sm[8];
+  if (p.scal[6] != 0.0) return;
+  const double dq = sumPartialsAll<256>(dqPartial, nDq, sm);
+  const double alpha = p.scal[0] / dq;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  double acc = 0;
+  if (t < p.n) { double v, mine; precondRow2(p, np, Dinv, L, t, p.r, p.q, alpha, v, mine); p.x[t] += alpha * p.d[t]; p.s[t] = v; acc = mine * v; }
+  const double s = blockSumL<256>(acc, sm);
+  if (threadIdx.x == 0) p.partial[blockIdx.x] = s;
+}
+
 // The three kernels above (dot_partial, pcg_update1, pcg_update2_commit) as ONE launch for systems of up to 65 536 unknowns: a thread-block
 // cluster of 8 CTAs x 1024 threads; the two global reductions of a CG iteration (d.q and r.s) go through distributed shared memory and two
 // cluster barriers instead of two kernel boundaries.  Every sum is formed in exactly the order of the three-kernel path - 256 consecutive
@@ -1087,6 +1118,17 @@ void launchP2pPushAndTail(const PcgDev& p, const P2pDev& x, cudaStream_t st, int
   FOR_P(p.P, CALL)
 #undef CALL
   *launches += 2;
+}
+void launchFullPcgInit(const PcgDev& p, int np, const double* Dinv, int L, const double* b, double tolerance, double residual, int absoluteTolerance, cudaStream_t st, int64_t* launches) {
+  pcg_full_init_kernel<<<p.nPartial, 256, 0, st>>>(p, np, Dinv, L, b);
+  pcg_init_finish_kernel<<<1, 256, 0, st>>>(p, tolerance, residual, absoluteTolerance);
+  *launches += 2;
+}
+void launchFullPcgTail(const PcgDev& p, int np, const double* Dinv, int L, cudaStream_t st, int64_t* launches) {
+  dot_partial_kernel<<<p.nPartialDq, 256, 0, st>>>(p.scal, p.d, p.q, p.n, p.partialDq);
+  pcg_full_update1_kernel<<<p.nPartial, 256, 0, st>>>(p, np, Dinv, L, p.partialDq, p.nPartialDq);
+  pcg_update2_commit_kernel<<<p.nPartialDq, 256, 0, st>>>(p, p.ticket);
+  *launches += 3;
 }
 void launchPcgTail(const PcgDev& p, cudaStream_t st, int64_t* launches, bool dotDone) {
   if (pcgFusedTail(p)) {
