@@ -112,7 +112,7 @@ struct g2ocu_solver {
   double pcgResidual = -1.0;      // LinearSolverPCG::_residual, persists across solves until init()
   // CUDA graph of kPcgGraphIters CG iterations (product + one-launch tail, + the peer-memory push when sharded): launched instead of the
   // individual kernels between two convergence polls; re-captured when a kernel argument changes (matrix, lambda, transport)
-  cudaGraphExec_t pcgGraph = nullptr; double pcgGraphLambda = 0; bool pcgGraphP2p = false; const double* pcgGraphA = nullptr; int pcgGraphN = 0;
+  cudaGraphExec_t pcgGraph = nullptr; double pcgGraphLambda = 0; bool pcgGraphP2p = false; const double* pcgGraphA = nullptr; int pcgGraphN = 0; int64_t pcgGraphKernels = 0;
   int tileMinTrack = kTileMinTrack;                            // tracks with fewer observations go through the pair kernel
   int lastPcgIterations = 0; int64_t totalPcgIterations = 0;   // of the last solve / of all solves since g2ocu_reset_counters
   bool errorsValid = false; double chi2Robust = 0, chi2Plain = 0;
@@ -582,16 +582,19 @@ int buildSystem(g2ocu_solver* s) {
 
 const int kPcgGraphIters = 4;
 // The CG iterations between two convergence polls as one graph launch (the kernels are tens of microseconds long at most - at 8 GPUs
-// shorter than their launch gaps).  Only with the one-launch tail; not while per-kernel timing is on.
-int ensurePcgGraph(g2ocu_solver* s, bool p2p) {
+// shorter than their launch gaps).  Single GPU and the peer-memory slab PCG; not with NCCL in the loop, not while per-kernel timing is on.
+int ensurePcgGraph(g2ocu_solver* s, bool p2p, int64_t* kernelsPerLaunch) {
   PcgDev& pc = s->pcg;
+  *kernelsPerLaunch = s->pcgGraphKernels;
   if (s->pcgGraph && s->pcgGraphLambda == pc.lambda && s->pcgGraphP2p == p2p && s->pcgGraphA == pc.A && s->pcgGraphN == pc.n) return G2OCU_OK;
   if (s->pcgGraph) { cudaGraphExecDestroy(s->pcgGraph); s->pcgGraph = nullptr; }
   int64_t dummy = 0;
   CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
   for (int k = 0; k < kPcgGraphIters; ++k) {
     launchSpmv(pc, pc.d, pc.q, s->stream, &dummy, true);
-    if (p2p) launchP2pPushAndTail(pc, s->p2p, s->stream, &dummy); else launchPcgTail(pc, s->stream, &dummy, false);
+    if (p2p && pcgFusedTail(pc)) launchP2pPushAndTail(pc, s->p2p, s->stream, &dummy);
+    else if (p2p) { launchP2pExchangeDot(pc, s->p2p, s->stream, &dummy); launchPcgTail(pc, s->stream, &dummy, true); }   // exchange fused with d.q, then the split tail
+    else launchPcgTail(pc, s->stream, &dummy, false);
   }
   cudaGraph_t graph = nullptr;
   CU(cudaStreamEndCapture(s->stream, &graph));
@@ -599,6 +602,7 @@ int ensurePcgGraph(g2ocu_solver* s, bool p2p) {
   cudaGraphDestroy(graph);
   if (e != cudaSuccess) { s->pcgGraph = nullptr; return fail(s, G2OCU_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
   s->pcgGraphLambda = pc.lambda; s->pcgGraphP2p = p2p; s->pcgGraphA = pc.A; s->pcgGraphN = pc.n;
+  s->pcgGraphKernels = dummy; *kernelsPerLaunch = dummy;     // what the launch helpers counted during the capture
   return G2OCU_OK;
 }
 
@@ -622,16 +626,17 @@ int solvePcg(g2ocu_solver* s, const double* rhs) {
     const int batch = std::min(want, maxIter - issued);
     const bool p2p = slab && s->p2pReady && pc.n <= s->p2p.cap;
     static const bool graphsOn = [] { const char* e = getenv("G2OCU_PCG_GRAPH"); return !(e && e[0] == '0'); }();
-    const bool useGraph = graphsOn && !s->kernelTiming && (slab ? (p2p && pcgFusedTailFits(pc)) : true);
+    const bool useGraph = graphsOn && !s->kernelTiming && (slab ? p2p : true);
     for (int k = 0; k < batch; ++k) {
       if (useGraph && issued + k > 0 && batch - k >= kPcgGraphIters) {      // (the first product of a solve clears q itself)
-        int rc = ensurePcgGraph(s, p2p); if (rc) return rc;
+        int64_t graphLaunches = 0;
+        int rc = ensurePcgGraph(s, p2p, &graphLaunches); if (rc) return rc;
         CU(cudaGraphLaunch(s->pcgGraph, s->stream));
-        s->launches += kPcgGraphIters * (p2p ? 3 : (pcgFusedTail(pc) ? 2 : 4)); k += kPcgGraphIters - 1;
+        s->launches += graphLaunches; k += kPcgGraphIters - 1;
         continue;
       }
       { KernelTimer pt(s, "pcg_spmv"); launchSpmv(pc, pc.d, pc.q, s->stream, &s->launches, issued + k > 0 && pcgSingleCtaTail(pc)); }
-      if (p2p && pcgFusedTailFits(pc)) { KernelTimer pt(s, "pcg_vec"); launchP2pPushAndTail(pc, s->p2p, s->stream, &s->launches); continue; }   // push + one kernel: wait for the peers, sum, d.q, recurrences
+      if (p2p && pcgFusedTail(pc)) { KernelTimer pt(s, "pcg_vec"); launchP2pPushAndTail(pc, s->p2p, s->stream, &s->launches); continue; }   // push + one kernel: wait for the peers, sum, d.q, recurrences
       if (p2p) { KernelTimer pt(s, "pcg_exchange"); launchP2pExchangeDot(pc, s->p2p, s->stream, &s->launches); }   // peer-memory all-reduce of q fused with d.q
       else if (slab) { KernelTimer pt(s, "pcg_exchange"); int rc = allreduceDev(s, pc.q, pc.n, 0); if (rc) return rc; }
       { KernelTimer pt(s, "pcg_vec"); launchPcgTail(pc, s->stream, &s->launches, p2p); }

@@ -126,7 +126,6 @@ void launchFullPcgInit(const PcgDev& p, int np, const double* Dinv, int L, const
 void launchFullPcgTail(const PcgDev& p, int np, const double* Dinv, int L, cudaStream_t st, int64_t* launches);
 void launchSpmv(const PcgDev& p, const double* src, double* dst, cudaStream_t st, int64_t* launches, bool dstIsZero = false);   // dst = (A + lambda I) src, symmetric upper
 bool pcgFusedTail(const PcgDev& p);        // launchPcgTail runs the recurrences as one cluster kernel (single GPU: small systems, see kernels_linear.cu)
-bool pcgFusedTailFits(const PcgDev& p);   // the one-launch tail can hold the system (slab PCG over peer memory uses it whenever it can)
 void launchP2pPushAndTail(const PcgDev& p, const P2pDev& x, cudaStream_t st, int64_t* launches);   // slab PCG: peer-memory exchange fused into that kernel
 bool pcgSingleCtaTail(const PcgDev& p);   // launchPcgTail zeroes q itself (small systems): the next launchSpmv may skip its memset
 

@@ -1101,15 +1101,15 @@ static bool pcgFusedTailEnabled() {
   static const bool on = [] { const char* e = getenv("G2OCU_PCG_TAIL"); return !(e && (e[0] == 's' || e[0] == 'S')); }();   // G2OCU_PCG_TAIL=split: the three-kernel path
   return on;
 }
-// Where the one-launch tail is used.  On one GPU: small systems only - its 8 CTAs work on 8 of the 148 SMs, and inside a CUDA graph the three
-// launches of the split path cost less than that from about 10^4 unknowns on (C1, 84 unknowns: 1185 vs 1061 LM it/s with / without it; C3,
-// 16 002: 35.3 vs 35.6; C2, 60 000: 312 vs 543).  In the slab PCG over peer memory: whenever the system fits (it saves a launch per exchange).
+// Where the one-launch tail is used: small systems only - its 8 CTAs work on 8 of the 148 SMs, and inside a CUDA graph the three launches of
+// the split path cost less than that from about 10^4 unknowns on (C1, 84 unknowns: 1185 vs 1061 LM it/s with / without it; C3, 16 002: 35.3 vs
+// 35.6; C2, 60 000: 312 vs 543; C3 in the slab PCG over peer memory, where it also absorbs the wait for the peers: 71.4 vs 72.5 on 2 GPUs, 121.0
+// vs 122.8 on 8).
 static int pcgFusedTailMax() {
   static const int n = [] { const char* e = getenv("G2OCU_PCG_FUSED_MAX"); const int v = e ? atoi(e) : 0; return v > 0 ? (v < kFusedTailMaxUnknowns ? v : kFusedTailMaxUnknowns) : 8192; }();   // developer switch
   return n;
 }
 bool pcgFusedTail(const PcgDev& p) { return pcgFusedTailEnabled() && p.n <= pcgFusedTailMax(); }
-bool pcgFusedTailFits(const PcgDev& p) { return pcgFusedTailEnabled() && p.n <= kFusedTailMaxUnknowns; }
 // slab PCG with the peer-memory exchange and the one-launch tail: push the partial product, the tail does the rest (waits for the peers,
 // sums, d.q, recurrences)
 void launchP2pPushAndTail(const PcgDev& p, const P2pDev& x, cudaStream_t st, int64_t* launches) {

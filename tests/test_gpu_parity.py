@@ -147,8 +147,8 @@ def test_force_stop_flag_ends_the_optimisation():
 
 def test_fused_pcg_tail_matches_the_three_kernel_path():
     """The CG recurrences of one iteration can run as ONE cluster kernel (distributed shared memory for the two reductions) for systems of up to
-    65 536 unknowns - on one GPU it is used for small systems, in the slab PCG over peer memory whenever it fits; G2OCU_PCG_FUSED_MAX raises the
-    single-GPU limit, G2OCU_PCG_TAIL=split selects the three-kernel path.  Every sum of the tail is formed in the same order on both; the
+    65 536 unknowns - it is used for small systems (below 8192 unknowns); G2OCU_PCG_FUSED_MAX raises the
+    limit, G2OCU_PCG_TAIL=split selects the three-kernel path.  Every sum of the tail is formed in the same order on both; the
     products before it add with atomics, so two runs agree to rounding, not to the bit: same LM trials, same PCG iteration counts, chi2 to 1e-9."""
     import json, os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
