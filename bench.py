@@ -487,7 +487,9 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "ours" and not os.environ.get("G2O_BENCH_ALLOW_SHORT_WARMUP"):
+    if args.warmup < 3 and args.impl in ("ours", "reference") and not os.environ.get("G2O_BENCH_ALLOW_SHORT_WARMUP"):
+        # timing rule: at least 3 warm-up steps.  Raised on BOTH arms so that they keep timing the same LM iterations; the JSON line reports it.
+        print(f"bench.py: --warmup {args.warmup} raised to 3 (timing rule; both arms)", file=sys.stderr, flush=True)
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
