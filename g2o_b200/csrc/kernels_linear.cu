@@ -169,7 +169,8 @@ __device__ __forceinline__ void pairDmma(double (&c)[2], double a, double b) {
 // scalar of W (row m of the pair its K slot belongs to, from the coefficient pass) and one of B_j and issues the DMMA of rows / columns
 // 0..7; for P = 9 row 8 and column 8 are three plain FMAs per lane on the ninth scalars of its K slot, summed over the 4 K lanes at the
 // end.  Against the scalar kernel above: 4 loads + 1 DMMA + 3 FMAs per 4/3 pairs instead of 18 loads + 12 FMAs + 9 shuffles per pair (that kernel sat at 86 % of the L1
-// pipe).  wIdx = index of the row-side W block per pair (d.pairW into d.Wshort, or d.pairEdgeI into the full W of the older tile path).
+// pipe).  (One pair per K step - L scalars + zero padding, so that a step's lanes read one W and one B block instead of two - was measured:
+// 5 % slower, the extra K steps cost more than the fewer cache lines save.)  wIdx = index of the row-side W block per pair (d.pairW into d.Wshort, or d.pairEdgeI into the full W of the older tile path).
 template <int P, int L> __global__ void __launch_bounds__(256) schur_pairs_dmma_kernel(SchurDev d, const double* __restrict__ Hpl, const double* __restrict__ W, const int32_t* __restrict__ wIdx) {
   constexpr int PP = P * P, PLn = P * L;
   constexpr bool kFringe = P > 8;
