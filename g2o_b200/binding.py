@@ -204,16 +204,24 @@ class CudaSolver:
 
     def compute_marginals(self, pairs):
         """``SparseOptimizer::computeMarginals(spinv, blockIndices)`` (sparse_optimizer.cpp:594-596): ``pairs`` = (row, col) hessian indices of pose
-        vertices; returns the list of blocks of the inverse of Hpp (poseDim x poseDim arrays), or None where the reference returns false."""
+        vertices (of any vertex when no point is marginalized: the reference's Hpp is then the whole system); returns the list of blocks of the inverse
+        of Hpp, or None where the reference returns false."""
         pairs = [(int(r), int(c)) for r, c in pairs]
         rows = np.array([p[0] for p in pairs], dtype=np.int32); cols = np.array([p[1] for p in pairs], dtype=np.int32)
-        dims = self.get_i32("dims"); P = int(dims[2]) // max(int(dims[0]), 1)
-        out = np.zeros(len(pairs) * P * P); ok = ctypes.c_int32(0)
+        ends = self.get_i32("pose_block_indices").astype(np.int64)          # cumulative block ends of the reference's Hpp (all vertices when no point is marginalized)
+        dim = np.diff(np.concatenate([[0], ends]))
+        if len(pairs) and (rows.min() < 0 or cols.min() < 0 or rows.max() >= len(dim) or cols.max() >= len(dim)):
+            raise G2oCudaError(_lib.E_INVALID, f"block index outside Hpp ({len(dim)} block rows)")
+        sizes = [int(dim[r] * dim[c]) for r, c in pairs]
+        out = np.zeros(max(sum(sizes), 1)); ok = ctypes.c_int32(0)
         self._ck(self._L.g2ocu_compute_marginals(self._h, len(pairs), rows.ctypes.data_as(ctypes.c_void_p), cols.ctypes.data_as(ctypes.c_void_p),
                                                  out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(ok)))
         if not ok.value:
             return None
-        return [out[i * P * P:(i + 1) * P * P].reshape(P, P, order="F").copy() for i in range(len(pairs))]
+        blocks, off = [], 0
+        for (r, c), sz in zip(pairs, sizes):
+            blocks.append(out[off:off + sz].reshape(int(dim[r]), int(dim[c]), order="F").copy()); off += sz
+        return blocks
 
     def vector_size(self) -> int: return int(self._L.g2ocu_vector_size(self._h))
     def x(self) -> np.ndarray: return self.get_f64("x")

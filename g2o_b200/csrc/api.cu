@@ -1293,20 +1293,30 @@ int g2ocu_multiply_hessian(g2ocu_solver* s, double* hostDest, const double* host
 // MarginalCovarianceCholesky, marginal_covariance_cholesky.cpp:153-222): blocks (row, col) of the inverse of Hpp as it stands - the pose
 // block of the last buildSystem, plus whatever setLambda has put on its diagonal.  Here: dense copy of Hpp, FP64 Cholesky on the tensor
 // pipe (kernels_dense.cu), (L L^T)^-1 applied to the unit columns of the requested block columns (at most 1 GiB of them at a time), the
-// requested blocks gathered on the device.  *computed = 0 where the reference's solvePattern returns false: factorisation failed.
+// requested blocks gathered on the device.  *computed = 0 where the reference's solvePattern returns false: factorisation failed.  With points
+// that are not marginalized the reference's Hpp is the whole system over all vertices in id order: blocks of two sizes, indexed as there.
 int g2ocu_compute_marginals(g2ocu_solver* s, int32_t nPairs, const int32_t* blockRows, const int32_t* blockCols, double* out, int32_t* computed) {
   int rc = requireBuilt(s); if (rc) return rc;
   if (computed) *computed = 0;
   if (nPairs < 0 || (nPairs > 0 && (!blockRows || !blockCols || !out))) return fail(s, G2OCU_E_INVALID, "g2ocu_compute_marginals: null argument");
   const Structure& st = s->st;
-  if (st.fullSystem) return fail(s, G2OCU_E_UNSUPPORTED, "g2ocu_compute_marginals: the graph has points that are not marginalized (its Hpp is the whole system with two block sizes); marginalize the points or use a pose graph");
-  const int P = st.P; const int64_t n = st.sizePoses;
+  const int P = st.P; const bool full = st.fullSystem;
+  // the matrix the reference calls Hpp: the pose block, or - points not marginalized - the whole system over all vertices in id order
+  const int64_t n = full ? (int64_t)st.sizePoses + st.sizeLandmarks : (int64_t)st.sizePoses;
+  const int nBlocks = full ? (int)st.refPoseBlockIndices.size() : st.numPoses;
   if (P != 3 && P != 6 && P != 9) return fail(s, G2OCU_E_UNSUPPORTED, "g2ocu_compute_marginals: pose dimension " + std::to_string(P));
-  if (n > kDenseMaxN) return fail(s, G2OCU_E_UNSUPPORTED, "g2ocu_compute_marginals: the dense factorisation is limited to pose systems of dimension <= " + std::to_string(kDenseMaxN) + " (this one has " + std::to_string(n) + ")");
+  if (full && s->world > 1) return fail(s, G2OCU_E_UNSUPPORTED, "g2ocu_compute_marginals: a graph whose points are not marginalized cannot be sharded");
+  if (n > kDenseMaxN) return fail(s, G2OCU_E_UNSUPPORTED, "g2ocu_compute_marginals: the dense factorisation is limited to systems of dimension <= " + std::to_string(kDenseMaxN) + " (this one has " + std::to_string(n) + ")");
   for (int i = 0; i < nPairs; ++i)
-    if (blockRows[i] < 0 || blockRows[i] >= st.numPoses || blockCols[i] < 0 || blockCols[i] >= st.numPoses)
-      return fail(s, G2OCU_E_INVALID, "g2ocu_compute_marginals: block (" + std::to_string(blockRows[i]) + ", " + std::to_string(blockCols[i]) + ") is outside Hpp (" + std::to_string(st.numPoses) + " block rows)");
+    if (blockRows[i] < 0 || blockRows[i] >= nBlocks || blockCols[i] < 0 || blockCols[i] >= nBlocks)
+      return fail(s, G2OCU_E_INVALID, "g2ocu_compute_marginals: block (" + std::to_string(blockRows[i]) + ", " + std::to_string(blockCols[i]) + ") is outside Hpp (" + std::to_string(nBlocks) + " block rows)");
   if (nPairs == 0) { if (computed) *computed = 1; return G2OCU_OK; }
+  // block index (the reference's) -> first scalar row in the device's layout, dimension
+  auto blockAt = [&](int b, int& scalar, int& dim) {
+    if (!full) { scalar = b * P; dim = P; return; }
+    const int begin = b ? st.refPoseBlockIndices[b - 1] : 0;
+    dim = st.refPoseBlockIndices[b] - begin; scalar = st.refToInternal[begin];   // a vertex's scalars are contiguous in both orders
+  };
   PhaseTimer pt(s, "marginals");
   PcgDev pc; rc = hppView(s, pc); if (rc) return rc;
   DVec<double> hppSum;
@@ -1317,40 +1327,50 @@ int g2ocu_compute_marginals(g2ocu_solver* s, int32_t nPairs, const int32_t* bloc
     pc.A = hppSum.p;
   }
   CU(s->denseH.alloc((size_t)n * n)); CU(s->denseInfo.alloc(1));
-  launchDenseAssemble(pc, s->denseH.p, s->stream, &s->launches);
+  if (full) launchDenseAssembleFull(pc, s->Hll.p, s->Hpl.p, s->hplRowIdx.p, s->hplLm.p, (int)st.hplRowIdx.size(), st.numLandmarks, st.L, s->denseH.p, (int)n, s->stream, &s->launches);
+  else launchDenseAssemble(pc, s->denseH.p, s->stream, &s->launches);
   launchDenseCholeskyFactor(s->denseH.p, (int)n, s->denseInfo.p, s->stream, &s->launches);
   CU(cudaMemcpyAsync(s->hostInfo, s->denseInfo.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   rc = syncStream(s); if (rc) return rc;
   if (*s->hostInfo != 0) return G2OCU_OK;                            // not positive definite: solvePattern == false
-  // pairs by block column; a batch = as many distinct block columns as fit the column budget
+  // pairs by block column; a batch = as many distinct block columns as fit the column budget (1 GiB of right-hand sides)
   std::vector<int32_t> order(nPairs);
   for (int i = 0; i < nPairs; ++i) order[i] = i;
   std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return blockCols[a] < blockCols[b]; });
-  const int64_t slotsMax = std::max<int64_t>(1, ((int64_t)1 << 27) / n / P);
-  DVec<double> X, outDev; DVec<int32_t> dCol, dRow, dSlot, dOut;
-  CU(outDev.alloc((size_t)nPairs * P * P));
+  std::vector<int64_t> outOffAll(nPairs + 1, 0);
+  for (int i = 0; i < nPairs; ++i) { int sr, dr, sc, dc; blockAt(blockRows[i], sr, dr); blockAt(blockCols[i], sc, dc); outOffAll[i + 1] = outOffAll[i] + (int64_t)dr * dc; }
+  const int64_t colsMax = std::max<int64_t>(16, ((int64_t)1 << 27) / n);
+  DVec<double> X, outDev; DVec<int32_t> dColScalar, dRowScalar, dRowDim, dColStart, dColDim; DVec<int64_t> dOutOff;
+  CU(outDev.alloc((size_t)outOffAll[nPairs]));
   size_t at = 0;
   while (at < order.size()) {
-    std::vector<int32_t> cols, pr, ps, po;
-    int minRow = st.numPoses;
+    std::vector<int32_t> colScalar, rowScalar, rowDim, colStart, colDim; std::vector<int64_t> outOff;
+    int lastCol = -1, curStart = 0, curDim = 0, minRow = (int)n, minCol = (int)n;
     size_t e = at;
     for (; e < order.size(); ++e) {
       const int32_t c = blockCols[order[e]];
-      if (cols.empty() || cols.back() != c) { if ((int64_t)cols.size() == slotsMax) break; cols.push_back(c); }
-      pr.push_back(blockRows[order[e]]); ps.push_back((int32_t)cols.size() - 1); po.push_back(order[e]);
-      minRow = std::min(minRow, (int)blockRows[order[e]]);
+      if (c != lastCol) {
+        int sc, dc; blockAt(c, sc, dc);
+        if (!colScalar.empty() && (int64_t)colScalar.size() + dc > colsMax) break;
+        curStart = (int)colScalar.size(); curDim = dc; lastCol = c; minCol = std::min(minCol, sc);
+        for (int q = 0; q < dc; ++q) colScalar.push_back(sc + q);
+      }
+      int sr, dr; blockAt(blockRows[order[e]], sr, dr);
+      rowScalar.push_back(sr); rowDim.push_back(dr); colStart.push_back(curStart); colDim.push_back(curDim); outOff.push_back(outOffAll[order[e]]);
+      minRow = std::min(minRow, sr);
     }
-    const int nSlots = (int)cols.size(), nrhs = nSlots * P;
+    const int nrhs = (int)colScalar.size();
     CU(X.alloc((size_t)n * nrhs));
-    CU(dCol.upload(cols, s->stream)); CU(dRow.upload(pr, s->stream)); CU(dSlot.upload(ps, s->stream)); CU(dOut.upload(po, s->stream));
-    launchUnitColumns(X.p, (size_t)n, dCol.p, P, nSlots, s->stream, &s->launches);
-    launchDenseSolveMany(s->denseH.p, (int)n, X.p, (size_t)n, nrhs, cols.front() * P, minRow * P, s->stream, &s->launches);
-    launchGatherBlocks(X.p, (size_t)n, dRow.p, dSlot.p, dOut.p, (int)pr.size(), P, outDev.p, s->stream, &s->launches);
+    CU(dColScalar.upload(colScalar, s->stream)); CU(dRowScalar.upload(rowScalar, s->stream)); CU(dRowDim.upload(rowDim, s->stream));
+    CU(dColStart.upload(colStart, s->stream)); CU(dColDim.upload(colDim, s->stream)); CU(dOutOff.upload(outOff, s->stream));
+    launchUnitColumns(X.p, (size_t)n, dColScalar.p, nrhs, s->stream, &s->launches);
+    launchDenseSolveMany(s->denseH.p, (int)n, X.p, (size_t)n, nrhs, minCol, minRow, s->stream, &s->launches);
+    launchGatherBlocks(X.p, (size_t)n, dRowScalar.p, dRowDim.p, dColStart.p, dColDim.p, dOutOff.p, (int)rowScalar.size(), outDev.p, s->stream, &s->launches);
     CU(cudaGetLastError());
     rc = syncStream(s); if (rc) return rc;                           // the host staging vectors go out of scope
     at = e;
   }
-  CU(cudaMemcpyAsync(out, outDev.p, (size_t)nPairs * P * P * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaMemcpyAsync(out, outDev.p, (size_t)outOffAll[nPairs] * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   rc = syncStream(s); if (rc) return rc;
   if (computed) *computed = 1;
   return G2OCU_OK;

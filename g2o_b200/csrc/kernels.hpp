@@ -145,8 +145,11 @@ void launchDenseAssemble(const PcgDev& p, double* H, cudaStream_t st, int64_t* l
 int launchDenseCholeskySolve(double* H, int n, const double* b, double* x, int* info, cudaStream_t st, int64_t* launches);
 int launchDenseCholeskyFactor(double* H, int n, int* info, cudaStream_t st, int64_t* launches);
 // blocks of the inverse (computeMarginals): unit columns, (L L^T)^-1 applied to many columns, P x P blocks picked out of the result
-void launchUnitColumns(double* X, size_t ldx, const int32_t* blockCol, int P, int nSlots, cudaStream_t st, int64_t* launches);
+void launchUnitColumns(double* X, size_t ldx, const int32_t* colScalar, int nCols, cudaStream_t st, int64_t* launches);
 void launchDenseSolveMany(const double* H, int n, double* X, size_t ldx, int nrhs, int firstNonZero, int firstNeeded, cudaStream_t st, int64_t* launches);
-void launchGatherBlocks(const double* X, size_t ldx, const int32_t* pairRow, const int32_t* pairSlot, const int32_t* pairOut, int nPairs, int P, double* out, cudaStream_t st, int64_t* launches);
+void launchGatherBlocks(const double* X, size_t ldx, const int32_t* rowScalar, const int32_t* rowDim, const int32_t* colStart, const int32_t* colDim, const int64_t* outOff, int nPairs,
+                        double* out, cudaStream_t st, int64_t* launches);
+void launchDenseAssembleFull(const PcgDev& hpp, const double* Hll, const double* Hpl, const int32_t* hplRow, const int32_t* hplLm, int nHplBlocks, int numLandmarks, int L, double* H, int n,
+                             cudaStream_t st, int64_t* launches);
 
 }  // namespace g2ocu

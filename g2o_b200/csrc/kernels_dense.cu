@@ -263,20 +263,35 @@ __global__ void __launch_bounds__(256) trsm_update_bwd_kernel(const double* __re
   __syncthreads();
   if (threadIdx.x < nc) { double r = 0; for (int q = 0; q < 8; ++q) r += sm[threadIdx.x][q]; X[(size_t)(c0 + threadIdx.x) * ldx + k0 + j] -= r; }
 }
-// column slot * P + q of X = unit vector of scalar column blockCol[slot] * P + q
-__global__ void unit_columns_kernel(double* __restrict__ X, size_t ldx, const int32_t* __restrict__ blockCol, int P, int nSlots) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nSlots * P) return;
-  const int slot = t / P, q = t - slot * P;
-  X[(size_t)t * ldx + (size_t)blockCol[slot] * P + q] = 1.0;
+// column c of X = unit vector of scalar index colScalar[c]
+__global__ void unit_columns_kernel(double* __restrict__ X, size_t ldx, const int32_t* __restrict__ colScalar, int nCols) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < nCols) X[(size_t)c * ldx + (size_t)colScalar[c]] = 1.0;
 }
-// out block i (P x P, column-major) = rows of block pairRow[i] of the P columns of slot pairSlot[i]
-__global__ void gather_blocks_kernel(const double* __restrict__ X, size_t ldx, const int32_t* __restrict__ pairRow, const int32_t* __restrict__ pairSlot,
-                                     const int32_t* __restrict__ pairOut, int P, double* __restrict__ out) {
-  const int i = blockIdx.x, el = threadIdx.x;
-  if (el >= P * P) return;
-  const int r = el % P, c = el / P;
-  out[(size_t)pairOut[i] * P * P + el] = X[(size_t)(pairSlot[i] * P + c) * ldx + (size_t)pairRow[i] * P + r];
+// out block i (rowDim x colDim, column-major, at out + outOff[i]) = rows [rowScalar[i], + rowDim[i]) of the columns [colStart[i], + colDim[i]) of X
+__global__ void gather_blocks_kernel(const double* __restrict__ X, size_t ldx, const int32_t* __restrict__ rowScalar, const int32_t* __restrict__ rowDim,
+                                     const int32_t* __restrict__ colStart, const int32_t* __restrict__ colDim, const int64_t* __restrict__ outOff, double* __restrict__ out) {
+  const int i = blockIdx.x, nr = rowDim[i], nc = colDim[i];
+  for (int el = threadIdx.x; el < nr * nc; el += blockDim.x) {
+    const int r = el % nr, c = el / nr;
+    out[outOff[i] + el] = X[(size_t)(colStart[i] + c) * ldx + (size_t)rowScalar[i] + r];
+  }
+}
+// the point blocks and the pose-point blocks of a whole system [Hpp Hpl; Hpl^T Hll] + lambda I into the dense matrix (internal order: poses, then points)
+__global__ void dense_assemble_hll_kernel(const double* __restrict__ Hll, int numLandmarks, int L, int np, double lambda, double* __restrict__ H, int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= numLandmarks * L * L) return;
+  const int l = t / (L * L), el = t - l * L * L, r = el % L, c = el / L;
+  H[(size_t)(np + l * L + r) + (size_t)(np + l * L + c) * n] = Hll[t] + (r == c ? lambda : 0.0);
+}
+__global__ void dense_assemble_hpl_kernel(const double* __restrict__ Hpl, const int32_t* __restrict__ hplRow, const int32_t* __restrict__ hplLm, int nBlocks, int P, int L, int np,
+                                          double* __restrict__ H, int n) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)nBlocks * P * L) return;
+  const int k = (int)(t / (P * L)), el = (int)(t - (int64_t)k * P * L), r = el % P, c = el / P;
+  const size_t gi = (size_t)hplRow[k] * P + r, gj = (size_t)np + (size_t)hplLm[k] * L + c;
+  const double v = Hpl[t];
+  H[gi + gj * n] = v; H[gj + gi * n] = v;
 }
 
 }  // namespace
@@ -354,13 +369,28 @@ void launchDenseSolveMany(const double* H, int n, double* X, size_t ldx, int nrh
     trsv_diag_bwd_kernel<<<nrhs, 256, 0, st>>>(H, n, k0, nb, X, ldx); *launches += 1;
   }
 }
-void launchUnitColumns(double* X, size_t ldx, const int32_t* blockCol, int P, int nSlots, cudaStream_t st, int64_t* launches) {
-  cudaMemsetAsync(X, 0, sizeof(double) * ldx * (size_t)nSlots * P, st);
-  unit_columns_kernel<<<(nSlots * P + 127) / 128, 128, 0, st>>>(X, ldx, blockCol, P, nSlots); *launches += 1;
+void launchUnitColumns(double* X, size_t ldx, const int32_t* colScalar, int nCols, cudaStream_t st, int64_t* launches) {
+  cudaMemsetAsync(X, 0, sizeof(double) * ldx * (size_t)nCols, st);
+  unit_columns_kernel<<<(nCols + 127) / 128, 128, 0, st>>>(X, ldx, colScalar, nCols); *launches += 1;
 }
-void launchGatherBlocks(const double* X, size_t ldx, const int32_t* pairRow, const int32_t* pairSlot, const int32_t* pairOut, int nPairs, int P, double* out, cudaStream_t st, int64_t* launches) {
+void launchGatherBlocks(const double* X, size_t ldx, const int32_t* rowScalar, const int32_t* rowDim, const int32_t* colStart, const int32_t* colDim, const int64_t* outOff, int nPairs,
+                        double* out, cudaStream_t st, int64_t* launches) {
   if (nPairs <= 0) return;
-  gather_blocks_kernel<<<nPairs, 96, 0, st>>>(X, ldx, pairRow, pairSlot, pairOut, P, out); *launches += 1;
+  gather_blocks_kernel<<<nPairs, 96, 0, st>>>(X, ldx, rowScalar, rowDim, colStart, colDim, outOff, out); *launches += 1;
+}
+// dense copy of the whole system of a graph whose points are not marginalized: hpp = the PCG view of Hpp (its lambda goes on every diagonal)
+void launchDenseAssembleFull(const PcgDev& hpp, const double* Hll, const double* Hpl, const int32_t* hplRow, const int32_t* hplLm, int nHplBlocks, int numLandmarks, int L, double* H, int n,
+                             cudaStream_t st, int64_t* launches) {
+  cudaMemsetAsync(H, 0, sizeof(double) * (size_t)n * n, st);
+  switch (hpp.P) {
+    case 3: dense_assemble_kernel<3><<<hpp.nb, 9 * 28, 0, st>>>(hpp, H, n); break;
+    case 6: dense_assemble_kernel<6><<<hpp.nb, 36 * 7, 0, st>>>(hpp, H, n); break;
+    case 9: dense_assemble_kernel<9><<<hpp.nb, 81 * 3, 0, st>>>(hpp, H, n); break;
+    default: break;
+  }
+  if (numLandmarks > 0) dense_assemble_hll_kernel<<<(numLandmarks * L * L + 255) / 256, 256, 0, st>>>(Hll, numLandmarks, L, hpp.n, hpp.lambda, H, n);
+  if (nHplBlocks > 0) dense_assemble_hpl_kernel<<<(unsigned)(((int64_t)nHplBlocks * hpp.P * L + 255) / 256), 256, 0, st>>>(Hpl, hplRow, hplLm, nHplBlocks, hpp.P, L, hpp.n, H, n);
+  *launches += 3;
 }
 
 }  // namespace g2ocu

@@ -11,6 +11,7 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <map>
 #include <set>
 #include <sstream>
 
@@ -113,7 +114,8 @@ int main(int argc, char** argv) {
   const int result = optimizer.optimize(maxIterations);
   if (maxIterations > 0 && result <= 0) std::cerr << "optimize() returned " << result << ": the solver failed, result might be invalid" << std::endl;
   if (computeMarginals && !(maxIterations > 0 && result <= 0)) {   // g2o.cpp:581-608: per active vertex the blocks (h, h) and (h - 1, h) of the inverse
-    std::vector<std::pair<int, int> > blockIndices; std::vector<int> ids;
+    std::vector<std::pair<int, int> > blockIndices; std::vector<int> ids; std::map<int, int> dimOf;
+    for (const auto* v : optimizer.vertexList()) if (v->hessianIndex() >= 0) dimOf[v->hessianIndex()] = v->dimension();
     for (const auto* v : optimizer.vertexList()) {
       if (v->hessianIndex() >= 0) { blockIndices.push_back(std::make_pair(v->hessianIndex(), v->hessianIndex())); ids.push_back(v->id()); }
       if (v->hessianIndex() > 0) { blockIndices.push_back(std::make_pair(v->hessianIndex() - 1, v->hessianIndex())); ids.push_back(v->id()); }
@@ -123,8 +125,8 @@ int main(int argc, char** argv) {
       for (size_t i = 0; i < blockIndices.size(); ++i) {
         if (blockIndices[i].first == blockIndices[i].second) std::cerr << "Vertex id:" << ids[i] << std::endl;
         std::cerr << "inv block :" << blockIndices[i].first << ", " << blockIndices[i].second << std::endl;
-        const int d = (int)std::lround(std::sqrt((double)spinv[i].size()));
-        for (int r = 0; r < d; ++r) { for (int c = 0; c < d; ++c) std::cerr << (c ? " " : "") << std::setprecision(6) << std::defaultfloat << spinv[i][r + (size_t)d * c]; std::cerr << std::endl; }
+        const int nr = dimOf[blockIndices[i].first], nc = nr ? (int)(spinv[i].size() / (size_t)nr) : 0;
+        for (int r = 0; r < nr; ++r) { for (int c = 0; c < nc; ++c) std::cerr << (c ? " " : "") << std::setprecision(6) << std::defaultfloat << spinv[i][r + (size_t)nr * c]; std::cerr << std::endl; }
       }
     }
   }

@@ -146,15 +146,23 @@ void SparseOptimizer::pop() { check(_handle, g2ocu_pop(_handle), "SparseOptimize
 void SparseOptimizer::discardTop() { check(_handle, g2ocu_discard_top(_handle), "SparseOptimizer::discardTop"); }
 bool SparseOptimizer::computeMarginals(std::vector<std::vector<number_t> >& spinv, const std::vector<std::pair<int, int> >& blockIndices) {
   spinv.clear();
-  int32_t dims[4] = {0, 0, 0, 0};
-  if (!_handle || g2ocu_get_i32(_handle, "dims", dims, 4) < 4 || dims[0] <= 0) return false;
-  const size_t PP = (size_t)(dims[2] / dims[0]) * (size_t)(dims[2] / dims[0]);
-  std::vector<int32_t> rows, cols;
-  for (const auto& rc : blockIndices) { rows.push_back(rc.first); cols.push_back(rc.second); }
-  std::vector<number_t> out(blockIndices.size() * PP);
+  if (!_handle) return false;
+  const int64_t nb = g2ocu_get_i32(_handle, "pose_block_indices", nullptr, 0);   // cumulative block ends of Hpp (every vertex when no point is marginalized)
+  if (nb <= 0) return false;
+  std::vector<int32_t> ends((size_t)nb);
+  g2ocu_get_i32(_handle, "pose_block_indices", ends.data(), nb);
+  std::vector<int32_t> rows, cols; std::vector<size_t> sizes; size_t total = 0;
+  for (const auto& rc : blockIndices) {
+    if (rc.first < 0 || rc.first >= nb || rc.second < 0 || rc.second >= nb) { std::cerr << "SparseOptimizer::computeMarginals: block index outside Hpp" << std::endl; return false; }
+    rows.push_back(rc.first); cols.push_back(rc.second);
+    sizes.push_back((size_t)(ends[rc.first] - (rc.first ? ends[rc.first - 1] : 0)) * (size_t)(ends[rc.second] - (rc.second ? ends[rc.second - 1] : 0)));
+    total += sizes.back();
+  }
+  std::vector<number_t> out(total ? total : 1);
   int32_t computed = 0;
   if (!check(_handle, g2ocu_compute_marginals(_handle, (int32_t)blockIndices.size(), rows.data(), cols.data(), out.data(), &computed), "SparseOptimizer::computeMarginals") || !computed) return false;
-  for (size_t i = 0; i < blockIndices.size(); ++i) spinv.emplace_back(out.begin() + i * PP, out.begin() + (i + 1) * PP);
+  size_t off = 0;
+  for (size_t i = 0; i < blockIndices.size(); ++i) { spinv.emplace_back(out.begin() + off, out.begin() + off + sizes[i]); off += sizes[i]; }
   return true;
 }
 

@@ -200,21 +200,29 @@ void fillBatchStatistics(const g2ocu_iteration_stats& st) {
 // rows of Hpp, the requested blocks allocated); false where the reference's solvePattern answers false (no factorisation) and where the
 // backend has no answer (points that are not marginalized, pose systems beyond the dense factorisation's limit).
 static bool marginalsFromDevice(g2ocu_solver* h, SparseBlockMatrix<MatrixX>& spinv, const std::vector<std::pair<int, int>>& blockIndices) {
-  int32_t dims[4] = {0, 0, 0, 0};
-  if (!h || g2ocu_get_i32(h, "dims", dims, 4) < 4 || dims[0] <= 0) return false;
-  const int nb = dims[0], P = dims[2] / dims[0];
-  std::vector<int32_t> rows, cols;
-  for (const auto& rc : blockIndices) { rows.push_back(rc.first); cols.push_back(rc.second); }
-  std::vector<double> out(blockIndices.size() * (size_t)P * P);
+  if (!h) return false;
+  const int64_t nb = g2ocu_get_i32(h, "pose_block_indices", nullptr, 0);      // cumulative block ends of Hpp (every vertex when no point is marginalized)
+  if (nb <= 0) return false;
+  std::vector<int32_t> ends((size_t)nb);
+  g2ocu_get_i32(h, "pose_block_indices", ends.data(), nb);
+  auto dimOf = [&](int b) { return ends[b] - (b ? ends[b - 1] : 0); };
+  std::vector<int32_t> rows, cols; size_t total = 0;
+  for (const auto& rc : blockIndices) {
+    if (rc.first < 0 || rc.first >= nb || rc.second < 0 || rc.second >= nb) return false;
+    rows.push_back(rc.first); cols.push_back(rc.second); total += (size_t)dimOf(rc.first) * dimOf(rc.second);
+  }
+  std::vector<double> out(total ? total : 1);
   int32_t computed = 0;
   if (g2ocu_compute_marginals(h, (int32_t)blockIndices.size(), rows.data(), cols.data(), out.data(), &computed) != G2OCU_OK) { std::cerr << "solver_cuda: " << g2ocu_last_error(h) << std::endl; return false; }
   if (!computed) return false;
-  std::vector<int> blockEnds(nb);
-  for (int i = 0; i < nb; ++i) blockEnds[i] = (i + 1) * P;
-  spinv = SparseBlockMatrix<MatrixX>(blockEnds.data(), blockEnds.data(), nb, nb, true);
+  std::vector<int> blockEnds(ends.begin(), ends.end());
+  spinv = SparseBlockMatrix<MatrixX>(blockEnds.data(), blockEnds.data(), (int)nb, (int)nb, true);
+  size_t off = 0;
   for (size_t i = 0; i < blockIndices.size(); ++i) {
     MatrixX* b = spinv.block(rows[i], cols[i], true);
-    for (int c = 0; c < P; ++c) for (int r = 0; r < P; ++r) (*b)(r, c) = out[i * (size_t)P * P + (size_t)c * P + r];
+    const int nr = dimOf(rows[i]), nc = dimOf(cols[i]);
+    for (int c = 0; c < nc; ++c) for (int r = 0; r < nr; ++r) (*b)(r, c) = out[off + (size_t)c * nr + r];
+    off += (size_t)nr * nc;
   }
   return true;
 }

@@ -214,11 +214,12 @@ int g2ocu_discard_top(g2ocu_solver* s);
 int g2ocu_compute_lambda_init(g2ocu_solver* s, double* lambda);
 int g2ocu_compute_scale(g2ocu_solver* s, double lambda, double* scale);
 int g2ocu_multiply_hessian(g2ocu_solver* s, double* host_dest, const double* host_src);
-/* Blocks of the inverse of Hpp (the marginal covariances of pose vertices): pair i = (block_rows[i], block_cols[i]) in hessian-index
- * units, as the std::pair<int,int> list of SparseOptimizer::computeMarginals; out receives n_pairs blocks of poseDim x poseDim doubles, each
- * column-major (the MatrixX blocks of `spinv`).  *computed = 1 / 0 is the bool the reference returns (0: Hpp is not positive definite).
- * Needs a built system (g2ocu_build_system or an iteration).  G2OCU_E_UNSUPPORTED for graphs whose points are not marginalized and for
- * pose systems beyond the dense factorisation's limit (40 000 scalar rows). */
+/* Blocks of the inverse of Hpp (marginal covariances): pair i = (block_rows[i], block_cols[i]) in hessian-index units, as the
+ * std::pair<int,int> list of SparseOptimizer::computeMarginals; out receives the n_pairs blocks one after the other, each rows x cols
+ * doubles column-major (the MatrixX blocks of `spinv`; the block sizes follow from "pose_block_indices").  Hpp is what the reference calls
+ * so: the pose block - or, when no point is marginalized, the whole system over all vertices in id order (blocks of two sizes).
+ * *computed = 1 / 0 is the bool the reference returns (0: Hpp is not positive definite).  Needs a built system (g2ocu_build_system or an
+ * iteration).  G2OCU_E_UNSUPPORTED for systems beyond the dense factorisation's limit (40 000 scalar rows). */
 int g2ocu_compute_marginals(g2ocu_solver* s, int32_t n_pairs, const int32_t* block_rows, const int32_t* block_cols, double* out, int32_t* computed);
 
 int g2ocu_solver_iteration(g2ocu_solver* s, int32_t algorithm, int32_t iteration, g2ocu_iteration_stats* stats);

@@ -259,16 +259,31 @@ def test_compute_marginals_are_blocks_of_the_inverse_of_hpp(name):
         s.compute_marginals([(0, nb)])
 
 
-def test_compute_marginals_of_a_singular_system_and_of_a_full_system():
-    """Not positive definite -> the bool of the reference's solvePattern is false (None here); points that are not marginalized -> unsupported."""
+def test_compute_marginals_of_a_singular_system():
+    """Not positive definite -> the bool of the reference's solvePattern is false (None here)."""
     g = W.sphere(nodes_per_level=8, laps=4, fix_first=False)          # gauge freedom: Hpp is singular
     s = CudaSolver(g, "gn_var_cuda", device=0); s.initialize_optimization(); s.init(); s.build_structure(); s.compute_active_errors(); s.build_system()
     s.set_lambda(-1.0)                                                 # make sure a pivot goes negative whatever the rounding does
     assert s.compute_marginals([(0, 0)]) is None
+
+
+def test_compute_marginals_of_a_whole_system():
+    """Points that are not marginalized: Hpp is the whole system over all vertices in id order (blocks of 3 and 2 on a 2-D SLAM graph).  Every
+    diagonal block and a few rectangular ones against numpy's inverse of the dense matrix rebuilt from H v products in the reference's order."""
     g = W.slam2d(n_poses=60, n_landmarks=20, world_size=10.0, marginalize_landmarks=False)
     s = CudaSolver(g, "gn_var_cuda", device=0); s.initialize_optimization(); s.init(); s.build_structure(); s.compute_active_errors(); s.build_system()
-    with pytest.raises(Exception):
-        s.compute_marginals([(0, 0)])
+    ends = s.get_i32("pose_block_indices").astype(int); n = int(ends[-1]); starts = np.concatenate([[0], ends[:-1]])
+    H = np.stack([s.multiply_hessian(np.eye(n)[:, j]) for j in range(n)], axis=1)
+    assert np.max(np.abs(H - H.T)) <= 1e-9 * np.max(np.abs(H))
+    inv = np.linalg.inv(H); scale = float(np.max(np.abs(inv)))
+    nb = len(ends)
+    assert {int(e - b) for b, e in zip(starts, ends)} == {2, 3}
+    pairs = [(i, i) for i in range(nb)] + [(0, nb - 1), (nb - 1, 0), (nb // 2, nb // 3), (1, nb - 2)]
+    got = s.compute_marginals(pairs)
+    assert got is not None and len(got) == len(pairs)
+    for (r, c), b in zip(pairs, got):
+        want = inv[starts[r]:ends[r], starts[c]:ends[c]]
+        assert b.shape == want.shape and np.max(np.abs(b - want)) <= 1e-9 * scale, (r, c)
 
 
 def test_gauss_newton_sphere():

@@ -381,6 +381,9 @@ MARGINALS = {
     "sphere": (lambda: W.sphere(nodes_per_level=12, laps=6), "var_csparse", "gn_var_cuda"),
     "sphere_expmap": (lambda: W.sphere_expmap(nodes_per_level=10, laps=5), "var_csparse", "gn_var_cuda"),
     "slam2d_odometry_chain": (lambda: W.slam2d(n_poses=300, n_landmarks=0, world_size=20.0), "3_2_csparse", "gn_fix3_2_cuda"),
+    # points that are not marginalized: the reference's Hpp is the whole system over all vertices in id order, 3 x 3 and 2 x 2 diagonal blocks and
+    # 3 x 2 / 2 x 3 off-diagonal ones (what tutorial_slam2d asks computeMarginals for: landmark covariances)
+    "slam2d_points_in_the_system": (lambda: W.slam2d(n_poses=150, n_landmarks=40, world_size=14.0, marginalize_landmarks=False), "var_csparse", "gn_var_cuda"),
 }
 
 
@@ -395,7 +398,7 @@ def test_marginals_against_the_reference_s_solve_pattern(name):
     g = fn()
     ref = oracle.ReferenceG2o(g, "gn", bs, threads=1); assert ref.initialize_optimization(); ref.optimize(1)
     s = CudaSolver(g, solver, device=0); s.initialize_optimization(); s.init(); s.build_structure(); s.compute_active_errors(); s.build_system()
-    n = int(s.get_i32("dims")[0])
+    n = len(s.get_i32("pose_block_indices"))                 # block rows of the reference's Hpp
     rng = np.random.default_rng(3)
     pairs = [(0, 0), (n - 1, n - 1), (0, n - 1), (n - 1, 0)] + [(int(a), int(b)) for a, b in rng.integers(0, n, size=(12, 2))] + [(i, i) for i in range(0, n, max(1, n // 9))]
     want, got = ref.compute_marginals(pairs), s.compute_marginals(pairs)
