@@ -283,9 +283,22 @@ int downloadEstimates(g2ocu_solver* s) {
   return G2OCU_OK;
 }
 
+// G2OCU_TRACE=1: wall time of the phases of the device-side set-up on stderr (host_structure.cpp prints the ones before it)
+struct DeviceTrace {
+  static bool on() { static const bool v = [] { const char* e = std::getenv("G2OCU_TRACE"); return e && *e && *e != '0'; }(); return v; }
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void mark(const char* what) {
+    if (!on()) return;
+    const auto n = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[g2ocu] buildDevice    %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+
 int buildDevice(g2ocu_solver* s) {
   const Structure& st = s->st; const HostGraph& g = s->g;
   cudaStream_t stream = s->stream;
+  DeviceTrace trace;
   for (auto* es : s->sets) delete es;
   s->sets.clear(); s->mhReady = false;
   int rc = uploadEstimates(s); if (rc) return rc;
@@ -305,6 +318,7 @@ int buildDevice(g2ocu_solver* s) {
     sys.Hll = s->Hll.p; sys.Hpl = s->Hpl.p;
   } else { sys.Hll = nullptr; sys.Hpl = nullptr; }
 
+  trace.mark("estimates, matrices");
   // ---- edge sets ----
   size_t maxScratch = 4096;
   for (const EdgeSet& hs : st.sets) {
@@ -319,6 +333,7 @@ int buildDevice(g2ocu_solver* s) {
     d.slot0 = es->slot0.p; d.slot1 = es->slot1.p; d.block = es->block.p; d.transposed = es->transposed.p; d.pos = es->pos.p;
     std::vector<double> meas((size_t)n * M), info((size_t)n * E * E), prm((size_t)n * NP), delta(n);
     std::vector<int32_t> kind(n);
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < n; ++i) {
       const int e = st.activeEdges[hs.pos[i]];
       std::memcpy(&meas[(size_t)i * M], &g.eMeas[g.eMeasOff[e]], sizeof(double) * M);
@@ -328,20 +343,27 @@ int buildDevice(g2ocu_solver* s) {
     }
     CU(es->meas.upload(meas, stream)); d.meas = es->meas.p;
     // information: identity / uniform / per edge
-    bool uniform = true, identity = true;
-    for (int i = 0; i < n && uniform; ++i) uniform = std::memcmp(&info[(size_t)i * E * E], &info[0], sizeof(double) * E * E) == 0;
+    bool identity = true;
+    int notUniform = 0;
+#pragma omp parallel for schedule(static) reduction(| : notUniform)
+    for (int i = 0; i < n; ++i) notUniform |= std::memcmp(&info[(size_t)i * E * E], &info[0], sizeof(double) * E * E) != 0;
+    const bool uniform = !notUniform;
     for (int k = 0; k < E * E && identity; ++k) identity = info[k] == ((k % (E + 1)) == 0 ? 1.0 : 0.0);
     if (uniform && identity) d.infoMode = 0;
     else if (uniform) { info.resize((size_t)E * E); d.infoMode = 1; }
     else d.infoMode = 2;
     if (d.infoMode) { CU(es->info.upload(info, stream)); d.info = es->info.p; }
-    bool kUniform = true;
-    for (int i = 1; i < n && kUniform; ++i) kUniform = kind[i] == kind[0] && delta[i] == delta[0];
+    int kDiffers = 0;
+#pragma omp parallel for schedule(static) reduction(| : kDiffers)
+    for (int i = 1; i < n; ++i) kDiffers |= !(kind[i] == kind[0] && delta[i] == delta[0]);
+    const bool kUniform = !kDiffers;
     if (kUniform) { d.kernelMode = kind[0] ? 1 : 0; d.kKind = kind[0]; d.kDelta = delta[0]; }
     else { d.kernelMode = 2; CU(es->kernelKind.upload(kind, stream)); CU(es->kernelDelta.upload(delta, stream)); d.kernelKind = es->kernelKind.p; d.kernelDelta = es->kernelDelta.p; }
     if (NP) {
-      bool pUniform = true;
-      for (int i = 1; i < n && pUniform; ++i) pUniform = std::memcmp(&prm[(size_t)i * NP], &prm[0], sizeof(double) * NP) == 0;
+      int pDiffers = 0;
+#pragma omp parallel for schedule(static) reduction(| : pDiffers)
+      for (int i = 1; i < n; ++i) pDiffers |= std::memcmp(&prm[(size_t)i * NP], &prm[0], sizeof(double) * NP) != 0;
+      const bool pUniform = !pDiffers;
       if (pUniform) { prm.resize(NP); d.prmMode = 1; } else d.prmMode = 2;
       CU(es->prm.upload(prm, stream)); d.prm = es->prm.p;
     }
@@ -355,6 +377,7 @@ int buildDevice(g2ocu_solver* s) {
     CU(cudaStreamSynchronize(stream));   // staging vectors die here
     maxScratch = std::max(maxScratch, (size_t)errorScratchDoubles(n));
   }
+  trace.mark("edge sets");
   CU(s->scratch.alloc(maxScratch)); CU(s->out2.alloc(16));   // [0,1] chi2, [4] max diagonal, [5,6] computeScale, [8..15] Dogleg dot products
   {
     auto contiguous = [&](const std::vector<int32_t>& verts, int vtype, int64_t& off) {
@@ -411,10 +434,19 @@ int buildDevice(g2ocu_solver* s) {
           entries.push_back({((int64_t)ri.tile << 32) | (uint32_t)rj.tile, l, ri.base, baseJ, maskJ, (uint8_t)ri.mask});
         }
     }
+    trace.mark("tile entries");
     {
-      std::stable_sort(shortLm.begin(), shortLm.end(), [&](int32_t a, int32_t b) { return st.hplRowIdx[st.hplColPtr[a]] < st.hplRowIdx[st.hplColPtr[b]]; });
-      std::vector<int32_t> pI, pJ;
-      for (int32_t l : shortLm) { const int cb = st.hplColPtr[l], ce = st.hplColPtr[l + 1]; for (int i = cb; i < ce; ++i) for (int j = i; j < ce; ++j) { pI.push_back(i); pJ.push_back(j); } }
+      // the pairs (block i, block j), i <= j, of every short track, landmarks in index order (their order inside a target block only decides the
+      // order of a segment's sum); offsets by a prefix sum so that the lists fill in parallel
+      std::vector<int64_t> pairOff(shortLm.size() + 1, 0);
+      for (size_t q = 0; q < shortLm.size(); ++q) { const int64_t k = st.hplColPtr[shortLm[q] + 1] - st.hplColPtr[shortLm[q]]; pairOff[q + 1] = pairOff[q] + k * (k + 1) / 2; }
+      std::vector<int32_t> pI((size_t)pairOff.back()), pJ((size_t)pairOff.back());
+#pragma omp parallel for schedule(static, 4096)
+      for (int64_t q = 0; q < (int64_t)shortLm.size(); ++q) {
+        const int cb = st.hplColPtr[shortLm[q]], ce = st.hplColPtr[shortLm[q] + 1];
+        int64_t o = pairOff[q];
+        for (int i = cb; i < ce; ++i) for (int j = i; j < ce; ++j) { pI[o] = i; pJ[o] = j; ++o; }
+      }
       {  // sort the pairs by target Hschur block (counting sort) and cut them into segments of one block each
         const size_t np = pI.size();
         std::vector<int32_t> slot(np);
@@ -453,6 +485,7 @@ int buildDevice(g2ocu_solver* s) {
         sd.hplShortIdx = s->hplShortIdx.p; sd.pairW = s->pairW.p; sd.Wshort = s->Wshort.p;
       }
     }
+    trace.mark("pair lists");
     {  // tile entries grouped by (row tile, column strip), split in chunks of at most kTileChunk entries (one CTA each)
       const int kTileChunk = useMma ? 1024 : 256;
       // inside a tile: landmarks that touch the same groups of 8 column cameras next to each other (the K-packed tile kernel skips a group
@@ -498,6 +531,7 @@ int buildDevice(g2ocu_solver* s) {
       sd.chunkI = s->tChunkI.p; sd.chunkJ = s->tChunkJ.p; sd.chunkBegin = s->tChunkB.p; sd.chunkEnd = s->tChunkE.p;
       sd.entLm = s->tEntLm.p; sd.entBaseI = s->tEntBI.p; sd.entBaseJ = s->tEntBJ.p; sd.entMaskJ = s->tEntMJ.p; sd.entMaskI = s->tEntMI.p;
     }
+    trace.mark("tile chunks, slot tables");
     if (useMma && !schurKpackEnabled()) { CU(s->W.alloc((size_t)st.hplRowIdx.size() * P * L + 2)); CU(s->W.zero(stream)); sd.W = s->W.p; }
     // multi-GPU: the reduced system is reduce-scattered into equal block ranges (the last one padded), rank r solves with blocks [r c, (r+1) c)
     CU(s->S.alloc((s->world > 1 ? (size_t)s->slabBlocks * s->world * P * P : (size_t)st.sColIdx.size() * P * P) + 2)); CU(s->S.zero(stream));   // +2: 16-byte aligned bulk copies may read one double past the last block
@@ -509,6 +543,7 @@ int buildDevice(g2ocu_solver* s) {
     sd.S = s->S.p; sd.Dinv = s->Dinv.p; sd.db = s->dbv.p; sd.bschur = s->bschur.p;
     CU(cudaStreamSynchronize(stream));
   }
+  trace.mark("Schur buffers");
   // ---- PCG structures over A = Hschur (Schur) or Hpp ----
   PcgDev& pc = s->pcg; pc = PcgDev();
   const std::vector<int32_t>& rowPtr = st.doSchur ? st.sRowPtr : st.hppRowPtr;
@@ -541,6 +576,7 @@ int buildDevice(g2ocu_solver* s) {
   CU(s->pcgTicket.alloc(4)); CU(s->pcgTicket.zero(stream)); pc.ticket = s->pcgTicket.p;
   CU(cudaStreamSynchronize(stream));
   CU(cudaGetLastError());
+  trace.mark("PCG structures");
   return G2OCU_OK;
 }
 
