@@ -1408,6 +1408,7 @@ int g2ocu_compute_marginals(g2ocu_solver* s, int32_t nPairs, const int32_t* bloc
   }
   CU(cudaMemcpyAsync(out, outDev.p, (size_t)outOffAll[nPairs] * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   rc = syncStream(s); if (rc) return rc;
+  if (s->cfg.linear_solver != G2OCU_LINEAR_DENSE) s->denseH.release();   // n x n doubles: only the dense solver keeps its matrix between calls
   if (computed) *computed = 1;
   return G2OCU_OK;
 }
