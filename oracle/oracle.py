@@ -363,6 +363,35 @@ class Oracle:
             raise KeyError(name)
         return np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0)
 
+    def dense_hpp(self) -> np.ndarray:
+        """The reference's Hpp (the pose block; the whole system when no point is marginalized) as a dense symmetric matrix, from its upper blocks
+        in CCS order (sparse_block_matrix_ccs.h:48-199), block sizes from the cumulative block ends."""
+        ends = self.get_i32("pose_block_indices").astype(np.int64); starts = np.concatenate([[0], ends[:-1]])
+        colptr, rowidx, vals = self.get_i32("hpp_colptr"), self.get_i32("hpp_rowidx"), self.get_f64("hpp_values")
+        n = int(ends[-1]); H = np.zeros((n, n)); off = 0
+        for c in range(len(ends)):
+            dc = int(ends[c] - starts[c])
+            for k in range(int(colptr[c]), int(colptr[c + 1])):
+                r = int(rowidx[k]); dr = int(ends[r] - starts[r])
+                blk = vals[off:off + dr * dc].reshape(dr, dc, order="F"); off += dr * dc
+                H[starts[r]:ends[r], starts[c]:ends[c]] = blk
+                H[starts[c]:ends[c], starts[r]:ends[r]] = blk.T
+        return H
+
+    def compute_marginals(self, pairs):
+        """SparseOptimizer::computeMarginals (sparse_optimizer.cpp:594-596 -> block_solver.hpp:451-459 -> LinearSolver::solvePattern on Hpp): the
+        blocks (row, col) of the inverse of Hpp as it stands.  The reference's CSparse / CHOLMOD back-ends get the requested entries from the
+        Cholesky factor by the Takahashi recursion (marginal_covariance_cholesky.cpp:52-100, 153-222), which yields entries of the exact inverse;
+        restated here as that definition: Cholesky (numpy), inverse, blocks.  None when Hpp is not positive definite (solvePattern == false)."""
+        H = self.dense_hpp()
+        try:
+            Lc = np.linalg.cholesky(H)
+        except np.linalg.LinAlgError:
+            return None
+        Li = np.linalg.inv(Lc); inv = Li.T @ Li
+        ends = self.get_i32("pose_block_indices").astype(np.int64); starts = np.concatenate([[0], ends[:-1]])
+        return [inv[starts[r]:ends[r], starts[c]:ends[c]].copy() for r, c in pairs]
+
     def set_estimates(self, est: np.ndarray):
         self._L.orc_set_estimates(self._h, _dp(np.ascontiguousarray(est, dtype=np.float64)))
 

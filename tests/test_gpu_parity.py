@@ -249,6 +249,10 @@ def test_compute_marginals_are_blocks_of_the_inverse_of_hpp(name):
     assert got is not None and len(got) == len(pairs)
     for (r, c), b in zip(pairs, got):
         assert np.max(np.abs(b - inv[r * P:(r + 1) * P, c * P:(c + 1) * P])) <= 1e-9 * scale, (name, r, c)
+    assert o.algorithm_init() and o.build_structure()                   # ... and against the oracle's restatement on its own Hpp
+    o.compute_active_errors(); o.build_system()
+    for b, w in zip(got[-6:], o.compute_marginals(pairs[-6:])):
+        assert b.shape == w.shape and np.max(np.abs(b - w)) <= 1e-8 * scale, name
     s.set_lambda(0.5)                                                  # the reference factorises Hpp as it stands: damped until restoreDiagonal
     inv2 = np.linalg.inv(H + 0.5 * np.eye(H.shape[0]))
     b = s.compute_marginals([(1, 1)])[0]

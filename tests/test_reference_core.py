@@ -387,6 +387,25 @@ MARGINALS = {
 }
 
 
+@pytest.mark.parametrize("name", list(MARGINALS))
+def test_oracle_marginals_against_the_reference_s_solve_pattern(name):
+    """CPU: the oracle's restatement of computeMarginals (blocks of the inverse of Hpp) against the compiled reference with LinearSolverCSparse
+    (solvePattern + MarginalCovarianceCholesky), both on the Hpp of the first linearisation."""
+    fn, bs, _ = MARGINALS[name]
+    g = fn()
+    ref = oracle.ReferenceG2o(g, "gn", bs, threads=1); assert ref.initialize_optimization(); ref.optimize(1)
+    o = oracle.Oracle(g, "gn", "pcg"); assert o.initialize_optimization() and o.algorithm_init() and o.build_structure()
+    o.compute_active_errors(); o.build_system()
+    n = len(o.get_i32("pose_block_indices"))
+    rng = np.random.default_rng(4)
+    pairs = [(0, 0), (n - 1, n - 1), (0, n - 1), (n - 1, 0)] + [(int(a), int(b)) for a, b in rng.integers(0, n, size=(10, 2))]
+    want, got = ref.compute_marginals(pairs), o.compute_marginals(pairs)
+    assert want is not None and got is not None
+    scale = max(float(np.max(np.abs(b))) for b in want)
+    for (r, c), a, b in zip(pairs, got, want):
+        assert a.shape == b.shape and np.max(np.abs(a - b)) <= 1e-9 * scale, (name, r, c)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(MARGINALS))
 def test_marginals_against_the_reference_s_solve_pattern(name):
